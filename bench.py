@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the semantic-tier hot path (BASELINE.json configs[2]).
+
+Workload: 10 M docs x 384-dim f16 slab, a batch of 1024 queries, exact fused cosine + top-k.
+A "step" is one pass of the hot path over one 1024-query batch.  At N > 1 the corpus is
+row-sharded across the ranks (strong scaling, BASELINE configs[3]); every rank scans its shard
+for all queries and one NCCL all-gather of the per-rank top-k keys feeds the merge kernel.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for how each field is computed.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "queries_per_sec_f16_cosine_topk_10Mx384"
+UNIT = "queries/s"
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--rows", type=int, default=10_000_000)
+    p.add_argument("--dim", type=int, default=384)
+    p.add_argument("--batch", type=int, default=1024)
+    p.add_argument("--k", type=int, default=10)
+    p.add_argument("--cpu-rows", type=int, default=0, help="rows of the CPU sample (0 = same as --rows)")
+    p.add_argument("--cpu-queries", type=int, default=4, help="queries per CPU step (a sample of the batch)")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    return p.parse_args()
+
+
+def workload_config(a, n_gpus):
+    return {
+        "workload": f"configs[2]: {a.rows} docs x {a.dim}-dim f16, batch {a.batch} queries, exact cosine top-{a.k}",
+        "rows": a.rows, "dim": a.dim, "batch": a.batch, "k": a.k,
+        "corpus": "clustered (64 centroids, noise 0.30) — reference bench generator fsvi_int8_two_pass.rs:199-231",
+        "storage": "f16 slab, f32 query, f32 accumulate (reference accumulation tree, bit-exact)",
+        "sharding": "single GPU" if n_gpus == 1 else f"rows sharded over {n_gpus} ranks, one all-gather of top-k keys",
+        "l2": "inputs larger than L2 (slab per GPU >> 126 MB); no explicit flush",
+    }
+
+
+# ── CPU arm: the oracle restatement of the reference scan on the host cores ──────────────────
+def cpu_arm(a, steps, warmup):
+    """Times oracle.fs_oracle.search_top_k (reference restatement: AVX2+F16C dot, 1024-row chunks,
+    per-chunk heaps, serial merge; all host threads) on a bounded sample: the full-size corpus,
+    `cpu_queries` queries of the batch per step, queries back to back (the reference's
+    production model, benches/batched_query_scan.rs:108-126)."""
+    from oracle import fs_oracle as fo
+
+    rows = a.cpu_rows or a.rows
+    threads = fo.host_threads()
+    t0 = time.perf_counter()
+    slab, _ = fo.synth_rows(1, 1, 0, rows, a.dim, threads=threads)
+    gen_s = time.perf_counter() - t0
+    queries = [fo.clustered_query(q, a.dim) for q in range(a.cpu_queries)]
+
+    def step():
+        for q in queries:
+            fo.search_top_k(slab, q, a.k, threads=threads)
+
+    for _ in range(warmup):
+        step()
+    times = []
+    for _ in range(steps):
+        t = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t)
+    per_query = sum(times) / (steps * a.cpu_queries)
+    per_query_full = per_query * (a.rows / rows)  # the scan is linear in rows
+    return dict(value=1.0 / per_query_full, per_query_ms=per_query_full * 1e3, threads=threads, rows=rows,
+                gen_s=gen_s, ms_per_step=1e3 * sum(times) / steps,
+                sample=f"{rows} rows x {a.dim} (of {a.rows}), {a.cpu_queries} of {a.batch} queries per step, "
+                       f"{steps} steps after {warmup} warm-ups" + ("" if rows == a.rows else ", scaled linearly in rows"))
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_arm(a, a.steps, a.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(a, a.gpus),
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "port",
+                         "sample": r["sample"], "cpu": cpu_model(), "per_query_ms": r["per_query_ms"]},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference = the oracle port of the reference's SIMD CPU scan (the Rust workspace cannot be "
+                "built in this image: no cargo/rustc); a step scans the corpus for a sample of the batch",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ── clocks ────────────────────────────────────────────────────────────────────────────────────
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            parts = [x.strip() for x in r.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ── our arm ───────────────────────────────────────────────────────────────────────────────────
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+
+    import frankensearch_b200 as fs
+    from frankensearch_b200.sharded import ShardedGpuIndex, shard_bounds
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product has no CPU fallback (use --impl reference "
+                         "for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # corpus shard, generated on the device by the reference's bench generator
+    lo, hi = shard_bounds(a.rows, world, rank)
+    slab = torch.empty((hi - lo, a.dim), dtype=torch.int16, device=dev)
+    fs._ffi.check(fs._ffi.lib().fsgpu_synth_rows_device(local_rank, 1, 1, lo, hi - lo, a.dim, 64, 0.30,
+                                                        slab.data_ptr(), None))
+    ix = fs.GpuVectorIndex.from_device_tensor(slab, row_base=lo)
+    sharded = ShardedGpuIndex(ix) if world > 1 else None
+
+    # queries: the reference generator's clustered queries, built on the host (tiny)
+    from frankensearch_b200 import _ffi  # noqa: F401
+    q_host = torch.empty((a.batch, a.dim), dtype=torch.float32).pin_memory()
+    q_np = q_host.numpy()
+    _fill_queries(q_np, a.dim)
+    d_queries = q_host.to(dev, non_blocking=False)
+
+    def step_device():
+        if sharded is not None:
+            return sharded.search_top_k_device(d_queries, a.k)
+        return ix.search_top_k_device(d_queries, a.k, want_hits=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(a.warmup, 3)):
+        step_device()
+    barrier()
+    ix.profile_read(reset=True)
+    ix.profile_enable(True)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    start.record()
+    for _ in range(a.steps):
+        out = step_device()
+    end.record()
+    barrier()
+    elapsed_ms = start.elapsed_time(end)
+    prof = ix.profile_read(reset=True)
+    ix.profile_enable(False)
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / a.steps
+    value = a.batch * a.steps / (elapsed_ms / 1e3)
+
+    # e2e: the host-buffer C-ABI call (fsgpu_search_top_k): pinned host queries -> device, search,
+    # hits -> host, every step inside the timed region
+    hits_host = torch.empty((a.batch, a.k, 2), dtype=torch.int32).pin_memory()
+    counts_host = torch.empty(a.batch, dtype=torch.int32).pin_memory()
+
+    def step_e2e():
+        if sharded is None:
+            fs._ffi.check(fs._ffi.lib().fsgpu_search_top_k(ix.handle, q_host.data_ptr(), a.batch, a.k, a.dim,
+                                                           hits_host.data_ptr(), counts_host.data_ptr()))
+        else:
+            dq = q_host.to(dev, non_blocking=True)
+            _, mh, mc = sharded.search_top_k_device(dq, a.k)
+            hits_host.copy_(mh, non_blocking=True)
+            counts_host.copy_(mc, non_blocking=True)
+            torch.cuda.synchronize(dev)
+
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        step_e2e()
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = a.batch * a.steps / float(t.item())
+
+    # sanity: the timed result is a real answer (sorted keys, k hits per query)
+    keys = out[0]
+    assert bool((keys[:, :-1] > keys[:, 1:]).all().item()) if a.k > 1 else True, "result keys are not sorted"
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except (OSError, ValueError):
+            pass
+        peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        scan_launches = max(prof["scan_launches"], 1)
+        avg_ms = prof["scan_ms"] / scan_launches
+        bytes_per_launch = prof["scan_bytes"] / scan_launches
+        achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "scan_kernel_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except (OSError, ValueError):
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+            "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(a, world),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                         "frac": achieved / peak_gbs if peak_gbs else None, "traffic": traffic,
+                         "kernel": "scan_topk_fast_kernel", "launches_timed": prof["scan_launches"],
+                         "avg_launch_ms": avg_ms, "bytes_per_launch": bytes_per_launch,
+                         "queries_per_launch": a.batch * a.steps / scan_launches, "peak_source": peak_src,
+                         "scan_share_of_step": prof["scan_ms"] / elapsed_ms if elapsed_ms else None},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": a.batch * a.dim * 4,
+                    "d2h_bytes_per_step": a.batch * a.k * 8 + a.batch * 4},
+            "gpu_launches": prof["scan_launches"] + prof["merge_launches"] + prof["other_launches"],
+            "clocks": clocks,
+        }
+        if not a.no_cpu_baseline and world == 1:
+            aa = argparse.Namespace(**vars(a))
+            r = cpu_arm(aa, steps=2, warmup=1)
+            line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "port",
+                                    "sample": r["sample"], "cpu": cpu_model(), "per_query_ms": r["per_query_ms"]}
+        print(json.dumps(line), flush=True)
+    ix.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _fill_queries(q_np, dim):
+    """clustered queries of the reference bench (fsvi_int8_two_pass.rs:285-287), NumPy restatement
+    (host-side input preparation; ~1 ms per query, outside every timed region)."""
+    def raw(seed):
+        s = np.uint64(seed | 1)
+        out = np.empty(dim, dtype=np.float32)
+        s = int(s)
+        for d in range(dim):
+            s ^= (s << 13) & 0xFFFFFFFFFFFFFFFF
+            s ^= s >> 7
+            s ^= (s << 17) & 0xFFFFFFFFFFFFFFFF
+            out[d] = np.float32(np.float32(s >> 40) / np.float32(8388608.0) - np.float32(1.0))
+        return out
+
+    def norm(v):
+        acc = np.float32(0)
+        for x in v:
+            acc = np.float32(acc + np.float32(x * x))
+        n = np.sqrt(acc)
+        return (v / n).astype(np.float32) if n > 1e-12 else v
+
+    cents = {}
+    for q in range(q_np.shape[0]):
+        c = q % 64
+        if c not in cents:
+            cents[c] = norm(raw(0xC0000000 + c))
+        q_np[q] = norm((cents[c] + np.float32(0.30) * raw(0xDEAD0000 + q)).astype(np.float32))
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,13 @@
+"""frankensearch_b200 — the B200 (sm_100a) semantic-tier hot path of frankensearch behind the
+reference's own seams: exact f16 cosine scan + top-k, RRF, two-tier blend, query encoders.
+
+Everything numeric runs in libfsgpu.so (hand-written CUDA, include/fsgpu.h).  There is no CPU
+fallback; importing succeeds without a GPU so that host logic can be tested, but every compute
+entry point raises `SearchError(SubsystemError)` when no CUDA device is usable.
+"""
+from ._ffi import SearchError  # noqa: F401
+from .types import FusedHit, RrfConfig, ScoredResult, VectorHit, candidate_count  # noqa: F401
+from .index import GpuVectorIndex  # noqa: F401
+from .fusion import blend_two_tier, blend_two_tier_aligned, rrf_fuse  # noqa: F401
+from .embed import Model2VecEmbedder  # noqa: F401
+from .sharded import ShardedGpuIndex, shard_bounds  # noqa: F401

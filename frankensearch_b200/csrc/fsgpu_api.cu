@@ -1,0 +1,1136 @@
+// fsgpu_api.cu — C ABI (include/fsgpu.h) over the sm_100a kernels: index lifetime, launch
+// planning, host<->device staging, FSVI v1 reader.  No CPU compute path exists in this file:
+// every search/fusion/embedding entry point launches kernels or fails.
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <cerrno>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "fsgpu.h"
+#include "fsgpu_common.cuh"
+#include "fusion_kernels.cuh"
+#include "scan_kernels.cuh"
+#include "synth_kernels.cuh"
+
+using namespace fsgpu;
+
+// ─── errors ─────────────────────────────────────────────────────────────────────────────────
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess)                                                                 \
+            return fail(FSGPU_ERR_SUBSYSTEM, "gpu: %s failed: %s (%s:%d)", #expr,              \
+                        cudaGetErrorString(_e), __FILE__, __LINE__);                           \
+    } while (0)
+
+extern "C" const char* fsgpu_last_error(void) { return g_last_error.c_str(); }
+extern "C" int fsgpu_abi_version(void) { return FSGPU_ABI_VERSION; }
+
+extern "C" int fsgpu_device_count(int* out_count) {
+    if (!out_count) return fail(FSGPU_ERR_INVALID_CONFIG, "out_count is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *out_count = 0;
+        return fail(FSGPU_ERR_SUBSYSTEM, "gpu: no usable CUDA device: %s", cudaGetErrorString(e));
+    }
+    *out_count = n;
+    return FSGPU_OK;
+}
+
+extern "C" void fsgpu_index_options_default(fsgpu_index_options* o) {
+    if (!o) return;
+    o->device = 0;
+    o->reduce_order = FSGPU_REDUCE_HALVES_PAIRWISE;
+    o->tail_fma = 1;
+    o->slab_is_device = 0;
+    o->row_base = 0;
+}
+
+// ─── small RAII device buffer that only grows ───────────────────────────────────────────────
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    cudaError_t reserve(size_t want) {
+        if (want <= bytes) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) bytes = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    template <class T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// ─── the index handle ───────────────────────────────────────────────────────────────────────
+struct fsgpu_index {
+    int device = 0;
+    int num_sms = 0;
+    uint64_t n_rows = 0, row_base = 0;
+    uint32_t dim = 0;
+    int reduce_order = 0, tail_fma = 1;
+    uint16_t* d_slab = nullptr;
+    bool owns_slab = false;
+    uint8_t* d_tomb = nullptr;
+    cudaStream_t stream = nullptr;
+    mutable std::mutex mu;
+    // workspaces (grow-only, guarded by mu)
+    mutable DevBuf ws_partial, ws_queries, ws_keys, ws_hits, ws_counts, ws_sort_a, ws_sort_b,
+        ws_cub, ws_rows, ws_scores, ws_present;
+    uint32_t* d_error = nullptr;
+    // launch accounting (guarded by mu)
+    mutable bool profiling = false;
+    mutable fsgpu_profile prof{};
+    mutable std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pending, ev_free;
+    // host-side doc-id table
+    std::vector<uint8_t> doc_bytes;
+    std::vector<uint64_t> doc_off;
+};
+
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+// ─── launch planning ────────────────────────────────────────────────────────────────────────
+constexpr uint32_t kFusedMaxK = 1024;
+
+static uint32_t host_next_pow2(uint32_t x) {
+    uint32_t p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+static uint32_t cand_capacity(uint32_t k) { return host_next_pow2(std::max(2 * k, k + 512)); }
+
+typedef void (*ScanKernel)(const ScanArgs);
+
+template <int NJ, int QB, int R>
+static ScanKernel fast_kernel() { return scan_topk_fast_kernel<NJ, QB, R>; }
+
+template <int NJ>
+static ScanKernel pick_fast_qb(int qb, int r) {
+    if (r == 2) {
+        switch (qb) {
+            case 1: return fast_kernel<NJ, 1, 2>();
+            case 2: return fast_kernel<NJ, 2, 2>();
+            case 4: return fast_kernel<NJ, 4, 2>();
+        }
+    } else {
+        switch (qb) {
+            case 1: return fast_kernel<NJ, 1, 1>();
+            case 2: return fast_kernel<NJ, 2, 1>();
+            case 4: return fast_kernel<NJ, 4, 1>();
+            case 8: return fast_kernel<NJ, 8, 1>();
+        }
+    }
+    return nullptr;
+}
+static ScanKernel pick_fast(uint32_t dim, int qb, int r) {
+    switch (dim) {
+        case 128: return pick_fast_qb<4>(qb, r);
+        case 256: return pick_fast_qb<8>(qb, r);
+        case 384: return pick_fast_qb<12>(qb, r);
+    }
+    return nullptr;
+}
+
+struct ScanPlan {
+    ScanKernel kernel = nullptr;
+    int qb = 1, r = 1;
+    uint32_t tile_rows = 8;
+    uint32_t cap = 1024, sync_every = 1;
+    size_t smem = 0;
+    int grid = 1;
+};
+
+static int make_plan(const fsgpu_index* ix, uint32_t k, int qb_want, ScanPlan* plan) {
+    ScanPlan p;
+    p.cap = cand_capacity(k);
+    int r = env_int("FSGPU_SCAN_R", 1);
+    if (r != 1 && r != 2) r = 1;
+    if (qb_want == 8) r = 1;
+    p.kernel = pick_fast(ix->dim, qb_want, r);
+    if (p.kernel) {
+        p.qb = qb_want;
+        p.r = r;
+        p.tile_rows = kScanWarps * 8 * r;
+    } else {
+        p.kernel = scan_topk_generic_kernel;
+        p.qb = 1;
+        p.r = 1;
+        p.tile_rows = kScanWarps;
+    }
+    p.sync_every = std::max<uint32_t>(1, std::min<uint32_t>(16, (p.cap - k) / (2 * p.tile_rows)));
+    p.smem = scan_smem_bytes(p.qb, p.cap, ix->dim);
+    CUDA_TRY(cudaFuncSetAttribute(p.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, p.kernel, kScanThreads, p.smem));
+    if (per_sm < 1)
+        return fail(FSGPU_ERR_INVALID_CONFIG, "scan kernel does not fit (k=%u dim=%u smem=%zu)", k,
+                    ix->dim, p.smem);
+    const int cap_per_sm = env_int("FSGPU_SCAN_CTAS_PER_SM", 0);
+    if (cap_per_sm > 0) per_sm = std::min(per_sm, cap_per_sm);
+    const uint64_t n_tiles = (ix->n_rows + p.tile_rows - 1) / p.tile_rows;
+    p.grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)per_sm * ix->num_sms, n_tiles));
+    *plan = p;
+    return FSGPU_OK;
+}
+
+static int launch_merge(const MergeArgs& m, uint32_t batch, cudaStream_t stream) {
+    const size_t smem = (size_t)m.cap * 8 + 16;
+    CUDA_TRY(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    merge_topk_kernel<<<batch, kScanThreads, smem, stream>>>(m);
+    CUDA_TRY(cudaGetLastError());
+    return FSGPU_OK;
+}
+
+// Exact top-k for `batch` device-resident queries; outputs may be NULL.  Caller holds ix->mu.
+static int search_device_locked(const fsgpu_index* ix, const float* d_queries, uint32_t batch,
+                                uint32_t k, uint64_t* d_out_keys, fsgpu_hit* d_out_hits,
+                                uint32_t* d_out_counts, cudaStream_t stream) {
+    if (batch == 0) return FSGPU_OK;
+    if (k == 0 || ix->n_rows == 0) {  // search.rs:438-440
+        if (d_out_counts) CUDA_TRY(cudaMemsetAsync(d_out_counts, 0, (size_t)batch * 4, stream));
+        return FSGPU_OK;
+    }
+    CUDA_TRY(cudaMemsetAsync(ix->d_error, 0, 4, stream));
+    if (k > kFusedMaxK) {
+        // `limit >= n` / very large k arm (search.rs:449-473): score every row, radix sort.
+        const uint64_t n = ix->n_rows;
+        CUDA_TRY(ix->ws_sort_a.reserve(n * 8));
+        CUDA_TRY(ix->ws_sort_b.reserve(n * 8));
+        size_t cub_bytes = 0;
+        CUDA_TRY(cub::DeviceRadixSort::SortKeysDescending(nullptr, cub_bytes, ix->ws_sort_a.as<uint64_t>(),
+                                                         ix->ws_sort_b.as<uint64_t>(), n, 0, 64, stream));
+        CUDA_TRY(ix->ws_cub.reserve(cub_bytes));
+        const uint32_t k_eff = (uint32_t)std::min<uint64_t>(k, n);
+        const int grid = (int)std::min<uint64_t>((n + kScanWarps - 1) / kScanWarps, (uint64_t)ix->num_sms * 8);
+        for (uint32_t b = 0; b < batch; ++b) {
+            score_all_kernel<<<grid, kScanThreads, (size_t)ix->dim * 4, stream>>>(
+                ix->d_slab, ix->d_tomb, n, ix->row_base, ix->dim, d_queries + (size_t)b * ix->dim,
+                ix->reduce_order, ix->tail_fma, ix->ws_sort_a.as<uint64_t>());
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cub::DeviceRadixSort::SortKeysDescending(
+                ix->ws_cub.p, cub_bytes, ix->ws_sort_a.as<uint64_t>(), ix->ws_sort_b.as<uint64_t>(), n, 0,
+                64, stream));
+            emit_sorted_prefix_kernel<<<std::max(1u, std::min(1024u, (k + kScanWarps - 1) / kScanWarps)),
+                                        kScanThreads, 0, stream>>>(
+                ix->ws_sort_b.as<uint64_t>(), k_eff, k, ix->d_slab, d_queries + (size_t)b * ix->dim,
+                ix->n_rows, ix->row_base, ix->dim, ix->reduce_order, ix->tail_fma,
+                d_out_keys ? d_out_keys + (size_t)b * k : nullptr,
+                d_out_hits ? d_out_hits + (size_t)b * k : nullptr, d_out_counts ? d_out_counts + b : nullptr);
+            CUDA_TRY(cudaGetLastError());
+            ix->prof.other_launches += 5;  // score-all + radix sort passes + emit
+        }
+        return FSGPU_OK;
+    }
+
+    const int qb_max = std::max(1, env_int("FSGPU_SCAN_QB", 4));
+    uint32_t done = 0;
+    while (done < batch) {
+        const uint32_t left = batch - done;
+        int qb = 1;
+        for (int c : {8, 4, 2, 1})
+            if (c <= qb_max && (uint32_t)c <= left) {
+                qb = c;
+                break;
+            }
+        ScanPlan plan;
+        int rc = make_plan(ix, k, qb, &plan);
+        if (rc) return rc;
+        qb = plan.qb;
+        CUDA_TRY(ix->ws_partial.reserve((size_t)plan.grid * qb * k * 8));
+        ScanArgs a{};
+        a.slab = ix->d_slab;
+        a.tombstones = ix->d_tomb;
+        a.queries = d_queries + (size_t)done * ix->dim;
+        a.n_rows = ix->n_rows;
+        a.row_base = ix->row_base;
+        a.dim = ix->dim;
+        a.k = k;
+        a.cap = plan.cap;
+        a.sync_every = plan.sync_every;
+        a.reduce_order = ix->reduce_order;
+        a.tail_fma = ix->tail_fma;
+        a.partial = ix->ws_partial.as<uint64_t>();
+        a.error_flag = ix->d_error;
+        std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+        if (ix->profiling) {
+            if (!ix->ev_free.empty()) {
+                ev = ix->ev_free.back();
+                ix->ev_free.pop_back();
+            } else {
+                CUDA_TRY(cudaEventCreate(&ev.first));
+                CUDA_TRY(cudaEventCreate(&ev.second));
+            }
+            CUDA_TRY(cudaEventRecord(ev.first, stream));
+        }
+        plan.kernel<<<plan.grid, kScanThreads, plan.smem, stream>>>(a);
+        CUDA_TRY(cudaGetLastError());
+        if (ix->profiling) {
+            CUDA_TRY(cudaEventRecord(ev.second, stream));
+            ix->ev_pending.push_back(ev);
+        }
+        ix->prof.scan_launches += 1;
+        ix->prof.merge_launches += 1;
+        ix->prof.scan_bytes += ix->n_rows * ix->dim * 2ull;
+
+        MergeArgs m{};
+        m.keys = a.partial;
+        m.list_stride = (uint64_t)qb * k;
+        m.query_stride = k;
+        m.n_lists = (uint32_t)plan.grid;
+        m.k_in = k;
+        m.k_out = k;
+        m.cap = plan.cap;
+        m.out_keys = d_out_keys ? d_out_keys + (size_t)done * k : nullptr;
+        m.out_hits = d_out_hits ? d_out_hits + (size_t)done * k : nullptr;
+        m.out_counts = d_out_counts ? d_out_counts + done : nullptr;
+        m.slab = ix->d_slab;
+        m.queries = a.queries;
+        m.n_rows = ix->n_rows;
+        m.row_base = ix->row_base;
+        m.dim = ix->dim;
+        m.reduce_order = ix->reduce_order;
+        m.tail_fma = ix->tail_fma;
+        m.error_flag = ix->d_error;
+        rc = launch_merge(m, (uint32_t)qb, stream);
+        if (rc) return rc;
+        done += (uint32_t)qb;
+    }
+    return FSGPU_OK;
+}
+
+static int check_error_flag(const fsgpu_index* ix, cudaStream_t stream) {
+    uint32_t flag = 0;
+    CUDA_TRY(cudaMemcpyAsync(&flag, ix->d_error, 4, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    if (flag) return fail(FSGPU_ERR_SUBSYSTEM, "gpu: top-k candidate buffer contract violated");
+    return FSGPU_OK;
+}
+
+// ─── index creation ─────────────────────────────────────────────────────────────────────────
+static int index_alloc_common(fsgpu_index* ix, const fsgpu_index_options* o, uint64_t n_rows,
+                              uint32_t dim) {
+    if (dim == 0) return fail(FSGPU_ERR_INVALID_CONFIG, "dimension must be non-zero");
+    if (o->reduce_order < 0 || o->reduce_order > 4)
+        return fail(FSGPU_ERR_INVALID_CONFIG, "reduce_order %d out of range", o->reduce_order);
+    if (o->row_base + n_rows > 0xFFFFFFFFull)
+        return fail(FSGPU_ERR_INVALID_CONFIG, "row_base + n_rows exceeds the u32 range of VectorHit.index");
+    int ndev = 0;
+    int rc = fsgpu_device_count(&ndev);
+    if (rc) return rc;
+    if (o->device < 0 || o->device >= ndev)
+        return fail(FSGPU_ERR_INVALID_CONFIG, "device %d not present (%d devices)", o->device, ndev);
+    ix->device = o->device;
+    ix->n_rows = n_rows;
+    ix->dim = dim;
+    ix->row_base = o->row_base;
+    ix->reduce_order = o->reduce_order;
+    ix->tail_fma = o->tail_fma ? 1 : 0;
+    CUDA_TRY(cudaSetDevice(ix->device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, ix->device));
+    if (prop.major < 10)
+        return fail(FSGPU_ERR_SUBSYSTEM, "gpu: device %d is sm_%d%d; this library is built for sm_100a only",
+                    ix->device, prop.major, prop.minor);
+    ix->num_sms = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaMalloc(&ix->d_error, 4));
+    CUDA_TRY(cudaMemset(ix->d_error, 0, 4));
+    return FSGPU_OK;
+}
+
+static int upload_tombstones(fsgpu_index* ix, const uint8_t* bitmap) {
+    if (ix->d_tomb) {
+        cudaFree(ix->d_tomb);
+        ix->d_tomb = nullptr;
+    }
+    if (!bitmap || ix->n_rows == 0) return FSGPU_OK;
+    const size_t bytes = (ix->n_rows + 7) / 8;
+    CUDA_TRY(cudaMalloc(&ix->d_tomb, bytes));
+    CUDA_TRY(cudaMemcpy(ix->d_tomb, bitmap, bytes, cudaMemcpyHostToDevice));
+    return FSGPU_OK;
+}
+
+extern "C" void fsgpu_index_destroy(fsgpu_index* ix) {
+    if (!ix) return;
+    {
+        DeviceGuard g(ix->device);
+        if (ix->stream) cudaStreamSynchronize(ix->stream);
+        if (ix->owns_slab && ix->d_slab) cudaFree(ix->d_slab);
+        if (ix->d_tomb) cudaFree(ix->d_tomb);
+        if (ix->d_error) cudaFree(ix->d_error);
+        for (auto* v : {&ix->ev_pending, &ix->ev_free})
+            for (auto& ev : *v) {
+                cudaEventDestroy(ev.first);
+                cudaEventDestroy(ev.second);
+            }
+        for (DevBuf* b : {&ix->ws_partial, &ix->ws_queries, &ix->ws_keys, &ix->ws_hits, &ix->ws_counts,
+                          &ix->ws_sort_a, &ix->ws_sort_b, &ix->ws_cub, &ix->ws_rows, &ix->ws_scores,
+                          &ix->ws_present})
+            b->release();
+        if (ix->stream) cudaStreamDestroy(ix->stream);
+    }
+    delete ix;
+}
+
+extern "C" int fsgpu_index_create_f16(const uint16_t* slab, uint64_t n_rows, uint32_t dim,
+                                      const uint8_t* tombstones, const fsgpu_index_options* opts,
+                                      fsgpu_index** out) {
+    if (!out) return fail(FSGPU_ERR_INVALID_CONFIG, "out is NULL");
+    *out = nullptr;
+    fsgpu_index_options o;
+    if (opts) o = *opts; else fsgpu_index_options_default(&o);
+    if (n_rows && !slab) return fail(FSGPU_ERR_INVALID_CONFIG, "slab is NULL");
+    DeviceGuard g(o.device);
+    fsgpu_index* ix = new fsgpu_index();
+    int rc = index_alloc_common(ix, &o, n_rows, dim);
+    if (rc) { fsgpu_index_destroy(ix); return rc; }
+    const size_t bytes = (size_t)n_rows * dim * 2;
+    cudaError_t e = cudaSuccess;
+    if (o.slab_is_device) {
+        ix->d_slab = const_cast<uint16_t*>(slab);
+        ix->owns_slab = false;
+        if ((reinterpret_cast<uintptr_t>(slab) & 15u) != 0) {
+            fsgpu_index_destroy(ix);
+            return fail(FSGPU_ERR_INVALID_CONFIG, "device slab must be 16-byte aligned");
+        }
+    } else if (bytes) {
+        e = cudaMalloc(&ix->d_slab, bytes);
+        if (e == cudaSuccess) e = cudaMemcpy(ix->d_slab, slab, bytes, cudaMemcpyHostToDevice);
+        ix->owns_slab = true;
+    }
+    if (e != cudaSuccess) {
+        fsgpu_index_destroy(ix);
+        return fail(FSGPU_ERR_SUBSYSTEM, "gpu: slab upload failed: %s", cudaGetErrorString(e));
+    }
+    rc = upload_tombstones(ix, tombstones);
+    if (rc) { fsgpu_index_destroy(ix); return rc; }
+    *out = ix;
+    return FSGPU_OK;
+}
+
+extern "C" int fsgpu_index_create_f32(const float* rows, uint64_t n_rows, uint32_t dim,
+                                      const uint8_t* tombstones, const fsgpu_index_options* opts,
+                                      fsgpu_index** out) {
+    if (!out) return fail(FSGPU_ERR_INVALID_CONFIG, "out is NULL");
+    *out = nullptr;
+    fsgpu_index_options o;
+    if (opts) o = *opts; else fsgpu_index_options_default(&o);
+    if (n_rows && !rows) return fail(FSGPU_ERR_INVALID_CONFIG, "rows is NULL");
+    DeviceGuard g(o.device);
+    fsgpu_index* ix = new fsgpu_index();
+    int rc = index_alloc_common(ix, &o, n_rows, dim);
+    if (rc) { fsgpu_index_destroy(ix); return rc; }
+    const uint64_t count = n_rows * dim;
+    if (count) {
+        const float* d_src = rows;
+        float* staged = nullptr;
+        cudaError_t e = cudaMalloc(&ix->d_slab, count * 2);
+        ix->owns_slab = true;
+        if (e == cudaSuccess && !o.slab_is_device) {
+            e = cudaMalloc(&staged, count * 4);
+            if (e == cudaSuccess) e = cudaMemcpy(staged, rows, count * 4, cudaMemcpyHostToDevice);
+            d_src = staged;
+        }
+        if (e == cudaSuccess) {
+            encode_f16_kernel<<<ix->num_sms * 8, 256, 0, ix->stream>>>(d_src, count, ix->d_slab);
+            e = cudaGetLastError();
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ix->stream);
+        }
+        if (staged) cudaFree(staged);
+        if (e != cudaSuccess) {
+            fsgpu_index_destroy(ix);
+            return fail(FSGPU_ERR_SUBSYSTEM, "gpu: f32->f16 encode failed: %s", cudaGetErrorString(e));
+        }
+    }
+    rc = upload_tombstones(ix, tombstones);
+    if (rc) { fsgpu_index_destroy(ix); return rc; }
+    *out = ix;
+    return FSGPU_OK;
+}
+
+extern "C" uint64_t fsgpu_index_rows(const fsgpu_index* ix) { return ix ? ix->n_rows : 0; }
+extern "C" uint32_t fsgpu_index_dim(const fsgpu_index* ix) { return ix ? ix->dim : 0; }
+extern "C" uint64_t fsgpu_index_row_base(const fsgpu_index* ix) { return ix ? ix->row_base : 0; }
+extern "C" int fsgpu_index_device(const fsgpu_index* ix) { return ix ? ix->device : -1; }
+extern "C" const void* fsgpu_index_device_slab(const fsgpu_index* ix) { return ix ? ix->d_slab : nullptr; }
+
+extern "C" int fsgpu_index_set_doc_ids(fsgpu_index* ix, const uint8_t* bytes, const uint64_t* offsets) {
+    if (!ix || !offsets) return fail(FSGPU_ERR_INVALID_CONFIG, "index or offsets is NULL");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    ix->doc_off.assign(offsets, offsets + ix->n_rows + 1);
+    const uint64_t total = ix->doc_off.back();
+    if (total && !bytes) return fail(FSGPU_ERR_INVALID_CONFIG, "doc-id bytes is NULL");
+    ix->doc_bytes.assign(bytes, bytes + total);
+    return FSGPU_OK;
+}
+
+extern "C" int fsgpu_index_doc_id(const fsgpu_index* ix, uint64_t global_row, const uint8_t** out_ptr,
+                                  uint32_t* out_len) {
+    if (!ix || !out_ptr || !out_len) return fail(FSGPU_ERR_INVALID_CONFIG, "NULL argument");
+    if (ix->doc_off.empty()) return fail(FSGPU_ERR_INVALID_CONFIG, "index has no doc-id table");
+    if (global_row < ix->row_base || global_row - ix->row_base >= ix->n_rows)
+        return fail(FSGPU_ERR_INVALID_CONFIG, "row %llu is not in this shard", (unsigned long long)global_row);
+    const uint64_t r = global_row - ix->row_base;
+    *out_ptr = ix->doc_bytes.data() + ix->doc_off[r];
+    *out_len = (uint32_t)(ix->doc_off[r + 1] - ix->doc_off[r]);
+    return FSGPU_OK;
+}
+
+extern "C" int fsgpu_index_read_rows_f16(const fsgpu_index* ix, uint64_t row_start, uint64_t n,
+                                         uint16_t* out_bits) {
+    if (!ix || (n && !out_bits)) return fail(FSGPU_ERR_INVALID_CONFIG, "NULL argument");
+    if (row_start > ix->n_rows || n > ix->n_rows - row_start)
+        return fail(FSGPU_ERR_INVALID_CONFIG, "row range outside the index");
+    if (n == 0) return FSGPU_OK;
+    std::lock_guard<std::mutex> lock(ix->mu);
+    DeviceGuard g(ix->device);
+    CUDA_TRY(cudaMemcpy(out_bits, ix->d_slab + row_start * ix->dim, (size_t)n * ix->dim * 2,
+                        cudaMemcpyDeviceToHost));
+    return FSGPU_OK;
+}
+
+extern "C" int fsgpu_index_set_tombstones(fsgpu_index* ix, const uint8_t* bitmap) {
+    if (!ix) return fail(FSGPU_ERR_INVALID_CONFIG, "index is NULL");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    DeviceGuard g(ix->device);
+    CUDA_TRY(cudaStreamSynchronize(ix->stream));
+    return upload_tombstones(ix, bitmap);
+}
+
+extern "C" int fsgpu_index_profile_enable(fsgpu_index* ix, int on) {
+    if (!ix) return fail(FSGPU_ERR_INVALID_CONFIG, "index is NULL");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    ix->profiling = on != 0;
+    return FSGPU_OK;
+}
+
+extern "C" int fsgpu_index_profile_read(fsgpu_index* ix, fsgpu_profile* out, int reset) {
+    if (!ix || !out) return fail(FSGPU_ERR_INVALID_CONFIG, "NULL argument");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    DeviceGuard g(ix->device);
+    for (auto& ev : ix->ev_pending) {
+        CUDA_TRY(cudaEventSynchronize(ev.second));
+        float ms = 0.0f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, ev.first, ev.second));
+        ix->prof.scan_ms += ms;
+        ix->ev_free.push_back(ev);
+    }
+    ix->ev_pending.clear();
+    *out = ix->prof;
+    if (reset) ix->prof = fsgpu_profile{};
+    return FSGPU_OK;
+}
+
+// ─── search ─────────────────────────────────────────────────────────────────────────────────
+extern "C" int fsgpu_search_top_k_device(const fsgpu_index* ix, const float* d_queries, uint32_t batch,
+                                         uint32_t k, uint64_t* d_out_keys, fsgpu_hit* d_out_hits,
+                                         uint32_t* d_out_counts, void* stream) {
+    if (!ix) return fail(FSGPU_ERR_INVALID_CONFIG, "index is NULL");
+    if (batch && !d_queries) return fail(FSGPU_ERR_INVALID_CONFIG, "queries is NULL");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t s = stream ? (cudaStream_t)stream : ix->stream;
+    if (k && d_out_keys) CUDA_TRY(cudaMemsetAsync(d_out_keys, 0, (size_t)batch * k * 8, s));
+    int rc = search_device_locked(ix, d_queries, batch, k, d_out_keys, d_out_hits, d_out_counts, s);
+    if (rc) return rc;
+    if (!stream) return check_error_flag(ix, s);
+    return FSGPU_OK;
+}
+
+extern "C" int fsgpu_search_top_k(const fsgpu_index* ix, const float* queries, uint32_t batch, uint32_t k,
+                                  uint32_t dim, fsgpu_hit* out, uint32_t* out_counts) {
+    if (!ix) return fail(FSGPU_ERR_INVALID_CONFIG, "index is NULL");
+    if (dim != ix->dim)  // ensure_query_dimension (search.rs:1602-1610)
+        return fail(FSGPU_ERR_DIMENSION_MISMATCH, "expected %u, found %u", ix->dim, dim);
+    if (batch == 0) return FSGPU_OK;
+    if (!queries || !out_counts || (k && !out)) return fail(FSGPU_ERR_INVALID_CONFIG, "NULL argument");
+    if (k == 0 || ix->n_rows == 0) {
+        memset(out_counts, 0, (size_t)batch * 4);
+        return FSGPU_OK;
+    }
+    std::lock_guard<std::mutex> lock(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t s = ix->stream;
+    CUDA_TRY(ix->ws_queries.reserve((size_t)batch * dim * 4));
+    CUDA_TRY(ix->ws_hits.reserve((size_t)batch * k * sizeof(fsgpu_hit)));
+    CUDA_TRY(ix->ws_counts.reserve((size_t)batch * 4));
+    CUDA_TRY(cudaMemcpyAsync(ix->ws_queries.p, queries, (size_t)batch * dim * 4, cudaMemcpyHostToDevice, s));
+    int rc = search_device_locked(ix, ix->ws_queries.as<float>(), batch, k, nullptr,
+                                  ix->ws_hits.as<fsgpu_hit>(), ix->ws_counts.as<uint32_t>(), s);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out, ix->ws_hits.p, (size_t)batch * k * sizeof(fsgpu_hit), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(out_counts, ix->ws_counts.p, (size_t)batch * 4, cudaMemcpyDeviceToHost, s));
+    return check_error_flag(ix, s);
+}
+
+extern "C" int fsgpu_merge_top_k_device(int device, const uint64_t* d_keys, const float* d_scores,
+                                        uint32_t batch, uint32_t n_lists, uint32_t k_in,
+                                        uint64_t list_stride, uint64_t query_stride, uint32_t k_out,
+                                        uint64_t* d_out_keys, fsgpu_hit* d_out_hits,
+                                        uint32_t* d_out_counts, void* stream) {
+    if (batch == 0) return FSGPU_OK;
+    if (!d_keys) return fail(FSGPU_ERR_INVALID_CONFIG, "keys is NULL");
+    if (k_out == 0 || k_in == 0 || n_lists == 0) {
+        DeviceGuard g(device);
+        if (d_out_counts) CUDA_TRY(cudaMemsetAsync(d_out_counts, 0, (size_t)batch * 4, (cudaStream_t)stream));
+        return FSGPU_OK;
+    }
+    DeviceGuard g(device);
+    static thread_local uint32_t* d_errs[64] = {nullptr};  // per-thread, per-device scratch flag
+    if (device < 0 || device >= 64) return fail(FSGPU_ERR_INVALID_CONFIG, "device %d out of range", device);
+    if (!d_errs[device]) CUDA_TRY(cudaMalloc(&d_errs[device], 4));
+    uint32_t* d_err = d_errs[device];
+    MergeArgs m{};
+    m.keys = d_keys;
+    m.scores = d_scores;
+    m.list_stride = list_stride;
+    m.query_stride = query_stride;
+    m.n_lists = n_lists;
+    m.k_in = k_in;
+    m.k_out = k_out;
+    m.cap = cand_capacity(k_out);
+    if ((size_t)m.cap * 8 + 16 > 200 * 1024)
+        return fail(FSGPU_ERR_INVALID_CONFIG, "k_out=%u exceeds the device merge window", k_out);
+    m.out_keys = d_out_keys;
+    m.out_hits = d_out_hits;
+    m.out_counts = d_out_counts;
+    m.error_flag = d_err;
+    cudaStream_t s = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemsetAsync(d_err, 0, 4, s));
+    int rc = launch_merge(m, batch, s);
+    if (rc) return rc;
+    if (!stream) CUDA_TRY(cudaStreamSynchronize(s));
+    return FSGPU_OK;
+}
+
+// ─── gather-dot ─────────────────────────────────────────────────────────────────────────────
+extern "C" int fsgpu_scores_for_rows_device(const fsgpu_index* ix, const float* d_queries, uint32_t batch,
+                                            const uint32_t* d_rows, uint32_t n_per_query,
+                                            float* d_out_scores, uint8_t* d_out_present, void* stream) {
+    if (!ix) return fail(FSGPU_ERR_INVALID_CONFIG, "index is NULL");
+    if (batch == 0 || n_per_query == 0) return FSGPU_OK;
+    std::lock_guard<std::mutex> lock(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t s = stream ? (cudaStream_t)stream : ix->stream;
+    dim3 grid((n_per_query + kScanWarps - 1) / kScanWarps, batch);
+    scores_for_rows_kernel<<<grid, kScanThreads, 0, s>>>(ix->d_slab, ix->n_rows, ix->row_base, ix->dim,
+                                                         d_queries, d_rows, n_per_query, ix->reduce_order,
+                                                         ix->tail_fma, d_out_scores, d_out_present);
+    CUDA_TRY(cudaGetLastError());
+    if (!stream) CUDA_TRY(cudaStreamSynchronize(s));
+    return FSGPU_OK;
+}
+
+extern "C" int fsgpu_scores_for_rows(const fsgpu_index* ix, const float* query, uint32_t dim,
+                                     const uint32_t* rows, uint32_t n, float* out_scores,
+                                     uint8_t* out_present) {
+    if (!ix) return fail(FSGPU_ERR_INVALID_CONFIG, "index is NULL");
+    if (dim != ix->dim) return fail(FSGPU_ERR_DIMENSION_MISMATCH, "expected %u, found %u", ix->dim, dim);
+    if (n == 0) return FSGPU_OK;
+    if (!query || !rows || !out_scores) return fail(FSGPU_ERR_INVALID_CONFIG, "NULL argument");
+    {
+        std::lock_guard<std::mutex> lock(ix->mu);
+        DeviceGuard g(ix->device);
+        cudaStream_t s = ix->stream;
+        CUDA_TRY(ix->ws_queries.reserve((size_t)dim * 4));
+        CUDA_TRY(ix->ws_rows.reserve((size_t)n * 4));
+        CUDA_TRY(ix->ws_scores.reserve((size_t)n * 4));
+        CUDA_TRY(ix->ws_present.reserve(n));
+        CUDA_TRY(cudaMemcpyAsync(ix->ws_queries.p, query, (size_t)dim * 4, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(ix->ws_rows.p, rows, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+        dim3 grid((n + kScanWarps - 1) / kScanWarps, 1);
+        scores_for_rows_kernel<<<grid, kScanThreads, 0, s>>>(
+            ix->d_slab, ix->n_rows, ix->row_base, ix->dim, ix->ws_queries.as<float>(),
+            ix->ws_rows.as<uint32_t>(), n, ix->reduce_order, ix->tail_fma, ix->ws_scores.as<float>(),
+            ix->ws_present.as<uint8_t>());
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(out_scores, ix->ws_scores.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+        if (out_present)
+            CUDA_TRY(cudaMemcpyAsync(out_present, ix->ws_present.p, n, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+    }
+    return FSGPU_OK;
+}
+
+// ─── fusion ─────────────────────────────────────────────────────────────────────────────────
+static void sanitize_rrf(const fsgpu_rrf_config* c, RrfArgs* a) {
+    double k = c ? c->k : 60.0, wl = c ? c->lexical_weight : 1.0, ws = c ? c->semantic_weight : 1.0;
+    if (!(std::isfinite(k) && k >= 0.0)) k = 60.0;        // rrf.rs:124-130
+    if (!(std::isfinite(wl) && wl > 0.0)) wl = 1.0;       // rrf.rs:92-98
+    if (!(std::isfinite(ws) && ws > 0.0)) ws = 1.0;
+    a->k = k;
+    a->w_lex = wl;
+    a->w_sem = ws;
+    a->tiebreak = c ? c->tiebreak : 0;
+}
+
+static int launch_rrf(RrfArgs& a, uint32_t batch, cudaStream_t s) {
+    const uint32_t m = a.n_lex_max + a.n_sem_max;
+    if (m > kFusionMaxEntries)
+        return fail(FSGPU_ERR_INVALID_CONFIG, "rrf: %u candidates exceed the device window of %u", m,
+                    kFusionMaxEntries);
+    const size_t smem = (size_t)host_next_pow2(std::max(m, 1u)) * 20 + 16;
+    CUDA_TRY(cudaFuncSetAttribute(rrf_fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rrf_fuse_kernel<<<batch, kFusionThreads, smem, s>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    return FSGPU_OK;
+}
+
+extern "C" int fsgpu_rrf_fuse_device(int device, const fsgpu_rrf_config* config, uint32_t batch,
+                                     const uint64_t* d_lex_ids, const float* d_lex_scores,
+                                     const uint32_t* d_lex_tie, const uint32_t* d_lex_counts,
+                                     uint32_t n_lex_max, const fsgpu_hit* d_sem_hits,
+                                     const uint32_t* d_sem_tie, const uint32_t* d_sem_counts,
+                                     uint32_t n_sem_max, uint32_t limit, uint32_t offset,
+                                     fsgpu_fused_hit* d_out, uint32_t* d_out_counts, void* stream) {
+    if (batch == 0) return FSGPU_OK;
+    DeviceGuard g(device);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (limit == 0) {
+        if (d_out_counts) CUDA_TRY(cudaMemsetAsync(d_out_counts, 0, (size_t)batch * 4, s));
+        return FSGPU_OK;
+    }
+    RrfArgs a{};
+    sanitize_rrf(config, &a);
+    a.lex_ids = d_lex_ids;
+    a.lex_scores = d_lex_scores;
+    a.lex_tie = d_lex_tie;
+    a.lex_counts = d_lex_counts;
+    a.n_lex_max = n_lex_max;
+    a.sem_hits = d_sem_hits;
+    a.sem_tie = d_sem_tie;
+    a.sem_counts = d_sem_counts;
+    a.n_sem_max = n_sem_max;
+    a.limit = limit;
+    a.offset = offset;
+    a.out = d_out;
+    a.out_counts = d_out_counts;
+    int rc = launch_rrf(a, batch, s);
+    if (rc) return rc;
+    if (!stream) CUDA_TRY(cudaStreamSynchronize(s));
+    return FSGPU_OK;
+}
+
+namespace {
+struct Staging {  // one-shot device staging for the host fusion/encoder entry points
+    std::vector<void*> ptrs;
+    ~Staging() {
+        for (void* p : ptrs) cudaFree(p);
+    }
+    template <class T>
+    cudaError_t up(const T* host, size_t count, T** dev) {
+        *dev = nullptr;
+        if (!host || count == 0) return cudaSuccess;
+        void* p = nullptr;
+        cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+        if (e != cudaSuccess) return e;
+        ptrs.push_back(p);
+        *dev = reinterpret_cast<T*>(p);
+        return cudaMemcpy(p, host, count * sizeof(T), cudaMemcpyHostToDevice);
+    }
+    template <class T>
+    cudaError_t alloc(size_t count, T** dev) {
+        void* p = nullptr;
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(1, count) * sizeof(T));
+        if (e != cudaSuccess) return e;
+        ptrs.push_back(p);
+        *dev = reinterpret_cast<T*>(p);
+        return cudaSuccess;
+    }
+};
+}  // namespace
+
+extern "C" int fsgpu_rrf_fuse(int device, const fsgpu_rrf_config* config, uint32_t batch,
+                              const uint64_t* lex_ids, const float* lex_scores, const uint32_t* lex_tie,
+                              const uint32_t* lex_counts, uint32_t n_lex_max, const uint32_t* sem_rows,
+                              const float* sem_scores, const uint32_t* sem_tie, const uint32_t* sem_counts,
+                              uint32_t n_sem_max, uint32_t limit, uint32_t offset, fsgpu_fused_hit* out,
+                              uint32_t* out_counts) {
+    if (batch == 0) return FSGPU_OK;
+    if (!out_counts) return fail(FSGPU_ERR_INVALID_CONFIG, "out_counts is NULL");
+    int ndev = 0;
+    int rc = fsgpu_device_count(&ndev);
+    if (rc) return rc;
+    if (device < 0 || device >= ndev) return fail(FSGPU_ERR_INVALID_CONFIG, "device %d not present", device);
+    if (limit == 0) {  // rrf.rs:1172-1183 window == 0
+        memset(out_counts, 0, (size_t)batch * 4);
+        return FSGPU_OK;
+    }
+    if (!out) return fail(FSGPU_ERR_INVALID_CONFIG, "out is NULL");
+    const size_t nl = (size_t)batch * n_lex_max, ns = (size_t)batch * n_sem_max;
+    for (size_t i = 0; i < nl; ++i)
+        if (lex_ids[i] >> 40) return fail(FSGPU_ERR_INVALID_CONFIG, "rrf: lexical id exceeds 40 bits");
+    for (const uint32_t* t : {lex_tie, sem_tie})
+        if (t)
+            for (size_t i = 0; i < (t == lex_tie ? nl : ns); ++i)
+                if (t[i] >> kTieBits)
+                    return fail(FSGPU_ERR_INVALID_CONFIG, "rrf: tie rank exceeds %u bits", kTieBits);
+    DeviceGuard g(device);
+    Staging st;
+    RrfArgs a{};
+    sanitize_rrf(config, &a);
+    uint64_t* d_lex_ids; float* d_lex_scores; uint32_t *d_lex_tie, *d_lex_counts;
+    uint32_t *d_sem_rows, *d_sem_tie, *d_sem_counts; float* d_sem_scores;
+    fsgpu_fused_hit* d_out; uint32_t* d_out_counts;
+    CUDA_TRY(st.up(lex_ids, nl, &d_lex_ids));
+    CUDA_TRY(st.up(lex_scores, nl, &d_lex_scores));
+    CUDA_TRY(st.up(lex_tie, nl, &d_lex_tie));
+    CUDA_TRY(st.up(lex_counts, batch, &d_lex_counts));
+    CUDA_TRY(st.up(sem_rows, ns, &d_sem_rows));
+    CUDA_TRY(st.up(sem_scores, ns, &d_sem_scores));
+    CUDA_TRY(st.up(sem_tie, ns, &d_sem_tie));
+    CUDA_TRY(st.up(sem_counts, batch, &d_sem_counts));
+    CUDA_TRY(st.alloc((size_t)batch * limit, &d_out));
+    CUDA_TRY(st.alloc(batch, &d_out_counts));
+    a.lex_ids = d_lex_ids; a.lex_scores = d_lex_scores; a.lex_tie = d_lex_tie; a.lex_counts = d_lex_counts;
+    a.n_lex_max = n_lex_max;
+    a.sem_rows = d_sem_rows; a.sem_scores = d_sem_scores; a.sem_tie = d_sem_tie; a.sem_counts = d_sem_counts;
+    a.n_sem_max = n_sem_max;
+    a.limit = limit; a.offset = offset; a.out = d_out; a.out_counts = d_out_counts;
+    rc = launch_rrf(a, batch, nullptr);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpy(out, d_out, (size_t)batch * limit * sizeof(fsgpu_fused_hit), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(out_counts, d_out_counts, (size_t)batch * 4, cudaMemcpyDeviceToHost));
+    return FSGPU_OK;
+}
+
+extern "C" int fsgpu_blend_two_tier(int device, float blend_factor, const uint32_t* fast_rows,
+                                    const float* fast_scores, const uint32_t* fast_tie, uint32_t n_fast,
+                                    const uint32_t* quality_rows, const float* quality_scores,
+                                    const uint8_t* quality_present, const uint32_t* quality_tie,
+                                    uint32_t n_quality, fsgpu_hit* out, uint32_t* out_count) {
+    if (!out_count) return fail(FSGPU_ERR_INVALID_CONFIG, "out_count is NULL");
+    int ndev = 0;
+    int rc = fsgpu_device_count(&ndev);
+    if (rc) return rc;
+    if (device < 0 || device >= ndev) return fail(FSGPU_ERR_INVALID_CONFIG, "device %d not present", device);
+    const bool union_form = quality_rows != nullptr;
+    if (!union_form && n_quality != n_fast && n_quality != 0)
+        return fail(FSGPU_ERR_INVALID_CONFIG, "aligned blend needs one quality slot per fast hit");
+    const uint32_t m = n_fast + (union_form ? n_quality : 0);
+    if (m == 0) {
+        *out_count = 0;
+        return FSGPU_OK;
+    }
+    if (m > kFusionMaxEntries)
+        return fail(FSGPU_ERR_INVALID_CONFIG, "blend: %u hits exceed the device window of %u", m, kFusionMaxEntries);
+    DeviceGuard g(device);
+    Staging st;
+    BlendArgs a{};
+    float alpha = blend_factor;  // blend.rs:518-524
+    if (!std::isfinite(alpha)) alpha = 0.7f;
+    alpha = std::min(1.0f, std::max(0.0f, alpha));
+    a.alpha = alpha;
+    uint32_t *d_fr, *d_ft, *d_qr, *d_qt; float *d_fs, *d_qs; uint8_t* d_qp; fsgpu_hit* d_out; uint32_t* d_cnt;
+    std::vector<uint8_t> none;
+    const uint32_t nq_eff = union_form ? n_quality : n_fast;
+    if (!union_form && n_quality == 0) {  // aligned form with no quality scores at all
+        none.assign(n_fast, 0);
+        quality_present = none.data();
+    }
+    std::vector<float> zero_q;
+    if (!quality_scores) {
+        zero_q.assign(nq_eff, 0.0f);
+        quality_scores = zero_q.data();
+    }
+    CUDA_TRY(st.up(fast_rows, n_fast, &d_fr));
+    CUDA_TRY(st.up(fast_scores, n_fast, &d_fs));
+    CUDA_TRY(st.up(fast_tie, n_fast, &d_ft));
+    CUDA_TRY(st.up(quality_rows, union_form ? n_quality : 0, &d_qr));
+    CUDA_TRY(st.up(quality_scores, nq_eff, &d_qs));
+    CUDA_TRY(st.up(quality_present, union_form ? 0 : n_fast, &d_qp));
+    CUDA_TRY(st.up(quality_tie, union_form ? n_quality : 0, &d_qt));
+    CUDA_TRY(st.alloc(m, &d_out));
+    CUDA_TRY(st.alloc(1, &d_cnt));
+    a.fast_rows = d_fr; a.fast_scores = d_fs; a.fast_tie = d_ft; a.n_fast = n_fast;
+    a.quality_rows = d_qr; a.quality_scores = d_qs; a.quality_present = d_qp; a.quality_tie = d_qt;
+    a.n_quality = nq_eff;
+    a.out = d_out; a.out_count = d_cnt;
+    const size_t smem = (size_t)host_next_pow2(m) * 20 + 16;
+    CUDA_TRY(cudaFuncSetAttribute(blend_two_tier_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    blend_two_tier_kernel<<<1, kFusionThreads, smem>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    uint32_t cnt = 0;
+    CUDA_TRY(cudaMemcpy(&cnt, d_cnt, 4, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(out, d_out, (size_t)cnt * sizeof(fsgpu_hit), cudaMemcpyDeviceToHost));
+    *out_count = cnt;
+    return FSGPU_OK;
+}
+
+// ─── potion ─────────────────────────────────────────────────────────────────────────────────
+struct fsgpu_potion {
+    int device = 0;
+    uint64_t vocab = 0;
+    uint32_t dim = 0;
+    float* d_table = nullptr;
+    cudaStream_t stream = nullptr;
+    mutable std::mutex mu;
+};
+
+extern "C" void fsgpu_potion_destroy(fsgpu_potion* e) {
+    if (!e) return;
+    {
+        DeviceGuard g(e->device);
+        if (e->stream) {
+            cudaStreamSynchronize(e->stream);
+            cudaStreamDestroy(e->stream);
+        }
+        if (e->d_table) cudaFree(e->d_table);
+    }
+    delete e;
+}
+
+extern "C" int fsgpu_potion_create(const float* table, uint64_t vocab, uint32_t dim, int device,
+                                   fsgpu_potion** out) {
+    if (!out) return fail(FSGPU_ERR_INVALID_CONFIG, "out is NULL");
+    *out = nullptr;
+    if (!table || vocab == 0 || dim == 0)  // validate_model2vec_accumulation_shape (embed/src/simd.rs:118+)
+        return fail(FSGPU_ERR_INVALID_CONFIG, "potion table must be a non-empty [vocab, dim] matrix");
+    int ndev = 0;
+    int rc = fsgpu_device_count(&ndev);
+    if (rc) return rc;
+    if (device < 0 || device >= ndev) return fail(FSGPU_ERR_INVALID_CONFIG, "device %d not present", device);
+    fsgpu_potion* e = new fsgpu_potion();
+    e->device = device;
+    e->vocab = vocab;
+    e->dim = dim;
+    DeviceGuard g(device);
+    cudaError_t err = cudaMalloc(&e->d_table, vocab * dim * 4);
+    if (err == cudaSuccess) err = cudaMemcpy(e->d_table, table, vocab * dim * 4, cudaMemcpyHostToDevice);
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+    if (err != cudaSuccess) {
+        fsgpu_potion_destroy(e);
+        return fail(FSGPU_ERR_SUBSYSTEM, "gpu: potion table upload failed: %s", cudaGetErrorString(err));
+    }
+    *out = e;
+    return FSGPU_OK;
+}
+
+extern "C" int fsgpu_potion_embed_device(const fsgpu_potion* e, const uint32_t* d_ids, const uint64_t* d_offsets,
+                                         uint32_t batch, float* d_out, void* stream) {
+    if (!e) return fail(FSGPU_ERR_INVALID_CONFIG, "encoder is NULL");
+    if (batch == 0) return FSGPU_OK;
+    std::lock_guard<std::mutex> lock(e->mu);
+    DeviceGuard g(e->device);
+    cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+    potion_embed_kernel<<<batch, 256, (size_t)e->dim * 4, s>>>(e->d_table, e->vocab, e->dim, d_ids, d_offsets, d_out);
+    CUDA_TRY(cudaGetLastError());
+    if (!stream) CUDA_TRY(cudaStreamSynchronize(s));
+    return FSGPU_OK;
+}
+
+extern "C" int fsgpu_potion_embed(const fsgpu_potion* e, const uint32_t* ids, const uint64_t* offsets,
+                                  uint32_t batch, float* out) {
+    if (!e) return fail(FSGPU_ERR_INVALID_CONFIG, "encoder is NULL");
+    if (batch == 0) return FSGPU_OK;
+    if (!offsets || !out) return fail(FSGPU_ERR_INVALID_CONFIG, "NULL argument");
+    const uint64_t total = offsets[batch];
+    DeviceGuard g(e->device);
+    Staging st;
+    uint32_t* d_ids; uint64_t* d_off; float* d_out;
+    std::vector<uint32_t> pad(1, 0);
+    CUDA_TRY(st.up(total ? ids : pad.data(), std::max<uint64_t>(1, total), &d_ids));
+    CUDA_TRY(st.up(offsets, (size_t)batch + 1, &d_off));
+    CUDA_TRY(st.alloc((size_t)batch * e->dim, &d_out));
+    int rc = fsgpu_potion_embed_device(e, d_ids, d_off, batch, d_out, nullptr);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpy(out, d_out, (size_t)batch * e->dim * 4, cudaMemcpyDeviceToHost));
+    return FSGPU_OK;
+}
+
+// ─── synthetic corpora ──────────────────────────────────────────────────────────────────────
+extern "C" int fsgpu_synth_rows_device(int device, int kind, uint64_t seed_base, uint64_t row_start,
+                                       uint64_t n_rows, uint32_t dim, uint32_t n_centroids, float noise,
+                                       uint16_t* d_out_f16, void* stream) {
+    if (n_rows == 0) return FSGPU_OK;
+    if (!d_out_f16 || dim == 0) return fail(FSGPU_ERR_INVALID_CONFIG, "NULL output or zero dim");
+    if (kind != 0 && kind != 1) return fail(FSGPU_ERR_INVALID_CONFIG, "kind must be 0 (uniform) or 1 (clustered)");
+    if (kind == 1 && n_centroids == 0) return fail(FSGPU_ERR_INVALID_CONFIG, "clustered corpus needs centroids");
+    DeviceGuard g(device);
+    cudaStream_t s = (cudaStream_t)stream;
+    float* d_cent = nullptr;
+    if (kind == 1) {
+        CUDA_TRY(cudaMalloc(&d_cent, (size_t)n_centroids * dim * 4));
+        synth_centroids_kernel<<<(n_centroids + 63) / 64, 64, 0, s>>>(n_centroids, dim, d_cent);
+    }
+    synth_rows_kernel<<<(unsigned)((n_rows + 127) / 128), 128, 0, s>>>(kind, seed_base, row_start, n_rows, dim,
+                                                                       n_centroids, noise, d_cent, d_out_f16);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (d_cent) cudaFree(d_cent);
+    if (e != cudaSuccess) return fail(FSGPU_ERR_SUBSYSTEM, "gpu: synth kernel failed: %s", cudaGetErrorString(e));
+    return FSGPU_OK;
+}
+
+// ─── FSVI v1 reader (crates/frankensearch-index/src/lib.rs:6-43, :4049-4144, :6114) ─────────
+static uint32_t crc32_ieee(const uint8_t* p, size_t n) {
+    static uint32_t table[256];
+    static std::once_flag once;
+    std::call_once(once, [] {
+        for (uint32_t i = 0; i < 256; ++i) {
+            uint32_t c = i;
+            for (int k = 0; k < 8; ++k) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+            table[i] = c;
+        }
+    });
+    uint32_t c = 0xFFFFFFFFu;
+    for (size_t i = 0; i < n; ++i) c = table[(c ^ p[i]) & 0xFF] ^ (c >> 8);
+    return c ^ 0xFFFFFFFFu;
+}
+
+template <class T>
+static bool rd(const std::vector<uint8_t>& d, size_t* cur, T* out) {
+    if (*cur + sizeof(T) > d.size()) return false;
+    memcpy(out, d.data() + *cur, sizeof(T));  // little-endian host
+    *cur += sizeof(T);
+    return true;
+}
+
+extern "C" int fsgpu_index_open_fsvi(const char* path, uint64_t row_start, uint64_t n_rows_or_0,
+                                     const fsgpu_index_options* opts, fsgpu_index** out) {
+    if (!out) return fail(FSGPU_ERR_INVALID_CONFIG, "out is NULL");
+    *out = nullptr;
+    if (!path) return fail(FSGPU_ERR_INVALID_CONFIG, "path is NULL");
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(FSGPU_ERR_IO, "cannot open %s: %s", path, strerror(errno));
+    fseek(f, 0, SEEK_END);
+    const long fsize = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    // header + record table + string table are read whole; the slab is read by row range
+    std::vector<uint8_t> head((size_t)std::min<long>(fsize, 4 + 2 + 2 + 65535 + 2 + 65535 + 4 + 1 + 3 + 8 + 8 + 4));
+    if (fread(head.data(), 1, head.size(), f) != head.size()) {
+        fclose(f);
+        return fail(FSGPU_ERR_IO, "short read on %s", path);
+    }
+    auto corrupt = [&](const char* why) {
+        fclose(f);
+        return fail(FSGPU_ERR_INDEX_CORRUPTED, "%s: %s", path, why);
+    };
+    size_t cur = 0;
+    uint8_t magic[4];
+    uint16_t version = 0, len16 = 0;
+    if (head.size() < 4) return corrupt("file too small");
+    memcpy(magic, head.data(), 4);
+    cur = 4;
+    if (memcmp(magic, "FSVI", 4) != 0) return corrupt("bad magic");
+    if (!rd(head, &cur, &version)) return corrupt("truncated header");
+    if (version != 1) return corrupt("unsupported FSVI version (only v1 is read here)");
+    if (!rd(head, &cur, &len16) || cur + len16 > head.size()) return corrupt("truncated embedder_id");
+    cur += len16;
+    if (!rd(head, &cur, &len16) || cur + len16 > head.size()) return corrupt("truncated embedder_revision");
+    cur += len16;
+    uint32_t dim = 0, crc_stored = 0;
+    uint8_t quant = 0, reserved[3];
+    uint64_t record_count = 0, vectors_offset = 0;
+    if (!rd(head, &cur, &dim) || !rd(head, &cur, &quant) || !rd(head, &cur, &reserved) ||
+        !rd(head, &cur, &record_count) || !rd(head, &cur, &vectors_offset))
+        return corrupt("truncated header");
+    const size_t crc_end = cur;
+    if (!rd(head, &cur, &crc_stored)) return corrupt("truncated header crc");
+    if (crc32_ieee(head.data(), crc_end) != crc_stored) return corrupt("header CRC mismatch");
+    if (quant > 1) return corrupt("unknown quantization");
+    if (quant == 0) {
+        // an f32 slab is scored by dot_product_f32_bytes_f32 in the reference (search.rs:1300-1321);
+        // re-encoding it to f16 here would silently change scores.
+        fclose(f);
+        return fail(FSGPU_ERR_INVALID_CONFIG, "%s: f32-quantised FSVI is not supported on the device path (f16 only)", path);
+    }
+    if (dim == 0) return corrupt("zero dimension");
+    const size_t records_offset = cur;
+    const uint64_t elem = quant == 1 ? 2 : 4;
+    if (vectors_offset % 64 != 0) return corrupt("vector slab is not 64-byte aligned");
+    if (records_offset + record_count * 16 > vectors_offset ||
+        vectors_offset + record_count * dim * elem > (uint64_t)fsize)
+        return corrupt("section offsets exceed file size");
+    if (row_start > record_count) {
+        fclose(f);
+        return fail(FSGPU_ERR_INVALID_CONFIG, "row_start beyond record_count");
+    }
+    const uint64_t n = n_rows_or_0 ? std::min(n_rows_or_0, record_count - row_start) : record_count - row_start;
+
+    std::vector<uint8_t> meta(vectors_offset - records_offset);
+    fseek(f, (long)records_offset, SEEK_SET);
+    if (!meta.empty() && fread(meta.data(), 1, meta.size(), f) != meta.size()) return corrupt("short read (records)");
+    const uint8_t* strings = meta.data() + record_count * 16;
+    const size_t strings_len = meta.size() - record_count * 16;
+    std::vector<uint8_t> tomb((n + 7) / 8, 0);
+    bool any_tomb = false;
+    std::vector<uint8_t> doc_bytes;
+    std::vector<uint64_t> doc_off(n + 1, 0);
+    for (uint64_t r = 0; r < n; ++r) {
+        const uint8_t* rec = meta.data() + (row_start + r) * 16;
+        uint32_t off;
+        uint16_t len, flags;
+        memcpy(&off, rec + 8, 4);
+        memcpy(&len, rec + 12, 2);
+        memcpy(&flags, rec + 14, 2);
+        if ((size_t)off + len > strings_len) return corrupt("doc_id outside string table");
+        doc_bytes.insert(doc_bytes.end(), strings + off, strings + off + len);
+        doc_off[r + 1] = doc_bytes.size();
+        if (flags & 1) {
+            tomb[r >> 3] |= (uint8_t)(1u << (r & 7));
+            any_tomb = true;
+        }
+    }
+    std::vector<uint8_t> slab((size_t)(n * dim * elem));
+    fseek(f, (long)(vectors_offset + row_start * dim * elem), SEEK_SET);
+    if (!slab.empty() && fread(slab.data(), 1, slab.size(), f) != slab.size()) return corrupt("short read (slab)");
+    fclose(f);
+
+    fsgpu_index_options o;
+    if (opts) o = *opts; else fsgpu_index_options_default(&o);
+    o.slab_is_device = 0;
+    o.tail_fma = 1;  // file-backed index scores with the bytes kernel (search.rs:1283)
+    if (o.row_base == 0) o.row_base = row_start;
+    fsgpu_index* ix = nullptr;
+    int rc = fsgpu_index_create_f16(reinterpret_cast<const uint16_t*>(slab.data()), n, dim,
+                                    any_tomb ? tomb.data() : nullptr, &o, &ix);
+    if (rc) return rc;
+    ix->doc_bytes.swap(doc_bytes);
+    ix->doc_off.swap(doc_off);
+    *out = ix;
+    return FSGPU_OK;
+}

@@ -1,0 +1,171 @@
+// fsgpu_common.cuh — shared device helpers: IEEE-exact scalar ops, order keys, the generic
+// warp-cooperative exact dot, CTA-wide bitonic sort and the bounded top-k candidate buffer.
+#pragma once
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "fsgpu.h"
+
+namespace fsgpu {
+
+typedef ::fsgpu_hit fsgpu_hit_t;
+typedef ::fsgpu_fused_hit fsgpu_fused_hit_t;
+
+constexpr uint32_t kNegInfOrdered = 0x007FFFFFu;  // ascending total-order image of -inf
+
+// ─── exact arithmetic (never contracted into FMA) ───────────────────────────────────────────
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+
+// Final 8-lane horizontal add in the configured `wide::f32x8::reduce_add` lane order
+// (include/fsgpu.h fsgpu_reduce_order; crates/frankensearch-index/src/simd.rs:439).
+__device__ __forceinline__ float reduce8(const float v[8], int order) {
+    switch (order) {
+        case 1:
+            return add_rn(add_rn(add_rn(v[0], v[4]), add_rn(v[2], v[6])),
+                          add_rn(add_rn(v[1], v[5]), add_rn(v[3], v[7])));
+        case 2:
+            return add_rn(add_rn(add_rn(add_rn(v[0], v[1]), v[2]), v[3]),
+                          add_rn(add_rn(add_rn(v[4], v[5]), v[6]), v[7]));
+        case 3:
+            return add_rn(add_rn(add_rn(v[0], v[2]), add_rn(v[1], v[3])),
+                          add_rn(add_rn(v[4], v[6]), add_rn(v[5], v[7])));
+        case 4:
+            return add_rn(
+                add_rn(add_rn(add_rn(add_rn(add_rn(add_rn(v[0], v[1]), v[2]), v[3]), v[4]), v[5]),
+                       v[6]),
+                v[7]);
+        default:
+            return add_rn(add_rn(add_rn(v[0], v[1]), add_rn(v[2], v[3])),
+                          add_rn(add_rn(v[4], v[5]), add_rn(v[6], v[7])));
+    }
+}
+
+__device__ __forceinline__ float h2f(uint16_t bits) {
+    return __half2float(__ushort_as_half(bits));  // exact widening (simd.rs:67-81)
+}
+
+// ─── order keys (search.rs:1655-1686) ───────────────────────────────
+// score_key: NaN -> -inf.  Ascending u32 image of f32::total_cmp, then
+// key = (ordered << 32) | ~global_row  so that a LARGER u64 is a BETTER hit (higher score, then
+// lower row).  Key 0 is impossible for a real hit (ordered >= 0x007FFFFF) and marks "empty".
+__device__ __forceinline__ uint32_t ordered_score(float s) {
+    uint32_t u = __float_as_uint(s);
+    if ((u & 0x7FFFFFFFu) > 0x7F800000u) u = 0xFF800000u;  // NaN -> -inf
+    return (u & 0x80000000u) ? ~u : (u ^ 0x80000000u);
+}
+__device__ __forceinline__ float unordered_score(uint32_t o) {
+    const uint32_t u = (o & 0x80000000u) ? (o ^ 0x80000000u) : ~o;
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ uint64_t make_key(float score, uint32_t global_row) {
+    return ((uint64_t)ordered_score(score) << 32) | (uint32_t)(~global_row);
+}
+__device__ __forceinline__ uint32_t key_row(uint64_t key) { return ~(uint32_t)key; }
+__device__ __forceinline__ float key_score(uint64_t key) {
+    return unordered_score((uint32_t)(key >> 32));
+}
+
+__device__ __forceinline__ bool tombstoned(const uint8_t* __restrict__ bitmap, uint64_t local_row) {
+    return bitmap != nullptr && ((__ldg(bitmap + (local_row >> 3)) >> (local_row & 7)) & 1u);
+}
+
+// ─── generic exact dot: one warp per row, any dim ───────────────────────────────────────────
+// Lane t = 8a + l owns chain (accumulator a, SIMD lane l) of the reference kernel
+// (crates/frankensearch-index/src/simd.rs:418-444): whole groups of four 8-element chunks go to
+// accumulators 0..3, left-over chunks to accumulator 0, `(s0+s1)+(s2+s3)`, 8-lane reduce, then
+// the scalar tail (`mul_add` when tail_fma, else mul then add).  All 32 lanes must call; every
+// lane returns the score.  `q` may be global or shared.
+__device__ __forceinline__ float warp_exact_dot(const uint16_t* __restrict__ row,
+                                                const float* __restrict__ q, uint32_t dim,
+                                                int reduce_order, int tail_fma) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t chunks = dim >> 3;
+    const uint32_t groups = chunks >> 2;
+    float acc = 0.0f;
+    for (uint32_t g = 0; g < groups; ++g) {
+        const uint32_t e = g * 32u + lane;
+        acc = add_rn(acc, mul_rn(h2f(row[e]), q[e]));
+    }
+    for (uint32_t c = groups * 4u; c < chunks; ++c) {
+        if (lane < 8u) {
+            const uint32_t e = c * 8u + lane;
+            acc = add_rn(acc, mul_rn(h2f(row[e]), q[e]));
+        }
+    }
+    acc = add_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 8));   // s0+s1 | s2+s3
+    acc = add_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 16));  // (s0+s1)+(s2+s3)
+    float v[8];
+#pragma unroll
+    for (int l = 0; l < 8; ++l) v[l] = __shfl_sync(0xffffffffu, acc, l);
+    float result = reduce8(v, reduce_order);
+    for (uint32_t e = chunks * 8u; e < dim; ++e) {
+        const float val = h2f(row[e]);
+        result = tail_fma ? __fmaf_rn(val, q[e], result) : add_rn(result, mul_rn(val, q[e]));
+    }
+    return result;
+}
+
+// ─── CTA-wide bitonic sort, descending, n a power of two, keys in shared memory ─────────────
+__device__ __forceinline__ void cta_sort_desc(uint64_t* keys, uint32_t n) {
+    for (uint32_t k = 2; k <= n; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+                const uint32_t ixj = i ^ j;
+                if (ixj > i) {
+                    const uint64_t a = keys[i], b = keys[ixj];
+                    const bool desc = (i & k) == 0;
+                    if (desc ? (a < b) : (a > b)) {
+                        keys[i] = b;
+                        keys[ixj] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t next_pow2(uint32_t x) {
+    return x <= 1 ? 1u : 1u << (32 - __clz(x - 1));
+}
+
+// ─── bounded candidate buffer (one per query per CTA) ───────────────────────────────────────
+// Threads append keys that beat `tau` (the k-th best key seen so far, 0 until k keys are held);
+// `compact` (CTA-collective) sorts, keeps the best k and raises tau.  Equivalent to the
+// reference's bounded heap + cutoff (search.rs:1285-1295, :1688-1702): what survives is exactly
+// the k largest keys pushed, independent of push order.
+struct CandBuf {
+    uint64_t* keys;  // [cap] shared
+    uint32_t* cnt;   // shared
+    uint64_t* tau;   // shared
+};
+
+__device__ __forceinline__ bool cand_push(const CandBuf& b, uint32_t cap, uint64_t key) {
+    const uint32_t pos = atomicAdd(b.cnt, 1u);
+    if (pos < cap) {
+        b.keys[pos] = key;
+        return true;
+    }
+    return false;  // capacity contract violated (caller reports)
+}
+
+// CTA-collective.  All threads must call with identical arguments.
+__device__ __forceinline__ void cand_compact(const CandBuf& b, uint32_t cap, uint32_t k) {
+    __syncthreads();
+    const uint32_t n = min(*b.cnt, cap);
+    const uint32_t n2 = min(next_pow2(n), cap);
+    for (uint32_t i = n + threadIdx.x; i < n2; i += blockDim.x) b.keys[i] = 0ull;
+    __syncthreads();
+    cta_sort_desc(b.keys, n2);
+    if (threadIdx.x == 0) {
+        const uint32_t kept = min(n, k);
+        *b.cnt = kept;
+        *b.tau = kept >= k ? b.keys[k - 1] : 0ull;
+    }
+    __syncthreads();
+}
+
+}  // namespace fsgpu

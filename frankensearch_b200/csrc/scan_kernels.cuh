@@ -1,0 +1,429 @@
+// scan_kernels.cuh — the fused exact f16 scan + top-k kernels.
+//
+// Reference path replaced: VectorIndex::search_top_k_internal -> scan_parallel ->
+// scan_range_chunk -> dot_product_f16_bytes_f32 -> insert_candidate -> merge_partial_heaps ->
+// resolve_hits (crates/frankensearch-index/src/search.rs:426-494, :1013-1036, :1257-1327,
+// :1688-1720, :1493-1500; simd.rs:398-446).
+//
+// Data layout in HBM: the slab is n_rows x dim IEEE f16, row-major, 16-byte aligned rows
+// (dim % 8 == 0 on the fast path).  One pass streams it exactly once for QB queries.
+#pragma once
+
+#include "fsgpu_common.cuh"
+
+namespace fsgpu {
+
+constexpr int kScanThreads = 256;
+constexpr int kScanWarps = kScanThreads / 32;
+
+struct ScanArgs {
+    const uint16_t* slab;      // [n_rows, dim] f16 bits
+    const uint8_t* tombstones; // packed bitmap or nullptr
+    const float* queries;      // [QB, dim] f32 (device)
+    uint64_t n_rows;           // local rows
+    uint64_t row_base;         // global row of local row 0
+    uint32_t dim;
+    uint32_t k;                // per-CTA keep
+    uint32_t cap;              // candidate buffer capacity (power of two)
+    uint32_t sync_every;       // tiles between compaction checks
+    int reduce_order;
+    int tail_fma;
+    uint64_t* partial;         // [gridDim.x, QB, k] keys, 0-padded
+    uint32_t* error_flag;      // set to 1 on a capacity contract violation
+};
+
+__device__ __forceinline__ uint4 ld_stream_16(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& x, float f[8]) {
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&x.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&x.y));
+    const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&x.z));
+    const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&x.w));
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+    f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+
+// Shared-memory carve-up shared by the scan kernels.
+struct ScanSmem {
+    uint64_t* cand;  // [QB][cap]
+    uint64_t* tau;   // [QB]
+    float* q;        // [QB][dim]
+    uint32_t* cnt;   // [QB]
+};
+__host__ __device__ inline size_t scan_smem_bytes(int qb, uint32_t cap, uint32_t dim) {
+    return (size_t)qb * cap * 8 + (size_t)qb * 8 + (size_t)qb * dim * 4 + (size_t)qb * 4 + 16;
+}
+__device__ __forceinline__ ScanSmem carve_scan_smem(unsigned char* base, int qb, uint32_t cap,
+                                                    uint32_t dim) {
+    ScanSmem s;
+    s.cand = reinterpret_cast<uint64_t*>(base);
+    s.tau = s.cand + (size_t)qb * cap;
+    s.q = reinterpret_cast<float*>(s.tau + qb);
+    s.cnt = reinterpret_cast<uint32_t*>(s.q + (size_t)qb * dim);
+    return s;
+}
+
+// CTA-collective: at a sync point, compact every buffer that could overflow before the next
+// one and refresh the per-thread float thresholds.
+template <int QB>
+__device__ __forceinline__ void scan_sync_point(const ScanSmem& sm, uint32_t cap, uint32_t k,
+                                                uint32_t trigger, bool force, float thr[QB]) {
+    __syncthreads();
+#pragma unroll
+    for (int qi = 0; qi < QB; ++qi) {
+        const uint32_t c = sm.cnt[qi];
+        if (force || c > trigger) {  // CTA-uniform: read after the barrier
+            CandBuf b{sm.cand + (size_t)qi * cap, sm.cnt + qi, sm.tau + qi};
+            cand_compact(b, cap, k);
+        }
+    }
+#pragma unroll
+    for (int qi = 0; qi < QB; ++qi) {
+        const uint64_t t = sm.tau[qi];
+        thr[qi] = t ? key_score(t) : -INFINITY;
+    }
+}
+
+template <int QB>
+__device__ __forceinline__ void scan_offer(const ScanSmem& sm, const ScanArgs& args, int qi,
+                                           float score, uint64_t local_row) {
+    const uint64_t key = make_key(score, (uint32_t)(args.row_base + local_row));
+    if (key > sm.tau[qi] && !tombstoned(args.tombstones, local_row)) {
+        CandBuf b{sm.cand + (size_t)qi * args.cap, sm.cnt + qi, sm.tau + qi};
+        if (!cand_push(b, args.cap, key)) atomicExch(args.error_flag, 1u);
+    }
+}
+
+template <int QB>
+__device__ __forceinline__ void scan_write_partials(const ScanSmem& sm, const ScanArgs& args) {
+    for (int qi = 0; qi < QB; ++qi) {
+        const uint32_t c = min(sm.cnt[qi], args.k);
+        uint64_t* out = args.partial + ((size_t)blockIdx.x * QB + qi) * args.k;
+        const uint64_t* src = sm.cand + (size_t)qi * args.cap;
+        for (uint32_t i = threadIdx.x; i < args.k; i += blockDim.x) out[i] = i < c ? src[i] : 0ull;
+    }
+}
+
+// ─── fast path: dim = 32*NJ, QB queries per pass, R row-groups per thread ───────────────────
+// Thread mapping (per warp): lane = 8a + r handles accumulator `a` (chunks 4j+a) of row r of
+// the warp's 8-row group: eight chains (a, l=0..7) per query live in registers, 16-byte loads
+// cover a row with 4 lanes x NJ loads (each warp-level load = 8 rows x 64 contiguous bytes,
+// whole sectors).  The reference tree `(s0+s1)+(s2+s3)` is two xor-shuffles (8, 16); every lane
+// then holds V[0..7] and applies the configured 8-lane order.  Products and sums are separate
+// IEEE roundings (mul.rn / add.rn), so scores are bit-identical to simd.rs:398-446.
+template <int NJ, int QB, int R>
+__global__ void __launch_bounds__(kScanThreads)
+scan_topk_fast_kernel(const ScanArgs args) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t dim = NJ * 32;
+    const ScanSmem sm = carve_scan_smem(smem_raw, QB, args.cap, dim);
+
+    for (uint32_t i = threadIdx.x; i < QB * dim; i += blockDim.x) sm.q[i] = args.queries[i];
+    if (threadIdx.x < QB) {
+        sm.cnt[threadIdx.x] = 0u;
+        sm.tau[threadIdx.x] = 0ull;
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int a = lane >> 3, r = lane & 7;
+    constexpr int kRowsPerWarp = 8 * R;
+    constexpr int kTileRows = kScanWarps * kRowsPerWarp;
+    const uint64_t n = args.n_rows;
+    const uint64_t n_tiles = (n + kTileRows - 1) / kTileRows;
+    const uint32_t trigger = args.cap - args.sync_every * kTileRows;
+    const uint4* slab4 = reinterpret_cast<const uint4*>(args.slab);
+
+    float thr[QB];
+#pragma unroll
+    for (int qi = 0; qi < QB; ++qi) thr[qi] = -INFINITY;
+
+    uint32_t it = 0;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const uint64_t row0 = tile * kTileRows + (uint64_t)warp * kRowsPerWarp + r;
+        uint4 x[R][NJ];
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+            const uint64_t row = row0 + rr * 8;
+            const uint64_t rowc = row < n ? row : n - 1;
+            const uint4* p = slab4 + rowc * (NJ * 4) + a;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) x[rr][j] = ld_stream_16(p + 4 * j);
+        }
+        float acc[R][QB][8];
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr)
+#pragma unroll
+            for (int qi = 0; qi < QB; ++qi)
+#pragma unroll
+                for (int l = 0; l < 8; ++l) acc[rr][qi][l] = 0.0f;
+
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            float xf[R][8];
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) unpack8(x[rr][j], xf[rr]);
+#pragma unroll
+            for (int qi = 0; qi < QB; ++qi) {
+                const float4* qp = reinterpret_cast<const float4*>(sm.q + qi * dim + (4 * j + a) * 8);
+                const float4 q0 = qp[0], q1 = qp[1];
+                const float qv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr)
+#pragma unroll
+                    for (int l = 0; l < 8; ++l)
+                        acc[rr][qi][l] = add_rn(acc[rr][qi][l], mul_rn(xf[rr][l], qv[l]));
+            }
+        }
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+            const uint64_t row = row0 + rr * 8;
+#pragma unroll
+            for (int qi = 0; qi < QB; ++qi) {
+                float v[8];
+#pragma unroll
+                for (int l = 0; l < 8; ++l) {
+                    float s = acc[rr][qi][l];
+                    s = add_rn(s, __shfl_xor_sync(0xffffffffu, s, 8));
+                    s = add_rn(s, __shfl_xor_sync(0xffffffffu, s, 16));
+                    v[l] = s;
+                }
+                const float score = reduce8(v, args.reduce_order);
+                if (!(score < thr[qi])) {  // rare once tau is established; NaN passes
+                    if ((qi & 3) == a && row < n) scan_offer<QB>(sm, args, qi, score, row);
+                }
+            }
+        }
+        if ((it + 1) % args.sync_every == 0)
+            scan_sync_point<QB>(sm, args.cap, args.k, trigger, false, thr);
+    }
+    scan_sync_point<QB>(sm, args.cap, args.k, trigger, true, thr);
+    scan_write_partials<QB>(sm, args);
+}
+
+// ─── generic path: any dim (tails included), one warp per row, one query per pass ───────────
+__global__ void __launch_bounds__(kScanThreads)
+scan_topk_generic_kernel(const ScanArgs args) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const ScanSmem sm = carve_scan_smem(smem_raw, 1, args.cap, args.dim);
+    for (uint32_t i = threadIdx.x; i < args.dim; i += blockDim.x) sm.q[i] = args.queries[i];
+    if (threadIdx.x == 0) {
+        sm.cnt[0] = 0u;
+        sm.tau[0] = 0ull;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int kTileRows = kScanWarps;  // one row per warp per iteration
+    const uint64_t n = args.n_rows;
+    const uint64_t n_tiles = (n + kTileRows - 1) / kTileRows;
+    const uint32_t trigger = args.cap - args.sync_every * kTileRows;
+    float thr[1] = {-INFINITY};
+    uint32_t it = 0;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const uint64_t row = tile * kTileRows + warp;
+        const uint64_t rowc = row < n ? row : n - 1;
+        const float score = warp_exact_dot(args.slab + rowc * args.dim, sm.q, args.dim,
+                                           args.reduce_order, args.tail_fma);
+        if (!(score < thr[0]) && lane == 0 && row < n) scan_offer<1>(sm, args, 0, score, row);
+        if ((it + 1) % args.sync_every == 0)
+            scan_sync_point<1>(sm, args.cap, args.k, trigger, false, thr);
+    }
+    scan_sync_point<1>(sm, args.cap, args.k, trigger, true, thr);
+    scan_write_partials<1>(sm, args);
+}
+
+// ─── merge: one CTA per query over `n_lists` lists of `k_in` keys ───────────────────────────
+// merge_partial_heaps (search.rs:1704-1720) + the best-first sort of resolve_hits
+// (search.rs:1493-1500).  Also the cross-shard merge after the all-gather.
+struct MergeArgs {
+    const uint64_t* keys;     // key of (query b, list g, slot i) at keys[g*list_stride + b*query_stride + i]
+    const float* scores;      // optional raw scores, same addressing (travel with the keys)
+    uint64_t list_stride;
+    uint64_t query_stride;
+    uint32_t n_lists;
+    uint32_t k_in;
+    uint32_t k_out;
+    uint32_t cap;             // power of two, >= 2*k_out
+    uint64_t* out_keys;       // [batch, k_out] (nullable)
+    fsgpu_hit_t* out_hits;    // [batch, k_out] (nullable)
+    uint32_t* out_counts;     // [batch] (nullable)
+    // optional exact re-computation of -inf/NaN class scores from the local slab
+    const uint16_t* slab;
+    const float* queries;     // [batch, dim]
+    uint64_t n_rows, row_base;
+    uint32_t dim;
+    int reduce_order, tail_fma;
+    uint32_t* error_flag;
+};
+
+__global__ void __launch_bounds__(kScanThreads) merge_topk_kernel(const MergeArgs args) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* cand = reinterpret_cast<uint64_t*>(smem_raw);
+    uint64_t* tau = cand + args.cap;
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(tau + 1);
+    const uint32_t b = blockIdx.x;
+    if (threadIdx.x == 0) {
+        *cnt = 0u;
+        *tau = 0ull;
+    }
+    __syncthreads();
+    const CandBuf buf{cand, cnt, tau};
+    const uint64_t total = (uint64_t)args.n_lists * args.k_in;
+    const uint32_t step = blockDim.x;
+    // between compaction checks at most `chunk` pushes can happen
+    const uint32_t chunk = max(step, ((args.cap - args.k_out) / 2 / step) * step);
+    const uint32_t trigger = args.cap - chunk;
+    for (uint64_t base = 0; base < total; base += chunk) {
+        const uint64_t t = *tau;
+        for (uint32_t o = threadIdx.x; o < chunk; o += step) {
+            const uint64_t idx = base + o;
+            if (idx < total) {
+                const uint64_t g = idx / args.k_in, i = idx % args.k_in;
+                const uint64_t key = args.keys[g * args.list_stride + b * args.query_stride + i];
+                if (key > t) {
+                    if (!cand_push(buf, args.cap, key)) atomicExch(args.error_flag, 1u);
+                }
+            }
+        }
+        __syncthreads();
+        if (*cnt > trigger) cand_compact(buf, args.cap, args.k_out);
+        __syncthreads();
+    }
+    cand_compact(buf, args.cap, args.k_out);
+    const uint32_t count = *cnt;
+    if (threadIdx.x == 0 && args.out_counts) args.out_counts[b] = count;
+    if (args.out_keys)
+        for (uint32_t i = threadIdx.x; i < args.k_out; i += step)
+            args.out_keys[(size_t)b * args.k_out + i] = i < count ? cand[i] : 0ull;
+    if (args.out_hits) {
+        for (uint32_t i = threadIdx.x; i < args.k_out; i += step) {
+            fsgpu_hit_t h;
+            h.row = i < count ? key_row(cand[i]) : 0xFFFFFFFFu;
+            h.score = i < count ? key_score(cand[i]) : 0.0f;
+            args.out_hits[(size_t)b * args.k_out + i] = h;
+        }
+        __syncthreads();
+        // score_key folded NaN into -inf for ordering; VectorHit carries the RAW score
+        // (search.rs:1549-1553), so -inf class entries get their raw value back.
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (uint32_t i = warp; i < count; i += kScanWarps) {
+            const uint64_t key = cand[i];
+            if ((uint32_t)(key >> 32) != kNegInfOrdered) continue;  // warp-uniform
+            float raw = -INFINITY;
+            bool have = false;
+            if (args.scores) {
+                for (uint64_t idx = lane; idx < total && !have; idx += 32) {
+                    const uint64_t g = idx / args.k_in, j = idx % args.k_in;
+                    const uint64_t off = g * args.list_stride + b * args.query_stride + j;
+                    if (args.keys[off] == key) {
+                        raw = args.scores[off];
+                        have = true;
+                    }
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, have);
+                if (m) raw = __shfl_sync(0xffffffffu, raw, __ffs(m) - 1);
+                have = m != 0;
+            }
+            if (!have && args.slab) {
+                const uint64_t grow = key_row(key);
+                if (grow >= args.row_base && grow - args.row_base < args.n_rows) {
+                    raw = warp_exact_dot(args.slab + (grow - args.row_base) * args.dim,
+                                         args.queries + (size_t)b * args.dim, args.dim,
+                                         args.reduce_order, args.tail_fma);
+                }
+            }
+            if (lane == 0) args.out_hits[(size_t)b * args.k_out + i].score = raw;
+        }
+    }
+}
+
+// ─── gather-dot: quality_scores_for_hits (two_tier.rs:1566-1631, :1946-1973) ────────────────
+__global__ void __launch_bounds__(kScanThreads)
+scores_for_rows_kernel(const uint16_t* __restrict__ slab, uint64_t n_rows, uint64_t row_base,
+                       uint32_t dim, const float* __restrict__ queries,
+                       const uint32_t* __restrict__ rows, uint32_t n_per_query, int reduce_order,
+                       int tail_fma, float* __restrict__ out_scores,
+                       uint8_t* __restrict__ out_present) {
+    const uint32_t b = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const uint32_t i = blockIdx.x * kScanWarps + (threadIdx.x >> 5);
+    if (i >= n_per_query) return;
+    const size_t o = (size_t)b * n_per_query + i;
+    const uint64_t grow = rows[o];
+    const bool ok = rows[o] != 0xFFFFFFFFu && grow >= row_base && grow - row_base < n_rows;
+    float s = 0.0f;
+    if (ok)
+        s = warp_exact_dot(slab + (grow - row_base) * dim, queries + (size_t)b * dim, dim,
+                           reduce_order, tail_fma);
+    if (lane == 0) {
+        out_scores[o] = s;
+        if (out_present) out_present[o] = ok ? 1 : 0;
+    }
+}
+
+// ─── score-all: the `limit >= n` / very large k arm (search.rs:449-473) ─────────────────────
+// Writes one order key per live row (0 for tombstoned rows); the caller sorts descending.
+__global__ void __launch_bounds__(kScanThreads)
+score_all_kernel(const uint16_t* __restrict__ slab, const uint8_t* __restrict__ tombstones,
+                 uint64_t n_rows, uint64_t row_base, uint32_t dim,
+                 const float* __restrict__ query, int reduce_order, int tail_fma,
+                 uint64_t* __restrict__ out_keys) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* q = reinterpret_cast<float*>(smem_raw);
+    for (uint32_t i = threadIdx.x; i < dim; i += blockDim.x) q[i] = query[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    for (uint64_t row = (uint64_t)blockIdx.x * kScanWarps + (threadIdx.x >> 5); row < n_rows;
+         row += (uint64_t)gridDim.x * kScanWarps) {
+        const float s = warp_exact_dot(slab + row * dim, q, dim, reduce_order, tail_fma);
+        if (lane == 0)
+            out_keys[row] = tombstoned(tombstones, row) ? 0ull
+                                                        : make_key(s, (uint32_t)(row_base + row));
+    }
+}
+
+// Emits the first `k_eff` keys of a descending-sorted key array as the result of one query:
+// count = number of live (non-zero) keys, raw scores restored for the -inf/NaN class.
+__global__ void __launch_bounds__(kScanThreads)
+emit_sorted_prefix_kernel(const uint64_t* __restrict__ sorted, uint32_t k_eff, uint32_t k_out,
+                          const uint16_t* __restrict__ slab, const float* __restrict__ query,
+                          uint64_t n_rows, uint64_t row_base, uint32_t dim, int reduce_order,
+                          int tail_fma, uint64_t* __restrict__ out_keys,
+                          fsgpu_hit_t* __restrict__ out_hits, uint32_t* __restrict__ out_count) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && out_count && k_eff == 0) *out_count = 0;
+    for (uint32_t i = warp_global; i < k_out; i += n_warps) {  // warp-uniform loop
+        const uint64_t key = i < k_eff ? sorted[i] : 0ull;
+        if (out_keys && lane == 0) out_keys[i] = key;
+        if (key != 0 && lane == 0 && out_count) {
+            const bool last = (i + 1 == k_eff) || sorted[i + 1] == 0ull;
+            if (last) *out_count = i + 1;
+        }
+        if (i == 0 && key == 0 && lane == 0 && out_count) *out_count = 0;
+        if (out_hits) {
+            float score = key ? key_score(key) : 0.0f;
+            if (key && (uint32_t)(key >> 32) == kNegInfOrdered) {
+                const uint64_t grow = key_row(key);
+                if (grow >= row_base && grow - row_base < n_rows)
+                    score = warp_exact_dot(slab + (grow - row_base) * dim, query, dim, reduce_order,
+                                           tail_fma);
+            }
+            if (lane == 0) {
+                fsgpu_hit_t h;
+                h.row = key ? key_row(key) : 0xFFFFFFFFu;
+                h.score = score;
+                out_hits[i] = h;
+            }
+        }
+    }
+}
+
+}  // namespace fsgpu

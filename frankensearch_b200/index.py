@@ -1,0 +1,242 @@
+"""Host-side mirror of the reference vector-index seam over the C ABI.
+
+`GpuVectorIndex` presents the method set the reference searchers call on
+`VectorIndex` / `InMemoryVectorIndex` (crates/frankensearch-index/src/search.rs:192-206,
+crates/frankensearch-index/src/in_memory.rs:1667, :2555) and
+`TwoTierIndex::quality_scores_for_hits` (two_tier.rs:1566-1631).  All arithmetic happens in
+libfsgpu.so on the GPU; this file is plumbing (buffers, doc-id strings, error mapping).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import SearchError, check, ptr
+from .types import VectorHit
+
+REDUCE_ORDERS = {
+    "halves_pairwise": 0, "avx_tree": 1, "halves_sequential": 2, "halves_stride2": 3, "sequential": 4,
+}
+
+
+def _options(device: int, reduce_order, tail_fma: bool, slab_is_device: bool, row_base: int):
+    o = _ffi.IndexOptions()
+    _ffi.lib().fsgpu_index_options_default(C.byref(o))
+    o.device = device
+    o.reduce_order = REDUCE_ORDERS[reduce_order] if isinstance(reduce_order, str) else int(reduce_order)
+    o.tail_fma = 1 if tail_fma else 0
+    o.slab_is_device = 1 if slab_is_device else 0
+    o.row_base = row_base
+    return o
+
+
+def _bitmap(flags) -> Optional[np.ndarray]:
+    if flags is None:
+        return None
+    flags = np.asarray(flags, dtype=bool)
+    return np.packbits(flags, bitorder="little") if flags.any() else None
+
+
+class GpuVectorIndex:
+    """One f16 slab shard resident on one B200."""
+
+    def __init__(self, handle: int, doc_ids: Optional[Sequence[str]] = None, dedup_doc_ids: bool = False,
+                 keepalive=None):
+        self._h = C.c_void_p(handle)
+        self._doc_ids = list(doc_ids) if doc_ids is not None else None
+        self._dedup = dedup_doc_ids
+        self._keepalive = keepalive  # e.g. the torch tensor that owns an adopted device slab
+        self._L = _ffi.lib()
+
+    # ── construction ────────────────────────────────────────────────────────────────────────
+    @classmethod
+    def from_vectors(cls, doc_ids: Optional[Sequence[str]], vectors, *, device: int = 0,
+                     reduce_order="halves_pairwise", tail_fma: bool = False, row_base: int = 0,
+                     tombstones=None) -> "GpuVectorIndex":
+        """InMemoryVectorIndex::from_vectors (in_memory.rs:1667-1730): f32 rows in caller order,
+        encoded to f16 with round-to-nearest-even on the device (simd.rs:2245-2304)."""
+        v = np.ascontiguousarray(vectors, dtype=np.float32)
+        if v.ndim != 2:
+            raise SearchError("InvalidConfig", "vectors must be [n, dim]")
+        if doc_ids is not None and len(doc_ids) != v.shape[0]:
+            raise SearchError("InvalidConfig", "doc_ids and vectors differ in length")
+        if v.size and not np.isfinite(v).all():  # write_record (lib.rs:3647-3653)
+            raise SearchError("InvalidConfig", "all embedding values must be finite")
+        h = C.c_void_p()
+        o = _options(device, reduce_order, tail_fma, False, row_base)
+        bm = _bitmap(tombstones)
+        check(_ffi.lib().fsgpu_index_create_f32(ptr(v), v.shape[0], v.shape[1], ptr(bm), C.byref(o), C.byref(h)))
+        return cls(h.value, doc_ids)
+
+    @classmethod
+    def from_f16_bits(cls, doc_ids: Optional[Sequence[str]], slab_bits, *, device: int = 0,
+                      reduce_order="halves_pairwise", tail_fma: bool = True, row_base: int = 0,
+                      tombstones=None) -> "GpuVectorIndex":
+        """A ready f16 slab (uint16 bit patterns, [n, dim]) — the FSVI vector slab layout
+        (lib.rs:6-43)."""
+        s = np.ascontiguousarray(slab_bits, dtype=np.uint16)
+        if s.ndim != 2:
+            raise SearchError("InvalidConfig", "slab must be [n, dim]")
+        h = C.c_void_p()
+        o = _options(device, reduce_order, tail_fma, False, row_base)
+        bm = _bitmap(tombstones)
+        check(_ffi.lib().fsgpu_index_create_f16(ptr(s), s.shape[0], s.shape[1], ptr(bm), C.byref(o), C.byref(h)))
+        return cls(h.value, doc_ids)
+
+    @classmethod
+    def from_device_tensor(cls, slab, *, doc_ids: Optional[Sequence[str]] = None,
+                           reduce_order="halves_pairwise", tail_fma: bool = True, row_base: int = 0,
+                           tombstones=None) -> "GpuVectorIndex":
+        """Adopt a CUDA tensor [n, dim] of f16 (torch.float16 / int16 / uint16) without copying."""
+        if not slab.is_cuda or slab.dim() != 2 or not slab.is_contiguous() or slab.element_size() != 2:
+            raise SearchError("InvalidConfig", "slab must be a contiguous 2-byte CUDA tensor [n, dim]")
+        h = C.c_void_p()
+        o = _options(slab.device.index or 0, reduce_order, tail_fma, True, row_base)
+        bm = _bitmap(tombstones)
+        check(_ffi.lib().fsgpu_index_create_f16(slab.data_ptr(), slab.shape[0], slab.shape[1], ptr(bm),
+                                                C.byref(o), C.byref(h)))
+        return cls(h.value, doc_ids, keepalive=slab)
+
+    @classmethod
+    def open(cls, path: str, *, device: int = 0, reduce_order="halves_pairwise", row_start: int = 0,
+             n_rows: int = 0) -> "GpuVectorIndex":
+        """VectorIndex::open (lib.rs:819) for an FSVI v1 / f16 file; doc ids come from the file."""
+        h = C.c_void_p()
+        o = _options(device, reduce_order, True, False, row_start)
+        check(_ffi.lib().fsgpu_index_open_fsvi(path.encode(), row_start, n_rows, C.byref(o), C.byref(h)))
+        ix = cls(h.value, None, dedup_doc_ids=True)
+        ix._doc_ids_from_handle = True
+        return ix
+
+    def close(self) -> None:
+        if self._h:
+            self._L.fsgpu_index_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ── accessors ───────────────────────────────────────────────────────────────────────────
+    def record_count(self) -> int:
+        return int(self._L.fsgpu_index_rows(self._h))
+
+    def dimension(self) -> int:
+        return int(self._L.fsgpu_index_dim(self._h))
+
+    def row_base(self) -> int:
+        return int(self._L.fsgpu_index_row_base(self._h))
+
+    def device(self) -> int:
+        return int(self._L.fsgpu_index_device(self._h))
+
+    @property
+    def handle(self) -> C.c_void_p:
+        return self._h
+
+    def doc_id_at(self, row: int) -> Optional[str]:
+        """VectorIndex::doc_id_at (lib.rs:3801-3824) for a GLOBAL row."""
+        if self._doc_ids is not None:
+            return self._doc_ids[row - self.row_base()]
+        p, n = C.c_void_p(), C.c_uint32()
+        rc = self._L.fsgpu_index_doc_id(self._h, row, C.byref(p), C.byref(n))
+        if rc != 0:
+            return None
+        return C.string_at(p, n.value).decode("utf-8")
+
+    def read_rows_f16(self, row_start: int, n: int) -> np.ndarray:
+        """Raw f16 bit patterns of local rows [row_start, row_start+n) (VectorIndex::vector_at_f16)."""
+        out = np.zeros((n, self.dimension()), dtype=np.uint16)
+        check(self._L.fsgpu_index_read_rows_f16(self._h, row_start, n, ptr(out)))
+        return out
+
+    def profile_enable(self, on: bool = True) -> None:
+        check(self._L.fsgpu_index_profile_enable(self._h, 1 if on else 0))
+
+    def profile_read(self, reset: bool = True) -> dict:
+        p = _ffi.Profile()
+        check(self._L.fsgpu_index_profile_read(self._h, C.byref(p), 1 if reset else 0))
+        return dict(scan_launches=int(p.scan_launches), merge_launches=int(p.merge_launches),
+                    other_launches=int(p.other_launches), scan_bytes=int(p.scan_bytes), scan_ms=float(p.scan_ms))
+
+    def set_tombstones(self, flags) -> None:
+        """Soft-delete flags (record flag bit 0, lib.rs:172; honoured by the scan, search.rs:1281)."""
+        bm = _bitmap(flags)
+        check(self._L.fsgpu_index_set_tombstones(self._h, ptr(bm)))
+
+    # ── exact search ────────────────────────────────────────────────────────────────────────
+    def search_top_k_batch(self, queries, limit: int):
+        """`batch` queries in one call.  Returns (rows u32 [B,k], scores f32 [B,k], counts u32 [B])."""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        if q.ndim == 1:
+            q = q[None, :]
+        b, dim = q.shape
+        k = int(limit)
+        hits = np.zeros((b, max(k, 1)), dtype=np.dtype([("row", np.uint32), ("score", np.float32)]))
+        counts = np.zeros(b, dtype=np.uint32)
+        check(self._L.fsgpu_search_top_k(self._h, ptr(q), b, k, dim, ptr(hits), ptr(counts)))
+        return hits["row"][:, :k].copy(), hits["score"][:, :k].copy(), counts
+
+    def search_top_k(self, query, limit: int, filter=None) -> List[VectorHit]:
+        """VectorIndex::search_top_k (search.rs:192-206) / InMemoryVectorIndex::search_top_k
+        (in_memory.rs:2555): best-first hits, `limit == 0` or empty index -> []."""
+        if filter is not None:
+            raise SearchError("InvalidConfig", "SearchFilter is not supported on the device path yet")
+        q = np.ascontiguousarray(query, dtype=np.float32).reshape(-1)
+        rows, scores, counts = self.search_top_k_batch(q[None, :], limit)
+        n = int(counts[0])
+        hits = [VectorHit(int(rows[0, i]), float(scores[0, i]), self.doc_id_at(int(rows[0, i]))) for i in range(n)]
+        if self._dedup:  # resolve_sorted_entries: first (= best) occurrence of a doc id wins (search.rs:1540)
+            seen, out = set(), []
+            for h in hits:
+                if h.doc_id in seen:
+                    continue
+                seen.add(h.doc_id)
+                out.append(h)
+            hits = out
+        return hits
+
+    def search_top_k_device(self, d_queries, limit: int, *, want_hits: bool = True, stream=None):
+        """Device-resident form: `d_queries` is a CUDA float32 tensor [B, dim].  Returns torch
+        tensors (keys int64 [B,k], hits int32-view [B,k,2] or None, counts int32 [B])."""
+        import torch
+
+        if d_queries.dtype != torch.float32 or not d_queries.is_cuda or not d_queries.is_contiguous():
+            raise SearchError("InvalidConfig", "d_queries must be a contiguous CUDA float32 tensor")
+        if d_queries.dim() != 2 or d_queries.shape[1] != self.dimension():
+            raise SearchError("DimensionMismatch", f"expected {self.dimension()}, found {d_queries.shape[-1]}")
+        b, k = d_queries.shape[0], int(limit)
+        dev = d_queries.device
+        keys = torch.zeros((b, max(k, 1)), dtype=torch.int64, device=dev)
+        hits = torch.zeros((b, max(k, 1), 2), dtype=torch.int32, device=dev) if want_hits else None
+        counts = torch.zeros(b, dtype=torch.int32, device=dev)
+        s = torch.cuda.current_stream(dev).cuda_stream if stream is None else stream
+        check(self._L.fsgpu_search_top_k_device(self._h, d_queries.data_ptr(), b, k, keys.data_ptr(),
+                                                hits.data_ptr() if want_hits else None, counts.data_ptr(), s))
+        return keys, hits, counts
+
+    # ── two-tier rescoring ──────────────────────────────────────────────────────────────────
+    def scores_for_rows(self, query, rows):
+        q = np.ascontiguousarray(query, dtype=np.float32).reshape(-1)
+        r = np.ascontiguousarray(rows, dtype=np.uint32)
+        out = np.zeros(r.size, dtype=np.float32)
+        present = np.zeros(r.size, dtype=np.uint8)
+        check(self._L.fsgpu_scores_for_rows(self._h, ptr(q), q.size, ptr(r), r.size, ptr(out), ptr(present)))
+        return out, present.astype(bool)
+
+    def quality_scores_for_hits(self, query, hits: Sequence[VectorHit], alignment=None) -> List[Optional[float]]:
+        """TwoTierIndex::quality_scores_for_hits (two_tier.rs:1566-1631): quality-tier dot at the
+        row aligned with each fast hit.  `alignment[fast_row]` maps to the quality row (None =
+        identical row order, the `Aligned` case of two_tier.rs:404-409); a missing row gives None."""
+        rows = []
+        for h in hits:
+            r = h.index if alignment is None else alignment.get(h.index, 0xFFFFFFFF) \
+                if isinstance(alignment, dict) else int(alignment[h.index])
+            rows.append(0xFFFFFFFF if r is None or r < 0 else r)
+        scores, present = self.scores_for_rows(query, np.asarray(rows, dtype=np.uint32))
+        return [float(s) if p else None for s, p in zip(scores, present)]

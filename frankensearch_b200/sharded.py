@@ -1,0 +1,82 @@
+"""Row-sharded exact search across the GPUs of one box.
+
+One process per GPU (torch.distributed, NCCL over NVLink).  Rank r owns the contiguous global
+rows [r*N/G, (r+1)*N/G); a search is: local fused scan+top-k on every rank -> ONE all-gather of
+the per-rank `batch x k` packed order keys (+ raw scores) -> the same k-way merge kernel on every
+rank.  Because the key order is a strict total order on (score_key, global_row)
+(crates/frankensearch-index/src/search.rs:1669-1686) the merged result is identical to the
+single-index result — this is merge_partial_heaps (search.rs:1704-1720) lifted across devices.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+from . import _ffi
+from ._ffi import SearchError, check
+
+
+def shard_bounds(n_rows: int, world_size: int, rank: int) -> Tuple[int, int]:
+    """Contiguous row range of `rank`: [rank*N/G, (rank+1)*N/G) (integer division as written)."""
+    if world_size <= 0 or not (0 <= rank < world_size):
+        raise SearchError("InvalidConfig", f"rank {rank} outside world of {world_size}")
+    return (rank * n_rows) // world_size, ((rank + 1) * n_rows) // world_size
+
+
+class ShardedGpuIndex:
+    """`local_search(d_queries, k) -> (keys int64 [B,k], scores f32 [B,k])` and
+    `merge(keys [G,B,k], scores [G,B,k], k) -> (keys [B,k], hits, counts)` default to the CUDA
+    kernels; tests inject CPU stand-ins to exercise the plumbing over gloo."""
+
+    def __init__(self, local_index, *, group=None, local_search: Optional[Callable] = None,
+                 merge: Optional[Callable] = None):
+        import torch.distributed as dist
+
+        self._dist = dist
+        self._ix = local_index
+        self._group = group
+        self._world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self._local_search = local_search or self._cuda_local_search
+        self._merge = merge or self._cuda_merge
+
+    # CUDA stages -----------------------------------------------------------------------------
+    def _cuda_local_search(self, d_queries, k: int):
+        import torch
+
+        keys, hits, _counts = self._ix.search_top_k_device(d_queries, k, want_hits=True)
+        scores = hits[..., 1].contiguous().view(torch.float32)
+        return keys, scores
+
+    def _cuda_merge(self, keys, scores, k: int):
+        import torch
+
+        g, b, k_in = keys.shape
+        dev = keys.device
+        out_keys = torch.zeros((b, k), dtype=torch.int64, device=dev)
+        out_hits = torch.zeros((b, k, 2), dtype=torch.int32, device=dev)
+        counts = torch.zeros(b, dtype=torch.int32, device=dev)
+        s = torch.cuda.current_stream(dev).cuda_stream
+        check(_ffi.lib().fsgpu_merge_top_k_device(dev.index or 0, keys.data_ptr(), scores.data_ptr(), b, g, k_in,
+                                                  b * k_in, k_in, k, out_keys.data_ptr(), out_hits.data_ptr(),
+                                                  counts.data_ptr(), s))
+        return out_keys, out_hits, counts
+
+    # the sharded search ------------------------------------------------------------------------
+    def search_top_k_device(self, d_queries, k: int):
+        """Every rank passes the same queries; every rank returns the same merged result."""
+        import torch
+
+        keys, scores = self._local_search(d_queries, k)
+        if self._world == 1:
+            return self._merge(keys.unsqueeze(0), scores.unsqueeze(0), k)
+        g = self._world
+        all_keys = torch.empty((g,) + tuple(keys.shape), dtype=keys.dtype, device=keys.device)
+        all_scores = torch.empty((g,) + tuple(scores.shape), dtype=scores.dtype, device=scores.device)
+        # one collective: keys and scores travel in a single packed buffer
+        packed = torch.cat([keys.reshape(-1).view(torch.int32), scores.reshape(-1).view(torch.int32)])
+        flat = torch.empty(g * packed.numel(), dtype=torch.int32, device=packed.device)
+        self._dist.all_gather_into_tensor(flat, packed, group=self._group)
+        gathered = flat.view(g, packed.numel())
+        nk = keys.numel() * 2
+        all_keys.copy_(gathered[:, :nk].contiguous().view(torch.int64).view(all_keys.shape))
+        all_scores.copy_(gathered[:, nk:].contiguous().view(torch.float32).view(all_scores.shape))
+        return self._merge(all_keys, all_scores, k)

@@ -1,0 +1,261 @@
+/*
+ * fsgpu.h — C ABI of the B200 (sm_100a) semantic-tier hot path for frankensearch.
+ *
+ * The reference (a Rust workspace) has no FFI for this path; its seams are inherent methods and
+ * free functions.  Each entry point below names the reference interface it
+ * replaces (paths relative to the reference checkout).  INTEGRATION.md shows the Rust
+ * `extern "C"` binding a maintainer would add.
+ *
+ * Conventions
+ *   - return 0 (FSGPU_OK) on success, otherwise an fsgpu_status that maps 1:1 onto a
+ *     `SearchError` variant (crates/frankensearch-core/src/error.rs:12-247); the message is
+ *     available from fsgpu_last_error() (thread-local).
+ *   - plain pointers and sizes only; the caller owns every input and output buffer.
+ *   - "host" entry points take host pointers and copy; "_device" entry points take device
+ *     pointers on the index's GPU and enqueue on `stream` (a cudaStream_t passed as void*;
+ *     NULL = the index's own stream, in which case the call synchronises before returning).
+ *   - every entry point is thread-safe; calls on one index are serialised internally.
+ *   - there is no CPU fallback: without a usable CUDA device every call fails with
+ *     FSGPU_ERR_SUBSYSTEM.
+ *   - rows are GLOBAL row numbers: `row_base + local row`, so per-shard results from a
+ *     row-sharded corpus merge into exactly the single-index answer.
+ */
+#ifndef FSGPU_H
+#define FSGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FSGPU_ABI_VERSION 1
+
+typedef enum fsgpu_status {
+    FSGPU_OK = 0,
+    FSGPU_ERR_DIMENSION_MISMATCH = 1, /* SearchError::DimensionMismatch  error.rs:82  */
+    FSGPU_ERR_INVALID_CONFIG = 2,     /* SearchError::InvalidConfig      error.rs:169 */
+    FSGPU_ERR_INDEX_CORRUPTED = 3,    /* SearchError::IndexCorrupted     error.rs:60  */
+    FSGPU_ERR_EMBEDDING_FAILED = 4,   /* SearchError::EmbeddingFailed    error.rs:30  */
+    FSGPU_ERR_CANCELLED = 5,          /* SearchError::Cancelled          error.rs:210 */
+    FSGPU_ERR_SUBSYSTEM = 6,          /* SearchError::SubsystemError{subsystem:"gpu"} error.rs:235 */
+    FSGPU_ERR_IO = 7                  /* SearchError::Io */
+} fsgpu_status;
+
+/* Lane order of the final 8-lane horizontal add of the reference dot kernel
+ * (`wide::f32x8::reduce_add`, crates/frankensearch-index/src/simd.rs:439).  wide 1.6.1 is not
+ * vendored in the reference checkout, so the order is a switch (SURVEY.md §7 "hard parts"). */
+typedef enum fsgpu_reduce_order {
+    FSGPU_REDUCE_HALVES_PAIRWISE = 0,   /* ((v0+v1)+(v2+v3)) + ((v4+v5)+(v6+v7))  default */
+    FSGPU_REDUCE_AVX_TREE = 1,          /* ((v0+v4)+(v2+v6)) + ((v1+v5)+(v3+v7)) */
+    FSGPU_REDUCE_HALVES_SEQUENTIAL = 2, /* (((v0+v1)+v2)+v3) + (((v4+v5)+v6)+v7) */
+    FSGPU_REDUCE_HALVES_STRIDE2 = 3,    /* ((v0+v2)+(v1+v3)) + ((v4+v6)+(v5+v7)) */
+    FSGPU_REDUCE_SEQUENTIAL = 4         /* ((((((v0+v1)+v2)+v3)+v4)+v5)+v6)+v7 */
+} fsgpu_reduce_order;
+
+typedef struct fsgpu_index fsgpu_index; /* opaque: one f16 slab shard resident on one GPU */
+
+/* VectorHit without the doc-id string (crates/frankensearch-core/src/types.rs:88-95):
+ * `row` is VectorHit.index, `score` the raw f32 dot (NaN preserved).  The host resolves
+ * doc ids for the winners only, as the reference does (search.rs:1549-1553). */
+typedef struct fsgpu_hit {
+    uint32_t row;
+    float score;
+} fsgpu_hit;
+
+typedef struct fsgpu_index_options {
+    int32_t device;        /* CUDA device ordinal */
+    int32_t reduce_order;  /* fsgpu_reduce_order */
+    int32_t tail_fma;      /* 1: FSVI/bytes kernel tail (`mul_add`, simd.rs:440-444);
+                              0: in-memory slice kernel tail (`+= a*b`, simd.rs:298-300).
+                              Only matters when dim % 8 != 0. */
+    int32_t slab_is_device;/* 1: `slab` is already a device pointer on `device`; it is used in
+                              place (no copy) and must outlive the index */
+    uint64_t row_base;     /* global row number of local row 0 (row-sharded corpora) */
+} fsgpu_index_options;
+
+/* ---- library ------------------------------------------------------------------------------ */
+int fsgpu_abi_version(void);
+const char* fsgpu_last_error(void);          /* thread-local, never NULL */
+int fsgpu_device_count(int* out_count);
+void fsgpu_index_options_default(fsgpu_index_options* opts);
+
+/* ---- index lifetime ----------------------------------------------------------------------- */
+/* Replaces InMemoryVectorIndex::from_vectors (crates/frankensearch-index/src/in_memory.rs:1667)
+ * and the mmap'd slab of VectorIndex::open (crates/frankensearch-index/src/lib.rs:819):
+ * `slab` is n_rows x dim little-endian IEEE f16, row-major, caller order.  `tombstones` is an
+ * optional packed bitmap (bit r%8 of byte r/8 set = record flag 0x0001, lib.rs:172) of the
+ * rows to skip (search.rs:1281). */
+int fsgpu_index_create_f16(const uint16_t* slab, uint64_t n_rows, uint32_t dim,
+                           const uint8_t* tombstones, const fsgpu_index_options* opts,
+                           fsgpu_index** out);
+/* Same from f32 rows, encoded on the device with round-to-nearest-even exactly like
+ * encode_f32_to_f16_extend (crates/frankensearch-index/src/simd.rs:2245-2304). */
+int fsgpu_index_create_f32(const float* rows, uint64_t n_rows, uint32_t dim,
+                           const uint8_t* tombstones, const fsgpu_index_options* opts,
+                           fsgpu_index** out);
+/* Opens a reference-written FSVI v1 file (layout: crates/frankensearch-index/src/lib.rs:6-43;
+ * header CRC lib.rs:6114; f16 or f32 quantisation) and uploads rows [row_start, row_start+n)
+ * (n_rows_or_0 == 0: to the end).  Tombstone flags and the doc-id string table are kept on the
+ * host side of the handle (fsgpu_index_doc_id). */
+int fsgpu_index_open_fsvi(const char* path, uint64_t row_start, uint64_t n_rows_or_0,
+                          const fsgpu_index_options* opts, fsgpu_index** out);
+void fsgpu_index_destroy(fsgpu_index* index);
+
+uint64_t fsgpu_index_rows(const fsgpu_index* index);      /* VectorIndex::record_count */
+uint32_t fsgpu_index_dim(const fsgpu_index* index);       /* VectorIndex::dimension    */
+uint64_t fsgpu_index_row_base(const fsgpu_index* index);
+int fsgpu_index_device(const fsgpu_index* index);
+const void* fsgpu_index_device_slab(const fsgpu_index* index);
+/* Optional host-side doc-id table (concatenated UTF-8 + offsets[n_rows+1]); FSVI-opened
+ * indexes have one already.  Replaces VectorIndex::doc_id_at (lib.rs:3801-3824). */
+int fsgpu_index_set_doc_ids(fsgpu_index* index, const uint8_t* bytes, const uint64_t* offsets);
+int fsgpu_index_doc_id(const fsgpu_index* index, uint64_t global_row, const uint8_t** out_ptr,
+                       uint32_t* out_len);
+/* Replaces VectorIndex::vector_at_f16 (crates/frankensearch-index/src/lib.rs, raw slab rows):
+ * copies local rows [row_start, row_start + n) back to the host as f16 bit patterns. */
+int fsgpu_index_read_rows_f16(const fsgpu_index* index, uint64_t row_start, uint64_t n,
+                              uint16_t* out_bits);
+/* Replaces VectorIndex::soft_delete's effect on the scan (flag bit 0, search.rs:1281). */
+int fsgpu_index_set_tombstones(fsgpu_index* index, const uint8_t* bitmap_or_null);
+
+/* ---- measurement ---------------------------------------------------------------------------- */
+/* Launch accounting for bench.py: counts every kernel this index launches and, while enabled,
+ * brackets each fused scan launch with CUDA events on its stream.  `scan_bytes` is the
+ * algorithmic traffic (n_rows * dim * 2 per scan launch). */
+typedef struct fsgpu_profile {
+    uint64_t scan_launches;
+    uint64_t merge_launches;
+    uint64_t other_launches;
+    uint64_t scan_bytes;
+    double scan_ms;        /* sum of event-timed scan launch durations (0 unless enabled) */
+} fsgpu_profile;
+int fsgpu_index_profile_enable(fsgpu_index* index, int on);
+int fsgpu_index_profile_read(fsgpu_index* index, fsgpu_profile* out, int reset);
+
+/* ---- exact scan + top-k -------------------------------------------------------------------- */
+/* Replaces VectorIndex::search_top_k / InMemoryVectorIndex::search_top_k
+ * (crates/frankensearch-index/src/search.rs:192-206, :426-494;
+ *  crates/frankensearch-index/src/in_memory.rs:2555, :2651-2710) for `batch` queries at once.
+ *   queries  [batch, dim] f32 row-major            dim != index dim -> DIMENSION_MISMATCH
+ *   out      [batch, k] hits, best first           out_counts[b] = hits written (min(k, live rows))
+ * Ordering is the reference's strict total order (search.rs:1655-1686): score_key (NaN -> -inf)
+ * by f32::total_cmp descending, ties -> lower row first.  Scores are bit-identical to the
+ * reference's dot kernel (simd.rs:398-446) for the configured reduce order.
+ * k == 0 or an empty index -> all counts 0 (search.rs:438-440). */
+int fsgpu_search_top_k(const fsgpu_index* index, const float* queries, uint32_t batch, uint32_t k,
+                       uint32_t dim, fsgpu_hit* out, uint32_t* out_counts);
+
+/* Device-resident form: d_queries [batch, dim] f32, d_out_keys [batch, k] packed 64-bit order
+ * keys (larger = better; 0 = empty slot), d_out_hits [batch, k] (nullable), d_out_counts
+ * [batch] (nullable).  Key layout: high 32 bits = ascending total-order image of score_key,
+ * low 32 bits = ~global_row. */
+int fsgpu_search_top_k_device(const fsgpu_index* index, const float* d_queries, uint32_t batch,
+                              uint32_t k, uint64_t* d_out_keys, fsgpu_hit* d_out_hits,
+                              uint32_t* d_out_counts, void* stream);
+
+/* Replaces merge_partial_heaps (search.rs:1704-1720) across shards: d_keys holds, per query,
+ * `n_lists` lists of `k_in` keys ([batch, n_lists, k_in], 0 = empty; e.g. an all-gather of
+ * per-rank results laid out rank-major is passed with `list_stride` = batch*k_in and
+ * `query_stride` = k_in); d_scores (nullable, same layout) are the raw scores that travel with
+ * the keys.  Writes the best k_out per query. */
+int fsgpu_merge_top_k_device(int device, const uint64_t* d_keys, const float* d_scores,
+                             uint32_t batch, uint32_t n_lists, uint32_t k_in, uint64_t list_stride,
+                             uint64_t query_stride, uint32_t k_out, uint64_t* d_out_keys,
+                             fsgpu_hit* d_out_hits, uint32_t* d_out_counts, void* stream);
+
+/* Replaces TwoTierIndex::quality_scores_for_hits -> VectorIndex::dot_query_at
+ * (crates/frankensearch-index/src/two_tier.rs:1566-1631, :1946-1973; lib.rs:3229-3239):
+ * out_scores[i] = dot(row rows[i], query); rows outside this shard (or UINT32_MAX) give
+ * out_present[i] = 0 (`None`). */
+int fsgpu_scores_for_rows(const fsgpu_index* index, const float* query, uint32_t dim,
+                          const uint32_t* rows, uint32_t n, float* out_scores,
+                          uint8_t* out_present);
+int fsgpu_scores_for_rows_device(const fsgpu_index* index, const float* d_queries, uint32_t batch,
+                                 const uint32_t* d_rows, uint32_t n_per_query, float* d_out_scores,
+                                 uint8_t* d_out_present, void* stream);
+
+/* ---- fusion -------------------------------------------------------------------------------- */
+typedef struct fsgpu_rrf_config { /* RrfConfig, crates/frankensearch-fusion/src/rrf.rs:25-48 */
+    double k;               /* non-finite or < 0 -> 60 (rrf.rs:124-130) */
+    double lexical_weight;  /* non-finite or <= 0 -> 1 (rrf.rs:92-98)   */
+    double semantic_weight;
+    int32_t tiebreak;       /* 0 LexicalThenId, 1 Hash (rrf.rs:52-65) */
+    int32_t reserved;
+} fsgpu_rrf_config;
+
+typedef struct fsgpu_fused_hit { /* FusedHit, crates/frankensearch-core/src/types.rs:3892-3925 */
+    double rrf_score;
+    int32_t semantic_rank;  /* position in the semantic list, -1 = None */
+    int32_t lexical_rank;   /* first position in the lexical list, -1 = None */
+    uint32_t semantic_row;  /* semantic_index, UINT32_MAX = None */
+    float semantic_score;
+    float lexical_score;
+    uint32_t in_both_sources;
+} fsgpu_fused_hit;
+
+/* Replaces rrf_fuse / fuse_by_strategy_for_vector_lane(Rrf) -> rrf_fuse_merge_inner
+ * (crates/frankensearch-fusion/src/rrf.rs:282-320, :970-1004, :1038-1210; comparator :179-198).
+ * Identity is an opaque 64-bit id per document: the host passes the vector row for documents
+ * that have one and any other unique value (>= 2^32) for lexical-only documents — the same
+ * doc-id -> row lookup the reference index already offers (lib.rs:3317).  `*_tie` are the
+ * level-4 tie-break ranks (smaller first; for LexicalThenId the byte-wise rank of the doc id,
+ * for Hash the rank of (fnv1a(doc_id), doc_id)); NULL = use the id itself.
+ * One fused list per query; all arrays are [batch, n_*] row-major on the host. */
+int fsgpu_rrf_fuse(int device, const fsgpu_rrf_config* config, uint32_t batch,
+                   const uint64_t* lex_ids, const float* lex_scores, const uint32_t* lex_tie,
+                   const uint32_t* lex_counts, uint32_t n_lex_max,
+                   const uint32_t* sem_rows, const float* sem_scores, const uint32_t* sem_tie,
+                   const uint32_t* sem_counts, uint32_t n_sem_max,
+                   uint32_t limit, uint32_t offset, fsgpu_fused_hit* out /*[batch, limit]*/,
+                   uint32_t* out_counts);
+int fsgpu_rrf_fuse_device(int device, const fsgpu_rrf_config* config, uint32_t batch,
+                          const uint64_t* d_lex_ids, const float* d_lex_scores,
+                          const uint32_t* d_lex_tie, const uint32_t* d_lex_counts,
+                          uint32_t n_lex_max, const fsgpu_hit* d_sem_hits, const uint32_t* d_sem_tie,
+                          const uint32_t* d_sem_counts, uint32_t n_sem_max, uint32_t limit,
+                          uint32_t offset, fsgpu_fused_hit* d_out, uint32_t* d_out_counts,
+                          void* stream);
+
+/* Replaces blend_two_tier / blend_two_tier_aligned(_unique)
+ * (crates/frankensearch-fusion/src/blend.rs:107-191, :213-286, :296-338).
+ * aligned form: quality_scores[i] / quality_present[i] belong to fast hit i.
+ * union form (quality_rows != NULL): a separately retrieved quality list, joined by row.
+ * `*_tie`: doc-id byte-order ranks for the final tie-break (NULL = row order).
+ * out [n_fast + n_quality] hits (row = VectorHit.index kept from the fast list when present). */
+int fsgpu_blend_two_tier(int device, float blend_factor,
+                         const uint32_t* fast_rows, const float* fast_scores,
+                         const uint32_t* fast_tie, uint32_t n_fast,
+                         const uint32_t* quality_rows, const float* quality_scores,
+                         const uint8_t* quality_present, const uint32_t* quality_tie,
+                         uint32_t n_quality, fsgpu_hit* out, uint32_t* out_count);
+
+/* ---- query encoders ------------------------------------------------------------------------ */
+typedef struct fsgpu_potion fsgpu_potion;
+/* Replaces Model2VecEmbedder (crates/frankensearch-embed/src/model2vec_embedder.rs:67):
+ * `table` is the [vocab, dim] f32 static embedding matrix (model.safetensors "embeddings"). */
+int fsgpu_potion_create(const float* table, uint64_t vocab, uint32_t dim, int device,
+                        fsgpu_potion** out);
+void fsgpu_potion_destroy(fsgpu_potion* enc);
+/* Replaces Model2VecEmbedder::embed_token_ids + finish_mean_pool_and_normalize
+ * (model2vec_embedder.rs:312-335, :435-451; embed/src/simd.rs:74-116): token ids of query b are
+ * ids[offsets[b] .. offsets[b+1]); tokenisation stays on the host.  out [batch, dim]. */
+int fsgpu_potion_embed(const fsgpu_potion* enc, const uint32_t* ids, const uint64_t* offsets,
+                       uint32_t batch, float* out);
+int fsgpu_potion_embed_device(const fsgpu_potion* enc, const uint32_t* d_ids,
+                              const uint64_t* d_offsets, uint32_t batch, float* d_out,
+                              void* stream);
+
+/* ---- synthetic corpora (bench / test utility) ---------------------------------------------- */
+/* The reference's bench generators on the device
+ * (crates/frankensearch-index/benches/fsvi_int8_two_pass.rs:199-231), bit-identical to the
+ * oracle's fso_synth_rows: kind 0 uniform, 1 clustered.  Writes n_rows x dim f16 at d_out. */
+int fsgpu_synth_rows_device(int device, int kind, uint64_t seed_base, uint64_t row_start,
+                            uint64_t n_rows, uint32_t dim, uint32_t n_centroids, float noise,
+                            uint16_t* d_out_f16, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FSGPU_H */

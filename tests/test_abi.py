@@ -1,0 +1,62 @@
+"""CPU: the C-ABI library loads and exports every symbol include/fsgpu.h declares; entry points
+fail loudly (SubsystemError) without a GPU — there is no CPU fallback."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "fsgpu.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(fsgpu_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported():
+    from frankensearch_b200 import _ffi
+
+    L = _ffi.lib()
+    syms = declared_symbols()
+    assert len(syms) >= 25
+    for s in syms:
+        assert hasattr(L, s), f"{s} declared in include/fsgpu.h but not exported by libfsgpu.so"
+    assert sorted(_ffi.EXPORTS) == syms, "frankensearch_b200/_ffi.py EXPORTS is out of date"
+    assert L.fsgpu_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    from frankensearch_b200 import _ffi
+
+    assert C.sizeof(_ffi.Hit) == 8
+    assert C.sizeof(_ffi.FusedHitC) == 32
+    assert C.sizeof(_ffi.IndexOptions) == 24
+    assert C.sizeof(_ffi.RrfConfigC) == 32
+
+
+def test_no_cpu_fallback_without_gpu(cuda_ok):
+    if cuda_ok:
+        pytest.skip("a GPU is present; the loud-failure path is exercised on the CPU box")
+    import frankensearch_b200 as fs
+
+    with pytest.raises(fs.SearchError) as e:
+        fs.GpuVectorIndex.from_vectors(["a"], np.ones((1, 8), dtype=np.float32))
+    assert e.value.kind == "SubsystemError"
+    with pytest.raises(fs.SearchError):
+        fs.rrf_fuse([fs.ScoredResult("a", 1.0)], [], 10)
+    with pytest.raises(fs.SearchError):
+        fs.Model2VecEmbedder(np.ones((4, 8), dtype=np.float32))
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under frankensearch_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "frankensearch_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "fs_oracle" not in text and "np_oracle" not in text and "libfs_oracle" not in text, f
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f

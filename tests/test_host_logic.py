@@ -1,0 +1,129 @@
+"""CPU: host-side logic of the product package (no kernels): FSVI writer layout, shard bounds,
+id/tie-rank bookkeeping, the sharded search plumbing over gloo (world_size 2)."""
+import os
+import struct
+import sys
+import zlib
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from frankensearch_b200 import fusion, sharded
+from frankensearch_b200.fsvi import write_fsvi_v1
+from frankensearch_b200.types import candidate_count, fnv1a_hash
+from oracle import np_oracle as no
+
+
+def test_candidate_count():
+    """rrf.rs:2652 candidate_count_multiplier_one and the default multiplier 3 (config.rs:174)."""
+    assert candidate_count(10, 5, 1) == 15
+    assert candidate_count(0, 10, 1) == 10
+    assert candidate_count(10, 0, 3) == 30
+
+
+def test_fsvi_writer_layout(tmp_path):
+    """lib.rs:6-43 layout; rows sorted by (fnv1a(doc_id), doc_id) (lib.rs:3758-3762)."""
+    rng = np.random.default_rng(1)
+    ids = [f"doc-{i:06}" for i in range(50)]
+    vec = rng.standard_normal((50, 16)).astype(np.float32)
+    p = str(tmp_path / "x.fsvi")
+    perm = write_fsvi_v1(p, "bench-16", 16, ids, vec, tombstones=[i == 3 for i in range(50)])
+    data = open(p, "rb").read()
+    assert data[:4] == b"FSVI" and struct.unpack_from("<H", data, 4)[0] == 1
+    cur = 6
+    n = struct.unpack_from("<H", data, cur)[0]; cur += 2 + n
+    n = struct.unpack_from("<H", data, cur)[0]; cur += 2 + n
+    dim, quant = struct.unpack_from("<IB", data, cur); cur += 8
+    count, voff = struct.unpack_from("<QQ", data, cur); cur += 16
+    assert (dim, quant, count) == (16, 1, 50) and voff % 64 == 0
+    assert struct.unpack_from("<I", data, cur)[0] == zlib.crc32(data[:cur]) & 0xFFFFFFFF
+    cur += 4
+    recs = [struct.unpack_from("<QIHH", data, cur + 16 * i) for i in range(50)]
+    hashes = [r[0] for r in recs]
+    assert hashes == sorted(hashes)
+    strings = data[cur + 800:]
+    for row, (h, off, ln, flags) in enumerate(recs):
+        doc = strings[off:off + ln].decode()
+        assert doc == ids[perm[row]] and h == fnv1a_hash(doc.encode())
+        assert flags == (1 if perm[row] == 3 else 0)
+    slab = np.frombuffer(data, dtype=np.uint16, count=50 * 16, offset=voff).reshape(50, 16)
+    assert np.array_equal(slab, no.encode_f16(vec[perm]))
+
+
+def test_shard_bounds_cover_and_are_contiguous():
+    for n in (0, 1, 7, 1000, 10_000_001):
+        for g in (1, 2, 3, 8):
+            spans = [sharded.shard_bounds(n, g, r) for r in range(g)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(g - 1))
+
+
+def test_tie_ranks_follow_reference_orders():
+    ids = fusion._dense_ids(["b", "a", "b", "ä", "B"])
+    assert ids == {"b": 0, "a": 1, "ä": 2, "B": 3}
+    tie = fusion._tie_ranks(ids, "LexicalThenId")
+    assert sorted(tie, key=tie.get) == ["B", "a", "b", "ä"]  # byte order, like Rust str::cmp
+    tie_h = fusion._tie_ranks(ids, "Hash")
+    assert sorted(tie_h, key=tie_h.get) == sorted(ids, key=lambda d: (fnv1a_hash(d.encode()), d.encode()))
+
+
+# ── sharded search plumbing over gloo, world_size 2 ──────────────────────────────────────────
+def _np_local_search(slab_bits, base):
+    def run(queries, k):
+        keys = np.zeros((queries.shape[0], k), dtype=np.uint64)
+        scores = np.zeros((queries.shape[0], k), dtype=np.float32)
+        for b in range(queries.shape[0]):
+            s = no.dot_rows(slab_bits, queries[b].numpy(), 0)
+            rows, sc = no.top_k(s, k)
+            kk = no.order_keys(sc, rows + np.uint64(base))
+            # product keys are "larger is better": complement of the ascending sort key
+            keys[b, :len(kk)] = ~kk
+            scores[b, :len(kk)] = sc
+        return torch.from_numpy(keys.view(np.int64)), torch.from_numpy(scores)
+    return run
+
+
+def _np_merge(keys, scores, k):
+    g, b, k_in = keys.shape
+    out = np.zeros((b, k), dtype=np.uint64)
+    u = keys.numpy().view(np.uint64)
+    for q in range(b):
+        allk = np.sort(u[:, q, :].reshape(-1))[::-1]
+        allk = allk[allk != 0][:k]
+        out[q, :len(allk)] = allk
+    return torch.from_numpy(out.view(np.int64)), None, None
+
+
+def _worker(rank, world, port, slab, queries, k, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lo, hi = sharded.shard_bounds(slab.shape[0], world, rank)
+        ix = sharded.ShardedGpuIndex(None, local_search=_np_local_search(slab[lo:hi], lo), merge=_np_merge)
+        keys, _, _ = ix.search_top_k_device(torch.from_numpy(queries), k)
+        ret[rank] = keys.numpy().view(np.uint64).copy()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_search_equals_single_index_over_gloo():
+    """per-shard top-k + one all-gather + merge == the unsharded answer."""
+    from oracle import fs_oracle as fo
+
+    slab, _ = fo.synth_rows(1, 1, 0, 4001, 128)
+    slab[1000] = slab[3000]  # an exact cross-shard tie: lower global row must win
+    queries = np.stack([fo.clustered_query(q, 128) for q in range(3)])
+    k = 25
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29500 + os.getpid() % 2000
+    mp.spawn(_worker, args=(2, port, slab, queries, k, ret), nprocs=2, join=True)
+    assert np.array_equal(ret[0], ret[1])
+    for b in range(3):
+        rows, scores = fo.search_top_k(slab, queries[b], k)
+        want = ~no.order_keys(scores, rows)
+        assert np.array_equal(ret[0][b], want)
