@@ -57,14 +57,15 @@ struct ScanSmem {
     uint32_t* cnt;   // [QB]
 };
 __host__ __device__ inline size_t scan_smem_bytes(int qb, uint32_t cap, uint32_t dim) {
-    return (size_t)qb * cap * 8 + (size_t)qb * 8 + (size_t)qb * dim * 4 + (size_t)qb * 4 + 16;
+    const size_t tau_slots = ((size_t)qb + 1) & ~(size_t)1;  // keeps q[] 16-byte aligned (float4 loads)
+    return (size_t)qb * cap * 8 + tau_slots * 8 + (size_t)qb * dim * 4 + (size_t)qb * 4 + 16;
 }
 __device__ __forceinline__ ScanSmem carve_scan_smem(unsigned char* base, int qb, uint32_t cap,
                                                     uint32_t dim) {
     ScanSmem s;
     s.cand = reinterpret_cast<uint64_t*>(base);
     s.tau = s.cand + (size_t)qb * cap;
-    s.q = reinterpret_cast<float*>(s.tau + qb);
+    s.q = reinterpret_cast<float*>(s.tau + ((qb + 1) & ~1));
     s.cnt = reinterpret_cast<uint32_t*>(s.q + (size_t)qb * dim);
     return s;
 }
