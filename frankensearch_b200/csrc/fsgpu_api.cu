@@ -185,7 +185,7 @@ struct ScanPlan {
 static int make_plan(const fsgpu_index* ix, uint32_t k, int qb_want, ScanPlan* plan) {
     ScanPlan p;
     p.cap = cand_capacity(k);
-    int r = env_int("FSGPU_SCAN_R", 1);
+    int r = env_int("FSGPU_SCAN_R", 2);
     if (r != 1 && r != 2) r = 1;
     if (qb_want == 8) r = 1;
     p.kernel = pick_fast(ix->dim, qb_want, r);
@@ -292,6 +292,7 @@ static int search_device_locked(const fsgpu_index* ix, const float* d_queries, u
         a.sync_every = plan.sync_every;
         a.reduce_order = ix->reduce_order;
         a.tail_fma = ix->tail_fma;
+        a.allow_packed = env_int("FSGPU_SCAN_PACKED", 1);
         a.partial = ix->ws_partial.as<uint64_t>();
         a.error_flag = ix->d_error;
         std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};

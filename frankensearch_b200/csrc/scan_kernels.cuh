@@ -28,6 +28,7 @@ struct ScanArgs {
     uint32_t sync_every;       // tiles between compaction checks
     int reduce_order;
     int tail_fma;
+    int allow_packed;          // 0 forces the scalar mul.rn/add.rn path (A/B switch)
     uint64_t* partial;         // [gridDim.x, QB, k] keys, 0-padded
     uint32_t* error_flag;      // set to 1 on a capacity contract violation
 };
@@ -112,28 +113,124 @@ __device__ __forceinline__ void scan_write_partials(const ScanSmem& sm, const Sc
 }
 
 // ─── fast path: dim = 32*NJ, QB queries per pass, R row-groups per thread ───────────────────
-// Thread mapping (per warp): lane = 8a + r handles accumulator `a` (chunks 4j+a) of row r of
+// Thread mapping (per warp): lane = 4r + a handles accumulator `a` (chunks 4j+a) of row r of
 // the warp's 8-row group: eight chains (a, l=0..7) per query live in registers, 16-byte loads
-// cover a row with 4 lanes x NJ loads (each warp-level load = 8 rows x 64 contiguous bytes,
-// whole sectors).  The reference tree `(s0+s1)+(s2+s3)` is two xor-shuffles (8, 16); every lane
-// then holds V[0..7] and applies the configured 8-lane order.  Products and sums are separate
+// cover a row with 4 ADJACENT lanes x NJ loads (each warp-level load = 8 rows x 64 contiguous
+// bytes; a quarter-warp touches 2 half-lines = 2 L1 wavefronts.  The first version used
+// lane = 8a + r: 32 wavefronts per load and l1tex at 97 % — profiles/r01_scan_l1tex.md).
+// The reference tree `(s0+s1)+(s2+s3)` is two xor-shuffles (1, 2); every lane then holds
+// V[0..7] and applies the configured 8-lane order.  Products and sums are separate
 // IEEE roundings (mul.rn / add.rn), so scores are bit-identical to simd.rs:398-446.
-template <int NJ, int QB, int R>
-__global__ void __launch_bounds__(kScanThreads)
-scan_topk_fast_kernel(const ScanArgs args) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const uint32_t dim = NJ * 32;
-    const ScanSmem sm = carve_scan_smem(smem_raw, QB, args.cap, dim);
+// Packed-pair arithmetic (sm_100 f32x2 pipe): one issue slot multiplies / adds two chains.
+// ptxas contracts `mul.rn.f32x2` + `add.rn.f32x2` into FFMA2 (a fused rounding the reference
+// does not have), but it cannot fuse across differing FTZ modes, so the add carries `.ftz`.
+// That is bit-identical to the IEEE add as long as no operand or result is subnormal, which
+// the kernel guarantees by only taking this path when every non-zero |q_i| >= 2^-76: f16
+// values are integer multiples of 2^-24, so every product and every partial sum is an integer
+// multiple of 2^-123 — never a non-zero value below 2^-126.  Other queries use the scalar path.
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t mul2_rn(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t add2_rn_ftz(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
 
-    for (uint32_t i = threadIdx.x; i < QB * dim; i += blockDim.x) sm.q[i] = args.queries[i];
-    if (threadIdx.x < QB) {
-        sm.cnt[threadIdx.x] = 0u;
-        sm.tau[threadIdx.x] = 0ull;
+// Scores of R row-groups x QB queries for one warp iteration; v[rr][qi][0..7] on every lane.
+template <int NJ, int QB, int R, bool PACKED>
+__device__ __forceinline__ void scan_rows(const uint4 (&x)[R][NJ], const float* __restrict__ q_s,
+                                          int a, float (&v)[R][QB][8]) {
+    constexpr uint32_t dim = NJ * 32;
+    if constexpr (PACKED) {
+        uint64_t acc[R][QB][4];
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr)
+#pragma unroll
+            for (int qi = 0; qi < QB; ++qi)
+#pragma unroll
+                for (int m = 0; m < 4; ++m) acc[rr][qi][m] = 0ull;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            uint64_t xp[R][4];
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) {
+                float xf[8];
+                unpack8(x[rr][j], xf);
+#pragma unroll
+                for (int m = 0; m < 4; ++m) xp[rr][m] = pack2(xf[2 * m], xf[2 * m + 1]);
+            }
+#pragma unroll
+            for (int qi = 0; qi < QB; ++qi) {
+                const ulonglong2* qp = reinterpret_cast<const ulonglong2*>(q_s + qi * dim + (4 * j + a) * 8);
+                const ulonglong2 q0 = qp[0], q1 = qp[1];
+                const uint64_t qv[4] = {q0.x, q0.y, q1.x, q1.y};
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr)
+#pragma unroll
+                    for (int m = 0; m < 4; ++m)
+                        acc[rr][qi][m] = add2_rn_ftz(acc[rr][qi][m], mul2_rn(xp[rr][m], qv[m]));
+            }
+        }
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr)
+#pragma unroll
+            for (int qi = 0; qi < QB; ++qi)
+#pragma unroll
+                for (int m = 0; m < 4; ++m) unpack2(acc[rr][qi][m], v[rr][qi][2 * m], v[rr][qi][2 * m + 1]);
+    } else {
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr)
+#pragma unroll
+            for (int qi = 0; qi < QB; ++qi)
+#pragma unroll
+                for (int l = 0; l < 8; ++l) v[rr][qi][l] = 0.0f;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            float xf[R][8];
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) unpack8(x[rr][j], xf[rr]);
+#pragma unroll
+            for (int qi = 0; qi < QB; ++qi) {
+                const float4* qp = reinterpret_cast<const float4*>(q_s + qi * dim + (4 * j + a) * 8);
+                const float4 q0 = qp[0], q1 = qp[1];
+                const float qv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr)
+#pragma unroll
+                    for (int l = 0; l < 8; ++l)
+                        v[rr][qi][l] = add_rn(v[rr][qi][l], mul_rn(xf[rr][l], qv[l]));
+            }
+        }
     }
-    __syncthreads();
+    // reference tree (s0+s1)+(s2+s3) across the four lanes of a row
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr)
+#pragma unroll
+        for (int qi = 0; qi < QB; ++qi)
+#pragma unroll
+            for (int l = 0; l < 8; ++l) {
+                float s = v[rr][qi][l];
+                s = add_rn(s, __shfl_xor_sync(0xffffffffu, s, 1));  // s0+s1 | s2+s3
+                s = add_rn(s, __shfl_xor_sync(0xffffffffu, s, 2));  // (s0+s1)+(s2+s3)
+                v[rr][qi][l] = s;
+            }
+}
 
+template <int NJ, int QB, int R, bool PACKED>
+__device__ __forceinline__ void scan_loop(const ScanArgs& args, const ScanSmem& sm) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int a = lane >> 3, r = lane & 7;
+    const int a = lane & 3, r = lane >> 2;
     constexpr int kRowsPerWarp = 8 * R;
     constexpr int kTileRows = kScanWarps * kRowsPerWarp;
     const uint64_t n = args.n_rows;
@@ -157,45 +254,14 @@ scan_topk_fast_kernel(const ScanArgs args) {
 #pragma unroll
             for (int j = 0; j < NJ; ++j) x[rr][j] = ld_stream_16(p + 4 * j);
         }
-        float acc[R][QB][8];
-#pragma unroll
-        for (int rr = 0; rr < R; ++rr)
-#pragma unroll
-            for (int qi = 0; qi < QB; ++qi)
-#pragma unroll
-                for (int l = 0; l < 8; ++l) acc[rr][qi][l] = 0.0f;
-
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-            float xf[R][8];
-#pragma unroll
-            for (int rr = 0; rr < R; ++rr) unpack8(x[rr][j], xf[rr]);
-#pragma unroll
-            for (int qi = 0; qi < QB; ++qi) {
-                const float4* qp = reinterpret_cast<const float4*>(sm.q + qi * dim + (4 * j + a) * 8);
-                const float4 q0 = qp[0], q1 = qp[1];
-                const float qv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-#pragma unroll
-                for (int rr = 0; rr < R; ++rr)
-#pragma unroll
-                    for (int l = 0; l < 8; ++l)
-                        acc[rr][qi][l] = add_rn(acc[rr][qi][l], mul_rn(xf[rr][l], qv[l]));
-            }
-        }
+        float v[R][QB][8];
+        scan_rows<NJ, QB, R, PACKED>(x, sm.q, a, v);
 #pragma unroll
         for (int rr = 0; rr < R; ++rr) {
             const uint64_t row = row0 + rr * 8;
 #pragma unroll
             for (int qi = 0; qi < QB; ++qi) {
-                float v[8];
-#pragma unroll
-                for (int l = 0; l < 8; ++l) {
-                    float s = acc[rr][qi][l];
-                    s = add_rn(s, __shfl_xor_sync(0xffffffffu, s, 8));
-                    s = add_rn(s, __shfl_xor_sync(0xffffffffu, s, 16));
-                    v[l] = s;
-                }
-                const float score = reduce8(v, args.reduce_order);
+                const float score = reduce8(v[rr][qi], args.reduce_order);
                 if (!(score < thr[qi])) {  // rare once tau is established; NaN passes
                     if ((qi & 3) == a && row < n) scan_offer<QB>(sm, args, qi, score, row);
                 }
@@ -205,6 +271,31 @@ scan_topk_fast_kernel(const ScanArgs args) {
             scan_sync_point<QB>(sm, args.cap, args.k, trigger, false, thr);
     }
     scan_sync_point<QB>(sm, args.cap, args.k, trigger, true, thr);
+}
+
+template <int NJ, int QB, int R>
+__global__ void __launch_bounds__(kScanThreads)
+scan_topk_fast_kernel(const ScanArgs args) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t dim = NJ * 32;
+    const ScanSmem sm = carve_scan_smem(smem_raw, QB, args.cap, dim);
+
+    bool q_ok = true;  // packed-path precondition: every non-zero |q_i| >= 2^-76
+    for (uint32_t i = threadIdx.x; i < QB * dim; i += blockDim.x) {
+        const float qv = args.queries[i];
+        sm.q[i] = qv;
+        const uint32_t mag = __float_as_uint(qv) & 0x7FFFFFFFu;
+        q_ok = q_ok && (mag == 0u || mag >= 0x19800000u);
+    }
+    if (threadIdx.x < QB) {
+        sm.cnt[threadIdx.x] = 0u;
+        sm.tau[threadIdx.x] = 0ull;
+    }
+    const bool packed = __syncthreads_and(q_ok ? 1 : 0) != 0 && args.allow_packed != 0;
+    if (packed)
+        scan_loop<NJ, QB, R, true>(args, sm);
+    else
+        scan_loop<NJ, QB, R, false>(args, sm);
     scan_write_partials<QB>(sm, args);
 }
 

@@ -187,6 +187,25 @@ def test_scan_parity_special_values(gpu, cpu, fo):
         assert_same_hits(got, want, f"k={k}")
 
 
+def test_packed_path_precondition_and_scalar_fallback(gpu, cpu, fo):
+    """The f32x2 (FMUL2 + FADD2.FTZ) inner loop is only taken when every non-zero |q_i| >= 2^-76
+    (no subnormal can then arise, so FTZ is a no-op); tiny-component and subnormal queries take
+    the scalar mul.rn/add.rn loop.  Both must match the oracle bit for bit."""
+    slab, _ = fo.synth_rows(0, 5, 0, 4000, 384)
+    slab[7, :] = 0x0001          # smallest f16 subnormal everywhere
+    slab[9, :] = 0x8001
+    base = fo.normalize(fo.raw_vector(0x51, 384))
+    for scale, tweak in ((1.0, None), (1.0, 1e-25), (1.0, 1e-39), (1e-30, None), (1e-38, None), (1.0, 2.0 ** -76)):
+        q = (base * np.float32(scale)).astype(np.float32)
+        if tweak is not None:
+            q[::5] = np.float32(tweak)
+            q[1::7] = -np.float32(tweak)
+        for k in (10, 64):
+            want = cpu.search_bits(slab, q, k)
+            got = gpu.search_bits(slab, q, k)
+            assert_same_hits(got, want, f"scale={scale} tweak={tweak} k={k}")
+
+
 def test_batched_queries_match_single_queries(gpu, cpu, fo):
     """Batch sizes that exercise every QB grouping (8/4/2/1 remainders)."""
     import frankensearch_b200 as fs

@@ -26,10 +26,11 @@ def main():
     q = torch.randn((64, dim), device=dev)
     q = (q / q.norm(dim=1, keepdim=True)).contiguous()
     print(f"# rows={rows} dim={dim} k={k} bytes/pass={rows * dim * 2 / 1e9:.3f} GB")
-    print("qb r ctas/sm  ms/launch  GB/s   queries/s")
-    for qb, r, ctas in itertools.product((1, 2, 4, 8), (1, 2), (0, 1, 2, 3, 4)):
+    print("packed qb r ctas/sm  ms/launch  GB/s   queries/s")
+    for packed, qb, r, ctas in itertools.product((1, 0), (1, 2, 4, 8), (1, 2), (0, 2)):
         if qb == 8 and r == 2:
             continue
+        os.environ["FSGPU_SCAN_PACKED"] = str(packed)
         os.environ["FSGPU_SCAN_QB"] = str(qb)
         os.environ["FSGPU_SCAN_R"] = str(r)
         os.environ["FSGPU_SCAN_CTAS_PER_SM"] = str(ctas)
@@ -49,7 +50,7 @@ def main():
             continue
         ms = p["scan_ms"] / max(p["scan_launches"], 1)
         gbs = rows * dim * 2 / (ms * 1e-3) / 1e9
-        print(f"{qb:2d} {r} {ctas:7d}  {ms:9.4f}  {gbs:6.0f}  {qb / (ms * 1e-3):9.0f}", flush=True)
+        print(f"{packed} {qb:2d} {r} {ctas:7d}  {ms:9.4f}  {gbs:6.0f}  {qb / (ms * 1e-3):9.0f}", flush=True)
     ix.close()
 
 
