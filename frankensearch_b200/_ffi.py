@@ -62,7 +62,8 @@ class IndexOptions(C.Structure):
 
 class Profile(C.Structure):
     _fields_ = [("scan_launches", C.c_uint64), ("merge_launches", C.c_uint64), ("other_launches", C.c_uint64),
-                ("scan_bytes", C.c_uint64), ("scan_ms", C.c_double)]
+                ("scan_bytes", C.c_uint64), ("scan_ms", C.c_double), ("mma_launches", C.c_uint64),
+                ("mma_flops", C.c_double), ("redo_queries", C.c_uint64)]
 
 
 class RrfConfigC(C.Structure):

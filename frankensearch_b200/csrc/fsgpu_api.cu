@@ -17,6 +17,7 @@
 #include "fsgpu.h"
 #include "fsgpu_common.cuh"
 #include "fusion_kernels.cuh"
+#include "mma_scan_kernels.cuh"
 #include "scan_kernels.cuh"
 #include "synth_kernels.cuh"
 
@@ -117,6 +118,15 @@ struct fsgpu_index {
     mutable DevBuf ws_partial, ws_queries, ws_keys, ws_hits, ws_counts, ws_sort_a, ws_sort_b,
         ws_cub, ws_rows, ws_scores, ws_present;
     uint32_t* d_error = nullptr;
+    // batched tensor-core path (mma_scan_kernels.cuh): slab statistics for the error bound, the
+    // slab's TMA descriptor, workspaces
+    bool mma_ok = false;            // dim % 64 == 0, dim <= 512, every element finite, TMA usable
+    float max_row_norm = 0.0f;      // upper bound on ||row||_2 over the slab
+    CUtensorMap tm_slab;
+    mutable CUtensorMap tm_qhat;
+    mutable const void* tm_qhat_ptr = nullptr;
+    mutable uint32_t tm_qhat_rows = 0;
+    mutable DevBuf ws_qhat, ws_margin, ws_redo, ws_cand, ws_cand_count;
     // launch accounting (guarded by mu)
     mutable bool profiling = false;
     mutable fsgpu_profile prof{};
@@ -224,10 +234,11 @@ static int launch_merge(const MergeArgs& m, uint32_t batch, cudaStream_t stream)
     return FSGPU_OK;
 }
 
-// Exact top-k for `batch` device-resident queries; outputs may be NULL.  Caller holds ix->mu.
-static int search_device_locked(const fsgpu_index* ix, const float* d_queries, uint32_t batch,
-                                uint32_t k, uint64_t* d_out_keys, fsgpu_hit* d_out_hits,
-                                uint32_t* d_out_counts, cudaStream_t stream) {
+// Exact top-k for `batch` device-resident queries on the CUDA-core kernels; outputs may be NULL.
+// Caller holds ix->mu.
+static int search_exact_locked(const fsgpu_index* ix, const float* d_queries, uint32_t batch,
+                               uint32_t k, uint64_t* d_out_keys, fsgpu_hit* d_out_hits,
+                               uint32_t* d_out_counts, cudaStream_t stream) {
     if (batch == 0) return FSGPU_OK;
     if (k == 0 || ix->n_rows == 0) {  // search.rs:438-440
         if (d_out_counts) CUDA_TRY(cudaMemsetAsync(d_out_counts, 0, (size_t)batch * 4, stream));
@@ -342,6 +353,213 @@ static int search_device_locked(const fsgpu_index* ix, const float* d_queries, u
     return FSGPU_OK;
 }
 
+// ─── batched tensor-core path ───────────────────────────────────────────────────────────────
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// TMA descriptor of a row-major [rows, dim] f16 matrix read as [128 rows x 64 elements] boxes with
+// the 128-byte swizzle the UMMA shared-memory descriptors expect.
+static bool make_f16_tile_map(CUtensorMap* tm, const void* base, uint64_t rows, uint32_t dim, bool stream_once) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc || rows == 0) return false;
+    const cuuint64_t gdim[2] = {dim, rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)dim * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)kMmaKBlock, (cuuint32_t)kMmaN};
+    const cuuint32_t estr[2] = {1, 1};
+    (void)stream_once;
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// Slab statistics + TMA descriptor; decides whether the batched tensor-core path may serve this
+// index (otherwise every batch runs on the exact CUDA-core kernels).
+static int index_finish_setup(fsgpu_index* ix) {
+    ix->mma_ok = false;
+    if (ix->n_rows == 0 || ix->dim % kMmaKBlock != 0 || ix->dim > kMmaMaxDim ||
+        ix->n_rows > 0x7FFFFF00ull || (reinterpret_cast<uintptr_t>(ix->d_slab) & 15u) != 0)
+        return FSGPU_OK;
+    uint32_t* d_stats = nullptr;
+    CUDA_TRY(cudaMalloc(&d_stats, 8));
+    CUDA_TRY(cudaMemsetAsync(d_stats, 0, 8, ix->stream));
+    const int grid = (int)std::min<uint64_t>((ix->n_rows + 7) / 8, (uint64_t)ix->num_sms * 16);
+    slab_stats_kernel<<<grid, 256, 0, ix->stream>>>(ix->d_slab, ix->n_rows, ix->dim, d_stats);
+    uint32_t stats[2] = {0, 0};
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(stats, d_stats, 8, cudaMemcpyDeviceToHost, ix->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ix->stream);
+    cudaFree(d_stats);
+    if (e != cudaSuccess) return fail(FSGPU_ERR_SUBSYSTEM, "gpu: slab statistics failed: %s", cudaGetErrorString(e));
+    float norm;
+    memcpy(&norm, &stats[0], 4);
+    ix->max_row_norm = norm * 1.0001f;
+    const bool finite = stats[1] == 0 && std::isfinite(ix->max_row_norm);
+    ix->mma_ok = finite && make_f16_tile_map(&ix->tm_slab, ix->d_slab, ix->n_rows, ix->dim, true);
+    return FSGPU_OK;
+}
+
+static uint32_t mma_list_capacity(uint32_t k) { return std::max(256u, host_next_pow2(2 * k + 192)); }
+
+static int search_exact_locked(const fsgpu_index* ix, const float* d_queries, uint32_t batch, uint32_t k,
+                               uint64_t* d_out_keys, fsgpu_hit* d_out_hits, uint32_t* d_out_counts,
+                               cudaStream_t stream);
+
+// Up to num_sms*128 queries in ONE pass over the slab: prep -> tcgen05 scan -> exact refine.
+// Synchronises `stream` once (to learn which queries, if any, must be redone exactly).
+static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint32_t batch, uint32_t k,
+                             uint64_t* d_out_keys, fsgpu_hit* d_out_hits, uint32_t* d_out_counts,
+                             cudaStream_t stream) {
+    const uint32_t n_kb = ix->dim / kMmaKBlock;
+    const uint32_t cap = mma_list_capacity(k);
+    const size_t smem_limit = 227 * 1024;
+    const size_t fixed = mma_scan_smem_bytes(n_kb, 0, cap);
+    if (fixed + 2 * (size_t)kMmaTileBytes > smem_limit)
+        return fail(FSGPU_ERR_INVALID_CONFIG, "batched scan does not fit in shared memory (dim=%u k=%u)", ix->dim, k);
+    uint32_t n_stages = (uint32_t)std::min<size_t>(kMmaMaxStages, (smem_limit - fixed) / kMmaTileBytes);
+    const int stage_cap = env_int("FSGPU_MMA_STAGES", 0);
+    if (stage_cap >= 2) n_stages = std::min<uint32_t>(n_stages, (uint32_t)stage_cap);
+    const size_t smem = mma_scan_smem_bytes(n_kb, n_stages, cap);
+    CUDA_TRY(cudaFuncSetAttribute(mma_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint32_t buf_cap = cand_capacity(k);
+    const size_t refine_smem = (size_t)buf_cap * 8 + 16;
+    CUDA_TRY(cudaFuncSetAttribute(mma_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)refine_smem));
+
+    const uint32_t max_queries = (uint32_t)ix->num_sms * kMmaM;
+    std::vector<uint32_t> redo_host;
+    for (uint32_t done = 0; done < batch; done += max_queries) {
+        const uint32_t sub = std::min(max_queries, batch - done);
+        const uint32_t n_qb = (sub + kMmaM - 1) / kMmaM;
+        const uint32_t g = (uint32_t)ix->num_sms / n_qb;
+        const uint32_t grid = g * n_qb;
+        const uint32_t slots = n_qb * kMmaM;
+        CUDA_TRY(ix->ws_qhat.reserve((size_t)slots * ix->dim * 2));
+        CUDA_TRY(ix->ws_margin.reserve((size_t)slots * 4));
+        CUDA_TRY(ix->ws_redo.reserve((size_t)slots * 4));
+        CUDA_TRY(ix->ws_cand.reserve((size_t)grid * kMmaM * cap * 8));
+        CUDA_TRY(ix->ws_cand_count.reserve((size_t)grid * kMmaM * 4));
+        if (ix->tm_qhat_ptr != ix->ws_qhat.p || ix->tm_qhat_rows != slots) {
+            if (!make_f16_tile_map(&ix->tm_qhat, ix->ws_qhat.p, slots, ix->dim, false))
+                return fail(FSGPU_ERR_SUBSYSTEM, "gpu: cuTensorMapEncodeTiled failed for the query tile");
+            ix->tm_qhat_ptr = ix->ws_qhat.p;
+            ix->tm_qhat_rows = slots;
+        }
+        const float* q = d_queries + (size_t)done * ix->dim;
+        mma_prep_queries_kernel<<<slots, 128, 0, stream>>>(q, sub, ix->dim, ix->max_row_norm, ix->ws_qhat.as<__half>(),
+                                                           ix->ws_margin.as<float>(), ix->ws_redo.as<uint32_t>());
+        CUDA_TRY(cudaGetLastError());
+
+        MmaScanArgs a{};
+        a.n_rows = ix->n_rows;
+        a.row_base = ix->row_base;
+        a.tombstones = ix->d_tomb;
+        a.n_kblocks = n_kb;
+        a.n_qblocks = n_qb;
+        a.ctas_per_qblock = g;
+        a.batch = sub;
+        a.k = k;
+        a.cap = cap;
+        a.n_stages = n_stages;
+        a.margin2 = ix->ws_margin.as<float>();
+        a.cand = ix->ws_cand.as<uint64_t>();
+        a.cand_count = ix->ws_cand_count.as<uint32_t>();
+        a.redo = ix->ws_redo.as<uint32_t>();
+        std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+        if (ix->profiling) {
+            if (!ix->ev_free.empty()) {
+                ev = ix->ev_free.back();
+                ix->ev_free.pop_back();
+            } else {
+                CUDA_TRY(cudaEventCreate(&ev.first));
+                CUDA_TRY(cudaEventCreate(&ev.second));
+            }
+            CUDA_TRY(cudaEventRecord(ev.first, stream));
+        }
+        mma_scan_kernel<<<grid, kMmaThreads, smem, stream>>>(ix->tm_qhat, ix->tm_slab, a);
+        CUDA_TRY(cudaGetLastError());
+        if (ix->profiling) {
+            CUDA_TRY(cudaEventRecord(ev.second, stream));
+            ix->ev_pending.push_back(ev);
+        }
+        ix->prof.scan_launches += 1;
+        ix->prof.scan_bytes += ix->n_rows * ix->dim * 2ull;
+        ix->prof.mma_launches += 1;
+        ix->prof.mma_flops += 2.0 * (double)slots * (double)ix->n_rows * (double)ix->dim;
+        ix->prof.other_launches += 1;  // prep
+        ix->prof.merge_launches += 1;  // refine
+
+        MmaRefineArgs r{};
+        r.cand = a.cand;
+        r.cand_count = a.cand_count;
+        r.margin2 = a.margin2;
+        r.redo = a.redo;
+        r.n_qblocks = n_qb;
+        r.ctas_per_qblock = g;
+        r.cap = cap;
+        r.k = k;
+        r.buf_cap = buf_cap;
+        r.slab = ix->d_slab;
+        r.queries = q;
+        r.n_rows = ix->n_rows;
+        r.row_base = ix->row_base;
+        r.dim = ix->dim;
+        r.reduce_order = ix->reduce_order;
+        r.tail_fma = ix->tail_fma;
+        r.out_keys = d_out_keys ? d_out_keys + (size_t)done * k : nullptr;
+        r.out_hits = d_out_hits ? d_out_hits + (size_t)done * k : nullptr;
+        r.out_counts = d_out_counts ? d_out_counts + done : nullptr;
+        r.error_flag = ix->d_error;
+        mma_refine_kernel<<<sub, 256, refine_smem, stream>>>(r);
+        CUDA_TRY(cudaGetLastError());
+
+        redo_host.resize(sub);
+        uint32_t err_flag = 0;
+        CUDA_TRY(cudaMemcpyAsync(redo_host.data(), ix->ws_redo.p, (size_t)sub * 4, cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaMemcpyAsync(&err_flag, ix->d_error, 4, cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        if (err_flag) return fail(FSGPU_ERR_SUBSYSTEM, "gpu: top-k candidate buffer contract violated (refine)");
+        for (uint32_t b = 0; b < sub; ++b) {
+            if (!redo_host[b]) continue;
+            ix->prof.redo_queries += 1;
+            const size_t o = (size_t)done + b;
+            int rc = search_exact_locked(ix, d_queries + o * ix->dim, 1, k, d_out_keys ? d_out_keys + o * k : nullptr,
+                                         d_out_hits ? d_out_hits + o * k : nullptr,
+                                         d_out_counts ? d_out_counts + o : nullptr, stream);
+            if (rc) return rc;
+        }
+    }
+    return FSGPU_OK;
+}
+
+// Exact top-k for `batch` device-resident queries; outputs may be NULL.  Caller holds ix->mu.
+// Small batches stream the slab once per <= 4 queries on the CUDA cores (HBM-bound); batches of
+// FSGPU_MMA_MIN_BATCH (default 8) or more take the tensor-core pass.  Both give identical results.
+static int search_device_locked(const fsgpu_index* ix, const float* d_queries, uint32_t batch, uint32_t k,
+                                uint64_t* d_out_keys, fsgpu_hit* d_out_hits, uint32_t* d_out_counts,
+                                cudaStream_t stream) {
+    if (batch == 0) return FSGPU_OK;
+    const int min_batch = env_int("FSGPU_MMA_MIN_BATCH", 8);
+    const bool mma = ix->mma_ok && min_batch > 0 && batch >= (uint32_t)min_batch && k >= 1 && k <= kMmaMaxK &&
+                     ix->n_rows > 0;
+    if (mma) {
+        CUDA_TRY(cudaMemsetAsync(ix->d_error, 0, 4, stream));
+        return search_mma_locked(ix, d_queries, batch, k, d_out_keys, d_out_hits, d_out_counts, stream);
+    }
+    return search_exact_locked(ix, d_queries, batch, k, d_out_keys, d_out_hits, d_out_counts, stream);
+}
+
 static int check_error_flag(const fsgpu_index* ix, cudaStream_t stream) {
     uint32_t flag = 0;
     CUDA_TRY(cudaMemcpyAsync(&flag, ix->d_error, 4, cudaMemcpyDeviceToHost, stream));
@@ -409,7 +627,8 @@ extern "C" void fsgpu_index_destroy(fsgpu_index* ix) {
             }
         for (DevBuf* b : {&ix->ws_partial, &ix->ws_queries, &ix->ws_keys, &ix->ws_hits, &ix->ws_counts,
                           &ix->ws_sort_a, &ix->ws_sort_b, &ix->ws_cub, &ix->ws_rows, &ix->ws_scores,
-                          &ix->ws_present})
+                          &ix->ws_present, &ix->ws_qhat, &ix->ws_margin, &ix->ws_redo, &ix->ws_cand,
+                          &ix->ws_cand_count})
             b->release();
         if (ix->stream) cudaStreamDestroy(ix->stream);
     }
@@ -447,6 +666,7 @@ extern "C" int fsgpu_index_create_f16(const uint16_t* slab, uint64_t n_rows, uin
         return fail(FSGPU_ERR_SUBSYSTEM, "gpu: slab upload failed: %s", cudaGetErrorString(e));
     }
     rc = upload_tombstones(ix, tombstones);
+    if (!rc) rc = index_finish_setup(ix);
     if (rc) { fsgpu_index_destroy(ix); return rc; }
     *out = ix;
     return FSGPU_OK;
@@ -487,6 +707,7 @@ extern "C" int fsgpu_index_create_f32(const float* rows, uint64_t n_rows, uint32
         }
     }
     rc = upload_tombstones(ix, tombstones);
+    if (!rc) rc = index_finish_setup(ix);
     if (rc) { fsgpu_index_destroy(ix); return rc; }
     *out = ix;
     return FSGPU_OK;

@@ -1,0 +1,598 @@
+// mma_scan_kernels.cuh — the batched (>= 8 queries) form of the exact f16 scan + top-k.
+//
+// A batch of B queries against the slab is a dense contraction [B, D] x [D, N] (SURVEY.md §0
+// F5): on CUDA cores it is compute-bound at ~4 queries per corpus pass.  This path runs the
+// contraction on the 5th-gen tensor cores and keeps the result EXACT by construction:
+//
+//   1. prep:    q_hat = f16(q) (what the tensor core can take), and a rigorous per-query bound
+//               e_q >= |mma_score(row) - reference_score(row)| for every row of the index
+//               (Cauchy-Schwarz on the rounding residual + accumulation slack, see prep kernel).
+//   2. scan:    persistent warp-specialised kernel.  One CTA owns 128 queries (UMMA M = 128,
+//               resident in shared memory) and streams 128-row slab tiles (UMMA N = 128) through
+//               a TMA -> mbarrier -> tcgen05.mma -> TMEM pipeline.  TMEM lane = query, column =
+//               corpus row, so each epilogue thread owns one query: it keeps that query's gate
+//               in a register, and appends every row whose approximate score clears
+//               `tau_approx - 2 e_q` to the query's candidate list.  Any row of the exact top-k
+//               satisfies that inequality (proof in DESIGN.md "Batched scan"), so the lists are a
+//               superset of the exact answer.
+//   3. refine:  one CTA per query re-scores the (few) surviving candidates with the reference's
+//               exact accumulation tree (warp_exact_dot, simd.rs:398-446) and selects the top-k
+//               with the reference's total order (search.rs:1655-1686).
+//
+// The slab is read from HBM once per launch for up to 148*128 queries; the other query blocks
+// hit the same tiles in L2.  Queries the bound cannot cover (non-finite / f16-overflowing
+// components, or a tie band wider than the candidate list) are flagged and re-run by the caller
+// on the exact CUDA-core kernel (scan_kernels.cuh) — still on the GPU.
+#pragma once
+
+#include <cuda.h>
+
+#include "fsgpu_common.cuh"
+
+namespace fsgpu {
+
+constexpr int kMmaThreads = 192;    // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
+constexpr int kMmaM = 128;          // queries per CTA (UMMA M, cta_group::1)
+constexpr int kMmaN = 128;          // corpus rows per tile (UMMA N)
+constexpr int kMmaKBlock = 64;      // f16 elements per 128-byte swizzle row
+constexpr int kMmaTileBytes = kMmaN * kMmaKBlock * 2;  // 16 KiB: one [128 x 64] f16 K-block
+constexpr int kMmaAccStages = 4;    // 4 x 128 TMEM columns = the whole 512-column TMEM
+constexpr int kMmaMaxStages = 8;
+constexpr uint32_t kMmaMaxK = 256;  // larger k goes to the exact path
+constexpr uint32_t kMmaMaxDim = 512;
+
+struct MmaScanArgs {
+    uint64_t n_rows, row_base;
+    const uint8_t* tombstones;
+    uint32_t n_kblocks;        // dim / 64
+    uint32_t n_qblocks;        // ceil(batch / 128)
+    uint32_t ctas_per_qblock;  // gridDim.x = n_qblocks * ctas_per_qblock
+    uint32_t batch;
+    uint32_t k;
+    uint32_t cap;              // per-(CTA, query) candidate capacity, power of two >= k + 256
+    uint32_t n_stages;         // B ring depth
+    const float* margin2;      // [n_qblocks*128]  2*e_q, rounded up
+    uint64_t* cand;            // [gridDim.x][128][cap] approximate order keys
+    uint32_t* cand_count;      // [gridDim.x][128]
+    uint32_t* redo;            // [n_qblocks*128] != 0: query must be re-run on the exact path
+};
+
+// ─── PTX wrappers ───────────────────────────────────────────────────────────────────────────
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.b32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait (~4 s of SM clocks): a pipeline bug must trap, not hang the device.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 1023u) == 0u && clock64() - t0 > 8000000000ll) __trap();
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
+}
+// 2-D tiled TMA load: box lands at `dst` (shared), completion bytes are posted on `bar`.
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int32_t c0,
+                                            int32_t c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, f16 inputs, f32 accumulate, issued by ONE thread.
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Arrives on `bar` when every tcgen05.mma issued so far by this thread has completed.
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+                 : "memory");
+}
+// 32 consecutive accumulator columns of this thread's TMEM lane.
+__device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]),
+          "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]),
+          "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor of a K-major [rows x 64] f16 tile stored with the 128-byte
+// swizzle TMA produces (rows 128 B apart, 8-row groups 1024 B apart): start address >> 4,
+// leading byte offset unused, stride byte offset 1024 >> 4, descriptor version 1 (sm_100),
+// layout type 2 = SWIZZLE_128B.  Advancing 16 elements along K adds 32 bytes to the start.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// Instruction descriptor: D = f32 (bits 4-5 = 1), A = B = f16 (0), both K-major, N >> 3 at bit
+// 17, M >> 4 at bit 24.
+__device__ __forceinline__ constexpr uint32_t umma_idesc_f16(uint32_t m, uint32_t n) {
+    return (1u << 4) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+
+// ─── prep: q -> q_hat (f16), error bound, safety flags ──────────────────────────────────────
+// One CTA per (padded) query slot.  For slot b < batch:
+//   q_hat_i = f16_rn(q_i);  r = ||q - q_hat||_2;  nq = ||q||_2   (accumulated in f64)
+//   e = max_row_norm * ( r + (D*2^-22 + (D/32+8)*2^-23) * (nq + r) ) * 1.01
+// where, for every row x of the index (||x|| <= max_row_norm, all finite):
+//   |sum x_i (q_i - q_hat_i)|            <= ||x|| r                      (Cauchy-Schwarz)
+//   |tensor-core f32 accumulation error| <= D * 2^-22 * sum|x_i q_hat_i| (one truncation per add,
+//                                           2x slack) <= D*2^-22 ||x|| (nq + r)
+//   |reference rounding error|           <= (D/32+8) * 2^-23 * sum|x_i q_i|  (mul + D/32 chain adds
+//                                           + 5 tree adds, round-to-nearest, 2x slack)
+// margin2 = 2e rounded up.  Queries with a non-finite component or |q_i| > 65504 cannot be
+// represented: they get q_hat = 0 and redo = 1.  Padding slots get redo = 0, q_hat = 0.
+__global__ void __launch_bounds__(128)
+mma_prep_queries_kernel(const float* __restrict__ queries, uint32_t batch, uint32_t dim, float max_row_norm,
+                        __half* __restrict__ q_hat, float* __restrict__ margin2, uint32_t* __restrict__ redo) {
+    const uint32_t b = blockIdx.x;
+    __shared__ double s_r2[4], s_n2[4];
+    __shared__ int s_bad;
+    if (threadIdx.x == 0) s_bad = 0;
+    __syncthreads();
+    double r2 = 0.0, n2 = 0.0;
+    bool bad = false;
+    if (b < batch) {
+        for (uint32_t i = threadIdx.x; i < dim; i += blockDim.x) {
+            const float q = queries[(size_t)b * dim + i];
+            if (!(fabsf(q) <= 65504.0f)) bad = true;  // NaN, inf or f16 overflow
+            const __half h = __float2half_rn(q);
+            const double d = (double)q - (double)__half2float(h);
+            r2 += d * d;
+            n2 += (double)q * (double)q;
+        }
+    }
+    if (bad) atomicOr(&s_bad, 1);
+    for (int o = 16; o > 0; o >>= 1) {
+        r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+        n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        s_r2[threadIdx.x >> 5] = r2;
+        s_n2[threadIdx.x >> 5] = n2;
+    }
+    __syncthreads();
+    const bool is_bad = s_bad != 0;
+    for (uint32_t i = threadIdx.x; i < dim; i += blockDim.x) {
+        float q = 0.0f;
+        if (b < batch && !is_bad) q = queries[(size_t)b * dim + i];
+        q_hat[(size_t)b * dim + i] = __float2half_rn(q);
+    }
+    if (threadIdx.x == 0) {
+        const double r = sqrt(s_r2[0] + s_r2[1] + s_r2[2] + s_r2[3]);
+        const double nq = sqrt(s_n2[0] + s_n2[1] + s_n2[2] + s_n2[3]);
+        const double d = (double)dim;
+        const double slack = d * (1.0 / 4194304.0) + (d / 32.0 + 8.0) * (1.0 / 8388608.0);
+        const double e = (double)max_row_norm * (r + slack * (nq + r)) * 1.01;
+        float m2 = __double2float_ru(2.0 * e);
+        if (!(m2 >= 0.0f) || is_bad) m2 = 0.0f;
+        margin2[b] = m2;
+        redo[b] = (b < batch && is_bad) ? 1u : 0u;
+    }
+}
+
+// ─── index statistics for the bound: max row norm, all-finite flag ──────────────────────────
+// stats[0] = bits of max ||row||_2 (f32, rounded up generously by the caller), stats[1] = 1 if
+// any element is inf/NaN.
+__global__ void __launch_bounds__(256)
+slab_stats_kernel(const uint16_t* __restrict__ slab, uint64_t n_rows, uint32_t dim, uint32_t* __restrict__ stats) {
+    const int lane = threadIdx.x & 31;
+    float local_max = 0.0f;
+    bool nonfinite = false;
+    for (uint64_t row = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5); row < n_rows; row += (uint64_t)gridDim.x * 8) {
+        const uint16_t* p = slab + row * dim;
+        float acc = 0.0f;
+        for (uint32_t i = lane; i < dim; i += 32) {
+            const uint16_t bits = p[i];
+            if ((bits & 0x7C00u) == 0x7C00u) nonfinite = true;
+            const float x = h2f(bits);
+            acc = __fmaf_ru(x, x, acc);
+        }
+        for (int o = 16; o > 0; o >>= 1) acc = __fadd_ru(acc, __shfl_xor_sync(0xffffffffu, acc, o));
+        local_max = fmaxf(local_max, acc);
+    }
+    if (__any_sync(0xffffffffu, nonfinite) && lane == 0) atomicOr(stats + 1, 1u);
+    if (lane == 0 && local_max > 0.0f && local_max == local_max)
+        atomicMax(stats, __float_as_uint(__fsqrt_ru(local_max)));  // non-negative floats order as uints
+}
+
+// ─── warp-cooperative bitonic sort (descending) of n = 2^m keys in shared memory ────────────
+__device__ __forceinline__ void warp_sort_desc(uint64_t* keys, uint32_t n, uint32_t lane) {
+    for (uint32_t k = 2; k <= n; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = lane; i < n; i += 32) {
+                const uint32_t ixj = i ^ j;
+                if (ixj > i) {
+                    const uint64_t a = keys[i], b = keys[ixj];
+                    const bool desc = (i & k) == 0;
+                    if (desc ? (a < b) : (a > b)) {
+                        keys[i] = b;
+                        keys[ixj] = a;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// Compacts the candidate list of the query owned by lane `owner` of this warp: sort, find
+// tau = k-th best approximate score, keep every entry with score >= tau - margin2 (the band that
+// may still hold exact top-k rows).  Returns (kept count, new gate) to every lane; kept ==
+// 0xFFFFFFFF means the band does not fit and the query must be redone on the exact path.
+__device__ __forceinline__ void warp_compact_list(uint64_t* list, uint32_t count, uint32_t cap, uint32_t k,
+                                                  float margin2, uint64_t* scratch, uint32_t lane,
+                                                  uint32_t* out_kept, float* out_gate) {
+    for (uint32_t i = lane; i < cap; i += 32) scratch[i] = i < count ? list[i] : 0ull;
+    __syncwarp();
+    warp_sort_desc(scratch, cap, lane);
+    float gate = -INFINITY;
+    if (count >= k) gate = __fsub_rd(key_score(scratch[k - 1]), margin2);
+    uint32_t kept = 0;
+    for (uint32_t i = lane; i < count; i += 32) kept += key_score(scratch[i]) >= gate ? 1u : 0u;
+    for (int o = 16; o > 0; o >>= 1) kept += __shfl_xor_sync(0xffffffffu, kept, o);
+    if (kept + kMmaN > cap) {
+        *out_kept = 0xFFFFFFFFu;
+        *out_gate = INFINITY;
+    } else {
+        for (uint32_t i = lane; i < kept; i += 32) list[i] = scratch[i];
+        *out_kept = kept;
+        *out_gate = gate;
+    }
+    __syncwarp();
+}
+
+// ─── the scan ───────────────────────────────────────────────────────────────────────────────
+// Shared memory (1024-byte aligned): A[n_kblocks][16 KiB] | B[n_stages][16 KiB] |
+// scratch[4 epilogue warps][cap] u64 | barriers.
+__host__ __device__ inline size_t mma_scan_smem_bytes(uint32_t n_kblocks, uint32_t n_stages, uint32_t cap) {
+    return 1024 + (size_t)(n_kblocks + n_stages) * kMmaTileBytes + 4 * (size_t)cap * 8 + 256;
+}
+
+__global__ void __launch_bounds__(kMmaThreads, 1)
+mma_scan_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_x,
+                const MmaScanArgs args) {
+    extern __shared__ uint8_t smem_dyn[];
+    const uint32_t raw = smem_u32(smem_dyn);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_dyn + (base - raw);
+    const uint32_t a_smem = base;
+    const uint32_t b_smem = a_smem + args.n_kblocks * kMmaTileBytes;
+    uint64_t* scratch_all = reinterpret_cast<uint64_t*>(base_ptr + (size_t)(args.n_kblocks + args.n_stages) * kMmaTileBytes);
+    uint64_t* bars = scratch_all + 4 * (size_t)args.cap;
+    // barrier slots: [0..8) full, [8..16) empty, [16..20) tmem_full, [20..24) tmem_empty, 24 a_full
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](uint32_t s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](uint32_t s) { return bar0 + 8u * (8u + s); };
+    auto tfull_bar = [&](uint32_t a) { return bar0 + 8u * (16u + a); };
+    auto tempty_bar = [&](uint32_t a) { return bar0 + 8u * (20u + a); };
+    const uint32_t afull_bar = bar0 + 8u * 24u;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t qb = blockIdx.x % args.n_qblocks;
+    const uint32_t j0 = blockIdx.x / args.n_qblocks;
+    const uint32_t g = args.ctas_per_qblock;
+    const uint64_t n_tiles = (args.n_rows + kMmaN - 1) / kMmaN;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_q);
+        tma_prefetch_desc(&tm_x);
+        for (uint32_t s = 0; s < args.n_stages; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (uint32_t a = 0; a < kMmaAccStages; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 4);  // one arrival per epilogue warp
+        }
+        mbar_init(afull_bar, 1);
+        fence_barrier_init();
+    } else if (warp == 2) {
+        tmem_alloc(smem_u32(tmem_slot), 512);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer =====
+            mbar_expect_tx(afull_bar, args.n_kblocks * kMmaTileBytes);
+            for (uint32_t kb = 0; kb < args.n_kblocks; ++kb)
+                tma_load_2d(a_smem + kb * kMmaTileBytes, &tm_q, afull_bar, (int32_t)(kb * kMmaKBlock),
+                            (int32_t)(qb * kMmaM));
+            uint32_t stage = 0, phase = 0;
+            for (uint64_t tile = j0; tile < n_tiles; tile += g) {
+                for (uint32_t kb = 0; kb < args.n_kblocks; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    mbar_expect_tx(full_bar(stage), kMmaTileBytes);
+                    tma_load_2d(b_smem + stage * kMmaTileBytes, &tm_x, full_bar(stage), (int32_t)(kb * kMmaKBlock),
+                                (int32_t)(tile * kMmaN));
+                    if (++stage == args.n_stages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            constexpr uint32_t idesc = umma_idesc_f16(kMmaM, kMmaN);
+            mbar_wait(afull_bar, 0);
+            tc_fence_after();
+            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            for (uint64_t tile = j0; tile < n_tiles; tile += g) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * kMmaN;
+                for (uint32_t kb = 0; kb < args.n_kblocks; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = a_smem + kb * kMmaTileBytes;
+                    const uint32_t b_addr = b_smem + stage * kMmaTileBytes;
+#pragma unroll
+                    for (uint32_t k4 = 0; k4 < kMmaKBlock / 16; ++k4) {
+                        umma_f16(d_tmem, umma_desc_sw128(a_addr + k4 * 32u), umma_desc_sw128(b_addr + k4 * 32u),
+                                 idesc, (kb | k4) != 0u ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar(stage));  // frees the B stage when these MMAs retire
+                    if (++stage == args.n_stages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+                if (++acc == kMmaAccStages) {
+                    acc = 0;
+                    acc_phase ^= 1u;
+                }
+            }
+        }
+    } else {
+        // ===== epilogue: TMEM lane = query, column = corpus row =====
+        const uint32_t quarter = warp & 3u;  // the TMEM lane quarter this warp may read
+        const uint32_t m = quarter * 32u + lane;
+        const uint32_t query = qb * kMmaM + m;
+        const bool live = query < args.batch && args.redo[query] == 0u;
+        const float margin2 = args.margin2[query];
+        float gate = live ? -INFINITY : INFINITY;
+        uint32_t count = 0;
+        uint64_t* list = args.cand + ((size_t)blockIdx.x * kMmaM + m) * args.cap;
+        uint64_t* scratch = scratch_all + (size_t)(warp - 2u) * args.cap;
+        const uint32_t trigger = args.cap - kMmaN;
+        uint32_t acc = 0, acc_phase = 0;
+        for (uint64_t tile = j0; tile < n_tiles; tile += g) {
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            const uint64_t row0 = tile * kMmaN;
+            const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * kMmaN;
+#pragma unroll 1
+            for (uint32_t c = 0; c < kMmaN / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld_x32(taddr + c * 32u, v);
+                tmem_ld_wait();
+                float mx = __uint_as_float(v[0]);
+#pragma unroll
+                for (int i = 1; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+                if (mx >= gate) {  // rare once the gate is established
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float s = __uint_as_float(v[i]);
+                        if (s >= gate) {
+                            const uint64_t row = row0 + c * 32u + (uint32_t)i;
+                            if (row < args.n_rows && !tombstoned(args.tombstones, row) && count < args.cap)
+                                list[count++] = make_key(s, (uint32_t)(args.row_base + row));
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));  // accumulator drained -> MMA may reuse it
+            if (++acc == kMmaAccStages) {
+                acc = 0;
+                acc_phase ^= 1u;
+            }
+            // keep room for a whole tile of appends before the next one
+            uint32_t need = __ballot_sync(0xffffffffu, count > trigger);
+            while (need) {
+                const uint32_t owner = __ffs(need) - 1u;
+                need &= need - 1u;
+                const uint32_t cnt_o = __shfl_sync(0xffffffffu, count, owner);
+                const float mar_o = __shfl_sync(0xffffffffu, margin2, owner);
+                uint64_t* list_o = args.cand + ((size_t)blockIdx.x * kMmaM + quarter * 32u + owner) * args.cap;
+                __syncwarp();  // the owner's appends are visible to the warp
+                uint32_t kept;
+                float new_gate;
+                warp_compact_list(list_o, cnt_o, args.cap, args.k, mar_o, scratch, lane, &kept, &new_gate);
+                if (lane == owner) {
+                    if (kept == 0xFFFFFFFFu) {
+                        args.redo[query] = 2u;  // tie band wider than the list: exact path redoes it
+                        count = 0;
+                        gate = INFINITY;
+                    } else {
+                        count = kept;
+                        gate = new_gate;
+                    }
+                }
+            }
+        }
+        args.cand_count[(size_t)blockIdx.x * kMmaM + m] = count;
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ─── refine: exact re-scoring of the candidate superset, one CTA per query ──────────────────
+struct MmaRefineArgs {
+    const uint64_t* cand;        // [n_ctas][128][cap]
+    const uint32_t* cand_count;  // [n_ctas][128]
+    const float* margin2;        // [n_qblocks*128]
+    const uint32_t* redo;        // [n_qblocks*128]
+    uint32_t n_qblocks, ctas_per_qblock, cap, k;
+    uint32_t buf_cap;            // shared candidate buffer capacity (power of two)
+    const uint16_t* slab;
+    const float* queries;        // [batch, dim] f32 (the ORIGINAL queries)
+    uint64_t n_rows, row_base;
+    uint32_t dim;
+    int reduce_order, tail_fma;
+    uint64_t* out_keys;          // [batch, k] (nullable)
+    fsgpu_hit_t* out_hits;       // [batch, k] (nullable)
+    uint32_t* out_counts;        // [batch] (nullable)
+    uint32_t* error_flag;
+};
+
+__global__ void __launch_bounds__(256) mma_refine_kernel(const MmaRefineArgs args) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* cand = reinterpret_cast<uint64_t*>(smem_raw);
+    uint64_t* tau = cand + args.buf_cap;
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(tau + 1);
+    const uint32_t b = blockIdx.x;
+    const uint32_t qb = b / kMmaM, m = b % kMmaM;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t step = blockDim.x;
+    if (args.redo[b] != 0u) return;  // the caller re-runs this query on the exact path
+    if (threadIdx.x == 0) {
+        *cnt = 0u;
+        *tau = 0ull;
+    }
+    __syncthreads();
+    const CandBuf buf{cand, cnt, tau};
+    const uint32_t trigger = args.buf_cap - step;
+
+    // pass 1: tau_a = k-th best APPROXIMATE key over every list of this query
+    for (uint32_t j = 0; j < args.ctas_per_qblock; ++j) {
+        const size_t slot = (size_t)(qb + (size_t)args.n_qblocks * j) * kMmaM + m;
+        const uint32_t n = min(args.cand_count[slot], args.cap);
+        const uint64_t* list = args.cand + slot * args.cap;
+        for (uint32_t base = 0; base < n; base += step) {  // CTA-uniform trip count
+            const uint64_t t = *tau;
+            const uint32_t i = base + threadIdx.x;
+            if (i < n) {
+                const uint64_t key = list[i];
+                if (key > t && !cand_push(buf, args.buf_cap, key)) atomicExch(args.error_flag, 1u);
+            }
+            __syncthreads();
+            if (*cnt > trigger) cand_compact(buf, args.buf_cap, args.k);
+            __syncthreads();
+        }
+    }
+    cand_compact(buf, args.buf_cap, args.k);
+    const uint32_t have = *cnt;
+    float gate = -INFINITY;
+    if (have >= args.k) gate = __fsub_rd(key_score(cand[args.k - 1]), args.margin2[b]);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *cnt = 0u;
+        *tau = 0ull;
+    }
+    __syncthreads();
+
+    // pass 2: every entry inside the band is re-scored exactly and competes on its exact key
+    const float* q = args.queries + (size_t)b * args.dim;
+    for (uint32_t j = 0; j < args.ctas_per_qblock; ++j) {
+        const size_t slot = (size_t)(qb + (size_t)args.n_qblocks * j) * kMmaM + m;
+        const uint32_t n = min(args.cand_count[slot], args.cap);
+        const uint64_t* list = args.cand + slot * args.cap;
+        for (uint32_t base = 0; base < n; base += step) {
+            const uint32_t i = base + threadIdx.x;
+            uint64_t key = 0ull;
+            bool pass = false;
+            if (i < n) {
+                key = list[i];
+                pass = key_score(key) >= gate;
+            }
+            uint32_t mask = __ballot_sync(0xffffffffu, pass);
+            while (mask) {
+                const uint32_t src = __ffs(mask) - 1u;
+                mask &= mask - 1u;
+                const uint32_t grow = key_row(__shfl_sync(0xffffffffu, key, src));
+                const uint64_t local = (uint64_t)grow - args.row_base;
+                const float s = warp_exact_dot(args.slab + local * args.dim, q, args.dim, args.reduce_order,
+                                               args.tail_fma);
+                if (lane == 0) {
+                    const uint64_t exact = make_key(s, grow);
+                    if (exact > *tau && !cand_push(buf, args.buf_cap, exact)) atomicExch(args.error_flag, 1u);
+                }
+            }
+            __syncthreads();
+            if (*cnt > trigger) cand_compact(buf, args.buf_cap, args.k);
+            __syncthreads();
+        }
+    }
+    cand_compact(buf, args.buf_cap, args.k);
+    const uint32_t count = *cnt;
+    if (threadIdx.x == 0 && args.out_counts) args.out_counts[b] = count;
+    for (uint32_t i = threadIdx.x; i < args.k; i += step) {
+        const uint64_t key = i < count ? cand[i] : 0ull;
+        if (args.out_keys) args.out_keys[(size_t)b * args.k + i] = key;
+        if (args.out_hits) {
+            fsgpu_hit_t h;
+            h.row = key ? key_row(key) : 0xFFFFFFFFu;
+            h.score = key ? key_score(key) : 0.0f;
+            args.out_hits[(size_t)b * args.k + i] = h;
+        }
+    }
+    (void)warp;
+}
+
+}  // namespace fsgpu

@@ -162,7 +162,9 @@ class GpuVectorIndex:
         p = _ffi.Profile()
         check(self._L.fsgpu_index_profile_read(self._h, C.byref(p), 1 if reset else 0))
         return dict(scan_launches=int(p.scan_launches), merge_launches=int(p.merge_launches),
-                    other_launches=int(p.other_launches), scan_bytes=int(p.scan_bytes), scan_ms=float(p.scan_ms))
+                    other_launches=int(p.other_launches), scan_bytes=int(p.scan_bytes), scan_ms=float(p.scan_ms),
+                    mma_launches=int(p.mma_launches), mma_flops=float(p.mma_flops),
+                    redo_queries=int(p.redo_queries))
 
     def set_tombstones(self, flags) -> None:
         """Soft-delete flags (record flag bit 0, lib.rs:172; honoured by the scan, search.rs:1281)."""

@@ -130,6 +130,9 @@ typedef struct fsgpu_profile {
     uint64_t other_launches;
     uint64_t scan_bytes;
     double scan_ms;        /* sum of event-timed scan launch durations (0 unless enabled) */
+    uint64_t mma_launches; /* scan launches that ran on the tensor-core batched kernel */
+    double mma_flops;      /* 2 * query slots * rows * dim summed over those launches */
+    uint64_t redo_queries; /* queries of batched launches re-run on the exact CUDA-core kernel */
 } fsgpu_profile;
 int fsgpu_index_profile_enable(fsgpu_index* index, int on);
 int fsgpu_index_profile_read(fsgpu_index* index, fsgpu_profile* out, int reset);
@@ -143,7 +146,11 @@ int fsgpu_index_profile_read(fsgpu_index* index, fsgpu_profile* out, int reset);
  * Ordering is the reference's strict total order (search.rs:1655-1686): score_key (NaN -> -inf)
  * by f32::total_cmp descending, ties -> lower row first.  Scores are bit-identical to the
  * reference's dot kernel (simd.rs:398-446) for the configured reduce order.
- * k == 0 or an empty index -> all counts 0 (search.rs:438-440). */
+ * k == 0 or an empty index -> all counts 0 (search.rs:438-440).
+ * Batches of >= 8 queries (FSGPU_MMA_MIN_BATCH) with k <= 256 on an all-finite slab whose dim is
+ * a multiple of 64 take ONE tensor-core pass over the slab (tcgen05/TMA, mma_scan_kernels.cuh)
+ * followed by an exact re-scoring of a provable superset of the top-k; results are identical
+ * to the per-query path.  That path synchronises the stream once per call. */
 int fsgpu_search_top_k(const fsgpu_index* index, const float* queries, uint32_t batch, uint32_t k,
                        uint32_t dim, fsgpu_hit* out, uint32_t* out_counts);
 
