@@ -126,7 +126,7 @@ struct fsgpu_index {
     mutable CUtensorMap tm_qhat;
     mutable const void* tm_qhat_ptr = nullptr;
     mutable uint32_t tm_qhat_rows = 0;
-    mutable DevBuf ws_qhat, ws_margin, ws_redo, ws_cand, ws_cand_count;
+    mutable DevBuf ws_qhat, ws_margin, ws_gate, ws_redo, ws_cand, ws_cand_count;
     // launch accounting (guarded by mu)
     mutable bool profiling = false;
     mutable fsgpu_profile prof{};
@@ -411,31 +411,61 @@ static int index_finish_setup(fsgpu_index* ix) {
     return FSGPU_OK;
 }
 
-static uint32_t mma_list_capacity(uint32_t k) { return std::max(256u, host_next_pow2(2 * k + 192)); }
-
 static int search_exact_locked(const fsgpu_index* ix, const float* d_queries, uint32_t batch, uint32_t k,
                                uint64_t* d_out_keys, fsgpu_hit* d_out_hits, uint32_t* d_out_counts,
                                cudaStream_t stream);
 
-// Up to num_sms*128 queries in ONE pass over the slab: prep -> tcgen05 scan -> exact refine.
-// Synchronises `stream` once (to learn which queries, if any, must be redone exactly).
+// The sample cascade of one batched search (mma_scan_kernels.cuh header): tiles per level, the
+// selection rank k' used for intermediate gates, and the per-query list capacity.
+struct MmaCascade {
+    uint64_t n_tiles = 0, t0 = 0, t1 = 0;  // t1 == 0: two levels only; t0 == n_tiles: one level
+    uint32_t k_sel = 16, cap = 2048;
+};
+
+static MmaCascade plan_cascade(uint64_t n_rows, uint32_t k) {
+    // Appends per query: level 0 keeps all t0*128 sample scores (deterministic); level 1 expects
+    // k' * t1/t0 and level 2 k' * n_tiles/t1, both minimised by t1 = sqrt(t0 * n_tiles) at
+    // L = k' * sqrt(n_tiles/t0).  t0 balances the deterministic dump against slack * L.
+    MmaCascade c;
+    c.n_tiles = (n_rows + kMmaN - 1) / kMmaN;
+    c.k_sel = std::max(k, 16u);
+    const double slack = std::max(2, env_int("FSGPU_MMA_LIST_SLACK", 6));
+    const double t0_bal = std::pow(slack * c.k_sel * std::sqrt((double)c.n_tiles) / kMmaN, 2.0 / 3.0);
+    const uint64_t t0_min = ((uint64_t)8 * c.k_sel + kMmaN - 1) / kMmaN;
+    c.t0 = std::min<uint64_t>(c.n_tiles, std::max<uint64_t>({16, t0_min, (uint64_t)std::ceil(t0_bal)}));
+    double random_part = 0.0;
+    if (c.n_tiles > 8 * c.t0) {
+        c.t1 = (uint64_t)std::llround(std::sqrt((double)c.t0 * (double)c.n_tiles));
+        c.t1 = std::min(c.n_tiles, std::max(c.t1, 2 * c.t0));
+        random_part = std::max((double)c.k_sel * (double)c.t1 / (double)c.t0,
+                               (double)c.k_sel * (double)c.n_tiles / (double)c.t1);
+    } else if (c.t0 < c.n_tiles) {
+        random_part = (double)c.k_sel * (double)c.n_tiles / (double)c.t0;
+    }
+    const double want = std::max((double)c.t0 * kMmaN, std::min(slack * random_part, 4194304.0));
+    c.cap = (uint32_t)(((uint64_t)want + 255) / 256 * 256);
+    return c;
+}
+
+// Up to num_sms*128 queries in ONE full pass over the slab (+ ~1.5 % of sample passes):
+// prep -> [scan sample, gate] x 2 -> scan all -> exact refine.  Synchronises `stream` once (to learn
+// which queries, if any, must be redone exactly).
 static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint32_t batch, uint32_t k,
                              uint64_t* d_out_keys, fsgpu_hit* d_out_hits, uint32_t* d_out_counts,
                              cudaStream_t stream) {
     const uint32_t n_kb = ix->dim / kMmaKBlock;
-    const uint32_t cap = mma_list_capacity(k);
     const size_t smem_limit = 227 * 1024;
-    const size_t fixed = mma_scan_smem_bytes(n_kb, 0, cap);
-    if (fixed + 2 * (size_t)kMmaTileBytes > smem_limit)
-        return fail(FSGPU_ERR_INVALID_CONFIG, "batched scan does not fit in shared memory (dim=%u k=%u)", ix->dim, k);
+    const size_t fixed = mma_scan_smem_bytes(n_kb, 0);
     uint32_t n_stages = (uint32_t)std::min<size_t>(kMmaMaxStages, (smem_limit - fixed) / kMmaTileBytes);
     const int stage_cap = env_int("FSGPU_MMA_STAGES", 0);
     if (stage_cap >= 2) n_stages = std::min<uint32_t>(n_stages, (uint32_t)stage_cap);
-    const size_t smem = mma_scan_smem_bytes(n_kb, n_stages, cap);
+    if (n_stages < 2) return fail(FSGPU_ERR_INVALID_CONFIG, "batched scan does not fit in shared memory (dim=%u)", ix->dim);
+    const size_t smem = mma_scan_smem_bytes(n_kb, n_stages);
     CUDA_TRY(cudaFuncSetAttribute(mma_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const uint32_t buf_cap = cand_capacity(k);
-    const size_t refine_smem = (size_t)buf_cap * 8 + 16;
-    CUDA_TRY(cudaFuncSetAttribute(mma_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)refine_smem));
+    const MmaCascade cas = plan_cascade(ix->n_rows, k);
+    const uint32_t sel_cap = cand_capacity(cas.k_sel), fin_cap = cand_capacity(k);
+    CUDA_TRY(cudaFuncSetAttribute(mma_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sel_cap * 8 + 16)));
+    CUDA_TRY(cudaFuncSetAttribute(mma_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(fin_cap * 8 + 16)));
 
     const uint32_t max_queries = (uint32_t)ix->num_sms * kMmaM;
     std::vector<uint32_t> redo_host;
@@ -447,9 +477,10 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
         const uint32_t slots = n_qb * kMmaM;
         CUDA_TRY(ix->ws_qhat.reserve((size_t)slots * ix->dim * 2));
         CUDA_TRY(ix->ws_margin.reserve((size_t)slots * 4));
+        CUDA_TRY(ix->ws_gate.reserve((size_t)slots * 4));
         CUDA_TRY(ix->ws_redo.reserve((size_t)slots * 4));
-        CUDA_TRY(ix->ws_cand.reserve((size_t)grid * kMmaM * cap * 8));
-        CUDA_TRY(ix->ws_cand_count.reserve((size_t)grid * kMmaM * 4));
+        CUDA_TRY(ix->ws_cand.reserve((size_t)slots * cas.cap * sizeof(MmaCand)));
+        CUDA_TRY(ix->ws_cand_count.reserve((size_t)slots * 4));
         if (ix->tm_qhat_ptr != ix->ws_qhat.p || ix->tm_qhat_rows != slots) {
             if (!make_f16_tile_map(&ix->tm_qhat, ix->ws_qhat.p, slots, ix->dim, false))
                 return fail(FSGPU_ERR_SUBSYSTEM, "gpu: cuTensorMapEncodeTiled failed for the query tile");
@@ -457,9 +488,11 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
             ix->tm_qhat_rows = slots;
         }
         const float* q = d_queries + (size_t)done * ix->dim;
+        CUDA_TRY(cudaMemsetAsync(ix->ws_cand_count.p, 0, (size_t)slots * 4, stream));
         mma_prep_queries_kernel<<<slots, 128, 0, stream>>>(q, sub, ix->dim, ix->max_row_norm, ix->ws_qhat.as<__half>(),
                                                            ix->ws_margin.as<float>(), ix->ws_redo.as<uint32_t>());
         CUDA_TRY(cudaGetLastError());
+        ix->prof.other_launches += 1;
 
         MmaScanArgs a{};
         a.n_rows = ix->n_rows;
@@ -469,13 +502,43 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
         a.n_qblocks = n_qb;
         a.ctas_per_qblock = g;
         a.batch = sub;
-        a.k = k;
-        a.cap = cap;
         a.n_stages = n_stages;
-        a.margin2 = ix->ws_margin.as<float>();
-        a.cand = ix->ws_cand.as<uint64_t>();
-        a.cand_count = ix->ws_cand_count.as<uint32_t>();
         a.redo = ix->ws_redo.as<uint32_t>();
+        a.cand = ix->ws_cand.as<MmaCand>();
+        a.cand_count = ix->ws_cand_count.as<uint32_t>();
+        a.cap = cas.cap;
+        MmaGateArgs ga{};
+        ga.cand = a.cand;
+        ga.cand_count = a.cand_count;
+        ga.margin2 = ix->ws_margin.as<float>();
+        ga.redo = a.redo;
+        ga.gate = ix->ws_gate.as<float>();
+        ga.cap = cas.cap;
+        ga.k_sel = cas.k_sel;
+        ga.buf_cap = sel_cap;
+        ga.error_flag = ix->d_error;
+
+        // sample levels: strided tiles, each level's k'-th best gates the next
+        const uint64_t level_tiles[2] = {cas.t0 < cas.n_tiles ? cas.t0 : 0, cas.t1};
+        bool have_gate = false;
+        for (int lvl = 0; lvl < 2; ++lvl) {
+            if (!level_tiles[lvl]) continue;
+            a.tile_first = 0;
+            a.tile_stride = cas.n_tiles / level_tiles[lvl];
+            a.tile_count = level_tiles[lvl];
+            a.gate = have_gate ? ix->ws_gate.as<float>() : nullptr;
+            mma_scan_kernel<<<grid, kMmaThreads, smem, stream>>>(ix->tm_qhat, ix->tm_slab, a);
+            CUDA_TRY(cudaGetLastError());
+            mma_gate_kernel<<<sub, 256, sel_cap * 8 + 16, stream>>>(ga);
+            CUDA_TRY(cudaGetLastError());
+            ix->prof.other_launches += 2;
+            have_gate = true;
+        }
+        // the full pass
+        a.tile_first = 0;
+        a.tile_stride = 1;
+        a.tile_count = cas.n_tiles;
+        a.gate = have_gate ? ix->ws_gate.as<float>() : nullptr;
         std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
         if (ix->profiling) {
             if (!ix->ev_free.empty()) {
@@ -497,19 +560,16 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
         ix->prof.scan_bytes += ix->n_rows * ix->dim * 2ull;
         ix->prof.mma_launches += 1;
         ix->prof.mma_flops += 2.0 * (double)slots * (double)ix->n_rows * (double)ix->dim;
-        ix->prof.other_launches += 1;  // prep
         ix->prof.merge_launches += 1;  // refine
 
         MmaRefineArgs r{};
         r.cand = a.cand;
         r.cand_count = a.cand_count;
-        r.margin2 = a.margin2;
-        r.redo = a.redo;
-        r.n_qblocks = n_qb;
-        r.ctas_per_qblock = g;
-        r.cap = cap;
+        r.margin2 = ga.margin2;
+        r.redo = ix->ws_redo.as<uint32_t>();
+        r.cap = cas.cap;
         r.k = k;
-        r.buf_cap = buf_cap;
+        r.buf_cap = fin_cap;
         r.slab = ix->d_slab;
         r.queries = q;
         r.n_rows = ix->n_rows;
@@ -521,7 +581,7 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
         r.out_hits = d_out_hits ? d_out_hits + (size_t)done * k : nullptr;
         r.out_counts = d_out_counts ? d_out_counts + done : nullptr;
         r.error_flag = ix->d_error;
-        mma_refine_kernel<<<sub, 256, refine_smem, stream>>>(r);
+        mma_refine_kernel<<<sub, 256, fin_cap * 8 + 16, stream>>>(r);
         CUDA_TRY(cudaGetLastError());
 
         redo_host.resize(sub);
@@ -627,7 +687,7 @@ extern "C" void fsgpu_index_destroy(fsgpu_index* ix) {
             }
         for (DevBuf* b : {&ix->ws_partial, &ix->ws_queries, &ix->ws_keys, &ix->ws_hits, &ix->ws_counts,
                           &ix->ws_sort_a, &ix->ws_sort_b, &ix->ws_cub, &ix->ws_rows, &ix->ws_scores,
-                          &ix->ws_present, &ix->ws_qhat, &ix->ws_margin, &ix->ws_redo, &ix->ws_cand,
+                          &ix->ws_present, &ix->ws_qhat, &ix->ws_margin, &ix->ws_gate, &ix->ws_redo, &ix->ws_cand,
                           &ix->ws_cand_count})
             b->release();
         if (ix->stream) cudaStreamDestroy(ix->stream);

@@ -10,19 +10,23 @@
 //   2. scan:    persistent warp-specialised kernel.  One CTA owns 128 queries (UMMA M = 128,
 //               resident in shared memory) and streams 128-row slab tiles (UMMA N = 128) through
 //               a TMA -> mbarrier -> tcgen05.mma -> TMEM pipeline.  TMEM lane = query, column =
-//               corpus row, so each epilogue thread owns one query: it keeps that query's gate
-//               in a register, and appends every row whose approximate score clears
-//               `tau_approx - 2 e_q` to the query's candidate list.  Any row of the exact top-k
-//               satisfies that inequality (proof in DESIGN.md "Batched scan"), so the lists are a
-//               superset of the exact answer.
-//   3. refine:  one CTA per query re-scores the (few) surviving candidates with the reference's
-//               exact accumulation tree (warp_exact_dot, simd.rs:398-446) and selects the top-k
-//               with the reference's total order (search.rs:1655-1686).
+//               corpus row, so each epilogue thread owns one query: it holds that query's gate
+//               in a register and appends every row whose approximate score clears it to the
+//               query's candidate list (a 3-input-max tree rejects 8 rows per 4 instructions).
+//               Gates come from a sample cascade: level 0 keeps every score of ~16 strided
+//               tiles, level 1 scans ~sqrt(16 * n_tiles) strided tiles against the k'-th best
+//               of level 0, level 2 scans everything against the k'-th best of level 1 minus
+//               2 e_q.  The k'-th best (k' = max(k, 16)) of any subset is a lower bound of the
+//               corpus' k-th best, so every row of the exact top-k clears the final gate
+//               (proof in DESIGN.md "Batched scan") and the final list is a superset of it.
+//   3. refine:  one CTA per query re-scores the band [tau_approx - 2 e_q, inf) of its list with
+//               the reference's exact accumulation tree (warp_exact_dot, simd.rs:398-446) and
+//               selects the top-k with the reference's total order (search.rs:1655-1686).
 //
 // The slab is read from HBM once per launch for up to 148*128 queries; the other query blocks
 // hit the same tiles in L2.  Queries the bound cannot cover (non-finite / f16-overflowing
-// components, or a tie band wider than the candidate list) are flagged and re-run by the caller
-// on the exact CUDA-core kernel (scan_kernels.cuh) — still on the GPU.
+// components, or a candidate list that overflowed, e.g. a huge tie band) are flagged and re-run
+// by the caller on the exact CUDA-core kernel (scan_kernels.cuh) — still on the GPU.
 #pragma once
 
 #include <cuda.h>
@@ -41,6 +45,12 @@ constexpr int kMmaMaxStages = 8;
 constexpr uint32_t kMmaMaxK = 256;  // larger k goes to the exact path
 constexpr uint32_t kMmaMaxDim = 512;
 
+// One candidate: the approximate (tensor-core) score and the GLOBAL row.
+struct __align__(8) MmaCand {
+    float score;
+    uint32_t row;
+};
+
 struct MmaScanArgs {
     uint64_t n_rows, row_base;
     const uint8_t* tombstones;
@@ -48,13 +58,14 @@ struct MmaScanArgs {
     uint32_t n_qblocks;        // ceil(batch / 128)
     uint32_t ctas_per_qblock;  // gridDim.x = n_qblocks * ctas_per_qblock
     uint32_t batch;
-    uint32_t k;
-    uint32_t cap;              // per-(CTA, query) candidate capacity, power of two >= k + 256
     uint32_t n_stages;         // B ring depth
-    const float* margin2;      // [n_qblocks*128]  2*e_q, rounded up
-    uint64_t* cand;            // [gridDim.x][128][cap] approximate order keys
-    uint32_t* cand_count;      // [gridDim.x][128]
-    uint32_t* redo;            // [n_qblocks*128] != 0: query must be re-run on the exact path
+    // the tiles of this level: first + i*stride, i in [0, count)
+    uint64_t tile_first, tile_stride, tile_count;
+    const float* gate;         // [n_qblocks*128] static per-query gate (nullptr = -inf: keep everything)
+    const uint32_t* redo;      // [n_qblocks*128] != 0: query is served by the exact path, skip it
+    MmaCand* cand;             // [n_qblocks*128][cap]
+    uint32_t* cand_count;      // [n_qblocks*128] appended entries (may exceed cap = overflow)
+    uint32_t cap;
 };
 
 // ─── PTX wrappers ───────────────────────────────────────────────────────────────────────────
@@ -247,58 +258,43 @@ slab_stats_kernel(const uint16_t* __restrict__ slab, uint64_t n_rows, uint32_t d
         atomicMax(stats, __float_as_uint(__fsqrt_ru(local_max)));  // non-negative floats order as uints
 }
 
-// ─── warp-cooperative bitonic sort (descending) of n = 2^m keys in shared memory ────────────
-__device__ __forceinline__ void warp_sort_desc(uint64_t* keys, uint32_t n, uint32_t lane) {
-    for (uint32_t k = 2; k <= n; k <<= 1) {
-        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-            for (uint32_t i = lane; i < n; i += 32) {
-                const uint32_t ixj = i ^ j;
-                if (ixj > i) {
-                    const uint64_t a = keys[i], b = keys[ixj];
-                    const bool desc = (i & k) == 0;
-                    if (desc ? (a < b) : (a > b)) {
-                        keys[i] = b;
-                        keys[ixj] = a;
-                    }
-                }
-            }
-            __syncwarp();
+// ─── the scan ───────────────────────────────────────────────────────────────────────────────
+// Shared memory (1024-byte aligned): A[n_kblocks][16 KiB] | B[n_stages][16 KiB] | barriers.
+__host__ __device__ inline size_t mma_scan_smem_bytes(uint32_t n_kblocks, uint32_t n_stages) {
+    return 1024 + (size_t)(n_kblocks + n_stages) * kMmaTileBytes + 256;
+}
+
+// Appends (score, global row) to the query's list.  Lists are append-only within a level; the
+// count keeps growing past `cap` so the consumer can see that (and by how much) it overflowed.
+__device__ __forceinline__ void mma_append(const MmaScanArgs& args, MmaCand* list, uint32_t* count, float s,
+                                           uint64_t row) {
+    if (row < args.n_rows && !tombstoned(args.tombstones, row)) {
+        const uint32_t pos = atomicAdd(count, 1u);
+        if (pos < args.cap) {
+            MmaCand c;
+            c.score = s;
+            c.row = (uint32_t)(args.row_base + row);
+            list[pos] = c;
         }
     }
 }
 
-// Compacts the candidate list of the query owned by lane `owner` of this warp: sort, find
-// tau = k-th best approximate score, keep every entry with score >= tau - margin2 (the band that
-// may still hold exact top-k rows).  Returns (kept count, new gate) to every lane; kept ==
-// 0xFFFFFFFF means the band does not fit and the query must be redone on the exact path.
-__device__ __forceinline__ void warp_compact_list(uint64_t* list, uint32_t count, uint32_t cap, uint32_t k,
-                                                  float margin2, uint64_t* scratch, uint32_t lane,
-                                                  uint32_t* out_kept, float* out_gate) {
-    for (uint32_t i = lane; i < cap; i += 32) scratch[i] = i < count ? list[i] : 0ull;
-    __syncwarp();
-    warp_sort_desc(scratch, cap, lane);
-    float gate = -INFINITY;
-    if (count >= k) gate = __fsub_rd(key_score(scratch[k - 1]), margin2);
-    uint32_t kept = 0;
-    for (uint32_t i = lane; i < count; i += 32) kept += key_score(scratch[i]) >= gate ? 1u : 0u;
-    for (int o = 16; o > 0; o >>= 1) kept += __shfl_xor_sync(0xffffffffu, kept, o);
-    if (kept + kMmaN > cap) {
-        *out_kept = 0xFFFFFFFFu;
-        *out_gate = INFINITY;
-    } else {
-        for (uint32_t i = lane; i < kept; i += 32) list[i] = scratch[i];
-        *out_kept = kept;
-        *out_gate = gate;
+// 8 accumulator columns of one query against its gate: one 3-input-max tree, then (rarely) the
+// individual compares.
+#define FSGPU_MMA_CHECK8(V, BASE)                                                                      \
+    {                                                                                                  \
+        const float m01 = fmaxf(fmaxf(__uint_as_float(V[BASE + 0]), __uint_as_float(V[BASE + 1])),     \
+                                __uint_as_float(V[BASE + 2]));                                         \
+        const float m02 = fmaxf(fmaxf(__uint_as_float(V[BASE + 3]), __uint_as_float(V[BASE + 4])),     \
+                                __uint_as_float(V[BASE + 5]));                                         \
+        const float m03 = fmaxf(fmaxf(__uint_as_float(V[BASE + 6]), __uint_as_float(V[BASE + 7])), m01); \
+        if (fmaxf(m02, m03) >= gate) {                                                                 \
+            _Pragma("unroll") for (int i8 = 0; i8 < 8; ++i8) {                                         \
+                const float s8 = __uint_as_float(V[BASE + i8]);                                        \
+                if (s8 >= gate) mma_append(args, list, count, s8, row0 + (uint32_t)(BASE + i8));       \
+            }                                                                                          \
+        }                                                                                              \
     }
-    __syncwarp();
-}
-
-// ─── the scan ───────────────────────────────────────────────────────────────────────────────
-// Shared memory (1024-byte aligned): A[n_kblocks][16 KiB] | B[n_stages][16 KiB] |
-// scratch[4 epilogue warps][cap] u64 | barriers.
-__host__ __device__ inline size_t mma_scan_smem_bytes(uint32_t n_kblocks, uint32_t n_stages, uint32_t cap) {
-    return 1024 + (size_t)(n_kblocks + n_stages) * kMmaTileBytes + 4 * (size_t)cap * 8 + 256;
-}
 
 __global__ void __launch_bounds__(kMmaThreads, 1)
 mma_scan_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_x,
@@ -309,8 +305,7 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     uint8_t* base_ptr = smem_dyn + (base - raw);
     const uint32_t a_smem = base;
     const uint32_t b_smem = a_smem + args.n_kblocks * kMmaTileBytes;
-    uint64_t* scratch_all = reinterpret_cast<uint64_t*>(base_ptr + (size_t)(args.n_kblocks + args.n_stages) * kMmaTileBytes);
-    uint64_t* bars = scratch_all + 4 * (size_t)args.cap;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base_ptr + (size_t)(args.n_kblocks + args.n_stages) * kMmaTileBytes);
     // barrier slots: [0..8) full, [8..16) empty, [16..20) tmem_full, [20..24) tmem_empty, 24 a_full
     const uint32_t bar0 = smem_u32(bars);
     auto full_bar = [&](uint32_t s) { return bar0 + 8u * s; };
@@ -324,7 +319,6 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const uint32_t qb = blockIdx.x % args.n_qblocks;
     const uint32_t j0 = blockIdx.x / args.n_qblocks;
     const uint32_t g = args.ctas_per_qblock;
-    const uint64_t n_tiles = (args.n_rows + kMmaN - 1) / kMmaN;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_q);
@@ -355,7 +349,8 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 tma_load_2d(a_smem + kb * kMmaTileBytes, &tm_q, afull_bar, (int32_t)(kb * kMmaKBlock),
                             (int32_t)(qb * kMmaM));
             uint32_t stage = 0, phase = 0;
-            for (uint64_t tile = j0; tile < n_tiles; tile += g) {
+            for (uint64_t i = j0; i < args.tile_count; i += g) {
+                const uint64_t tile = args.tile_first + i * args.tile_stride;
                 for (uint32_t kb = 0; kb < args.n_kblocks; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     mbar_expect_tx(full_bar(stage), kMmaTileBytes);
@@ -375,7 +370,7 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             mbar_wait(afull_bar, 0);
             tc_fence_after();
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-            for (uint64_t tile = j0; tile < n_tiles; tile += g) {
+            for (uint64_t i = j0; i < args.tile_count; i += g) {
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * kMmaN;
@@ -408,36 +403,30 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const uint32_t m = quarter * 32u + lane;
         const uint32_t query = qb * kMmaM + m;
         const bool live = query < args.batch && args.redo[query] == 0u;
-        const float margin2 = args.margin2[query];
-        float gate = live ? -INFINITY : INFINITY;
-        uint32_t count = 0;
-        uint64_t* list = args.cand + ((size_t)blockIdx.x * kMmaM + m) * args.cap;
-        uint64_t* scratch = scratch_all + (size_t)(warp - 2u) * args.cap;
-        const uint32_t trigger = args.cap - kMmaN;
+        const float gate = live ? (args.gate ? args.gate[query] : -INFINITY) : INFINITY;
+        MmaCand* list = args.cand + (size_t)query * args.cap;
+        uint32_t* count = args.cand_count + query;
         uint32_t acc = 0, acc_phase = 0;
-        for (uint64_t tile = j0; tile < n_tiles; tile += g) {
+        for (uint64_t i = j0; i < args.tile_count; i += g) {
+            const uint64_t tile = args.tile_first + i * args.tile_stride;
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
-            const uint64_t row0 = tile * kMmaN;
             const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * kMmaN;
-#pragma unroll 1
-            for (uint32_t c = 0; c < kMmaN / 32; ++c) {
-                uint32_t v[32];
-                tmem_ld_x32(taddr + c * 32u, v);
+            uint32_t va[32], vb[32];
+            tmem_ld_x32(taddr, va);
+#pragma unroll
+            for (uint32_t c = 0; c < kMmaN / 32; c += 2) {
                 tmem_ld_wait();
-                float mx = __uint_as_float(v[0]);
-#pragma unroll
-                for (int i = 1; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-                if (mx >= gate) {  // rare once the gate is established
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const float s = __uint_as_float(v[i]);
-                        if (s >= gate) {
-                            const uint64_t row = row0 + c * 32u + (uint32_t)i;
-                            if (row < args.n_rows && !tombstoned(args.tombstones, row) && count < args.cap)
-                                list[count++] = make_key(s, (uint32_t)(args.row_base + row));
-                        }
-                    }
+                tmem_ld_x32(taddr + (c + 1) * 32u, vb);  // in flight while chunk c is checked
+                {
+                    const uint64_t row0 = tile * kMmaN + c * 32u;
+                    FSGPU_MMA_CHECK8(va, 0) FSGPU_MMA_CHECK8(va, 8) FSGPU_MMA_CHECK8(va, 16) FSGPU_MMA_CHECK8(va, 24)
+                }
+                tmem_ld_wait();
+                if (c + 2 < kMmaN / 32) tmem_ld_x32(taddr + (c + 2) * 32u, va);
+                {
+                    const uint64_t row0 = tile * kMmaN + (c + 1) * 32u;
+                    FSGPU_MMA_CHECK8(vb, 0) FSGPU_MMA_CHECK8(vb, 8) FSGPU_MMA_CHECK8(vb, 16) FSGPU_MMA_CHECK8(vb, 24)
                 }
             }
             tc_fence_before();
@@ -447,31 +436,7 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 acc = 0;
                 acc_phase ^= 1u;
             }
-            // keep room for a whole tile of appends before the next one
-            uint32_t need = __ballot_sync(0xffffffffu, count > trigger);
-            while (need) {
-                const uint32_t owner = __ffs(need) - 1u;
-                need &= need - 1u;
-                const uint32_t cnt_o = __shfl_sync(0xffffffffu, count, owner);
-                const float mar_o = __shfl_sync(0xffffffffu, margin2, owner);
-                uint64_t* list_o = args.cand + ((size_t)blockIdx.x * kMmaM + quarter * 32u + owner) * args.cap;
-                __syncwarp();  // the owner's appends are visible to the warp
-                uint32_t kept;
-                float new_gate;
-                warp_compact_list(list_o, cnt_o, args.cap, args.k, mar_o, scratch, lane, &kept, &new_gate);
-                if (lane == owner) {
-                    if (kept == 0xFFFFFFFFu) {
-                        args.redo[query] = 2u;  // tie band wider than the list: exact path redoes it
-                        count = 0;
-                        gate = INFINITY;
-                    } else {
-                        count = kept;
-                        gate = new_gate;
-                    }
-                }
-            }
         }
-        args.cand_count[(size_t)blockIdx.x * kMmaM + m] = count;
     }
 
     tc_fence_before();
@@ -481,14 +446,70 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tmem_dealloc(tmem_base, 512);
     }
 }
+#undef FSGPU_MMA_CHECK8
+
+// ─── gate: k'-th best approximate score of a level's list -> the next level's static gate ───
+// One CTA per query.  Any subset's k'-th best is a lower bound of the full corpus' k'-th (<= k-th)
+// best, so the gate stays valid when the list overflowed (first `cap` entries are used).
+struct MmaGateArgs {
+    const MmaCand* cand;
+    uint32_t* cand_count;   // reset to 0 for the next level
+    const float* margin2;
+    const uint32_t* redo;
+    float* gate;            // out
+    uint32_t cap, k_sel, buf_cap;
+    uint32_t* error_flag;
+};
+
+__device__ __forceinline__ void mma_select_topk(const CandBuf& buf, uint32_t buf_cap, uint32_t k,
+                                                const MmaCand* list, uint32_t n, uint32_t* error_flag) {
+    const uint32_t step = blockDim.x;
+    const uint32_t trigger = buf_cap - step;
+    for (uint32_t base = 0; base < n; base += step) {  // CTA-uniform trip count
+        const uint64_t t = *buf.tau;
+        const uint32_t i = base + threadIdx.x;
+        if (i < n) {
+            const MmaCand c = list[i];
+            const uint64_t key = make_key(c.score, c.row);
+            if (key > t && !cand_push(buf, buf_cap, key)) atomicExch(error_flag, 1u);
+        }
+        __syncthreads();
+        if (*buf.cnt > trigger) cand_compact(buf, buf_cap, k);
+        __syncthreads();
+    }
+    cand_compact(buf, buf_cap, k);
+}
+
+__global__ void __launch_bounds__(256) mma_gate_kernel(const MmaGateArgs args) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* cand = reinterpret_cast<uint64_t*>(smem_raw);
+    uint64_t* tau = cand + args.buf_cap;
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(tau + 1);
+    const uint32_t b = blockIdx.x;
+    if (args.redo[b] != 0u) return;
+    if (threadIdx.x == 0) {
+        *cnt = 0u;
+        *tau = 0ull;
+    }
+    __syncthreads();
+    const CandBuf buf{cand, cnt, tau};
+    const uint32_t n = min(args.cand_count[b], args.cap);
+    mma_select_topk(buf, args.buf_cap, args.k_sel, args.cand + (size_t)b * args.cap, n, args.error_flag);
+    if (threadIdx.x == 0) {
+        float gate = -INFINITY;
+        if (*cnt >= args.k_sel) gate = __fsub_rd(key_score(cand[args.k_sel - 1]), args.margin2[b]);
+        args.gate[b] = gate;
+        args.cand_count[b] = 0u;
+    }
+}
 
 // ─── refine: exact re-scoring of the candidate superset, one CTA per query ──────────────────
 struct MmaRefineArgs {
-    const uint64_t* cand;        // [n_ctas][128][cap]
-    const uint32_t* cand_count;  // [n_ctas][128]
-    const float* margin2;        // [n_qblocks*128]
-    const uint32_t* redo;        // [n_qblocks*128]
-    uint32_t n_qblocks, ctas_per_qblock, cap, k;
+    const MmaCand* cand;         // [slots][cap]
+    const uint32_t* cand_count;  // [slots]
+    const float* margin2;        // [slots]
+    uint32_t* redo;              // [slots]; set to 2 when the final list overflowed
+    uint32_t cap, k;
     uint32_t buf_cap;            // shared candidate buffer capacity (power of two)
     const uint16_t* slab;
     const float* queries;        // [batch, dim] f32 (the ORIGINAL queries)
@@ -507,10 +528,14 @@ __global__ void __launch_bounds__(256) mma_refine_kernel(const MmaRefineArgs arg
     uint64_t* tau = cand + args.buf_cap;
     uint32_t* cnt = reinterpret_cast<uint32_t*>(tau + 1);
     const uint32_t b = blockIdx.x;
-    const uint32_t qb = b / kMmaM, m = b % kMmaM;
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lane = threadIdx.x & 31;
     const uint32_t step = blockDim.x;
     if (args.redo[b] != 0u) return;  // the caller re-runs this query on the exact path
+    const uint32_t n = args.cand_count[b];
+    if (n > args.cap) {  // the superset is incomplete: exact path
+        if (threadIdx.x == 0) args.redo[b] = 2u;
+        return;
+    }
     if (threadIdx.x == 0) {
         *cnt = 0u;
         *tau = 0ull;
@@ -518,28 +543,12 @@ __global__ void __launch_bounds__(256) mma_refine_kernel(const MmaRefineArgs arg
     __syncthreads();
     const CandBuf buf{cand, cnt, tau};
     const uint32_t trigger = args.buf_cap - step;
+    const MmaCand* list = args.cand + (size_t)b * args.cap;
 
-    // pass 1: tau_a = k-th best APPROXIMATE key over every list of this query
-    for (uint32_t j = 0; j < args.ctas_per_qblock; ++j) {
-        const size_t slot = (size_t)(qb + (size_t)args.n_qblocks * j) * kMmaM + m;
-        const uint32_t n = min(args.cand_count[slot], args.cap);
-        const uint64_t* list = args.cand + slot * args.cap;
-        for (uint32_t base = 0; base < n; base += step) {  // CTA-uniform trip count
-            const uint64_t t = *tau;
-            const uint32_t i = base + threadIdx.x;
-            if (i < n) {
-                const uint64_t key = list[i];
-                if (key > t && !cand_push(buf, args.buf_cap, key)) atomicExch(args.error_flag, 1u);
-            }
-            __syncthreads();
-            if (*cnt > trigger) cand_compact(buf, args.buf_cap, args.k);
-            __syncthreads();
-        }
-    }
-    cand_compact(buf, args.buf_cap, args.k);
-    const uint32_t have = *cnt;
+    // pass 1: tau_a = k-th best APPROXIMATE key of the list
+    mma_select_topk(buf, args.buf_cap, args.k, list, n, args.error_flag);
     float gate = -INFINITY;
-    if (have >= args.k) gate = __fsub_rd(key_score(cand[args.k - 1]), args.margin2[b]);
+    if (*cnt >= args.k) gate = __fsub_rd(key_score(cand[args.k - 1]), args.margin2[b]);
     __syncthreads();
     if (threadIdx.x == 0) {
         *cnt = 0u;
@@ -549,35 +558,32 @@ __global__ void __launch_bounds__(256) mma_refine_kernel(const MmaRefineArgs arg
 
     // pass 2: every entry inside the band is re-scored exactly and competes on its exact key
     const float* q = args.queries + (size_t)b * args.dim;
-    for (uint32_t j = 0; j < args.ctas_per_qblock; ++j) {
-        const size_t slot = (size_t)(qb + (size_t)args.n_qblocks * j) * kMmaM + m;
-        const uint32_t n = min(args.cand_count[slot], args.cap);
-        const uint64_t* list = args.cand + slot * args.cap;
-        for (uint32_t base = 0; base < n; base += step) {
-            const uint32_t i = base + threadIdx.x;
-            uint64_t key = 0ull;
-            bool pass = false;
-            if (i < n) {
-                key = list[i];
-                pass = key_score(key) >= gate;
-            }
-            uint32_t mask = __ballot_sync(0xffffffffu, pass);
-            while (mask) {
-                const uint32_t src = __ffs(mask) - 1u;
-                mask &= mask - 1u;
-                const uint32_t grow = key_row(__shfl_sync(0xffffffffu, key, src));
-                const uint64_t local = (uint64_t)grow - args.row_base;
-                const float s = warp_exact_dot(args.slab + local * args.dim, q, args.dim, args.reduce_order,
-                                               args.tail_fma);
-                if (lane == 0) {
-                    const uint64_t exact = make_key(s, grow);
-                    if (exact > *tau && !cand_push(buf, args.buf_cap, exact)) atomicExch(args.error_flag, 1u);
-                }
-            }
-            __syncthreads();
-            if (*cnt > trigger) cand_compact(buf, args.buf_cap, args.k);
-            __syncthreads();
+    for (uint32_t base = 0; base < n; base += step) {
+        const uint32_t i = base + threadIdx.x;
+        MmaCand c;
+        c.score = -INFINITY;
+        c.row = 0;
+        bool pass = false;
+        if (i < n) {
+            c = list[i];
+            pass = c.score >= gate;
         }
+        uint32_t mask = __ballot_sync(0xffffffffu, pass);
+        while (mask) {
+            const uint32_t src = __ffs(mask) - 1u;
+            mask &= mask - 1u;
+            const uint32_t grow = __shfl_sync(0xffffffffu, c.row, src);
+            const uint64_t local = (uint64_t)grow - args.row_base;
+            const float s = warp_exact_dot(args.slab + local * args.dim, q, args.dim, args.reduce_order,
+                                           args.tail_fma);
+            if (lane == 0) {
+                const uint64_t exact = make_key(s, grow);
+                if (exact > *tau && !cand_push(buf, args.buf_cap, exact)) atomicExch(args.error_flag, 1u);
+            }
+        }
+        __syncthreads();
+        if (*cnt > trigger) cand_compact(buf, args.buf_cap, args.k);
+        __syncthreads();
     }
     cand_compact(buf, args.buf_cap, args.k);
     const uint32_t count = *cnt;
@@ -592,7 +598,6 @@ __global__ void __launch_bounds__(256) mma_refine_kernel(const MmaRefineArgs arg
             args.out_hits[(size_t)b * args.k + i] = h;
         }
     }
-    (void)warp;
 }
 
 }  // namespace fsgpu
