@@ -419,7 +419,14 @@ static int search_exact_locked(const fsgpu_index* ix, const float* d_queries, ui
 // selection rank k' used for intermediate gates, and the per-query list capacity.
 struct MmaCascade {
     uint64_t n_tiles = 0, t0 = 0, t1 = 0;  // t1 == 0: two levels only; t0 == n_tiles: one level
-    uint32_t k_sel = 16, cap = 2048;
+    uint32_t k_sel = 16;
+    double slack = 6.0, random_part = 0.0;  // expected gate-clearing rows per query and level
+    // capacity of one (CTA, query) list when `g` CTAs share a query block
+    uint32_t list_cap(uint32_t g) const {
+        const uint64_t dump = (t0 + g - 1) / g * kMmaN;  // level 0 keeps every score of its tiles
+        const uint64_t rnd = (uint64_t)std::min(slack * random_part / g, 4194304.0) + 64;
+        return (uint32_t)((std::max(dump, rnd) + 63) / 64 * 64);
+    }
 };
 
 static MmaCascade plan_cascade(uint64_t n_rows, uint32_t k) {
@@ -429,21 +436,18 @@ static MmaCascade plan_cascade(uint64_t n_rows, uint32_t k) {
     MmaCascade c;
     c.n_tiles = (n_rows + kMmaN - 1) / kMmaN;
     c.k_sel = std::max(k, 16u);
-    const double slack = std::max(2, env_int("FSGPU_MMA_LIST_SLACK", 6));
-    const double t0_bal = std::pow(slack * c.k_sel * std::sqrt((double)c.n_tiles) / kMmaN, 2.0 / 3.0);
+    c.slack = std::max(2, env_int("FSGPU_MMA_LIST_SLACK", 6));
+    const double t0_bal = std::pow(c.slack * c.k_sel * std::sqrt((double)c.n_tiles) / kMmaN, 2.0 / 3.0);
     const uint64_t t0_min = ((uint64_t)8 * c.k_sel + kMmaN - 1) / kMmaN;
     c.t0 = std::min<uint64_t>(c.n_tiles, std::max<uint64_t>({16, t0_min, (uint64_t)std::ceil(t0_bal)}));
-    double random_part = 0.0;
     if (c.n_tiles > 8 * c.t0) {
         c.t1 = (uint64_t)std::llround(std::sqrt((double)c.t0 * (double)c.n_tiles));
         c.t1 = std::min(c.n_tiles, std::max(c.t1, 2 * c.t0));
-        random_part = std::max((double)c.k_sel * (double)c.t1 / (double)c.t0,
-                               (double)c.k_sel * (double)c.n_tiles / (double)c.t1);
+        c.random_part = std::max((double)c.k_sel * (double)c.t1 / (double)c.t0,
+                                 (double)c.k_sel * (double)c.n_tiles / (double)c.t1);
     } else if (c.t0 < c.n_tiles) {
-        random_part = (double)c.k_sel * (double)c.n_tiles / (double)c.t0;
+        c.random_part = (double)c.k_sel * (double)c.n_tiles / (double)c.t0;
     }
-    const double want = std::max((double)c.t0 * kMmaN, std::min(slack * random_part, 4194304.0));
-    c.cap = (uint32_t)(((uint64_t)want + 255) / 256 * 256);
     return c;
 }
 
@@ -479,8 +483,9 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
         CUDA_TRY(ix->ws_margin.reserve((size_t)slots * 4));
         CUDA_TRY(ix->ws_gate.reserve((size_t)slots * 4));
         CUDA_TRY(ix->ws_redo.reserve((size_t)slots * 4));
-        CUDA_TRY(ix->ws_cand.reserve((size_t)slots * cas.cap * sizeof(MmaCand)));
-        CUDA_TRY(ix->ws_cand_count.reserve((size_t)slots * 4));
+        const uint32_t cap = cas.list_cap(g);
+        CUDA_TRY(ix->ws_cand.reserve((size_t)grid * kMmaM * cap * sizeof(MmaCand)));
+        CUDA_TRY(ix->ws_cand_count.reserve((size_t)grid * kMmaM * 4));
         if (ix->tm_qhat_ptr != ix->ws_qhat.p || ix->tm_qhat_rows != slots) {
             if (!make_f16_tile_map(&ix->tm_qhat, ix->ws_qhat.p, slots, ix->dim, false))
                 return fail(FSGPU_ERR_SUBSYSTEM, "gpu: cuTensorMapEncodeTiled failed for the query tile");
@@ -488,7 +493,6 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
             ix->tm_qhat_rows = slots;
         }
         const float* q = d_queries + (size_t)done * ix->dim;
-        CUDA_TRY(cudaMemsetAsync(ix->ws_cand_count.p, 0, (size_t)slots * 4, stream));
         mma_prep_queries_kernel<<<slots, 128, 0, stream>>>(q, sub, ix->dim, ix->max_row_norm, ix->ws_qhat.as<__half>(),
                                                            ix->ws_margin.as<float>(), ix->ws_redo.as<uint32_t>());
         CUDA_TRY(cudaGetLastError());
@@ -506,14 +510,12 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
         a.redo = ix->ws_redo.as<uint32_t>();
         a.cand = ix->ws_cand.as<MmaCand>();
         a.cand_count = ix->ws_cand_count.as<uint32_t>();
-        a.cap = cas.cap;
+        a.cap = cap;
         MmaGateArgs ga{};
-        ga.cand = a.cand;
-        ga.cand_count = a.cand_count;
+        ga.lists = MmaLists{a.cand, a.cand_count, n_qb, g, cap};
         ga.margin2 = ix->ws_margin.as<float>();
         ga.redo = a.redo;
         ga.gate = ix->ws_gate.as<float>();
-        ga.cap = cas.cap;
         ga.k_sel = cas.k_sel;
         ga.buf_cap = sel_cap;
         ga.error_flag = ix->d_error;
@@ -523,8 +525,7 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
         bool have_gate = false;
         for (int lvl = 0; lvl < 2; ++lvl) {
             if (!level_tiles[lvl]) continue;
-            a.tile_first = 0;
-            a.tile_stride = cas.n_tiles / level_tiles[lvl];
+            a.tile_stride = env_int("FSGPU_MMA_SAMPLE_CONTIG", 0) ? 1 : cas.n_tiles / level_tiles[lvl];
             a.tile_count = level_tiles[lvl];
             a.gate = have_gate ? ix->ws_gate.as<float>() : nullptr;
             mma_scan_kernel<<<grid, kMmaThreads, smem, stream>>>(ix->tm_qhat, ix->tm_slab, a);
@@ -535,7 +536,6 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
             have_gate = true;
         }
         // the full pass
-        a.tile_first = 0;
         a.tile_stride = 1;
         a.tile_count = cas.n_tiles;
         a.gate = have_gate ? ix->ws_gate.as<float>() : nullptr;
@@ -563,11 +563,9 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
         ix->prof.merge_launches += 1;  // refine
 
         MmaRefineArgs r{};
-        r.cand = a.cand;
-        r.cand_count = a.cand_count;
+        r.lists = ga.lists;
         r.margin2 = ga.margin2;
         r.redo = ix->ws_redo.as<uint32_t>();
-        r.cap = cas.cap;
         r.k = k;
         r.buf_cap = fin_cap;
         r.slab = ix->d_slab;

@@ -59,18 +59,33 @@ struct MmaScanArgs {
     uint32_t ctas_per_qblock;  // gridDim.x = n_qblocks * ctas_per_qblock
     uint32_t batch;
     uint32_t n_stages;         // B ring depth
-    // the tiles of this level: first + i*stride, i in [0, count)
-    uint64_t tile_first, tile_stride, tile_count;
+    // the tiles of this level: tile_of(i) = i*stride + jitter(i) % stride, i in [0, count): one
+    // pseudo-random tile per stratum (a constant stride camps on a few HBM channels: a strided
+    // sample pass ran at 140 GB/s, profiles/r01_mma_v3_L1_strided_ncu.json)
+    uint64_t tile_stride, tile_count;
     const float* gate;         // [n_qblocks*128] static per-query gate (nullptr = -inf: keep everything)
     const uint32_t* redo;      // [n_qblocks*128] != 0: query is served by the exact path, skip it
-    MmaCand* cand;             // [n_qblocks*128][cap]
-    uint32_t* cand_count;      // [n_qblocks*128] appended entries (may exceed cap = overflow)
+    MmaCand* cand;             // [gridDim.x][128][cap]: one private list per (CTA, query)
+    uint32_t* cand_count;      // [gridDim.x][128] appended entries (may exceed cap = overflow)
     uint32_t cap;
 };
 
 // ─── PTX wrappers ───────────────────────────────────────────────────────────────────────────
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+// True on exactly one (elected) lane of a converged warp; lets ptxas keep the tcgen05 / TMA
+// issue sequences on the uniform datapath without per-instruction serialisation loops.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.b32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -156,6 +171,12 @@ __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&v)[32]) {
           "=r"(v[30]), "=r"(v[31])
         : "r"(taddr)
         : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -264,37 +285,39 @@ __host__ __device__ inline size_t mma_scan_smem_bytes(uint32_t n_kblocks, uint32
     return 1024 + (size_t)(n_kblocks + n_stages) * kMmaTileBytes + 256;
 }
 
-// Appends (score, global row) to the query's list.  Lists are append-only within a level; the
-// count keeps growing past `cap` so the consumer can see that (and by how much) it overflowed.
-__device__ __forceinline__ void mma_append(const MmaScanArgs& args, MmaCand* list, uint32_t* count, float s,
+__device__ __forceinline__ uint64_t mma_tile_of(const MmaScanArgs& args, uint64_t i) {
+    const uint64_t jitter = args.tile_stride > 1 ? (uint64_t)(((uint32_t)i * 0x9E3779B1u) >> 8) % args.tile_stride : 0;
+    return i * args.tile_stride + jitter;
+}
+
+// Appends (score, global row) to this thread's private list: a plain store, no atomics and no
+// returned value to wait for.  The count keeps growing past `cap` so the consumer sees overflow.
+__device__ __forceinline__ void mma_append(const MmaScanArgs& args, MmaCand* list, uint32_t& count, float s,
                                            uint64_t row) {
     if (row < args.n_rows && !tombstoned(args.tombstones, row)) {
-        const uint32_t pos = atomicAdd(count, 1u);
-        if (pos < args.cap) {
+        if (count < args.cap) {
             MmaCand c;
             c.score = s;
             c.row = (uint32_t)(args.row_base + row);
-            list[pos] = c;
+            list[count] = c;
         }
+        ++count;
     }
 }
 
-// 8 accumulator columns of one query against its gate: one 3-input-max tree, then (rarely) the
-// individual compares.
-#define FSGPU_MMA_CHECK8(V, BASE)                                                                      \
-    {                                                                                                  \
-        const float m01 = fmaxf(fmaxf(__uint_as_float(V[BASE + 0]), __uint_as_float(V[BASE + 1])),     \
-                                __uint_as_float(V[BASE + 2]));                                         \
-        const float m02 = fmaxf(fmaxf(__uint_as_float(V[BASE + 3]), __uint_as_float(V[BASE + 4])),     \
-                                __uint_as_float(V[BASE + 5]));                                         \
-        const float m03 = fmaxf(fmaxf(__uint_as_float(V[BASE + 6]), __uint_as_float(V[BASE + 7])), m01); \
-        if (fmaxf(m02, m03) >= gate) {                                                                 \
-            _Pragma("unroll") for (int i8 = 0; i8 < 8; ++i8) {                                         \
-                const float s8 = __uint_as_float(V[BASE + i8]);                                        \
-                if (s8 >= gate) mma_append(args, list, count, s8, row0 + (uint32_t)(BASE + i8));       \
-            }                                                                                          \
-        }                                                                                              \
-    }
+// Max of 8 accumulator columns (3-input max tree): one bit of the thread's "hot group" mask.
+__device__ __forceinline__ uint32_t mma_hot_bit(const uint32_t (&v)[32], int base, float gate, uint32_t bit) {
+    const float m1 = fmaxf(fmaxf(__uint_as_float(v[base + 0]), __uint_as_float(v[base + 1])),
+                           __uint_as_float(v[base + 2]));
+    const float m2 = fmaxf(fmaxf(__uint_as_float(v[base + 3]), __uint_as_float(v[base + 4])),
+                           __uint_as_float(v[base + 5]));
+    const float m3 = fmaxf(fmaxf(__uint_as_float(v[base + 6]), __uint_as_float(v[base + 7])), m1);
+    return fmaxf(m2, m3) >= gate ? bit : 0u;
+}
+__device__ __forceinline__ uint32_t mma_hot_bits(const uint32_t (&v)[32], float gate, uint32_t shift) {
+    return mma_hot_bit(v, 0, gate, 1u << shift) | mma_hot_bit(v, 8, gate, 2u << shift) |
+           mma_hot_bit(v, 16, gate, 4u << shift) | mma_hot_bit(v, 24, gate, 8u << shift);
+}
 
 __global__ void __launch_bounds__(kMmaThreads, 1)
 mma_scan_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_x,
@@ -342,59 +365,65 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
-            // ===== TMA producer =====
+        // ===== TMA producer (whole warp loops, one elected lane issues) =====
+        if (elect_one()) {
             mbar_expect_tx(afull_bar, args.n_kblocks * kMmaTileBytes);
             for (uint32_t kb = 0; kb < args.n_kblocks; ++kb)
                 tma_load_2d(a_smem + kb * kMmaTileBytes, &tm_q, afull_bar, (int32_t)(kb * kMmaKBlock),
                             (int32_t)(qb * kMmaM));
-            uint32_t stage = 0, phase = 0;
-            for (uint64_t i = j0; i < args.tile_count; i += g) {
-                const uint64_t tile = args.tile_first + i * args.tile_stride;
-                for (uint32_t kb = 0; kb < args.n_kblocks; ++kb) {
-                    mbar_wait(empty_bar(stage), phase ^ 1u);
+        }
+        __syncwarp();
+        uint32_t stage = 0, phase = 0;
+        for (uint64_t i = j0; i < args.tile_count; i += g) {
+            const int32_t row_coord = (int32_t)(mma_tile_of(args, i) * kMmaN);
+            for (uint32_t kb = 0; kb < args.n_kblocks; ++kb) {
+                mbar_wait(empty_bar(stage), phase ^ 1u);
+                if (elect_one()) {
                     mbar_expect_tx(full_bar(stage), kMmaTileBytes);
                     tma_load_2d(b_smem + stage * kMmaTileBytes, &tm_x, full_bar(stage), (int32_t)(kb * kMmaKBlock),
-                                (int32_t)(tile * kMmaN));
-                    if (++stage == args.n_stages) {
-                        stage = 0;
-                        phase ^= 1u;
-                    }
+                                row_coord);
+                }
+                __syncwarp();
+                if (++stage == args.n_stages) {
+                    stage = 0;
+                    phase ^= 1u;
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ===== MMA issuer =====
-            constexpr uint32_t idesc = umma_idesc_f16(kMmaM, kMmaN);
-            mbar_wait(afull_bar, 0);
+        // ===== MMA issuer (whole warp loops, one elected lane issues) =====
+        constexpr uint32_t idesc = umma_idesc_f16(kMmaM, kMmaN);
+        const uint64_t a_desc0 = umma_desc_sw128(a_smem);
+        const uint64_t b_desc0 = umma_desc_sw128(b_smem);
+        mbar_wait(afull_bar, 0);
+        tc_fence_after();
+        uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+        for (uint64_t i = j0; i < args.tile_count; i += g) {
+            mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
             tc_fence_after();
-            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-            for (uint64_t i = j0; i < args.tile_count; i += g) {
-                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+            const uint32_t d_tmem = tmem_base + acc * kMmaN;
+            for (uint32_t kb = 0; kb < args.n_kblocks; ++kb) {
+                mbar_wait(full_bar(stage), phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * kMmaN;
-                for (uint32_t kb = 0; kb < args.n_kblocks; ++kb) {
-                    mbar_wait(full_bar(stage), phase);
-                    tc_fence_after();
-                    const uint32_t a_addr = a_smem + kb * kMmaTileBytes;
-                    const uint32_t b_addr = b_smem + stage * kMmaTileBytes;
+                if (elect_one()) {
+                    // descriptors advance in units of 16 bytes: 1024 per K-block tile, 2 per 16 elements
+                    const uint64_t a_desc = a_desc0 + (uint64_t)(kb * (kMmaTileBytes >> 4));
+                    const uint64_t b_desc = b_desc0 + (uint64_t)(stage * (kMmaTileBytes >> 4));
 #pragma unroll
-                    for (uint32_t k4 = 0; k4 < kMmaKBlock / 16; ++k4) {
-                        umma_f16(d_tmem, umma_desc_sw128(a_addr + k4 * 32u), umma_desc_sw128(b_addr + k4 * 32u),
-                                 idesc, (kb | k4) != 0u ? 1u : 0u);
-                    }
+                    for (uint32_t k4 = 0; k4 < kMmaKBlock / 16; ++k4)
+                        umma_f16(d_tmem, a_desc + 2u * k4, b_desc + 2u * k4, idesc, (kb | k4) != 0u ? 1u : 0u);
                     umma_commit(empty_bar(stage));  // frees the B stage when these MMAs retire
-                    if (++stage == args.n_stages) {
-                        stage = 0;
-                        phase ^= 1u;
-                    }
+                    if (kb + 1 == args.n_kblocks) umma_commit(tfull_bar(acc));  // accumulator complete
                 }
-                umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
-                if (++acc == kMmaAccStages) {
-                    acc = 0;
-                    acc_phase ^= 1u;
+                __syncwarp();
+                if (++stage == args.n_stages) {
+                    stage = 0;
+                    phase ^= 1u;
                 }
+            }
+            if (++acc == kMmaAccStages) {
+                acc = 0;
+                acc_phase ^= 1u;
             }
         }
     } else {
@@ -404,29 +433,46 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const uint32_t query = qb * kMmaM + m;
         const bool live = query < args.batch && args.redo[query] == 0u;
         const float gate = live ? (args.gate ? args.gate[query] : -INFINITY) : INFINITY;
-        MmaCand* list = args.cand + (size_t)query * args.cap;
-        uint32_t* count = args.cand_count + query;
+        MmaCand* list = args.cand + ((size_t)blockIdx.x * kMmaM + m) * args.cap;
+        uint32_t count = 0;
         uint32_t acc = 0, acc_phase = 0;
         for (uint64_t i = j0; i < args.tile_count; i += g) {
-            const uint64_t tile = args.tile_first + i * args.tile_stride;
+            const uint64_t tile = mma_tile_of(args, i);
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * kMmaN;
+            // fast path: 16 groups of 8 columns -> one "some column clears the gate" bit each
             uint32_t va[32], vb[32];
+            uint32_t hot = 0;
             tmem_ld_x32(taddr, va);
+            tmem_ld_wait();
+            tmem_ld_x32(taddr + 32u, vb);  // in flight while the previous chunk is reduced
+            hot |= mma_hot_bits(va, gate, 0);
+            tmem_ld_wait();
+            tmem_ld_x32(taddr + 64u, va);
+            hot |= mma_hot_bits(vb, gate, 4);
+            tmem_ld_wait();
+            tmem_ld_x32(taddr + 96u, vb);
+            hot |= mma_hot_bits(va, gate, 8);
+            tmem_ld_wait();
+            hot |= mma_hot_bits(vb, gate, 12);
+            // slow path (rare): the warp re-reads each hot group and the owning lanes append.  One
+            // compact copy of the append code instead of 128 unrolled ones (instruction cache).
+            uint32_t hot_warp = __reduce_or_sync(0xffffffffu, hot);
+#pragma unroll 1
+            while (hot_warp) {
+                const uint32_t grp = __ffs(hot_warp) - 1u;
+                hot_warp &= hot_warp - 1u;
+                uint32_t w[8];
+                tmem_ld_x8(taddr + grp * 8u, w);
+                tmem_ld_wait();
+                if (hot & (1u << grp)) {
+                    const uint64_t row0 = tile * kMmaN + grp * 8u;
 #pragma unroll
-            for (uint32_t c = 0; c < kMmaN / 32; c += 2) {
-                tmem_ld_wait();
-                tmem_ld_x32(taddr + (c + 1) * 32u, vb);  // in flight while chunk c is checked
-                {
-                    const uint64_t row0 = tile * kMmaN + c * 32u;
-                    FSGPU_MMA_CHECK8(va, 0) FSGPU_MMA_CHECK8(va, 8) FSGPU_MMA_CHECK8(va, 16) FSGPU_MMA_CHECK8(va, 24)
-                }
-                tmem_ld_wait();
-                if (c + 2 < kMmaN / 32) tmem_ld_x32(taddr + (c + 2) * 32u, va);
-                {
-                    const uint64_t row0 = tile * kMmaN + (c + 1) * 32u;
-                    FSGPU_MMA_CHECK8(vb, 0) FSGPU_MMA_CHECK8(vb, 8) FSGPU_MMA_CHECK8(vb, 16) FSGPU_MMA_CHECK8(vb, 24)
+                    for (int i = 0; i < 8; ++i) {
+                        const float s8 = __uint_as_float(w[i]);
+                        if (s8 >= gate) mma_append(args, list, count, s8, row0 + (uint32_t)i);
+                    }
                 }
             }
             tc_fence_before();
@@ -437,6 +483,7 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 acc_phase ^= 1u;
             }
         }
+        args.cand_count[(size_t)blockIdx.x * kMmaM + m] = count;
     }
 
     tc_fence_before();
@@ -446,36 +493,50 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tmem_dealloc(tmem_base, 512);
     }
 }
-#undef FSGPU_MMA_CHECK8
 
-// ─── gate: k'-th best approximate score of a level's list -> the next level's static gate ───
+// ─── gate: k'-th best approximate score of a level's lists -> the next level's static gate ──
 // One CTA per query.  Any subset's k'-th best is a lower bound of the full corpus' k'-th (<= k-th)
-// best, so the gate stays valid when the list overflowed (first `cap` entries are used).
+// best, so the gate stays valid when a list overflowed (its first `cap` entries are used).
+struct MmaLists {
+    const MmaCand* cand;         // [n_qblocks*ctas_per_qblock][128][cap]
+    const uint32_t* cand_count;  // [n_qblocks*ctas_per_qblock][128]
+    uint32_t n_qblocks, ctas_per_qblock, cap;
+};
+// list j of query slot b lives in CTA (qb + n_qblocks*j)
+__device__ __forceinline__ size_t mma_list_slot(const MmaLists& l, uint32_t b, uint32_t j) {
+    return ((size_t)(b / kMmaM) + (size_t)l.n_qblocks * j) * kMmaM + (b % kMmaM);
+}
+
 struct MmaGateArgs {
-    const MmaCand* cand;
-    uint32_t* cand_count;   // reset to 0 for the next level
+    MmaLists lists;
     const float* margin2;
     const uint32_t* redo;
     float* gate;            // out
-    uint32_t cap, k_sel, buf_cap;
+    uint32_t k_sel, buf_cap;
     uint32_t* error_flag;
 };
 
+// CTA-collective: pushes every entry of every list of query `b` through the bounded buffer.
 __device__ __forceinline__ void mma_select_topk(const CandBuf& buf, uint32_t buf_cap, uint32_t k,
-                                                const MmaCand* list, uint32_t n, uint32_t* error_flag) {
+                                                const MmaLists& l, uint32_t b, uint32_t* error_flag) {
     const uint32_t step = blockDim.x;
     const uint32_t trigger = buf_cap - step;
-    for (uint32_t base = 0; base < n; base += step) {  // CTA-uniform trip count
-        const uint64_t t = *buf.tau;
-        const uint32_t i = base + threadIdx.x;
-        if (i < n) {
-            const MmaCand c = list[i];
-            const uint64_t key = make_key(c.score, c.row);
-            if (key > t && !cand_push(buf, buf_cap, key)) atomicExch(error_flag, 1u);
+    for (uint32_t j = 0; j < l.ctas_per_qblock; ++j) {
+        const size_t slot = mma_list_slot(l, b, j);
+        const uint32_t n = min(l.cand_count[slot], l.cap);
+        const MmaCand* list = l.cand + slot * l.cap;
+        for (uint32_t base = 0; base < n; base += step) {  // CTA-uniform trip count
+            const uint64_t t = *buf.tau;
+            const uint32_t i = base + threadIdx.x;
+            if (i < n) {
+                const MmaCand c = list[i];
+                const uint64_t key = make_key(c.score, c.row);
+                if (key > t && !cand_push(buf, buf_cap, key)) atomicExch(error_flag, 1u);
+            }
+            __syncthreads();
+            if (*buf.cnt > trigger) cand_compact(buf, buf_cap, k);
+            __syncthreads();
         }
-        __syncthreads();
-        if (*buf.cnt > trigger) cand_compact(buf, buf_cap, k);
-        __syncthreads();
     }
     cand_compact(buf, buf_cap, k);
 }
@@ -493,23 +554,20 @@ __global__ void __launch_bounds__(256) mma_gate_kernel(const MmaGateArgs args) {
     }
     __syncthreads();
     const CandBuf buf{cand, cnt, tau};
-    const uint32_t n = min(args.cand_count[b], args.cap);
-    mma_select_topk(buf, args.buf_cap, args.k_sel, args.cand + (size_t)b * args.cap, n, args.error_flag);
+    mma_select_topk(buf, args.buf_cap, args.k_sel, args.lists, b, args.error_flag);
     if (threadIdx.x == 0) {
         float gate = -INFINITY;
         if (*cnt >= args.k_sel) gate = __fsub_rd(key_score(cand[args.k_sel - 1]), args.margin2[b]);
         args.gate[b] = gate;
-        args.cand_count[b] = 0u;
     }
 }
 
 // ─── refine: exact re-scoring of the candidate superset, one CTA per query ──────────────────
 struct MmaRefineArgs {
-    const MmaCand* cand;         // [slots][cap]
-    const uint32_t* cand_count;  // [slots]
+    MmaLists lists;
     const float* margin2;        // [slots]
-    uint32_t* redo;              // [slots]; set to 2 when the final list overflowed
-    uint32_t cap, k;
+    uint32_t* redo;              // [slots]; set to 2 when a final list overflowed
+    uint32_t k;
     uint32_t buf_cap;            // shared candidate buffer capacity (power of two)
     const uint16_t* slab;
     const float* queries;        // [batch, dim] f32 (the ORIGINAL queries)
@@ -527,26 +585,30 @@ __global__ void __launch_bounds__(256) mma_refine_kernel(const MmaRefineArgs arg
     uint64_t* cand = reinterpret_cast<uint64_t*>(smem_raw);
     uint64_t* tau = cand + args.buf_cap;
     uint32_t* cnt = reinterpret_cast<uint32_t*>(tau + 1);
+    __shared__ int s_overflow;
     const uint32_t b = blockIdx.x;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t step = blockDim.x;
+    const MmaLists& l = args.lists;
     if (args.redo[b] != 0u) return;  // the caller re-runs this query on the exact path
-    const uint32_t n = args.cand_count[b];
-    if (n > args.cap) {  // the superset is incomplete: exact path
-        if (threadIdx.x == 0) args.redo[b] = 2u;
-        return;
-    }
     if (threadIdx.x == 0) {
         *cnt = 0u;
         *tau = 0ull;
+        s_overflow = 0;
     }
     __syncthreads();
+    for (uint32_t j = threadIdx.x; j < l.ctas_per_qblock; j += step)
+        if (l.cand_count[mma_list_slot(l, b, j)] > l.cap) s_overflow = 1;
+    __syncthreads();
+    if (s_overflow) {  // the superset is incomplete: exact path
+        if (threadIdx.x == 0) args.redo[b] = 2u;
+        return;
+    }
     const CandBuf buf{cand, cnt, tau};
     const uint32_t trigger = args.buf_cap - step;
-    const MmaCand* list = args.cand + (size_t)b * args.cap;
 
-    // pass 1: tau_a = k-th best APPROXIMATE key of the list
-    mma_select_topk(buf, args.buf_cap, args.k, list, n, args.error_flag);
+    // pass 1: tau_a = k-th best APPROXIMATE key over the lists
+    mma_select_topk(buf, args.buf_cap, args.k, l, b, args.error_flag);
     float gate = -INFINITY;
     if (*cnt >= args.k) gate = __fsub_rd(key_score(cand[args.k - 1]), args.margin2[b]);
     __syncthreads();
@@ -558,32 +620,37 @@ __global__ void __launch_bounds__(256) mma_refine_kernel(const MmaRefineArgs arg
 
     // pass 2: every entry inside the band is re-scored exactly and competes on its exact key
     const float* q = args.queries + (size_t)b * args.dim;
-    for (uint32_t base = 0; base < n; base += step) {
-        const uint32_t i = base + threadIdx.x;
-        MmaCand c;
-        c.score = -INFINITY;
-        c.row = 0;
-        bool pass = false;
-        if (i < n) {
-            c = list[i];
-            pass = c.score >= gate;
-        }
-        uint32_t mask = __ballot_sync(0xffffffffu, pass);
-        while (mask) {
-            const uint32_t src = __ffs(mask) - 1u;
-            mask &= mask - 1u;
-            const uint32_t grow = __shfl_sync(0xffffffffu, c.row, src);
-            const uint64_t local = (uint64_t)grow - args.row_base;
-            const float s = warp_exact_dot(args.slab + local * args.dim, q, args.dim, args.reduce_order,
-                                           args.tail_fma);
-            if (lane == 0) {
-                const uint64_t exact = make_key(s, grow);
-                if (exact > *tau && !cand_push(buf, args.buf_cap, exact)) atomicExch(args.error_flag, 1u);
+    for (uint32_t j = 0; j < l.ctas_per_qblock; ++j) {
+        const size_t slot = mma_list_slot(l, b, j);
+        const uint32_t n = l.cand_count[slot];
+        const MmaCand* list = l.cand + slot * l.cap;
+        for (uint32_t base = 0; base < n; base += step) {
+            const uint32_t i = base + threadIdx.x;
+            MmaCand c;
+            c.score = -INFINITY;
+            c.row = 0;
+            bool pass = false;
+            if (i < n) {
+                c = list[i];
+                pass = c.score >= gate;
             }
+            uint32_t mask = __ballot_sync(0xffffffffu, pass);
+            while (mask) {
+                const uint32_t src = __ffs(mask) - 1u;
+                mask &= mask - 1u;
+                const uint32_t grow = __shfl_sync(0xffffffffu, c.row, src);
+                const uint64_t local = (uint64_t)grow - args.row_base;
+                const float s = warp_exact_dot(args.slab + local * args.dim, q, args.dim, args.reduce_order,
+                                               args.tail_fma);
+                if (lane == 0) {
+                    const uint64_t exact = make_key(s, grow);
+                    if (exact > *tau && !cand_push(buf, args.buf_cap, exact)) atomicExch(args.error_flag, 1u);
+                }
+            }
+            __syncthreads();
+            if (*cnt > trigger) cand_compact(buf, args.buf_cap, args.k);
+            __syncthreads();
         }
-        __syncthreads();
-        if (*cnt > trigger) cand_compact(buf, args.buf_cap, args.k);
-        __syncthreads();
     }
     cand_compact(buf, args.buf_cap, args.k);
     const uint32_t count = *cnt;
