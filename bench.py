@@ -44,6 +44,8 @@ def parse_args():
     p.add_argument("--cpu-rows", type=int, default=0, help="rows of the CPU sample (0 = same as --rows)")
     p.add_argument("--cpu-queries", type=int, default=4, help="queries per CPU step (a sample of the batch)")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--hbm-batch", type=int, default=128,
+                   help="also time the HBM-bound regime with this many queries per pass (0 = skip)")
     return p.parse_args()
 
 
@@ -52,7 +54,7 @@ def workload_config(a, n_gpus):
         "workload": f"configs[2]: {a.rows} docs x {a.dim}-dim f16, batch {a.batch} queries, exact cosine top-{a.k}",
         "rows": a.rows, "dim": a.dim, "batch": a.batch, "k": a.k,
         "corpus": "clustered (64 centroids, noise 0.30) — reference bench generator fsvi_int8_two_pass.rs:199-231",
-        "storage": "f16 slab, f32 query, f32 accumulate (reference accumulation tree, bit-exact)",
+        "storage": "f16 slab, f32 query; tensor-core candidate pass (f16 x f16 -> f32) + exact re-scoring with the reference accumulation tree (bit-exact results)",
         "sharding": "single GPU" if n_gpus == 1 else f"rows sharded over {n_gpus} ranks, one all-gather of top-k keys",
         "l2": "inputs larger than L2 (slab per GPU >> 126 MB); no explicit flush",
     }
@@ -265,6 +267,36 @@ def run_ours(a):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = a.batch * a.steps / float(t.item())
 
+    # the HBM-bound regime of the same kernel: one query block (<= 128 queries) per corpus pass
+    hbm = None
+    if a.hbm_batch > 0:
+        qb = d_queries[: min(a.hbm_batch, a.batch)].contiguous()
+
+        def step_hbm():
+            if sharded is not None:
+                return sharded.search_top_k_device(qb, a.k)
+            return ix.search_top_k_device(qb, a.k, want_hits=True)
+
+        for _ in range(3):
+            step_hbm()
+        barrier()
+        ix.profile_read(reset=True)
+        ix.profile_enable(True)
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0.record()
+        for _ in range(a.steps):
+            step_hbm()
+        h1.record()
+        barrier()
+        hp = ix.profile_read(reset=True)
+        ix.profile_enable(False)
+        h_ms = hp["scan_ms"] / max(hp["scan_launches"], 1)
+        hbm = {"batch": int(qb.shape[0]), "avg_launch_ms": h_ms,
+               "bytes_per_launch": hp["scan_bytes"] / max(hp["scan_launches"], 1),
+               "achieved_gbs": hp["scan_bytes"] / max(hp["scan_launches"], 1) / (h_ms * 1e-3) / 1e9 if h_ms else 0.0,
+               "ms_per_step": h0.elapsed_time(h1) / a.steps,
+               "kernel": "mma_scan_kernel" if hp["mma_launches"] else "scan_topk_fast_kernel"}
+
     # sanity: the timed result is a real answer (sorted keys, k hits per query)
     keys = out[0]
     assert bool((keys[:, :-1] > keys[:, 1:]).all().item()) if a.k > 1 else True, "result keys are not sorted"
@@ -276,11 +308,13 @@ def run_ours(a):
         except (OSError, ValueError):
             pass
         peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        peak_tf = float(peaks.get("bf16_tflops", 1590.0))
+        peak_tf_sus = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md: 6650 GB/s, 1590 TFLOP/s)"
         scan_launches = max(prof["scan_launches"], 1)
         avg_ms = prof["scan_ms"] / scan_launches
         bytes_per_launch = prof["scan_bytes"] / scan_launches
-        achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+        hbm_achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
         traffic = None
         tp = os.path.join(ROOT, "profiles", "scan_kernel_traffic.json")
         if os.path.exists(tp):
@@ -288,17 +322,37 @@ def run_ours(a):
                 traffic = json.load(open(tp)).get("dram_bytes_per_launch")
             except (OSError, ValueError):
                 traffic = None
+        if prof["mma_launches"]:
+            # a 1024-query batch is a dense [B,D]x[D,N] contraction: tensor-bound
+            flops = prof["mma_flops"] / prof["mma_launches"]
+            achieved_tf = flops / (avg_ms * 1e-3) / 1e12 if avg_ms > 0 else 0.0
+            roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                        "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic,
+                        "kernel": "mma_scan_kernel (tcgen05.mma kind::f16, M=128 queries x N=128 rows, K=dim)",
+                        "flops_per_launch": flops, "frac_of_sustained_peak": achieved_tf / peak_tf_sus,
+                        "peak_sustained": peak_tf_sus,
+                        "hbm_gbs_same_launch": hbm_achieved, "hbm_frac_same_launch": hbm_achieved / peak_gbs}
+        else:
+            roofline = {"bound": "hbm", "achieved": hbm_achieved, "peak": peak_gbs, "unit": "GB/s",
+                        "frac": hbm_achieved / peak_gbs if peak_gbs else None, "traffic": traffic,
+                        "kernel": "scan_topk_fast_kernel"}
+        roofline.update({"launches_timed": prof["scan_launches"], "avg_launch_ms": avg_ms,
+                         "bytes_per_launch": bytes_per_launch,
+                         "queries_per_launch": a.batch * a.steps / scan_launches, "peak_source": peak_src,
+                         "scan_share_of_step": prof["scan_ms"] / elapsed_ms if elapsed_ms else None,
+                         "redo_queries": prof["redo_queries"]})
+        if hbm is not None:
+            hbm["peak_gbs"] = peak_gbs
+            hbm["frac"] = hbm["achieved_gbs"] / peak_gbs if peak_gbs else None
+            hbm["note"] = ("same kernel, one 128-query block per corpus pass: the HBM-bound regime "
+                           "(algorithmic bytes = rows*dim*2 per launch)")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(a, world),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                         "frac": achieved / peak_gbs if peak_gbs else None, "traffic": traffic,
-                         "kernel": "scan_topk_fast_kernel", "launches_timed": prof["scan_launches"],
-                         "avg_launch_ms": avg_ms, "bytes_per_launch": bytes_per_launch,
-                         "queries_per_launch": a.batch * a.steps / scan_launches, "peak_source": peak_src,
-                         "scan_share_of_step": prof["scan_ms"] / elapsed_ms if elapsed_ms else None},
+            "roofline": roofline,
+            "roofline_hbm_regime": hbm,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": a.batch * a.dim * 4,
                     "d2h_bytes_per_step": a.batch * a.k * 8 + a.batch * 4},
             "gpu_launches": prof["scan_launches"] + prof["merge_launches"] + prof["other_launches"],
