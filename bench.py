@@ -34,7 +34,7 @@ UNIT = "queries/s"
 def parse_args():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--rows", type=int, default=10_000_000)
@@ -126,49 +126,71 @@ def run_reference(a):
 
 # ── clocks ────────────────────────────────────────────────────────────────────────────────────
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled every ~5 ms through NVML while a timed region runs
+    (nvidia-smi -lms cannot sample a 40 ms region); falls back to nvidia-smi if NVML is missing."""
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20,
+               "hw_thermal_slowdown": 0x40, "hw_power_brake_slowdown": 0x80}
 
     def __init__(self, gpu_index: int):
-        self.rows = []
-        self.proc = None
+        self.sm, self.mask, self.max_mhz = [], 0, None
+        self.stop_flag = threading.Event()
+        self.nvml = None
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
-                 "-i", str(gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(gpu_index))
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+    @staticmethod
+    def _physical_index(i):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            parts = [p.strip() for p in vis.split(",") if p.strip()]
+            if i < len(parts) and parts[i].isdigit():
+                return int(parts[i])
+        return i
+
+    def _run(self):
+        if self.nvml is not None:
+            n = self.nvml
+            while not self.stop_flag.is_set():
+                try:
+                    self.sm.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+                    self.mask |= int(n.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    try:
+                        self.mask |= int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                    except Exception:
+                        pass
+                time.sleep(0.004)
+            return
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm,"
+                                      "clocks_event_reasons.hw_slowdown,clocks_event_reasons.sw_power_cap,"
+                                      "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.hw_thermal_slowdown",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.splitlines()[0].split(",")]
+                self.sm.append(float(parts[0]))
+                self.max_mhz = float(parts[1])
+                for name, v in zip(("hw_slowdown", "sw_power_cap", "sw_thermal_slowdown", "hw_thermal_slowdown"), parts[2:6]):
+                    if v.lower().startswith("active"):
+                        self.mask |= self.REASONS[name]
+            except Exception:
+                return
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            parts = [x.strip() for x in r.split(",")]
-            if len(parts) < 6:
-                continue
-            try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
-            except ValueError:
-                continue
-            for name, v in zip(names, parts[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        self.stop_flag.set()
+        self.thread.join(timeout=6)
+        reasons = sorted(name for name, bit in self.REASONS.items() if self.mask & bit)
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_min_mhz": min(self.sm) if self.sm else None,
+                "sm_max_mhz": self.max_mhz, "samples": len(self.sm), "reasons": reasons,
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ── our arm ───────────────────────────────────────────────────────────────────────────────────

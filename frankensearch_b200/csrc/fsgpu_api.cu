@@ -419,27 +419,28 @@ static int search_exact_locked(const fsgpu_index* ix, const float* d_queries, ui
 // selection rank k' used for intermediate gates, and the per-query list capacity.
 struct MmaCascade {
     uint64_t n_tiles = 0, t0 = 0, t1 = 0;  // t1 == 0: two levels only; t0 == n_tiles: one level
-    uint32_t k_sel = 16;
+    uint32_t k_sel = 16, tile_rows = kMmaN;
     double slack = 6.0, random_part = 0.0;  // expected gate-clearing rows per query and level
-    // capacity of one (CTA, query) list when `g` CTAs share a query block
+    // capacity of one (CTA, query) list when `g` CTAs (or CTA pairs) share a query block
     uint32_t list_cap(uint32_t g) const {
-        const uint64_t dump = (t0 + g - 1) / g * kMmaN;  // level 0 keeps every score of its tiles
+        const uint64_t dump = (t0 + g - 1) / g * tile_rows;  // level 0 keeps every score of its tiles
         const uint64_t rnd = (uint64_t)std::min(slack * random_part / g, 4194304.0) + 64;
         return (uint32_t)((std::max(dump, rnd) + 63) / 64 * 64);
     }
 };
 
-static MmaCascade plan_cascade(uint64_t n_rows, uint32_t k) {
+static MmaCascade plan_cascade(uint64_t n_rows, uint32_t k, uint32_t tile_rows) {
     // Appends per query: level 0 keeps all t0*128 sample scores (deterministic); level 1 expects
     // k' * t1/t0 and level 2 k' * n_tiles/t1, both minimised by t1 = sqrt(t0 * n_tiles) at
     // L = k' * sqrt(n_tiles/t0).  t0 balances the deterministic dump against slack * L.
     MmaCascade c;
-    c.n_tiles = (n_rows + kMmaN - 1) / kMmaN;
+    c.tile_rows = tile_rows;
+    c.n_tiles = (n_rows + tile_rows - 1) / tile_rows;
     c.k_sel = std::max(k, 16u);
     c.slack = std::max(2, env_int("FSGPU_MMA_LIST_SLACK", 6));
-    const double t0_bal = std::pow(c.slack * c.k_sel * std::sqrt((double)c.n_tiles) / kMmaN, 2.0 / 3.0);
-    const uint64_t t0_min = ((uint64_t)8 * c.k_sel + kMmaN - 1) / kMmaN;
-    c.t0 = std::min<uint64_t>(c.n_tiles, std::max<uint64_t>({16, t0_min, (uint64_t)std::ceil(t0_bal)}));
+    const double t0_bal = std::pow(c.slack * c.k_sel * std::sqrt((double)c.n_tiles) / tile_rows, 2.0 / 3.0);
+    const uint64_t t0_min = ((uint64_t)8 * c.k_sel + tile_rows - 1) / tile_rows;
+    c.t0 = std::min<uint64_t>(c.n_tiles, std::max<uint64_t>({(uint64_t)2048 / tile_rows, t0_min, (uint64_t)std::ceil(t0_bal)}));
     if (c.n_tiles > 8 * c.t0) {
         c.t1 = (uint64_t)std::llround(std::sqrt((double)c.t0 * (double)c.n_tiles));
         c.t1 = std::min(c.n_tiles, std::max(c.t1, 2 * c.t0));
@@ -465,19 +466,27 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
     if (stage_cap >= 2) n_stages = std::min<uint32_t>(n_stages, (uint32_t)stage_cap);
     if (n_stages < 2) return fail(FSGPU_ERR_INVALID_CONFIG, "batched scan does not fit in shared memory (dim=%u)", ix->dim);
     const size_t smem = mma_scan_smem_bytes(n_kb, n_stages);
-    CUDA_TRY(cudaFuncSetAttribute(mma_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const MmaCascade cas = plan_cascade(ix->n_rows, k);
+    // CTA-pair form (cta_group::2, 256 queries x 256 rows per MMA) unless FSGPU_MMA_PAIR=0
+    // ... and unless the batch is a single 128-query block: that regime is HBM-bound and the
+    // single-CTA form streams it faster (6.7 vs 5.8 TB/s at 10 M x 384, profiles/r01_sweep_mma_v6.txt)
+    const bool pair = env_int("FSGPU_MMA_PAIR", 1) != 0 && ix->num_sms >= 2 && batch > kMmaM;
+    auto scan_kernel = pair ? mma_scan_pair_kernel : mma_scan_kernel;
+    CUDA_TRY(cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint32_t units = pair ? (uint32_t)ix->num_sms / 2 : (uint32_t)ix->num_sms;  // CTAs or CTA pairs
+    const uint32_t unit_queries = pair ? 2 * kMmaM : kMmaM;
+    const MmaCascade cas = plan_cascade(ix->n_rows, k, pair ? kPairN : kMmaN);
     const uint32_t sel_cap = cand_capacity(cas.k_sel), fin_cap = cand_capacity(k);
     CUDA_TRY(cudaFuncSetAttribute(mma_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sel_cap * 8 + 16)));
     CUDA_TRY(cudaFuncSetAttribute(mma_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(fin_cap * 8 + 16)));
 
-    const uint32_t max_queries = (uint32_t)ix->num_sms * kMmaM;
+    const uint32_t max_queries = units * unit_queries;
     std::vector<uint32_t> redo_host;
     for (uint32_t done = 0; done < batch; done += max_queries) {
         const uint32_t sub = std::min(max_queries, batch - done);
-        const uint32_t n_qb = (sub + kMmaM - 1) / kMmaM;
-        const uint32_t g = (uint32_t)ix->num_sms / n_qb;
-        const uint32_t grid = g * n_qb;
+        const uint32_t n_units = (sub + unit_queries - 1) / unit_queries;  // query blocks or query pairs
+        const uint32_t n_qb = pair ? 2 * n_units : n_units;                // 128-query blocks incl. padding
+        const uint32_t g = units / n_units;
+        const uint32_t grid = g * n_units * (pair ? 2 : 1);
         const uint32_t slots = n_qb * kMmaM;
         CUDA_TRY(ix->ws_qhat.reserve((size_t)slots * ix->dim * 2));
         CUDA_TRY(ix->ws_margin.reserve((size_t)slots * 4));
@@ -512,7 +521,7 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
         a.cand_count = ix->ws_cand_count.as<uint32_t>();
         a.cap = cap;
         MmaGateArgs ga{};
-        ga.lists = MmaLists{a.cand, a.cand_count, n_qb, g, cap};
+        ga.lists = MmaLists{a.cand, a.cand_count, n_qb, g, cap, pair ? 1u : 0u};
         ga.margin2 = ix->ws_margin.as<float>();
         ga.redo = a.redo;
         ga.gate = ix->ws_gate.as<float>();
@@ -528,7 +537,7 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
             a.tile_stride = env_int("FSGPU_MMA_SAMPLE_CONTIG", 0) ? 1 : cas.n_tiles / level_tiles[lvl];
             a.tile_count = level_tiles[lvl];
             a.gate = have_gate ? ix->ws_gate.as<float>() : nullptr;
-            mma_scan_kernel<<<grid, kMmaThreads, smem, stream>>>(ix->tm_qhat, ix->tm_slab, a);
+            scan_kernel<<<grid, kMmaThreads, smem, stream>>>(ix->tm_qhat, ix->tm_slab, a);
             CUDA_TRY(cudaGetLastError());
             mma_gate_kernel<<<sub, 256, sel_cap * 8 + 16, stream>>>(ga);
             CUDA_TRY(cudaGetLastError());
@@ -550,7 +559,7 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
             }
             CUDA_TRY(cudaEventRecord(ev.first, stream));
         }
-        mma_scan_kernel<<<grid, kMmaThreads, smem, stream>>>(ix->tm_qhat, ix->tm_slab, a);
+        scan_kernel<<<grid, kMmaThreads, smem, stream>>>(ix->tm_qhat, ix->tm_slab, a);
         CUDA_TRY(cudaGetLastError());
         if (ix->profiling) {
             CUDA_TRY(cudaEventRecord(ev.second, stream));

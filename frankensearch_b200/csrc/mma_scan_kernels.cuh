@@ -158,6 +158,63 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                  : "memory");
 }
+// ---- CTA-pair (cta_group::2) forms: one MMA spans the two SMs of a TPC -----------------------
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // shared::cluster address of the same offset in CTA rank 0
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose completion bytes are posted on the LEADER CTA's barrier (the barrier may live in
+// the other CTA of the pair than the destination tile).
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int32_t c0,
+                                                 int32_t c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(tm), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
+        : "memory");
+}
+// Arrive on the barrier at the same offset in CTA `rank` of the cluster.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
+    asm volatile(
+        "{\n"
+        ".reg .b32 remote;\n"
+        "mapa.shared::cluster.u32 remote, %0, %1;\n"
+        "mbarrier.arrive.shared::cluster.b64 _, [remote];\n"
+        "}\n" ::"r"(bar), "r"(rank)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t slot_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[smem of both CTAs, M/2 rows each] * B[smem of both CTAs, N/2 rows each]^T
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Arrives on the barrier at this offset in BOTH CTAs when the pair's MMAs issued so far retire.
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(bar), "h"((uint16_t)3)
+        : "memory");
+}
+
 // 32 consecutive accumulator columns of this thread's TMEM lane.
 __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
@@ -319,6 +376,45 @@ __device__ __forceinline__ uint32_t mma_hot_bits(const uint32_t (&v)[32], float 
            mma_hot_bit(v, 16, gate, 4u << shift) | mma_hot_bit(v, 24, gate, 8u << shift);
 }
 
+// One accumulator tile of COLS columns for this thread's query.  Fast path: COLS/8 groups of 8
+// columns -> one "some column clears the gate" bit each.  Slow path (rare): the warp re-reads each
+// hot group and the owning lanes append — one compact copy of the append code instead of COLS
+// unrolled ones (instruction cache).
+template <int COLS>
+__device__ __forceinline__ void mma_epilogue_tile(const MmaScanArgs& args, uint32_t taddr, uint64_t tile_row0,
+                                                  float gate, MmaCand* list, uint32_t& count) {
+    static_assert(COLS % 64 == 0 && COLS <= 256, "hot mask is 32 bits of 8-column groups");
+    uint32_t va[32], vb[32];
+    uint32_t hot = 0;
+    tmem_ld_x32(taddr, va);
+#pragma unroll
+    for (int c = 0; c < COLS / 32; c += 2) {
+        tmem_ld_wait();
+        tmem_ld_x32(taddr + (c + 1) * 32u, vb);  // in flight while the previous chunk is reduced
+        hot |= mma_hot_bits(va, gate, 4 * c);
+        tmem_ld_wait();
+        if (c + 2 < COLS / 32) tmem_ld_x32(taddr + (c + 2) * 32u, va);
+        hot |= mma_hot_bits(vb, gate, 4 * (c + 1));
+    }
+    uint32_t hot_warp = __reduce_or_sync(0xffffffffu, hot);
+#pragma unroll 1
+    while (hot_warp) {
+        const uint32_t grp = __ffs(hot_warp) - 1u;
+        hot_warp &= hot_warp - 1u;
+        uint32_t w[8];
+        tmem_ld_x8(taddr + grp * 8u, w);
+        tmem_ld_wait();
+        if (hot & (1u << grp)) {
+            const uint64_t row0 = tile_row0 + grp * 8u;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float s8 = __uint_as_float(w[i]);
+                if (s8 >= gate) mma_append(args, list, count, s8, row0 + (uint32_t)i);
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kMmaThreads, 1)
 mma_scan_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_x,
                 const MmaScanArgs args) {
@@ -441,40 +537,7 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * kMmaN;
-            // fast path: 16 groups of 8 columns -> one "some column clears the gate" bit each
-            uint32_t va[32], vb[32];
-            uint32_t hot = 0;
-            tmem_ld_x32(taddr, va);
-            tmem_ld_wait();
-            tmem_ld_x32(taddr + 32u, vb);  // in flight while the previous chunk is reduced
-            hot |= mma_hot_bits(va, gate, 0);
-            tmem_ld_wait();
-            tmem_ld_x32(taddr + 64u, va);
-            hot |= mma_hot_bits(vb, gate, 4);
-            tmem_ld_wait();
-            tmem_ld_x32(taddr + 96u, vb);
-            hot |= mma_hot_bits(va, gate, 8);
-            tmem_ld_wait();
-            hot |= mma_hot_bits(vb, gate, 12);
-            // slow path (rare): the warp re-reads each hot group and the owning lanes append.  One
-            // compact copy of the append code instead of 128 unrolled ones (instruction cache).
-            uint32_t hot_warp = __reduce_or_sync(0xffffffffu, hot);
-#pragma unroll 1
-            while (hot_warp) {
-                const uint32_t grp = __ffs(hot_warp) - 1u;
-                hot_warp &= hot_warp - 1u;
-                uint32_t w[8];
-                tmem_ld_x8(taddr + grp * 8u, w);
-                tmem_ld_wait();
-                if (hot & (1u << grp)) {
-                    const uint64_t row0 = tile * kMmaN + grp * 8u;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float s8 = __uint_as_float(w[i]);
-                        if (s8 >= gate) mma_append(args, list, count, s8, row0 + (uint32_t)i);
-                    }
-                }
-            }
+            mma_epilogue_tile<kMmaN>(args, taddr, tile * kMmaN, gate, list, count);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));  // accumulator drained -> MMA may reuse it
@@ -494,17 +557,180 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
 }
 
+// ─── the scan, CTA-pair form ────────────────────────────────────────────────────────────────
+// Two CTAs of a cluster (the two SMs of a TPC) run ONE tcgen05.mma.cta_group::2 of M = 256
+// queries (128 per CTA, each CTA's q_hat tile in its own shared memory and its accumulators in
+// its own TMEM) by N = 256 corpus rows (each CTA TMA-loads 128 of them).  Every slab byte is
+// fetched from L2 once per 256 queries and read from shared memory once per 256-query MMA: half
+// the L2->SM and shared-memory traffic per flop of the single-CTA form, which ran at the L2->SM
+// fabric limit (profiles/r01_mma_v5_b1024_ncu.json: 54 % tensor-pipe active, time unchanged when
+// half the MMAs were dropped).  Rank 0 (leader) issues the MMAs; barriers: `full`/`a_full`/
+// `tmem_empty` live on the leader, `empty`/`tmem_full` are signalled in both CTAs by multicast
+// commits.
+constexpr int kPairN = 256;
+constexpr int kPairAccStages = 2;  // 2 x 256 TMEM columns
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMmaThreads, 1)
+mma_scan_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_x,
+                     const MmaScanArgs args) {
+    extern __shared__ uint8_t smem_dyn[];
+    const uint32_t raw = smem_u32(smem_dyn);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_dyn + (base - raw);
+    const uint32_t a_smem = base;
+    const uint32_t b_smem = a_smem + args.n_kblocks * kMmaTileBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base_ptr + (size_t)(args.n_kblocks + args.n_stages) * kMmaTileBytes);
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](uint32_t s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](uint32_t s) { return bar0 + 8u * (8u + s); };
+    auto tfull_bar = [&](uint32_t a) { return bar0 + 8u * (16u + a); };
+    auto tempty_bar = [&](uint32_t a) { return bar0 + 8u * (20u + a); };
+    const uint32_t afull_bar = bar0 + 8u * 24u;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const uint32_t pair = blockIdx.x >> 1;
+    const uint32_t n_qpairs = args.n_qblocks >> 1;  // n_qblocks is even
+    const uint32_t qb = (pair % n_qpairs) * 2u + rank;
+    const uint32_t j0 = pair / n_qpairs;
+    const uint32_t g = args.ctas_per_qblock;  // CTA pairs per query pair
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_q);
+        tma_prefetch_desc(&tm_x);
+        for (uint32_t s = 0; s < args.n_stages; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (uint32_t a = 0; a < kPairAccStages; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 8);  // one arrival per epilogue warp of BOTH CTAs
+        }
+        mbar_init(afull_bar, 1);
+        fence_barrier_init();
+    } else if (warp == 2) {
+        tmem_alloc_pair(smem_u32(tmem_slot), 512);
+    }
+    tc_fence_before();
+    cluster_sync_all();  // barrier inits and TMEM allocations of both CTAs are visible
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs; completion bytes land on the leader's barriers) =====
+        if (elect_one()) {
+            if (rank == 0) mbar_expect_tx(afull_bar, 2u * args.n_kblocks * kMmaTileBytes);
+            for (uint32_t kb = 0; kb < args.n_kblocks; ++kb)
+                tma_load_2d_pair(a_smem + kb * kMmaTileBytes, &tm_q, afull_bar, (int32_t)(kb * kMmaKBlock),
+                                 (int32_t)(qb * kMmaM));
+        }
+        __syncwarp();
+        uint32_t stage = 0, phase = 0;
+        for (uint64_t i = j0; i < args.tile_count; i += g) {
+            const int32_t row_coord = (int32_t)(mma_tile_of(args, i) * kPairN + rank * kMmaN);
+            for (uint32_t kb = 0; kb < args.n_kblocks; ++kb) {
+                mbar_wait(empty_bar(stage), phase ^ 1u);
+                if (elect_one()) {
+                    if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * kMmaTileBytes);
+                    tma_load_2d_pair(b_smem + stage * kMmaTileBytes, &tm_x, full_bar(stage),
+                                     (int32_t)(kb * kMmaKBlock), row_coord);
+                }
+                __syncwarp();
+                if (++stage == args.n_stages) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0) {
+            // ===== MMA issuer (leader CTA only) =====
+            constexpr uint32_t idesc = umma_idesc_f16(2 * kMmaM, kPairN);
+            const uint64_t a_desc0 = umma_desc_sw128(a_smem);
+            const uint64_t b_desc0 = umma_desc_sw128(b_smem);
+            mbar_wait(afull_bar, 0);
+            tc_fence_after();
+            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            for (uint64_t i = j0; i < args.tile_count; i += g) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * kPairN;
+                for (uint32_t kb = 0; kb < args.n_kblocks; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint64_t a_desc = a_desc0 + (uint64_t)(kb * (kMmaTileBytes >> 4));
+                        const uint64_t b_desc = b_desc0 + (uint64_t)(stage * (kMmaTileBytes >> 4));
+#pragma unroll
+                        for (uint32_t k4 = 0; k4 < kMmaKBlock / 16; ++k4)
+                            umma_f16_pair(d_tmem, a_desc + 2u * k4, b_desc + 2u * k4, idesc, (kb | k4) != 0u ? 1u : 0u);
+                        umma_commit_pair(empty_bar(stage));  // frees this stage in BOTH CTAs
+                        if (kb + 1 == args.n_kblocks) umma_commit_pair(tfull_bar(acc));
+                    }
+                    __syncwarp();
+                    if (++stage == args.n_stages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                if (++acc == kPairAccStages) {
+                    acc = 0;
+                    acc_phase ^= 1u;
+                }
+            }
+        }
+    } else {
+        // ===== epilogue (both CTAs): TMEM lane = query of this CTA, column = row of the pair tile =====
+        const uint32_t quarter = warp & 3u;
+        const uint32_t m = quarter * 32u + lane;
+        const uint32_t query = qb * kMmaM + m;
+        const bool live = query < args.batch && args.redo[query] == 0u;
+        const float gate = live ? (args.gate ? args.gate[query] : -INFINITY) : INFINITY;
+        MmaCand* list = args.cand + ((size_t)blockIdx.x * kMmaM + m) * args.cap;
+        uint32_t count = 0;
+        uint32_t acc = 0, acc_phase = 0;
+        for (uint64_t i = j0; i < args.tile_count; i += g) {
+            const uint64_t tile = mma_tile_of(args, i);
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * kPairN;
+            mma_epilogue_tile<kPairN>(args, taddr, tile * kPairN, gate, list, count);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tempty_bar(acc), 0);  // leader may reuse the accumulator
+            if (++acc == kPairAccStages) {
+                acc = 0;
+                acc_phase ^= 1u;
+            }
+        }
+        args.cand_count[(size_t)blockIdx.x * kMmaM + m] = count;
+    }
+
+    tc_fence_before();
+    cluster_sync_all();  // neither CTA may leave while the other can still signal it
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, 512);
+    }
+}
+
 // ─── gate: k'-th best approximate score of a level's lists -> the next level's static gate ──
 // One CTA per query.  Any subset's k'-th best is a lower bound of the full corpus' k'-th (<= k-th)
 // best, so the gate stays valid when a list overflowed (its first `cap` entries are used).
 struct MmaLists {
-    const MmaCand* cand;         // [n_qblocks*ctas_per_qblock][128][cap]
-    const uint32_t* cand_count;  // [n_qblocks*ctas_per_qblock][128]
+    const MmaCand* cand;         // [grid][128][cap]
+    const uint32_t* cand_count;  // [grid][128]
     uint32_t n_qblocks, ctas_per_qblock, cap;
+    uint32_t pair;               // 1: lists were written by mma_scan_pair_kernel
 };
-// list j of query slot b lives in CTA (qb + n_qblocks*j)
+// list j of query slot b: single-CTA form -> CTA (qb + n_qblocks*j); pair form -> CTA
+// 2*(qb/2 + (n_qblocks/2)*j) + qb%2
 __device__ __forceinline__ size_t mma_list_slot(const MmaLists& l, uint32_t b, uint32_t j) {
-    return ((size_t)(b / kMmaM) + (size_t)l.n_qblocks * j) * kMmaM + (b % kMmaM);
+    const uint32_t qb = b / kMmaM;
+    const size_t cta = l.pair ? 2 * ((size_t)(qb >> 1) + (size_t)(l.n_qblocks >> 1) * j) + (qb & 1u)
+                              : (size_t)qb + (size_t)l.n_qblocks * j;
+    return cta * kMmaM + (b % kMmaM);
 }
 
 struct MmaGateArgs {
