@@ -422,9 +422,10 @@ struct MmaCascade {
     uint32_t k_sel = 16, tile_rows = kMmaN;
     double slack = 6.0, random_part = 0.0;  // expected gate-clearing rows per query and level
     // capacity of one (CTA, query) list when `g` CTAs (or CTA pairs) share a query block
+    // (each CTA keeps two lists per query, one per half of the tile's columns)
     uint32_t list_cap(uint32_t g) const {
-        const uint64_t dump = (t0 + g - 1) / g * tile_rows;  // level 0 keeps every score of its tiles
-        const uint64_t rnd = (uint64_t)std::min(slack * random_part / g, 4194304.0) + 64;
+        const uint64_t dump = (t0 + g - 1) / g * (tile_rows / 2);  // level 0 keeps every score of its tiles
+        const uint64_t rnd = (uint64_t)std::min(slack * random_part / (2.0 * g), 4194304.0) + 64;
         return (uint32_t)((std::max(dump, rnd) + 63) / 64 * 64);
     }
 };
@@ -475,9 +476,11 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
     const uint32_t units = pair ? (uint32_t)ix->num_sms / 2 : (uint32_t)ix->num_sms;  // CTAs or CTA pairs
     const uint32_t unit_queries = pair ? 2 * kMmaM : kMmaM;
     const MmaCascade cas = plan_cascade(ix->n_rows, k, pair ? kPairN : kMmaN);
-    const uint32_t sel_cap = cand_capacity(cas.k_sel), fin_cap = cand_capacity(k);
-    CUDA_TRY(cudaFuncSetAttribute(mma_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sel_cap * 8 + 16)));
-    CUDA_TRY(cudaFuncSetAttribute(mma_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(fin_cap * 8 + 16)));
+    const uint32_t fin_cap = cand_capacity(k);
+    const size_t gate_smem = mma_stage_smem_bytes(kMmaStageScores, false);
+    const size_t refine_smem = (size_t)fin_cap * 8 + 16 + mma_stage_smem_bytes(kMmaStagePairs, true);
+    CUDA_TRY(cudaFuncSetAttribute(mma_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gate_smem));
+    CUDA_TRY(cudaFuncSetAttribute(mma_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)refine_smem));
 
     const uint32_t max_queries = units * unit_queries;
     std::vector<uint32_t> redo_host;
@@ -493,8 +496,8 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
         CUDA_TRY(ix->ws_gate.reserve((size_t)slots * 4));
         CUDA_TRY(ix->ws_redo.reserve((size_t)slots * 4));
         const uint32_t cap = cas.list_cap(g);
-        CUDA_TRY(ix->ws_cand.reserve((size_t)grid * kMmaM * cap * sizeof(MmaCand)));
-        CUDA_TRY(ix->ws_cand_count.reserve((size_t)grid * kMmaM * 4));
+        CUDA_TRY(ix->ws_cand.reserve((size_t)grid * 2 * kMmaM * cap * sizeof(MmaCand)));
+        CUDA_TRY(ix->ws_cand_count.reserve((size_t)grid * 2 * kMmaM * 4));
         if (ix->tm_qhat_ptr != ix->ws_qhat.p || ix->tm_qhat_rows != slots) {
             if (!make_f16_tile_map(&ix->tm_qhat, ix->ws_qhat.p, slots, ix->dim, false))
                 return fail(FSGPU_ERR_SUBSYSTEM, "gpu: cuTensorMapEncodeTiled failed for the query tile");
@@ -526,8 +529,6 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
         ga.redo = a.redo;
         ga.gate = ix->ws_gate.as<float>();
         ga.k_sel = cas.k_sel;
-        ga.buf_cap = sel_cap;
-        ga.error_flag = ix->d_error;
 
         // sample levels: strided tiles, each level's k'-th best gates the next
         const uint64_t level_tiles[2] = {cas.t0 < cas.n_tiles ? cas.t0 : 0, cas.t1};
@@ -539,7 +540,7 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
             a.gate = have_gate ? ix->ws_gate.as<float>() : nullptr;
             scan_kernel<<<grid, kMmaThreads, smem, stream>>>(ix->tm_qhat, ix->tm_slab, a);
             CUDA_TRY(cudaGetLastError());
-            mma_gate_kernel<<<sub, 256, sel_cap * 8 + 16, stream>>>(ga);
+            mma_gate_kernel<<<sub, 256, gate_smem, stream>>>(ga);
             CUDA_TRY(cudaGetLastError());
             ix->prof.other_launches += 2;
             have_gate = true;
@@ -588,7 +589,7 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
         r.out_hits = d_out_hits ? d_out_hits + (size_t)done * k : nullptr;
         r.out_counts = d_out_counts ? d_out_counts + done : nullptr;
         r.error_flag = ix->d_error;
-        mma_refine_kernel<<<sub, 256, fin_cap * 8 + 16, stream>>>(r);
+        mma_refine_kernel<<<sub, 256, refine_smem, stream>>>(r);
         CUDA_TRY(cudaGetLastError());
 
         redo_host.resize(sub);

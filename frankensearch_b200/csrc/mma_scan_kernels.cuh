@@ -35,7 +35,8 @@
 
 namespace fsgpu {
 
-constexpr int kMmaThreads = 192;    // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
+constexpr int kMmaThreads = 320;    // warp 0: TMA producer, warp 1: MMA issuer, warps 2-9: epilogue
+constexpr int kMmaEpiWarps = 8;     // two warps per TMEM lane quarter, each takes half of the columns
 constexpr int kMmaM = 128;          // queries per CTA (UMMA M, cta_group::1)
 constexpr int kMmaN = 128;          // corpus rows per tile (UMMA N)
 constexpr int kMmaKBlock = 64;      // f16 elements per 128-byte swizzle row
@@ -65,8 +66,8 @@ struct MmaScanArgs {
     uint64_t tile_stride, tile_count;
     const float* gate;         // [n_qblocks*128] static per-query gate (nullptr = -inf: keep everything)
     const uint32_t* redo;      // [n_qblocks*128] != 0: query is served by the exact path, skip it
-    MmaCand* cand;             // [gridDim.x][128][cap]: one private list per (CTA, query)
-    uint32_t* cand_count;      // [gridDim.x][128] appended entries (may exceed cap = overflow)
+    MmaCand* cand;             // [gridDim.x][2][128][cap]: one private list per epilogue thread
+    uint32_t* cand_count;      // [gridDim.x][2][128] appended entries (may exceed cap = overflow)
     uint32_t cap;
 };
 
@@ -397,13 +398,9 @@ __device__ __forceinline__ void mma_epilogue_tile(const MmaScanArgs& args, uint3
         hot |= mma_hot_bits(vb, gate, 4 * (c + 1));
     }
     uint32_t hot_warp = __reduce_or_sync(0xffffffffu, hot);
-#pragma unroll 1
-    while (hot_warp) {
-        const uint32_t grp = __ffs(hot_warp) - 1u;
-        hot_warp &= hot_warp - 1u;
-        uint32_t w[8];
-        tmem_ld_x8(taddr + grp * 8u, w);
-        tmem_ld_wait();
+    if (hot_warp == 0u) return;
+    // two groups in flight: the TMEM read of the next hot group overlaps the appends of this one
+    auto check8 = [&](const uint32_t (&w)[8], uint32_t grp) {
         if (hot & (1u << grp)) {
             const uint64_t row0 = tile_row0 + grp * 8u;
 #pragma unroll
@@ -412,6 +409,31 @@ __device__ __forceinline__ void mma_epilogue_tile(const MmaScanArgs& args, uint3
                 if (s8 >= gate) mma_append(args, list, count, s8, row0 + (uint32_t)i);
             }
         }
+    };
+    uint32_t wa[8], wb[8];
+    uint32_t ga = __ffs(hot_warp) - 1u, gb;
+    hot_warp &= hot_warp - 1u;
+    tmem_ld_x8(taddr + ga * 8u, wa);
+#pragma unroll 1
+    while (true) {
+        tmem_ld_wait();
+        gb = 0xFFFFFFFFu;
+        if (hot_warp) {
+            gb = __ffs(hot_warp) - 1u;
+            hot_warp &= hot_warp - 1u;
+            tmem_ld_x8(taddr + gb * 8u, wb);
+        }
+        check8(wa, ga);
+        if (gb == 0xFFFFFFFFu) break;
+        tmem_ld_wait();
+        ga = 0xFFFFFFFFu;
+        if (hot_warp) {
+            ga = __ffs(hot_warp) - 1u;
+            hot_warp &= hot_warp - 1u;
+            tmem_ld_x8(taddr + ga * 8u, wa);
+        }
+        check8(wb, gb);
+        if (ga == 0xFFFFFFFFu) break;
     }
 }
 
@@ -448,7 +470,7 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
         for (uint32_t a = 0; a < kMmaAccStages; ++a) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), 4);  // one arrival per epilogue warp
+            mbar_init(tempty_bar(a), kMmaEpiWarps);  // one arrival per epilogue warp
         }
         mbar_init(afull_bar, 1);
         fence_barrier_init();
@@ -529,15 +551,17 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const uint32_t query = qb * kMmaM + m;
         const bool live = query < args.batch && args.redo[query] == 0u;
         const float gate = live ? (args.gate ? args.gate[query] : -INFINITY) : INFINITY;
-        MmaCand* list = args.cand + ((size_t)blockIdx.x * kMmaM + m) * args.cap;
+        const uint32_t half = (warp - 2u) >> 2;  // which half of the tile's columns this warp checks
+        const size_t list_id = ((size_t)blockIdx.x * 2u + half) * kMmaM + m;
+        MmaCand* list = args.cand + list_id * args.cap;
         uint32_t count = 0;
         uint32_t acc = 0, acc_phase = 0;
         for (uint64_t i = j0; i < args.tile_count; i += g) {
             const uint64_t tile = mma_tile_of(args, i);
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * kMmaN;
-            mma_epilogue_tile<kMmaN>(args, taddr, tile * kMmaN, gate, list, count);
+            const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * kMmaN + half * (kMmaN / 2);
+            mma_epilogue_tile<kMmaN / 2>(args, taddr, tile * kMmaN + half * (kMmaN / 2), gate, list, count);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));  // accumulator drained -> MMA may reuse it
@@ -546,7 +570,7 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 acc_phase ^= 1u;
             }
         }
-        args.cand_count[(size_t)blockIdx.x * kMmaM + m] = count;
+        args.cand_count[list_id] = count;
     }
 
     tc_fence_before();
@@ -605,7 +629,7 @@ mma_scan_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         }
         for (uint32_t a = 0; a < kPairAccStages; ++a) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), 8);  // one arrival per epilogue warp of BOTH CTAs
+            mbar_init(tempty_bar(a), 2 * kMmaEpiWarps);  // one arrival per epilogue warp of BOTH CTAs
         }
         mbar_init(afull_bar, 1);
         fence_barrier_init();
@@ -687,15 +711,17 @@ mma_scan_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         const uint32_t query = qb * kMmaM + m;
         const bool live = query < args.batch && args.redo[query] == 0u;
         const float gate = live ? (args.gate ? args.gate[query] : -INFINITY) : INFINITY;
-        MmaCand* list = args.cand + ((size_t)blockIdx.x * kMmaM + m) * args.cap;
+        const uint32_t half = (warp - 2u) >> 2;
+        const size_t list_id = ((size_t)blockIdx.x * 2u + half) * kMmaM + m;
+        MmaCand* list = args.cand + list_id * args.cap;
         uint32_t count = 0;
         uint32_t acc = 0, acc_phase = 0;
         for (uint64_t i = j0; i < args.tile_count; i += g) {
             const uint64_t tile = mma_tile_of(args, i);
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * kPairN;
-            mma_epilogue_tile<kPairN>(args, taddr, tile * kPairN, gate, list, count);
+            const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * kPairN + half * (kPairN / 2);
+            mma_epilogue_tile<kPairN / 2>(args, taddr, tile * kPairN + half * (kPairN / 2), gate, list, count);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(tempty_bar(acc), 0);  // leader may reuse the accumulator
@@ -704,7 +730,7 @@ mma_scan_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                 acc_phase ^= 1u;
             }
         }
-        args.cand_count[(size_t)blockIdx.x * kMmaM + m] = count;
+        args.cand_count[list_id] = count;
     }
 
     tc_fence_before();
@@ -715,77 +741,192 @@ mma_scan_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     }
 }
 
-// ─── gate: k'-th best approximate score of a level's lists -> the next level's static gate ──
-// One CTA per query.  Any subset's k'-th best is a lower bound of the full corpus' k'-th (<= k-th)
-// best, so the gate stays valid when a list overflowed (its first `cap` entries are used).
+// ─── candidate lists as the gate / refine kernels see them ──────────────────────────────────
 struct MmaLists {
     const MmaCand* cand;         // [grid][128][cap]
     const uint32_t* cand_count;  // [grid][128]
     uint32_t n_qblocks, ctas_per_qblock, cap;
     uint32_t pair;               // 1: lists were written by mma_scan_pair_kernel
 };
-// list j of query slot b: single-CTA form -> CTA (qb + n_qblocks*j); pair form -> CTA
-// 2*(qb/2 + (n_qblocks/2)*j) + qb%2
+// Query slot b has 2*ctas_per_qblock lists (two epilogue threads per CTA).  List j lives in CTA
+// c(j/2), half j%2, where c(i) = qb + n_qblocks*i (single-CTA form) or
+// 2*(qb/2 + (n_qblocks/2)*i) + qb%2 (pair form).
+__device__ __forceinline__ uint32_t mma_list_count(const MmaLists& l) { return 2u * l.ctas_per_qblock; }
 __device__ __forceinline__ size_t mma_list_slot(const MmaLists& l, uint32_t b, uint32_t j) {
-    const uint32_t qb = b / kMmaM;
-    const size_t cta = l.pair ? 2 * ((size_t)(qb >> 1) + (size_t)(l.n_qblocks >> 1) * j) + (qb & 1u)
-                              : (size_t)qb + (size_t)l.n_qblocks * j;
-    return cta * kMmaM + (b % kMmaM);
+    const uint32_t qb = b / kMmaM, i = j >> 1;
+    const size_t cta = l.pair ? 2 * ((size_t)(qb >> 1) + (size_t)(l.n_qblocks >> 1) * i) + (qb & 1u)
+                              : (size_t)qb + (size_t)l.n_qblocks * i;
+    return (cta * 2u + (j & 1u)) * kMmaM + (b % kMmaM);
 }
 
+// ─── staging + radix select ─────────────────────────────────────────────────────────────────
+// A query's candidates are spread over 2*ctas_per_qblock short lists.  Walking them one after
+// another costs two dependent L2 round trips per list (36-296 lists): the first versions of the
+// gate/refine kernels spent 100-500 us there.  Instead every warp takes whole lists in parallel
+// and the entries are flattened into shared memory once.
+constexpr uint32_t kMmaMaxLists = 2 * 160;      // >= 2 * SM count
+constexpr uint32_t kMmaStageScores = 16384;     // gate kernel: ordered scores only (64 KiB)
+constexpr uint32_t kMmaStagePairs = 8192;       // refine kernel: ordered score + row (64 KiB)
+
+struct MmaStageSmem {
+    uint32_t* hist;   // [256]
+    uint32_t* ctl;    // [4]
+    uint32_t* offs;   // [kMmaMaxLists + 1] exclusive offsets of the lists in the flattened array
+    uint32_t* score;  // [cap] ascending total-order image of the approximate scores
+    uint32_t* row;    // [cap] or nullptr
+    uint32_t cap;
+};
+__host__ __device__ inline size_t mma_stage_smem_bytes(uint32_t cap, bool with_rows) {
+    return (size_t)(256 + 4 + kMmaMaxLists + 4) * 4 + (size_t)cap * (with_rows ? 8 : 4);
+}
+__device__ __forceinline__ MmaStageSmem carve_stage_smem(unsigned char* base, uint32_t cap, bool with_rows) {
+    MmaStageSmem sm;
+    sm.hist = reinterpret_cast<uint32_t*>(base);
+    sm.ctl = sm.hist + 256;
+    sm.offs = sm.ctl + 4;
+    sm.score = sm.offs + kMmaMaxLists + 4;
+    sm.row = with_rows ? sm.score + cap : nullptr;
+    sm.cap = cap;
+    return sm;
+}
+
+// CTA-collective.  Returns the total number of entries (lists clipped to their capacity); the
+// flattened copy is valid iff total <= sm.cap.
+__device__ __forceinline__ uint32_t mma_stage_lists(const MmaStageSmem& sm, const MmaLists& l, uint32_t b) {
+    const uint32_t n_lists = mma_list_count(l);
+    for (uint32_t j = threadIdx.x; j < n_lists; j += blockDim.x)
+        sm.offs[j + 1] = min(l.cand_count[mma_list_slot(l, b, j)], l.cap);
+    if (threadIdx.x == 0) sm.offs[0] = 0u;
+    __syncthreads();
+    if (threadIdx.x < 32) {  // warp 0: inclusive scan of the counts, 32 at a time
+        uint32_t carry = 0;
+        for (uint32_t base = 0; base < n_lists; base += 32) {
+            const uint32_t j = base + threadIdx.x;
+            uint32_t v = j < n_lists ? sm.offs[j + 1] : 0u;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+                if ((int)threadIdx.x >= o) v += t;
+            }
+            if (j < n_lists) sm.offs[j + 1] = v + carry;
+            carry += __shfl_sync(0xffffffffu, v, 31);
+        }
+    }
+    __syncthreads();
+    const uint32_t total = sm.offs[n_lists];
+    if (total > sm.cap) return total;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+    for (uint32_t j = warp; j < n_lists; j += n_warps) {
+        const uint32_t off = sm.offs[j], n = sm.offs[j + 1] - off;
+        const MmaCand* list = l.cand + mma_list_slot(l, b, j) * l.cap;
+        for (uint32_t i = lane; i < n; i += 32) {
+            const MmaCand c = list[i];
+            sm.score[off + i] = ordered_score(c.score);
+            if (sm.row) sm.row[off + i] = c.row;
+        }
+    }
+    __syncthreads();
+    return total;
+}
+
+// Histogram update, warp-aggregated for the common case that every active lane hits one bin
+// (scores of one query share their exponent byte).  All 32 lanes must call.
+__device__ __forceinline__ void mma_hist_add(uint32_t* hist, bool active, uint32_t bin) {
+    const uint32_t amask = __ballot_sync(0xffffffffu, active);
+    if (amask == 0u) return;
+    const uint32_t leader = __ffs(amask) - 1u;
+    const uint32_t lbin = __shfl_sync(0xffffffffu, bin, leader);
+    const uint32_t same = __ballot_sync(0xffffffffu, active && bin == lbin);
+    if (same == amask) {
+        if ((threadIdx.x & 31u) == leader) atomicAdd(&hist[lbin], __popc(amask));
+    } else if (active) {
+        atomicAdd(&hist[bin], 1u);
+    }
+}
+
+// CTA-collective radix select (4 passes of 8 bits) of the k-th largest ordered score.  `staged`
+// selects the flattened shared-memory copy, otherwise the lists are re-read from global memory
+// every pass (only when they do not fit).  Requires total >= k.
+__device__ __forceinline__ uint32_t mma_kth_best(const MmaStageSmem& sm, const MmaLists& l, uint32_t b, uint32_t k,
+                                                 uint32_t total, bool staged) {
+    const uint32_t step = blockDim.x;
+    uint32_t prefix = 0, mask = 0, k_rem = k;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        for (uint32_t i = threadIdx.x; i < 256; i += step) sm.hist[i] = 0u;
+        __syncthreads();
+        if (staged) {
+            for (uint32_t base = 0; base < total; base += step) {  // warp-uniform trip count
+                const uint32_t i = base + threadIdx.x;
+                const uint32_t u = i < total ? sm.score[i] : 0u;
+                mma_hist_add(sm.hist, i < total && (u & mask) == prefix, (u >> shift) & 255u);
+            }
+        } else {
+            for (uint32_t j = 0; j < mma_list_count(l); ++j) {
+                const uint32_t n = sm.offs[j + 1] - sm.offs[j];
+                const MmaCand* list = l.cand + mma_list_slot(l, b, j) * l.cap;
+                for (uint32_t base = 0; base < n; base += step) {
+                    const uint32_t i = base + threadIdx.x;
+                    const uint32_t u = i < n ? ordered_score(list[i].score) : 0u;
+                    mma_hist_add(sm.hist, i < n && (u & mask) == prefix, (u >> shift) & 255u);
+                }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {  // warp 0: the bin holding the k_rem-th largest; lane L owns bins [8L, 8L+8)
+            uint32_t local[8], sum = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                local[i] = sm.hist[threadIdx.x * 8 + i];
+                sum += local[i];
+            }
+            uint32_t above = 0;  // entries in bins owned by higher lanes
+            for (int src = 31; src >= 0; --src) {
+                const uint32_t v = __shfl_sync(0xffffffffu, sum, src);
+                if (src > (int)threadIdx.x) above += v;
+            }
+            if (above < k_rem && above + sum >= k_rem) {  // exactly one lane
+                uint32_t acc = above;
+                for (int i = 7; i >= 0; --i) {
+                    if (acc + local[i] >= k_rem) {
+                        sm.ctl[0] = prefix | ((uint32_t)(threadIdx.x * 8 + i) << shift);
+                        sm.ctl[1] = k_rem - acc;
+                        break;
+                    }
+                    acc += local[i];
+                }
+            }
+        }
+        __syncthreads();
+        prefix = sm.ctl[0];
+        k_rem = sm.ctl[1];
+        mask |= 255u << shift;
+        __syncthreads();
+    }
+    return prefix;
+}
+
+// ─── gate: k'-th best approximate score of a level's lists -> the next level's static gate ──
+// One CTA per query.  Any subset's k'-th best is a lower bound of the full corpus' k'-th (<= k-th)
+// best, so the gate stays valid when a list overflowed (its first `cap` entries are used).
 struct MmaGateArgs {
     MmaLists lists;
     const float* margin2;
     const uint32_t* redo;
     float* gate;            // out
-    uint32_t k_sel, buf_cap;
-    uint32_t* error_flag;
+    uint32_t k_sel;
 };
-
-// CTA-collective: pushes every entry of every list of query `b` through the bounded buffer.
-__device__ __forceinline__ void mma_select_topk(const CandBuf& buf, uint32_t buf_cap, uint32_t k,
-                                                const MmaLists& l, uint32_t b, uint32_t* error_flag) {
-    const uint32_t step = blockDim.x;
-    const uint32_t trigger = buf_cap - step;
-    for (uint32_t j = 0; j < l.ctas_per_qblock; ++j) {
-        const size_t slot = mma_list_slot(l, b, j);
-        const uint32_t n = min(l.cand_count[slot], l.cap);
-        const MmaCand* list = l.cand + slot * l.cap;
-        for (uint32_t base = 0; base < n; base += step) {  // CTA-uniform trip count
-            const uint64_t t = *buf.tau;
-            const uint32_t i = base + threadIdx.x;
-            if (i < n) {
-                const MmaCand c = list[i];
-                const uint64_t key = make_key(c.score, c.row);
-                if (key > t && !cand_push(buf, buf_cap, key)) atomicExch(error_flag, 1u);
-            }
-            __syncthreads();
-            if (*buf.cnt > trigger) cand_compact(buf, buf_cap, k);
-            __syncthreads();
-        }
-    }
-    cand_compact(buf, buf_cap, k);
-}
 
 __global__ void __launch_bounds__(256) mma_gate_kernel(const MmaGateArgs args) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint64_t* cand = reinterpret_cast<uint64_t*>(smem_raw);
-    uint64_t* tau = cand + args.buf_cap;
-    uint32_t* cnt = reinterpret_cast<uint32_t*>(tau + 1);
     const uint32_t b = blockIdx.x;
     if (args.redo[b] != 0u) return;
-    if (threadIdx.x == 0) {
-        *cnt = 0u;
-        *tau = 0ull;
+    const MmaStageSmem sm = carve_stage_smem(smem_raw, kMmaStageScores, false);
+    const uint32_t total = mma_stage_lists(sm, args.lists, b);
+    float gate = -INFINITY;
+    if (total >= args.k_sel) {  // CTA-uniform
+        const uint32_t u = mma_kth_best(sm, args.lists, b, args.k_sel, total, total <= sm.cap);
+        gate = __fsub_rd(unordered_score(u), args.margin2[b]);
     }
-    __syncthreads();
-    const CandBuf buf{cand, cnt, tau};
-    mma_select_topk(buf, args.buf_cap, args.k_sel, args.lists, b, args.error_flag);
-    if (threadIdx.x == 0) {
-        float gate = -INFINITY;
-        if (*cnt >= args.k_sel) gate = __fsub_rd(key_score(cand[args.k_sel - 1]), args.margin2[b]);
-        args.gate[b] = gate;
-    }
+    if (threadIdx.x == 0) args.gate[b] = gate;
 }
 
 // ─── refine: exact re-scoring of the candidate superset, one CTA per query ──────────────────
@@ -806,6 +947,23 @@ struct MmaRefineArgs {
     uint32_t* error_flag;
 };
 
+// Re-scores (warp-cooperatively) the rows whose lanes hold `pass` and offers the exact keys.
+__device__ __forceinline__ void mma_rescore_round(const MmaRefineArgs& args, const CandBuf& buf, const float* q,
+                                                  bool pass, uint32_t grow) {
+    uint32_t mask = __ballot_sync(0xffffffffu, pass);
+    while (mask) {
+        const uint32_t src = __ffs(mask) - 1u;
+        mask &= mask - 1u;
+        const uint32_t r = __shfl_sync(0xffffffffu, grow, src);
+        const uint64_t local = (uint64_t)r - args.row_base;
+        const float s = warp_exact_dot(args.slab + local * args.dim, q, args.dim, args.reduce_order, args.tail_fma);
+        if ((threadIdx.x & 31u) == 0u) {
+            const uint64_t exact = make_key(s, r);
+            if (exact > *buf.tau && !cand_push(buf, args.buf_cap, exact)) atomicExch(args.error_flag, 1u);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) mma_refine_kernel(const MmaRefineArgs args) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* cand = reinterpret_cast<uint64_t*>(smem_raw);
@@ -813,7 +971,6 @@ __global__ void __launch_bounds__(256) mma_refine_kernel(const MmaRefineArgs arg
     uint32_t* cnt = reinterpret_cast<uint32_t*>(tau + 1);
     __shared__ int s_overflow;
     const uint32_t b = blockIdx.x;
-    const uint32_t lane = threadIdx.x & 31;
     const uint32_t step = blockDim.x;
     const MmaLists& l = args.lists;
     if (args.redo[b] != 0u) return;  // the caller re-runs this query on the exact path
@@ -823,7 +980,7 @@ __global__ void __launch_bounds__(256) mma_refine_kernel(const MmaRefineArgs arg
         s_overflow = 0;
     }
     __syncthreads();
-    for (uint32_t j = threadIdx.x; j < l.ctas_per_qblock; j += step)
+    for (uint32_t j = threadIdx.x; j < mma_list_count(l); j += step)
         if (l.cand_count[mma_list_slot(l, b, j)] > l.cap) s_overflow = 1;
     __syncthreads();
     if (s_overflow) {  // the superset is incomplete: exact path
@@ -832,50 +989,43 @@ __global__ void __launch_bounds__(256) mma_refine_kernel(const MmaRefineArgs arg
     }
     const CandBuf buf{cand, cnt, tau};
     const uint32_t trigger = args.buf_cap - step;
+    const MmaStageSmem sm = carve_stage_smem(smem_raw + ((size_t)args.buf_cap * 8 + 16), kMmaStagePairs, true);
+    const uint32_t total = mma_stage_lists(sm, l, b);
+    const bool staged = total <= sm.cap;
 
-    // pass 1: tau_a = k-th best APPROXIMATE key over the lists
-    mma_select_topk(buf, args.buf_cap, args.k, l, b, args.error_flag);
-    float gate = -INFINITY;
-    if (*cnt >= args.k) gate = __fsub_rd(key_score(cand[args.k - 1]), args.margin2[b]);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        *cnt = 0u;
-        *tau = 0ull;
+    // pass 1: tau_a = k-th best APPROXIMATE score (radix select); band gate in the ordered domain
+    uint32_t gate_u = 0u;  // below every real score: keep everything when fewer than k entries exist
+    if (total >= args.k) {
+        const uint32_t u = mma_kth_best(sm, l, b, args.k, total, staged);
+        gate_u = ordered_score(__fsub_rd(unordered_score(u), args.margin2[b]));
     }
-    __syncthreads();
 
     // pass 2: every entry inside the band is re-scored exactly and competes on its exact key
     const float* q = args.queries + (size_t)b * args.dim;
-    for (uint32_t j = 0; j < l.ctas_per_qblock; ++j) {
-        const size_t slot = mma_list_slot(l, b, j);
-        const uint32_t n = l.cand_count[slot];
-        const MmaCand* list = l.cand + slot * l.cap;
-        for (uint32_t base = 0; base < n; base += step) {
+    if (staged) {
+        for (uint32_t base = 0; base < total; base += step) {
             const uint32_t i = base + threadIdx.x;
-            MmaCand c;
-            c.score = -INFINITY;
-            c.row = 0;
-            bool pass = false;
-            if (i < n) {
-                c = list[i];
-                pass = c.score >= gate;
-            }
-            uint32_t mask = __ballot_sync(0xffffffffu, pass);
-            while (mask) {
-                const uint32_t src = __ffs(mask) - 1u;
-                mask &= mask - 1u;
-                const uint32_t grow = __shfl_sync(0xffffffffu, c.row, src);
-                const uint64_t local = (uint64_t)grow - args.row_base;
-                const float s = warp_exact_dot(args.slab + local * args.dim, q, args.dim, args.reduce_order,
-                                               args.tail_fma);
-                if (lane == 0) {
-                    const uint64_t exact = make_key(s, grow);
-                    if (exact > *tau && !cand_push(buf, args.buf_cap, exact)) atomicExch(args.error_flag, 1u);
-                }
-            }
+            const bool pass = i < total && sm.score[i] >= gate_u;
+            mma_rescore_round(args, buf, q, pass, pass ? sm.row[i] : 0u);
             __syncthreads();
             if (*cnt > trigger) cand_compact(buf, args.buf_cap, args.k);
             __syncthreads();
+        }
+    } else {
+        for (uint32_t j = 0; j < mma_list_count(l); ++j) {
+            const uint32_t n = sm.offs[j + 1] - sm.offs[j];
+            const MmaCand* list = l.cand + mma_list_slot(l, b, j) * l.cap;
+            for (uint32_t base = 0; base < n; base += step) {
+                const uint32_t i = base + threadIdx.x;
+                MmaCand c;
+                c.score = 0.0f;
+                c.row = 0;
+                if (i < n) c = list[i];
+                mma_rescore_round(args, buf, q, i < n && ordered_score(c.score) >= gate_u, c.row);
+                __syncthreads();
+                if (*cnt > trigger) cand_compact(buf, args.buf_cap, args.k);
+                __syncthreads();
+            }
         }
     }
     cand_compact(buf, args.buf_cap, args.k);
