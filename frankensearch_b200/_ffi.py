@@ -66,6 +66,25 @@ class Profile(C.Structure):
                 ("mma_flops", C.c_double), ("redo_queries", C.c_uint64)]
 
 
+class MiniLmLayerWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "qkv_w", "qkv_b", "attn_out_w", "attn_out_b", "attn_ln_g", "attn_ln_b", "ffn_in_w", "ffn_in_b",
+        "ffn_out_w", "ffn_out_b", "ffn_ln_g", "ffn_ln_b")]
+
+
+class MiniLmWeights(C.Structure):
+    _fields_ = [("vocab_size", C.c_uint32), ("max_positions", C.c_uint32), ("n_layers", C.c_uint32),
+                ("hidden", C.c_uint32), ("heads", C.c_uint32), ("intermediate", C.c_uint32),
+                ("ln_eps", C.c_float), ("reserved", C.c_uint32),
+                ("word_emb", C.c_void_p), ("pos_emb", C.c_void_p), ("type_emb", C.c_void_p),
+                ("emb_ln_g", C.c_void_p), ("emb_ln_b", C.c_void_p), ("layers", C.POINTER(MiniLmLayerWeights))]
+
+
+class MiniLmProfile(C.Structure):
+    _fields_ = [("gemm_launches", C.c_uint64), ("other_launches", C.c_uint64), ("gemm_flops", C.c_double),
+                ("gemm_ms", C.c_double)]
+
+
 class RrfConfigC(C.Structure):
     _fields_ = [
         ("k", C.c_double),
@@ -88,6 +107,8 @@ EXPORTS = [
     "fsgpu_rrf_fuse", "fsgpu_rrf_fuse_device", "fsgpu_blend_two_tier", "fsgpu_potion_create",
     "fsgpu_potion_destroy", "fsgpu_potion_embed", "fsgpu_potion_embed_device",
     "fsgpu_synth_rows_device",
+    "fsgpu_minilm_create", "fsgpu_minilm_destroy", "fsgpu_minilm_embed", "fsgpu_minilm_embed_device",
+    "fsgpu_minilm_profile_enable", "fsgpu_minilm_profile_read",
 ]
 
 _vp = C.c_void_p
@@ -150,6 +171,13 @@ def lib() -> C.CDLL:
     L.fsgpu_potion_embed_device.argtypes = [_vp, _vp, _vp, C.c_uint32, _vp, _vp]
     L.fsgpu_synth_rows_device.argtypes = [C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32,
                                           C.c_uint32, C.c_float, _vp, _vp]
+    L.fsgpu_minilm_create.argtypes = [C.POINTER(MiniLmWeights), C.c_int, C.POINTER(_vp)]
+    L.fsgpu_minilm_destroy.argtypes = [_vp]
+    L.fsgpu_minilm_destroy.restype = None
+    L.fsgpu_minilm_embed.argtypes = [_vp, _vp, _vp, C.c_uint32, C.c_uint32, _vp]
+    L.fsgpu_minilm_embed_device.argtypes = [_vp, _vp, _vp, C.c_uint32, C.c_uint32, _vp, _vp]
+    L.fsgpu_minilm_profile_enable.argtypes = [_vp, C.c_int]
+    L.fsgpu_minilm_profile_read.argtypes = [_vp, C.POINTER(MiniLmProfile), C.c_int]
     _lib = L
     return L
 

@@ -1,0 +1,419 @@
+// minilm_kernels.cuh — the MiniLM-L6-v2 query encoder on sm_100a.
+//
+// Reference contract: FastEmbedEmbedder (crates/frankensearch-embed/src/fastembed_embedder.rs:317-353,
+// :416-426) = BERT encoder (all-MiniLM-L6-v2: H = 384, L = 6, 12 heads x 32, FFN 1536, erf-GELU,
+// post-LN, eps 1e-12 — the architecture stated in-repo at crates/frankensearch-rerank/src/native.rs:36-45,
+// :366-432, :587-626) -> attention-mask mean pool -> L2 (eps 1e-12) -> adapter L2 with a zero-vector
+// guard (crates/frankensearch-embed/src/model_manifest.rs:300-304).  The arithmetic itself lives in
+// un-vendored third-party code (fastembed 6.0.0 -> ort -> ONNX Runtime) and the reference pins its
+// values only through a SHA-256 digest, so VALUE PARITY IS UNPINNED: the checker is a PyTorch f32
+// BertModel with the same (seeded) weights, tolerance 1e-3 on the 384 outputs (tests/test_gpu_minilm.py).
+//
+// Layout: the batch is flattened to M = batch * t_pad token rows.  Every linear layer is ONE
+// persistent tcgen05 GEMM  C[M, N] = A[M, K] * W[N, K]^T  (PyTorch's [out, in] weight layout is
+// already K-major): TMA -> mbarrier ring -> tcgen05.mma.kind::f16 -> TMEM -> fused epilogue
+// (bias, residual, erf-GELU, f32 and/or split-f16 outputs).  To keep f32-level accuracy on f16
+// tensor cores each f32 operand is carried as hi + lo f16 halves and three products are
+// accumulated (A_hi W_hi + A_lo W_hi + A_hi W_lo; the dropped lo*lo term is < 2^-22 relative).
+// Attention itself (12 heads x 32 dims, T <= 512 keys) is < 3 % of the FLOPs at query lengths
+// and runs on CUDA cores in f32; LayerNorm / embedding / pooling are row-wise f32 kernels.
+#pragma once
+
+#include "mma_scan_kernels.cuh"
+
+namespace fsgpu {
+
+constexpr int kGemmThreads = 192;  // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int kGemmTileM = 128, kGemmTileN = 128;
+constexpr int kGemmAccStages = 2;
+
+struct GemmArgs {
+    uint32_t m, n, k;          // n % 128 == 0, k % 64 == 0
+    uint32_t n_stages;
+    uint32_t products;         // 3: hi/lo split of both operands, 1: hi halves only
+    const float* bias;         // [n]
+    const float* residual;     // [m, n] or nullptr
+    float* out_f32;            // [m, n] or nullptr
+    __half* out_hi;            // [m, n] or nullptr   (split-f16 copy of the result for the next GEMM)
+    __half* out_lo;
+    int gelu;                  // erf-GELU after bias
+};
+
+__host__ __device__ inline size_t gemm_smem_bytes(uint32_t n_stages, uint32_t products) {
+    return 1024 + (size_t)n_stages * (products == 3 ? 4 : 2) * kMmaTileBytes + 256;
+}
+
+__device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
+    hi = __float2half_rn(v);
+    lo = __float2half_rn(v - __half2float(hi));
+}
+
+__device__ __forceinline__ float gelu_erf(float x) {  // 0.5 x (1 + erf(x / sqrt 2)), native.rs:170-186
+    return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+// Persistent GEMM: CTA c computes output tiles c, c + grid, ... (tile = m_tile * tiles_n + n_tile).
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_f16split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                     const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
+                     const GemmArgs args) {
+    extern __shared__ uint8_t smem_dyn[];
+    const uint32_t raw = smem_u32(smem_dyn);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_dyn + (base - raw);
+    const uint32_t per_stage = (args.products == 3 ? 4u : 2u) * kMmaTileBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base_ptr + (size_t)args.n_stages * per_stage);
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](uint32_t s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](uint32_t s) { return bar0 + 8u * (8u + s); };
+    auto tfull_bar = [&](uint32_t a) { return bar0 + 8u * (16u + a); };
+    auto tempty_bar = [&](uint32_t a) { return bar0 + 8u * (20u + a); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t tiles_m = (args.m + kGemmTileM - 1) / kGemmTileM, tiles_n = args.n / kGemmTileN;
+    const uint32_t n_tiles = tiles_m * tiles_n, n_kb = args.k / kMmaKBlock;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_a_hi);
+        tma_prefetch_desc(&tm_w_hi);
+        for (uint32_t s = 0; s < args.n_stages; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (uint32_t a = 0; a < kGemmAccStages; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 4);
+        }
+        fence_barrier_init();
+    } else if (warp == 2) {
+        tmem_alloc(smem_u32(tmem_slot), kGemmAccStages * kGemmTileN);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        uint32_t stage = 0, phase = 0;
+        for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const int32_t row_a = (int32_t)((t / tiles_n) * kGemmTileM), row_w = (int32_t)((t % tiles_n) * kGemmTileN);
+            for (uint32_t kb = 0; kb < n_kb; ++kb) {
+                mbar_wait(empty_bar(stage), phase ^ 1u);
+                if (elect_one()) {
+                    const uint32_t s0 = base + stage * per_stage;
+                    const int32_t kc = (int32_t)(kb * kMmaKBlock);
+                    mbar_expect_tx(full_bar(stage), per_stage);
+                    tma_load_2d(s0, &tm_a_hi, full_bar(stage), kc, row_a);
+                    tma_load_2d(s0 + kMmaTileBytes, &tm_w_hi, full_bar(stage), kc, row_w);
+                    if (args.products == 3) {
+                        tma_load_2d(s0 + 2 * kMmaTileBytes, &tm_a_lo, full_bar(stage), kc, row_a);
+                        tma_load_2d(s0 + 3 * kMmaTileBytes, &tm_w_lo, full_bar(stage), kc, row_w);
+                    }
+                }
+                __syncwarp();
+                if (++stage == args.n_stages) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        constexpr uint32_t idesc = umma_idesc_f16(kGemmTileM, kGemmTileN);
+        uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+        for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * kGemmTileN;
+            for (uint32_t kb = 0; kb < n_kb; ++kb) {
+                mbar_wait(full_bar(stage), phase);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t s0 = base + stage * per_stage;
+                    const uint64_t a_hi = umma_desc_sw128(s0), w_hi = umma_desc_sw128(s0 + kMmaTileBytes);
+                    const uint64_t a_lo = umma_desc_sw128(s0 + 2 * kMmaTileBytes);
+                    const uint64_t w_lo = umma_desc_sw128(s0 + 3 * kMmaTileBytes);
+#pragma unroll
+                    for (uint32_t k4 = 0; k4 < kMmaKBlock / 16; ++k4)
+                        umma_f16(d_tmem, a_hi + 2u * k4, w_hi + 2u * k4, idesc, (kb | k4) != 0u ? 1u : 0u);
+                    if (args.products == 3) {
+#pragma unroll
+                        for (uint32_t k4 = 0; k4 < kMmaKBlock / 16; ++k4) {
+                            umma_f16(d_tmem, a_lo + 2u * k4, w_hi + 2u * k4, idesc, 1u);
+                            umma_f16(d_tmem, a_hi + 2u * k4, w_lo + 2u * k4, idesc, 1u);
+                        }
+                    }
+                    umma_commit(empty_bar(stage));
+                    if (kb + 1 == n_kb) umma_commit(tfull_bar(acc));
+                }
+                __syncwarp();
+                if (++stage == args.n_stages) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+            if (++acc == kGemmAccStages) {
+                acc = 0;
+                acc_phase ^= 1u;
+            }
+        }
+    } else {
+        // ===== epilogue: TMEM lane = output row, column = output feature =====
+        const uint32_t quarter = warp & 3u;
+        uint32_t acc = 0, acc_phase = 0;
+        for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const uint32_t row = (t / tiles_n) * kGemmTileM + quarter * 32u + lane;
+            const uint32_t col0 = (t % tiles_n) * kGemmTileN;
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * kGemmTileN;
+#pragma unroll 1
+            for (uint32_t c = 0; c < kGemmTileN / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld_x32(taddr + c * 32u, v);
+                tmem_ld_wait();
+                if (row < args.m) {
+                    const size_t o = (size_t)row * args.n + col0 + c * 32u;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        float4 r;
+                        const float4 b4 = *reinterpret_cast<const float4*>(args.bias + col0 + c * 32u + i);
+                        r.x = __uint_as_float(v[i]) + b4.x;
+                        r.y = __uint_as_float(v[i + 1]) + b4.y;
+                        r.z = __uint_as_float(v[i + 2]) + b4.z;
+                        r.w = __uint_as_float(v[i + 3]) + b4.w;
+                        if (args.residual) {
+                            const float4 s4 = *reinterpret_cast<const float4*>(args.residual + o + i);
+                            r.x += s4.x; r.y += s4.y; r.z += s4.z; r.w += s4.w;
+                        }
+                        if (args.gelu) {
+                            r.x = gelu_erf(r.x); r.y = gelu_erf(r.y); r.z = gelu_erf(r.z); r.w = gelu_erf(r.w);
+                        }
+                        if (args.out_f32) *reinterpret_cast<float4*>(args.out_f32 + o + i) = r;
+                        if (args.out_hi) {
+                            __half h[4], l[4];
+                            split_f16(r.x, h[0], l[0]); split_f16(r.y, h[1], l[1]);
+                            split_f16(r.z, h[2], l[2]); split_f16(r.w, h[3], l[3]);
+                            *reinterpret_cast<uint2*>(args.out_hi + o + i) = *reinterpret_cast<uint2*>(h);
+                            *reinterpret_cast<uint2*>(args.out_lo + o + i) = *reinterpret_cast<uint2*>(l);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (++acc == kGemmAccStages) {
+                acc = 0;
+                acc_phase ^= 1u;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kGemmAccStages * kGemmTileN);
+    }
+}
+
+// ─── row-wise f32 kernels ───────────────────────────────────────────────────────────────────
+// One warp per token row of H = 384 (12 values per lane).  LayerNorm as PyTorch computes it:
+// mean, then biased variance of (x - mean), eps inside the sqrt.
+constexpr int kHidden = 384;
+
+__device__ __forceinline__ void layernorm_row(float (&x)[12], const float* __restrict__ g, const float* __restrict__ b,
+                                              float eps, uint32_t lane) {
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) s += x[i];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.0f / kHidden);
+    float v = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        const float d = x[i] - mean;
+        v = fmaf(d, d, v);
+    }
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const float inv = rsqrtf(v * (1.0f / kHidden) + eps);
+    // rsqrtf is within 2 ulp; one Newton step brings it to correctly-rounded quality
+    const float var_eps = v * (1.0f / kHidden) + eps;
+    const float inv2 = inv * (1.5f - 0.5f * var_eps * inv * inv);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        const uint32_t d = lane + 32u * i;
+        x[i] = (x[i] - mean) * inv2 * g[d] + b[d];
+    }
+}
+
+__device__ __forceinline__ void store_row(const float (&x)[12], size_t row, float* out_f32, __half* out_hi,
+                                          __half* out_lo, uint32_t lane) {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        const size_t o = row * kHidden + lane + 32u * i;
+        out_f32[o] = x[i];
+        __half h, l;
+        split_f16(x[i], h, l);
+        out_hi[o] = h;
+        out_lo[o] = l;
+    }
+}
+
+// embeddings: word[id] + position[t] + token_type[0] -> LayerNorm   (BertEmbeddings)
+__global__ void __launch_bounds__(256)
+minilm_embed_kernel(const int32_t* __restrict__ ids, uint32_t batch, uint32_t t_pad, uint32_t vocab,
+                    const float* __restrict__ word, const float* __restrict__ pos, const float* __restrict__ type0,
+                    const float* __restrict__ g, const float* __restrict__ b, float eps, float* out_f32,
+                    __half* out_hi, __half* out_lo) {
+    const uint32_t lane = threadIdx.x & 31;
+    const size_t row = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= (size_t)batch * t_pad) return;
+    const uint32_t t = (uint32_t)(row % t_pad);
+    int32_t id = ids[row];
+    if (id < 0 || (uint32_t)id >= vocab) id = 0;  // pad slots / out-of-range ids read row 0 (masked later)
+    float x[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        const uint32_t d = lane + 32u * i;
+        x[i] = word[(size_t)id * kHidden + d] + pos[(size_t)t * kHidden + d] + type0[d];
+    }
+    layernorm_row(x, g, b, eps, lane);
+    store_row(x, row, out_f32, out_hi, out_lo, lane);
+}
+
+// post-LN residual block tail: LayerNorm(pre) where `pre` already holds linear + bias + residual
+__global__ void __launch_bounds__(256)
+minilm_layernorm_kernel(const float* __restrict__ pre, size_t rows, const float* __restrict__ g,
+                        const float* __restrict__ b, float eps, float* out_f32, __half* out_hi, __half* out_lo) {
+    const uint32_t lane = threadIdx.x & 31;
+    const size_t row = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    float x[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) x[i] = pre[row * kHidden + lane + 32u * i];
+    layernorm_row(x, g, b, eps, lane);
+    store_row(x, row, out_f32, out_hi, out_lo, lane);
+}
+
+// ─── attention: one CTA per (sequence, head); f32 on CUDA cores ─────────────────────────────
+// qkv [M, 1152] f32 = [q | k | v], head h at columns h*32.  softmax(q k^T / sqrt(32)) over the
+// sequence's valid keys (native.rs:82-133), context written as split f16 for the out-projection.
+constexpr int kHeads = 12, kHeadDim = 32;
+
+__global__ void __launch_bounds__(128)
+minilm_attention_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ lens, uint32_t t_pad,
+                        __half* __restrict__ ctx_hi, __half* __restrict__ ctx_lo) {
+    extern __shared__ __align__(16) float att_smem[];
+    const uint32_t b = blockIdx.x / kHeads, h = blockIdx.x % kHeads;
+    const uint32_t len = min((uint32_t)max(lens[b], 0), t_pad);
+    float* ks = att_smem;                       // [len][33]  (padded rows: conflict-free column reads)
+    float* vs = ks + (size_t)t_pad * 33;        // [len][33]
+    float* ps = vs + (size_t)t_pad * 33;        // [4 warps][t_pad] probabilities of the row in flight
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t row0 = (size_t)b * t_pad;
+    for (uint32_t i = threadIdx.x; i < len * kHeadDim; i += blockDim.x) {
+        const uint32_t t = i / kHeadDim, d = i % kHeadDim;
+        const float* src = qkv + (row0 + t) * (3 * kHidden) + h * kHeadDim + d;
+        ks[t * 33 + d] = src[kHidden];
+        vs[t * 33 + d] = src[2 * kHidden];
+    }
+    __syncthreads();
+    const float scale = 0.17677669529663688110f;  // 1 / sqrt(32)
+    float* p = ps + (size_t)warp * t_pad;
+    for (uint32_t t = warp; t < t_pad; t += 4) {
+        const size_t o = (row0 + t) * kHidden + h * kHeadDim + lane;
+        if (t >= len) {  // pad rows: defined output, never read by the pooling
+            ctx_hi[o] = __float2half_rn(0.0f);
+            ctx_lo[o] = __float2half_rn(0.0f);
+            continue;
+        }
+        const float qd = qkv[(row0 + t) * (3 * kHidden) + h * kHeadDim + lane];  // lane = dim
+        float mx = -INFINITY;
+        for (uint32_t j0 = 0; j0 < len; j0 += 32) {
+            const uint32_t j = j0 + lane;
+            float s = 0.0f;
+#pragma unroll
+            for (int d = 0; d < kHeadDim; ++d) {
+                const float qv = __shfl_sync(0xffffffffu, qd, d);
+                s = fmaf(qv, j < len ? ks[j * 33 + d] : 0.0f, s);
+            }
+            s *= scale;
+            if (j < len) {
+                p[j] = s;
+                mx = fmaxf(mx, s);
+            }
+        }
+        for (int o2 = 16; o2 > 0; o2 >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o2));
+        __syncwarp();
+        float sum = 0.0f;
+        for (uint32_t j = lane; j < len; j += 32) {
+            const float e = expf(p[j] - mx);
+            p[j] = e;
+            sum += e;
+        }
+        for (int o2 = 16; o2 > 0; o2 >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o2);
+        __syncwarp();
+        float acc = 0.0f;  // lane = output dim
+        for (uint32_t j = 0; j < len; ++j) acc = fmaf(p[j], vs[j * 33 + lane], acc);
+        acc /= sum;
+        __half hi, lo;
+        split_f16(acc, hi, lo);
+        ctx_hi[o] = hi;
+        ctx_lo[o] = lo;
+        __syncwarp();
+    }
+}
+
+// ─── pooling: masked mean -> L2 (eps 1e-12) -> adapter L2 with zero-vector guard ─────────────
+__global__ void __launch_bounds__(128)
+minilm_pool_kernel(const float* __restrict__ hidden, const int32_t* __restrict__ lens, uint32_t t_pad,
+                   float* __restrict__ out) {
+    const uint32_t b = blockIdx.x;
+    const uint32_t len = min((uint32_t)max(lens[b], 0), t_pad);
+    __shared__ float red[4];
+    float v[3];
+    float part = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const uint32_t d = threadIdx.x + 128u * i;
+        float s = 0.0f;
+        for (uint32_t t = 0; t < len; ++t) s += hidden[((size_t)b * t_pad + t) * kHidden + d];
+        v[i] = len ? s / (float)len : 0.0f;  // sum(mask * h) / clamp(sum(mask), 1e-9)
+        part = fmaf(v[i], v[i], part);
+    }
+    auto block_sum = [&](float x) {
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = x;
+        __syncthreads();
+        return (red[0] + red[1]) + (red[2] + red[3]);
+    };
+    const float n1 = fmaxf(sqrtf(block_sum(part)), 1e-12f);  // fastembed normalize
+    float part2 = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        v[i] = v[i] / n1;
+        part2 = fmaf(v[i], v[i], part2);
+    }
+    const float norm_sq = block_sum(part2);  // adapter normalize_in_place (fastembed_embedder.rs:416-426)
+    const bool ok = isfinite(norm_sq) && norm_sq > 1.1920929e-07f;
+    const float inv = ok ? 1.0f / sqrtf(norm_sq) : 0.0f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) out[(size_t)b * kHidden + threadIdx.x + 128u * i] = ok ? v[i] * inv : 0.0f;
+}
+
+// f32 -> split f16 (weights at load time)
+__global__ void split_f16_kernel(const float* __restrict__ src, size_t n, __half* __restrict__ hi,
+                                 __half* __restrict__ lo) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        __half h, l;
+        split_f16(src[i], h, l);
+        hi[i] = h;
+        lo[i] = l;
+    }
+}
+
+}  // namespace fsgpu

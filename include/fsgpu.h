@@ -254,6 +254,47 @@ int fsgpu_potion_embed_device(const fsgpu_potion* enc, const uint32_t* d_ids,
                               const uint64_t* d_offsets, uint32_t batch, float* d_out,
                               void* stream);
 
+/* MiniLM-L6-v2 (BERT) query encoder.  Replaces FastEmbedEmbedder::embed / embed_batch
+ * (crates/frankensearch-embed/src/fastembed_embedder.rs:317-398, :416-426): BERT forward with the
+ * architecture stated at crates/frankensearch-rerank/src/native.rs:36-45 (H = 384, 12 heads x 32,
+ * erf-GELU, post-LN), attention-mask mean pool, L2 (eps 1e-12), adapter L2 with zero-vector guard
+ * (crates/frankensearch-embed/src/model_manifest.rs:300-304).  Tokenisation ([CLS] ... [SEP],
+ * truncation to 512, batch-longest padding; model_manifest.rs:74-80) stays on the host.
+ * All weights are f32 host arrays in PyTorch layout ([out, in] row-major for linear layers);
+ * qkv_w is the row-wise concatenation query | key | value. */
+typedef struct fsgpu_minilm fsgpu_minilm;
+typedef struct fsgpu_minilm_layer_weights {
+    const float *qkv_w, *qkv_b;             /* [3H, H], [3H] */
+    const float *attn_out_w, *attn_out_b;   /* [H, H], [H]   */
+    const float *attn_ln_g, *attn_ln_b;     /* [H]           */
+    const float *ffn_in_w, *ffn_in_b;       /* [I, H], [I]   */
+    const float *ffn_out_w, *ffn_out_b;     /* [H, I], [H]   */
+    const float *ffn_ln_g, *ffn_ln_b;       /* [H]           */
+} fsgpu_minilm_layer_weights;
+typedef struct fsgpu_minilm_weights {
+    uint32_t vocab_size, max_positions, n_layers, hidden, heads, intermediate;
+    float ln_eps;                            /* 1e-12 */
+    uint32_t reserved;
+    const float *word_emb, *pos_emb, *type_emb; /* [vocab, H], [max_positions, H], [>=1, H] (row 0 used) */
+    const float *emb_ln_g, *emb_ln_b;        /* [H] */
+    const fsgpu_minilm_layer_weights* layers; /* [n_layers] */
+} fsgpu_minilm_weights;
+typedef struct fsgpu_minilm_profile {
+    uint64_t gemm_launches, other_launches;
+    double gemm_flops;     /* 2*M*N*K per tensor-core product actually issued, summed */
+    double gemm_ms;        /* event-timed GEMM durations (0 unless enabled) */
+} fsgpu_minilm_profile;
+int fsgpu_minilm_create(const fsgpu_minilm_weights* weights, int device, fsgpu_minilm** out);
+void fsgpu_minilm_destroy(fsgpu_minilm* enc);
+/* ids [batch, max_len] int32 (slots >= lens[b] ignored), lens [batch] (0 = empty text -> zero
+ * vector, fastembed_embedder.rs:432-434); out [batch, hidden] f32, L2-normalised. */
+int fsgpu_minilm_embed(const fsgpu_minilm* enc, const int32_t* ids, const int32_t* lens, uint32_t batch,
+                       uint32_t max_len, float* out);
+int fsgpu_minilm_embed_device(const fsgpu_minilm* enc, const int32_t* d_ids, const int32_t* d_lens,
+                              uint32_t batch, uint32_t max_len, float* d_out, void* stream);
+int fsgpu_minilm_profile_enable(fsgpu_minilm* enc, int on);
+int fsgpu_minilm_profile_read(fsgpu_minilm* enc, fsgpu_minilm_profile* out, int reset);
+
 /* ---- synthetic corpora (bench / test utility) ---------------------------------------------- */
 /* The reference's bench generators on the device
  * (crates/frankensearch-index/benches/fsvi_int8_two_pass.rs:199-231), bit-identical to the
