@@ -1610,6 +1610,7 @@ static int minilm_gemm(const fsgpu_minilm* e, const SplitMat& a, const SplitMat&
     ga.out_hi = out_hi;
     ga.out_lo = out_lo;
     ga.gelu = gelu;
+    ga.debug_skip_epilogue = env_int("FSGPU_GEMM_SKIP_EPILOGUE", 0);
     const size_t smem = gemm_smem_bytes(ga.n_stages, products);
     CUDA_TRY(cudaFuncSetAttribute(gemm_f16split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)gemm_smem_bytes(6, 1)));
@@ -1671,7 +1672,11 @@ static int minilm_embed_locked(const fsgpu_minilm* e, const int32_t* d_ids, cons
         const MiniLmLayer& L = e->layers[li];
         int rc = minilm_gemm(e, e->act_h, L.qkv, m, L.qkv_b, nullptr, qkv32, nullptr, nullptr, 0, products, s);
         if (rc) return rc;
-        minilm_attention_kernel<<<batch * kHeads, 128, att_smem, s>>>(qkv32, d_lens, max_len, e->act_ctx.hi, e->act_ctx.lo);
+        if (max_len <= 32)
+            minilm_attention_short_kernel<<<(batch * kHeads + 3) / 4, 128, 0, s>>>(qkv32, d_lens, batch, max_len,
+                                                                                   e->act_ctx.hi, e->act_ctx.lo);
+        else
+            minilm_attention_kernel<<<batch * kHeads, 128, att_smem, s>>>(qkv32, d_lens, max_len, e->act_ctx.hi, e->act_ctx.lo);
         CUDA_TRY(cudaGetLastError());
         rc = minilm_gemm(e, e->act_ctx, L.attn_out, m, L.attn_out_b, h32, pre32, nullptr, nullptr, 0, products, s);
         if (rc) return rc;

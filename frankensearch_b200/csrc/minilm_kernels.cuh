@@ -23,7 +23,7 @@
 
 namespace fsgpu {
 
-constexpr int kGemmThreads = 192;  // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int kGemmThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
 constexpr int kGemmTileM = 128, kGemmTileN = 128;
 constexpr int kGemmAccStages = 2;
 
@@ -37,6 +37,7 @@ struct GemmArgs {
     __half* out_hi;            // [m, n] or nullptr   (split-f16 copy of the result for the next GEMM)
     __half* out_lo;
     int gelu;                  // erf-GELU after bias
+    int debug_skip_epilogue;   // perf experiment only: accumulators are drained but nothing is stored
 };
 
 __host__ __device__ inline size_t gemm_smem_bytes(uint32_t n_stages, uint32_t products) {
@@ -83,7 +84,7 @@ gemm_f16split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
         }
         for (uint32_t a = 0; a < kGemmAccStages; ++a) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), 4);
+            mbar_init(tempty_bar(a), 8);
         }
         fence_barrier_init();
     } else if (warp == 2) {
@@ -162,19 +163,20 @@ gemm_f16split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
     } else {
         // ===== epilogue: TMEM lane = output row, column = output feature =====
         const uint32_t quarter = warp & 3u;
+        const uint32_t half = (warp - 2u) >> 2;  // which 64 of the tile's 128 columns this warp stores
         uint32_t acc = 0, acc_phase = 0;
         for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
             const uint32_t row = (t / tiles_n) * kGemmTileM + quarter * 32u + lane;
-            const uint32_t col0 = (t % tiles_n) * kGemmTileN;
+            const uint32_t col0 = (t % tiles_n) * kGemmTileN + half * (kGemmTileN / 2);
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * kGemmTileN;
+            const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * kGemmTileN + half * (kGemmTileN / 2);
 #pragma unroll 1
-            for (uint32_t c = 0; c < kGemmTileN / 32; ++c) {
+            for (uint32_t c = 0; c < kGemmTileN / 64; ++c) {
                 uint32_t v[32];
                 tmem_ld_x32(taddr + c * 32u, v);
                 tmem_ld_wait();
-                if (row < args.m) {
+                if (row < args.m && !args.debug_skip_epilogue) {
                     const size_t o = (size_t)row * args.n + col0 + c * 32u;
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) {
@@ -364,6 +366,59 @@ minilm_attention_kernel(const float* __restrict__ qkv, const int32_t* __restrict
         ctx_hi[o] = hi;
         ctx_lo[o] = lo;
         __syncwarp();
+    }
+}
+
+// Short sequences (t_pad <= 32, the query-encoding case): one WARP per (sequence, head).  Lane j
+// keeps key row j in registers, V sits in a padded per-warp shared tile; no block barriers.
+__global__ void __launch_bounds__(128)
+minilm_attention_short_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ lens, uint32_t batch,
+                              uint32_t t_pad, __half* __restrict__ ctx_hi, __half* __restrict__ ctx_lo) {
+    __shared__ float vs_all[4][32 * 33];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t unit = blockIdx.x * 4 + warp;
+    if (unit >= batch * kHeads) return;
+    const uint32_t b = unit / kHeads, h = unit % kHeads;
+    const uint32_t len = min((uint32_t)max(lens[b], 0), t_pad);
+    float* vs = vs_all[warp];
+    const size_t row0 = (size_t)b * t_pad;
+    float kreg[kHeadDim];
+    {
+        const float* src = qkv + (row0 + min(lane, t_pad - 1)) * (3 * kHidden) + h * kHeadDim;
+#pragma unroll
+        for (int d = 0; d < kHeadDim; d += 4) {
+            const float4 k4 = *reinterpret_cast<const float4*>(src + kHidden + d);
+            const float4 v4 = *reinterpret_cast<const float4*>(src + 2 * kHidden + d);
+            kreg[d] = k4.x; kreg[d + 1] = k4.y; kreg[d + 2] = k4.z; kreg[d + 3] = k4.w;
+            vs[lane * 33 + d] = v4.x; vs[lane * 33 + d + 1] = v4.y; vs[lane * 33 + d + 2] = v4.z; vs[lane * 33 + d + 3] = v4.w;
+        }
+    }
+    __syncwarp();
+    const float scale = 0.17677669529663688110f;
+    for (uint32_t t = 0; t < t_pad; ++t) {
+        const size_t o = (row0 + t) * kHidden + h * kHeadDim + lane;
+        if (t >= len) {
+            ctx_hi[o] = __float2half_rn(0.0f);
+            ctx_lo[o] = __float2half_rn(0.0f);
+            continue;
+        }
+        const float qd = qkv[(row0 + t) * (3 * kHidden) + h * kHeadDim + lane];  // lane = dim
+        float s = 0.0f;
+#pragma unroll
+        for (int d = 0; d < kHeadDim; ++d) s = fmaf(__shfl_sync(0xffffffffu, qd, d), kreg[d], s);  // lane = key
+        s = lane < len ? s * scale : -INFINITY;
+        float mx = s;
+        for (int o2 = 16; o2 > 0; o2 >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o2));
+        const float e = lane < len ? expf(s - mx) : 0.0f;
+        float sum = e;
+        for (int o2 = 16; o2 > 0; o2 >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o2);
+        float acc = 0.0f;  // lane = output dim
+        for (uint32_t j = 0; j < len; ++j) acc = fmaf(__shfl_sync(0xffffffffu, e, j), vs[j * 33 + lane], acc);
+        acc /= sum;
+        __half hi, lo;
+        split_f16(acc, hi, lo);
+        ctx_hi[o] = hi;
+        ctx_lo[o] = lo;
     }
 }
 
