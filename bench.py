@@ -350,7 +350,7 @@ def run_ours(a):
             achieved_tf = flops / (avg_ms * 1e-3) / 1e12 if avg_ms > 0 else 0.0
             roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                         "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic,
-                        "kernel": "mma_scan_kernel (tcgen05.mma kind::f16, M=128 queries x N=128 rows, K=dim)",
+                        "kernel": "mma_scan_pair_kernel (tcgen05.mma.cta_group::2 kind::f16, M=256 queries x N=256 rows per CTA pair, K=dim)",
                         "flops_per_launch": flops, "frac_of_sustained_peak": achieved_tf / peak_tf_sus,
                         "peak_sustained": peak_tf_sus,
                         "hbm_gbs_same_launch": hbm_achieved, "hbm_frac_same_launch": hbm_achieved / peak_gbs}
