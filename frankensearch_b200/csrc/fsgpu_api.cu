@@ -113,6 +113,8 @@ struct fsgpu_index {
     uint16_t* d_slab = nullptr;
     bool owns_slab = false;
     uint8_t* d_tomb = nullptr;
+    mutable const uint8_t* d_excl = nullptr;  // per-call exclusion bitmap (tombstones | !filter), else nullptr
+    mutable DevBuf ws_excl, ws_allow;
     cudaStream_t stream = nullptr;
     mutable std::mutex mu;
     // workspaces (grow-only, guarded by mu)
@@ -259,7 +261,7 @@ static int search_exact_locked(const fsgpu_index* ix, const float* d_queries, ui
         const int grid = (int)std::min<uint64_t>((n + kScanWarps - 1) / kScanWarps, (uint64_t)ix->num_sms * 8);
         for (uint32_t b = 0; b < batch; ++b) {
             score_all_kernel<<<grid, kScanThreads, (size_t)ix->dim * 4, stream>>>(
-                ix->d_slab, ix->d_tomb, n, ix->row_base, ix->dim, d_queries + (size_t)b * ix->dim,
+                ix->d_slab, ix->d_excl ? ix->d_excl : ix->d_tomb, n, ix->row_base, ix->dim, d_queries + (size_t)b * ix->dim,
                 ix->reduce_order, ix->tail_fma, ix->ws_sort_a.as<uint64_t>());
             CUDA_TRY(cudaGetLastError());
             CUDA_TRY(cub::DeviceRadixSort::SortKeysDescending(
@@ -294,7 +296,7 @@ static int search_exact_locked(const fsgpu_index* ix, const float* d_queries, ui
         CUDA_TRY(ix->ws_partial.reserve((size_t)plan.grid * qb * k * 8));
         ScanArgs a{};
         a.slab = ix->d_slab;
-        a.tombstones = ix->d_tomb;
+        a.tombstones = ix->d_excl ? ix->d_excl : ix->d_tomb;
         a.queries = d_queries + (size_t)done * ix->dim;
         a.n_rows = ix->n_rows;
         a.row_base = ix->row_base;
@@ -514,7 +516,7 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
         MmaScanArgs a{};
         a.n_rows = ix->n_rows;
         a.row_base = ix->row_base;
-        a.tombstones = ix->d_tomb;
+        a.tombstones = ix->d_excl ? ix->d_excl : ix->d_tomb;
         a.n_kblocks = n_kb;
         a.n_qblocks = n_qb;
         a.ctas_per_qblock = g;
@@ -696,7 +698,7 @@ extern "C" void fsgpu_index_destroy(fsgpu_index* ix) {
             }
         for (DevBuf* b : {&ix->ws_partial, &ix->ws_queries, &ix->ws_keys, &ix->ws_hits, &ix->ws_counts,
                           &ix->ws_sort_a, &ix->ws_sort_b, &ix->ws_cub, &ix->ws_rows, &ix->ws_scores,
-                          &ix->ws_present, &ix->ws_qhat, &ix->ws_margin, &ix->ws_gate, &ix->ws_redo, &ix->ws_cand,
+                          &ix->ws_present, &ix->ws_excl, &ix->ws_allow, &ix->ws_qhat, &ix->ws_margin, &ix->ws_gate, &ix->ws_redo, &ix->ws_cand,
                           &ix->ws_cand_count})
             b->release();
         if (ix->stream) cudaStreamDestroy(ix->stream);
@@ -891,6 +893,78 @@ extern "C" int fsgpu_search_top_k(const fsgpu_index* ix, const float* queries, u
     CUDA_TRY(cudaMemcpyAsync(ix->ws_queries.p, queries, (size_t)batch * dim * 4, cudaMemcpyHostToDevice, s));
     int rc = search_device_locked(ix, ix->ws_queries.as<float>(), batch, k, nullptr,
                                   ix->ws_hits.as<fsgpu_hit>(), ix->ws_counts.as<uint32_t>(), s);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out, ix->ws_hits.p, (size_t)batch * k * sizeof(fsgpu_hit), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(out_counts, ix->ws_counts.p, (size_t)batch * 4, cudaMemcpyDeviceToHost, s));
+    return check_error_flag(ix, s);
+}
+
+// ─── filtered search ────────────────────────────────────────────────────────────────────────
+__global__ void combine_exclusion_kernel(const uint8_t* __restrict__ tomb, const uint8_t* __restrict__ allow,
+                                         size_t n_bytes, uint8_t* __restrict__ out) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_bytes; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = (uint8_t)((tomb ? tomb[i] : 0u) | (uint8_t)~allow[i]);
+}
+
+// Caller holds ix->mu.  `d_allow`: device bitmap, bit r%8 of byte r/8 set = local row r may be returned.
+static int search_filtered_locked(const fsgpu_index* ix, const float* d_queries, uint32_t batch, uint32_t k,
+                                  const uint8_t* d_allow, uint64_t* d_out_keys, fsgpu_hit* d_out_hits,
+                                  uint32_t* d_out_counts, cudaStream_t s) {
+    if (!d_allow || ix->n_rows == 0) return search_device_locked(ix, d_queries, batch, k, d_out_keys, d_out_hits, d_out_counts, s);
+    const size_t n_bytes = (ix->n_rows + 7) / 8;
+    CUDA_TRY(ix->ws_excl.reserve(n_bytes));
+    combine_exclusion_kernel<<<(unsigned)std::min<size_t>((n_bytes + 255) / 256, 4096), 256, 0, s>>>(
+        ix->d_tomb, d_allow, n_bytes, ix->ws_excl.as<uint8_t>());
+    CUDA_TRY(cudaGetLastError());
+    ix->prof.other_launches += 1;
+    ix->d_excl = ix->ws_excl.as<uint8_t>();
+    const int rc = search_device_locked(ix, d_queries, batch, k, d_out_keys, d_out_hits, d_out_counts, s);
+    ix->d_excl = nullptr;
+    return rc;
+}
+
+extern "C" int fsgpu_search_top_k_filtered_device(const fsgpu_index* ix, const float* d_queries, uint32_t batch,
+                                                  uint32_t k, const uint8_t* d_allow_bitmap, uint64_t* d_out_keys,
+                                                  fsgpu_hit* d_out_hits, uint32_t* d_out_counts, void* stream) {
+    if (!ix) return fail(FSGPU_ERR_INVALID_CONFIG, "index is NULL");
+    if (batch && !d_queries) return fail(FSGPU_ERR_INVALID_CONFIG, "queries is NULL");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t s = stream ? (cudaStream_t)stream : ix->stream;
+    if (k && d_out_keys) CUDA_TRY(cudaMemsetAsync(d_out_keys, 0, (size_t)batch * k * 8, s));
+    int rc = search_filtered_locked(ix, d_queries, batch, k, d_allow_bitmap, d_out_keys, d_out_hits, d_out_counts, s);
+    if (rc) return rc;
+    if (!stream) return check_error_flag(ix, s);
+    return FSGPU_OK;
+}
+
+extern "C" int fsgpu_search_top_k_filtered(const fsgpu_index* ix, const float* queries, uint32_t batch, uint32_t k,
+                                           uint32_t dim, const uint8_t* allow_bitmap, fsgpu_hit* out,
+                                           uint32_t* out_counts) {
+    if (!ix) return fail(FSGPU_ERR_INVALID_CONFIG, "index is NULL");
+    if (dim != ix->dim) return fail(FSGPU_ERR_DIMENSION_MISMATCH, "expected %u, found %u", ix->dim, dim);
+    if (batch == 0) return FSGPU_OK;
+    if (!queries || !out_counts || (k && !out)) return fail(FSGPU_ERR_INVALID_CONFIG, "NULL argument");
+    if (k == 0 || ix->n_rows == 0) {
+        memset(out_counts, 0, (size_t)batch * 4);
+        return FSGPU_OK;
+    }
+    std::lock_guard<std::mutex> lock(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t s = ix->stream;
+    CUDA_TRY(ix->ws_queries.reserve((size_t)batch * dim * 4));
+    CUDA_TRY(ix->ws_hits.reserve((size_t)batch * k * sizeof(fsgpu_hit)));
+    CUDA_TRY(ix->ws_counts.reserve((size_t)batch * 4));
+    CUDA_TRY(cudaMemcpyAsync(ix->ws_queries.p, queries, (size_t)batch * dim * 4, cudaMemcpyHostToDevice, s));
+    const uint8_t* d_allow = nullptr;
+    if (allow_bitmap) {
+        const size_t n_bytes = (ix->n_rows + 7) / 8;
+        CUDA_TRY(ix->ws_allow.reserve(n_bytes));
+        CUDA_TRY(cudaMemcpyAsync(ix->ws_allow.p, allow_bitmap, n_bytes, cudaMemcpyHostToDevice, s));
+        d_allow = ix->ws_allow.as<uint8_t>();
+    }
+    int rc = search_filtered_locked(ix, ix->ws_queries.as<float>(), batch, k, d_allow, nullptr,
+                                    ix->ws_hits.as<fsgpu_hit>(), ix->ws_counts.as<uint32_t>(), s);
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(out, ix->ws_hits.p, (size_t)batch * k * sizeof(fsgpu_hit), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(out_counts, ix->ws_counts.p, (size_t)batch * 4, cudaMemcpyDeviceToHost, s));

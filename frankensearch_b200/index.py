@@ -172,7 +172,23 @@ class GpuVectorIndex:
         check(self._L.fsgpu_index_set_tombstones(self._h, ptr(bm)))
 
     # ── exact search ────────────────────────────────────────────────────────────────────────
-    def search_top_k_batch(self, queries, limit: int):
+    def _allow_bitmap(self, filter) -> Optional[np.ndarray]:
+        """`filter` is the reference's `SearchFilter` seen from the host: a callable
+        `doc_id -> bool` (SearchFilter::matches, crates/frankensearch-core/src/filter.rs:19) or a
+        boolean array over local rows.  Returns the packed allow-bitmap the C ABI takes."""
+        if filter is None:
+            return None
+        n = self.record_count()
+        if callable(filter):
+            base = self.row_base()
+            mask = np.fromiter((bool(filter(self.doc_id_at(base + r))) for r in range(n)), dtype=bool, count=n)
+        else:
+            mask = np.asarray(filter, dtype=bool).reshape(-1)
+            if mask.size != n:
+                raise SearchError("InvalidConfig", f"filter mask has {mask.size} entries, index has {n} rows")
+        return np.packbits(mask, bitorder="little")
+
+    def search_top_k_batch(self, queries, limit: int, filter=None):
         """`batch` queries in one call.  Returns (rows u32 [B,k], scores f32 [B,k], counts u32 [B])."""
         q = np.ascontiguousarray(queries, dtype=np.float32)
         if q.ndim == 1:
@@ -181,16 +197,18 @@ class GpuVectorIndex:
         k = int(limit)
         hits = np.zeros((b, max(k, 1)), dtype=np.dtype([("row", np.uint32), ("score", np.float32)]))
         counts = np.zeros(b, dtype=np.uint32)
-        check(self._L.fsgpu_search_top_k(self._h, ptr(q), b, k, dim, ptr(hits), ptr(counts)))
+        if filter is None:
+            check(self._L.fsgpu_search_top_k(self._h, ptr(q), b, k, dim, ptr(hits), ptr(counts)))
+        else:
+            bm = self._allow_bitmap(filter)
+            check(self._L.fsgpu_search_top_k_filtered(self._h, ptr(q), b, k, dim, ptr(bm), ptr(hits), ptr(counts)))
         return hits["row"][:, :k].copy(), hits["score"][:, :k].copy(), counts
 
     def search_top_k(self, query, limit: int, filter=None) -> List[VectorHit]:
         """VectorIndex::search_top_k (search.rs:192-206) / InMemoryVectorIndex::search_top_k
         (in_memory.rs:2555): best-first hits, `limit == 0` or empty index -> []."""
-        if filter is not None:
-            raise SearchError("InvalidConfig", "SearchFilter is not supported on the device path yet")
         q = np.ascontiguousarray(query, dtype=np.float32).reshape(-1)
-        rows, scores, counts = self.search_top_k_batch(q[None, :], limit)
+        rows, scores, counts = self.search_top_k_batch(q[None, :], limit, filter=filter)
         n = int(counts[0])
         hits = [VectorHit(int(rows[0, i]), float(scores[0, i]), self.doc_id_at(int(rows[0, i]))) for i in range(n)]
         if self._dedup:  # resolve_sorted_entries: first (= best) occurrence of a doc id wins (search.rs:1540)

@@ -162,6 +162,19 @@ int fsgpu_search_top_k_device(const fsgpu_index* index, const float* d_queries, 
                               uint32_t k, uint64_t* d_out_keys, fsgpu_hit* d_out_hits,
                               uint32_t* d_out_counts, void* stream);
 
+/* The `filter: Option<&dyn SearchFilter>` argument of VectorIndex::search_top_k
+ * (crates/frankensearch-index/src/search.rs:192-206; applied before heap admission,
+ * search.rs:1329-1447): the host evaluates the filter per doc id / doc-id hash and passes a packed
+ * bitmap over LOCAL rows (bit r%8 of byte r/8 set = row r may be returned; NULL = no filter).
+ * One filter per call, shared by every query of the batch.  Excluded rows never count towards
+ * k, exactly like tombstones. */
+int fsgpu_search_top_k_filtered(const fsgpu_index* index, const float* queries, uint32_t batch, uint32_t k,
+                                uint32_t dim, const uint8_t* allow_bitmap, fsgpu_hit* out,
+                                uint32_t* out_counts);
+int fsgpu_search_top_k_filtered_device(const fsgpu_index* index, const float* d_queries, uint32_t batch,
+                                       uint32_t k, const uint8_t* d_allow_bitmap, uint64_t* d_out_keys,
+                                       fsgpu_hit* d_out_hits, uint32_t* d_out_counts, void* stream);
+
 /* Replaces merge_partial_heaps (search.rs:1704-1720) across shards: d_keys holds, per query,
  * `n_lists` lists of `k_in` keys ([batch, n_lists, k_in], 0 = empty; e.g. an all-gather of
  * per-rank results laid out rank-major is passed with `list_stride` = batch*k_in and

@@ -226,3 +226,38 @@ def test_batched_1m_x_384_batch_1024(fs, cpu, fo):
     slab_cpu = slab_gpu.cpu().numpy().view(np.uint16)
     assert_batch_matches_oracle(cpu, slab_cpu, qs, k, (r1, s1, c1), which=[0, 1, 511, 1023])
     ix.close()
+
+
+def test_filtered_search_matches_oracle_with_exclusions(fs, cpu, fo):
+    """SearchFilter (search.rs:192-206, :1329-1447) as an allow-bitmap: filtered-out rows behave
+    like tombstones on both the per-query and the batched path, and compose with tombstones."""
+    slab, _ = fo.synth_rows(1, 31, 0, 25000, 128)
+    ids = [f"doc-{i:06}" for i in range(25000)]
+    rng = np.random.default_rng(3)
+    tomb = rng.random(25000) < 0.1
+    allow = rng.random(25000) < 0.4
+    ix = fs.GpuVectorIndex.from_f16_bits(ids, slab, tombstones=tomb)
+    qs = np.stack([fo.clustered_query(i, 128) for i in range(20)])
+    excluded = tomb | ~allow
+    for batch in (1, 20):  # per-query kernel, batched tensor-core kernel
+        got = ix.search_top_k_batch(qs[:batch], 30, filter=allow)
+        assert_batch_matches_oracle(cpu, slab, qs[:batch], 30, got, tombstones=excluded, ctx=f"batch={batch}")
+    hits = ix.search_top_k(qs[0], 10, filter=lambda d: int(d[4:]) % 3 == 0)
+    want_rows, _ = cpu.search_bits(slab, qs[0], 10, tombstones=tomb | (np.arange(25000) % 3 != 0))
+    assert [h.index for h in hits] == want_rows and all(int(h.doc_id[4:]) % 3 == 0 for h in hits)
+    # the filter is per call: the next unfiltered search sees every live row again
+    got = ix.search_top_k_batch(qs[:3], 30)
+    assert_batch_matches_oracle(cpu, slab, qs[:3], 30, got, tombstones=tomb)
+    ix.close()
+
+
+def test_batched_super_batches_beyond_one_launch(fs, cpu, fo):
+    """More queries than one launch holds (148 SMs x 128): the call loops over super-batches."""
+    slab, _ = fo.synth_rows(0, 41, 0, 700, 64)
+    rng = np.random.default_rng(8)
+    qs = rng.uniform(-1, 1, (19500, 64)).astype(np.float32)
+    ix = fs.GpuVectorIndex.from_f16_bits(None, slab)
+    got, prof = search_with_profile(ix, qs, 5)
+    assert prof["mma_launches"] >= 2
+    assert_batch_matches_oracle(cpu, slab, qs, 5, got, which=[0, 127, 128, 9471, 18943, 18944, 19499])
+    ix.close()
