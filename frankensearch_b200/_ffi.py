@@ -104,7 +104,7 @@ EXPORTS = [
     "fsgpu_index_set_tombstones", "fsgpu_index_read_rows_f16", "fsgpu_index_profile_enable",
     "fsgpu_index_profile_read", "fsgpu_search_top_k", "fsgpu_search_top_k_device",
     "fsgpu_search_top_k_filtered", "fsgpu_search_top_k_filtered_device",
-    "fsgpu_merge_top_k_device", "fsgpu_scores_for_rows", "fsgpu_scores_for_rows_device",
+    "fsgpu_merge_top_k_device", "fsgpu_merge_top_k_hits_device", "fsgpu_scores_for_rows", "fsgpu_scores_for_rows_device",
     "fsgpu_rrf_fuse", "fsgpu_rrf_fuse_device", "fsgpu_blend_two_tier", "fsgpu_potion_create",
     "fsgpu_potion_destroy", "fsgpu_potion_embed", "fsgpu_potion_embed_device",
     "fsgpu_synth_rows_device",
@@ -158,6 +158,8 @@ def lib() -> C.CDLL:
     L.fsgpu_search_top_k_filtered_device.argtypes = [_vp, _vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp, _vp, _vp]
     L.fsgpu_merge_top_k_device.argtypes = [C.c_int, _vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64,
                                            C.c_uint64, C.c_uint32, _vp, _vp, _vp, _vp]
+    L.fsgpu_merge_top_k_hits_device.argtypes = [C.c_int, _vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64,
+                                                C.c_uint64, C.c_uint32, _vp, _vp, _vp, _vp]
     L.fsgpu_scores_for_rows.argtypes = [_vp, _vp, C.c_uint32, _vp, C.c_uint32, _vp, _vp]
     L.fsgpu_scores_for_rows_device.argtypes = [_vp, _vp, C.c_uint32, _vp, C.c_uint32, _vp, _vp, _vp]
     L.fsgpu_rrf_fuse.argtypes = [C.c_int, C.POINTER(RrfConfigC), C.c_uint32, _vp, _vp, _vp, _vp, C.c_uint32,

@@ -480,9 +480,18 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
     const uint32_t unit_queries = pair ? 2 * kMmaM : kMmaM;
     const MmaCascade cas = plan_cascade(ix->n_rows, k, pair ? kPairN : kMmaN);
     const uint32_t fin_cap = cand_capacity(k);
-    const size_t gate_smem = mma_stage_smem_bytes(kMmaStageScores, false);
-    const size_t refine_smem = (size_t)fin_cap * 8 + 16 + mma_stage_smem_bytes(kMmaStagePairs, true);
-    CUDA_TRY(cudaFuncSetAttribute(mma_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gate_smem));
+    // shared-memory staging of the candidate lists, sized from the expected list lengths (smaller
+    // CTAs -> one wave of gate/refine CTAs); longer lists take the kernels' unstaged path
+    auto stage_cap_for = [](double expected, uint32_t limit) {
+        return std::min(limit, std::max(1024u, host_next_pow2((uint32_t)std::min(2.5 * expected + 256.0, 1.0e6))));
+    };
+    const uint32_t gate0_cap = stage_cap_for((double)cas.t0 * cas.tile_rows / 2.5, kMmaStageScores);  // exact dump size
+    const uint32_t gate1_cap = stage_cap_for(cas.random_part, kMmaStageScores);
+    const uint32_t refine_cap = stage_cap_for(cas.t0 < cas.n_tiles ? cas.random_part : (double)cas.t0 * cas.tile_rows / 2.5,
+                                              kMmaStagePairs);
+    const size_t gate_smem_max = mma_stage_smem_bytes(kMmaStageScores, false);
+    const size_t refine_smem = (size_t)fin_cap * 8 + 16 + mma_stage_smem_bytes(refine_cap, true);
+    CUDA_TRY(cudaFuncSetAttribute(mma_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gate_smem_max));
     CUDA_TRY(cudaFuncSetAttribute(mma_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)refine_smem));
 
     const uint32_t max_queries = units * unit_queries;
@@ -543,7 +552,8 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
             a.gate = have_gate ? ix->ws_gate.as<float>() : nullptr;
             scan_kernel<<<grid, kMmaThreads, smem, stream>>>(ix->tm_qhat, ix->tm_slab, a);
             CUDA_TRY(cudaGetLastError());
-            mma_gate_kernel<<<sub, 256, gate_smem, stream>>>(ga);
+            ga.stage_cap = have_gate ? gate1_cap : gate0_cap;
+            mma_gate_kernel<<<sub, 256, mma_stage_smem_bytes(ga.stage_cap, false), stream>>>(ga);
             CUDA_TRY(cudaGetLastError());
             ix->prof.other_launches += 2;
             have_gate = true;
@@ -581,6 +591,7 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
         r.redo = ix->ws_redo.as<uint32_t>();
         r.k = k;
         r.buf_cap = fin_cap;
+        r.stage_cap = refine_cap;
         r.slab = ix->d_slab;
         r.queries = q;
         r.n_rows = ix->n_rows;
@@ -971,11 +982,33 @@ extern "C" int fsgpu_search_top_k_filtered(const fsgpu_index* ix, const float* q
     return check_error_flag(ix, s);
 }
 
+static int merge_top_k_impl(int device, const uint64_t* d_keys, const float* d_scores, const fsgpu_hit* d_hits_in,
+                            uint32_t batch, uint32_t n_lists, uint32_t k_in, uint64_t list_stride,
+                            uint64_t query_stride, uint32_t k_out, uint64_t* d_out_keys, fsgpu_hit* d_out_hits,
+                            uint32_t* d_out_counts, void* stream);
+
 extern "C" int fsgpu_merge_top_k_device(int device, const uint64_t* d_keys, const float* d_scores,
                                         uint32_t batch, uint32_t n_lists, uint32_t k_in,
                                         uint64_t list_stride, uint64_t query_stride, uint32_t k_out,
                                         uint64_t* d_out_keys, fsgpu_hit* d_out_hits,
                                         uint32_t* d_out_counts, void* stream) {
+    return merge_top_k_impl(device, d_keys, d_scores, nullptr, batch, n_lists, k_in, list_stride, query_stride, k_out,
+                            d_out_keys, d_out_hits, d_out_counts, stream);
+}
+
+extern "C" int fsgpu_merge_top_k_hits_device(int device, const uint64_t* d_keys, const fsgpu_hit* d_hits,
+                                             uint32_t batch, uint32_t n_lists, uint32_t k_in,
+                                             uint64_t list_stride, uint64_t query_stride, uint32_t k_out,
+                                             uint64_t* d_out_keys, fsgpu_hit* d_out_hits,
+                                             uint32_t* d_out_counts, void* stream) {
+    return merge_top_k_impl(device, d_keys, nullptr, d_hits, batch, n_lists, k_in, list_stride, query_stride, k_out,
+                            d_out_keys, d_out_hits, d_out_counts, stream);
+}
+
+static int merge_top_k_impl(int device, const uint64_t* d_keys, const float* d_scores, const fsgpu_hit* d_hits_in,
+                            uint32_t batch, uint32_t n_lists, uint32_t k_in, uint64_t list_stride,
+                            uint64_t query_stride, uint32_t k_out, uint64_t* d_out_keys, fsgpu_hit* d_out_hits,
+                            uint32_t* d_out_counts, void* stream) {
     if (batch == 0) return FSGPU_OK;
     if (!d_keys) return fail(FSGPU_ERR_INVALID_CONFIG, "keys is NULL");
     if (k_out == 0 || k_in == 0 || n_lists == 0) {
@@ -991,6 +1024,7 @@ extern "C" int fsgpu_merge_top_k_device(int device, const uint64_t* d_keys, cons
     MergeArgs m{};
     m.keys = d_keys;
     m.scores = d_scores;
+    m.hits_in = d_hits_in;
     m.list_stride = list_stride;
     m.query_stride = query_stride;
     m.n_lists = n_lists;

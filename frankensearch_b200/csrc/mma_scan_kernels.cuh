@@ -913,13 +913,14 @@ struct MmaGateArgs {
     const uint32_t* redo;
     float* gate;            // out
     uint32_t k_sel;
+    uint32_t stage_cap;     // staged scores per CTA (sized by the host from the expected list lengths)
 };
 
 __global__ void __launch_bounds__(256) mma_gate_kernel(const MmaGateArgs args) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t b = blockIdx.x;
     if (args.redo[b] != 0u) return;
-    const MmaStageSmem sm = carve_stage_smem(smem_raw, kMmaStageScores, false);
+    const MmaStageSmem sm = carve_stage_smem(smem_raw, args.stage_cap, false);
     const uint32_t total = mma_stage_lists(sm, args.lists, b);
     float gate = -INFINITY;
     if (total >= args.k_sel) {  // CTA-uniform
@@ -936,6 +937,7 @@ struct MmaRefineArgs {
     uint32_t* redo;              // [slots]; set to 2 when a final list overflowed
     uint32_t k;
     uint32_t buf_cap;            // shared candidate buffer capacity (power of two)
+    uint32_t stage_cap;          // staged (score, row) pairs per CTA
     const uint16_t* slab;
     const float* queries;        // [batch, dim] f32 (the ORIGINAL queries)
     uint64_t n_rows, row_base;
@@ -989,7 +991,7 @@ __global__ void __launch_bounds__(256) mma_refine_kernel(const MmaRefineArgs arg
     }
     const CandBuf buf{cand, cnt, tau};
     const uint32_t trigger = args.buf_cap - step;
-    const MmaStageSmem sm = carve_stage_smem(smem_raw + ((size_t)args.buf_cap * 8 + 16), kMmaStagePairs, true);
+    const MmaStageSmem sm = carve_stage_smem(smem_raw + ((size_t)args.buf_cap * 8 + 16), args.stage_cap, true);
     const uint32_t total = mma_stage_lists(sm, l, b);
     const bool staged = total <= sm.cap;
 

@@ -336,6 +336,7 @@ scan_topk_generic_kernel(const ScanArgs args) {
 struct MergeArgs {
     const uint64_t* keys;     // key of (query b, list g, slot i) at keys[g*list_stride + b*query_stride + i]
     const float* scores;      // optional raw scores, same addressing (travel with the keys)
+    const fsgpu_hit_t* hits_in;  // ... or the hits that travelled with the keys (score field is used)
     uint64_t list_stride;
     uint64_t query_stride;
     uint32_t n_lists;
@@ -409,12 +410,12 @@ __global__ void __launch_bounds__(kScanThreads) merge_topk_kernel(const MergeArg
             if ((uint32_t)(key >> 32) != kNegInfOrdered) continue;  // warp-uniform
             float raw = -INFINITY;
             bool have = false;
-            if (args.scores) {
+            if (args.scores || args.hits_in) {
                 for (uint64_t idx = lane; idx < total && !have; idx += 32) {
                     const uint64_t g = idx / args.k_in, j = idx % args.k_in;
                     const uint64_t off = g * args.list_stride + b * args.query_stride + j;
                     if (args.keys[off] == key) {
-                        raw = args.scores[off];
+                        raw = args.scores ? args.scores[off] : args.hits_in[off].score;
                         have = true;
                     }
                 }

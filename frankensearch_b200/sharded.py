@@ -35,6 +35,7 @@ class ShardedGpuIndex:
         self._ix = local_index
         self._group = group
         self._world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self._fast = local_search is None and merge is None  # both stages are the CUDA kernels
         self._local_search = local_search or self._cuda_local_search
         self._merge = merge or self._cuda_merge
 
@@ -60,11 +61,36 @@ class ShardedGpuIndex:
                                                   counts.data_ptr(), s))
         return out_keys, out_hits, counts
 
+    def _cuda_search_packed(self, d_queries, k: int):
+        """CUDA path with ONE packed buffer per rank: [keys | hits] as int64 [2, B, k] -> one
+        all-gather -> the merge kernel reads keys and the hits' raw scores in place (no copies)."""
+        import torch
+
+        keys, hits, counts = self._ix.search_top_k_device(d_queries, k, want_hits=True)
+        if self._world == 1:
+            return keys, hits, counts
+        b = keys.shape[0]
+        dev = keys.device
+        packed = torch.stack([keys, hits.view(torch.int64).view(b, k)])
+        g = self._world
+        flat = torch.empty((g, 2, b, k), dtype=torch.int64, device=dev)
+        self._dist.all_gather_into_tensor(flat, packed, group=self._group)
+        out_keys = torch.empty((b, k), dtype=torch.int64, device=dev)
+        out_hits = torch.empty((b, k, 2), dtype=torch.int32, device=dev)
+        out_counts = torch.empty(b, dtype=torch.int32, device=dev)
+        s = torch.cuda.current_stream(dev).cuda_stream
+        check(_ffi.lib().fsgpu_merge_top_k_hits_device(dev.index or 0, flat.data_ptr(), flat.data_ptr() + b * k * 8, b, g,
+                                                       k, 2 * b * k, k, k, out_keys.data_ptr(), out_hits.data_ptr(),
+                                                       out_counts.data_ptr(), s))
+        return out_keys, out_hits, out_counts
+
     # the sharded search ------------------------------------------------------------------------
     def search_top_k_device(self, d_queries, k: int):
         """Every rank passes the same queries; every rank returns the same merged result."""
         import torch
 
+        if self._fast and k > 0:
+            return self._cuda_search_packed(d_queries, k)
         keys, scores = self._local_search(d_queries, k)
         if self._world == 1:
             return self._merge(keys.unsqueeze(0), scores.unsqueeze(0), k)

@@ -185,6 +185,13 @@ int fsgpu_merge_top_k_device(int device, const uint64_t* d_keys, const float* d_
                              uint64_t query_stride, uint32_t k_out, uint64_t* d_out_keys,
                              fsgpu_hit* d_out_hits, uint32_t* d_out_counts, void* stream);
 
+/* Same merge, with the raw scores taken from the fsgpu_hit records that travelled with the keys
+ * (same addressing as d_keys): lets a sharded caller all-gather ONE buffer [keys | hits] per rank. */
+int fsgpu_merge_top_k_hits_device(int device, const uint64_t* d_keys, const fsgpu_hit* d_hits,
+                                  uint32_t batch, uint32_t n_lists, uint32_t k_in, uint64_t list_stride,
+                                  uint64_t query_stride, uint32_t k_out, uint64_t* d_out_keys,
+                                  fsgpu_hit* d_out_hits, uint32_t* d_out_counts, void* stream);
+
 /* Replaces TwoTierIndex::quality_scores_for_hits -> VectorIndex::dot_query_at
  * (crates/frankensearch-index/src/two_tier.rs:1566-1631, :1946-1973; lib.rs:3229-3239):
  * out_scores[i] = dot(row rows[i], query); rows outside this shard (or UINT32_MAX) give
