@@ -627,12 +627,14 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
 
 // Exact top-k for `batch` device-resident queries; outputs may be NULL.  Caller holds ix->mu.
 // Small batches stream the slab once per <= 4 queries on the CUDA cores (HBM-bound); batches of
-// FSGPU_MMA_MIN_BATCH (default 8) or more take the tensor-core pass.  Both give identical results.
+// FSGPU_MMA_MIN_BATCH (default 3) or more take the tensor-core pass (one pass of the slab for the
+// whole batch beats two CUDA-core passes from 3 queries on: profiles/r01_sweep_k.txt).  Both give
+// identical results.
 static int search_device_locked(const fsgpu_index* ix, const float* d_queries, uint32_t batch, uint32_t k,
                                 uint64_t* d_out_keys, fsgpu_hit* d_out_hits, uint32_t* d_out_counts,
                                 cudaStream_t stream) {
     if (batch == 0) return FSGPU_OK;
-    const int min_batch = env_int("FSGPU_MMA_MIN_BATCH", 8);
+    const int min_batch = env_int("FSGPU_MMA_MIN_BATCH", 3);
     const bool mma = ix->mma_ok && min_batch > 0 && batch >= (uint32_t)min_batch && k >= 1 && k <= kMmaMaxK &&
                      ix->n_rows > 0;
     if (mma) {

@@ -1,4 +1,4 @@
-// mma_scan_kernels.cuh — the batched (>= 8 queries) form of the exact f16 scan + top-k.
+// mma_scan_kernels.cuh — the batched (>= 3 queries) form of the exact f16 scan + top-k.
 //
 // A batch of B queries against the slab is a dense contraction [B, D] x [D, N] (SURVEY.md §0
 // F5): on CUDA cores it is compute-bound at ~4 queries per corpus pass.  This path runs the
@@ -43,7 +43,7 @@ constexpr int kMmaKBlock = 64;      // f16 elements per 128-byte swizzle row
 constexpr int kMmaTileBytes = kMmaN * kMmaKBlock * 2;  // 16 KiB: one [128 x 64] f16 K-block
 constexpr int kMmaAccStages = 4;    // 4 x 128 TMEM columns = the whole 512-column TMEM
 constexpr int kMmaMaxStages = 8;
-constexpr uint32_t kMmaMaxK = 256;  // larger k goes to the exact path
+constexpr uint32_t kMmaMaxK = 1024;  // larger k goes to the exact path (score-all + radix sort)
 constexpr uint32_t kMmaMaxDim = 512;
 
 // One candidate: the approximate (tensor-core) score and the GLOBAL row.

@@ -147,7 +147,7 @@ int fsgpu_index_profile_read(fsgpu_index* index, fsgpu_profile* out, int reset);
  * by f32::total_cmp descending, ties -> lower row first.  Scores are bit-identical to the
  * reference's dot kernel (simd.rs:398-446) for the configured reduce order.
  * k == 0 or an empty index -> all counts 0 (search.rs:438-440).
- * Batches of >= 8 queries (FSGPU_MMA_MIN_BATCH) with k <= 256 on an all-finite slab whose dim is
+ * Batches of >= 3 queries (FSGPU_MMA_MIN_BATCH) with k <= 1024 on an all-finite slab whose dim is
  * a multiple of 64 take ONE tensor-core pass over the slab (tcgen05/TMA, mma_scan_kernels.cuh)
  * followed by an exact re-scoring of a provable superset of the top-k; results are identical
  * to the per-query path.  That path synchronises the stream once per call. */

@@ -261,3 +261,30 @@ def test_batched_super_batches_beyond_one_launch(fs, cpu, fo):
     assert prof["mma_launches"] >= 2
     assert_batch_matches_oracle(cpu, slab, qs, 5, got, which=[0, 127, 128, 9471, 18943, 18944, 19499])
     ix.close()
+
+
+def test_batched_large_k_up_to_1024(fs, cpu, fo):
+    """k = 1000 (BASELINE configs[4] "rerank top-1000") stays on the tensor-core path: long
+    candidate lists take the kernels' unstaged selection path."""
+    slab, _ = fo.synth_rows(1, 51, 0, 60000, 128)
+    qs = np.stack([fo.clustered_query(i, 128) for i in range(12)])
+    ix = fs.GpuVectorIndex.from_f16_bits(None, slab)
+    for k in (600, 1000, 1024):
+        got, prof = search_with_profile(ix, qs, k)
+        assert prof["mma_launches"] >= 1
+        assert_batch_matches_oracle(cpu, slab, qs, k, got, which=[0, 5, 11], ctx=f"k={k}")
+    got, prof = search_with_profile(ix, qs, 1025)  # beyond the fused limit: score-all + sort arm
+    assert prof["mma_launches"] == 0
+    assert_batch_matches_oracle(cpu, slab, qs, 1025, got, which=[3])
+    ix.close()
+
+
+def test_small_batches_take_the_tensor_core_path_from_three_queries(fs, cpu, fo):
+    slab, _ = fo.synth_rows(1, 61, 0, 30000, 384)
+    qs = np.stack([fo.clustered_query(i, 384) for i in range(7)])
+    ix = fs.GpuVectorIndex.from_f16_bits(None, slab)
+    for b, want_mma in ((1, False), (2, False), (3, True), (7, True)):
+        got, prof = search_with_profile(ix, qs[:b], 10)
+        assert (prof["mma_launches"] >= 1) == want_mma
+        assert_batch_matches_oracle(cpu, slab, qs[:b], 10, got, ctx=f"b={b}")
+    ix.close()
