@@ -375,12 +375,13 @@ static EncodeTiledFn encode_tiled_fn() {
 
 // TMA descriptor of a row-major [rows, dim] f16 matrix read as [128 rows x 64 elements] boxes with
 // the 128-byte swizzle the UMMA shared-memory descriptors expect.
-static bool make_f16_tile_map(CUtensorMap* tm, const void* base, uint64_t rows, uint32_t dim, bool stream_once) {
+static bool make_f16_tile_map(CUtensorMap* tm, const void* base, uint64_t rows, uint32_t dim, bool stream_once,
+                              uint32_t box_rows = kMmaN) {
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc || rows == 0) return false;
     const cuuint64_t gdim[2] = {dim, rows};
     const cuuint64_t gstride[1] = {(cuuint64_t)dim * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)kMmaKBlock, (cuuint32_t)kMmaN};
+    const cuuint32_t box[2] = {(cuuint32_t)kMmaKBlock, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     (void)stream_once;
     return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
@@ -434,15 +435,17 @@ struct MmaCascade {
 };
 
 static MmaCascade plan_cascade(uint64_t n_rows, uint32_t k, uint32_t tile_rows) {
-    // Appends per query: level 0 keeps all t0*128 sample scores (deterministic); level 1 expects
-    // k' * t1/t0 and level 2 k' * n_tiles/t1, both minimised by t1 = sqrt(t0 * n_tiles) at
-    // L = k' * sqrt(n_tiles/t0).  t0 balances the deterministic dump against slack * L.
+    // Appends per query: level 0 keeps all t0*tile_rows sample scores (deterministic); level 1
+    // expects k' * t1/t0 and level 2 k' * n_tiles/t1, both minimised by t1 = sqrt(t0 * n_tiles) at
+    // L = k' * sqrt(n_tiles/t0).
     MmaCascade c;
     c.tile_rows = tile_rows;
     c.n_tiles = (n_rows + tile_rows - 1) / tile_rows;
     c.k_sel = std::max(k, 16u);
     c.slack = std::max(2, env_int("FSGPU_MMA_LIST_SLACK", 6));
-    const double t0_bal = std::pow(c.slack * c.k_sel * std::sqrt((double)c.n_tiles) / tile_rows, 2.0 / 3.0);
+    // t0 minimises the total number of appended candidates per query, t0*tile_rows + 2 k' sqrt(n_tiles/t0)
+    // (appends, not MMAs, are what the sample levels cost: ~0.1 us of warp time each)
+    const double t0_bal = std::pow(c.k_sel * std::sqrt((double)c.n_tiles) / tile_rows, 2.0 / 3.0);
     const uint64_t t0_min = ((uint64_t)8 * c.k_sel + tile_rows - 1) / tile_rows;
     c.t0 = std::min<uint64_t>(c.n_tiles, std::max<uint64_t>({(uint64_t)2048 / tile_rows, t0_min, (uint64_t)std::ceil(t0_bal)}));
     if (c.n_tiles > 8 * c.t0) {
@@ -1540,7 +1543,8 @@ extern "C" int fsgpu_index_open_fsvi(const char* path, uint64_t row_start, uint6
 namespace {
 struct SplitMat {  // an f32 matrix carried as hi + lo f16 halves, with its TMA descriptors
     __half *hi = nullptr, *lo = nullptr;
-    CUtensorMap tm_hi, tm_lo;
+    CUtensorMap tm_hi, tm_lo;      // [128 rows x 64] boxes
+    CUtensorMap tm64_hi, tm64_lo;  // [64 rows x 64] boxes (weights: the 128-wide tail tile of the pair GEMM)
     uint64_t rows = 0;
     uint32_t cols = 0;
 };
@@ -1596,7 +1600,9 @@ static int minilm_upload_split(fsgpu_minilm* e, const float* host, uint64_t rows
     if (err != cudaSuccess) return fail(FSGPU_ERR_SUBSYSTEM, "gpu: minilm weight upload failed: %s", cudaGetErrorString(err));
     m->rows = rows;
     m->cols = cols;
-    if (!make_f16_tile_map(&m->tm_hi, m->hi, rows, cols, false) || !make_f16_tile_map(&m->tm_lo, m->lo, rows, cols, false))
+    if (!make_f16_tile_map(&m->tm_hi, m->hi, rows, cols, false) || !make_f16_tile_map(&m->tm_lo, m->lo, rows, cols, false) ||
+        !make_f16_tile_map(&m->tm64_hi, m->hi, rows, cols, false, 64) ||
+        !make_f16_tile_map(&m->tm64_lo, m->lo, rows, cols, false, 64))
         return fail(FSGPU_ERR_SUBSYSTEM, "gpu: cuTensorMapEncodeTiled failed for a minilm weight");
     return FSGPU_OK;
 }
@@ -1724,8 +1730,20 @@ static int minilm_gemm(const fsgpu_minilm* e, const SplitMat& a, const SplitMat&
     const size_t smem = gemm_smem_bytes(ga.n_stages, products);
     CUDA_TRY(cudaFuncSetAttribute(gemm_f16split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)gemm_smem_bytes(6, 1)));
-    const uint32_t tiles = ((m + kGemmTileM - 1) / kGemmTileM) * (ga.n / kGemmTileN);
-    const uint32_t grid = std::min<uint32_t>(tiles, (uint32_t)e->num_sms);
+    // CTA-pair tiles (256 x 256) are opt-in (FSGPU_MINILM_PAIR=1): measured 9 % slower than 128 x 128
+    // tiles at 1024 x 32 tokens — the epilogue's global loads/stores, not tile traffic, bound these
+    // K = 384 GEMMs (profiles/r01_minilm_gemm_attn_out_ncu.json)
+    const bool pair = m >= 2 * kGemmTileM && e->num_sms >= 2 && env_int("FSGPU_MINILM_PAIR", 0) != 0;
+    uint32_t tiles, grid;
+    if (pair) {
+        CUDA_TRY(cudaFuncSetAttribute(gemm_f16split_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)gemm_smem_bytes(6, 1)));
+        tiles = ((m + 2 * kGemmTileM - 1) / (2 * kGemmTileM)) * ((ga.n + kGemmPairN - 1) / kGemmPairN);
+        grid = 2 * std::min<uint32_t>(tiles, (uint32_t)e->num_sms / 2);
+    } else {
+        tiles = ((m + kGemmTileM - 1) / kGemmTileM) * (ga.n / kGemmTileN);
+        grid = std::min<uint32_t>(tiles, (uint32_t)e->num_sms);
+    }
     std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
     if (e->profiling) {
         if (!e->ev_free.empty()) {
@@ -1737,7 +1755,11 @@ static int minilm_gemm(const fsgpu_minilm* e, const SplitMat& a, const SplitMat&
         }
         CUDA_TRY(cudaEventRecord(ev.first, stream));
     }
-    gemm_f16split_kernel<<<grid, kGemmThreads, smem, stream>>>(a.tm_hi, a.tm_lo, w.tm_hi, w.tm_lo, ga);
+    if (pair)
+        gemm_f16split_pair_kernel<<<grid, kGemmThreads, smem, stream>>>(a.tm_hi, a.tm_lo, w.tm_hi, w.tm_lo, w.tm64_hi,
+                                                                        w.tm64_lo, ga);
+    else
+        gemm_f16split_kernel<<<grid, kGemmThreads, smem, stream>>>(a.tm_hi, a.tm_lo, w.tm_hi, w.tm_lo, ga);
     CUDA_TRY(cudaGetLastError());
     if (e->profiling) {
         CUDA_TRY(cudaEventRecord(ev.second, stream));

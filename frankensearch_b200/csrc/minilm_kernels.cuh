@@ -41,7 +41,7 @@ struct GemmArgs {
 };
 
 __host__ __device__ inline size_t gemm_smem_bytes(uint32_t n_stages, uint32_t products) {
-    return 1024 + (size_t)n_stages * (products == 3 ? 4 : 2) * kMmaTileBytes + 256;
+    return 1024 + (size_t)n_stages * (products == 3 ? 4 : 2) * kMmaTileBytes + 256 + 8 * 128 * 4;
 }
 
 __device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
@@ -51,6 +51,57 @@ __device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
 
 __device__ __forceinline__ float gelu_erf(float x) {  // 0.5 x (1 + erf(x / sqrt 2)), native.rs:170-186
     return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+// Epilogue of one warp over its [32 rows x n_cols] part of an accumulator tile (lane = row).
+// With the whole shared-memory carve-out given to the TMA ring the L1 cache is a few KiB, so every
+// "cached" global load is an L2 round trip: the first version re-loaded the bias in front of each
+// float4 of outputs and spent ~19 k cycles per tile waiting on those loads (4 x the MMA time).
+// Here the warp's bias slice is staged in shared memory once per tile and the residual float4s
+// of a 32-column chunk are all in flight before the accumulator chunk is consumed.
+__device__ __forceinline__ void gemm_epilogue_warp(const GemmArgs& args, uint32_t taddr, uint32_t row, uint32_t col0,
+                                                   uint32_t n_cols, float* bias_s, uint32_t lane) {
+    for (uint32_t i = lane; i < n_cols; i += 32) bias_s[i] = args.bias[col0 + i];
+    __syncwarp();
+    const bool has_row = row < args.m && args.debug_skip_epilogue != 1;
+#pragma unroll 1
+    for (uint32_t c = 0; c < n_cols / 32; ++c) {
+        const size_t o = (size_t)row * args.n + col0 + c * 32u;
+        float4 res[8];
+        if (args.residual && has_row) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) res[i] = *reinterpret_cast<const float4*>(args.residual + o + 4 * i);
+        }
+        uint32_t v[32];
+        tmem_ld_x32(taddr + c * 32u, v);
+        tmem_ld_wait();
+        if (has_row) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c * 32u + 4 * i);
+                float4 r;
+                r.x = __uint_as_float(v[4 * i]) + b4.x;
+                r.y = __uint_as_float(v[4 * i + 1]) + b4.y;
+                r.z = __uint_as_float(v[4 * i + 2]) + b4.z;
+                r.w = __uint_as_float(v[4 * i + 3]) + b4.w;
+                if (args.residual) {
+                    r.x += res[i].x; r.y += res[i].y; r.z += res[i].z; r.w += res[i].w;
+                }
+                if (args.gelu) {
+                    r.x = gelu_erf(r.x); r.y = gelu_erf(r.y); r.z = gelu_erf(r.z); r.w = gelu_erf(r.w);
+                }
+                if (args.out_f32) *reinterpret_cast<float4*>(args.out_f32 + o + 4 * i) = r;
+                if (args.out_hi) {
+                    __half h[4], l[4];
+                    split_f16(r.x, h[0], l[0]); split_f16(r.y, h[1], l[1]);
+                    split_f16(r.z, h[2], l[2]); split_f16(r.w, h[3], l[3]);
+                    *reinterpret_cast<uint2*>(args.out_hi + o + 4 * i) = *reinterpret_cast<uint2*>(h);
+                    *reinterpret_cast<uint2*>(args.out_lo + o + 4 * i) = *reinterpret_cast<uint2*>(l);
+                }
+            }
+        }
+    }
+    __syncwarp();
 }
 
 // Persistent GEMM: CTA c computes output tiles c, c + grid, ... (tile = m_tile * tiles_n + n_tile).
@@ -164,6 +215,7 @@ gemm_f16split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
         // ===== epilogue: TMEM lane = output row, column = output feature =====
         const uint32_t quarter = warp & 3u;
         const uint32_t half = (warp - 2u) >> 2;  // which 64 of the tile's 128 columns this warp stores
+        float* bias_s = reinterpret_cast<float*>(bars + 32) + (warp - 2u) * 128;
         uint32_t acc = 0, acc_phase = 0;
         for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
             const uint32_t row = (t / tiles_n) * kGemmTileM + quarter * 32u + lane;
@@ -171,39 +223,7 @@ gemm_f16split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * kGemmTileN + half * (kGemmTileN / 2);
-#pragma unroll 1
-            for (uint32_t c = 0; c < kGemmTileN / 64; ++c) {
-                uint32_t v[32];
-                tmem_ld_x32(taddr + c * 32u, v);
-                tmem_ld_wait();
-                if (row < args.m && !args.debug_skip_epilogue) {
-                    const size_t o = (size_t)row * args.n + col0 + c * 32u;
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        float4 r;
-                        const float4 b4 = *reinterpret_cast<const float4*>(args.bias + col0 + c * 32u + i);
-                        r.x = __uint_as_float(v[i]) + b4.x;
-                        r.y = __uint_as_float(v[i + 1]) + b4.y;
-                        r.z = __uint_as_float(v[i + 2]) + b4.z;
-                        r.w = __uint_as_float(v[i + 3]) + b4.w;
-                        if (args.residual) {
-                            const float4 s4 = *reinterpret_cast<const float4*>(args.residual + o + i);
-                            r.x += s4.x; r.y += s4.y; r.z += s4.z; r.w += s4.w;
-                        }
-                        if (args.gelu) {
-                            r.x = gelu_erf(r.x); r.y = gelu_erf(r.y); r.z = gelu_erf(r.z); r.w = gelu_erf(r.w);
-                        }
-                        if (args.out_f32) *reinterpret_cast<float4*>(args.out_f32 + o + i) = r;
-                        if (args.out_hi) {
-                            __half h[4], l[4];
-                            split_f16(r.x, h[0], l[0]); split_f16(r.y, h[1], l[1]);
-                            split_f16(r.z, h[2], l[2]); split_f16(r.w, h[3], l[3]);
-                            *reinterpret_cast<uint2*>(args.out_hi + o + i) = *reinterpret_cast<uint2*>(h);
-                            *reinterpret_cast<uint2*>(args.out_lo + o + i) = *reinterpret_cast<uint2*>(l);
-                        }
-                    }
-                }
-            }
+            gemm_epilogue_warp(args, taddr, row, col0, kGemmTileN / 2, bias_s, lane);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -218,6 +238,167 @@ gemm_f16split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc(tmem_base, kGemmAccStages * kGemmTileN);
+    }
+}
+
+// ─── the same GEMM on CTA pairs ─────────────────────────────────────────────────────────────
+// With K = 384 and 128 x 128 tiles the single-CTA GEMM re-reads ~21 GB of A/W tiles from L2 per
+// 1024-query batch and sits at the L2->SM fabric limit (22-62 % tensor-pipe active).  Here two CTAs
+// of a cluster share one tcgen05.mma.cta_group::2: M = 256 output rows (128 per CTA: its A tile in
+// its own shared memory, its accumulators in its own TMEM) x N = 256 features (each CTA TMA-loads
+// 128 weight rows), i.e. half the L2 traffic per flop.  A 128-wide tail tile (N % 256 == 128) uses
+// the N = 128 instruction shape with 64 weight rows per CTA.  Barrier protocol as in
+// mma_scan_pair_kernel: `full` / `tmem_empty` on the leader, `empty` / `tmem_full` multicast.
+constexpr int kGemmPairN = 256;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_f16split_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                          const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
+                          const __grid_constant__ CUtensorMap tm_w64_hi, const __grid_constant__ CUtensorMap tm_w64_lo,
+                          const GemmArgs args) {
+    extern __shared__ uint8_t smem_dyn[];
+    const uint32_t raw = smem_u32(smem_dyn);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_dyn + (base - raw);
+    const uint32_t per_stage = (args.products == 3 ? 4u : 2u) * kMmaTileBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base_ptr + (size_t)args.n_stages * per_stage);
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](uint32_t s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](uint32_t s) { return bar0 + 8u * (8u + s); };
+    auto tfull_bar = [&](uint32_t a) { return bar0 + 8u * (16u + a); };
+    auto tempty_bar = [&](uint32_t a) { return bar0 + 8u * (20u + a); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const uint32_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const uint32_t tiles_m = (args.m + 2 * kGemmTileM - 1) / (2 * kGemmTileM);
+    const uint32_t tiles_n = (args.n + kGemmPairN - 1) / kGemmPairN;  // the last one may be 128 wide
+    const uint32_t n_tiles = tiles_m * tiles_n, n_kb = args.k / kMmaKBlock;
+    auto tile_width = [&](uint32_t nt) { return min((uint32_t)kGemmPairN, args.n - nt * kGemmPairN); };
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_a_hi);
+        tma_prefetch_desc(&tm_w_hi);
+        for (uint32_t s = 0; s < args.n_stages; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (uint32_t a = 0; a < kGemmAccStages; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 16);  // 8 epilogue warps of both CTAs
+        }
+        fence_barrier_init();
+    } else if (warp == 2) {
+        tmem_alloc_pair(smem_u32(tmem_slot), kGemmAccStages * kGemmPairN);
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs; completion bytes land on the leader's barriers) =====
+        uint32_t stage = 0, phase = 0;
+        for (uint32_t t = pair; t < n_tiles; t += n_pairs) {
+            const uint32_t nt = t % tiles_n, width = tile_width(nt);
+            const int32_t row_a = (int32_t)((t / tiles_n) * 2 * kGemmTileM + rank * kGemmTileM);
+            const int32_t row_w = (int32_t)(nt * kGemmPairN + rank * (width / 2));
+            const bool wide = width == kGemmPairN;
+            const uint32_t w_bytes = wide ? kMmaTileBytes : kMmaTileBytes / 2;
+            const uint32_t bytes_per_cta = (args.products == 3 ? 2u : 1u) * (kMmaTileBytes + w_bytes);
+            for (uint32_t kb = 0; kb < n_kb; ++kb) {
+                mbar_wait(empty_bar(stage), phase ^ 1u);
+                if (elect_one()) {
+                    const uint32_t s0 = base + stage * per_stage;
+                    const int32_t kc = (int32_t)(kb * kMmaKBlock);
+                    if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * bytes_per_cta);
+                    tma_load_2d_pair(s0, &tm_a_hi, full_bar(stage), kc, row_a);
+                    tma_load_2d_pair(s0 + kMmaTileBytes, wide ? &tm_w_hi : &tm_w64_hi, full_bar(stage), kc, row_w);
+                    if (args.products == 3) {
+                        tma_load_2d_pair(s0 + 2 * kMmaTileBytes, &tm_a_lo, full_bar(stage), kc, row_a);
+                        tma_load_2d_pair(s0 + 3 * kMmaTileBytes, wide ? &tm_w_lo : &tm_w64_lo, full_bar(stage), kc, row_w);
+                    }
+                }
+                __syncwarp();
+                if (++stage == args.n_stages) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0) {
+            // ===== MMA issuer (leader CTA only) =====
+            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            for (uint32_t t = pair; t < n_tiles; t += n_pairs) {
+                const uint32_t idesc = tile_width(t % tiles_n) == kGemmPairN ? umma_idesc_f16(2 * kGemmTileM, kGemmPairN)
+                                                                             : umma_idesc_f16(2 * kGemmTileM, kGemmPairN / 2);
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * kGemmPairN;
+                for (uint32_t kb = 0; kb < n_kb; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t s0 = base + stage * per_stage;
+                        const uint64_t a_hi = umma_desc_sw128(s0), w_hi = umma_desc_sw128(s0 + kMmaTileBytes);
+                        const uint64_t a_lo = umma_desc_sw128(s0 + 2 * kMmaTileBytes);
+                        const uint64_t w_lo = umma_desc_sw128(s0 + 3 * kMmaTileBytes);
+#pragma unroll
+                        for (uint32_t k4 = 0; k4 < kMmaKBlock / 16; ++k4)
+                            umma_f16_pair(d_tmem, a_hi + 2u * k4, w_hi + 2u * k4, idesc, (kb | k4) != 0u ? 1u : 0u);
+                        if (args.products == 3) {
+#pragma unroll
+                            for (uint32_t k4 = 0; k4 < kMmaKBlock / 16; ++k4) {
+                                umma_f16_pair(d_tmem, a_lo + 2u * k4, w_hi + 2u * k4, idesc, 1u);
+                                umma_f16_pair(d_tmem, a_hi + 2u * k4, w_lo + 2u * k4, idesc, 1u);
+                            }
+                        }
+                        umma_commit_pair(empty_bar(stage));
+                        if (kb + 1 == n_kb) umma_commit_pair(tfull_bar(acc));
+                    }
+                    __syncwarp();
+                    if (++stage == args.n_stages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                if (++acc == kGemmAccStages) {
+                    acc = 0;
+                    acc_phase ^= 1u;
+                }
+            }
+        }
+    } else {
+        // ===== epilogue (both CTAs): TMEM lane = one of this CTA's 128 rows, column = feature =====
+        const uint32_t quarter = warp & 3u;
+        const uint32_t half = (warp - 2u) >> 2;
+        float* bias_s = reinterpret_cast<float*>(bars + 32) + (warp - 2u) * 128;
+        uint32_t acc = 0, acc_phase = 0;
+        for (uint32_t t = pair; t < n_tiles; t += n_pairs) {
+            const uint32_t nt = t % tiles_n, width = tile_width(nt);
+            const uint32_t row = (t / tiles_n) * 2 * kGemmTileM + rank * kGemmTileM + quarter * 32u + lane;
+            const uint32_t cols_per_warp = width / 2;  // 128 or 64
+            const uint32_t col0 = nt * kGemmPairN + half * cols_per_warp;
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * kGemmPairN + half * cols_per_warp;
+            gemm_epilogue_warp(args, taddr, row, col0, cols_per_warp, bias_s, lane);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tempty_bar(acc), 0);
+            if (++acc == kGemmAccStages) {
+                acc = 0;
+                acc_phase ^= 1u;
+            }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, kGemmAccStages * kGemmPairN);
     }
 }
 

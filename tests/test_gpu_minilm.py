@@ -114,6 +114,21 @@ def test_minilm_single_product_mode_is_within_tolerance(fs, bert):
     assert np.all(cos >= 1.0 - 1e-3), cos.min()
 
 
+def test_minilm_cta_pair_gemm_variant_matches(fs, bert):
+    """FSGPU_MINILM_PAIR=1: the cta_group::2 256 x 256 tile form of the same GEMMs (incl. the
+    128-wide tail tiles of N = 1152 and N = 384)."""
+    rng = np.random.default_rng(7)
+    batches = random_batches(rng, 40, 8, 32)  # 40 * 32 = 1280 rows >= one 256-row pair tile
+    e = fs.MiniLmEmbedder(mr.state_dict_numpy(bert))
+    os.environ["FSGPU_MINILM_PAIR"] = "1"
+    try:
+        got = e.embed_token_ids_batch(batches)
+    finally:
+        del os.environ["FSGPU_MINILM_PAIR"]
+        e.close()
+    assert check(got, mr.reference_embed(bert, batches)) <= 2e-4
+
+
 def test_minilm_errors(fs, bert):
     sd = mr.state_dict_numpy(bert)
     bad = dict(sd)
