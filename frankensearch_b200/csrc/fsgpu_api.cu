@@ -16,8 +16,7 @@
 
 #include "fsgpu.h"
 #include "fsgpu_common.cuh"
-#include "fusion_kernels.cuh"
-#include "minilm_kernels.cuh"
+#include "fsgpu_host.cuh"
 #include "mma_scan_kernels.cuh"
 #include "scan_kernels.cuh"
 #include "synth_kernels.cuh"
@@ -27,7 +26,7 @@ using namespace fsgpu;
 // ─── errors ─────────────────────────────────────────────────────────────────────────────────
 static thread_local std::string g_last_error;
 
-static int fail(int code, const char* fmt, ...) {
+int fsgpu_fail(int code, const char* fmt, ...) {
     char buf[1024];
     va_list ap;
     va_start(ap, fmt);
@@ -36,14 +35,6 @@ static int fail(int code, const char* fmt, ...) {
     g_last_error = buf;
     return code;
 }
-
-#define CUDA_TRY(expr)                                                                         \
-    do {                                                                                       \
-        cudaError_t _e = (expr);                                                               \
-        if (_e != cudaSuccess)                                                                 \
-            return fail(FSGPU_ERR_SUBSYSTEM, "gpu: %s failed: %s (%s:%d)", #expr,              \
-                        cudaGetErrorString(_e), __FILE__, __LINE__);                           \
-    } while (0)
 
 extern "C" const char* fsgpu_last_error(void) { return g_last_error.c_str(); }
 extern "C" int fsgpu_abi_version(void) { return FSGPU_ABI_VERSION; }
@@ -68,40 +59,6 @@ extern "C" void fsgpu_index_options_default(fsgpu_index_options* o) {
     o->slab_is_device = 0;
     o->row_base = 0;
 }
-
-// ─── small RAII device buffer that only grows ───────────────────────────────────────────────
-struct DevBuf {
-    void* p = nullptr;
-    size_t bytes = 0;
-    cudaError_t reserve(size_t want) {
-        if (want <= bytes) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr;
-        bytes = 0;
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e == cudaSuccess) bytes = want;
-        return e;
-    }
-    void release() {
-        if (p) cudaFree(p);
-        p = nullptr;
-        bytes = 0;
-    }
-    template <class T>
-    T* as() const { return reinterpret_cast<T*>(p); }
-};
-
-struct DeviceGuard {
-    int prev = -1;
-    bool ok = false;
-    explicit DeviceGuard(int dev) {
-        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
-        ok = cudaSetDevice(dev) == cudaSuccess;
-    }
-    ~DeviceGuard() {
-        if (prev >= 0) cudaSetDevice(prev);
-    }
-};
 
 // ─── the index handle ───────────────────────────────────────────────────────────────────────
 struct fsgpu_index {
@@ -139,19 +96,9 @@ struct fsgpu_index {
     std::vector<uint64_t> doc_off;
 };
 
-static int env_int(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return (v && *v) ? atoi(v) : dflt;
-}
-
 // ─── launch planning ────────────────────────────────────────────────────────────────────────
 constexpr uint32_t kFusedMaxK = 1024;
 
-static uint32_t host_next_pow2(uint32_t x) {
-    uint32_t p = 1;
-    while (p < x) p <<= 1;
-    return p;
-}
 static uint32_t cand_capacity(uint32_t k) { return host_next_pow2(std::max(2 * k, k + 512)); }
 
 typedef void (*ScanKernel)(const ScanArgs);
@@ -375,15 +322,15 @@ static EncodeTiledFn encode_tiled_fn() {
 
 // TMA descriptor of a row-major [rows, dim] f16 matrix read as [128 rows x 64 elements] boxes with
 // the 128-byte swizzle the UMMA shared-memory descriptors expect.
-static bool make_f16_tile_map(CUtensorMap* tm, const void* base, uint64_t rows, uint32_t dim, bool stream_once,
-                              uint32_t box_rows = kMmaN) {
+bool fsgpu_tma_available() { return encode_tiled_fn() != nullptr; }
+
+bool make_f16_tile_map(CUtensorMap* tm, const void* base, uint64_t rows, uint32_t dim, uint32_t box_rows) {
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc || rows == 0) return false;
     const cuuint64_t gdim[2] = {dim, rows};
     const cuuint64_t gstride[1] = {(cuuint64_t)dim * 2};
     const cuuint32_t box[2] = {(cuuint32_t)kMmaKBlock, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
-    (void)stream_once;
     return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -411,7 +358,7 @@ static int index_finish_setup(fsgpu_index* ix) {
     memcpy(&norm, &stats[0], 4);
     ix->max_row_norm = norm * 1.0001f;
     const bool finite = stats[1] == 0 && std::isfinite(ix->max_row_norm);
-    ix->mma_ok = finite && make_f16_tile_map(&ix->tm_slab, ix->d_slab, ix->n_rows, ix->dim, true);
+    ix->mma_ok = finite && make_f16_tile_map(&ix->tm_slab, ix->d_slab, ix->n_rows, ix->dim);
     return FSGPU_OK;
 }
 
@@ -514,7 +461,7 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
         CUDA_TRY(ix->ws_cand.reserve((size_t)grid * 2 * kMmaM * cap * sizeof(MmaCand)));
         CUDA_TRY(ix->ws_cand_count.reserve((size_t)grid * 2 * kMmaM * 4));
         if (ix->tm_qhat_ptr != ix->ws_qhat.p || ix->tm_qhat_rows != slots) {
-            if (!make_f16_tile_map(&ix->tm_qhat, ix->ws_qhat.p, slots, ix->dim, false))
+            if (!make_f16_tile_map(&ix->tm_qhat, ix->ws_qhat.p, slots, ix->dim))
                 return fail(FSGPU_ERR_SUBSYSTEM, "gpu: cuTensorMapEncodeTiled failed for the query tile");
             ix->tm_qhat_ptr = ix->ws_qhat.p;
             ix->tm_qhat_rows = slots;
@@ -1099,292 +1046,6 @@ extern "C" int fsgpu_scores_for_rows(const fsgpu_index* ix, const float* query, 
     return FSGPU_OK;
 }
 
-// ─── fusion ─────────────────────────────────────────────────────────────────────────────────
-static void sanitize_rrf(const fsgpu_rrf_config* c, RrfArgs* a) {
-    double k = c ? c->k : 60.0, wl = c ? c->lexical_weight : 1.0, ws = c ? c->semantic_weight : 1.0;
-    if (!(std::isfinite(k) && k >= 0.0)) k = 60.0;        // rrf.rs:124-130
-    if (!(std::isfinite(wl) && wl > 0.0)) wl = 1.0;       // rrf.rs:92-98
-    if (!(std::isfinite(ws) && ws > 0.0)) ws = 1.0;
-    a->k = k;
-    a->w_lex = wl;
-    a->w_sem = ws;
-    a->tiebreak = c ? c->tiebreak : 0;
-}
-
-static int launch_rrf(RrfArgs& a, uint32_t batch, cudaStream_t s) {
-    const uint32_t m = a.n_lex_max + a.n_sem_max;
-    if (m > kFusionMaxEntries)
-        return fail(FSGPU_ERR_INVALID_CONFIG, "rrf: %u candidates exceed the device window of %u", m,
-                    kFusionMaxEntries);
-    const size_t smem = (size_t)host_next_pow2(std::max(m, 1u)) * 20 + 16;
-    CUDA_TRY(cudaFuncSetAttribute(rrf_fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    rrf_fuse_kernel<<<batch, kFusionThreads, smem, s>>>(a);
-    CUDA_TRY(cudaGetLastError());
-    return FSGPU_OK;
-}
-
-extern "C" int fsgpu_rrf_fuse_device(int device, const fsgpu_rrf_config* config, uint32_t batch,
-                                     const uint64_t* d_lex_ids, const float* d_lex_scores,
-                                     const uint32_t* d_lex_tie, const uint32_t* d_lex_counts,
-                                     uint32_t n_lex_max, const fsgpu_hit* d_sem_hits,
-                                     const uint32_t* d_sem_tie, const uint32_t* d_sem_counts,
-                                     uint32_t n_sem_max, uint32_t limit, uint32_t offset,
-                                     fsgpu_fused_hit* d_out, uint32_t* d_out_counts, void* stream) {
-    if (batch == 0) return FSGPU_OK;
-    DeviceGuard g(device);
-    cudaStream_t s = (cudaStream_t)stream;
-    if (limit == 0) {
-        if (d_out_counts) CUDA_TRY(cudaMemsetAsync(d_out_counts, 0, (size_t)batch * 4, s));
-        return FSGPU_OK;
-    }
-    RrfArgs a{};
-    sanitize_rrf(config, &a);
-    a.lex_ids = d_lex_ids;
-    a.lex_scores = d_lex_scores;
-    a.lex_tie = d_lex_tie;
-    a.lex_counts = d_lex_counts;
-    a.n_lex_max = n_lex_max;
-    a.sem_hits = d_sem_hits;
-    a.sem_tie = d_sem_tie;
-    a.sem_counts = d_sem_counts;
-    a.n_sem_max = n_sem_max;
-    a.limit = limit;
-    a.offset = offset;
-    a.out = d_out;
-    a.out_counts = d_out_counts;
-    int rc = launch_rrf(a, batch, s);
-    if (rc) return rc;
-    if (!stream) CUDA_TRY(cudaStreamSynchronize(s));
-    return FSGPU_OK;
-}
-
-namespace {
-struct Staging {  // one-shot device staging for the host fusion/encoder entry points
-    std::vector<void*> ptrs;
-    ~Staging() {
-        for (void* p : ptrs) cudaFree(p);
-    }
-    template <class T>
-    cudaError_t up(const T* host, size_t count, T** dev) {
-        *dev = nullptr;
-        if (!host || count == 0) return cudaSuccess;
-        void* p = nullptr;
-        cudaError_t e = cudaMalloc(&p, count * sizeof(T));
-        if (e != cudaSuccess) return e;
-        ptrs.push_back(p);
-        *dev = reinterpret_cast<T*>(p);
-        return cudaMemcpy(p, host, count * sizeof(T), cudaMemcpyHostToDevice);
-    }
-    template <class T>
-    cudaError_t alloc(size_t count, T** dev) {
-        void* p = nullptr;
-        cudaError_t e = cudaMalloc(&p, std::max<size_t>(1, count) * sizeof(T));
-        if (e != cudaSuccess) return e;
-        ptrs.push_back(p);
-        *dev = reinterpret_cast<T*>(p);
-        return cudaSuccess;
-    }
-};
-}  // namespace
-
-extern "C" int fsgpu_rrf_fuse(int device, const fsgpu_rrf_config* config, uint32_t batch,
-                              const uint64_t* lex_ids, const float* lex_scores, const uint32_t* lex_tie,
-                              const uint32_t* lex_counts, uint32_t n_lex_max, const uint32_t* sem_rows,
-                              const float* sem_scores, const uint32_t* sem_tie, const uint32_t* sem_counts,
-                              uint32_t n_sem_max, uint32_t limit, uint32_t offset, fsgpu_fused_hit* out,
-                              uint32_t* out_counts) {
-    if (batch == 0) return FSGPU_OK;
-    if (!out_counts) return fail(FSGPU_ERR_INVALID_CONFIG, "out_counts is NULL");
-    int ndev = 0;
-    int rc = fsgpu_device_count(&ndev);
-    if (rc) return rc;
-    if (device < 0 || device >= ndev) return fail(FSGPU_ERR_INVALID_CONFIG, "device %d not present", device);
-    if (limit == 0) {  // rrf.rs:1172-1183 window == 0
-        memset(out_counts, 0, (size_t)batch * 4);
-        return FSGPU_OK;
-    }
-    if (!out) return fail(FSGPU_ERR_INVALID_CONFIG, "out is NULL");
-    const size_t nl = (size_t)batch * n_lex_max, ns = (size_t)batch * n_sem_max;
-    for (size_t i = 0; i < nl; ++i)
-        if (lex_ids[i] >> 40) return fail(FSGPU_ERR_INVALID_CONFIG, "rrf: lexical id exceeds 40 bits");
-    for (const uint32_t* t : {lex_tie, sem_tie})
-        if (t)
-            for (size_t i = 0; i < (t == lex_tie ? nl : ns); ++i)
-                if (t[i] >> kTieBits)
-                    return fail(FSGPU_ERR_INVALID_CONFIG, "rrf: tie rank exceeds %u bits", kTieBits);
-    DeviceGuard g(device);
-    Staging st;
-    RrfArgs a{};
-    sanitize_rrf(config, &a);
-    uint64_t* d_lex_ids; float* d_lex_scores; uint32_t *d_lex_tie, *d_lex_counts;
-    uint32_t *d_sem_rows, *d_sem_tie, *d_sem_counts; float* d_sem_scores;
-    fsgpu_fused_hit* d_out; uint32_t* d_out_counts;
-    CUDA_TRY(st.up(lex_ids, nl, &d_lex_ids));
-    CUDA_TRY(st.up(lex_scores, nl, &d_lex_scores));
-    CUDA_TRY(st.up(lex_tie, nl, &d_lex_tie));
-    CUDA_TRY(st.up(lex_counts, batch, &d_lex_counts));
-    CUDA_TRY(st.up(sem_rows, ns, &d_sem_rows));
-    CUDA_TRY(st.up(sem_scores, ns, &d_sem_scores));
-    CUDA_TRY(st.up(sem_tie, ns, &d_sem_tie));
-    CUDA_TRY(st.up(sem_counts, batch, &d_sem_counts));
-    CUDA_TRY(st.alloc((size_t)batch * limit, &d_out));
-    CUDA_TRY(st.alloc(batch, &d_out_counts));
-    a.lex_ids = d_lex_ids; a.lex_scores = d_lex_scores; a.lex_tie = d_lex_tie; a.lex_counts = d_lex_counts;
-    a.n_lex_max = n_lex_max;
-    a.sem_rows = d_sem_rows; a.sem_scores = d_sem_scores; a.sem_tie = d_sem_tie; a.sem_counts = d_sem_counts;
-    a.n_sem_max = n_sem_max;
-    a.limit = limit; a.offset = offset; a.out = d_out; a.out_counts = d_out_counts;
-    rc = launch_rrf(a, batch, nullptr);
-    if (rc) return rc;
-    CUDA_TRY(cudaMemcpy(out, d_out, (size_t)batch * limit * sizeof(fsgpu_fused_hit), cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(out_counts, d_out_counts, (size_t)batch * 4, cudaMemcpyDeviceToHost));
-    return FSGPU_OK;
-}
-
-extern "C" int fsgpu_blend_two_tier(int device, float blend_factor, const uint32_t* fast_rows,
-                                    const float* fast_scores, const uint32_t* fast_tie, uint32_t n_fast,
-                                    const uint32_t* quality_rows, const float* quality_scores,
-                                    const uint8_t* quality_present, const uint32_t* quality_tie,
-                                    uint32_t n_quality, fsgpu_hit* out, uint32_t* out_count) {
-    if (!out_count) return fail(FSGPU_ERR_INVALID_CONFIG, "out_count is NULL");
-    int ndev = 0;
-    int rc = fsgpu_device_count(&ndev);
-    if (rc) return rc;
-    if (device < 0 || device >= ndev) return fail(FSGPU_ERR_INVALID_CONFIG, "device %d not present", device);
-    const bool union_form = quality_rows != nullptr;
-    if (!union_form && n_quality != n_fast && n_quality != 0)
-        return fail(FSGPU_ERR_INVALID_CONFIG, "aligned blend needs one quality slot per fast hit");
-    const uint32_t m = n_fast + (union_form ? n_quality : 0);
-    if (m == 0) {
-        *out_count = 0;
-        return FSGPU_OK;
-    }
-    if (m > kFusionMaxEntries)
-        return fail(FSGPU_ERR_INVALID_CONFIG, "blend: %u hits exceed the device window of %u", m, kFusionMaxEntries);
-    DeviceGuard g(device);
-    Staging st;
-    BlendArgs a{};
-    float alpha = blend_factor;  // blend.rs:518-524
-    if (!std::isfinite(alpha)) alpha = 0.7f;
-    alpha = std::min(1.0f, std::max(0.0f, alpha));
-    a.alpha = alpha;
-    uint32_t *d_fr, *d_ft, *d_qr, *d_qt; float *d_fs, *d_qs; uint8_t* d_qp; fsgpu_hit* d_out; uint32_t* d_cnt;
-    std::vector<uint8_t> none;
-    const uint32_t nq_eff = union_form ? n_quality : n_fast;
-    if (!union_form && n_quality == 0) {  // aligned form with no quality scores at all
-        none.assign(n_fast, 0);
-        quality_present = none.data();
-    }
-    std::vector<float> zero_q;
-    if (!quality_scores) {
-        zero_q.assign(nq_eff, 0.0f);
-        quality_scores = zero_q.data();
-    }
-    CUDA_TRY(st.up(fast_rows, n_fast, &d_fr));
-    CUDA_TRY(st.up(fast_scores, n_fast, &d_fs));
-    CUDA_TRY(st.up(fast_tie, n_fast, &d_ft));
-    CUDA_TRY(st.up(quality_rows, union_form ? n_quality : 0, &d_qr));
-    CUDA_TRY(st.up(quality_scores, nq_eff, &d_qs));
-    CUDA_TRY(st.up(quality_present, union_form ? 0 : n_fast, &d_qp));
-    CUDA_TRY(st.up(quality_tie, union_form ? n_quality : 0, &d_qt));
-    CUDA_TRY(st.alloc(m, &d_out));
-    CUDA_TRY(st.alloc(1, &d_cnt));
-    a.fast_rows = d_fr; a.fast_scores = d_fs; a.fast_tie = d_ft; a.n_fast = n_fast;
-    a.quality_rows = d_qr; a.quality_scores = d_qs; a.quality_present = d_qp; a.quality_tie = d_qt;
-    a.n_quality = nq_eff;
-    a.out = d_out; a.out_count = d_cnt;
-    const size_t smem = (size_t)host_next_pow2(m) * 20 + 16;
-    CUDA_TRY(cudaFuncSetAttribute(blend_two_tier_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    blend_two_tier_kernel<<<1, kFusionThreads, smem>>>(a);
-    CUDA_TRY(cudaGetLastError());
-    uint32_t cnt = 0;
-    CUDA_TRY(cudaMemcpy(&cnt, d_cnt, 4, cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(out, d_out, (size_t)cnt * sizeof(fsgpu_hit), cudaMemcpyDeviceToHost));
-    *out_count = cnt;
-    return FSGPU_OK;
-}
-
-// ─── potion ─────────────────────────────────────────────────────────────────────────────────
-struct fsgpu_potion {
-    int device = 0;
-    uint64_t vocab = 0;
-    uint32_t dim = 0;
-    float* d_table = nullptr;
-    cudaStream_t stream = nullptr;
-    mutable std::mutex mu;
-};
-
-extern "C" void fsgpu_potion_destroy(fsgpu_potion* e) {
-    if (!e) return;
-    {
-        DeviceGuard g(e->device);
-        if (e->stream) {
-            cudaStreamSynchronize(e->stream);
-            cudaStreamDestroy(e->stream);
-        }
-        if (e->d_table) cudaFree(e->d_table);
-    }
-    delete e;
-}
-
-extern "C" int fsgpu_potion_create(const float* table, uint64_t vocab, uint32_t dim, int device,
-                                   fsgpu_potion** out) {
-    if (!out) return fail(FSGPU_ERR_INVALID_CONFIG, "out is NULL");
-    *out = nullptr;
-    if (!table || vocab == 0 || dim == 0)  // validate_model2vec_accumulation_shape (embed/src/simd.rs:118+)
-        return fail(FSGPU_ERR_INVALID_CONFIG, "potion table must be a non-empty [vocab, dim] matrix");
-    int ndev = 0;
-    int rc = fsgpu_device_count(&ndev);
-    if (rc) return rc;
-    if (device < 0 || device >= ndev) return fail(FSGPU_ERR_INVALID_CONFIG, "device %d not present", device);
-    fsgpu_potion* e = new fsgpu_potion();
-    e->device = device;
-    e->vocab = vocab;
-    e->dim = dim;
-    DeviceGuard g(device);
-    cudaError_t err = cudaMalloc(&e->d_table, vocab * dim * 4);
-    if (err == cudaSuccess) err = cudaMemcpy(e->d_table, table, vocab * dim * 4, cudaMemcpyHostToDevice);
-    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
-    if (err != cudaSuccess) {
-        fsgpu_potion_destroy(e);
-        return fail(FSGPU_ERR_SUBSYSTEM, "gpu: potion table upload failed: %s", cudaGetErrorString(err));
-    }
-    *out = e;
-    return FSGPU_OK;
-}
-
-extern "C" int fsgpu_potion_embed_device(const fsgpu_potion* e, const uint32_t* d_ids, const uint64_t* d_offsets,
-                                         uint32_t batch, float* d_out, void* stream) {
-    if (!e) return fail(FSGPU_ERR_INVALID_CONFIG, "encoder is NULL");
-    if (batch == 0) return FSGPU_OK;
-    std::lock_guard<std::mutex> lock(e->mu);
-    DeviceGuard g(e->device);
-    cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
-    potion_embed_kernel<<<batch, 256, (size_t)e->dim * 4, s>>>(e->d_table, e->vocab, e->dim, d_ids, d_offsets, d_out);
-    CUDA_TRY(cudaGetLastError());
-    if (!stream) CUDA_TRY(cudaStreamSynchronize(s));
-    return FSGPU_OK;
-}
-
-extern "C" int fsgpu_potion_embed(const fsgpu_potion* e, const uint32_t* ids, const uint64_t* offsets,
-                                  uint32_t batch, float* out) {
-    if (!e) return fail(FSGPU_ERR_INVALID_CONFIG, "encoder is NULL");
-    if (batch == 0) return FSGPU_OK;
-    if (!offsets || !out) return fail(FSGPU_ERR_INVALID_CONFIG, "NULL argument");
-    const uint64_t total = offsets[batch];
-    DeviceGuard g(e->device);
-    Staging st;
-    uint32_t* d_ids; uint64_t* d_off; float* d_out;
-    std::vector<uint32_t> pad(1, 0);
-    CUDA_TRY(st.up(total ? ids : pad.data(), std::max<uint64_t>(1, total), &d_ids));
-    CUDA_TRY(st.up(offsets, (size_t)batch + 1, &d_off));
-    CUDA_TRY(st.alloc((size_t)batch * e->dim, &d_out));
-    int rc = fsgpu_potion_embed_device(e, d_ids, d_off, batch, d_out, nullptr);
-    if (rc) return rc;
-    CUDA_TRY(cudaMemcpy(out, d_out, (size_t)batch * e->dim * 4, cudaMemcpyDeviceToHost));
-    return FSGPU_OK;
-}
-
 // ─── synthetic corpora ──────────────────────────────────────────────────────────────────────
 extern "C" int fsgpu_synth_rows_device(int device, int kind, uint64_t seed_base, uint64_t row_start,
                                        uint64_t n_rows, uint32_t dim, uint32_t n_centroids, float noise,
@@ -1539,349 +1200,3 @@ extern "C" int fsgpu_index_open_fsvi(const char* path, uint64_t row_start, uint6
     return FSGPU_OK;
 }
 
-// ─── MiniLM-L6 encoder ──────────────────────────────────────────────────────────────────────
-namespace {
-struct SplitMat {  // an f32 matrix carried as hi + lo f16 halves, with its TMA descriptors
-    __half *hi = nullptr, *lo = nullptr;
-    CUtensorMap tm_hi, tm_lo;      // [128 rows x 64] boxes
-    CUtensorMap tm64_hi, tm64_lo;  // [64 rows x 64] boxes (weights: the 128-wide tail tile of the pair GEMM)
-    uint64_t rows = 0;
-    uint32_t cols = 0;
-};
-struct MiniLmLayer {
-    SplitMat qkv, attn_out, ffn_in, ffn_out;
-    float *qkv_b = nullptr, *attn_out_b = nullptr, *attn_ln_g = nullptr, *attn_ln_b = nullptr, *ffn_in_b = nullptr,
-          *ffn_out_b = nullptr, *ffn_ln_g = nullptr, *ffn_ln_b = nullptr;
-};
-}  // namespace
-
-struct fsgpu_minilm {
-    int device = 0, num_sms = 0;
-    uint32_t vocab = 0, max_pos = 0, n_layers = 0, hidden = 0, inter = 0;
-    float eps = 1e-12f;
-    float *word = nullptr, *pos = nullptr, *type0 = nullptr, *emb_g = nullptr, *emb_b = nullptr;
-    std::vector<MiniLmLayer> layers;
-    std::vector<void*> owned;  // every device allocation of the weights
-    cudaStream_t stream = nullptr;
-    mutable std::mutex mu;
-    // activations (grow-only, guarded by mu)
-    mutable DevBuf ws_h32, ws_pre32, ws_qkv32, ws_ids, ws_lens, ws_out;
-    mutable SplitMat act_h, act_ctx, act_ffn;
-    mutable uint64_t act_rows = 0;
-    mutable bool profiling = false;
-    mutable fsgpu_minilm_profile prof{};
-    mutable std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pending, ev_free;
-};
-
-static int minilm_upload(fsgpu_minilm* e, const float* host, size_t count, float** dev) {
-    if (!host) return fail(FSGPU_ERR_INVALID_CONFIG, "minilm: a weight pointer is NULL");
-    CUDA_TRY(cudaMalloc(dev, count * 4));
-    e->owned.push_back(*dev);
-    CUDA_TRY(cudaMemcpy(*dev, host, count * 4, cudaMemcpyHostToDevice));
-    return FSGPU_OK;
-}
-
-static int minilm_upload_split(fsgpu_minilm* e, const float* host, uint64_t rows, uint32_t cols, SplitMat* m) {
-    float* tmp = nullptr;
-    if (!host) return fail(FSGPU_ERR_INVALID_CONFIG, "minilm: a weight pointer is NULL");
-    const size_t n = (size_t)rows * cols;
-    CUDA_TRY(cudaMalloc(&tmp, n * 4));
-    cudaError_t err = cudaMemcpy(tmp, host, n * 4, cudaMemcpyHostToDevice);
-    if (err == cudaSuccess) err = cudaMalloc(&m->hi, n * 2);
-    if (err == cudaSuccess) e->owned.push_back(m->hi);
-    if (err == cudaSuccess) err = cudaMalloc(&m->lo, n * 2);
-    if (err == cudaSuccess) e->owned.push_back(m->lo);
-    if (err == cudaSuccess) {
-        split_f16_kernel<<<e->num_sms * 4, 256, 0, e->stream>>>(tmp, n, m->hi, m->lo);
-        err = cudaGetLastError();
-        if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
-    }
-    cudaFree(tmp);
-    if (err != cudaSuccess) return fail(FSGPU_ERR_SUBSYSTEM, "gpu: minilm weight upload failed: %s", cudaGetErrorString(err));
-    m->rows = rows;
-    m->cols = cols;
-    if (!make_f16_tile_map(&m->tm_hi, m->hi, rows, cols, false) || !make_f16_tile_map(&m->tm_lo, m->lo, rows, cols, false) ||
-        !make_f16_tile_map(&m->tm64_hi, m->hi, rows, cols, false, 64) ||
-        !make_f16_tile_map(&m->tm64_lo, m->lo, rows, cols, false, 64))
-        return fail(FSGPU_ERR_SUBSYSTEM, "gpu: cuTensorMapEncodeTiled failed for a minilm weight");
-    return FSGPU_OK;
-}
-
-extern "C" void fsgpu_minilm_destroy(fsgpu_minilm* e) {
-    if (!e) return;
-    {
-        DeviceGuard g(e->device);
-        if (e->stream) cudaStreamSynchronize(e->stream);
-        for (void* p : e->owned) cudaFree(p);
-        for (SplitMat* m : {&e->act_h, &e->act_ctx, &e->act_ffn}) {
-            if (m->hi) cudaFree(m->hi);
-            if (m->lo) cudaFree(m->lo);
-        }
-        for (DevBuf* b : {&e->ws_h32, &e->ws_pre32, &e->ws_qkv32, &e->ws_ids, &e->ws_lens, &e->ws_out}) b->release();
-        for (auto* v : {&e->ev_pending, &e->ev_free})
-            for (auto& ev : *v) {
-                cudaEventDestroy(ev.first);
-                cudaEventDestroy(ev.second);
-            }
-        if (e->stream) cudaStreamDestroy(e->stream);
-    }
-    delete e;
-}
-
-extern "C" int fsgpu_minilm_create(const fsgpu_minilm_weights* w, int device, fsgpu_minilm** out) {
-    if (!out) return fail(FSGPU_ERR_INVALID_CONFIG, "out is NULL");
-    *out = nullptr;
-    if (!w || !w->layers) return fail(FSGPU_ERR_INVALID_CONFIG, "minilm: weights is NULL");
-    if (w->hidden != kHidden || w->heads != kHeads)
-        return fail(FSGPU_ERR_INVALID_CONFIG, "minilm: only hidden=384 / heads=12 (all-MiniLM-L6-v2 geometry) is built, got %u / %u",
-                    w->hidden, w->heads);
-    if (w->intermediate == 0 || w->intermediate % 128 != 0 || w->n_layers == 0 || w->vocab_size == 0 || w->max_positions == 0)
-        return fail(FSGPU_ERR_INVALID_CONFIG, "minilm: bad geometry (intermediate=%u layers=%u vocab=%u positions=%u)",
-                    w->intermediate, w->n_layers, w->vocab_size, w->max_positions);
-    int ndev = 0;
-    int rc = fsgpu_device_count(&ndev);
-    if (rc) return rc;
-    if (device < 0 || device >= ndev) return fail(FSGPU_ERR_INVALID_CONFIG, "device %d not present", device);
-    if (!encode_tiled_fn()) return fail(FSGPU_ERR_SUBSYSTEM, "gpu: cuTensorMapEncodeTiled is unavailable");
-    DeviceGuard g(device);
-    fsgpu_minilm* e = new fsgpu_minilm();
-    e->device = device;
-    cudaDeviceProp prop;
-    cudaError_t err = cudaGetDeviceProperties(&prop, device);
-    if (err == cudaSuccess && prop.major < 10) {
-        delete e;
-        return fail(FSGPU_ERR_SUBSYSTEM, "gpu: device %d is sm_%d%d; this library is built for sm_100a only", device,
-                    prop.major, prop.minor);
-    }
-    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
-    if (err != cudaSuccess) {
-        delete e;
-        return fail(FSGPU_ERR_SUBSYSTEM, "gpu: %s", cudaGetErrorString(err));
-    }
-    e->num_sms = prop.multiProcessorCount;
-    e->vocab = w->vocab_size;
-    e->max_pos = w->max_positions;
-    e->n_layers = w->n_layers;
-    e->hidden = w->hidden;
-    e->inter = w->intermediate;
-    e->eps = w->ln_eps;
-    const uint32_t H = kHidden, I = w->intermediate;
-    rc = minilm_upload(e, w->word_emb, (size_t)w->vocab_size * H, &e->word);
-    if (!rc) rc = minilm_upload(e, w->pos_emb, (size_t)w->max_positions * H, &e->pos);
-    if (!rc) rc = minilm_upload(e, w->type_emb, H, &e->type0);
-    if (!rc) rc = minilm_upload(e, w->emb_ln_g, H, &e->emb_g);
-    if (!rc) rc = minilm_upload(e, w->emb_ln_b, H, &e->emb_b);
-    e->layers.resize(w->n_layers);
-    for (uint32_t i = 0; i < w->n_layers && !rc; ++i) {
-        const fsgpu_minilm_layer_weights& s = w->layers[i];
-        MiniLmLayer& d = e->layers[i];
-        rc = minilm_upload_split(e, s.qkv_w, 3 * H, H, &d.qkv);
-        if (!rc) rc = minilm_upload_split(e, s.attn_out_w, H, H, &d.attn_out);
-        if (!rc) rc = minilm_upload_split(e, s.ffn_in_w, I, H, &d.ffn_in);
-        if (!rc) rc = minilm_upload_split(e, s.ffn_out_w, H, I, &d.ffn_out);
-        if (!rc) rc = minilm_upload(e, s.qkv_b, 3 * H, &d.qkv_b);
-        if (!rc) rc = minilm_upload(e, s.attn_out_b, H, &d.attn_out_b);
-        if (!rc) rc = minilm_upload(e, s.attn_ln_g, H, &d.attn_ln_g);
-        if (!rc) rc = minilm_upload(e, s.attn_ln_b, H, &d.attn_ln_b);
-        if (!rc) rc = minilm_upload(e, s.ffn_in_b, I, &d.ffn_in_b);
-        if (!rc) rc = minilm_upload(e, s.ffn_out_b, H, &d.ffn_out_b);
-        if (!rc) rc = minilm_upload(e, s.ffn_ln_g, H, &d.ffn_ln_g);
-        if (!rc) rc = minilm_upload(e, s.ffn_ln_b, H, &d.ffn_ln_b);
-    }
-    if (rc) {
-        fsgpu_minilm_destroy(e);
-        return rc;
-    }
-    *out = e;
-    return FSGPU_OK;
-}
-
-static int minilm_reserve_act(const fsgpu_minilm* e, SplitMat* m, uint64_t rows, uint32_t cols) {
-    if (m->hi) cudaFree(m->hi);
-    if (m->lo) cudaFree(m->lo);
-    m->hi = m->lo = nullptr;
-    CUDA_TRY(cudaMalloc(&m->hi, (size_t)rows * cols * 2));
-    CUDA_TRY(cudaMalloc(&m->lo, (size_t)rows * cols * 2));
-    m->rows = rows;
-    m->cols = cols;
-    if (!make_f16_tile_map(&m->tm_hi, m->hi, rows, cols, false) || !make_f16_tile_map(&m->tm_lo, m->lo, rows, cols, false))
-        return fail(FSGPU_ERR_SUBSYSTEM, "gpu: cuTensorMapEncodeTiled failed for a minilm activation");
-    (void)e;
-    return FSGPU_OK;
-}
-
-// C[m, n] = A * W^T (+ bias, residual, GELU); caller holds e->mu.
-static int minilm_gemm(const fsgpu_minilm* e, const SplitMat& a, const SplitMat& w, uint32_t m, const float* bias,
-                       const float* residual, float* out_f32, __half* out_hi, __half* out_lo, int gelu,
-                       uint32_t products, cudaStream_t stream) {
-    GemmArgs ga{};
-    ga.m = m;
-    ga.n = (uint32_t)w.rows;
-    ga.k = w.cols;
-    ga.products = products;
-    ga.n_stages = products == 3 ? 3 : 6;
-    ga.bias = bias;
-    ga.residual = residual;
-    ga.out_f32 = out_f32;
-    ga.out_hi = out_hi;
-    ga.out_lo = out_lo;
-    ga.gelu = gelu;
-    ga.debug_skip_epilogue = env_int("FSGPU_GEMM_SKIP_EPILOGUE", 0);
-    const size_t smem = gemm_smem_bytes(ga.n_stages, products);
-    CUDA_TRY(cudaFuncSetAttribute(gemm_f16split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)gemm_smem_bytes(6, 1)));
-    // CTA-pair tiles (256 x 256) are opt-in (FSGPU_MINILM_PAIR=1): measured 9 % slower than 128 x 128
-    // tiles at 1024 x 32 tokens — the epilogue's global loads/stores, not tile traffic, bound these
-    // K = 384 GEMMs (profiles/r01_minilm_gemm_attn_out_ncu.json)
-    const bool pair = m >= 2 * kGemmTileM && e->num_sms >= 2 && env_int("FSGPU_MINILM_PAIR", 0) != 0;
-    uint32_t tiles, grid;
-    if (pair) {
-        CUDA_TRY(cudaFuncSetAttribute(gemm_f16split_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)gemm_smem_bytes(6, 1)));
-        tiles = ((m + 2 * kGemmTileM - 1) / (2 * kGemmTileM)) * ((ga.n + kGemmPairN - 1) / kGemmPairN);
-        grid = 2 * std::min<uint32_t>(tiles, (uint32_t)e->num_sms / 2);
-    } else {
-        tiles = ((m + kGemmTileM - 1) / kGemmTileM) * (ga.n / kGemmTileN);
-        grid = std::min<uint32_t>(tiles, (uint32_t)e->num_sms);
-    }
-    std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
-    if (e->profiling) {
-        if (!e->ev_free.empty()) {
-            ev = e->ev_free.back();
-            e->ev_free.pop_back();
-        } else {
-            CUDA_TRY(cudaEventCreate(&ev.first));
-            CUDA_TRY(cudaEventCreate(&ev.second));
-        }
-        CUDA_TRY(cudaEventRecord(ev.first, stream));
-    }
-    if (pair)
-        gemm_f16split_pair_kernel<<<grid, kGemmThreads, smem, stream>>>(a.tm_hi, a.tm_lo, w.tm_hi, w.tm_lo, w.tm64_hi,
-                                                                        w.tm64_lo, ga);
-    else
-        gemm_f16split_kernel<<<grid, kGemmThreads, smem, stream>>>(a.tm_hi, a.tm_lo, w.tm_hi, w.tm_lo, ga);
-    CUDA_TRY(cudaGetLastError());
-    if (e->profiling) {
-        CUDA_TRY(cudaEventRecord(ev.second, stream));
-        e->ev_pending.push_back(ev);
-    }
-    e->prof.gemm_launches += 1;
-    e->prof.gemm_flops += 2.0 * (double)m * ga.n * ga.k * products;
-    return FSGPU_OK;
-}
-
-// Caller holds e->mu and has selected the device.
-static int minilm_embed_locked(const fsgpu_minilm* e, const int32_t* d_ids, const int32_t* d_lens, uint32_t batch,
-                               uint32_t max_len, float* d_out, cudaStream_t s, bool sync) {
-    if (max_len == 0 || max_len > e->max_pos)
-        return fail(FSGPU_ERR_EMBEDDING_FAILED, "minilm: max_len %u outside 1..%u", max_len, e->max_pos);
-    const uint64_t rows = (uint64_t)batch * max_len;
-    if (rows > 0x7FFFFF00ull) return fail(FSGPU_ERR_INVALID_CONFIG, "minilm: batch * max_len too large");
-    const uint32_t m = (uint32_t)rows, H = kHidden, I = e->inter;
-    if (rows != e->act_rows) {  // descriptors carry the row count: (re)build on a shape change
-        CUDA_TRY(cudaStreamSynchronize(s));
-        int rc = minilm_reserve_act(e, &e->act_h, rows, H);
-        if (!rc) rc = minilm_reserve_act(e, &e->act_ctx, rows, H);
-        if (!rc) rc = minilm_reserve_act(e, &e->act_ffn, rows, I);
-        if (rc) return rc;
-        e->act_rows = rows;
-    }
-    CUDA_TRY(e->ws_h32.reserve(rows * H * 4));
-    CUDA_TRY(e->ws_pre32.reserve(rows * H * 4));
-    CUDA_TRY(e->ws_qkv32.reserve(rows * 3 * H * 4));
-    const uint32_t products = env_int("FSGPU_MINILM_PRODUCTS", 3) == 1 ? 1 : 3;
-    const unsigned row_blocks = (unsigned)((rows + 7) / 8);
-    float* h32 = e->ws_h32.as<float>();
-    float* pre32 = e->ws_pre32.as<float>();
-    float* qkv32 = e->ws_qkv32.as<float>();
-
-    minilm_embed_kernel<<<row_blocks, 256, 0, s>>>(d_ids, batch, max_len, e->vocab, e->word, e->pos, e->type0, e->emb_g,
-                                                   e->emb_b, e->eps, h32, e->act_h.hi, e->act_h.lo);
-    CUDA_TRY(cudaGetLastError());
-    const size_t att_smem = ((size_t)2 * max_len * 33 + (size_t)4 * max_len) * 4;
-    CUDA_TRY(cudaFuncSetAttribute(minilm_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem));
-    for (uint32_t li = 0; li < e->n_layers; ++li) {
-        const MiniLmLayer& L = e->layers[li];
-        int rc = minilm_gemm(e, e->act_h, L.qkv, m, L.qkv_b, nullptr, qkv32, nullptr, nullptr, 0, products, s);
-        if (rc) return rc;
-        if (max_len <= 32)
-            minilm_attention_short_kernel<<<(batch * kHeads + 3) / 4, 128, 0, s>>>(qkv32, d_lens, batch, max_len,
-                                                                                   e->act_ctx.hi, e->act_ctx.lo);
-        else
-            minilm_attention_kernel<<<batch * kHeads, 128, att_smem, s>>>(qkv32, d_lens, max_len, e->act_ctx.hi, e->act_ctx.lo);
-        CUDA_TRY(cudaGetLastError());
-        rc = minilm_gemm(e, e->act_ctx, L.attn_out, m, L.attn_out_b, h32, pre32, nullptr, nullptr, 0, products, s);
-        if (rc) return rc;
-        minilm_layernorm_kernel<<<row_blocks, 256, 0, s>>>(pre32, rows, L.attn_ln_g, L.attn_ln_b, e->eps, h32, e->act_h.hi,
-                                                           e->act_h.lo);
-        CUDA_TRY(cudaGetLastError());
-        rc = minilm_gemm(e, e->act_h, L.ffn_in, m, L.ffn_in_b, nullptr, nullptr, e->act_ffn.hi, e->act_ffn.lo, 1, products, s);
-        if (rc) return rc;
-        rc = minilm_gemm(e, e->act_ffn, L.ffn_out, m, L.ffn_out_b, h32, pre32, nullptr, nullptr, 0, products, s);
-        if (rc) return rc;
-        minilm_layernorm_kernel<<<row_blocks, 256, 0, s>>>(pre32, rows, L.ffn_ln_g, L.ffn_ln_b, e->eps, h32, e->act_h.hi,
-                                                           e->act_h.lo);
-        CUDA_TRY(cudaGetLastError());
-        e->prof.other_launches += 3;
-    }
-    minilm_pool_kernel<<<batch, 128, 0, s>>>(h32, d_lens, max_len, d_out);
-    CUDA_TRY(cudaGetLastError());
-    e->prof.other_launches += 2;
-    if (sync) CUDA_TRY(cudaStreamSynchronize(s));
-    return FSGPU_OK;
-}
-
-extern "C" int fsgpu_minilm_embed_device(const fsgpu_minilm* e, const int32_t* d_ids, const int32_t* d_lens,
-                                         uint32_t batch, uint32_t max_len, float* d_out, void* stream) {
-    if (!e) return fail(FSGPU_ERR_INVALID_CONFIG, "encoder is NULL");
-    if (batch == 0) return FSGPU_OK;
-    if (!d_ids || !d_lens || !d_out) return fail(FSGPU_ERR_INVALID_CONFIG, "NULL argument");
-    std::lock_guard<std::mutex> lock(e->mu);
-    DeviceGuard g(e->device);
-    return minilm_embed_locked(e, d_ids, d_lens, batch, max_len, d_out, stream ? (cudaStream_t)stream : e->stream,
-                               stream == nullptr);
-}
-
-extern "C" int fsgpu_minilm_embed(const fsgpu_minilm* e, const int32_t* ids, const int32_t* lens, uint32_t batch,
-                                  uint32_t max_len, float* out) {
-    if (!e) return fail(FSGPU_ERR_INVALID_CONFIG, "encoder is NULL");
-    if (batch == 0) return FSGPU_OK;
-    if (!ids || !lens || !out) return fail(FSGPU_ERR_INVALID_CONFIG, "NULL argument");
-    std::lock_guard<std::mutex> lock(e->mu);
-    DeviceGuard g(e->device);
-    CUDA_TRY(e->ws_ids.reserve((size_t)batch * max_len * 4));
-    CUDA_TRY(e->ws_lens.reserve((size_t)batch * 4));
-    CUDA_TRY(e->ws_out.reserve((size_t)batch * kHidden * 4));
-    CUDA_TRY(cudaMemcpyAsync(e->ws_ids.p, ids, (size_t)batch * max_len * 4, cudaMemcpyHostToDevice, e->stream));
-    CUDA_TRY(cudaMemcpyAsync(e->ws_lens.p, lens, (size_t)batch * 4, cudaMemcpyHostToDevice, e->stream));
-    int rc = minilm_embed_locked(e, e->ws_ids.as<int32_t>(), e->ws_lens.as<int32_t>(), batch, max_len,
-                                 e->ws_out.as<float>(), e->stream, false);
-    if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(out, e->ws_out.p, (size_t)batch * kHidden * 4, cudaMemcpyDeviceToHost, e->stream));
-    CUDA_TRY(cudaStreamSynchronize(e->stream));
-    return FSGPU_OK;
-}
-
-extern "C" int fsgpu_minilm_profile_enable(fsgpu_minilm* e, int on) {
-    if (!e) return fail(FSGPU_ERR_INVALID_CONFIG, "encoder is NULL");
-    std::lock_guard<std::mutex> lock(e->mu);
-    e->profiling = on != 0;
-    return FSGPU_OK;
-}
-
-extern "C" int fsgpu_minilm_profile_read(fsgpu_minilm* e, fsgpu_minilm_profile* out, int reset) {
-    if (!e || !out) return fail(FSGPU_ERR_INVALID_CONFIG, "NULL argument");
-    std::lock_guard<std::mutex> lock(e->mu);
-    DeviceGuard g(e->device);
-    for (auto& ev : e->ev_pending) {
-        CUDA_TRY(cudaEventSynchronize(ev.second));
-        float ms = 0.0f;
-        CUDA_TRY(cudaEventElapsedTime(&ms, ev.first, ev.second));
-        e->prof.gemm_ms += ms;
-        e->ev_free.push_back(ev);
-    }
-    e->ev_pending.clear();
-    *out = e->prof;
-    if (reset) e->prof = fsgpu_minilm_profile{};
-    return FSGPU_OK;
-}

@@ -1,0 +1,360 @@
+// fsgpu_minilm.cu — C ABI of the MiniLM-L6-v2 encoder over minilm_kernels.cuh (weights upload,
+// activation workspaces, the per-layer launch sequence).  No CPU compute path.
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "fsgpu.h"
+#include "fsgpu_common.cuh"
+#include "fsgpu_host.cuh"
+#include "minilm_kernels.cuh"
+
+using namespace fsgpu;
+
+// ─── MiniLM-L6 encoder ──────────────────────────────────────────────────────────────────────
+namespace {
+struct SplitMat {  // an f32 matrix carried as hi + lo f16 halves, with its TMA descriptors
+    __half *hi = nullptr, *lo = nullptr;
+    CUtensorMap tm_hi, tm_lo;      // [128 rows x 64] boxes
+    CUtensorMap tm64_hi, tm64_lo;  // [64 rows x 64] boxes (weights: the 128-wide tail tile of the pair GEMM)
+    uint64_t rows = 0;
+    uint32_t cols = 0;
+};
+struct MiniLmLayer {
+    SplitMat qkv, attn_out, ffn_in, ffn_out;
+    float *qkv_b = nullptr, *attn_out_b = nullptr, *attn_ln_g = nullptr, *attn_ln_b = nullptr, *ffn_in_b = nullptr,
+          *ffn_out_b = nullptr, *ffn_ln_g = nullptr, *ffn_ln_b = nullptr;
+};
+}  // namespace
+
+struct fsgpu_minilm {
+    int device = 0, num_sms = 0;
+    uint32_t vocab = 0, max_pos = 0, n_layers = 0, hidden = 0, inter = 0;
+    float eps = 1e-12f;
+    float *word = nullptr, *pos = nullptr, *type0 = nullptr, *emb_g = nullptr, *emb_b = nullptr;
+    std::vector<MiniLmLayer> layers;
+    std::vector<void*> owned;  // every device allocation of the weights
+    cudaStream_t stream = nullptr;
+    mutable std::mutex mu;
+    // activations (grow-only, guarded by mu)
+    mutable DevBuf ws_h32, ws_pre32, ws_qkv32, ws_ids, ws_lens, ws_out;
+    mutable SplitMat act_h, act_ctx, act_ffn;
+    mutable uint64_t act_rows = 0;
+    mutable bool profiling = false;
+    mutable fsgpu_minilm_profile prof{};
+    mutable std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pending, ev_free;
+};
+
+static int minilm_upload(fsgpu_minilm* e, const float* host, size_t count, float** dev) {
+    if (!host) return fail(FSGPU_ERR_INVALID_CONFIG, "minilm: a weight pointer is NULL");
+    CUDA_TRY(cudaMalloc(dev, count * 4));
+    e->owned.push_back(*dev);
+    CUDA_TRY(cudaMemcpy(*dev, host, count * 4, cudaMemcpyHostToDevice));
+    return FSGPU_OK;
+}
+
+static int minilm_upload_split(fsgpu_minilm* e, const float* host, uint64_t rows, uint32_t cols, SplitMat* m) {
+    float* tmp = nullptr;
+    if (!host) return fail(FSGPU_ERR_INVALID_CONFIG, "minilm: a weight pointer is NULL");
+    const size_t n = (size_t)rows * cols;
+    CUDA_TRY(cudaMalloc(&tmp, n * 4));
+    cudaError_t err = cudaMemcpy(tmp, host, n * 4, cudaMemcpyHostToDevice);
+    if (err == cudaSuccess) err = cudaMalloc(&m->hi, n * 2);
+    if (err == cudaSuccess) e->owned.push_back(m->hi);
+    if (err == cudaSuccess) err = cudaMalloc(&m->lo, n * 2);
+    if (err == cudaSuccess) e->owned.push_back(m->lo);
+    if (err == cudaSuccess) {
+        split_f16_kernel<<<e->num_sms * 4, 256, 0, e->stream>>>(tmp, n, m->hi, m->lo);
+        err = cudaGetLastError();
+        if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+    }
+    cudaFree(tmp);
+    if (err != cudaSuccess) return fail(FSGPU_ERR_SUBSYSTEM, "gpu: minilm weight upload failed: %s", cudaGetErrorString(err));
+    m->rows = rows;
+    m->cols = cols;
+    if (!make_f16_tile_map(&m->tm_hi, m->hi, rows, cols) || !make_f16_tile_map(&m->tm_lo, m->lo, rows, cols) ||
+        !make_f16_tile_map(&m->tm64_hi, m->hi, rows, cols, 64) ||
+        !make_f16_tile_map(&m->tm64_lo, m->lo, rows, cols, 64))
+        return fail(FSGPU_ERR_SUBSYSTEM, "gpu: cuTensorMapEncodeTiled failed for a minilm weight");
+    return FSGPU_OK;
+}
+
+extern "C" void fsgpu_minilm_destroy(fsgpu_minilm* e) {
+    if (!e) return;
+    {
+        DeviceGuard g(e->device);
+        if (e->stream) cudaStreamSynchronize(e->stream);
+        for (void* p : e->owned) cudaFree(p);
+        for (SplitMat* m : {&e->act_h, &e->act_ctx, &e->act_ffn}) {
+            if (m->hi) cudaFree(m->hi);
+            if (m->lo) cudaFree(m->lo);
+        }
+        for (DevBuf* b : {&e->ws_h32, &e->ws_pre32, &e->ws_qkv32, &e->ws_ids, &e->ws_lens, &e->ws_out}) b->release();
+        for (auto* v : {&e->ev_pending, &e->ev_free})
+            for (auto& ev : *v) {
+                cudaEventDestroy(ev.first);
+                cudaEventDestroy(ev.second);
+            }
+        if (e->stream) cudaStreamDestroy(e->stream);
+    }
+    delete e;
+}
+
+extern "C" int fsgpu_minilm_create(const fsgpu_minilm_weights* w, int device, fsgpu_minilm** out) {
+    if (!out) return fail(FSGPU_ERR_INVALID_CONFIG, "out is NULL");
+    *out = nullptr;
+    if (!w || !w->layers) return fail(FSGPU_ERR_INVALID_CONFIG, "minilm: weights is NULL");
+    if (w->hidden != kHidden || w->heads != kHeads)
+        return fail(FSGPU_ERR_INVALID_CONFIG, "minilm: only hidden=384 / heads=12 (all-MiniLM-L6-v2 geometry) is built, got %u / %u",
+                    w->hidden, w->heads);
+    if (w->intermediate == 0 || w->intermediate % 128 != 0 || w->n_layers == 0 || w->vocab_size == 0 || w->max_positions == 0)
+        return fail(FSGPU_ERR_INVALID_CONFIG, "minilm: bad geometry (intermediate=%u layers=%u vocab=%u positions=%u)",
+                    w->intermediate, w->n_layers, w->vocab_size, w->max_positions);
+    int ndev = 0;
+    int rc = fsgpu_device_count(&ndev);
+    if (rc) return rc;
+    if (device < 0 || device >= ndev) return fail(FSGPU_ERR_INVALID_CONFIG, "device %d not present", device);
+    if (!fsgpu_tma_available()) return fail(FSGPU_ERR_SUBSYSTEM, "gpu: cuTensorMapEncodeTiled is unavailable");
+    DeviceGuard g(device);
+    fsgpu_minilm* e = new fsgpu_minilm();
+    e->device = device;
+    cudaDeviceProp prop;
+    cudaError_t err = cudaGetDeviceProperties(&prop, device);
+    if (err == cudaSuccess && prop.major < 10) {
+        delete e;
+        return fail(FSGPU_ERR_SUBSYSTEM, "gpu: device %d is sm_%d%d; this library is built for sm_100a only", device,
+                    prop.major, prop.minor);
+    }
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+    if (err != cudaSuccess) {
+        delete e;
+        return fail(FSGPU_ERR_SUBSYSTEM, "gpu: %s", cudaGetErrorString(err));
+    }
+    e->num_sms = prop.multiProcessorCount;
+    e->vocab = w->vocab_size;
+    e->max_pos = w->max_positions;
+    e->n_layers = w->n_layers;
+    e->hidden = w->hidden;
+    e->inter = w->intermediate;
+    e->eps = w->ln_eps;
+    const uint32_t H = kHidden, I = w->intermediate;
+    rc = minilm_upload(e, w->word_emb, (size_t)w->vocab_size * H, &e->word);
+    if (!rc) rc = minilm_upload(e, w->pos_emb, (size_t)w->max_positions * H, &e->pos);
+    if (!rc) rc = minilm_upload(e, w->type_emb, H, &e->type0);
+    if (!rc) rc = minilm_upload(e, w->emb_ln_g, H, &e->emb_g);
+    if (!rc) rc = minilm_upload(e, w->emb_ln_b, H, &e->emb_b);
+    e->layers.resize(w->n_layers);
+    for (uint32_t i = 0; i < w->n_layers && !rc; ++i) {
+        const fsgpu_minilm_layer_weights& s = w->layers[i];
+        MiniLmLayer& d = e->layers[i];
+        rc = minilm_upload_split(e, s.qkv_w, 3 * H, H, &d.qkv);
+        if (!rc) rc = minilm_upload_split(e, s.attn_out_w, H, H, &d.attn_out);
+        if (!rc) rc = minilm_upload_split(e, s.ffn_in_w, I, H, &d.ffn_in);
+        if (!rc) rc = minilm_upload_split(e, s.ffn_out_w, H, I, &d.ffn_out);
+        if (!rc) rc = minilm_upload(e, s.qkv_b, 3 * H, &d.qkv_b);
+        if (!rc) rc = minilm_upload(e, s.attn_out_b, H, &d.attn_out_b);
+        if (!rc) rc = minilm_upload(e, s.attn_ln_g, H, &d.attn_ln_g);
+        if (!rc) rc = minilm_upload(e, s.attn_ln_b, H, &d.attn_ln_b);
+        if (!rc) rc = minilm_upload(e, s.ffn_in_b, I, &d.ffn_in_b);
+        if (!rc) rc = minilm_upload(e, s.ffn_out_b, H, &d.ffn_out_b);
+        if (!rc) rc = minilm_upload(e, s.ffn_ln_g, H, &d.ffn_ln_g);
+        if (!rc) rc = minilm_upload(e, s.ffn_ln_b, H, &d.ffn_ln_b);
+    }
+    if (rc) {
+        fsgpu_minilm_destroy(e);
+        return rc;
+    }
+    *out = e;
+    return FSGPU_OK;
+}
+
+static int minilm_reserve_act(const fsgpu_minilm* e, SplitMat* m, uint64_t rows, uint32_t cols) {
+    if (m->hi) cudaFree(m->hi);
+    if (m->lo) cudaFree(m->lo);
+    m->hi = m->lo = nullptr;
+    CUDA_TRY(cudaMalloc(&m->hi, (size_t)rows * cols * 2));
+    CUDA_TRY(cudaMalloc(&m->lo, (size_t)rows * cols * 2));
+    m->rows = rows;
+    m->cols = cols;
+    if (!make_f16_tile_map(&m->tm_hi, m->hi, rows, cols) || !make_f16_tile_map(&m->tm_lo, m->lo, rows, cols))
+        return fail(FSGPU_ERR_SUBSYSTEM, "gpu: cuTensorMapEncodeTiled failed for a minilm activation");
+    (void)e;
+    return FSGPU_OK;
+}
+
+// C[m, n] = A * W^T (+ bias, residual, GELU); caller holds e->mu.
+static int minilm_gemm(const fsgpu_minilm* e, const SplitMat& a, const SplitMat& w, uint32_t m, const float* bias,
+                       const float* residual, float* out_f32, __half* out_hi, __half* out_lo, int gelu,
+                       uint32_t products, cudaStream_t stream) {
+    GemmArgs ga{};
+    ga.m = m;
+    ga.n = (uint32_t)w.rows;
+    ga.k = w.cols;
+    ga.products = products;
+    ga.n_stages = products == 3 ? 3 : 6;
+    ga.bias = bias;
+    ga.residual = residual;
+    ga.out_f32 = out_f32;
+    ga.out_hi = out_hi;
+    ga.out_lo = out_lo;
+    ga.gelu = gelu;
+    ga.debug_skip_epilogue = env_int("FSGPU_GEMM_SKIP_EPILOGUE", 0);
+    const size_t smem = gemm_smem_bytes(ga.n_stages, products);
+    CUDA_TRY(cudaFuncSetAttribute(gemm_f16split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)gemm_smem_bytes(6, 1)));
+    // CTA-pair tiles (256 x 256) are opt-in (FSGPU_MINILM_PAIR=1): measured 9 % slower than 128 x 128
+    // tiles at 1024 x 32 tokens — the epilogue's global loads/stores, not tile traffic, bound these
+    // K = 384 GEMMs (profiles/r01_minilm_gemm_attn_out_ncu.json)
+    const bool pair = m >= 2 * kGemmTileM && e->num_sms >= 2 && env_int("FSGPU_MINILM_PAIR", 0) != 0;
+    uint32_t tiles, grid;
+    if (pair) {
+        CUDA_TRY(cudaFuncSetAttribute(gemm_f16split_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)gemm_smem_bytes(6, 1)));
+        tiles = ((m + 2 * kGemmTileM - 1) / (2 * kGemmTileM)) * ((ga.n + kGemmPairN - 1) / kGemmPairN);
+        grid = 2 * std::min<uint32_t>(tiles, (uint32_t)e->num_sms / 2);
+    } else {
+        tiles = ((m + kGemmTileM - 1) / kGemmTileM) * (ga.n / kGemmTileN);
+        grid = std::min<uint32_t>(tiles, (uint32_t)e->num_sms);
+    }
+    std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+    if (e->profiling) {
+        if (!e->ev_free.empty()) {
+            ev = e->ev_free.back();
+            e->ev_free.pop_back();
+        } else {
+            CUDA_TRY(cudaEventCreate(&ev.first));
+            CUDA_TRY(cudaEventCreate(&ev.second));
+        }
+        CUDA_TRY(cudaEventRecord(ev.first, stream));
+    }
+    if (pair)
+        gemm_f16split_pair_kernel<<<grid, kGemmThreads, smem, stream>>>(a.tm_hi, a.tm_lo, w.tm_hi, w.tm_lo, w.tm64_hi,
+                                                                        w.tm64_lo, ga);
+    else
+        gemm_f16split_kernel<<<grid, kGemmThreads, smem, stream>>>(a.tm_hi, a.tm_lo, w.tm_hi, w.tm_lo, ga);
+    CUDA_TRY(cudaGetLastError());
+    if (e->profiling) {
+        CUDA_TRY(cudaEventRecord(ev.second, stream));
+        e->ev_pending.push_back(ev);
+    }
+    e->prof.gemm_launches += 1;
+    e->prof.gemm_flops += 2.0 * (double)m * ga.n * ga.k * products;
+    return FSGPU_OK;
+}
+
+// Caller holds e->mu and has selected the device.
+static int minilm_embed_locked(const fsgpu_minilm* e, const int32_t* d_ids, const int32_t* d_lens, uint32_t batch,
+                               uint32_t max_len, float* d_out, cudaStream_t s, bool sync) {
+    if (max_len == 0 || max_len > e->max_pos)
+        return fail(FSGPU_ERR_EMBEDDING_FAILED, "minilm: max_len %u outside 1..%u", max_len, e->max_pos);
+    const uint64_t rows = (uint64_t)batch * max_len;
+    if (rows > 0x7FFFFF00ull) return fail(FSGPU_ERR_INVALID_CONFIG, "minilm: batch * max_len too large");
+    const uint32_t m = (uint32_t)rows, H = kHidden, I = e->inter;
+    if (rows != e->act_rows) {  // descriptors carry the row count: (re)build on a shape change
+        CUDA_TRY(cudaStreamSynchronize(s));
+        int rc = minilm_reserve_act(e, &e->act_h, rows, H);
+        if (!rc) rc = minilm_reserve_act(e, &e->act_ctx, rows, H);
+        if (!rc) rc = minilm_reserve_act(e, &e->act_ffn, rows, I);
+        if (rc) return rc;
+        e->act_rows = rows;
+    }
+    CUDA_TRY(e->ws_h32.reserve(rows * H * 4));
+    CUDA_TRY(e->ws_pre32.reserve(rows * H * 4));
+    CUDA_TRY(e->ws_qkv32.reserve(rows * 3 * H * 4));
+    const uint32_t products = env_int("FSGPU_MINILM_PRODUCTS", 3) == 1 ? 1 : 3;
+    const unsigned row_blocks = (unsigned)((rows + 7) / 8);
+    float* h32 = e->ws_h32.as<float>();
+    float* pre32 = e->ws_pre32.as<float>();
+    float* qkv32 = e->ws_qkv32.as<float>();
+
+    minilm_embed_kernel<<<row_blocks, 256, 0, s>>>(d_ids, batch, max_len, e->vocab, e->word, e->pos, e->type0, e->emb_g,
+                                                   e->emb_b, e->eps, h32, e->act_h.hi, e->act_h.lo);
+    CUDA_TRY(cudaGetLastError());
+    const size_t att_smem = ((size_t)2 * max_len * 33 + (size_t)4 * max_len) * 4;
+    CUDA_TRY(cudaFuncSetAttribute(minilm_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem));
+    for (uint32_t li = 0; li < e->n_layers; ++li) {
+        const MiniLmLayer& L = e->layers[li];
+        int rc = minilm_gemm(e, e->act_h, L.qkv, m, L.qkv_b, nullptr, qkv32, nullptr, nullptr, 0, products, s);
+        if (rc) return rc;
+        if (max_len <= 32)
+            minilm_attention_short_kernel<<<(batch * kHeads + 3) / 4, 128, 0, s>>>(qkv32, d_lens, batch, max_len,
+                                                                                   e->act_ctx.hi, e->act_ctx.lo);
+        else
+            minilm_attention_kernel<<<batch * kHeads, 128, att_smem, s>>>(qkv32, d_lens, max_len, e->act_ctx.hi, e->act_ctx.lo);
+        CUDA_TRY(cudaGetLastError());
+        rc = minilm_gemm(e, e->act_ctx, L.attn_out, m, L.attn_out_b, h32, pre32, nullptr, nullptr, 0, products, s);
+        if (rc) return rc;
+        minilm_layernorm_kernel<<<row_blocks, 256, 0, s>>>(pre32, rows, L.attn_ln_g, L.attn_ln_b, e->eps, h32, e->act_h.hi,
+                                                           e->act_h.lo);
+        CUDA_TRY(cudaGetLastError());
+        rc = minilm_gemm(e, e->act_h, L.ffn_in, m, L.ffn_in_b, nullptr, nullptr, e->act_ffn.hi, e->act_ffn.lo, 1, products, s);
+        if (rc) return rc;
+        rc = minilm_gemm(e, e->act_ffn, L.ffn_out, m, L.ffn_out_b, h32, pre32, nullptr, nullptr, 0, products, s);
+        if (rc) return rc;
+        minilm_layernorm_kernel<<<row_blocks, 256, 0, s>>>(pre32, rows, L.ffn_ln_g, L.ffn_ln_b, e->eps, h32, e->act_h.hi,
+                                                           e->act_h.lo);
+        CUDA_TRY(cudaGetLastError());
+        e->prof.other_launches += 3;
+    }
+    minilm_pool_kernel<<<batch, 128, 0, s>>>(h32, d_lens, max_len, d_out);
+    CUDA_TRY(cudaGetLastError());
+    e->prof.other_launches += 2;
+    if (sync) CUDA_TRY(cudaStreamSynchronize(s));
+    return FSGPU_OK;
+}
+
+extern "C" int fsgpu_minilm_embed_device(const fsgpu_minilm* e, const int32_t* d_ids, const int32_t* d_lens,
+                                         uint32_t batch, uint32_t max_len, float* d_out, void* stream) {
+    if (!e) return fail(FSGPU_ERR_INVALID_CONFIG, "encoder is NULL");
+    if (batch == 0) return FSGPU_OK;
+    if (!d_ids || !d_lens || !d_out) return fail(FSGPU_ERR_INVALID_CONFIG, "NULL argument");
+    std::lock_guard<std::mutex> lock(e->mu);
+    DeviceGuard g(e->device);
+    return minilm_embed_locked(e, d_ids, d_lens, batch, max_len, d_out, stream ? (cudaStream_t)stream : e->stream,
+                               stream == nullptr);
+}
+
+extern "C" int fsgpu_minilm_embed(const fsgpu_minilm* e, const int32_t* ids, const int32_t* lens, uint32_t batch,
+                                  uint32_t max_len, float* out) {
+    if (!e) return fail(FSGPU_ERR_INVALID_CONFIG, "encoder is NULL");
+    if (batch == 0) return FSGPU_OK;
+    if (!ids || !lens || !out) return fail(FSGPU_ERR_INVALID_CONFIG, "NULL argument");
+    std::lock_guard<std::mutex> lock(e->mu);
+    DeviceGuard g(e->device);
+    CUDA_TRY(e->ws_ids.reserve((size_t)batch * max_len * 4));
+    CUDA_TRY(e->ws_lens.reserve((size_t)batch * 4));
+    CUDA_TRY(e->ws_out.reserve((size_t)batch * kHidden * 4));
+    CUDA_TRY(cudaMemcpyAsync(e->ws_ids.p, ids, (size_t)batch * max_len * 4, cudaMemcpyHostToDevice, e->stream));
+    CUDA_TRY(cudaMemcpyAsync(e->ws_lens.p, lens, (size_t)batch * 4, cudaMemcpyHostToDevice, e->stream));
+    int rc = minilm_embed_locked(e, e->ws_ids.as<int32_t>(), e->ws_lens.as<int32_t>(), batch, max_len,
+                                 e->ws_out.as<float>(), e->stream, false);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out, e->ws_out.p, (size_t)batch * kHidden * 4, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return FSGPU_OK;
+}
+
+extern "C" int fsgpu_minilm_profile_enable(fsgpu_minilm* e, int on) {
+    if (!e) return fail(FSGPU_ERR_INVALID_CONFIG, "encoder is NULL");
+    std::lock_guard<std::mutex> lock(e->mu);
+    e->profiling = on != 0;
+    return FSGPU_OK;
+}
+
+extern "C" int fsgpu_minilm_profile_read(fsgpu_minilm* e, fsgpu_minilm_profile* out, int reset) {
+    if (!e || !out) return fail(FSGPU_ERR_INVALID_CONFIG, "NULL argument");
+    std::lock_guard<std::mutex> lock(e->mu);
+    DeviceGuard g(e->device);
+    for (auto& ev : e->ev_pending) {
+        CUDA_TRY(cudaEventSynchronize(ev.second));
+        float ms = 0.0f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, ev.first, ev.second));
+        e->prof.gemm_ms += ms;
+        e->ev_free.push_back(ev);
+    }
+    e->ev_pending.clear();
+    *out = e->prof;
+    if (reset) e->prof = fsgpu_minilm_profile{};
+    return FSGPU_OK;
+}

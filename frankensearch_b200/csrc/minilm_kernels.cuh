@@ -19,7 +19,8 @@
 // and runs on CUDA cores in f32; LayerNorm / embedding / pooling are row-wise f32 kernels.
 #pragma once
 
-#include "mma_scan_kernels.cuh"
+#include "fsgpu_common.cuh"
+#include "tc_ptx.cuh"
 
 namespace fsgpu {
 
