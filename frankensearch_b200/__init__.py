@@ -11,3 +11,4 @@ from .index import GpuVectorIndex  # noqa: F401
 from .fusion import blend_two_tier, blend_two_tier_aligned, rrf_fuse  # noqa: F401
 from .embed import MiniLmEmbedder, Model2VecEmbedder  # noqa: F401
 from .sharded import ShardedGpuIndex, shard_bounds  # noqa: F401
+from .searcher import GpuSyncTwoTierSearcher, SyncSearchOutcome, TwoTierConfig  # noqa: F401
