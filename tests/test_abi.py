@@ -60,3 +60,29 @@ def test_product_never_imports_oracle():
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "fs_oracle" not in text and "np_oracle" not in text and "libfs_oracle" not in text, f
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+
+
+def test_header_is_plain_c_and_the_c_example_compiles():
+    """include/fsgpu.h must be consumable by a C99 compiler (the boundary a Rust/C host binds);
+    examples/c_abi_smoke.c is the plain-C call sequence."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    src = os.path.join(ROOT, "examples", "c_abi_smoke.c")
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), src],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_rust_binding_source_lists_every_hot_path_symbol():
+    """bindings/rust (unbuilt here: no cargo) must stay in step with the header for the entry points
+    INTEGRATION.md wires up."""
+    text = open(os.path.join(ROOT, "bindings", "rust", "src", "lib.rs")).read()
+    bound = set(re.findall(r"pub fn (fsgpu_[a-z0-9_]+)\s*\(", text))
+    assert bound <= set(declared_symbols()), bound - set(declared_symbols())
+    for must in ("fsgpu_search_top_k", "fsgpu_search_top_k_filtered", "fsgpu_scores_for_rows", "fsgpu_rrf_fuse",
+                 "fsgpu_blend_two_tier", "fsgpu_potion_embed", "fsgpu_minilm_embed", "fsgpu_index_open_fsvi"):
+        assert must in bound, must
