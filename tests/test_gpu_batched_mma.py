@@ -288,3 +288,17 @@ def test_small_batches_take_the_tensor_core_path_from_three_queries(fs, cpu, fo)
         assert (prof["mma_launches"] >= 1) == want_mma
         assert_batch_matches_oracle(cpu, slab, qs[:b], 10, got, ctx=f"b={b}")
     ix.close()
+
+
+def test_randomised_soak_batched_equals_per_query_path(fs):
+    """A short run of tools/soak_batched.py (210 cases on the B200 box: profiles/r01_soak_batched_210_cases.txt):
+    adversarial corpora (ascending-by-score order, duplicates, extreme norms, exact ties), tombstones
+    and filters; rows, order and f32 score bits of the batched path must equal the per-query path."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "soak_batched.py"), "35", "7"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "soak ok" in r.stdout
