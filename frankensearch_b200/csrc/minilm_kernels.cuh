@@ -42,7 +42,7 @@ struct GemmArgs {
 };
 
 __host__ __device__ inline size_t gemm_smem_bytes(uint32_t n_stages, uint32_t products) {
-    return 1024 + (size_t)n_stages * (products == 3 ? 4 : 2) * kMmaTileBytes + 256 + 8 * 128 * 4;
+    return 1024 + (size_t)n_stages * (products == 3 ? 4 : 2) * kMmaTileBytes + 256 + 8 * 16 * 36 * 4;
 }
 
 __device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
@@ -54,55 +54,74 @@ __device__ __forceinline__ float gelu_erf(float x) {  // 0.5 x (1 + erf(x / sqrt
     return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
 
-// Epilogue of one warp over its [32 rows x n_cols] part of an accumulator tile (lane = row).
-// With the whole shared-memory carve-out given to the TMA ring the L1 cache is a few KiB, so every
-// "cached" global load is an L2 round trip: the first version re-loaded the bias in front of each
-// float4 of outputs and spent ~19 k cycles per tile waiting on those loads (4 x the MMA time).
-// Here the warp's bias slice is staged in shared memory once per tile and the residual float4s
-// of a 32-column chunk are all in flight before the accumulator chunk is consumed.
-__device__ __forceinline__ void gemm_epilogue_warp(const GemmArgs& args, uint32_t taddr, uint32_t row, uint32_t col0,
-                                                   uint32_t n_cols, float* bias_s, uint32_t lane) {
-    for (uint32_t i = lane; i < n_cols; i += 32) bias_s[i] = args.bias[col0 + i];
-    __syncwarp();
-    const bool has_row = row < args.m && args.debug_skip_epilogue != 1;
+// Epilogue of one warp over its [32 rows x n_cols] part of an accumulator tile.  TMEM hands each
+// lane one ROW; storing in that form issues 32-sector requests (one 16-byte piece per row) and the
+// stores, not the MMAs, bound the GEMM (no-store experiment: 3.36 -> 2.00 ms per 1024 x 32-token
+// batch).  So each 32 x 32 chunk goes through a padded shared-memory tile, 16 rows at a time, and
+// comes back with 8 lanes per row: bias / residual / outputs then move as float4s of full 128-byte
+// row segments, 4 rows per instruction.  Residual and bias for the chunk are in flight before the
+// accumulator chunk is consumed (the L1 is a few KiB next to a 227 KiB TMA ring: every global
+// load is an L2 round trip).
+constexpr int kGemmXposePitch = 36;                            // floats: 16-byte aligned, conflict-free
+constexpr int kGemmXposeFloats = 16 * kGemmXposePitch;         // per epilogue warp
+__device__ __forceinline__ void gemm_epilogue_warp(const GemmArgs& args, uint32_t taddr, uint32_t row_base,
+                                                   uint32_t col0, uint32_t n_cols, float* tile, uint32_t lane) {
+    const uint32_t cq = lane & 7u, rq = lane >> 3;  // float4 column chunk / row within a 4-row step
+    const bool live = args.debug_skip_epilogue != 1;
 #pragma unroll 1
     for (uint32_t c = 0; c < n_cols / 32; ++c) {
-        const size_t o = (size_t)row * args.n + col0 + c * 32u;
+        const uint32_t col = col0 + c * 32u + 4u * cq;
+        const float4 bias4 = *reinterpret_cast<const float4*>(args.bias + col);
         float4 res[8];
-        if (args.residual && has_row) {
+        if (args.residual) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) res[i] = *reinterpret_cast<const float4*>(args.residual + o + 4 * i);
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t r = row_base + (uint32_t)(j >> 2) * 16u + (uint32_t)(j & 3) * 4u + rq;
+                res[j] = r < args.m ? *reinterpret_cast<const float4*>(args.residual + (size_t)r * args.n + col)
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         }
         uint32_t v[32];
         tmem_ld_x32(taddr + c * 32u, v);
         tmem_ld_wait();
-        if (has_row) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c * 32u + 4 * i);
-                float4 r;
-                r.x = __uint_as_float(v[4 * i]) + b4.x;
-                r.y = __uint_as_float(v[4 * i + 1]) + b4.y;
-                r.z = __uint_as_float(v[4 * i + 2]) + b4.z;
-                r.w = __uint_as_float(v[4 * i + 3]) + b4.w;
+        for (int h = 0; h < 2; ++h) {
+            if ((int)(lane >> 4) == h) {
+                float4* dst = reinterpret_cast<float4*>(tile + (lane & 15u) * kGemmXposePitch);
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                         __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+            }
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const uint32_t rl = (uint32_t)it * 4u + rq;
+                const uint32_t r = row_base + (uint32_t)h * 16u + rl;
+                float4 x = *reinterpret_cast<const float4*>(tile + rl * kGemmXposePitch + 4u * cq);
+                x.x += bias4.x; x.y += bias4.y; x.z += bias4.z; x.w += bias4.w;
                 if (args.residual) {
-                    r.x += res[i].x; r.y += res[i].y; r.z += res[i].z; r.w += res[i].w;
+                    const float4 s4 = res[h * 4 + it];
+                    x.x += s4.x; x.y += s4.y; x.z += s4.z; x.w += s4.w;
                 }
                 if (args.gelu) {
-                    r.x = gelu_erf(r.x); r.y = gelu_erf(r.y); r.z = gelu_erf(r.z); r.w = gelu_erf(r.w);
+                    x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w);
                 }
-                if (args.out_f32) *reinterpret_cast<float4*>(args.out_f32 + o + 4 * i) = r;
-                if (args.out_hi) {
-                    __half h[4], l[4];
-                    split_f16(r.x, h[0], l[0]); split_f16(r.y, h[1], l[1]);
-                    split_f16(r.z, h[2], l[2]); split_f16(r.w, h[3], l[3]);
-                    *reinterpret_cast<uint2*>(args.out_hi + o + 4 * i) = *reinterpret_cast<uint2*>(h);
-                    *reinterpret_cast<uint2*>(args.out_lo + o + 4 * i) = *reinterpret_cast<uint2*>(l);
+                if (r < args.m && live) {
+                    const size_t o = (size_t)r * args.n + col;
+                    if (args.out_f32) *reinterpret_cast<float4*>(args.out_f32 + o) = x;
+                    if (args.out_hi) {
+                        __half hh[4], ll[4];
+                        split_f16(x.x, hh[0], ll[0]); split_f16(x.y, hh[1], ll[1]);
+                        split_f16(x.z, hh[2], ll[2]); split_f16(x.w, hh[3], ll[3]);
+                        *reinterpret_cast<uint2*>(args.out_hi + o) = *reinterpret_cast<uint2*>(hh);
+                        *reinterpret_cast<uint2*>(args.out_lo + o) = *reinterpret_cast<uint2*>(ll);
+                    }
                 }
             }
+            __syncwarp();
         }
     }
-    __syncwarp();
 }
 
 // Persistent GEMM: CTA c computes output tiles c, c + grid, ... (tile = m_tile * tiles_n + n_tile).
@@ -216,15 +235,15 @@ gemm_f16split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
         // ===== epilogue: TMEM lane = output row, column = output feature =====
         const uint32_t quarter = warp & 3u;
         const uint32_t half = (warp - 2u) >> 2;  // which 64 of the tile's 128 columns this warp stores
-        float* bias_s = reinterpret_cast<float*>(bars + 32) + (warp - 2u) * 128;
+        float* tile = reinterpret_cast<float*>(bars + 32) + (warp - 2u) * kGemmXposeFloats;
         uint32_t acc = 0, acc_phase = 0;
         for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-            const uint32_t row = (t / tiles_n) * kGemmTileM + quarter * 32u + lane;
+            const uint32_t row_base = (t / tiles_n) * kGemmTileM + quarter * 32u;
             const uint32_t col0 = (t % tiles_n) * kGemmTileN + half * (kGemmTileN / 2);
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * kGemmTileN + half * (kGemmTileN / 2);
-            gemm_epilogue_warp(args, taddr, row, col0, kGemmTileN / 2, bias_s, lane);
+            gemm_epilogue_warp(args, taddr, row_base, col0, kGemmTileN / 2, tile, lane);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -375,17 +394,17 @@ gemm_f16split_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __g
         // ===== epilogue (both CTAs): TMEM lane = one of this CTA's 128 rows, column = feature =====
         const uint32_t quarter = warp & 3u;
         const uint32_t half = (warp - 2u) >> 2;
-        float* bias_s = reinterpret_cast<float*>(bars + 32) + (warp - 2u) * 128;
+        float* tile = reinterpret_cast<float*>(bars + 32) + (warp - 2u) * kGemmXposeFloats;
         uint32_t acc = 0, acc_phase = 0;
         for (uint32_t t = pair; t < n_tiles; t += n_pairs) {
             const uint32_t nt = t % tiles_n, width = tile_width(nt);
-            const uint32_t row = (t / tiles_n) * 2 * kGemmTileM + rank * kGemmTileM + quarter * 32u + lane;
+            const uint32_t row_base = (t / tiles_n) * 2 * kGemmTileM + rank * kGemmTileM + quarter * 32u;
             const uint32_t cols_per_warp = width / 2;  // 128 or 64
             const uint32_t col0 = nt * kGemmPairN + half * cols_per_warp;
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * kGemmPairN + half * cols_per_warp;
-            gemm_epilogue_warp(args, taddr, row, col0, cols_per_warp, bias_s, lane);
+            gemm_epilogue_warp(args, taddr, row_base, col0, cols_per_warp, tile, lane);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(tempty_bar(acc), 0);
