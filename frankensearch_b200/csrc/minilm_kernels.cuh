@@ -570,56 +570,99 @@ minilm_attention_kernel(const float* __restrict__ qkv, const int32_t* __restrict
     }
 }
 
-// Short sequences (t_pad <= 32, the query-encoding case): one WARP per (sequence, head).  Lane j
-// keeps key row j in registers, V sits in a padded per-warp shared tile; no block barriers.
+// Short sequences (t_pad <= 32, the query-encoding case): one WARP per (sequence, head), one LANE
+// per query row.  K and V rows sit in a per-warp shared tile and are read as broadcast float4s;
+// each lane keeps its q row, its 32 scores and its 32 outputs in registers, so the soft-max needs
+// no shuffles and the two contractions are plain FMA streams (~2.9 k instructions per head against
+// ~4.8 k for the shuffle-broadcast form: 150 -> ~90 us per layer at 1024 x 32 tokens).
 __global__ void __launch_bounds__(128)
 minilm_attention_short_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ lens, uint32_t batch,
                               uint32_t t_pad, __half* __restrict__ ctx_hi, __half* __restrict__ ctx_lo) {
-    __shared__ float vs_all[4][32 * 33];
+    __shared__ __align__(16) float kv_all[4][2][32 * kHeadDim];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t unit = blockIdx.x * 4 + warp;
     if (unit >= batch * kHeads) return;
     const uint32_t b = unit / kHeads, h = unit % kHeads;
     const uint32_t len = min((uint32_t)max(lens[b], 0), t_pad);
-    float* vs = vs_all[warp];
+    float* ks = kv_all[warp][0];
+    float* vs = kv_all[warp][1];
     const size_t row0 = (size_t)b * t_pad;
-    float kreg[kHeadDim];
-    {
-        const float* src = qkv + (row0 + min(lane, t_pad - 1)) * (3 * kHidden) + h * kHeadDim;
+    // stage K and V rows [len][32]: 8 lanes per row, 4 rows per instruction
+    for (uint32_t r = lane >> 3; r < len; r += 4) {
+        const float* src = qkv + (row0 + r) * (3 * kHidden) + h * kHeadDim + 4 * (lane & 7);
+        *reinterpret_cast<float4*>(ks + r * kHeadDim + 4 * (lane & 7)) = *reinterpret_cast<const float4*>(src + kHidden);
+        *reinterpret_cast<float4*>(vs + r * kHeadDim + 4 * (lane & 7)) = *reinterpret_cast<const float4*>(src + 2 * kHidden);
+    }
+    const uint32_t t = lane;  // this lane's query row
+    const size_t o = (row0 + t) * kHidden + h * kHeadDim;
+    float q[kHeadDim];
+    if (t < len) {
+        const float4* qs = reinterpret_cast<const float4*>(qkv + (row0 + t) * (3 * kHidden) + h * kHeadDim);
 #pragma unroll
-        for (int d = 0; d < kHeadDim; d += 4) {
-            const float4 k4 = *reinterpret_cast<const float4*>(src + kHidden + d);
-            const float4 v4 = *reinterpret_cast<const float4*>(src + 2 * kHidden + d);
-            kreg[d] = k4.x; kreg[d + 1] = k4.y; kreg[d + 2] = k4.z; kreg[d + 3] = k4.w;
-            vs[lane * 33 + d] = v4.x; vs[lane * 33 + d + 1] = v4.y; vs[lane * 33 + d + 2] = v4.z; vs[lane * 33 + d + 3] = v4.w;
+        for (int d = 0; d < kHeadDim / 4; ++d) {
+            const float4 v4 = qs[d];
+            q[4 * d] = v4.x; q[4 * d + 1] = v4.y; q[4 * d + 2] = v4.z; q[4 * d + 3] = v4.w;
         }
+    } else {
+#pragma unroll
+        for (int d = 0; d < kHeadDim; ++d) q[d] = 0.0f;
     }
     __syncwarp();
-    const float scale = 0.17677669529663688110f;
-    for (uint32_t t = 0; t < t_pad; ++t) {
-        const size_t o = (row0 + t) * kHidden + h * kHeadDim + lane;
-        if (t >= len) {
-            ctx_hi[o] = __float2half_rn(0.0f);
-            ctx_lo[o] = __float2half_rn(0.0f);
-            continue;
-        }
-        const float qd = qkv[(row0 + t) * (3 * kHidden) + h * kHeadDim + lane];  // lane = dim
-        float s = 0.0f;
+    const float scale = 0.17677669529663688110f;  // 1 / sqrt(32)
+    float sc[32];
+    float mx = -INFINITY;
 #pragma unroll
-        for (int d = 0; d < kHeadDim; ++d) s = fmaf(__shfl_sync(0xffffffffu, qd, d), kreg[d], s);  // lane = key
-        s = lane < len ? s * scale : -INFINITY;
-        float mx = s;
-        for (int o2 = 16; o2 > 0; o2 >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o2));
-        const float e = lane < len ? expf(s - mx) : 0.0f;
-        float sum = e;
-        for (int o2 = 16; o2 > 0; o2 >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o2);
-        float acc = 0.0f;  // lane = output dim
-        for (uint32_t j = 0; j < len; ++j) acc = fmaf(__shfl_sync(0xffffffffu, e, j), vs[j * 33 + lane], acc);
-        acc /= sum;
-        __half hi, lo;
-        split_f16(acc, hi, lo);
-        ctx_hi[o] = hi;
-        ctx_lo[o] = lo;
+    for (int j = 0; j < 32; ++j) {
+        float a = -INFINITY;
+        if ((uint32_t)j < len) {  // warp-uniform
+            const float4* kr = reinterpret_cast<const float4*>(ks + j * kHeadDim);
+            a = 0.0f;
+#pragma unroll
+            for (int d = 0; d < kHeadDim / 4; ++d) {
+                const float4 k4 = kr[d];
+                a = fmaf(q[4 * d], k4.x, a);
+                a = fmaf(q[4 * d + 1], k4.y, a);
+                a = fmaf(q[4 * d + 2], k4.z, a);
+                a = fmaf(q[4 * d + 3], k4.w, a);
+            }
+            a *= scale;
+            mx = fmaxf(mx, a);
+        }
+        sc[j] = a;
+    }
+    float sum = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        sc[j] = (uint32_t)j < len ? expf(sc[j] - mx) : 0.0f;
+        sum += sc[j];
+    }
+    float out[kHeadDim];
+#pragma unroll
+    for (int d = 0; d < kHeadDim; ++d) out[d] = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        if ((uint32_t)j < len) {
+            const float4* vr = reinterpret_cast<const float4*>(vs + j * kHeadDim);
+            const float pj = sc[j];
+#pragma unroll
+            for (int d = 0; d < kHeadDim / 4; ++d) {
+                const float4 v4 = vr[d];
+                out[4 * d] = fmaf(pj, v4.x, out[4 * d]);
+                out[4 * d + 1] = fmaf(pj, v4.y, out[4 * d + 1]);
+                out[4 * d + 2] = fmaf(pj, v4.z, out[4 * d + 2]);
+                out[4 * d + 3] = fmaf(pj, v4.w, out[4 * d + 3]);
+            }
+        }
+    }
+    if (t >= t_pad) return;
+    const float inv = t < len ? 1.0f / sum : 0.0f;  // pad rows: defined zeros, never read by the pooling
+#pragma unroll
+    for (int d = 0; d < kHeadDim; d += 4) {
+        __half hh[4], ll[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) split_f16(t < len ? out[d + i] * inv : 0.0f, hh[i], ll[i]);
+        *reinterpret_cast<uint2*>(ctx_hi + o + d) = *reinterpret_cast<uint2*>(hh);
+        *reinterpret_cast<uint2*>(ctx_lo + o + d) = *reinterpret_cast<uint2*>(ll);
     }
 }
 
