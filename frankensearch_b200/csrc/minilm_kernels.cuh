@@ -50,8 +50,19 @@ __device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
     lo = __float2half_rn(v - __half2float(hi));
 }
 
-__device__ __forceinline__ float gelu_erf(float x) {  // 0.5 x (1 + erf(x / sqrt 2)), native.rs:170-186
-    return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+// 0.5 x (1 + erf(x / sqrt 2)) with erf by Abramowitz-Stegun 7.1.26 — the form the reference's own
+// native MiniLM uses (crates/frankensearch-rerank/src/native.rs:170-186): |erf error| <= 1.5e-7 plus
+// ~2e-7 from the fast reciprocal / exp2, i.e. <= 2e-7 |x| on the activation.  ~18 instructions
+// against ~30 for erff(): the FFN-in epilogue evaluates 50 M of these per layer at 1024 x 32 tokens.
+__device__ __forceinline__ float gelu_erf(float x) {
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    const float e = 1.0f - p * t * __expf(-z * z);  // erf(|x| / sqrt 2)
+    return 0.5f * x * (1.0f + copysignf(e, x));
 }
 
 // Epilogue of one warp over its [32 rows x n_cols] part of an accumulator tile.  TMEM hands each
