@@ -302,3 +302,18 @@ def test_randomised_soak_batched_equals_per_query_path(fs):
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "soak ok" in r.stdout
+
+
+def test_batched_f16_subnormal_rows(fs, cpu, fo):
+    """Rows made only of f16 subnormals (|x| < 2^-14): the tensor cores must treat them exactly
+    (no flush-to-zero) for the error bound to hold without help; either way the answer is exact."""
+    rng = np.random.default_rng(23)
+    slab = rng.integers(1, 1024, (9000, 128)).astype(np.uint16)           # subnormal magnitudes
+    slab |= (rng.integers(0, 2, (9000, 128)).astype(np.uint16) << 15)     # random signs
+    qs = rng.normal(size=(20, 128)).astype(np.float32)
+    ix = fs.GpuVectorIndex.from_f16_bits(None, slab)
+    got, prof = search_with_profile(ix, qs, 10)
+    assert prof["mma_launches"] >= 1
+    assert_batch_matches_oracle(cpu, slab, qs, 10, got)
+    assert prof["redo_queries"] == 0, "subnormal f16 inputs were not handled exactly by the MMA path"
+    ix.close()
