@@ -440,7 +440,7 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
     const uint32_t refine_cap = stage_cap_for(cas.t0 < cas.n_tiles ? cas.random_part : (double)cas.t0 * cas.tile_rows / 2.5,
                                               kMmaStagePairs);
     const size_t gate_smem_max = mma_stage_smem_bytes(kMmaStageScores, false);
-    const size_t refine_smem = (size_t)fin_cap * 8 + 16 + mma_stage_smem_bytes(refine_cap, true);
+    const size_t refine_smem = (size_t)fin_cap * 8 + 16 + mma_stage_smem_bytes(refine_cap, true) + (size_t)ix->dim * 4;
     CUDA_TRY(cudaFuncSetAttribute(mma_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gate_smem_max));
     CUDA_TRY(cudaFuncSetAttribute(mma_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)refine_smem));
 

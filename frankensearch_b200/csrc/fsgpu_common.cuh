@@ -85,6 +85,9 @@ __device__ __forceinline__ float warp_exact_dot(const uint16_t* __restrict__ row
     const uint32_t chunks = dim >> 3;
     const uint32_t groups = chunks >> 2;
     float acc = 0.0f;
+    // the adds stay in reference order; unrolling only lets the loads of four groups be in flight
+    // together (each is an L2 round trip when the row comes from a gather)
+#pragma unroll 4
     for (uint32_t g = 0; g < groups; ++g) {
         const uint32_t e = g * 32u + lane;
         acc = add_rn(acc, mul_rn(h2f(row[e]), q[e]));

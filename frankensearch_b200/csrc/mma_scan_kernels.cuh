@@ -819,16 +819,43 @@ __global__ void __launch_bounds__(256) mma_refine_kernel(const MmaRefineArgs arg
         gate_u = ordered_score(__fsub_rd(unordered_score(u), args.margin2[b]));
     }
 
-    // pass 2: every entry inside the band is re-scored exactly and competes on its exact key
-    const float* q = args.queries + (size_t)b * args.dim;
+    // pass 2: every entry inside the band is re-scored exactly and competes on its exact key.  The
+    // query is staged in shared memory first: read from global memory, every 32-element step of
+    // every exact dot paid an L2 round trip for it.
+    float* q = reinterpret_cast<float*>(sm.score + (size_t)sm.cap * 2);
+    for (uint32_t i = threadIdx.x; i < args.dim; i += step) q[i] = args.queries[(size_t)b * args.dim + i];
+    __syncthreads();
     if (staged) {
-        for (uint32_t base = 0; base < total; base += step) {
-            const uint32_t i = base + threadIdx.x;
-            const bool pass = i < total && sm.score[i] >= gate_u;
-            mma_rescore_round(args, buf, q, pass, pass ? sm.row[i] : 0u);
+        // (a) gather the rows of the band into a dense list (it reuses the score array: every thread
+        //     first folds the pass flags of its <= 32 entries into a register), (b) spread the exact
+        //     dots evenly over the warps — no barrier per 256 entries, no warp idling while another
+        //     re-scores (the first version spent half its time at those barriers).
+        uint32_t mine = 0;
+        for (uint32_t r = 0, i = threadIdx.x; i < total; ++r, i += step)
+            if (sm.score[i] >= gate_u) mine |= 1u << r;
+        if (threadIdx.x == 0) sm.ctl[2] = 0u;
+        __syncthreads();
+        uint32_t* band = sm.score;
+        for (uint32_t r = 0, i = threadIdx.x; i < total; ++r, i += step)
+            if (mine & (1u << r)) band[atomicAdd(&sm.ctl[2], 1u)] = sm.row[i];
+        __syncthreads();
+        const uint32_t n_band = sm.ctl[2];
+        const uint32_t warp = threadIdx.x >> 5, n_warps = step >> 5;
+        const uint32_t chunk = (args.buf_cap - args.k) & ~7u;  // pushes the buffer absorbs between compactions
+        for (uint32_t c0 = 0; c0 < n_band; c0 += chunk) {
+            const uint32_t c1 = min(n_band, c0 + chunk);
+            for (uint32_t e = c0 + warp; e < c1; e += n_warps) {
+                const uint32_t grow = band[e];
+                const uint64_t local = (uint64_t)grow - args.row_base;
+                const float sx = warp_exact_dot(args.slab + local * args.dim, q, args.dim, args.reduce_order,
+                                                args.tail_fma);
+                if ((threadIdx.x & 31u) == 0u) {
+                    const uint64_t exact = make_key(sx, grow);
+                    if (exact > *tau && !cand_push(buf, args.buf_cap, exact)) atomicExch(args.error_flag, 1u);
+                }
+            }
             __syncthreads();
-            if (*cnt > trigger) cand_compact(buf, args.buf_cap, args.k);
-            __syncthreads();
+            if (c1 < n_band) cand_compact(buf, args.buf_cap, args.k);
         }
     } else {
         for (uint32_t j = 0; j < mma_list_count(l); ++j) {
