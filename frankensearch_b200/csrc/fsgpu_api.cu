@@ -388,7 +388,9 @@ static MmaCascade plan_cascade(uint64_t n_rows, uint32_t k, uint32_t tile_rows) 
     MmaCascade c;
     c.tile_rows = tile_rows;
     c.n_tiles = (n_rows + tile_rows - 1) / tile_rows;
-    c.k_sel = std::max(k, 16u);
+    // k' >= k keeps the sample thresholds valid; k' >= 8 keeps their spread small (the number of
+    // corpus rows above a sample's k'-th best is ~Gamma(k') times its mean: 6x slack is never reached)
+    c.k_sel = std::max(k, 8u);
     c.slack = std::max(2, env_int("FSGPU_MMA_LIST_SLACK", 6));
     // t0 minimises the total number of appended candidates per query, t0*tile_rows + 2 k' sqrt(n_tiles/t0)
     // (appends, not MMAs, are what the sample levels cost: ~0.1 us of warp time each)

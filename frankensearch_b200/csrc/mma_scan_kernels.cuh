@@ -16,7 +16,7 @@
 //               Gates come from a sample cascade: level 0 keeps every score of ~16 strided
 //               tiles, level 1 scans ~sqrt(16 * n_tiles) strided tiles against the k'-th best
 //               of level 0, level 2 scans everything against the k'-th best of level 1 minus
-//               2 e_q.  The k'-th best (k' = max(k, 16)) of any subset is a lower bound of the
+//               2 e_q.  The k'-th best (k' = max(k, 8)) of any subset is a lower bound of the
 //               corpus' k-th best, so every row of the exact top-k clears the final gate
 //               (proof in DESIGN.md "Batched scan") and the final list is a superset of it.
 //   3. refine:  one CTA per query re-scores the band [tau_approx - 2 e_q, inf) of its list with
