@@ -199,7 +199,6 @@ static int minilm_gemm(const fsgpu_minilm* e, const SplitMat& a, const SplitMat&
     ga.out_hi = out_hi;
     ga.out_lo = out_lo;
     ga.gelu = gelu;
-    ga.debug_skip_epilogue = env_int("FSGPU_GEMM_SKIP_EPILOGUE", 0);
     const size_t smem = gemm_smem_bytes(ga.n_stages, products);
     CUDA_TRY(cudaFuncSetAttribute(gemm_f16split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)gemm_smem_bytes(6, 1)));

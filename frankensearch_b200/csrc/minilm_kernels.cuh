@@ -38,7 +38,6 @@ struct GemmArgs {
     __half* out_hi;            // [m, n] or nullptr   (split-f16 copy of the result for the next GEMM)
     __half* out_lo;
     int gelu;                  // erf-GELU after bias
-    int debug_skip_epilogue;   // perf experiment only: accumulators are drained but nothing is stored
 };
 
 __host__ __device__ inline size_t gemm_smem_bytes(uint32_t n_stages, uint32_t products) {
@@ -78,7 +77,6 @@ constexpr int kGemmXposeFloats = 16 * kGemmXposePitch;         // per epilogue w
 __device__ __forceinline__ void gemm_epilogue_warp(const GemmArgs& args, uint32_t taddr, uint32_t row_base,
                                                    uint32_t col0, uint32_t n_cols, float* tile, uint32_t lane) {
     const uint32_t cq = lane & 7u, rq = lane >> 3;  // float4 column chunk / row within a 4-row step
-    const bool live = args.debug_skip_epilogue != 1;
 #pragma unroll 1
     for (uint32_t c = 0; c < n_cols / 32; ++c) {
         const uint32_t col = col0 + c * 32u + 4u * cq;
@@ -118,7 +116,7 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmArgs& args, uint32_
                 if (args.gelu) {
                     x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w);
                 }
-                if (r < args.m && live) {
+                if (r < args.m) {
                     const size_t o = (size_t)r * args.n + col;
                     if (args.out_f32) *reinterpret_cast<float4*>(args.out_f32 + o) = x;
                     if (args.out_hi) {

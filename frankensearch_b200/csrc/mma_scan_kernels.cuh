@@ -165,19 +165,46 @@ __device__ __forceinline__ uint64_t mma_tile_of(const MmaScanArgs& args, uint64_
     return i * args.tile_stride + jitter;
 }
 
-// Appends (score, global row) to this thread's private list: a plain store, no atomics and no
-// returned value to wait for.  The count keeps growing past `cap` so the consumer sees overflow.
-__device__ __forceinline__ void mma_append(const MmaScanArgs& args, MmaCand* list, uint32_t& count, float s,
-                                           uint64_t row) {
-    if (row < args.n_rows && !tombstoned(args.tombstones, row)) {
-        if (count < args.cap) {
-            MmaCand c;
-            c.score = s;
-            c.row = (uint32_t)(args.row_base + row);
-            list[count] = c;
+// Appends the rows of one 8-column group that clear the gate to this thread's private list: plain
+// predicated stores, no atomics, no returned value to wait for and (in the common case: no
+// tombstones, tile inside the corpus) no branches — the branchy per-row form cost ~135 cycles of
+// warp time per appended row, which is what the sample levels and large-k passes are made of.
+// The count keeps growing past `cap` so the consumer sees overflow.
+__device__ __forceinline__ void mma_append8(const MmaScanArgs& args, MmaCand* list, uint32_t& count,
+                                            const uint32_t (&w)[8], float gate, uint64_t row0) {
+    const bool interior = row0 + 8u <= args.n_rows && args.tombstones == nullptr;
+    const uint32_t grow0 = (uint32_t)(args.row_base + row0);
+    uint32_t c = count;
+    if (interior) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float s = __uint_as_float(w[i]);
+            const bool p = s >= gate;
+            if (p && c < args.cap) {
+                MmaCand e;
+                e.score = s;
+                e.row = grow0 + (uint32_t)i;
+                list[c] = e;
+            }
+            c += p ? 1u : 0u;
         }
-        ++count;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float s = __uint_as_float(w[i]);
+            const uint64_t row = row0 + (uint32_t)i;
+            if (s >= gate && row < args.n_rows && !tombstoned(args.tombstones, row)) {
+                if (c < args.cap) {
+                    MmaCand e;
+                    e.score = s;
+                    e.row = grow0 + (uint32_t)i;
+                    list[c] = e;
+                }
+                ++c;
+            }
+        }
     }
+    count = c;
 }
 
 // Max of 8 accumulator columns (3-input max tree): one bit of the thread's "hot group" mask.
@@ -218,14 +245,7 @@ __device__ __forceinline__ void mma_epilogue_tile(const MmaScanArgs& args, uint3
     if (hot_warp == 0u) return;
     // two groups in flight: the TMEM read of the next hot group overlaps the appends of this one
     auto check8 = [&](const uint32_t (&w)[8], uint32_t grp) {
-        if (hot & (1u << grp)) {
-            const uint64_t row0 = tile_row0 + grp * 8u;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float s8 = __uint_as_float(w[i]);
-                if (s8 >= gate) mma_append(args, list, count, s8, row0 + (uint32_t)i);
-            }
-        }
+        if (hot & (1u << grp)) mma_append8(args, list, count, w, gate, tile_row0 + grp * 8u);
     };
     uint32_t wa[8], wb[8];
     uint32_t ga = __ffs(hot_warp) - 1u, gb;
