@@ -86,7 +86,7 @@ struct fsgpu_index {
     mutable CUtensorMap tm_qhat;
     mutable const void* tm_qhat_ptr = nullptr;
     mutable uint32_t tm_qhat_rows = 0;
-    mutable DevBuf ws_qhat, ws_margin, ws_gate, ws_redo, ws_cand, ws_cand_count;
+    mutable DevBuf ws_qhat, ws_margin, ws_gate, ws_redo, ws_cand, ws_cand_count, ws_progress;
     // launch accounting (guarded by mu)
     mutable bool profiling = false;
     mutable fsgpu_profile prof{};
@@ -487,6 +487,12 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
         a.cand = ix->ws_cand.as<MmaCand>();
         a.cand_count = ix->ws_cand_count.as<uint32_t>();
         a.cap = cap;
+        // pacing of the pairs that share a tile stream (only meaningful with several query pairs)
+        const uint32_t lead = (uint32_t)std::max(0, env_int("FSGPU_MMA_LEAD", 16));
+        const bool paced = pair && n_units > 1 && lead > 0;
+        const size_t progress_bytes = (size_t)g * n_units * 4;
+        if (paced) CUDA_TRY(ix->ws_progress.reserve(progress_bytes));
+        a.lead = lead;
         MmaGateArgs ga{};
         ga.lists = MmaLists{a.cand, a.cand_count, n_qb, g, cap, pair ? 1u : 0u};
         ga.margin2 = ix->ws_margin.as<float>();
@@ -502,6 +508,8 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
             a.tile_stride = env_int("FSGPU_MMA_SAMPLE_CONTIG", 0) ? 1 : cas.n_tiles / level_tiles[lvl];
             a.tile_count = level_tiles[lvl];
             a.gate = have_gate ? ix->ws_gate.as<float>() : nullptr;
+            a.progress = paced ? ix->ws_progress.as<uint32_t>() : nullptr;
+            if (paced) CUDA_TRY(cudaMemsetAsync(ix->ws_progress.p, 0, progress_bytes, stream));
             scan_kernel<<<grid, kMmaThreads, smem, stream>>>(ix->tm_qhat, ix->tm_slab, a);
             CUDA_TRY(cudaGetLastError());
             ga.stage_cap = have_gate ? gate1_cap : gate0_cap;
@@ -514,6 +522,8 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
         a.tile_stride = 1;
         a.tile_count = cas.n_tiles;
         a.gate = have_gate ? ix->ws_gate.as<float>() : nullptr;
+        a.progress = paced ? ix->ws_progress.as<uint32_t>() : nullptr;
+        if (paced) CUDA_TRY(cudaMemsetAsync(ix->ws_progress.p, 0, progress_bytes, stream));
         std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
         if (ix->profiling) {
             if (!ix->ev_free.empty()) {
@@ -663,7 +673,7 @@ extern "C" void fsgpu_index_destroy(fsgpu_index* ix) {
             }
         for (DevBuf* b : {&ix->ws_partial, &ix->ws_queries, &ix->ws_keys, &ix->ws_hits, &ix->ws_counts,
                           &ix->ws_sort_a, &ix->ws_sort_b, &ix->ws_cub, &ix->ws_rows, &ix->ws_scores,
-                          &ix->ws_present, &ix->ws_excl, &ix->ws_allow, &ix->ws_qhat, &ix->ws_margin, &ix->ws_gate, &ix->ws_redo, &ix->ws_cand,
+                          &ix->ws_present, &ix->ws_excl, &ix->ws_allow, &ix->ws_progress, &ix->ws_qhat, &ix->ws_margin, &ix->ws_gate, &ix->ws_redo, &ix->ws_cand,
                           &ix->ws_cand_count})
             b->release();
         if (ix->stream) cudaStreamDestroy(ix->stream);

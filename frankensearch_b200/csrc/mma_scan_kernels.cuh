@@ -63,6 +63,11 @@ struct MmaScanArgs {
     uint64_t tile_stride, tile_count;
     const float* gate;         // [n_qblocks*128] static per-query gate (nullptr = -inf: keep everything)
     const uint32_t* redo;      // [n_qblocks*128] != 0: query is served by the exact path, skip it
+    // pacing (pair form, several query pairs per tile stream): progress[stream][query pair] = tiles
+    // whose loads have been issued; a pair never runs more than `lead` tiles ahead of the slowest
+    // pair that reads the same tiles, so those reads stay inside the L2 window.  nullptr = off.
+    uint32_t* progress;
+    uint32_t lead;
     MmaCand* cand;             // [gridDim.x][2][128][cap]: one private list per epilogue thread
     uint32_t* cand_count;      // [gridDim.x][2][128] appended entries (may exceed cap = overflow)
     uint32_t cap;
@@ -487,9 +492,23 @@ mma_scan_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                                  (int32_t)(qb * kMmaM));
         }
         __syncwarp();
-        uint32_t stage = 0, phase = 0;
-        for (uint64_t i = j0; i < args.tile_count; i += g) {
+        uint32_t stage = 0, phase = 0, li = 0;
+        volatile uint32_t* prog = args.progress ? args.progress + (size_t)j0 * n_qpairs : nullptr;
+        for (uint64_t i = j0; i < args.tile_count; i += g, ++li) {
             const int32_t row_coord = (int32_t)(mma_tile_of(args, i) * kPairN + rank * kMmaN);
+            // every 8th tile (an L2 round trip per tile would eat the TMA prefetch depth): wait for
+            // the slowest pair of this tile stream
+            if (prog && li > args.lead && (li & 7u) == 0u && lane == 0) {
+                const long long t0 = clock64();
+                for (uint32_t spins = 0;; ++spins) {
+                    uint32_t slowest = 0xFFFFFFFFu;
+                    for (uint32_t q = 0; q < n_qpairs; ++q) slowest = min(slowest, prog[q]);
+                    if (slowest + args.lead >= li) break;
+                    __nanosleep(200);
+                    if ((spins & 255u) == 255u && clock64() - t0 > 8000000000ll) __trap();
+                }
+            }
+            __syncwarp();
             for (uint32_t kb = 0; kb < args.n_kblocks; ++kb) {
                 mbar_wait(empty_bar(stage), phase ^ 1u);
                 if (elect_one()) {
@@ -503,7 +522,9 @@ mma_scan_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                     phase ^= 1u;
                 }
             }
+            if (prog && rank == 0 && lane == 0 && (li & 3u) == 3u) prog[pair % n_qpairs] = li + 1u;
         }
+        if (prog && rank == 0 && lane == 0) prog[pair % n_qpairs] = 0xFFFFFFF0u;  // done: never the slowest
     } else if (warp == 1) {
         if (rank == 0) {
             // ===== MMA issuer (leader CTA only) =====
