@@ -73,6 +73,9 @@ extern "C" {
     pub fn fsgpu_index_rows(index: *const fsgpu_index) -> u64;
     pub fn fsgpu_index_dim(index: *const fsgpu_index) -> u32;
     pub fn fsgpu_index_set_tombstones(index: *mut fsgpu_index, bitmap_or_null: *const u8) -> c_int;
+    pub fn fsgpu_index_read_tombstones(index: *const fsgpu_index, out_bitmap: *mut u8) -> c_int;
+    pub fn fsgpu_index_set_wal(index: *mut fsgpu_index, embeddings: *const f32, n_wal: u32, virtual_base: u64) -> c_int;
+    pub fn fsgpu_index_wal_rows(index: *const fsgpu_index) -> u32;
     pub fn fsgpu_index_doc_id(index: *const fsgpu_index, global_row: u64, out_ptr: *mut *const u8,
                               out_len: *mut u32) -> c_int;
 

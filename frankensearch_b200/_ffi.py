@@ -101,7 +101,8 @@ EXPORTS = [
     "fsgpu_index_create_f16", "fsgpu_index_create_f32", "fsgpu_index_open_fsvi", "fsgpu_index_destroy",
     "fsgpu_index_rows", "fsgpu_index_dim", "fsgpu_index_row_base", "fsgpu_index_device",
     "fsgpu_index_device_slab", "fsgpu_index_set_doc_ids", "fsgpu_index_doc_id",
-    "fsgpu_index_set_tombstones", "fsgpu_index_read_rows_f16", "fsgpu_index_profile_enable",
+    "fsgpu_index_set_tombstones", "fsgpu_index_read_tombstones",
+    "fsgpu_index_set_wal", "fsgpu_index_wal_rows", "fsgpu_index_read_rows_f16", "fsgpu_index_profile_enable",
     "fsgpu_index_profile_read", "fsgpu_search_top_k", "fsgpu_search_top_k_device",
     "fsgpu_search_top_k_filtered", "fsgpu_search_top_k_filtered_device",
     "fsgpu_merge_top_k_device", "fsgpu_merge_top_k_hits_device", "fsgpu_scores_for_rows", "fsgpu_scores_for_rows_device",
@@ -149,6 +150,10 @@ def lib() -> C.CDLL:
     L.fsgpu_index_set_doc_ids.argtypes = [_vp, _vp, _vp]
     L.fsgpu_index_doc_id.argtypes = [_vp, C.c_uint64, C.POINTER(_vp), C.POINTER(C.c_uint32)]
     L.fsgpu_index_set_tombstones.argtypes = [_vp, _vp]
+    L.fsgpu_index_read_tombstones.argtypes = [_vp, _vp]
+    L.fsgpu_index_set_wal.argtypes = [_vp, _vp, C.c_uint32, C.c_uint64]
+    L.fsgpu_index_wal_rows.argtypes = [_vp]
+    L.fsgpu_index_wal_rows.restype = C.c_uint32
     L.fsgpu_index_read_rows_f16.argtypes = [_vp, C.c_uint64, C.c_uint64, _vp]
     L.fsgpu_index_profile_enable.argtypes = [_vp, C.c_int]
     L.fsgpu_index_profile_read.argtypes = [_vp, C.POINTER(Profile), C.c_int]

@@ -72,6 +72,13 @@ struct fsgpu_index {
     uint8_t* d_tomb = nullptr;
     mutable const uint8_t* d_excl = nullptr;  // per-call exclusion bitmap (tombstones | !filter), else nullptr
     mutable DevBuf ws_excl, ws_allow;
+    // resident WAL rows (f32, appended since the last compaction): scored beside the slab and merged
+    // into the same top-k (search.rs:488-491, :1449-1475)
+    DevBuf d_wal;
+    uint32_t n_wal = 0;
+    uint64_t wal_base = 0;                       // hit row of WAL entry 0 (record_count, search.rs:1583)
+    mutable const uint8_t* d_wal_allow = nullptr;  // per-call allow bitmap (bit n_rows + w), else nullptr
+    mutable DevBuf ws_wal_main, ws_wal_keys;
     cudaStream_t stream = nullptr;
     mutable std::mutex mu;
     // workspaces (grow-only, guarded by mu)
@@ -381,6 +388,35 @@ struct MmaCascade {
     }
 };
 
+// FSGPU_MMA_TRACE=1: CUDA-event timestamps between the launches of one batched search, printed to
+// stderr after the call's synchronisation (a debugging aid: where the fixed per-call time goes).
+struct MmaTrace {
+    bool on = false;
+    cudaStream_t stream = nullptr;
+    std::vector<std::pair<const char*, cudaEvent_t>> marks;
+    void mark(const char* what) {
+        if (!on) return;
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        cudaEventRecord(e, stream);
+        marks.emplace_back(what, e);
+    }
+    void report(uint32_t batch, uint64_t rows) {
+        if (!on || marks.size() < 2) return;
+        fprintf(stderr, "[fsgpu trace] batch=%u rows=%llu:", batch, (unsigned long long)rows);
+        for (size_t i = 1; i < marks.size(); ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second);
+            fprintf(stderr, " %s=%.1fus", marks[i].first, ms * 1e3f);
+        }
+        float total = 0.f;
+        cudaEventElapsedTime(&total, marks.front().second, marks.back().second);
+        fprintf(stderr, " total=%.1fus\n", total * 1e3f);
+        for (auto& m : marks) cudaEventDestroy(m.second);
+        marks.clear();
+    }
+};
+
 static MmaCascade plan_cascade(uint64_t n_rows, uint32_t k, uint32_t tile_rows) {
     // Appends per query: level 0 keeps all t0*tile_rows sample scores (deterministic); level 1
     // expects k' * t1/t0 and level 2 k' * n_tiles/t1, both minimised by t1 = sqrt(t0 * n_tiles) at
@@ -469,6 +505,10 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
             ix->tm_qhat_rows = slots;
         }
         const float* q = d_queries + (size_t)done * ix->dim;
+        MmaTrace trace;
+        trace.on = env_int("FSGPU_MMA_TRACE", 0) != 0;
+        trace.stream = stream;
+        trace.mark("start");
         mma_prep_queries_kernel<<<slots, 128, 0, stream>>>(q, sub, ix->dim, ix->max_row_norm, ix->ws_qhat.as<__half>(),
                                                            ix->ws_margin.as<float>(), ix->ws_redo.as<uint32_t>());
         CUDA_TRY(cudaGetLastError());
@@ -510,8 +550,10 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
             a.gate = have_gate ? ix->ws_gate.as<float>() : nullptr;
             a.progress = paced ? ix->ws_progress.as<uint32_t>() : nullptr;
             if (paced) CUDA_TRY(cudaMemsetAsync(ix->ws_progress.p, 0, progress_bytes, stream));
+            trace.mark(lvl ? "gate0" : "prep");
             scan_kernel<<<grid, kMmaThreads, smem, stream>>>(ix->tm_qhat, ix->tm_slab, a);
             CUDA_TRY(cudaGetLastError());
+            trace.mark(lvl ? "scan1" : "scan0");
             ga.stage_cap = have_gate ? gate1_cap : gate0_cap;
             mma_gate_kernel<<<sub, 256, mma_stage_smem_bytes(ga.stage_cap, false), stream>>>(ga);
             CUDA_TRY(cudaGetLastError());
@@ -535,8 +577,10 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
             }
             CUDA_TRY(cudaEventRecord(ev.first, stream));
         }
+        trace.mark("gate_last");
         scan_kernel<<<grid, kMmaThreads, smem, stream>>>(ix->tm_qhat, ix->tm_slab, a);
         CUDA_TRY(cudaGetLastError());
+        trace.mark("scan_full");
         if (ix->profiling) {
             CUDA_TRY(cudaEventRecord(ev.second, stream));
             ix->ev_pending.push_back(ev);
@@ -567,12 +611,15 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
         r.error_flag = ix->d_error;
         mma_refine_kernel<<<sub, 256, refine_smem, stream>>>(r);
         CUDA_TRY(cudaGetLastError());
+        trace.mark("refine");
 
         redo_host.resize(sub);
         uint32_t err_flag = 0;
         CUDA_TRY(cudaMemcpyAsync(redo_host.data(), ix->ws_redo.p, (size_t)sub * 4, cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaMemcpyAsync(&err_flag, ix->d_error, 4, cudaMemcpyDeviceToHost, stream));
+        trace.mark("flags_d2h");
         CUDA_TRY(cudaStreamSynchronize(stream));
+        trace.report(sub, ix->n_rows);
         if (err_flag) return fail(FSGPU_ERR_SUBSYSTEM, "gpu: top-k candidate buffer contract violated (refine)");
         for (uint32_t b = 0; b < sub; ++b) {
             if (!redo_host[b]) continue;
@@ -592,9 +639,9 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
 // FSGPU_MMA_MIN_BATCH (default 3) or more take the tensor-core pass (one pass of the slab for the
 // whole batch beats two CUDA-core passes from 3 queries on: profiles/r01_sweep_k.txt).  Both give
 // identical results.
-static int search_device_locked(const fsgpu_index* ix, const float* d_queries, uint32_t batch, uint32_t k,
-                                uint64_t* d_out_keys, fsgpu_hit* d_out_hits, uint32_t* d_out_counts,
-                                cudaStream_t stream) {
+static int search_main_locked(const fsgpu_index* ix, const float* d_queries, uint32_t batch, uint32_t k,
+                              uint64_t* d_out_keys, fsgpu_hit* d_out_hits, uint32_t* d_out_counts,
+                              cudaStream_t stream) {
     if (batch == 0) return FSGPU_OK;
     const int min_batch = env_int("FSGPU_MMA_MIN_BATCH", 3);
     const bool mma = ix->mma_ok && min_batch > 0 && batch >= (uint32_t)min_batch && k >= 1 && k <= kMmaMaxK &&
@@ -604,6 +651,53 @@ static int search_device_locked(const fsgpu_index* ix, const float* d_queries, u
         return search_mma_locked(ix, d_queries, batch, k, d_out_keys, d_out_hits, d_out_counts, stream);
     }
     return search_exact_locked(ix, d_queries, batch, k, d_out_keys, d_out_hits, d_out_counts, stream);
+}
+
+// Main slab + resident WAL rows (VectorIndex::search_top_k_internal, search.rs:476-493): the slab's
+// top-k keys and one key per WAL row form one list per query, reduced by the same merge kernel.
+static int search_device_locked(const fsgpu_index* ix, const float* d_queries, uint32_t batch, uint32_t k,
+                                uint64_t* d_out_keys, fsgpu_hit* d_out_hits, uint32_t* d_out_counts,
+                                cudaStream_t stream) {
+    if (batch == 0) return FSGPU_OK;
+    if (ix->n_wal == 0 || k == 0)
+        return search_main_locked(ix, d_queries, batch, k, d_out_keys, d_out_hits, d_out_counts, stream);
+    const uint64_t* main_keys = nullptr;
+    if (ix->n_rows > 0) {
+        CUDA_TRY(ix->ws_wal_main.reserve((size_t)batch * k * 8));
+        CUDA_TRY(cudaMemsetAsync(ix->ws_wal_main.p, 0, (size_t)batch * k * 8, stream));
+        int rc = search_main_locked(ix, d_queries, batch, k, ix->ws_wal_main.as<uint64_t>(), nullptr, nullptr, stream);
+        if (rc) return rc;
+        main_keys = ix->ws_wal_main.as<uint64_t>();
+    }
+    const size_t stride = (size_t)k + ix->n_wal;
+    CUDA_TRY(ix->ws_wal_keys.reserve((size_t)batch * stride * 8));
+    const dim3 grid((ix->n_wal + kScanWarps - 1) / kScanWarps, batch);
+    wal_keys_kernel<<<grid, kScanThreads, 0, stream>>>(ix->d_wal.as<float>(), ix->n_wal, ix->wal_base, ix->dim,
+                                                       d_queries, ix->d_wal_allow, ix->n_rows, main_keys, k,
+                                                       ix->reduce_order, ix->ws_wal_keys.as<uint64_t>());
+    CUDA_TRY(cudaGetLastError());
+    ix->prof.other_launches += 1;
+    MergeArgs m{};
+    m.keys = ix->ws_wal_keys.as<uint64_t>();
+    m.list_stride = 0;
+    m.query_stride = stride;
+    m.n_lists = 1;
+    m.k_in = (uint32_t)stride;
+    m.k_out = k;
+    m.cap = cand_capacity(k);
+    m.out_keys = d_out_keys;
+    m.out_hits = d_out_hits;
+    m.out_counts = d_out_counts;
+    m.slab = ix->d_slab;  // raw NaN scores of main rows (WAL rows are always finite)
+    m.queries = d_queries;
+    m.n_rows = ix->n_rows;
+    m.row_base = ix->row_base;
+    m.dim = ix->dim;
+    m.reduce_order = ix->reduce_order;
+    m.tail_fma = ix->tail_fma;
+    m.error_flag = ix->d_error;
+    ix->prof.merge_launches += 1;
+    return launch_merge(m, batch, stream);
 }
 
 static int check_error_flag(const fsgpu_index* ix, cudaStream_t stream) {
@@ -808,6 +902,42 @@ extern "C" int fsgpu_index_set_tombstones(fsgpu_index* ix, const uint8_t* bitmap
     return upload_tombstones(ix, bitmap);
 }
 
+extern "C" int fsgpu_index_read_tombstones(const fsgpu_index* ix, uint8_t* out_bitmap) {
+    if (!ix || !out_bitmap) return fail(FSGPU_ERR_INVALID_CONFIG, "NULL argument");
+    const size_t bytes = (ix->n_rows + 7) / 8;
+    std::lock_guard<std::mutex> lock(ix->mu);
+    DeviceGuard g(ix->device);
+    if (!ix->d_tomb) {
+        memset(out_bitmap, 0, bytes);
+        return FSGPU_OK;
+    }
+    CUDA_TRY(cudaStreamSynchronize(ix->stream));
+    CUDA_TRY(cudaMemcpy(out_bitmap, ix->d_tomb, bytes, cudaMemcpyDeviceToHost));
+    return FSGPU_OK;
+}
+
+extern "C" int fsgpu_index_set_wal(fsgpu_index* ix, const float* embeddings, uint32_t n_wal, uint64_t virtual_base) {
+    if (!ix) return fail(FSGPU_ERR_INVALID_CONFIG, "index is NULL");
+    if (n_wal && !embeddings) return fail(FSGPU_ERR_INVALID_CONFIG, "embeddings is NULL");
+    if (virtual_base + n_wal > 0xFFFFFFFFull)  // resolve_wal_hit (search.rs:1590-1594)
+        return fail(FSGPU_ERR_INVALID_CONFIG, "WAL entry index exceeds u32 range");
+    if (n_wal && virtual_base < ix->row_base + ix->n_rows)
+        return fail(FSGPU_ERR_INVALID_CONFIG, "WAL rows must be numbered after the slab's rows (virtual_base %llu < %llu)",
+                    (unsigned long long)virtual_base, (unsigned long long)(ix->row_base + ix->n_rows));
+    std::lock_guard<std::mutex> lock(ix->mu);
+    DeviceGuard g(ix->device);
+    CUDA_TRY(cudaStreamSynchronize(ix->stream));
+    if (n_wal) {
+        CUDA_TRY(ix->d_wal.reserve((size_t)n_wal * ix->dim * 4));
+        CUDA_TRY(cudaMemcpy(ix->d_wal.p, embeddings, (size_t)n_wal * ix->dim * 4, cudaMemcpyHostToDevice));
+    }
+    ix->n_wal = n_wal;
+    ix->wal_base = virtual_base;
+    return FSGPU_OK;
+}
+
+extern "C" uint32_t fsgpu_index_wal_rows(const fsgpu_index* ix) { return ix ? ix->n_wal : 0; }
+
 extern "C" int fsgpu_index_profile_enable(fsgpu_index* ix, int on) {
     if (!ix) return fail(FSGPU_ERR_INVALID_CONFIG, "index is NULL");
     std::lock_guard<std::mutex> lock(ix->mu);
@@ -855,7 +985,7 @@ extern "C" int fsgpu_search_top_k(const fsgpu_index* ix, const float* queries, u
         return fail(FSGPU_ERR_DIMENSION_MISMATCH, "expected %u, found %u", ix->dim, dim);
     if (batch == 0) return FSGPU_OK;
     if (!queries || !out_counts || (k && !out)) return fail(FSGPU_ERR_INVALID_CONFIG, "NULL argument");
-    if (k == 0 || ix->n_rows == 0) {
+    if (k == 0 || (ix->n_rows == 0 && ix->n_wal == 0)) {
         memset(out_counts, 0, (size_t)batch * 4);
         return FSGPU_OK;
     }
@@ -885,16 +1015,21 @@ __global__ void combine_exclusion_kernel(const uint8_t* __restrict__ tomb, const
 static int search_filtered_locked(const fsgpu_index* ix, const float* d_queries, uint32_t batch, uint32_t k,
                                   const uint8_t* d_allow, uint64_t* d_out_keys, fsgpu_hit* d_out_hits,
                                   uint32_t* d_out_counts, cudaStream_t s) {
-    if (!d_allow || ix->n_rows == 0) return search_device_locked(ix, d_queries, batch, k, d_out_keys, d_out_hits, d_out_counts, s);
-    const size_t n_bytes = (ix->n_rows + 7) / 8;
-    CUDA_TRY(ix->ws_excl.reserve(n_bytes));
-    combine_exclusion_kernel<<<(unsigned)std::min<size_t>((n_bytes + 255) / 256, 4096), 256, 0, s>>>(
-        ix->d_tomb, d_allow, n_bytes, ix->ws_excl.as<uint8_t>());
-    CUDA_TRY(cudaGetLastError());
-    ix->prof.other_launches += 1;
-    ix->d_excl = ix->ws_excl.as<uint8_t>();
+    if (!d_allow || (ix->n_rows == 0 && ix->n_wal == 0))
+        return search_device_locked(ix, d_queries, batch, k, d_out_keys, d_out_hits, d_out_counts, s);
+    if (ix->n_rows > 0) {
+        const size_t n_bytes = (ix->n_rows + 7) / 8;
+        CUDA_TRY(ix->ws_excl.reserve(n_bytes));
+        combine_exclusion_kernel<<<(unsigned)std::min<size_t>((n_bytes + 255) / 256, 4096), 256, 0, s>>>(
+            ix->d_tomb, d_allow, n_bytes, ix->ws_excl.as<uint8_t>());
+        CUDA_TRY(cudaGetLastError());
+        ix->prof.other_launches += 1;
+        ix->d_excl = ix->ws_excl.as<uint8_t>();
+    }
+    ix->d_wal_allow = d_allow;  // WAL row w is bit n_rows + w of the same bitmap
     const int rc = search_device_locked(ix, d_queries, batch, k, d_out_keys, d_out_hits, d_out_counts, s);
     ix->d_excl = nullptr;
+    ix->d_wal_allow = nullptr;
     return rc;
 }
 
@@ -920,7 +1055,7 @@ extern "C" int fsgpu_search_top_k_filtered(const fsgpu_index* ix, const float* q
     if (dim != ix->dim) return fail(FSGPU_ERR_DIMENSION_MISMATCH, "expected %u, found %u", ix->dim, dim);
     if (batch == 0) return FSGPU_OK;
     if (!queries || !out_counts || (k && !out)) return fail(FSGPU_ERR_INVALID_CONFIG, "NULL argument");
-    if (k == 0 || ix->n_rows == 0) {
+    if (k == 0 || (ix->n_rows == 0 && ix->n_wal == 0)) {
         memset(out_counts, 0, (size_t)batch * 4);
         return FSGPU_OK;
     }
@@ -933,7 +1068,7 @@ extern "C" int fsgpu_search_top_k_filtered(const fsgpu_index* ix, const float* q
     CUDA_TRY(cudaMemcpyAsync(ix->ws_queries.p, queries, (size_t)batch * dim * 4, cudaMemcpyHostToDevice, s));
     const uint8_t* d_allow = nullptr;
     if (allow_bitmap) {
-        const size_t n_bytes = (ix->n_rows + 7) / 8;
+        const size_t n_bytes = (ix->n_rows + ix->n_wal + 7) / 8;
         CUDA_TRY(ix->ws_allow.reserve(n_bytes));
         CUDA_TRY(cudaMemcpyAsync(ix->ws_allow.p, allow_bitmap, n_bytes, cudaMemcpyHostToDevice, s));
         d_allow = ix->ws_allow.as<uint8_t>();

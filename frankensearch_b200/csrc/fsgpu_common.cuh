@@ -111,6 +111,39 @@ __device__ __forceinline__ float warp_exact_dot(const uint16_t* __restrict__ row
     return result;
 }
 
+// ─── exact f32·f32 dot for resident WAL rows: one warp per row, any dim ─────────────────────
+// dot_product_f32_f32 (crates/frankensearch-index/src/simd.rs:161-222 AVX2, :1559-1587 generic):
+// four 8-lane accumulators over whole groups of 32 elements, `(acc0+acc1)+(acc2+acc3)` FIRST, then
+// the left-over 8-element chunks are added to that combined vector (the f16 kernels add them to
+// accumulator 0 before combining), 8-lane reduce, scalar tail `result += a*b` (mul, then add).
+__device__ __forceinline__ float warp_exact_dot_f32(const float* __restrict__ row,
+                                                    const float* __restrict__ q, uint32_t dim,
+                                                    int reduce_order) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t chunks = dim >> 3;
+    const uint32_t groups = chunks >> 2;
+    float acc = 0.0f;
+#pragma unroll 4
+    for (uint32_t g = 0; g < groups; ++g) {
+        const uint32_t e = g * 32u + lane;
+        acc = add_rn(acc, mul_rn(row[e], q[e]));
+    }
+    acc = add_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 8));   // acc0+acc1 | acc2+acc3
+    acc = add_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 16));  // (acc0+acc1)+(acc2+acc3)
+    for (uint32_t c = groups * 4u; c < chunks; ++c) {
+        if (lane < 8u) {
+            const uint32_t e = c * 8u + lane;
+            acc = add_rn(acc, mul_rn(row[e], q[e]));
+        }
+    }
+    float v[8];
+#pragma unroll
+    for (int l = 0; l < 8; ++l) v[l] = __shfl_sync(0xffffffffu, acc, l);
+    float result = reduce8(v, reduce_order);
+    for (uint32_t e = chunks * 8u; e < dim; ++e) result = add_rn(result, mul_rn(row[e], q[e]));
+    return result;
+}
+
 // ─── CTA-wide bitonic sort, descending, n a power of two, keys in shared memory ─────────────
 __device__ __forceinline__ void cta_sort_desc(uint64_t* keys, uint32_t n) {
     for (uint32_t k = 2; k <= n; k <<= 1) {

@@ -436,6 +436,36 @@ __global__ void __launch_bounds__(kScanThreads) merge_topk_kernel(const MergeArg
     }
 }
 
+// ─── resident WAL rows: scan_wal (search.rs:1449-1475) ──────────────────────────────────────
+// One warp per (query, WAL row): exact f32 dot, non-finite scores skipped (search.rs:1466-1470),
+// optional allow bit (the filter evaluated by the host, search.rs:1457-1465).  WAL row w carries the
+// hit row `wal_base + w` (record_count + wal_idx, search.rs:1583-1597), which also reproduces the
+// heap order of the tagged index (every main row before every WAL row on equal scores, lower WAL
+// position first: wal.rs:557-569 with search.rs:1673-1678).  Writes the per-query list
+// [main keys (k) | WAL keys (n_wal)] that merge_topk_kernel reduces to the final top-k.
+__global__ void __launch_bounds__(kScanThreads)
+wal_keys_kernel(const float* __restrict__ wal, uint32_t n_wal, uint64_t wal_base, uint32_t dim,
+                const float* __restrict__ queries, const uint8_t* __restrict__ allow, uint64_t allow_bit0,
+                const uint64_t* __restrict__ main_keys, uint32_t k, int reduce_order,
+                uint64_t* __restrict__ out) {
+    const uint32_t b = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const size_t stride = (size_t)k + n_wal;
+    if (blockIdx.x == 0)
+        for (uint32_t i = threadIdx.x; i < k; i += blockDim.x)
+            out[b * stride + i] = main_keys ? main_keys[(size_t)b * k + i] : 0ull;
+    const uint32_t w = blockIdx.x * kScanWarps + (threadIdx.x >> 5);
+    if (w >= n_wal) return;
+    uint64_t key = 0ull;
+    const uint64_t bit = allow_bit0 + w;
+    const bool allowed = allow == nullptr || ((__ldg(allow + (bit >> 3)) >> (bit & 7)) & 1u);
+    if (allowed) {
+        const float s = warp_exact_dot_f32(wal + (size_t)w * dim, queries + (size_t)b * dim, dim, reduce_order);
+        if (isfinite(s)) key = make_key(s, (uint32_t)(wal_base + w));
+    }
+    if (lane == 0) out[b * stride + k + w] = key;
+}
+
 // ─── gather-dot: quality_scores_for_hits (two_tier.rs:1566-1631, :1946-1973) ────────────────
 __global__ void __launch_bounds__(kScanThreads)
 scores_for_rows_kernel(const uint16_t* __restrict__ slab, uint64_t n_rows, uint64_t row_base,

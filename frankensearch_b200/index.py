@@ -50,6 +50,10 @@ class GpuVectorIndex:
         self._dedup = dedup_doc_ids
         self._keepalive = keepalive  # e.g. the torch tensor that owns an adopted device slab
         self._L = _ffi.lib()
+        # mutable state of VectorIndex mirrored on the host: resident WAL rows and soft-delete flags
+        self._wal: List[tuple] = []          # [(doc_id, float32[dim])] in WAL order (wal.rs:101-107)
+        self._tomb: Optional[np.ndarray] = None
+        self._rows_of: Optional[dict] = None  # doc id -> local rows, built on first mutation
 
     # ── construction ────────────────────────────────────────────────────────────────────────
     @classmethod
@@ -69,7 +73,9 @@ class GpuVectorIndex:
         o = _options(device, reduce_order, tail_fma, False, row_base)
         bm = _bitmap(tombstones)
         check(_ffi.lib().fsgpu_index_create_f32(ptr(v), v.shape[0], v.shape[1], ptr(bm), C.byref(o), C.byref(h)))
-        return cls(h.value, doc_ids)
+        ix = cls(h.value, doc_ids)
+        ix._tomb = None if tombstones is None else np.asarray(tombstones, dtype=bool).copy()
+        return ix
 
     @classmethod
     def from_f16_bits(cls, doc_ids: Optional[Sequence[str]], slab_bits, *, device: int = 0,
@@ -84,7 +90,9 @@ class GpuVectorIndex:
         o = _options(device, reduce_order, tail_fma, False, row_base)
         bm = _bitmap(tombstones)
         check(_ffi.lib().fsgpu_index_create_f16(ptr(s), s.shape[0], s.shape[1], ptr(bm), C.byref(o), C.byref(h)))
-        return cls(h.value, doc_ids)
+        ix = cls(h.value, doc_ids)
+        ix._tomb = None if tombstones is None else np.asarray(tombstones, dtype=bool).copy()
+        return ix
 
     @classmethod
     def from_device_tensor(cls, slab, *, doc_ids: Optional[Sequence[str]] = None,
@@ -98,7 +106,9 @@ class GpuVectorIndex:
         bm = _bitmap(tombstones)
         check(_ffi.lib().fsgpu_index_create_f16(slab.data_ptr(), slab.shape[0], slab.shape[1], ptr(bm),
                                                 C.byref(o), C.byref(h)))
-        return cls(h.value, doc_ids, keepalive=slab)
+        ix = cls(h.value, doc_ids, keepalive=slab)
+        ix._tomb = None if tombstones is None else np.asarray(tombstones, dtype=bool).copy()
+        return ix
 
     @classmethod
     def open(cls, path: str, *, device: int = 0, reduce_order="halves_pairwise", row_start: int = 0,
@@ -109,6 +119,12 @@ class GpuVectorIndex:
         check(_ffi.lib().fsgpu_index_open_fsvi(path.encode(), row_start, n_rows, C.byref(o), C.byref(h)))
         ix = cls(h.value, None, dedup_doc_ids=True)
         ix._doc_ids_from_handle = True
+        n = ix.record_count()
+        if n:  # record flag bit 0 as stored in the file (lib.rs:172)
+            bm = np.zeros((n + 7) // 8, dtype=np.uint8)
+            check(ix._L.fsgpu_index_read_tombstones(ix._h, ptr(bm)))
+            flags = np.unpackbits(bm, bitorder="little")[:n].astype(bool)
+            ix._tomb = flags if flags.any() else None
         return ix
 
     def close(self) -> None:
@@ -140,7 +156,11 @@ class GpuVectorIndex:
         return self._h
 
     def doc_id_at(self, row: int) -> Optional[str]:
-        """VectorIndex::doc_id_at (lib.rs:3801-3824) for a GLOBAL row."""
+        """VectorIndex::doc_id_at (lib.rs:3801-3824) for a GLOBAL row; rows at or after
+        `record_count` are the resident WAL rows (resolve_wal_hit, search.rs:1560-1598)."""
+        w = row - self._wal_base()
+        if 0 <= w < len(self._wal):
+            return self._wal[w][0]
         if self._doc_ids is not None:
             return self._doc_ids[row - self.row_base()]
         p, n = C.c_void_p(), C.c_uint32()
@@ -170,6 +190,107 @@ class GpuVectorIndex:
         """Soft-delete flags (record flag bit 0, lib.rs:172; honoured by the scan, search.rs:1281)."""
         bm = _bitmap(flags)
         check(self._L.fsgpu_index_set_tombstones(self._h, ptr(bm)))
+        self._tomb = None if flags is None else np.asarray(flags, dtype=bool).copy()
+
+    def is_deleted(self, row: int) -> bool:
+        """VectorIndex::is_deleted (lib.rs:2401-2406) for a GLOBAL main row."""
+        r = row - self.row_base()
+        return bool(self._tomb is not None and 0 <= r < self._tomb.size and self._tomb[r])
+
+    # ── WAL: rows appended since the last compaction, searchable at once ────────────────────
+    def _wal_base(self) -> int:
+        return self.row_base() + self.record_count()
+
+    def wal_record_count(self) -> int:
+        return len(self._wal)
+
+    def wal_records(self):
+        """VectorIndex::wal_records (lib.rs:2259): (doc_id, embedding) in WAL order."""
+        return [(d, v.copy()) for d, v in self._wal]
+
+    def _main_rows_of(self, doc_id: str) -> List[int]:
+        if self._rows_of is None:
+            n, base = self.record_count(), self.row_base()
+            table: dict = {}
+            for r in range(n):
+                table.setdefault(self.doc_id_at(base + r), []).append(r)
+            self._rows_of = table
+        return self._rows_of.get(doc_id, [])
+
+    def _tombstone_rows(self, rows: Sequence[int]) -> int:
+        if self._tomb is None:
+            self._tomb = np.zeros(self.record_count(), dtype=bool)
+        changed = 0
+        for r in rows:
+            if not self._tomb[r]:
+                self._tomb[r] = True
+                changed += 1
+        if changed:
+            bm = _bitmap(self._tomb)  # named: the buffer must outlive the call
+            check(self._L.fsgpu_index_set_tombstones(self._h, ptr(bm)))
+        return changed
+
+    def _upload_wal(self) -> None:
+        dim = self.dimension()
+        emb = np.ascontiguousarray(np.stack([v for _, v in self._wal]) if self._wal
+                                   else np.zeros((0, dim)), dtype=np.float32)
+        check(self._L.fsgpu_index_set_wal(self._h, ptr(emb) if self._wal else None, len(self._wal),
+                                          self._wal_base()))
+
+    def append(self, doc_id: str, vector) -> None:
+        """VectorIndex::append (lib.rs:2532)."""
+        self.append_batch([(doc_id, vector)])
+
+    def append_batch(self, entries) -> None:
+        """VectorIndex::append_batch (lib.rs:2546-2720) without the durability half: validate every
+        entry first, keep the LAST entry of a doc id within the batch, supersede resident WAL rows
+        of the same doc ids, admit the new rows (searchable at once, scored as f32), tombstone the
+        main rows they replace."""
+        entries = list(entries)
+        if not entries:
+            return
+        dim = self.dimension()
+        checked = []
+        for doc_id, vector in entries:
+            v = np.ascontiguousarray(vector, dtype=np.float32).reshape(-1)
+            if v.size != dim:
+                raise SearchError("DimensionMismatch", f"expected {dim}, found {v.size}")
+            if not np.isfinite(v).all():
+                raise SearchError("InvalidConfig", "all embedding values must be finite")
+            norm_sq = np.float32(0.0)
+            with np.errstate(over="ignore"):
+                for x in v:  # vector_signal_usable (lib.rs:6133-6142): sequential f32 sum of squares
+                    norm_sq = np.float32(norm_sq + np.float32(x * x))
+            if not (norm_sq > 0.0 and np.isfinite(norm_sq)):
+                raise SearchError("InvalidConfig", "embedding norm must be non-zero and finite")
+            if len(doc_id.encode("utf-8")) > 0xFFFF:
+                raise SearchError("InvalidConfig", "doc_id byte length must fit in u16")
+            checked.append((doc_id, v))
+        seen, fresh = set(), []
+        for doc_id, v in reversed(checked):
+            if doc_id not in seen:
+                seen.add(doc_id)
+                fresh.append((doc_id, v))
+        fresh.reverse()
+        self._wal = [e for e in self._wal if e[0] not in seen] + fresh
+        self._upload_wal()
+        self._tombstone_rows([r for doc_id, _ in fresh for r in self._main_rows_of(doc_id)])
+
+    def soft_delete(self, doc_id: str) -> bool:
+        """VectorIndex::soft_delete (lib.rs:2303)."""
+        return self.soft_delete_batch([doc_id]) > 0
+
+    def soft_delete_batch(self, doc_ids: Sequence[str]) -> int:
+        """VectorIndex::soft_delete_batch (lib.rs:2314-2396): tombstone the live main rows of each
+        doc id and drop its resident WAL rows; returns how many records went live -> deleted."""
+        ids = set(doc_ids)
+        deleted = self._tombstone_rows([r for d in doc_ids for r in self._main_rows_of(d)])
+        kept = [e for e in self._wal if e[0] not in ids]
+        if len(kept) < len(self._wal):
+            deleted += len(self._wal) - len(kept)
+            self._wal = kept
+            self._upload_wal()
+        return deleted
 
     # ── exact search ────────────────────────────────────────────────────────────────────────
     def _allow_bitmap(self, filter) -> Optional[np.ndarray]:
@@ -179,12 +300,16 @@ class GpuVectorIndex:
         if filter is None:
             return None
         n = self.record_count()
-        if callable(filter):
+        n_wal = len(self._wal)
+        if callable(filter):  # WAL rows are filtered by doc id too (search.rs:1457-1465)
             base = self.row_base()
-            mask = np.fromiter((bool(filter(self.doc_id_at(base + r))) for r in range(n)), dtype=bool, count=n)
+            mask = np.fromiter((bool(filter(self.doc_id_at(base + r))) for r in range(n + n_wal)), dtype=bool,
+                               count=n + n_wal)
         else:
             mask = np.asarray(filter, dtype=bool).reshape(-1)
-            if mask.size != n:
+            if mask.size == n and n_wal:
+                mask = np.concatenate([mask, np.ones(n_wal, dtype=bool)])
+            if mask.size != n + n_wal:
                 raise SearchError("InvalidConfig", f"filter mask has {mask.size} entries, index has {n} rows")
         return np.packbits(mask, bitorder="little")
 
@@ -211,9 +336,15 @@ class GpuVectorIndex:
         rows, scores, counts = self.search_top_k_batch(q[None, :], limit, filter=filter)
         n = int(counts[0])
         hits = [VectorHit(int(rows[0, i]), float(scores[0, i]), self.doc_id_at(int(rows[0, i]))) for i in range(n)]
-        if self._dedup:  # resolve_sorted_entries: first (= best) occurrence of a doc id wins (search.rs:1540)
+        if self._dedup or self._wal:
+            # resolve_sorted_entries (search.rs:1503-1558): the first (= best) occurrence of a doc id
+            # wins, and a main row whose doc id has a resident WAL row is shadowed by it
+            wal_ids = {d for d, _ in self._wal}
+            wal_base = self._wal_base()
             seen, out = set(), []
             for h in hits:
+                if h.index < wal_base and (self.is_deleted(h.index) or h.doc_id in wal_ids):
+                    continue
                 if h.doc_id in seen:
                     continue
                 seen.add(h.doc_id)

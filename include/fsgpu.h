@@ -119,6 +119,22 @@ int fsgpu_index_read_rows_f16(const fsgpu_index* index, uint64_t row_start, uint
                               uint16_t* out_bits);
 /* Replaces VectorIndex::soft_delete's effect on the scan (flag bit 0, search.rs:1281). */
 int fsgpu_index_set_tombstones(fsgpu_index* index, const uint8_t* bitmap_or_null);
+/* VectorIndex::is_deleted (lib.rs:2401-2406) in bulk: the current soft-delete bitmap over local rows
+ * ((n_rows + 7) / 8 bytes; for an FSVI file, flag bit 0 of each record as read at open). */
+int fsgpu_index_read_tombstones(const fsgpu_index* index, uint8_t* out_bitmap);
+/* Replaces the resident WAL rows of VectorIndex (`wal_entries`: f32 embeddings appended since the
+ * last compaction, crates/frankensearch-index/src/lib.rs:2532-2720, wal.rs:101-107).  `embeddings`
+ * is host memory, [n_wal, dim] f32 in WAL order; n_wal = 0 clears.  Every search then also scores
+ * the WAL rows with dot_product_f32_f32 (simd.rs:134-222), skips non-finite scores and merges the
+ * rest into the same top-k (scan_wal, search.rs:1449-1475; search.rs:488-491).  WAL row w is
+ * reported as hit row `virtual_base + w` — the reference's `record_count + wal_idx`
+ * (search.rs:1583-1597) — so `virtual_base` must be >= row_base + n_rows and the sum must fit u32;
+ * on equal scores main rows rank before WAL rows (wal.rs:557-569).  Doc-id work — main rows
+ * shadowed by a WAL row of the same doc id, duplicate doc ids — stays with the host's resolve step
+ * (resolve_sorted_entries, search.rs:1503-1558), as do durability and compaction.  With a filter,
+ * the allow bitmap carries the WAL rows after the slab's: bit n_rows + w. */
+int fsgpu_index_set_wal(fsgpu_index* index, const float* embeddings, uint32_t n_wal, uint64_t virtual_base);
+uint32_t fsgpu_index_wal_rows(const fsgpu_index* index);
 
 /* ---- measurement ---------------------------------------------------------------------------- */
 /* Launch accounting for bench.py: counts every kernel this index launches and, while enabled,
@@ -165,7 +181,8 @@ int fsgpu_search_top_k_device(const fsgpu_index* index, const float* d_queries, 
 /* The `filter: Option<&dyn SearchFilter>` argument of VectorIndex::search_top_k
  * (crates/frankensearch-index/src/search.rs:192-206; applied before heap admission,
  * search.rs:1329-1447): the host evaluates the filter per doc id / doc-id hash and passes a packed
- * bitmap over LOCAL rows (bit r%8 of byte r/8 set = row r may be returned; NULL = no filter).
+ * bitmap over LOCAL rows (bit r%8 of byte r/8 set = row r may be returned; NULL = no filter),
+ * followed by one bit per resident WAL row (bit n_rows + w; search.rs:1457-1465).
  * One filter per call, shared by every query of the batch.  Excluded rows never count towards
  * k, exactly like tombstones. */
 int fsgpu_search_top_k_filtered(const fsgpu_index* index, const float* queries, uint32_t batch, uint32_t k,

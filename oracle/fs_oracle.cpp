@@ -212,6 +212,37 @@ inline float dot_fast(const uint16_t* row, const float* q, uint32_t dim, int ord
 #endif
 }
 
+// dot_product_f32_f32 (crates/frankensearch-index/src/simd.rs:161-222 AVX2, :1559-1587 generic) —
+// the score of a resident WAL row (f32 embedding).  Same four accumulators over whole groups of
+// 32, but the left-over 8-chunks are added AFTER `(acc0+acc1)+(acc2+acc3)`, and the scalar tail is
+// always `result += a*b` (mul then add).
+float dot_f32_f32_scalar(const float* a, const float* b, uint32_t dim, int reduce_order) {
+    const uint32_t chunks = dim / 8, groups = dim / 32;
+    float s[4][8];
+    for (auto& acc : s)
+        for (float& l : acc) l = 0.0f;
+    for (uint32_t g = 0; g < groups; ++g)
+        for (uint32_t acc = 0; acc < 4; ++acc)
+            for (uint32_t l = 0; l < 8; ++l) {
+                const uint32_t e = g * 32 + acc * 8 + l;
+                const float p = a[e] * b[e];
+                s[acc][l] = s[acc][l] + p;
+            }
+    float v[8];
+    for (uint32_t l = 0; l < 8; ++l) v[l] = (s[0][l] + s[1][l]) + (s[2][l] + s[3][l]);
+    for (uint32_t c = groups * 4; c < chunks; ++c)
+        for (uint32_t l = 0; l < 8; ++l) {
+            const float p = a[c * 8 + l] * b[c * 8 + l];
+            v[l] = v[l] + p;
+        }
+    float result = reduce8(v, reduce_order);
+    for (uint32_t e = chunks * 8; e < dim; ++e) {
+        const float p = a[e] * b[e];
+        result = result + p;
+    }
+    return result;
+}
+
 // ───────────────────────────── top-k ordering ─────────────────────────────────────────────
 // crates/frankensearch-index/src/search.rs:1655-1661 (score_key), :91-126 (HeapEntry::cmp),
 // :1673-1686 (compare_best_first, candidate_is_better).
@@ -406,6 +437,49 @@ FSO_API uint64_t fso_search_top_k(const uint16_t* slab, uint64_t n, uint32_t dim
         out_scores[i] = winners[i].score;
     }
     return out_n;
+}
+
+FSO_API float fso_dot_f32_f32(const float* a, const float* b, uint32_t dim, int reduce_order) {
+    return dot_f32_f32_scalar(a, b, dim, reduce_order);
+}
+
+// VectorIndex::search_top_k_internal with resident WAL rows (search.rs:426-494): the main-slab heap
+// (as fso_search_top_k; `exclude` = tombstones | !filter) then scan_wal (search.rs:1449-1475) into
+// the SAME bounded heap — WAL entry w is skipped when the filter rejects it or its score is not
+// finite, and enters as index WAL_INDEX_BIT | w (wal.rs:557-569), i.e. after every main row on
+// equal scores.  Winners are sorted best-first (resolve_hits, search.rs:1493-1500); a WAL winner is
+// written as row n + w (resolve_wal_hit, search.rs:1583-1597).  The doc-id part of
+// resolve_sorted_entries (shadowing, dedup) is host logic: oracle/np_oracle.py resolve_sorted_entries.
+FSO_API uint64_t fso_search_top_k_wal(const uint16_t* slab, uint64_t n, uint32_t dim, const uint8_t* exclude,
+                                      const float* wal, uint64_t n_wal, const uint8_t* wal_allow,
+                                      const float* query, uint64_t limit, int threads, int reduce_order,
+                                      int tail_fma, uint64_t* out_rows, float* out_scores) {
+    if (limit == 0 || (n == 0 && n_wal == 0)) return 0;
+    constexpr uint64_t kWalBit = 1ull << 63;
+    std::vector<Entry> heap;
+    if (n > 0) {
+        const uint64_t cap = std::min<uint64_t>(limit, n);
+        std::vector<uint64_t> rows(cap);
+        std::vector<float> scores(cap);
+        // limit >= n + n_wal without a filter is the reference's collect-all path; with the WAL the
+        // heap path and the collect-all path agree (full_recall_collect_all_matches_heap_prefix_with_wal,
+        // search.rs:2688), so the main part is taken from fso_search_top_k either way
+        const uint64_t got = fso_search_top_k(slab, n, dim, exclude, query, limit, threads, reduce_order,
+                                              tail_fma, rows.data(), scores.data());
+        for (uint64_t i = 0; i < got; ++i) insert_candidate(heap, Entry{rows[i], scores[i]}, (size_t)limit);
+    }
+    for (uint64_t w = 0; w < n_wal; ++w) {
+        if (wal_allow && !((wal_allow[w >> 3] >> (w & 7)) & 1u)) continue;
+        const float score = dot_f32_f32_scalar(wal + w * dim, query, dim, reduce_order);
+        if (!std::isfinite(score)) continue;
+        insert_candidate(heap, Entry{kWalBit | w, score}, (size_t)limit);
+    }
+    std::sort(heap.begin(), heap.end(), best_first_less);
+    for (size_t i = 0; i < heap.size(); ++i) {
+        out_rows[i] = (heap[i].index & kWalBit) ? n + (heap[i].index & ~kWalBit) : heap[i].index;
+        out_scores[i] = heap[i].score;
+    }
+    return heap.size();
 }
 
 // TwoTierIndex::quality_scores_for_hits -> dot_query_at

@@ -154,6 +154,43 @@ def search_top_k(slab_bits, query, limit: int, tombstones: Optional[np.ndarray] 
     return rows[:got].copy(), scores[:got].copy()
 
 
+def dot_f32_f32(a, b, reduce_order: int = DEFAULT_REDUCE) -> np.float32:
+    """dot_product_f32_f32 (simd.rs:134-222, :1559-1587) — the score of a resident WAL row."""
+    a, b = _c(a, np.float32), _c(b, np.float32)
+    assert a.size == b.size, "DimensionMismatch"
+    L = lib()
+    L.fso_dot_f32_f32.restype = C.c_float
+    L.fso_dot_f32_f32.argtypes = [_f32p, _f32p, C.c_uint32, C.c_int]
+    return np.float32(L.fso_dot_f32_f32(_p(a, _f32p), _p(b, _f32p), a.size, reduce_order))
+
+
+def search_top_k_wal(slab_bits, wal, query, limit: int, exclude: Optional[np.ndarray] = None,
+                     wal_allow: Optional[np.ndarray] = None, threads: Optional[int] = None,
+                     reduce_order: int = DEFAULT_REDUCE, tail_fma: bool = True):
+    """search_top_k_internal with resident WAL rows (search.rs:426-494, :1449-1475).  slab_bits
+    [n, dim] uint16, wal [n_wal, dim] float32; `exclude` / `wal_allow` are packed bitmaps.  Returns
+    (rows u64 — WAL row w as n + w, scores f32), best-first, before the doc-id resolve step."""
+    slab_bits = _c(slab_bits, np.uint16)
+    n, dim = slab_bits.shape
+    wal = _c(wal, np.float32).reshape(-1, dim)
+    n_wal = wal.shape[0]
+    query = _c(query, np.float32)
+    assert query.size == dim, "DimensionMismatch"
+    cap = max(min(int(limit), n + n_wal), 1)
+    rows = np.empty(cap, dtype=np.uint64)
+    scores = np.empty(cap, dtype=np.float32)
+    ex = None if exclude is None else _c(exclude, np.uint8)
+    wa = None if wal_allow is None else _c(wal_allow, np.uint8)
+    L = lib()
+    L.fso_search_top_k_wal.restype = C.c_uint64
+    L.fso_search_top_k_wal.argtypes = [_u16p, C.c_uint64, C.c_uint32, _u8p, _f32p, C.c_uint64, _u8p, _f32p,
+                                       C.c_uint64, C.c_int, C.c_int, C.c_int, _u64p, _f32p]
+    got = L.fso_search_top_k_wal(_p(slab_bits, _u16p), n, dim, _p(ex, _u8p), _p(wal, _f32p), n_wal,
+                                 _p(wa, _u8p), _p(query, _f32p), int(limit), threads or host_threads(),
+                                 reduce_order, int(tail_fma), _p(rows, _u64p), _p(scores, _f32p))
+    return rows[:got].copy(), scores[:got].copy()
+
+
 def scores_for_rows(slab_bits, query, rows, reduce_order: int = DEFAULT_REDUCE, tail_fma: bool = True):
     slab_bits = _c(slab_bits, np.uint16)
     n, dim = slab_bits.shape

@@ -131,3 +131,51 @@ def top_k(scores: np.ndarray, limit: int, live: np.ndarray | None = None):
     keys = order_keys(scores, rows)
     idx = np.argsort(keys, kind="stable")[:limit]
     return rows[idx], np.asarray(scores, dtype=np.float32)[idx]
+
+
+def dot_f32_f32(a: np.ndarray, b: np.ndarray, reduce_order: int = 0) -> np.float32:
+    """dot_product_f32_f32 (simd.rs:161-222, :1559-1587): left-over 8-chunks are added after the
+    four accumulators are combined; scalar tail is mul then add."""
+    a = np.asarray(a, dtype=np.float32)
+    b = np.asarray(b, dtype=np.float32)
+    dim = a.size
+    chunks, groups = dim // 8, dim // 32
+    s = np.zeros((4, 8), dtype=np.float32)
+    with np.errstate(all="ignore"):
+        for g in range(groups):
+            for acc in range(4):
+                lo = g * 32 + acc * 8
+                s[acc] = s[acc] + a[lo:lo + 8] * b[lo:lo + 8]
+        v = (s[0] + s[1]) + (s[2] + s[3])
+        for c in range(groups * 4, chunks):
+            v = v + a[c * 8:c * 8 + 8] * b[c * 8:c * 8 + 8]
+        result = _reduce8(v, reduce_order)
+        for e in range(chunks * 8, dim):
+            result = F32(result + F32(a[e] * b[e]))
+    return F32(result)
+
+
+def resolve_sorted_entries(rows, scores, main_doc_ids, wal_doc_ids, tombstones=None):
+    """The doc-id half of resolve_sorted_entries (search.rs:1503-1558) over best-first winners:
+    a WAL winner (row >= len(main_doc_ids)) is dropped if its doc id was already emitted; a main
+    winner is dropped if tombstoned, if ANY resident WAL row carries its doc id (shadowing), or if
+    its doc id was already emitted.  Returns [(row, score, doc_id)]."""
+    n = len(main_doc_ids)
+    wal_set = set(wal_doc_ids)
+    seen, out = set(), []
+    for r, sc in zip(rows, scores):
+        r = int(r)
+        if r >= n:
+            doc = wal_doc_ids[r - n]
+            if doc in seen:
+                continue
+            seen.add(doc)
+        else:
+            if tombstones is not None and tombstones[r]:
+                continue
+            doc = main_doc_ids[r]
+            if doc in wal_set or doc in seen:
+                continue
+            seen.add(doc)
+        out.append((r, np.float32(sc), doc))
+    return out

@@ -157,3 +157,77 @@ BLEND_ALIGNED = dict(
     scores=[0.10, None, 0.95, 0.40, 0.99, None],
     alphas=[0.0, 0.3, 0.7, 1.0, NAN],
 )
+
+
+# ── resident WAL rows (crates/frankensearch-index/src/search.rs:426-494, :1449-1558) ─────────
+# Each scenario: main rows, then a list of steps.  ("append", doc, vec) / ("append_batch", [(doc, vec)..]) /
+# ("soft_delete", doc, expect_bool) / ("search", query, k, filter_doc_ids_or_None, checks) where checks is a
+# dict of: ids (exact doc ids, best-first), n (hit count), first (doc id of hit 0), first_score_abs_lt,
+# absent (doc ids that must not appear), present (doc ids that must appear), wal_count.
+def _rows48():
+    return [(f"doc-{i:03}", [float(48 - i), 0.0, 0.0, 0.0]) for i in range(48)]
+
+
+E0 = [1.0, 0.0, 0.0, 0.0]
+WAL_SCENARIOS = [
+    # filter_applies_to_wal_entries (search.rs:2902)
+    dict(name="filter_applies_to_wal_entries", rows=[("doc-a", [1.0, 0.0, 0.0, 0.0])],
+         steps=[("append", "doc-b", [0.9, 0.0, 0.0, 0.0]), ("append", "doc-c", [0.8, 0.0, 0.0, 0.0]),
+                ("search", E0, 10, ["doc-b"], dict(ids=["doc-b"]))]),
+    # filter_works_with_wal_and_main_combined (search.rs:2925)
+    dict(name="filter_works_with_wal_and_main_combined",
+         rows=[("doc-a", [1.0, 0.0, 0.0, 0.0]), ("doc-b", [0.5, 0.0, 0.0, 0.0])],
+         steps=[("append", "doc-c", [0.9, 0.0, 0.0, 0.0]),
+                ("search", E0, 10, ["doc-a", "doc-c"], dict(ids=["doc-a", "doc-c"]))]),
+    # wal_only_search_returns_wal_entries (search.rs:2997)
+    dict(name="wal_only_search_returns_wal_entries", rows=[],
+         steps=[("append", "wal-a", [1.0, 0.0, 0.0, 0.0]), ("append", "wal-b", [0.5, 0.0, 0.0, 0.0]),
+                ("search", E0, 5, None, dict(ids=["wal-a", "wal-b"]))]),
+    # wal_entries_can_outrank_main_index (search.rs:3024)
+    dict(name="wal_entries_can_outrank_main_index",
+         rows=[("main-a", [0.3, 0.0, 0.0, 0.0]), ("main-b", [0.2, 0.0, 0.0, 0.0])],
+         steps=[("append", "wal-top", [1.0, 0.0, 0.0, 0.0]),
+                ("search", E0, 3, None, dict(ids=["wal-top", "main-a", "main-b"]))]),
+    # stale_main_entry_shadowed_by_wal (search.rs:3054): the WAL row (score 0) must be the only hit
+    dict(name="stale_main_entry_shadowed_by_wal", rows=[("doc-a", [1.0, 0.0])],
+         steps=[("append", "doc-a", [0.0, 1.0]),
+                ("search", [1.0, 0.0], 1, None, dict(n=1, first="doc-a", first_score_abs_lt=1.1920929e-07))]),
+    # wal_entries_rank_correctly_against_main (lib.rs:9880)
+    dict(name="wal_entries_rank_correctly_against_main", rows=[("main-mediocre", [0.5, 0.5, 0.0, 0.0])],
+         steps=[("append", "wal-perfect", [1.0, 0.0, 0.0, 0.0]),
+                ("search", E0, 2, None, dict(ids=["wal-perfect", "main-mediocre"]))]),
+    # append_duplicate_doc_id_both_searchable (lib.rs:9907): the WAL row shadows the main row
+    dict(name="append_duplicate_doc_id_shadows_main", rows=[("doc-a", [1.0, 0.0, 0.0, 0.0])],
+         steps=[("append", "doc-a", [0.0, 0.0, 0.0, 1.0]),
+                ("search", E0, 10, None, dict(ids=["doc-a"], wal_count=1))]),
+    # soft_delete_removes_wal_only_record_and_persists (lib.rs:10066)
+    dict(name="soft_delete_removes_wal_only_record", rows=[("main-0", [1.0, 0.0, 0.0, 0.0])],
+         steps=[("append", "wal-only", [0.0, 1.0, 0.0, 0.0]), ("soft_delete", "wal-only", True),
+                ("search", [0.0, 1.0, 0.0, 0.0], 10, None, dict(absent=["wal-only"], wal_count=0))]),
+    # soft_delete_clears_pending_wal_updates_for_same_doc_id (lib.rs:10102)
+    dict(name="soft_delete_clears_pending_wal_updates", rows=[("doc-a", [1.0, 0.0, 0.0, 0.0])],
+         steps=[("append", "doc-a", [0.0, 1.0, 0.0, 0.0]), ("append", "doc-b", [0.0, 0.0, 1.0, 0.0]),
+                ("soft_delete", "doc-a", True),
+                ("search", [0.0, 1.0, 0.0, 0.0], 10, None, dict(absent=["doc-a"], present=["doc-b"], wal_count=1))]),
+    # wal_entries_are_searchable_before_compaction (tests/fsvi_roundtrip.rs:510); normalised inputs
+    dict(name="wal_entries_are_searchable_before_compaction", rows=[("main-doc", [1.0, 0.0, 0.0, 0.0])],
+         steps=[("append", "wal-doc", [0.0, 1.0, 0.0, 0.0]),
+                ("search", [0.1104315, 0.9938837, 0.0, 0.0], 2, None, dict(first="wal-doc", n=2))]),
+    # an update inside one batch keeps the LAST entry of a doc id (append_batch_impl, lib.rs:2601-2611)
+    dict(name="append_batch_last_entry_of_a_doc_wins", rows=[("doc-a", [0.5, 0.0, 0.0, 0.0])],
+         steps=[("append_batch", [("doc-x", [0.1, 0.0, 0.0, 0.0]), ("doc-y", [0.7, 0.0, 0.0, 0.0]),
+                                  ("doc-x", [0.9, 0.0, 0.0, 0.0])]),
+                ("search", E0, 10, None, dict(ids=["doc-x", "doc-y", "doc-a"], wal_count=2))]),
+]
+
+
+# full_recall_collect_all_matches_heap_prefix_with_wal (search.rs:2688)
+def wal_full_recall_case():
+    return dict(rows=_rows48(),
+                wal=[("wal-top", [200.0, 0.0, 0.0, 0.0]), ("wal-mid", [24.5, 0.0, 0.0, 0.0]),
+                     ("wal-tail", [-1.0, 0.0, 0.0, 0.0])],
+                query=E0)
+
+
+# avx2_f32slicedot_matches_generic (simd.rs:2512): xorshift seed and dims of the f32 x f32 dot
+DOT_F32_XORSHIFT = dict(seed=0x7C6D5E4F3A2B1908, dims=[1, 7, 8, 9, 16, 31, 32, 33, 64, 100, 256, 384, 512])

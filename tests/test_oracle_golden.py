@@ -232,3 +232,53 @@ def test_synth_generator_matches_numpy(fo):
         assert np.array_equal(f16[r], no.encode_f16(want))
     u16, u32 = fo.synth_rows(0, 100, 0, 3, dim, want_f32=True)
     assert np.array_equal(bits(u32[2]), bits(norm(raw(102, dim))))
+
+
+# ── resident WAL rows ───────────────────────────────────────────────────────────────────────
+def test_f32_dot_matches_numpy_mirror(fo):
+    """simd.rs:2512 avx2_f32slicedot_matches_generic (same seed, same dims): the C++ statement of
+    dot_product_f32_f32 against the NumPy one, every reduce order."""
+    nxt = _xorshift_stream(rc.DOT_F32_XORSHIFT["seed"])
+    for dim in rc.DOT_F32_XORSHIFT["dims"]:
+        a = np.array([nxt() for _ in range(dim)], dtype=np.float32)
+        b = np.array([nxt() for _ in range(dim)], dtype=np.float32)
+        for order in range(5):
+            assert bits(fo.dot_f32_f32(a, b, order)) == bits(no.dot_f32_f32(a, b, order)), (dim, order)
+        # the value is a dot product (f64 check with a loose bound: orders differ only in rounding)
+        assert abs(float(fo.dot_f32_f32(a, b)) - float(np.dot(a.astype(np.float64), b.astype(np.float64)))) < 1e-4
+
+
+@pytest.mark.parametrize("scenario", rc.WAL_SCENARIOS, ids=[s["name"] for s in rc.WAL_SCENARIOS])
+def test_wal_known_answers(scenario):
+    from wal_model import OracleWalIndex, run_scenario
+
+    run_scenario(lambda ids, vecs, dim: OracleWalIndex(ids, vecs, dim), scenario)
+
+
+def test_wal_full_recall_collect_all_matches_heap_prefix():
+    """search.rs:2688 full_recall_collect_all_matches_heap_prefix_with_wal."""
+    from wal_model import OracleWalIndex
+
+    c = rc.wal_full_recall_case()
+    ix = OracleWalIndex([d for d, _ in c["rows"]], [v for _, v in c["rows"]], 4)
+    ix.append_batch(c["wal"])
+    total = len(c["rows"]) + len(c["wal"])
+    full = ix.search_top_k(c["query"], total + 10)
+    heap = ix.search_top_k(c["query"], total - 5)
+    assert len(full) == total and full[0][2] == "wal-top" and len(heap) == total - 5
+    for h, f in zip(heap, full):
+        assert h[2] == f[2] and h[0] == f[0] and bits(h[1]) == bits(f[1])
+    # WAL rows are numbered after the main rows (resolve_wal_hit, search.rs:1583-1597)
+    assert full[0][0] == 48 and [h[0] for h in full if h[2] == "wal-mid"] == [49]
+    # equal scores: the main row ranks before the WAL row (tagged index, wal.rs:557-569)
+    ix.append("wal-tie", [24.0, 0.0, 0.0, 0.0])
+    ids = [h[2] for h in ix.search_top_k(c["query"], total + 10)]
+    assert ids.index("doc-024") + 1 == ids.index("wal-tie")
+
+
+def test_wal_nonfinite_scores_are_skipped(fo):
+    """scan_wal (search.rs:1466-1470): a WAL row whose score is not finite never enters the heap."""
+    slab = fo.encode_f16(np.array([[1.0, 0.0, 0.0, 0.0]], dtype=np.float32))
+    wal = np.array([[3.0e38, 3.0e38, 0.0, 0.0], [0.5, 0.0, 0.0, 0.0]], dtype=np.float32)
+    rows, scores = fo.search_top_k_wal(slab, wal, np.array([2.0, 2.0, 0.0, 0.0], dtype=np.float32), 10)
+    assert list(rows) == [0, 2] and np.isfinite(scores).all()
