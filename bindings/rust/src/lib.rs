@@ -74,6 +74,10 @@ extern "C" {
     pub fn fsgpu_index_dim(index: *const fsgpu_index) -> u32;
     pub fn fsgpu_index_set_tombstones(index: *mut fsgpu_index, bitmap_or_null: *const u8) -> c_int;
     pub fn fsgpu_index_read_tombstones(index: *const fsgpu_index, out_bitmap: *mut u8) -> c_int;
+    pub fn fsgpu_index_set_doc_hashes(index: *mut fsgpu_index, hashes_or_null: *const u64) -> c_int;
+    pub fn fsgpu_search_top_k_hashes(index: *const fsgpu_index, queries: *const f32, batch: u32, k: u32, dim: u32,
+                                     allowed_sorted: *const u64, n_allowed: u32, wal_allow_bitmap: *const u8,
+                                     out: *mut fsgpu_hit, out_counts: *mut u32, out_used_gather: *mut c_int) -> c_int;
     pub fn fsgpu_index_set_wal(index: *mut fsgpu_index, embeddings: *const f32, n_wal: u32, virtual_base: u64) -> c_int;
     pub fn fsgpu_index_wal_rows(index: *const fsgpu_index) -> u32;
     pub fn fsgpu_index_doc_id(index: *const fsgpu_index, global_row: u64, out_ptr: *mut *const u8,

@@ -105,6 +105,7 @@ EXPORTS = [
     "fsgpu_index_set_wal", "fsgpu_index_wal_rows", "fsgpu_index_read_rows_f16", "fsgpu_index_profile_enable",
     "fsgpu_index_profile_read", "fsgpu_search_top_k", "fsgpu_search_top_k_device",
     "fsgpu_search_top_k_filtered", "fsgpu_search_top_k_filtered_device",
+    "fsgpu_index_set_doc_hashes", "fsgpu_search_top_k_hashes",
     "fsgpu_merge_top_k_device", "fsgpu_merge_top_k_hits_device", "fsgpu_scores_for_rows", "fsgpu_scores_for_rows_device",
     "fsgpu_rrf_fuse", "fsgpu_rrf_fuse_device", "fsgpu_blend_two_tier", "fsgpu_potion_create",
     "fsgpu_potion_destroy", "fsgpu_potion_embed", "fsgpu_potion_embed_device",
@@ -151,6 +152,9 @@ def lib() -> C.CDLL:
     L.fsgpu_index_doc_id.argtypes = [_vp, C.c_uint64, C.POINTER(_vp), C.POINTER(C.c_uint32)]
     L.fsgpu_index_set_tombstones.argtypes = [_vp, _vp]
     L.fsgpu_index_read_tombstones.argtypes = [_vp, _vp]
+    L.fsgpu_index_set_doc_hashes.argtypes = [_vp, _vp]
+    L.fsgpu_search_top_k_hashes.argtypes = [_vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, _vp, C.c_uint32, _vp,
+                                            _vp, _vp, C.POINTER(C.c_int)]
     L.fsgpu_index_set_wal.argtypes = [_vp, _vp, C.c_uint32, C.c_uint64]
     L.fsgpu_index_wal_rows.argtypes = [_vp]
     L.fsgpu_index_wal_rows.restype = C.c_uint32

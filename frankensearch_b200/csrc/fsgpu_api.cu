@@ -78,7 +78,16 @@ struct fsgpu_index {
     uint32_t n_wal = 0;
     uint64_t wal_base = 0;                       // hit row of WAL entry 0 (record_count, search.rs:1583)
     mutable const uint8_t* d_wal_allow = nullptr;  // per-call allow bitmap (bit n_rows + w), else nullptr
+    mutable bool wal_allow_bit0_is_zero = false;   // ... or a bitmap over the WAL rows alone (bit w)
     mutable DevBuf ws_wal_main, ws_wal_keys;
+    // doc-id hashes of the rows (record table field 0, lib.rs:130-174) for hash filters on the device
+    DevBuf d_hashes;
+    bool has_hashes = false;
+    // per-call selective gather (try_gather_filtered, search.rs:1114-1161): listed rows replace the scan
+    mutable const uint32_t* d_gather_pos = nullptr;
+    mutable const uint32_t* d_gather_count = nullptr;
+    mutable uint32_t gather_cap = 0;
+    mutable DevBuf ws_allowed, ws_gather_pos, ws_gather_count, ws_gather_keys;
     cudaStream_t stream = nullptr;
     mutable std::mutex mu;
     // workspaces (grow-only, guarded by mu)
@@ -653,19 +662,57 @@ static int search_main_locked(const fsgpu_index* ix, const float* d_queries, uin
     return search_exact_locked(ix, d_queries, batch, k, d_out_keys, d_out_hits, d_out_counts, stream);
 }
 
+// The selective arm of a filtered search: score only the listed rows (scan_gather_positions,
+// search.rs:1178-1255) and keep the best k.  Same outputs as search_main_locked.
+static int search_gather_locked(const fsgpu_index* ix, const float* d_queries, uint32_t batch, uint32_t k,
+                                uint64_t* d_out_keys, fsgpu_hit* d_out_hits, uint32_t* d_out_counts,
+                                cudaStream_t stream) {
+    const uint32_t cap = ix->gather_cap;
+    CUDA_TRY(ix->ws_gather_keys.reserve((size_t)batch * cap * 8));
+    const dim3 grid((cap + kScanWarps - 1) / kScanWarps, batch);
+    gather_keys_kernel<<<grid, kScanThreads, 0, stream>>>(ix->d_slab, ix->row_base, ix->dim, d_queries,
+                                                          ix->d_gather_pos, ix->d_gather_count, cap,
+                                                          ix->reduce_order, ix->tail_fma,
+                                                          ix->ws_gather_keys.as<uint64_t>());
+    CUDA_TRY(cudaGetLastError());
+    ix->prof.other_launches += 1;
+    ix->prof.merge_launches += 1;
+    MergeArgs m{};
+    m.keys = ix->ws_gather_keys.as<uint64_t>();
+    m.list_stride = 0;
+    m.query_stride = cap;
+    m.n_lists = 1;
+    m.k_in = cap;
+    m.k_out = k;
+    m.cap = cand_capacity(k);
+    m.out_keys = d_out_keys;
+    m.out_hits = d_out_hits;
+    m.out_counts = d_out_counts;
+    m.slab = ix->d_slab;
+    m.queries = d_queries;
+    m.n_rows = ix->n_rows;
+    m.row_base = ix->row_base;
+    m.dim = ix->dim;
+    m.reduce_order = ix->reduce_order;
+    m.tail_fma = ix->tail_fma;
+    m.error_flag = ix->d_error;
+    return launch_merge(m, batch, stream);
+}
+
 // Main slab + resident WAL rows (VectorIndex::search_top_k_internal, search.rs:476-493): the slab's
 // top-k keys and one key per WAL row form one list per query, reduced by the same merge kernel.
 static int search_device_locked(const fsgpu_index* ix, const float* d_queries, uint32_t batch, uint32_t k,
                                 uint64_t* d_out_keys, fsgpu_hit* d_out_hits, uint32_t* d_out_counts,
                                 cudaStream_t stream) {
     if (batch == 0) return FSGPU_OK;
+    auto main_search = (ix->d_gather_pos && k > 0 && ix->n_rows > 0) ? search_gather_locked : search_main_locked;
     if (ix->n_wal == 0 || k == 0)
-        return search_main_locked(ix, d_queries, batch, k, d_out_keys, d_out_hits, d_out_counts, stream);
+        return main_search(ix, d_queries, batch, k, d_out_keys, d_out_hits, d_out_counts, stream);
     const uint64_t* main_keys = nullptr;
     if (ix->n_rows > 0) {
         CUDA_TRY(ix->ws_wal_main.reserve((size_t)batch * k * 8));
         CUDA_TRY(cudaMemsetAsync(ix->ws_wal_main.p, 0, (size_t)batch * k * 8, stream));
-        int rc = search_main_locked(ix, d_queries, batch, k, ix->ws_wal_main.as<uint64_t>(), nullptr, nullptr, stream);
+        int rc = main_search(ix, d_queries, batch, k, ix->ws_wal_main.as<uint64_t>(), nullptr, nullptr, stream);
         if (rc) return rc;
         main_keys = ix->ws_wal_main.as<uint64_t>();
     }
@@ -673,7 +720,7 @@ static int search_device_locked(const fsgpu_index* ix, const float* d_queries, u
     CUDA_TRY(ix->ws_wal_keys.reserve((size_t)batch * stride * 8));
     const dim3 grid((ix->n_wal + kScanWarps - 1) / kScanWarps, batch);
     wal_keys_kernel<<<grid, kScanThreads, 0, stream>>>(ix->d_wal.as<float>(), ix->n_wal, ix->wal_base, ix->dim,
-                                                       d_queries, ix->d_wal_allow, ix->n_rows, main_keys, k,
+                                                       d_queries, ix->d_wal_allow, ix->wal_allow_bit0_is_zero ? 0 : ix->n_rows, main_keys, k,
                                                        ix->reduce_order, ix->ws_wal_keys.as<uint64_t>());
     CUDA_TRY(cudaGetLastError());
     ix->prof.other_launches += 1;
@@ -1081,6 +1128,112 @@ extern "C" int fsgpu_search_top_k_filtered(const fsgpu_index* ix, const float* q
     return check_error_flag(ix, s);
 }
 
+// ─── doc-id-hash filters ────────────────────────────────────────────────────────────────────
+extern "C" int fsgpu_index_set_doc_hashes(fsgpu_index* ix, const uint64_t* hashes) {
+    if (!ix) return fail(FSGPU_ERR_INVALID_CONFIG, "index is NULL");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    DeviceGuard g(ix->device);
+    CUDA_TRY(cudaStreamSynchronize(ix->stream));
+    ix->has_hashes = false;
+    if (!hashes || ix->n_rows == 0) return FSGPU_OK;
+    CUDA_TRY(ix->d_hashes.reserve(ix->n_rows * 8));
+    CUDA_TRY(cudaMemcpy(ix->d_hashes.p, hashes, ix->n_rows * 8, cudaMemcpyHostToDevice));
+    ix->has_hashes = true;
+    return FSGPU_OK;
+}
+
+extern "C" int fsgpu_search_top_k_hashes(const fsgpu_index* ix, const float* queries, uint32_t batch, uint32_t k,
+                                         uint32_t dim, const uint64_t* allowed_sorted, uint32_t n_allowed,
+                                         const uint8_t* wal_allow_bitmap, fsgpu_hit* out, uint32_t* out_counts,
+                                         int* out_used_gather) {
+    if (!ix) return fail(FSGPU_ERR_INVALID_CONFIG, "index is NULL");
+    if (dim != ix->dim) return fail(FSGPU_ERR_DIMENSION_MISMATCH, "expected %u, found %u", ix->dim, dim);
+    if (out_used_gather) *out_used_gather = 0;
+    if (batch == 0) return FSGPU_OK;
+    if (!queries || !out_counts || (k && !out)) return fail(FSGPU_ERR_INVALID_CONFIG, "NULL argument");
+    if (n_allowed && !allowed_sorted) return fail(FSGPU_ERR_INVALID_CONFIG, "allowed_sorted is NULL");
+    for (uint32_t i = 1; i < n_allowed; ++i)
+        if (allowed_sorted[i - 1] >= allowed_sorted[i])
+            return fail(FSGPU_ERR_INVALID_CONFIG, "allowed hashes must be strictly ascending");
+    if (ix->n_rows && !ix->has_hashes)
+        return fail(FSGPU_ERR_INVALID_CONFIG, "index has no doc-id hashes (fsgpu_index_set_doc_hashes)");
+    if (k == 0 || (ix->n_rows == 0 && ix->n_wal == 0)) {
+        memset(out_counts, 0, (size_t)batch * 4);
+        return FSGPU_OK;
+    }
+    std::lock_guard<std::mutex> lock(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t s = ix->stream;
+    CUDA_TRY(ix->ws_queries.reserve((size_t)batch * dim * 4));
+    CUDA_TRY(ix->ws_hits.reserve((size_t)batch * k * sizeof(fsgpu_hit)));
+    CUDA_TRY(ix->ws_counts.reserve((size_t)batch * 4));
+    CUDA_TRY(cudaMemcpyAsync(ix->ws_queries.p, queries, (size_t)batch * dim * 4, cudaMemcpyHostToDevice, s));
+    if (ix->n_wal) {
+        // WAL rows: the host evaluated the filter on their doc ids (search.rs:1457-1465); bit w = WAL row w
+        const size_t wal_bytes = (ix->n_wal + 7) / 8;
+        CUDA_TRY(ix->ws_allow.reserve(wal_bytes));
+        if (wal_allow_bitmap)
+            CUDA_TRY(cudaMemcpyAsync(ix->ws_allow.p, wal_allow_bitmap, wal_bytes, cudaMemcpyHostToDevice, s));
+        else
+            CUDA_TRY(cudaMemsetAsync(ix->ws_allow.p, 0xFF, wal_bytes, s));
+    }
+    // try_gather_filtered (search.rs:1114-1131): the selective arm when allowed * 50 < record_count
+    constexpr uint64_t kGatherSelectivityDivisor = 50;  // search.rs:33
+    bool gather = ix->n_rows > 0 && (uint64_t)n_allowed * kGatherSelectivityDivisor < ix->n_rows;
+    const uint32_t cap = std::max(64u, 2 * n_allowed);  // rows sharing a hash (collisions, duplicate doc ids)
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        if (ix->n_rows > 0) {
+            const size_t n_bytes = (ix->n_rows + 7) / 8;
+            CUDA_TRY(ix->ws_excl.reserve(n_bytes));
+            CUDA_TRY(ix->ws_allowed.reserve(std::max<size_t>(8, (size_t)n_allowed * 8)));
+            if (n_allowed)
+                CUDA_TRY(cudaMemcpyAsync(ix->ws_allowed.p, allowed_sorted, (size_t)n_allowed * 8, cudaMemcpyHostToDevice, s));
+            if (gather) {
+                CUDA_TRY(ix->ws_gather_pos.reserve((size_t)cap * 4));
+                CUDA_TRY(ix->ws_gather_count.reserve(4));
+                CUDA_TRY(cudaMemsetAsync(ix->ws_gather_count.p, 0, 4, s));
+            }
+            hash_filter_kernel<<<(unsigned)std::min<size_t>((n_bytes + 255) / 256, (size_t)ix->num_sms * 8), 256, 0, s>>>(
+                ix->d_hashes.as<uint64_t>(), ix->n_rows, ix->d_tomb, ix->ws_allowed.as<uint64_t>(), n_allowed,
+                ix->ws_excl.as<uint8_t>(), gather ? ix->ws_gather_pos.as<uint32_t>() : nullptr, cap,
+                gather ? ix->ws_gather_count.as<uint32_t>() : nullptr);
+            CUDA_TRY(cudaGetLastError());
+            ix->prof.other_launches += 1;
+            ix->d_excl = ix->ws_excl.as<uint8_t>();
+            if (gather) {
+                ix->d_gather_pos = ix->ws_gather_pos.as<uint32_t>();
+                ix->d_gather_count = ix->ws_gather_count.as<uint32_t>();
+                ix->gather_cap = cap;
+            }
+        }
+        // WAL allow bits live at bit n_rows + w of d_wal_allow: point it so that bit 0 of ws_allow lands there
+        ix->d_wal_allow = ix->n_wal ? ix->ws_allow.as<uint8_t>() : nullptr;
+        ix->wal_allow_bit0_is_zero = true;
+        int rc = search_device_locked(ix, ix->ws_queries.as<float>(), batch, k, nullptr,
+                                      ix->ws_hits.as<fsgpu_hit>(), ix->ws_counts.as<uint32_t>(), s);
+        ix->d_excl = nullptr;
+        ix->d_wal_allow = nullptr;
+        ix->wal_allow_bit0_is_zero = false;
+        ix->d_gather_pos = nullptr;
+        ix->d_gather_count = nullptr;
+        ix->gather_cap = 0;
+        if (rc) return rc;
+        uint32_t listed = 0;
+        if (gather)
+            CUDA_TRY(cudaMemcpyAsync(&listed, ix->ws_gather_count.p, 4, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(out, ix->ws_hits.p, (size_t)batch * k * sizeof(fsgpu_hit), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(out_counts, ix->ws_counts.p, (size_t)batch * 4, cudaMemcpyDeviceToHost, s));
+        rc = check_error_flag(ix, s);
+        if (rc) return rc;
+        if (!gather || listed <= cap) {
+            if (out_used_gather) *out_used_gather = gather ? 1 : 0;
+            return FSGPU_OK;
+        }
+        gather = false;  // more rows share the allowed hashes than the list holds: take the scan (same result)
+    }
+    return FSGPU_OK;
+}
+
 static int merge_top_k_impl(int device, const uint64_t* d_keys, const float* d_scores, const fsgpu_hit* d_hits_in,
                             uint32_t batch, uint32_t n_lists, uint32_t k_in, uint64_t list_stride,
                             uint64_t query_stride, uint32_t k_out, uint64_t* d_out_keys, fsgpu_hit* d_out_hits,
@@ -1312,10 +1465,12 @@ extern "C" int fsgpu_index_open_fsvi(const char* path, uint64_t row_start, uint6
     bool any_tomb = false;
     std::vector<uint8_t> doc_bytes;
     std::vector<uint64_t> doc_off(n + 1, 0);
+    std::vector<uint64_t> hashes(n);
     for (uint64_t r = 0; r < n; ++r) {
         const uint8_t* rec = meta.data() + (row_start + r) * 16;
         uint32_t off;
         uint16_t len, flags;
+        memcpy(&hashes[r], rec, 8);
         memcpy(&off, rec + 8, 4);
         memcpy(&len, rec + 12, 2);
         memcpy(&flags, rec + 14, 2);
@@ -1343,6 +1498,13 @@ extern "C" int fsgpu_index_open_fsvi(const char* path, uint64_t row_start, uint6
     if (rc) return rc;
     ix->doc_bytes.swap(doc_bytes);
     ix->doc_off.swap(doc_off);
+    if (n) {  // record-table hashes (FNV-1a of the doc id, lib.rs:6120-6127) for device-side hash filters
+        rc = fsgpu_index_set_doc_hashes(ix, hashes.data());
+        if (rc) {
+            fsgpu_index_destroy(ix);
+            return rc;
+        }
+    }
     *out = ix;
     return FSGPU_OK;
 }

@@ -466,6 +466,68 @@ wal_keys_kernel(const float* __restrict__ wal, uint32_t n_wal, uint64_t wal_base
     if (lane == 0) out[b * stride + k + w] = key;
 }
 
+// ─── doc-id-hash filters on the device ──────────────────────────────────────────────────────
+// BitsetFilter (crates/frankensearch-core/src/filter.rs:330-383): `matches_doc_id_hash(h) ==
+// Some(set.contains(h))`, applied to the 8-byte hash of each record before heap admission
+// (search.rs:1329-1447).  One thread per 8 rows: binary search of each row's hash in the sorted
+// allow-list, one byte of the EXCLUSION bitmap (tombstones | !allowed) out.  With `positions` the
+// allowed live rows are also appended to a list — the selective arm, try_gather_filtered
+// (search.rs:1114-1161), which scores only those rows; `*n_positions` may exceed `cap` (overflow:
+// the host falls back to the scan, the result is the same).
+__device__ __forceinline__ bool hash_in_sorted(const uint64_t* __restrict__ allowed, uint32_t n, uint64_t h) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        const uint64_t v = __ldg(allowed + mid);
+        if (v < h) lo = mid + 1; else hi = mid;
+    }
+    return lo < n && __ldg(allowed + lo) == h;
+}
+
+__global__ void __launch_bounds__(256)
+hash_filter_kernel(const uint64_t* __restrict__ row_hashes, uint64_t n_rows, const uint8_t* __restrict__ tomb,
+                   const uint64_t* __restrict__ allowed, uint32_t n_allowed, uint8_t* __restrict__ excl,
+                   uint32_t* __restrict__ positions, uint32_t cap, uint32_t* __restrict__ n_positions) {
+    const uint64_t n_bytes = (n_rows + 7) / 8;
+    for (uint64_t byte = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; byte < n_bytes;
+         byte += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t dead = tomb ? tomb[byte] : 0u;
+        uint32_t out = 0xFFu;
+        for (uint32_t j = 0; j < 8; ++j) {
+            const uint64_t r = byte * 8 + j;
+            if (r >= n_rows) break;
+            if (((dead >> j) & 1u) == 0 && hash_in_sorted(allowed, n_allowed, row_hashes[r])) {
+                out &= ~(1u << j);
+                if (positions) {
+                    const uint32_t pos = atomicAdd(n_positions, 1u);
+                    if (pos < cap) positions[pos] = (uint32_t)r;
+                }
+            }
+        }
+        excl[byte] = (uint8_t)out;
+    }
+}
+
+// gather_range (search.rs:1196-1255): exact score of each listed row, one warp per (query, row).
+// Slots past the list are key 0 (empty); merge_topk_kernel keeps the best k.
+__global__ void __launch_bounds__(kScanThreads)
+gather_keys_kernel(const uint16_t* __restrict__ slab, uint64_t row_base, uint32_t dim,
+                   const float* __restrict__ queries, const uint32_t* __restrict__ positions,
+                   const uint32_t* __restrict__ n_positions, uint32_t cap, int reduce_order, int tail_fma,
+                   uint64_t* __restrict__ out) {
+    const uint32_t b = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const uint32_t i = blockIdx.x * kScanWarps + (threadIdx.x >> 5);
+    if (i >= cap) return;
+    uint64_t key = 0ull;
+    if (i < min(*n_positions, cap)) {
+        const uint32_t row = positions[i];
+        const float s = warp_exact_dot(slab + (size_t)row * dim, queries + (size_t)b * dim, dim, reduce_order, tail_fma);
+        key = make_key(s, (uint32_t)(row_base + row));
+    }
+    if (lane == 0) out[(size_t)b * cap + i] = key;
+}
+
 // ─── gather-dot: quality_scores_for_hits (two_tier.rs:1566-1631, :1946-1973) ────────────────
 __global__ void __launch_bounds__(kScanThreads)
 scores_for_rows_kernel(const uint16_t* __restrict__ slab, uint64_t n_rows, uint64_t row_base,

@@ -15,7 +15,7 @@ import numpy as np
 
 from . import _ffi
 from ._ffi import SearchError, check, ptr
-from .types import VectorHit
+from .types import VectorHit, fnv1a_hash
 
 REDUCE_ORDERS = {
     "halves_pairwise": 0, "avx_tree": 1, "halves_sequential": 2, "halves_stride2": 3, "sequential": 4,
@@ -54,6 +54,8 @@ class GpuVectorIndex:
         self._wal: List[tuple] = []          # [(doc_id, float32[dim])] in WAL order (wal.rs:101-107)
         self._tomb: Optional[np.ndarray] = None
         self._rows_of: Optional[dict] = None  # doc id -> local rows, built on first mutation
+        self._hashes_on_device = False        # record-table hashes uploaded (FSVI files bring their own)
+        self.last_filter_arm: Optional[str] = None  # "gather" | "scan" | "bitmap" for the last filtered call
 
     # ── construction ────────────────────────────────────────────────────────────────────────
     @classmethod
@@ -119,6 +121,7 @@ class GpuVectorIndex:
         check(_ffi.lib().fsgpu_index_open_fsvi(path.encode(), row_start, n_rows, C.byref(o), C.byref(h)))
         ix = cls(h.value, None, dedup_doc_ids=True)
         ix._doc_ids_from_handle = True
+        ix._hashes_on_device = True
         n = ix.record_count()
         if n:  # record flag bit 0 as stored in the file (lib.rs:172)
             bm = np.zeros((n + 7) // 8, dtype=np.uint8)
@@ -292,6 +295,15 @@ class GpuVectorIndex:
             self._upload_wal()
         return deleted
 
+    def _ensure_doc_hashes(self) -> None:
+        if self._hashes_on_device or self.record_count() == 0:
+            return
+        if self._doc_ids is None:
+            raise SearchError("InvalidConfig", "a hash filter needs doc ids")
+        hashes = np.array([fnv1a_hash(d.encode("utf-8")) for d in self._doc_ids], dtype=np.uint64)
+        check(self._L.fsgpu_index_set_doc_hashes(self._h, ptr(hashes)))
+        self._hashes_on_device = True
+
     # ── exact search ────────────────────────────────────────────────────────────────────────
     def _allow_bitmap(self, filter) -> Optional[np.ndarray]:
         """`filter` is the reference's `SearchFilter` seen from the host: a callable
@@ -324,7 +336,22 @@ class GpuVectorIndex:
         counts = np.zeros(b, dtype=np.uint32)
         if filter is None:
             check(self._L.fsgpu_search_top_k(self._h, ptr(q), b, k, dim, ptr(hits), ptr(counts)))
+        elif callable(getattr(filter, "candidate_hashes", None)) and filter.candidate_hashes() is not None:
+            # BitsetFilter: decided by the record-table hash, on the device (search.rs:1329-1447),
+            # selective sets through the gather arm (search.rs:1114-1161)
+            self._ensure_doc_hashes()
+            allowed = np.array(sorted(filter.candidate_hashes()), dtype=np.uint64)
+            wal_allow = None
+            if self._wal:
+                wal_allow = np.packbits(np.array([bool(filter.matches(d)) for d, _ in self._wal], dtype=bool),
+                                        bitorder="little")
+            used = C.c_int(0)
+            check(self._L.fsgpu_search_top_k_hashes(self._h, ptr(q), b, k, dim, ptr(allowed) if allowed.size else None,
+                                                    allowed.size, ptr(wal_allow), ptr(hits), ptr(counts),
+                                                    C.byref(used)))
+            self.last_filter_arm = "gather" if used.value else "scan"
         else:
+            self.last_filter_arm = "bitmap"
             bm = self._allow_bitmap(filter)
             check(self._L.fsgpu_search_top_k_filtered(self._h, ptr(q), b, k, dim, ptr(bm), ptr(hits), ptr(counts)))
         return hits["row"][:, :k].copy(), hits["score"][:, :k].copy(), counts

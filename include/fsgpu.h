@@ -192,6 +192,22 @@ int fsgpu_search_top_k_filtered_device(const fsgpu_index* index, const float* d_
                                        uint32_t k, const uint8_t* d_allow_bitmap, uint64_t* d_out_keys,
                                        fsgpu_hit* d_out_hits, uint32_t* d_out_counts, void* stream);
 
+/* Doc-id-hash filters evaluated on the device.  `fsgpu_index_set_doc_hashes` gives the index the
+ * 8-byte FNV-1a doc-id hash of every local row (record-table field 0, lib.rs:130-174, :6120-6127);
+ * an FSVI file supplies them at open.  `fsgpu_search_top_k_hashes` is VectorIndex::search_top_k with
+ * a BitsetFilter (crates/frankensearch-core/src/filter.rs:330-383: a row passes iff its hash is in
+ * the set; search.rs:1329-1447): `allowed_sorted` is the set, strictly ascending.  When
+ * n_allowed * 50 < n_rows it takes the reference's selective arm, try_gather_filtered
+ * (search.rs:33, :1114-1255) — only the rows carrying an allowed hash are scored — otherwise the
+ * filtered scan; both give the same hits.  `wal_allow_bitmap` (nullable = all pass) holds one bit
+ * per resident WAL row, evaluated by the host on the WAL doc ids (search.rs:1457-1465).
+ * `out_used_gather` (nullable) reports which arm ran. */
+int fsgpu_index_set_doc_hashes(fsgpu_index* index, const uint64_t* hashes_or_null);
+int fsgpu_search_top_k_hashes(const fsgpu_index* index, const float* queries, uint32_t batch, uint32_t k,
+                              uint32_t dim, const uint64_t* allowed_sorted, uint32_t n_allowed,
+                              const uint8_t* wal_allow_bitmap, fsgpu_hit* out, uint32_t* out_counts,
+                              int* out_used_gather);
+
 /* Replaces merge_partial_heaps (search.rs:1704-1720) across shards: d_keys holds, per query,
  * `n_lists` lists of `k_in` keys ([batch, n_lists, k_in], 0 = empty; e.g. an all-gather of
  * per-rank results laid out rank-major is passed with `list_stride` = batch*k_in and
