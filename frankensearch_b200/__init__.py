@@ -9,7 +9,8 @@ from ._ffi import SearchError  # noqa: F401
 from .types import FusedHit, RrfConfig, ScoredResult, VectorHit, candidate_count  # noqa: F401
 from .index import GpuVectorIndex  # noqa: F401
 from .filter import BitsetFilter, PredicateFilter  # noqa: F401
-from .fusion import blend_two_tier, blend_two_tier_aligned, rrf_fuse  # noqa: F401
+from .fusion import (RankChanges, blend_two_tier, blend_two_tier_aligned, compute_rank_changes,  # noqa: F401
+                     kendall_tau, rrf_fuse)
 from .embed import MiniLmEmbedder, Model2VecEmbedder  # noqa: F401
 from .sharded import ShardedGpuIndex, shard_bounds  # noqa: F401
 from .searcher import GpuSyncTwoTierSearcher, SyncSearchOutcome, TwoTierConfig  # noqa: F401

@@ -131,3 +131,89 @@ def blend_two_tier_aligned(fast_hits: Sequence[VectorHit], quality_scores: Seque
         first_index.setdefault(h.doc_id, h.index)
     names = list(ids)
     return [VectorHit(first_index[names[int(o["row"])]], float(o["score"]), names[int(o["row"])]) for o in out]
+
+
+# ── phase-2 diagnostics: how much the quality tier reordered the fast tier ──────────────────
+# Host-side integer work on the two result lists (crates/frankensearch-fusion/src/blend.rs:365-544);
+# the searcher reports them with the refined results (searcher.rs:2560-2617).
+class RankChanges:
+    """blend.rs RankChanges: promoted / demoted / stable counts."""
+
+    __slots__ = ("promoted", "demoted", "stable")
+
+    def __init__(self, promoted: int = 0, demoted: int = 0, stable: int = 0):
+        self.promoted, self.demoted, self.stable = promoted, demoted, stable
+
+    def __eq__(self, other):
+        return (self.promoted, self.demoted, self.stable) == (other.promoted, other.demoted, other.stable)
+
+    def __repr__(self):
+        return f"RankChanges(promoted={self.promoted}, demoted={self.demoted}, stable={self.stable})"
+
+
+def build_rank_map(hits: Sequence[VectorHit]) -> Dict[str, int]:
+    """build_borrowed_rank_map (blend.rs:538-544): doc id -> rank, first occurrence wins."""
+    ranks: Dict[str, int] = {}
+    for rank, h in enumerate(hits):
+        ranks.setdefault(h.doc_id, rank)
+    return ranks
+
+
+def compute_rank_changes(initial: Sequence[VectorHit], refined: Sequence[VectorHit]) -> RankChanges:
+    """compute_rank_changes (blend.rs:365-409): promoted = rank improved or new in `refined`,
+    demoted = rank worsened or dropped from `refined`, stable = unchanged."""
+    a, b = build_rank_map(initial), build_rank_map(refined)
+    out = RankChanges()
+    for doc, old in a.items():
+        new = b.get(doc)
+        if new is None or new > old:
+            out.demoted += 1
+        elif new < old:
+            out.promoted += 1
+        else:
+            out.stable += 1
+    out.promoted += sum(1 for doc in b if doc not in a)
+    return out
+
+
+def _count_inversions(values: List[int]) -> int:
+    """merge_sort_inversions (blend.rs:461-516): pairs i < j with values[i] > values[j]."""
+    n = len(values)
+    if n <= 1:
+        return 0
+    mid = n // 2
+    left, right = values[:mid], values[mid:]
+    count = _count_inversions(left) + _count_inversions(right)
+    i = j = 0
+    merged = []
+    while i < len(left) and j < len(right):
+        if left[i] <= right[j]:
+            merged.append(left[i])
+            i += 1
+        else:
+            merged.append(right[j])
+            count += len(left) - i
+            j += 1
+    merged.extend(left[i:])
+    merged.extend(right[j:])
+    values[:] = merged
+    return count
+
+
+def kendall_tau(initial: Sequence[VectorHit], refined: Sequence[VectorHit]) -> Optional[float]:
+    """kendall_tau (blend.rs:411-459): rank correlation over the doc ids common to both lists, in
+    `initial` order (first occurrence of a doc id only); None with fewer than two common docs."""
+    refined_rank = build_rank_map(refined)
+    seen, ranks = set(), []
+    for h in initial:
+        r = refined_rank.get(h.doc_id)
+        if r is not None and h.doc_id not in seen:
+            seen.add(h.doc_id)
+            ranks.append(r)
+    n = len(ranks)
+    if n < 2:
+        return None
+    total = n * (n - 1) // 2
+    discordant = _count_inversions(ranks)
+    concordant = max(total - discordant, 0)
+    return (float(concordant) - float(discordant)) / float(total)

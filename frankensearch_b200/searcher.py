@@ -5,7 +5,9 @@ scan + top-k, quality re-scoring, blend, RRF) runs in libfsgpu.so.
 
 Honoured but not re-implemented: query admission / identity bundles, NQC adaptive
 down-weighting (the caller passes the effective `semantic_weight`, i.e. the behaviour of
-`with_nqc_dense_downweight_disabled`, sync_searcher.rs:474-481), explanations, rank-change metrics.
+`with_nqc_dense_downweight_disabled`, sync_searcher.rs:474-481), explanations.  Phase 2 also reports
+the rank-change diagnostics of the async searcher (searcher.rs:2405-2412): Kendall tau and
+promoted / demoted / stable counts between the fast pool and the blended pool.
 """
 from __future__ import annotations
 
@@ -15,7 +17,7 @@ from typing import Callable, List, Optional, Sequence
 
 import numpy as np
 
-from .fusion import blend_two_tier, blend_two_tier_aligned, rrf_fuse
+from .fusion import blend_two_tier, blend_two_tier_aligned, compute_rank_changes, kendall_tau, rrf_fuse
 from .index import GpuVectorIndex
 from .types import RrfConfig, ScoredResult, VectorHit, candidate_count
 
@@ -133,6 +135,8 @@ class GpuSyncTwoTierSearcher:
             blended = blend_two_tier_aligned(fast_hits, scores, self.config.quality_weight)
         metrics["phase2_vectors_searched"] = len(quality_scores_by_doc)
         metrics["quality_search_ms"] = ms(t3)
+        metrics["kendall_tau"] = kendall_tau(fast_hits, blended)             # searcher.rs:2405-2412
+        metrics["rank_changes"] = compute_rank_changes(fast_hits, blended)
         if lexical_hits is not None:
             refined = _fused_to_scored(rrf_fuse(lexical_hits, blended, k, 0, self._rrf_config()), k)  # :898-918
         else:

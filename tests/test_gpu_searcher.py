@@ -68,6 +68,10 @@ def test_sync_two_tier_searcher_matches_oracle_flow(fs, fo, attested, with_lexic
         want_initial, want_refined, fmap, qmap = oracle_flow(fo, fast_slab, qual_slab, ids, fq, qq, k, lexical,
                                                               attested, cfg)
         assert out.refined
+        rc_ = out.metrics["rank_changes"]  # searcher.rs:2405-2412: every fast-pool doc is counted once
+        assert rc_.demoted + rc_.stable + rc_.promoted >= 3 * k
+        tau = out.metrics["kendall_tau"]
+        assert tau is not None and -1.0 <= tau <= 1.0
         assert [(r.doc_id, np.float32(r.score).view(np.uint32)) for r in out.initial_results] == \
                [(d, np.float32(s).view(np.uint32)) for d, s in want_initial]
         assert [(r.doc_id, np.float32(r.score).view(np.uint32)) for r in out.final_results] == \

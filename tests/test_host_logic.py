@@ -127,3 +127,70 @@ def test_sharded_search_equals_single_index_over_gloo():
         rows, scores = fo.search_top_k(slab, queries[b], k)
         want = ~no.order_keys(scores, rows)
         assert np.array_equal(ret[0][b], want)
+
+
+# ── phase-2 diagnostics (crates/frankensearch-fusion/src/blend.rs:365-544 and its tests) ─────
+def _hit(doc, score, index):
+    from frankensearch_b200.types import VectorHit
+
+    return VectorHit(index, score, doc)
+
+
+def test_rank_changes_known_answers():
+    from frankensearch_b200.fusion import RankChanges, build_rank_map, compute_rank_changes
+
+    initial = [_hit("a", 1.0, 0), _hit("b", 0.9, 1), _hit("c", 0.8, 2)]
+    refined = [_hit("b", 1.0, 1), _hit("a", 0.9, 0), _hit("d", 0.7, 3)]
+    # compute_rank_changes_tracks_promoted_demoted_stable (blend.rs:817): b up + d new, a down + c dropped
+    assert compute_rank_changes(initial, refined) == RankChanges(2, 2, 0)
+    # compute_rank_changes_identical_lists_are_all_stable (blend.rs:898), _empty_lists (:907)
+    assert compute_rank_changes(initial[:2], initial[:2]) == RankChanges(0, 0, 2)
+    assert compute_rank_changes([], []) == RankChanges(0, 0, 0)
+    # compute_rank_changes_with_maps_all_new (blend.rs:1166)
+    assert compute_rank_changes([], refined) == RankChanges(3, 0, 0)
+    # build_borrowed_rank_map_first_occurrence_wins (blend.rs:1131)
+    assert build_rank_map([_hit("dup", 1.0, 0), _hit("other", 0.9, 1), _hit("dup", 0.5, 2)]) == {"dup": 0, "other": 1}
+
+
+def test_kendall_tau_known_answers():
+    from frankensearch_b200.fusion import kendall_tau
+
+    abc = [_hit("a", 1.0, 0), _hit("b", 0.9, 1), _hit("c", 0.8, 2)]
+    assert kendall_tau(abc, [_hit("a", 0.7, 0), _hit("b", 0.6, 1), _hit("c", 0.5, 2)]) == 1.0     # blend.rs:828
+    assert kendall_tau(abc, [_hit("c", 0.7, 2), _hit("b", 0.6, 1), _hit("a", 0.5, 0)]) == -1.0    # blend.rs:836
+    assert kendall_tau([_hit("a", 1.0, 0)], [_hit("b", 0.9, 1)]) is None                          # blend.rs:844
+    # kendall_tau_partial_overlap (blend.rs:915): common a, c, d -> refined ranks [2, 0, 3] -> 1/3
+    initial = [_hit("a", 1.0, 0), _hit("b", 0.9, 1), _hit("c", 0.8, 2), _hit("d", 0.7, 3)]
+    refined = [_hit("c", 1.0, 2), _hit("x", 0.9, 4), _hit("a", 0.8, 0), _hit("d", 0.7, 3)]
+    assert abs(kendall_tau(initial, refined) - 1.0 / 3.0) < 1e-10
+    assert kendall_tau([_hit("a", 1.0, 0), _hit("b", 0.5, 1)], [_hit("b", 1.0, 1), _hit("a", 0.5, 0)]) == -1.0  # :940
+    docs = [f"doc-{i:04}" for i in range(100)]
+    fwd = [_hit(d, 1.0, 0) for d in docs]
+    assert kendall_tau(fwd, [_hit(d, 0.5, 0) for d in docs]) == 1.0                                # blend.rs:951
+    assert kendall_tau(fwd, [_hit(d, 0.5, 0) for d in reversed(docs)]) == -1.0                     # blend.rs:968
+
+
+def test_kendall_tau_matches_naive_for_deterministic_permutations():
+    """blend.rs:1021: xorshift-shuffled rankings, merge-sort inversion count == O(n^2) pair count."""
+    from frankensearch_b200.fusion import kendall_tau
+
+    def shuffle(values, seed):
+        state = (seed + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+        for i in range(len(values) - 1, 0, -1):
+            state ^= (state << 13) & 0xFFFFFFFFFFFFFFFF
+            state ^= state >> 7
+            state ^= (state << 17) & 0xFFFFFFFFFFFFFFFF
+            j = state % (i + 1)
+            values[i], values[j] = values[j], values[i]
+
+    for n in (2, 3, 5, 17, 64, 257):
+        for seed in (1, 7, 1234567):
+            order = list(range(n))
+            shuffle(order, seed)
+            initial = [_hit(f"d{i}", 1.0, i) for i in range(n)]
+            refined = [_hit(f"d{i}", 1.0, i) for i in order]
+            rank = {f"d{i}": r for r, i in enumerate(order)}
+            ranks = [rank[f"d{i}"] for i in range(n)]
+            disc = sum(1 for i in range(n) for j in range(i + 1, n) if ranks[i] > ranks[j])
+            total = n * (n - 1) // 2
+            assert kendall_tau(initial, refined) == ((total - disc) - disc) / total
