@@ -795,7 +795,7 @@ static int upload_tombstones(fsgpu_index* ix, const uint8_t* bitmap) {
     if (!bitmap || ix->n_rows == 0) return FSGPU_OK;
     const size_t bytes = (ix->n_rows + 7) / 8;
     CUDA_TRY(cudaMalloc(&ix->d_tomb, bytes));
-    CUDA_TRY(cudaMemcpy(ix->d_tomb, bitmap, bytes, cudaMemcpyHostToDevice));
+    CUDA_TRY(h2d_complete(ix->d_tomb, bitmap, bytes));
     return FSGPU_OK;
 }
 
@@ -845,7 +845,7 @@ extern "C" int fsgpu_index_create_f16(const uint16_t* slab, uint64_t n_rows, uin
         }
     } else if (bytes) {
         e = cudaMalloc(&ix->d_slab, bytes);
-        if (e == cudaSuccess) e = cudaMemcpy(ix->d_slab, slab, bytes, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = h2d_complete(ix->d_slab, slab, bytes);
         ix->owns_slab = true;
     }
     if (e != cudaSuccess) {
@@ -879,7 +879,7 @@ extern "C" int fsgpu_index_create_f32(const float* rows, uint64_t n_rows, uint32
         ix->owns_slab = true;
         if (e == cudaSuccess && !o.slab_is_device) {
             e = cudaMalloc(&staged, count * 4);
-            if (e == cudaSuccess) e = cudaMemcpy(staged, rows, count * 4, cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) e = h2d_complete(staged, rows, count * 4);
             d_src = staged;
         }
         if (e == cudaSuccess) {
@@ -976,7 +976,7 @@ extern "C" int fsgpu_index_set_wal(fsgpu_index* ix, const float* embeddings, uin
     CUDA_TRY(cudaStreamSynchronize(ix->stream));
     if (n_wal) {
         CUDA_TRY(ix->d_wal.reserve((size_t)n_wal * ix->dim * 4));
-        CUDA_TRY(cudaMemcpy(ix->d_wal.p, embeddings, (size_t)n_wal * ix->dim * 4, cudaMemcpyHostToDevice));
+        CUDA_TRY(h2d_complete(ix->d_wal.p, embeddings, (size_t)n_wal * ix->dim * 4));
     }
     ix->n_wal = n_wal;
     ix->wal_base = virtual_base;
@@ -1137,7 +1137,7 @@ extern "C" int fsgpu_index_set_doc_hashes(fsgpu_index* ix, const uint64_t* hashe
     ix->has_hashes = false;
     if (!hashes || ix->n_rows == 0) return FSGPU_OK;
     CUDA_TRY(ix->d_hashes.reserve(ix->n_rows * 8));
-    CUDA_TRY(cudaMemcpy(ix->d_hashes.p, hashes, ix->n_rows * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(h2d_complete(ix->d_hashes.p, hashes, ix->n_rows * 8));
     ix->has_hashes = true;
     return FSGPU_OK;
 }

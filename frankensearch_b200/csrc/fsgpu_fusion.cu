@@ -227,7 +227,7 @@ extern "C" int fsgpu_potion_create(const float* table, uint64_t vocab, uint32_t 
     e->dim = dim;
     DeviceGuard g(device);
     cudaError_t err = cudaMalloc(&e->d_table, vocab * dim * 4);
-    if (err == cudaSuccess) err = cudaMemcpy(e->d_table, table, vocab * dim * 4, cudaMemcpyHostToDevice);
+    if (err == cudaSuccess) err = h2d_complete(e->d_table, table, vocab * dim * 4);
     if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
     if (err != cudaSuccess) {
         fsgpu_potion_destroy(e);

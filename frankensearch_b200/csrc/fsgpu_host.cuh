@@ -23,6 +23,16 @@ int fsgpu_fail(int code, const char* fmt, ...);
                         cudaGetErrorString(_e), __FILE__, __LINE__);                           \
     } while (0)
 
+// Host -> device copy that has LANDED when it returns.  A plain cudaMemcpy from pageable memory may
+// return once the bytes are staged, with the DMA still in flight on the legacy stream, and this
+// library's streams are non-blocking (they do not order against the legacy stream): a kernel
+// launched right after on one of them could read the destination too early.
+static inline cudaError_t h2d_complete(void* dst, const void* src, size_t bytes) {
+    cudaError_t e = cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamLegacy);
+    return e;
+}
+
 // Small RAII-free device buffer that only grows.
 struct DevBuf {
     void* p = nullptr;
@@ -72,7 +82,7 @@ struct Staging {
         if (e != cudaSuccess) return e;
         ptrs.push_back(p);
         *dev = reinterpret_cast<T*>(p);
-        return cudaMemcpy(p, host, count * sizeof(T), cudaMemcpyHostToDevice);
+        return h2d_complete(p, host, count * sizeof(T));
     }
     template <class T>
     cudaError_t alloc(size_t count, T** dev) {

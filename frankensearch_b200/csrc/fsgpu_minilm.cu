@@ -50,7 +50,7 @@ static int minilm_upload(fsgpu_minilm* e, const float* host, size_t count, float
     if (!host) return fail(FSGPU_ERR_INVALID_CONFIG, "minilm: a weight pointer is NULL");
     CUDA_TRY(cudaMalloc(dev, count * 4));
     e->owned.push_back(*dev);
-    CUDA_TRY(cudaMemcpy(*dev, host, count * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(h2d_complete(*dev, host, count * 4));
     return FSGPU_OK;
 }
 
@@ -59,7 +59,7 @@ static int minilm_upload_split(fsgpu_minilm* e, const float* host, uint64_t rows
     if (!host) return fail(FSGPU_ERR_INVALID_CONFIG, "minilm: a weight pointer is NULL");
     const size_t n = (size_t)rows * cols;
     CUDA_TRY(cudaMalloc(&tmp, n * 4));
-    cudaError_t err = cudaMemcpy(tmp, host, n * 4, cudaMemcpyHostToDevice);
+    cudaError_t err = h2d_complete(tmp, host, n * 4);
     if (err == cudaSuccess) err = cudaMalloc(&m->hi, n * 2);
     if (err == cudaSuccess) e->owned.push_back(m->hi);
     if (err == cudaSuccess) err = cudaMalloc(&m->lo, n * 2);

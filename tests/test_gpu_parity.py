@@ -499,3 +499,60 @@ def test_config3_10m_x_384_properties_and_full_oracle(gpu, cpu, fo):
     want = cpu.search_bits(host, q, k)
     assert_same_hits((rows[0].tolist(), scores[0]), want, "10M full oracle")
     ix.close()
+
+
+def test_concurrent_callers_share_one_index(gpu, cpu, fo):
+    """The reference's index methods take `&self` and are called from many threads at once
+    (`Arc<TwoTierIndex>`, searcher.rs:256); calls on one handle are serialised inside the library.
+    Eight threads mix single queries, batches (tensor-core pass), filtered searches and re-scoring
+    on one index; every result must equal the serial one."""
+    import threading
+
+    import frankensearch_b200 as fs
+
+    n, dim = 50000, 128
+    slab, _ = fo.synth_rows(1, 5, 0, n, dim)
+    ix = fs.GpuVectorIndex.from_f16_bits(None, slab)
+    queries = np.stack([fo.clustered_query(q, dim) for q in range(40)])
+    allow = np.arange(n) % 3 != 0
+    jobs = []
+    for t in range(8):
+        lo = t * 5
+        if t % 4 == 0:
+            jobs.append(("single", queries[lo], 10, None))
+        elif t % 4 == 1:
+            jobs.append(("batch", queries[lo:lo + 5], 100, None))
+        elif t % 4 == 2:
+            jobs.append(("batch", queries[lo:lo + 5], 10, allow))
+        else:
+            jobs.append(("rescore", queries[lo], np.arange(lo, lo + 64, dtype=np.uint32), None))
+
+    def run(job):
+        kind, q, k, mask = job
+        if kind == "rescore":
+            s, p = ix.scores_for_rows(q, k)
+            return s.view(np.uint32).copy(), p.copy()
+        r, s, c = ix.search_top_k_batch(q, k, filter=mask)
+        return r.copy(), s.view(np.uint32).copy(), c.copy()
+
+    serial = [run(j) for j in jobs]
+    errors, results = [], [[None] * 6 for _ in jobs]
+
+    def worker(i):
+        try:
+            for rep in range(6):
+                results[i][rep] = run(jobs[i])
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(len(jobs))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for i, want in enumerate(serial):
+        for rep in range(6):
+            for a, b in zip(results[i][rep], want):
+                assert np.array_equal(a, b), (i, rep)
+    ix.close()
