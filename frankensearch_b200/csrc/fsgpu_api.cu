@@ -93,7 +93,8 @@ struct fsgpu_index {
     // workspaces (grow-only, guarded by mu)
     mutable DevBuf ws_partial, ws_queries, ws_keys, ws_hits, ws_counts, ws_sort_a, ws_sort_b,
         ws_cub, ws_rows, ws_scores, ws_present;
-    uint32_t* d_error = nullptr;
+    uint32_t* d_error = nullptr;    // [2]: {contract-violation flag, "some query needs the exact path"}
+    uint32_t* h_flags = nullptr;    // pinned mirror of d_error[0..2): one small D2H per batched search
     // batched tensor-core path (mma_scan_kernels.cuh): slab statistics for the error bound, the
     // slab's TMA descriptor, workspaces
     bool mma_ok = false;            // dim % 64 == 0, dim <= 512, every element finite, TMA usable
@@ -618,18 +619,22 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
         r.out_hits = d_out_hits ? d_out_hits + (size_t)done * k : nullptr;
         r.out_counts = d_out_counts ? d_out_counts + done : nullptr;
         r.error_flag = ix->d_error;
+        r.redo_any = ix->d_error + 1;
         mma_refine_kernel<<<sub, 256, refine_smem, stream>>>(r);
         CUDA_TRY(cudaGetLastError());
         trace.mark("refine");
 
-        redo_host.resize(sub);
-        uint32_t err_flag = 0;
-        CUDA_TRY(cudaMemcpyAsync(redo_host.data(), ix->ws_redo.p, (size_t)sub * 4, cudaMemcpyDeviceToHost, stream));
-        CUDA_TRY(cudaMemcpyAsync(&err_flag, ix->d_error, 4, cudaMemcpyDeviceToHost, stream));
+        // one 8-byte read-back into pinned memory tells whether anything is left to do
+        CUDA_TRY(cudaMemcpyAsync(ix->h_flags, ix->d_error, 8, cudaMemcpyDeviceToHost, stream));
         trace.mark("flags_d2h");
         CUDA_TRY(cudaStreamSynchronize(stream));
         trace.report(sub, ix->n_rows);
-        if (err_flag) return fail(FSGPU_ERR_SUBSYSTEM, "gpu: top-k candidate buffer contract violated (refine)");
+        if (ix->h_flags[0]) return fail(FSGPU_ERR_SUBSYSTEM, "gpu: top-k candidate buffer contract violated (refine)");
+        if (!ix->h_flags[1]) continue;
+        redo_host.resize(sub);
+        CUDA_TRY(cudaMemcpyAsync(redo_host.data(), ix->ws_redo.p, (size_t)sub * 4, cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        CUDA_TRY(cudaMemsetAsync(ix->d_error + 1, 0, 4, stream));  // the next super-batch starts clean
         for (uint32_t b = 0; b < sub; ++b) {
             if (!redo_host[b]) continue;
             ix->prof.redo_queries += 1;
@@ -656,7 +661,7 @@ static int search_main_locked(const fsgpu_index* ix, const float* d_queries, uin
     const bool mma = ix->mma_ok && min_batch > 0 && batch >= (uint32_t)min_batch && k >= 1 && k <= kMmaMaxK &&
                      ix->n_rows > 0;
     if (mma) {
-        CUDA_TRY(cudaMemsetAsync(ix->d_error, 0, 4, stream));
+        CUDA_TRY(cudaMemsetAsync(ix->d_error, 0, 8, stream));
         return search_mma_locked(ix, d_queries, batch, k, d_out_keys, d_out_hits, d_out_counts, stream);
     }
     return search_exact_locked(ix, d_queries, batch, k, d_out_keys, d_out_hits, d_out_counts, stream);
@@ -782,8 +787,9 @@ static int index_alloc_common(fsgpu_index* ix, const fsgpu_index_options* o, uin
                     ix->device, prop.major, prop.minor);
     ix->num_sms = prop.multiProcessorCount;
     CUDA_TRY(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
-    CUDA_TRY(cudaMalloc(&ix->d_error, 4));
-    CUDA_TRY(cudaMemset(ix->d_error, 0, 4));
+    CUDA_TRY(cudaMalloc(&ix->d_error, 8));
+    CUDA_TRY(cudaMemset(ix->d_error, 0, 8));
+    CUDA_TRY(cudaHostAlloc(&ix->h_flags, 8, cudaHostAllocDefault));
     return FSGPU_OK;
 }
 
@@ -807,6 +813,7 @@ extern "C" void fsgpu_index_destroy(fsgpu_index* ix) {
         if (ix->owns_slab && ix->d_slab) cudaFree(ix->d_slab);
         if (ix->d_tomb) cudaFree(ix->d_tomb);
         if (ix->d_error) cudaFree(ix->d_error);
+        if (ix->h_flags) cudaFreeHost(ix->h_flags);
         for (auto* v : {&ix->ev_pending, &ix->ev_free})
             for (auto& ev : *v) {
                 cudaEventDestroy(ev.first);

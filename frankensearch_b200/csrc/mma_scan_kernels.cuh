@@ -805,6 +805,7 @@ struct MmaRefineArgs {
     fsgpu_hit_t* out_hits;       // [batch, k] (nullable)
     uint32_t* out_counts;        // [batch] (nullable)
     uint32_t* error_flag;
+    uint32_t* redo_any;          // set to 1 when any query of the launch needs the exact path
 };
 
 // Re-scores (warp-cooperatively) the rows whose lanes hold `pass` and offers the exact keys.
@@ -833,7 +834,10 @@ __global__ void __launch_bounds__(256) mma_refine_kernel(const MmaRefineArgs arg
     const uint32_t b = blockIdx.x;
     const uint32_t step = blockDim.x;
     const MmaLists& l = args.lists;
-    if (args.redo[b] != 0u) return;  // the caller re-runs this query on the exact path
+    if (args.redo[b] != 0u) {  // the caller re-runs this query on the exact path
+        if (threadIdx.x == 0) atomicOr(args.redo_any, 1u);
+        return;
+    }
     if (threadIdx.x == 0) {
         *cnt = 0u;
         *tau = 0ull;
@@ -844,7 +848,10 @@ __global__ void __launch_bounds__(256) mma_refine_kernel(const MmaRefineArgs arg
         if (l.cand_count[mma_list_slot(l, b, j)] > l.cap) s_overflow = 1;
     __syncthreads();
     if (s_overflow) {  // the superset is incomplete: exact path
-        if (threadIdx.x == 0) args.redo[b] = 2u;
+        if (threadIdx.x == 0) {
+            args.redo[b] = 2u;
+            atomicOr(args.redo_any, 1u);
+        }
         return;
     }
     const CandBuf buf{cand, cnt, tau};
