@@ -38,6 +38,7 @@ class ShardedGpuIndex:
         self._fast = local_search is None and merge is None  # both stages are the CUDA kernels
         self._local_search = local_search or self._cuda_local_search
         self._merge = merge or self._cuda_merge
+        self._packed_shape = None  # (batch, k, device) of the cached all-gather buffers
 
     # CUDA stages -----------------------------------------------------------------------------
     def _cuda_local_search(self, d_queries, k: int):
@@ -63,25 +64,36 @@ class ShardedGpuIndex:
 
     def _cuda_search_packed(self, d_queries, k: int):
         """CUDA path with ONE packed buffer per rank: [keys | hits] as int64 [2, B, k] -> one
-        all-gather -> the merge kernel reads keys and the hits' raw scores in place (no copies)."""
+        all-gather -> the merge kernel reads keys and the hits' raw scores in place (no copies).
+        The local search writes straight into the packed buffer; the packed and gathered buffers are
+        kept between calls (they are internal, and reuse is ordered by the stream)."""
         import torch
 
-        keys, hits, counts = self._ix.search_top_k_device(d_queries, k, want_hits=True)
         if self._world == 1:
-            return keys, hits, counts
-        b = keys.shape[0]
-        dev = keys.device
-        packed = torch.stack([keys, hits.view(torch.int64).view(b, k)])
-        g = self._world
-        flat = torch.empty((g, 2, b, k), dtype=torch.int64, device=dev)
+            return self._ix.search_top_k_device(d_queries, k, want_hits=True)
+        if d_queries.dtype != torch.float32 or not d_queries.is_cuda or not d_queries.is_contiguous():
+            raise SearchError("InvalidConfig", "d_queries must be a contiguous CUDA float32 tensor")
+        if d_queries.dim() != 2 or d_queries.shape[1] != self._ix.dimension():
+            raise SearchError("DimensionMismatch", f"expected {self._ix.dimension()}, found {d_queries.shape[-1]}")
+        b, g, dev = d_queries.shape[0], self._world, d_queries.device
+        shape = (b, k, dev)
+        if self._packed_shape != shape:
+            self._packed = torch.empty((2, b, k), dtype=torch.int64, device=dev)
+            self._gathered = torch.empty((g, 2, b, k), dtype=torch.int64, device=dev)
+            self._local_counts = torch.empty(b, dtype=torch.int32, device=dev)
+            self._packed_shape = shape
+        packed, flat = self._packed, self._gathered
+        s = torch.cuda.current_stream(dev).cuda_stream
+        L = _ffi.lib()
+        check(L.fsgpu_search_top_k_device(self._ix.handle, d_queries.data_ptr(), b, k, packed[0].data_ptr(),
+                                          packed[1].data_ptr(), self._local_counts.data_ptr(), s))
         self._dist.all_gather_into_tensor(flat, packed, group=self._group)
         out_keys = torch.empty((b, k), dtype=torch.int64, device=dev)
         out_hits = torch.empty((b, k, 2), dtype=torch.int32, device=dev)
         out_counts = torch.empty(b, dtype=torch.int32, device=dev)
-        s = torch.cuda.current_stream(dev).cuda_stream
-        check(_ffi.lib().fsgpu_merge_top_k_hits_device(dev.index or 0, flat.data_ptr(), flat.data_ptr() + b * k * 8, b, g,
-                                                       k, 2 * b * k, k, k, out_keys.data_ptr(), out_hits.data_ptr(),
-                                                       out_counts.data_ptr(), s))
+        check(L.fsgpu_merge_top_k_hits_device(dev.index or 0, flat.data_ptr(), flat.data_ptr() + b * k * 8, b, g,
+                                              k, 2 * b * k, k, k, out_keys.data_ptr(), out_hits.data_ptr(),
+                                              out_counts.data_ptr(), s))
         return out_keys, out_hits, out_counts
 
     # the sharded search ------------------------------------------------------------------------

@@ -1,0 +1,62 @@
+"""Multi-GPU parity of the row-sharded search, run under torchrun with NCCL:
+every rank owns a contiguous row shard; the merged result on EVERY rank must be bit-identical to
+one index over all rows (built on each rank's own GPU for the comparison).
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \\
+      --master-port 29617 tools/check_sharded_nccl.py [rows] [dim]
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import frankensearch_b200 as fs  # noqa: E402
+from frankensearch_b200.sharded import ShardedGpuIndex, shard_bounds  # noqa: E402
+
+
+def synth(dev_index, lo, n, dim):
+    slab = torch.empty((n, dim), dtype=torch.int16, device=torch.device("cuda", dev_index))
+    fs._ffi.check(fs._ffi.lib().fsgpu_synth_rows_device(dev_index, 1, 1, lo, n, dim, 64, 0.30, slab.data_ptr(), None))
+    return slab
+
+
+def main():
+    rows = int(sys.argv[1]) if len(sys.argv) > 1 else 400_000
+    dim = int(sys.argv[2]) if len(sys.argv) > 2 else 128
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    lo, hi = shard_bounds(rows, world, rank)
+    shard = fs.GpuVectorIndex.from_device_tensor(synth(local, lo, hi - lo, dim), row_base=lo)
+    whole = fs.GpuVectorIndex.from_device_tensor(synth(local, 0, rows, dim))
+    sharded = ShardedGpuIndex(shard)
+    g = torch.Generator(device="cpu").manual_seed(7)  # same queries on every rank
+    q_all = torch.randn((300, dim), generator=g)
+    q_all = (q_all / q_all.norm(dim=1, keepdim=True)).to(dev).contiguous()
+    bad = 0
+    for k in (1, 10, 100):
+        for batch in (1, 2, 5, 64, 300):
+            q = q_all[:batch].contiguous()
+            for rep in range(2):  # the second call reuses the cached all-gather buffers
+                keys, hits, counts = sharded.search_top_k_device(q, k)
+                wkeys, whits, wcounts = whole.search_top_k_device(q, k)
+                torch.cuda.synchronize()
+                ok = torch.equal(keys, wkeys) and torch.equal(hits, whits) and torch.equal(counts, wcounts)
+                if not ok:
+                    bad += 1
+                    print(f"rank {rank}: MISMATCH k={k} batch={batch} rep={rep}", flush=True)
+    t = torch.tensor([bad], device=dev)
+    dist.all_reduce(t)
+    if rank == 0:
+        print("SHARDED_NCCL_PARITY", "OK" if t.item() == 0 else f"FAILED ({t.item()} mismatches)", f"world={world}")
+    dist.destroy_process_group()
+    sys.exit(0 if t.item() == 0 else 1)
+
+
+if __name__ == "__main__":
+    main()
