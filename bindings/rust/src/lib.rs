@@ -73,6 +73,9 @@ extern "C" {
     pub fn fsgpu_index_rows(index: *const fsgpu_index) -> u64;
     pub fn fsgpu_index_dim(index: *const fsgpu_index) -> u32;
     pub fn fsgpu_index_set_tombstones(index: *mut fsgpu_index, bitmap_or_null: *const u8) -> c_int;
+    pub fn fsgpu_index_int8_ready(index: *const fsgpu_index) -> c_int;
+    pub fn fsgpu_index_read_codes_i8(index: *const fsgpu_index, row_start: u64, n: u64, out_codes: *mut i8,
+                                     out_scale: *mut f32) -> c_int;
     pub fn fsgpu_index_read_tombstones(index: *const fsgpu_index, out_bitmap: *mut u8) -> c_int;
     pub fn fsgpu_index_set_doc_hashes(index: *mut fsgpu_index, hashes_or_null: *const u64) -> c_int;
     pub fn fsgpu_search_top_k_hashes(index: *const fsgpu_index, queries: *const f32, batch: u32, k: u32, dim: u32,

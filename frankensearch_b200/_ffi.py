@@ -101,7 +101,8 @@ EXPORTS = [
     "fsgpu_index_create_f16", "fsgpu_index_create_f32", "fsgpu_index_open_fsvi", "fsgpu_index_destroy",
     "fsgpu_index_rows", "fsgpu_index_dim", "fsgpu_index_row_base", "fsgpu_index_device",
     "fsgpu_index_device_slab", "fsgpu_index_set_doc_ids", "fsgpu_index_doc_id",
-    "fsgpu_index_set_tombstones", "fsgpu_index_read_tombstones",
+    "fsgpu_index_set_tombstones", "fsgpu_index_read_tombstones", "fsgpu_index_int8_ready",
+    "fsgpu_index_read_codes_i8",
     "fsgpu_index_set_wal", "fsgpu_index_wal_rows", "fsgpu_index_read_rows_f16", "fsgpu_index_profile_enable",
     "fsgpu_index_profile_read", "fsgpu_search_top_k", "fsgpu_search_top_k_device",
     "fsgpu_search_top_k_filtered", "fsgpu_search_top_k_filtered_device",
@@ -152,6 +153,8 @@ def lib() -> C.CDLL:
     L.fsgpu_index_doc_id.argtypes = [_vp, C.c_uint64, C.POINTER(_vp), C.POINTER(C.c_uint32)]
     L.fsgpu_index_set_tombstones.argtypes = [_vp, _vp]
     L.fsgpu_index_read_tombstones.argtypes = [_vp, _vp]
+    L.fsgpu_index_int8_ready.argtypes = [_vp]
+    L.fsgpu_index_read_codes_i8.argtypes = [_vp, C.c_uint64, C.c_uint64, _vp, C.POINTER(C.c_float)]
     L.fsgpu_index_set_doc_hashes.argtypes = [_vp, _vp]
     L.fsgpu_search_top_k_hashes.argtypes = [_vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, _vp, C.c_uint32, _vp,
                                             _vp, _vp, C.POINTER(C.c_int)]

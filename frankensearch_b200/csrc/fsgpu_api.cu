@@ -104,6 +104,17 @@ struct fsgpu_index {
     mutable const void* tm_qhat_ptr = nullptr;
     mutable uint32_t tm_qhat_rows = 0;
     mutable DevBuf ws_qhat, ws_margin, ws_gate, ws_redo, ws_cand, ws_cand_count, ws_progress;
+    // int8 form of the batched path (FSGPU_MMA_I8=1 at index creation): corpus codes with the
+    // reference's corpus-wide scale (simd.rs:1842-1859), their TMA descriptor, the measured bound on
+    // the per-row quantisation error
+    DevBuf d_slab_i8;
+    bool i8_ok = false;
+    float i8_sx = 0.0f, i8_max_ex = 0.0f;
+    CUtensorMap tm_slab_i8;
+    mutable CUtensorMap tm_qhat_i8;
+    mutable const void* tm_qhat_i8_ptr = nullptr;
+    mutable uint32_t tm_qhat_i8_rows = 0;
+    mutable DevBuf ws_qscale;
     // launch accounting (guarded by mu)
     mutable bool profiling = false;
     mutable fsgpu_profile prof{};
@@ -353,6 +364,19 @@ bool make_f16_tile_map(CUtensorMap* tm, const void* base, uint64_t rows, uint32_
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// The same boxes over a row-major [rows, dim] matrix of 8-bit codes: 128 codes per 128-byte row.
+static bool make_u8_tile_map(CUtensorMap* tm, const void* base, uint64_t rows, uint32_t dim) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc || rows == 0) return false;
+    const cuuint64_t gdim[2] = {dim, rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)dim};
+    const cuuint32_t box[2] = {128, 128};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // Slab statistics + TMA descriptor; decides whether the batched tensor-core path may serve this
 // index (otherwise every batch runs on the exact CUDA-core kernels).
 static int index_finish_setup(fsgpu_index* ix) {
@@ -361,21 +385,55 @@ static int index_finish_setup(fsgpu_index* ix) {
         ix->n_rows > 0x7FFFFF00ull || (reinterpret_cast<uintptr_t>(ix->d_slab) & 15u) != 0)
         return FSGPU_OK;
     uint32_t* d_stats = nullptr;
-    CUDA_TRY(cudaMalloc(&d_stats, 8));
-    CUDA_TRY(cudaMemsetAsync(d_stats, 0, 8, ix->stream));
+    CUDA_TRY(cudaMalloc(&d_stats, 16));
+    CUDA_TRY(cudaMemsetAsync(d_stats, 0, 16, ix->stream));
     const int grid = (int)std::min<uint64_t>((ix->n_rows + 7) / 8, (uint64_t)ix->num_sms * 16);
     slab_stats_kernel<<<grid, 256, 0, ix->stream>>>(ix->d_slab, ix->n_rows, ix->dim, d_stats);
-    uint32_t stats[2] = {0, 0};
+    uint32_t stats[4] = {0, 0, 0, 0};
     cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaMemcpyAsync(stats, d_stats, 8, cudaMemcpyDeviceToHost, ix->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(stats, d_stats, 16, cudaMemcpyDeviceToHost, ix->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ix->stream);
-    cudaFree(d_stats);
-    if (e != cudaSuccess) return fail(FSGPU_ERR_SUBSYSTEM, "gpu: slab statistics failed: %s", cudaGetErrorString(e));
+    if (e != cudaSuccess) {
+        cudaFree(d_stats);
+        return fail(FSGPU_ERR_SUBSYSTEM, "gpu: slab statistics failed: %s", cudaGetErrorString(e));
+    }
     float norm;
     memcpy(&norm, &stats[0], 4);
     ix->max_row_norm = norm * 1.0001f;
     const bool finite = stats[1] == 0 && std::isfinite(ix->max_row_norm);
     ix->mma_ok = finite && make_f16_tile_map(&ix->tm_slab, ix->d_slab, ix->n_rows, ix->dim);
+
+    // int8 codes for the kind::i8 form (opt-in: half as many bytes again in HBM)
+    ix->i8_ok = false;
+    if (ix->mma_ok && ix->dim % 128 == 0 && env_int("FSGPU_MMA_I8", 0) != 0) {
+        // largest |element|: f16 magnitude bits -> f32
+        const uint16_t hb = (uint16_t)stats[2];
+        const uint32_t exp = (hb >> 10) & 0x1F, man = hb & 0x3FF;
+        const float max_abs = exp == 0 ? std::ldexp((float)man, -24) : std::ldexp((float)(man | 0x400), (int)exp - 25);
+        if (max_abs > 0.0f) {
+            const float scale = 127.0f / max_abs;  // simd.rs:1850
+            ix->i8_sx = max_abs / 127.0f;
+            e = ix->d_slab_i8.reserve(ix->n_rows * ix->dim);
+            if (e == cudaSuccess) e = cudaMemsetAsync(d_stats, 0, 16, ix->stream);
+            if (e == cudaSuccess) {
+                quantize_slab_i8_kernel<<<grid, 256, 0, ix->stream>>>(ix->d_slab, ix->n_rows, ix->dim, scale, ix->i8_sx,
+                                                                      ix->d_slab_i8.as<int8_t>(), d_stats);
+                e = cudaGetLastError();
+            }
+            if (e == cudaSuccess) e = cudaMemcpyAsync(stats, d_stats, 4, cudaMemcpyDeviceToHost, ix->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ix->stream);
+            if (e != cudaSuccess) {
+                cudaFree(d_stats);
+                return fail(FSGPU_ERR_SUBSYSTEM, "gpu: int8 slab build failed: %s", cudaGetErrorString(e));
+            }
+            float ex;
+            memcpy(&ex, &stats[0], 4);
+            ix->i8_max_ex = ex * 1.0001f;
+            ix->i8_ok = std::isfinite(ix->i8_max_ex) &&
+                        make_u8_tile_map(&ix->tm_slab_i8, ix->d_slab_i8.p, ix->n_rows, ix->dim);
+        }
+    }
+    cudaFree(d_stats);
     return FSGPU_OK;
 }
 
@@ -460,7 +518,8 @@ static MmaCascade plan_cascade(uint64_t n_rows, uint32_t k, uint32_t tile_rows) 
 static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint32_t batch, uint32_t k,
                              uint64_t* d_out_keys, fsgpu_hit* d_out_hits, uint32_t* d_out_counts,
                              cudaStream_t stream) {
-    const uint32_t n_kb = ix->dim / kMmaKBlock;
+    const bool i8 = ix->i8_ok && env_int("FSGPU_MMA_I8", 0) != 0;
+    const uint32_t n_kb = ix->dim / (i8 ? 128 : kMmaKBlock);  // 128-byte K-blocks
     const size_t smem_limit = 227 * 1024;
     const size_t fixed = mma_scan_smem_bytes(n_kb, 0);
     uint32_t n_stages = (uint32_t)std::min<size_t>(kMmaMaxStages, (smem_limit - fixed) / kMmaTileBytes);
@@ -472,7 +531,8 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
     // ... and unless the batch is a single 128-query block: that regime is HBM-bound and the
     // single-CTA form streams it faster (6.7 vs 5.8 TB/s at 10 M x 384, profiles/r01_sweep_mma_v6.txt)
     const bool pair = env_int("FSGPU_MMA_PAIR", 1) != 0 && ix->num_sms >= 2 && batch > kMmaM;
-    auto scan_kernel = pair ? mma_scan_pair_kernel : mma_scan_kernel;
+    auto scan_kernel = pair ? (i8 ? mma_scan_pair_kernel<true> : mma_scan_pair_kernel<false>)
+                            : (i8 ? mma_scan_kernel<true> : mma_scan_kernel<false>);
     CUDA_TRY(cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t units = pair ? (uint32_t)ix->num_sms / 2 : (uint32_t)ix->num_sms;  // CTAs or CTA pairs
     const uint32_t unit_queries = pair ? 2 * kMmaM : kMmaM;
@@ -508,7 +568,15 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
         const uint32_t cap = cas.list_cap(g);
         CUDA_TRY(ix->ws_cand.reserve((size_t)grid * 2 * kMmaM * cap * sizeof(MmaCand)));
         CUDA_TRY(ix->ws_cand_count.reserve((size_t)grid * 2 * kMmaM * 4));
-        if (ix->tm_qhat_ptr != ix->ws_qhat.p || ix->tm_qhat_rows != slots) {
+        if (i8) {
+            CUDA_TRY(ix->ws_qscale.reserve((size_t)slots * 4));
+            if (ix->tm_qhat_i8_ptr != ix->ws_qhat.p || ix->tm_qhat_i8_rows != slots) {
+                if (!make_u8_tile_map(&ix->tm_qhat_i8, ix->ws_qhat.p, slots, ix->dim))
+                    return fail(FSGPU_ERR_SUBSYSTEM, "gpu: cuTensorMapEncodeTiled failed for the query tile");
+                ix->tm_qhat_i8_ptr = ix->ws_qhat.p;
+                ix->tm_qhat_i8_rows = slots;
+            }
+        } else if (ix->tm_qhat_ptr != ix->ws_qhat.p || ix->tm_qhat_rows != slots) {
             if (!make_f16_tile_map(&ix->tm_qhat, ix->ws_qhat.p, slots, ix->dim))
                 return fail(FSGPU_ERR_SUBSYSTEM, "gpu: cuTensorMapEncodeTiled failed for the query tile");
             ix->tm_qhat_ptr = ix->ws_qhat.p;
@@ -519,8 +587,14 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
         trace.on = env_int("FSGPU_MMA_TRACE", 0) != 0;
         trace.stream = stream;
         trace.mark("start");
-        mma_prep_queries_kernel<<<slots, 128, 0, stream>>>(q, sub, ix->dim, ix->max_row_norm, ix->ws_qhat.as<__half>(),
-                                                           ix->ws_margin.as<float>(), ix->ws_redo.as<uint32_t>());
+        if (i8)
+            mma_prep_queries_i8_kernel<<<slots, 128, 0, stream>>>(q, sub, ix->dim, ix->max_row_norm, ix->i8_max_ex,
+                                                                  ix->i8_sx, ix->ws_qhat.as<int8_t>(),
+                                                                  ix->ws_margin.as<float>(), ix->ws_qscale.as<float>(),
+                                                                  ix->ws_redo.as<uint32_t>());
+        else
+            mma_prep_queries_kernel<<<slots, 128, 0, stream>>>(q, sub, ix->dim, ix->max_row_norm, ix->ws_qhat.as<__half>(),
+                                                               ix->ws_margin.as<float>(), ix->ws_redo.as<uint32_t>());
         CUDA_TRY(cudaGetLastError());
         ix->prof.other_launches += 1;
 
@@ -534,6 +608,7 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
         a.batch = sub;
         a.n_stages = n_stages;
         a.redo = ix->ws_redo.as<uint32_t>();
+        a.qscale = i8 ? ix->ws_qscale.as<float>() : nullptr;
         a.cand = ix->ws_cand.as<MmaCand>();
         a.cand_count = ix->ws_cand_count.as<uint32_t>();
         a.cap = cap;
@@ -561,7 +636,7 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
             a.progress = paced ? ix->ws_progress.as<uint32_t>() : nullptr;
             if (paced) CUDA_TRY(cudaMemsetAsync(ix->ws_progress.p, 0, progress_bytes, stream));
             trace.mark(lvl ? "gate0" : "prep");
-            scan_kernel<<<grid, kMmaThreads, smem, stream>>>(ix->tm_qhat, ix->tm_slab, a);
+            scan_kernel<<<grid, kMmaThreads, smem, stream>>>(i8 ? ix->tm_qhat_i8 : ix->tm_qhat, i8 ? ix->tm_slab_i8 : ix->tm_slab, a);
             CUDA_TRY(cudaGetLastError());
             trace.mark(lvl ? "scan1" : "scan0");
             ga.stage_cap = have_gate ? gate1_cap : gate0_cap;
@@ -588,7 +663,7 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
             CUDA_TRY(cudaEventRecord(ev.first, stream));
         }
         trace.mark("gate_last");
-        scan_kernel<<<grid, kMmaThreads, smem, stream>>>(ix->tm_qhat, ix->tm_slab, a);
+        scan_kernel<<<grid, kMmaThreads, smem, stream>>>(i8 ? ix->tm_qhat_i8 : ix->tm_qhat, i8 ? ix->tm_slab_i8 : ix->tm_slab, a);
         CUDA_TRY(cudaGetLastError());
         trace.mark("scan_full");
         if (ix->profiling) {
@@ -822,7 +897,9 @@ extern "C" void fsgpu_index_destroy(fsgpu_index* ix) {
         for (DevBuf* b : {&ix->ws_partial, &ix->ws_queries, &ix->ws_keys, &ix->ws_hits, &ix->ws_counts,
                           &ix->ws_sort_a, &ix->ws_sort_b, &ix->ws_cub, &ix->ws_rows, &ix->ws_scores,
                           &ix->ws_present, &ix->ws_excl, &ix->ws_allow, &ix->ws_progress, &ix->ws_qhat, &ix->ws_margin, &ix->ws_gate, &ix->ws_redo, &ix->ws_cand,
-                          &ix->ws_cand_count})
+                          &ix->ws_cand_count, &ix->d_wal, &ix->ws_wal_main, &ix->ws_wal_keys, &ix->d_hashes,
+                          &ix->ws_allowed, &ix->ws_gather_pos, &ix->ws_gather_count, &ix->ws_gather_keys,
+                          &ix->d_slab_i8, &ix->ws_qscale})
             b->release();
         if (ix->stream) cudaStreamDestroy(ix->stream);
     }
@@ -954,6 +1031,24 @@ extern "C" int fsgpu_index_set_tombstones(fsgpu_index* ix, const uint8_t* bitmap
     DeviceGuard g(ix->device);
     CUDA_TRY(cudaStreamSynchronize(ix->stream));
     return upload_tombstones(ix, bitmap);
+}
+
+extern "C" int fsgpu_index_int8_ready(const fsgpu_index* ix) { return ix && ix->i8_ok ? 1 : 0; }
+
+extern "C" int fsgpu_index_read_codes_i8(const fsgpu_index* ix, uint64_t row_start, uint64_t n, int8_t* out_codes,
+                                         float* out_scale) {
+    if (!ix || !out_codes) return fail(FSGPU_ERR_INVALID_CONFIG, "NULL argument");
+    if (!ix->i8_ok) return fail(FSGPU_ERR_INVALID_CONFIG, "index holds no int8 codes (FSGPU_MMA_I8=1 at creation, dim %% 128 == 0)");
+    if (row_start > ix->n_rows || n > ix->n_rows - row_start)
+        return fail(FSGPU_ERR_INVALID_CONFIG, "row range [%llu, +%llu) outside the index",
+                    (unsigned long long)row_start, (unsigned long long)n);
+    std::lock_guard<std::mutex> lock(ix->mu);
+    DeviceGuard g(ix->device);
+    CUDA_TRY(cudaStreamSynchronize(ix->stream));
+    CUDA_TRY(cudaMemcpy(out_codes, ix->d_slab_i8.as<int8_t>() + row_start * ix->dim, (size_t)n * ix->dim,
+                        cudaMemcpyDeviceToHost));
+    if (out_scale) *out_scale = ix->i8_sx;
+    return FSGPU_OK;
 }
 
 extern "C" int fsgpu_index_read_tombstones(const fsgpu_index* ix, uint8_t* out_bitmap) {

@@ -62,6 +62,7 @@ struct MmaScanArgs {
     // sample pass ran at 140 GB/s, profiles/r01_mma_v3_L1_strided_ncu.json)
     uint64_t tile_stride, tile_count;
     const float* gate;         // [n_qblocks*128] static per-query gate (nullptr = -inf: keep everything)
+    const float* qscale;       // int8 form only: [n_qblocks*128] score = accumulator * qscale[query]
     const uint32_t* redo;      // [n_qblocks*128] != 0: query is served by the exact path, skip it
     // pacing (pair form, several query pairs per tile stream): progress[stream][query pair] = tiles
     // whose loads have been issued; a pair never runs more than `lead` tiles ahead of the slowest
@@ -136,11 +137,12 @@ mma_prep_queries_kernel(const float* __restrict__ queries, uint32_t batch, uint3
 
 // ─── index statistics for the bound: max row norm, all-finite flag ──────────────────────────
 // stats[0] = bits of max ||row||_2 (f32, rounded up generously by the caller), stats[1] = 1 if
-// any element is inf/NaN.
+// any element is inf/NaN, stats[2] = f16 magnitude bits of the largest |element|.
 __global__ void __launch_bounds__(256)
 slab_stats_kernel(const uint16_t* __restrict__ slab, uint64_t n_rows, uint32_t dim, uint32_t* __restrict__ stats) {
     const int lane = threadIdx.x & 31;
     float local_max = 0.0f;
+    uint32_t abs_bits = 0u;  // largest |element| as f16 magnitude bits (finite magnitudes order as integers)
     bool nonfinite = false;
     for (uint64_t row = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5); row < n_rows; row += (uint64_t)gridDim.x * 8) {
         const uint16_t* p = slab + row * dim;
@@ -148,6 +150,7 @@ slab_stats_kernel(const uint16_t* __restrict__ slab, uint64_t n_rows, uint32_t d
         for (uint32_t i = lane; i < dim; i += 32) {
             const uint16_t bits = p[i];
             if ((bits & 0x7C00u) == 0x7C00u) nonfinite = true;
+            abs_bits = max(abs_bits, (uint32_t)(bits & 0x7FFFu));
             const float x = h2f(bits);
             acc = __fmaf_ru(x, x, acc);
         }
@@ -155,8 +158,120 @@ slab_stats_kernel(const uint16_t* __restrict__ slab, uint64_t n_rows, uint32_t d
         local_max = fmaxf(local_max, acc);
     }
     if (__any_sync(0xffffffffu, nonfinite) && lane == 0) atomicOr(stats + 1, 1u);
+    abs_bits = __reduce_max_sync(0xffffffffu, abs_bits);
+    if (lane == 0 && abs_bits) atomicMax(stats + 2, abs_bits);
     if (lane == 0 && local_max > 0.0f && local_max == local_max)
         atomicMax(stats, __float_as_uint(__fsqrt_ru(local_max)));  // non-negative floats order as uints
+}
+
+// ─── int8 form: corpus codes, query codes, error bound ──────────────────────────────────────
+// The reference's corpus-wide int8 quantiser (quantize_f16_slab_to_i8,
+// crates/frankensearch-index/src/simd.rs:1842-1859): scale = 127 / max|x|, code =
+// clamp(round_half_away(x * scale), -127, 127).  Here the codes feed tcgen05.mma kind::i8 (half the
+// HBM / L2 / shared-memory bytes and twice the MMA rate of the f16 form) and the result stays EXACT:
+// with x_i = sx*X_i + ex_i (sx = max|x| / 127 as used below, X the codes actually stored) and
+// y_i = sy*Y_i + ey_i,
+//     x.y = sx*sy * sum X_i Y_i  +  sum (sx X_i) ey_i  +  sum ex_i y_i
+//     |x.y - sx*sy*acc| <= (||x|| + ||ex||) ||ey|| + ||ex|| ||y||          (Cauchy-Schwarz, twice)
+// so with Ex = max over rows of ||ex_row|| (measured from the stored codes by this kernel, rounded
+// up) every row's approximate score is within e_q of its reference score; the candidate superset,
+// the exact re-score and the redo rules are those of the f16 form.
+// One warp per row; stats[0] = bits of max ||ex_row||_2 (f32, rounded up).
+__global__ void __launch_bounds__(256)
+quantize_slab_i8_kernel(const uint16_t* __restrict__ slab, uint64_t n_rows, uint32_t dim, float scale, float sx,
+                        int8_t* __restrict__ out, uint32_t* __restrict__ stats) {
+    const int lane = threadIdx.x & 31;
+    float local_max = 0.0f;
+    for (uint64_t row = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5); row < n_rows; row += (uint64_t)gridDim.x * 8) {
+        const uint16_t* p = slab + row * dim;
+        int8_t* o = out + row * dim;
+        float acc = 0.0f;
+        for (uint32_t i = lane * 4u; i < dim; i += 128u) {  // dim % 128 == 0: four codes per lane per step
+            const uint2 raw = *reinterpret_cast<const uint2*>(p + i);
+            const uint16_t h[4] = {(uint16_t)(raw.x & 0xFFFFu), (uint16_t)(raw.x >> 16), (uint16_t)(raw.y & 0xFFFFu),
+                                   (uint16_t)(raw.y >> 16)};
+            uint32_t packed = 0u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float x = h2f(h[j]);
+                const float c = fminf(fmaxf(roundf(__fmul_rn(x, scale)), -127.0f), 127.0f);
+                const float err = __fmaf_rn(-sx, c, x);  // one rounding; its 2^-24 relative error is in the 1.01
+                acc = __fmaf_ru(err, err, acc);
+                packed |= ((uint32_t)(uint8_t)(int8_t)(int)c) << (8 * j);
+            }
+            *reinterpret_cast<uint32_t*>(o + i) = packed;
+        }
+        for (int s2 = 16; s2 > 0; s2 >>= 1) acc = __fadd_ru(acc, __shfl_xor_sync(0xffffffffu, acc, s2));
+        local_max = fmaxf(local_max, acc);
+    }
+    if (lane == 0 && local_max > 0.0f) atomicMax(stats, __float_as_uint(__fsqrt_ru(local_max)));
+}
+
+// One CTA per (padded) query slot: codes Y (int8), qscale = sx*sy, margin2 = 2 e_q rounded up, with
+//   e_q = [ (R + Ex) ey + Ex nq + (D/32+8) 2^-23 R nq + 2^-21 (R + Ex)(nq + ey) ] * 1.01
+// (R = max row norm, nq = ||y||, ey = ||y - sy Y||; third term: the reference's own f32 rounding,
+// as in the f16 form; fourth: the roundings of qscale and of acc * qscale, 8x headroom).
+__global__ void __launch_bounds__(128)
+mma_prep_queries_i8_kernel(const float* __restrict__ queries, uint32_t batch, uint32_t dim, float max_row_norm,
+                           float max_ex, float sx, int8_t* __restrict__ q_hat, float* __restrict__ margin2,
+                           float* __restrict__ qscale, uint32_t* __restrict__ redo) {
+    const uint32_t b = blockIdx.x;
+    __shared__ double s_e2[4], s_n2[4];
+    __shared__ float s_max[4];
+    __shared__ int s_bad;
+    if (threadIdx.x == 0) s_bad = 0;
+    __syncthreads();
+    float amax = 0.0f;
+    bool bad = false;
+    if (b < batch) {
+        for (uint32_t i = threadIdx.x; i < dim; i += blockDim.x) {
+            const float q = queries[(size_t)b * dim + i];
+            if (!(fabsf(q) <= 3.0e38f)) bad = true;  // NaN or inf
+            amax = fmaxf(amax, fabsf(q));
+        }
+    }
+    if (bad) atomicOr(&s_bad, 1);
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = amax;
+    __syncthreads();
+    const bool is_bad = s_bad != 0;
+    amax = fmaxf(fmaxf(s_max[0], s_max[1]), fmaxf(s_max[2], s_max[3]));
+    const bool zero = !(amax > 0.0f) || is_bad || b >= batch;
+    const float scale = zero ? 0.0f : 127.0f / amax;
+    const float sy = zero ? 0.0f : amax / 127.0f;
+    double e2 = 0.0, n2 = 0.0;
+    for (uint32_t i = threadIdx.x; i < dim; i += blockDim.x) {
+        float q = 0.0f, c = 0.0f;
+        if (!zero) {
+            q = queries[(size_t)b * dim + i];
+            c = fminf(fmaxf(roundf(__fmul_rn(q, scale)), -127.0f), 127.0f);
+        }
+        q_hat[(size_t)b * dim + i] = (int8_t)(int)c;
+        const double d = (double)q - (double)sy * (double)c;
+        e2 += d * d;
+        n2 += (double)q * (double)q;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        e2 += __shfl_xor_sync(0xffffffffu, e2, o);
+        n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        s_e2[threadIdx.x >> 5] = e2;
+        s_n2[threadIdx.x >> 5] = n2;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const double ey = sqrt(s_e2[0] + s_e2[1] + s_e2[2] + s_e2[3]);
+        const double nq = sqrt(s_n2[0] + s_n2[1] + s_n2[2] + s_n2[3]);
+        const double d = (double)dim, R = (double)max_row_norm, Ex = (double)max_ex;
+        const double e = ((R + Ex) * ey + Ex * nq + (d / 32.0 + 8.0) * (1.0 / 8388608.0) * R * nq +
+                          (1.0 / 2097152.0) * (R + Ex) * (nq + ey)) * 1.01;
+        float m2 = __double2float_ru(2.0 * e);
+        if (!(m2 >= 0.0f) || !(m2 <= 3.0e38f) || is_bad) m2 = 0.0f;
+        margin2[b] = m2;
+        qscale[b] = __fmul_rn(sx, sy);
+        redo[b] = (b < batch && (is_bad || !(m2 <= 3.0e38f))) ? 1u : 0u;
+    }
 }
 
 // ─── the scan ───────────────────────────────────────────────────────────────────────────────
@@ -175,19 +290,38 @@ __device__ __forceinline__ uint64_t mma_tile_of(const MmaScanArgs& args, uint64_
 // tombstones, tile inside the corpus) no branches — the branchy per-row form cost ~135 cycles of
 // warp time per appended row, which is what the sample levels and large-k passes are made of.
 // The count keeps growing past `cap` so the consumer sees overflow.
+// Value domain of the accumulators: f32 (kind::f16) or s32 (kind::i8; score = acc * qscale, the
+// gate is compared in the integer domain).
+template <bool I8>
+struct MmaDom {
+    using Gate = float;
+    static __device__ __forceinline__ float val(uint32_t w) { return __uint_as_float(w); }
+    static __device__ __forceinline__ float score(uint32_t w, float) { return __uint_as_float(w); }
+};
+template <>
+struct MmaDom<true> {
+    using Gate = int32_t;
+    static __device__ __forceinline__ int32_t val(uint32_t w) { return (int32_t)w; }
+    static __device__ __forceinline__ float score(uint32_t w, float qscale) {
+        return __fmul_rn((float)(int32_t)w, qscale);  // |acc| <= dim * 127^2 < 2^24: the conversion is exact
+    }
+};
+
+template <bool I8>
 __device__ __forceinline__ void mma_append8(const MmaScanArgs& args, MmaCand* list, uint32_t& count,
-                                            const uint32_t (&w)[8], float gate, uint64_t row0) {
+                                            const uint32_t (&w)[8], typename MmaDom<I8>::Gate gate, float qscale,
+                                            uint64_t row0) {
+    using D = MmaDom<I8>;
     const bool interior = row0 + 8u <= args.n_rows && args.tombstones == nullptr;
     const uint32_t grow0 = (uint32_t)(args.row_base + row0);
     uint32_t c = count;
     if (interior) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const float s = __uint_as_float(w[i]);
-            const bool p = s >= gate;
+            const bool p = D::val(w[i]) >= gate;
             if (p && c < args.cap) {
                 MmaCand e;
-                e.score = s;
+                e.score = D::score(w[i], qscale);
                 e.row = grow0 + (uint32_t)i;
                 list[c] = e;
             }
@@ -196,12 +330,11 @@ __device__ __forceinline__ void mma_append8(const MmaScanArgs& args, MmaCand* li
     } else {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const float s = __uint_as_float(w[i]);
             const uint64_t row = row0 + (uint32_t)i;
-            if (s >= gate && row < args.n_rows && !tombstoned(args.tombstones, row)) {
+            if (D::val(w[i]) >= gate && row < args.n_rows && !tombstoned(args.tombstones, row)) {
                 if (c < args.cap) {
                     MmaCand e;
-                    e.score = s;
+                    e.score = D::score(w[i], qscale);
                     e.row = grow0 + (uint32_t)i;
                     list[c] = e;
                 }
@@ -221,7 +354,14 @@ __device__ __forceinline__ uint32_t mma_hot_bit(const uint32_t (&v)[32], int bas
     const float m3 = fmaxf(fmaxf(__uint_as_float(v[base + 6]), __uint_as_float(v[base + 7])), m1);
     return fmaxf(m2, m3) >= gate ? bit : 0u;
 }
-__device__ __forceinline__ uint32_t mma_hot_bits(const uint32_t (&v)[32], float gate, uint32_t shift) {
+__device__ __forceinline__ uint32_t mma_hot_bit(const uint32_t (&v)[32], int base, int32_t gate, uint32_t bit) {
+    const int32_t m1 = max(max((int32_t)v[base + 0], (int32_t)v[base + 1]), (int32_t)v[base + 2]);
+    const int32_t m2 = max(max((int32_t)v[base + 3], (int32_t)v[base + 4]), (int32_t)v[base + 5]);
+    const int32_t m3 = max(max((int32_t)v[base + 6], (int32_t)v[base + 7]), m1);
+    return max(m2, m3) >= gate ? bit : 0u;
+}
+template <class G>
+__device__ __forceinline__ uint32_t mma_hot_bits(const uint32_t (&v)[32], G gate, uint32_t shift) {
     return mma_hot_bit(v, 0, gate, 1u << shift) | mma_hot_bit(v, 8, gate, 2u << shift) |
            mma_hot_bit(v, 16, gate, 4u << shift) | mma_hot_bit(v, 24, gate, 8u << shift);
 }
@@ -230,9 +370,10 @@ __device__ __forceinline__ uint32_t mma_hot_bits(const uint32_t (&v)[32], float 
 // columns -> one "some column clears the gate" bit each.  Slow path (rare): the warp re-reads each
 // hot group and the owning lanes append — one compact copy of the append code instead of COLS
 // unrolled ones (instruction cache).
-template <int COLS>
+template <int COLS, bool I8>
 __device__ __forceinline__ void mma_epilogue_tile(const MmaScanArgs& args, uint32_t taddr, uint64_t tile_row0,
-                                                  float gate, MmaCand* list, uint32_t& count) {
+                                                  typename MmaDom<I8>::Gate gate, float qscale, MmaCand* list,
+                                                  uint32_t& count) {
     static_assert(COLS % 64 == 0 && COLS <= 256, "hot mask is 32 bits of 8-column groups");
     uint32_t va[32], vb[32];
     uint32_t hot = 0;
@@ -250,7 +391,7 @@ __device__ __forceinline__ void mma_epilogue_tile(const MmaScanArgs& args, uint3
     if (hot_warp == 0u) return;
     // two groups in flight: the TMEM read of the next hot group overlaps the appends of this one
     auto check8 = [&](const uint32_t (&w)[8], uint32_t grp) {
-        if (hot & (1u << grp)) mma_append8(args, list, count, w, gate, tile_row0 + grp * 8u);
+        if (hot & (1u << grp)) mma_append8<I8>(args, list, count, w, gate, qscale, tile_row0 + grp * 8u);
     };
     uint32_t wa[8], wb[8];
     uint32_t ga = __ffs(hot_warp) - 1u, gb;
@@ -279,10 +420,34 @@ __device__ __forceinline__ void mma_epilogue_tile(const MmaScanArgs& args, uint3
     }
 }
 
+// This thread's gate in the accumulator domain.  f32: the gate itself.  s32: the largest integer
+// bound that keeps every accumulator whose score (acc * qscale, rounded) reaches the gate.
+template <bool I8>
+__device__ __forceinline__ typename MmaDom<I8>::Gate mma_thread_gate(const MmaScanArgs& args, uint32_t query, bool live,
+                                                                    float* qscale_out) {
+    if constexpr (!I8) {
+        *qscale_out = 1.0f;
+        return live ? (args.gate ? args.gate[query] : -INFINITY) : INFINITY;
+    } else {
+        const float qs = live ? args.qscale[query] : 0.0f;
+        *qscale_out = qs;
+        if (!live) return 0x7FFFFFFF;
+        if (!args.gate) return (int32_t)0x80000000;
+        const float gf = args.gate[query];
+        if (!(qs > 0.0f)) return gf <= 0.0f ? (int32_t)0x80000000 : 0x7FFFFFFF;  // every score is 0
+        const float t = __fdiv_rd(gf, qs);
+        if (!(t > -2.0e9f)) return (int32_t)0x80000000;
+        if (t >= 2.0e9f) return 0x7FFFFFFF;
+        return (int32_t)floorf(t) - 2;  // two units of slack cover the roundings of t and of acc * qscale
+    }
+}
+
+template <bool I8>
 __global__ void __launch_bounds__(kMmaThreads, 1)
 mma_scan_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_x,
                 const MmaScanArgs args) {
     extern __shared__ uint8_t smem_dyn[];
+    constexpr uint32_t kElems = I8 ? 128u : 64u;  // elements per 128-byte K-block row
     const uint32_t raw = smem_u32(smem_dyn);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* base_ptr = smem_dyn + (base - raw);
@@ -329,7 +494,7 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         if (elect_one()) {
             mbar_expect_tx(afull_bar, args.n_kblocks * kMmaTileBytes);
             for (uint32_t kb = 0; kb < args.n_kblocks; ++kb)
-                tma_load_2d(a_smem + kb * kMmaTileBytes, &tm_q, afull_bar, (int32_t)(kb * kMmaKBlock),
+                tma_load_2d(a_smem + kb * kMmaTileBytes, &tm_q, afull_bar, (int32_t)(kb * kElems),
                             (int32_t)(qb * kMmaM));
         }
         __syncwarp();
@@ -340,7 +505,7 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 mbar_wait(empty_bar(stage), phase ^ 1u);
                 if (elect_one()) {
                     mbar_expect_tx(full_bar(stage), kMmaTileBytes);
-                    tma_load_2d(b_smem + stage * kMmaTileBytes, &tm_x, full_bar(stage), (int32_t)(kb * kMmaKBlock),
+                    tma_load_2d(b_smem + stage * kMmaTileBytes, &tm_x, full_bar(stage), (int32_t)(kb * kElems),
                                 row_coord);
                 }
                 __syncwarp();
@@ -352,7 +517,7 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
     } else if (warp == 1) {
         // ===== MMA issuer (whole warp loops, one elected lane issues) =====
-        constexpr uint32_t idesc = umma_idesc_f16(kMmaM, kMmaN);
+        constexpr uint32_t idesc = I8 ? umma_idesc_i8(kMmaM, kMmaN) : umma_idesc_f16(kMmaM, kMmaN);
         const uint64_t a_desc0 = umma_desc_sw128(a_smem);
         const uint64_t b_desc0 = umma_desc_sw128(b_smem);
         mbar_wait(afull_bar, 0);
@@ -370,8 +535,12 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                     const uint64_t a_desc = a_desc0 + (uint64_t)(kb * (kMmaTileBytes >> 4));
                     const uint64_t b_desc = b_desc0 + (uint64_t)(stage * (kMmaTileBytes >> 4));
 #pragma unroll
-                    for (uint32_t k4 = 0; k4 < kMmaKBlock / 16; ++k4)
-                        umma_f16(d_tmem, a_desc + 2u * k4, b_desc + 2u * k4, idesc, (kb | k4) != 0u ? 1u : 0u);
+                    for (uint32_t k4 = 0; k4 < 4; ++k4) {  // four 32-byte K-steps per 128-byte K-block
+                        if constexpr (I8)
+                            umma_i8(d_tmem, a_desc + 2u * k4, b_desc + 2u * k4, idesc, (kb | k4) != 0u ? 1u : 0u);
+                        else
+                            umma_f16(d_tmem, a_desc + 2u * k4, b_desc + 2u * k4, idesc, (kb | k4) != 0u ? 1u : 0u);
+                    }
                     umma_commit(empty_bar(stage));  // frees the B stage when these MMAs retire
                     if (kb + 1 == args.n_kblocks) umma_commit(tfull_bar(acc));  // accumulator complete
                 }
@@ -392,7 +561,8 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const uint32_t m = quarter * 32u + lane;
         const uint32_t query = qb * kMmaM + m;
         const bool live = query < args.batch && args.redo[query] == 0u;
-        const float gate = live ? (args.gate ? args.gate[query] : -INFINITY) : INFINITY;
+        float qscale;
+        const typename MmaDom<I8>::Gate gate = mma_thread_gate<I8>(args, query, live, &qscale);
         const uint32_t half = (warp - 2u) >> 2;  // which half of the tile's columns this warp checks
         const size_t list_id = ((size_t)blockIdx.x * 2u + half) * kMmaM + m;
         MmaCand* list = args.cand + list_id * args.cap;
@@ -403,7 +573,7 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * kMmaN + half * (kMmaN / 2);
-            mma_epilogue_tile<kMmaN / 2>(args, taddr, tile * kMmaN + half * (kMmaN / 2), gate, list, count);
+            mma_epilogue_tile<kMmaN / 2, I8>(args, taddr, tile * kMmaN + half * (kMmaN / 2), gate, qscale, list, count);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));  // accumulator drained -> MMA may reuse it
@@ -436,10 +606,12 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 constexpr int kPairN = 256;
 constexpr int kPairAccStages = 2;  // 2 x 256 TMEM columns
 
+template <bool I8>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMmaThreads, 1)
 mma_scan_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_x,
                      const MmaScanArgs args) {
     extern __shared__ uint8_t smem_dyn[];
+    constexpr uint32_t kElems = I8 ? 128u : 64u;  // elements per 128-byte K-block row
     const uint32_t raw = smem_u32(smem_dyn);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* base_ptr = smem_dyn + (base - raw);
@@ -488,7 +660,7 @@ mma_scan_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         if (elect_one()) {
             if (rank == 0) mbar_expect_tx(afull_bar, 2u * args.n_kblocks * kMmaTileBytes);
             for (uint32_t kb = 0; kb < args.n_kblocks; ++kb)
-                tma_load_2d_pair(a_smem + kb * kMmaTileBytes, &tm_q, afull_bar, (int32_t)(kb * kMmaKBlock),
+                tma_load_2d_pair(a_smem + kb * kMmaTileBytes, &tm_q, afull_bar, (int32_t)(kb * kElems),
                                  (int32_t)(qb * kMmaM));
         }
         __syncwarp();
@@ -514,7 +686,7 @@ mma_scan_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                 if (elect_one()) {
                     if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * kMmaTileBytes);
                     tma_load_2d_pair(b_smem + stage * kMmaTileBytes, &tm_x, full_bar(stage),
-                                     (int32_t)(kb * kMmaKBlock), row_coord);
+                                     (int32_t)(kb * kElems), row_coord);
                 }
                 __syncwarp();
                 if (++stage == args.n_stages) {
@@ -528,7 +700,7 @@ mma_scan_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     } else if (warp == 1) {
         if (rank == 0) {
             // ===== MMA issuer (leader CTA only) =====
-            constexpr uint32_t idesc = umma_idesc_f16(2 * kMmaM, kPairN);
+            constexpr uint32_t idesc = I8 ? umma_idesc_i8(2 * kMmaM, kPairN) : umma_idesc_f16(2 * kMmaM, kPairN);
             const uint64_t a_desc0 = umma_desc_sw128(a_smem);
             const uint64_t b_desc0 = umma_desc_sw128(b_smem);
             mbar_wait(afull_bar, 0);
@@ -545,8 +717,12 @@ mma_scan_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                         const uint64_t a_desc = a_desc0 + (uint64_t)(kb * (kMmaTileBytes >> 4));
                         const uint64_t b_desc = b_desc0 + (uint64_t)(stage * (kMmaTileBytes >> 4));
 #pragma unroll
-                        for (uint32_t k4 = 0; k4 < kMmaKBlock / 16; ++k4)
-                            umma_f16_pair(d_tmem, a_desc + 2u * k4, b_desc + 2u * k4, idesc, (kb | k4) != 0u ? 1u : 0u);
+                        for (uint32_t k4 = 0; k4 < 4; ++k4) {
+                            if constexpr (I8)
+                                umma_i8_pair(d_tmem, a_desc + 2u * k4, b_desc + 2u * k4, idesc, (kb | k4) != 0u ? 1u : 0u);
+                            else
+                                umma_f16_pair(d_tmem, a_desc + 2u * k4, b_desc + 2u * k4, idesc, (kb | k4) != 0u ? 1u : 0u);
+                        }
                         umma_commit_pair(empty_bar(stage));  // frees this stage in BOTH CTAs
                         if (kb + 1 == args.n_kblocks) umma_commit_pair(tfull_bar(acc));
                     }
@@ -568,7 +744,8 @@ mma_scan_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         const uint32_t m = quarter * 32u + lane;
         const uint32_t query = qb * kMmaM + m;
         const bool live = query < args.batch && args.redo[query] == 0u;
-        const float gate = live ? (args.gate ? args.gate[query] : -INFINITY) : INFINITY;
+        float qscale;
+        const typename MmaDom<I8>::Gate gate = mma_thread_gate<I8>(args, query, live, &qscale);
         const uint32_t half = (warp - 2u) >> 2;
         const size_t list_id = ((size_t)blockIdx.x * 2u + half) * kMmaM + m;
         MmaCand* list = args.cand + list_id * args.cap;
@@ -579,7 +756,7 @@ mma_scan_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * kPairN + half * (kPairN / 2);
-            mma_epilogue_tile<kPairN / 2>(args, taddr, tile * kPairN + half * (kPairN / 2), gate, list, count);
+            mma_epilogue_tile<kPairN / 2, I8>(args, taddr, tile * kPairN + half * (kPairN / 2), gate, qscale, list, count);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(tempty_bar(acc), 0);  // leader may reuse the accumulator

@@ -96,6 +96,18 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
         "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// kind::i8: A and B are signed 8-bit, D is s32 in TMEM; K = 32 elements (32 bytes) per instruction,
+// so descriptors and K-steps are byte-for-byte those of kind::f16.
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                        uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // Arrives on `bar` when every tcgen05.mma issued so far by this thread has completed.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
@@ -150,6 +162,16 @@ __device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, u
         "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void umma_i8_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // Arrives on the barrier at this offset in BOTH CTAs when the pair's MMAs issued so far retire.
 __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
     asm volatile(
@@ -191,6 +213,12 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 // 17, M >> 4 at bit 24.
 __device__ __forceinline__ constexpr uint32_t umma_idesc_f16(uint32_t m, uint32_t n) {
     return (1u << 4) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+
+// kind::i8 instruction descriptor: D = s32 (2 at bits 4-5), A and B signed 8-bit (1 at bits 7-9 and
+// 10-12), both K-major, N >> 3 at bit 17, M >> 4 at bit 24.
+__device__ __forceinline__ constexpr uint32_t umma_idesc_i8(uint32_t m, uint32_t n) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
 }  // namespace fsgpu

@@ -119,6 +119,17 @@ int fsgpu_index_read_rows_f16(const fsgpu_index* index, uint64_t row_start, uint
                               uint16_t* out_bits);
 /* Replaces VectorIndex::soft_delete's effect on the scan (flag bit 0, search.rs:1281). */
 int fsgpu_index_set_tombstones(fsgpu_index* index, const uint8_t* bitmap_or_null);
+/* int8 form of the batched scan (opt-in: environment FSGPU_MMA_I8=1 when the index is created and
+ * when it is searched; dim % 128 == 0).  The index then also holds the corpus as int8 codes made by
+ * the reference's corpus-wide quantiser (quantize_f16_slab_to_i8, crates/frankensearch-index/src/
+ * simd.rs:1842-1859: scale = 127 / max|x|, code = clamp(round(x * scale), -127, 127)) and batches
+ * run on tcgen05.mma kind::i8 — half the bytes and twice the MMA rate.  Results are unchanged (exact):
+ * the int8 score only selects a candidate superset under a proven error bound, the winners are
+ * re-scored with the reference's f16 arithmetic.  `fsgpu_index_read_codes_i8` copies codes back
+ * (parity with the reference quantiser); `out_scale` receives max|x| / 127. */
+int fsgpu_index_int8_ready(const fsgpu_index* index);
+int fsgpu_index_read_codes_i8(const fsgpu_index* index, uint64_t row_start, uint64_t n, int8_t* out_codes,
+                              float* out_scale);
 /* VectorIndex::is_deleted (lib.rs:2401-2406) in bulk: the current soft-delete bitmap over local rows
  * ((n_rows + 7) / 8 bytes; for an FSVI file, flag bit 0 of each record as read at open). */
 int fsgpu_index_read_tombstones(const fsgpu_index* index, uint8_t* out_bitmap);

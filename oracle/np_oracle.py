@@ -179,3 +179,17 @@ def resolve_sorted_entries(rows, scores, main_doc_ids, wal_doc_ids, tombstones=N
             seen.add(doc)
         out.append((r, np.float32(sc), doc))
     return out
+
+
+def quantize_f16_slab_to_i8(slab_bits: np.ndarray):
+    """quantize_f16_slab_to_i8_generic (simd.rs:1842-1859): one corpus-wide scale 127 / max|x|,
+    code = clamp(round_half_away_from_zero(x * scale), -127, 127).  Returns (codes int8, max_abs f32)."""
+    x = decode_f16(slab_bits)
+    max_abs = F32(np.max(np.abs(x))) if x.size else F32(0.0)
+    if not max_abs > 0:
+        return np.zeros(x.shape, dtype=np.int8), F32(0.0)
+    scale = F32(F32(127.0) / max_abs)
+    y = (x * scale).astype(np.float32)            # one f32 rounding, as `x.to_f32() * scale`
+    # f32::round = half away from zero; the +0.5 is done in f64 so it cannot itself round up
+    r = np.sign(y) * np.floor(np.abs(y).astype(np.float64) + 0.5)
+    return np.clip(r, -127.0, 127.0).astype(np.int8), max_abs

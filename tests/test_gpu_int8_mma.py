@@ -1,0 +1,145 @@
+"""int8 form of the batched scan (tcgen05.mma kind::i8, FSGPU_MMA_I8=1): corpus codes equal the
+reference's quantiser byte for byte, and search results stay EXACT — identical rows and score bits
+to the per-query path and the oracle — because the int8 score only selects a candidate superset
+under a proven error bound (mma_scan_kernels.cuh) and winners are re-scored in f16."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(x):
+    return np.asarray(x, dtype=np.float32).view(np.uint32)
+
+
+@pytest.fixture()
+def i8_env(monkeypatch):
+    monkeypatch.setenv("FSGPU_MMA_I8", "1")
+    yield
+
+
+def _index(fs, slab, **kw):
+    ix = fs.GpuVectorIndex.from_f16_bits(None, slab, **kw)
+    assert ix._L.fsgpu_index_int8_ready(ix._h) == 1
+    return ix
+
+
+def test_codes_match_the_reference_quantiser(i8_env, fo):
+    """quantize_f16_slab_to_i8 (simd.rs:1842-1859), values as in avx2_quantize_i8_matches_generic
+    (simd.rs:2545-2565: xorshift * 3.0) plus exact .5 ties and the clamp edge."""
+    import frankensearch_b200 as fs
+    from oracle import np_oracle as no
+    from test_oracle_golden import _xorshift_stream
+
+    nxt = _xorshift_stream(0x51ED270B9C4DA3F8)
+    vals = np.array([nxt() * np.float32(3.0) for _ in range(40 * 128)], dtype=np.float32).reshape(40, 128)
+    vals[0, :8] = [3.0, -3.0, 1.5, -1.5, 0.0, 2.9999, 1e-4, -1e-4]
+    slab = fo.encode_f16(vals)
+    ix = _index(fs, slab)
+    codes = np.zeros((40, 128), dtype=np.int8)
+    scale = fs._ffi.C.c_float(0.0)
+    fs._ffi.check(ix._L.fsgpu_index_read_codes_i8(ix._h, 0, 40, fs._ffi.ptr(codes), fs._ffi.C.byref(scale)))
+    want, max_abs = no.quantize_f16_slab_to_i8(slab)
+    assert np.array_equal(codes, want)
+    assert np.float32(scale.value) == np.float32(max_abs / np.float32(127.0))
+    assert codes.max() == 127 and codes.min() == -127
+    ix.close()
+
+
+@pytest.mark.parametrize("n,dim", [(50000, 128), (30000, 256), (20011, 384), (300, 128)])
+def test_int8_batches_equal_exact_path(i8_env, fo, n, dim, monkeypatch):
+    import frankensearch_b200 as fs
+
+    slab, _ = fo.synth_rows(1, 3, 0, n, dim)
+    tomb = np.arange(n) % 11 == 0
+    ix = _index(fs, slab, tombstones=tomb)
+    queries = np.stack([fo.clustered_query(q, dim) for q in range(300)])
+    for k in (1, 10, 100):
+        for batch in (3, 64, 129, 300):
+            monkeypatch.setenv("FSGPU_MMA_MIN_BATCH", "3")
+            ix.profile_read(reset=True)
+            rows, scores, counts = ix.search_top_k_batch(queries[:batch], k)
+            p = ix.profile_read(reset=True)
+            assert p["mma_launches"] >= 1
+            monkeypatch.setenv("FSGPU_MMA_MIN_BATCH", "0")
+            erows, escores, ecounts = ix.search_top_k_batch(queries[:batch], k)
+            assert np.array_equal(counts, ecounts), (k, batch)
+            assert np.array_equal(rows, erows), (k, batch)
+            assert np.array_equal(bits(scores), bits(escores)), (k, batch)
+    monkeypatch.setenv("FSGPU_MMA_MIN_BATCH", "3")
+    rows, scores, counts = ix.search_top_k_batch(queries[:8], 20)
+    for b in range(8):  # and against the oracle
+        wr, ws = fo.search_top_k(slab, queries[b], 20, fo.pack_bitmap(tomb))
+        assert np.array_equal(rows[b, :int(counts[b])].astype(np.uint64), wr)
+        assert np.array_equal(bits(scores[b, :int(counts[b])]), bits(ws))
+    ix.close()
+
+
+def test_int8_adversarial_inputs_stay_exact(i8_env, fo, monkeypatch):
+    """Queries the int8 bound handles badly must still come out exact (wide margins -> bigger
+    candidate lists, or the redo path): unnormalised and huge queries, a zero query, a one-hot query,
+    a query dominated by one component, near-duplicate rows (dense tie band), an outlier element that
+    inflates the corpus scale, non-finite queries."""
+    import frankensearch_b200 as fs
+
+    n, dim = 40000, 128
+    rng = np.random.default_rng(3)
+    slab, _ = fo.synth_rows(1, 9, 0, n, dim)
+    vec = fo.decode_f16(slab)
+    vec[1000:1400] = vec[1000] + 1e-3 * rng.standard_normal((400, dim)).astype(np.float32)  # near duplicates
+    vec[5000:5064] = vec[5000]                                                              # exact duplicates
+    vec[77, 5] = 30.0                                                                       # outlier -> coarse scale
+    slab = fo.encode_f16(vec)
+    ix = _index(fs, slab)
+    qs = [fo.clustered_query(i, dim) for i in range(24)]
+    qs[1] = qs[1] * np.float32(1000.0)
+    qs[2] = qs[2] * np.float32(1e-6)
+    qs[3] = np.zeros(dim, dtype=np.float32)
+    qs[4] = np.eye(dim, dtype=np.float32)[7]
+    qs[5] = qs[5].copy(); qs[5][3] = 500.0
+    qs[6] = vec[1000].copy()
+    qs[7] = vec[5000].copy()
+    qs[8] = qs[8].copy(); qs[8][0] = np.float32("nan")
+    qs[9] = qs[9].copy(); qs[9][1] = np.float32("inf")
+    qs[10] = qs[10] * np.float32(3e37)
+    q = np.stack(qs).astype(np.float32)
+    for k in (10, 100):
+        monkeypatch.setenv("FSGPU_MMA_MIN_BATCH", "3")
+        rows, scores, counts = ix.search_top_k_batch(q, k)
+        monkeypatch.setenv("FSGPU_MMA_MIN_BATCH", "0")
+        erows, escores, ecounts = ix.search_top_k_batch(q, k)
+        assert np.array_equal(counts, ecounts)
+        assert np.array_equal(rows, erows)
+        assert np.array_equal(bits(scores), bits(escores))
+    ix.close()
+
+
+def test_int8_one_million_rows_batch_1024(i8_env, fo, monkeypatch):
+    import torch
+
+    import frankensearch_b200 as fs
+
+    n, dim = 1_000_000, 384
+    dev = torch.device("cuda", 0)
+    slab = torch.empty((n, dim), dtype=torch.int16, device=dev)
+    fs._ffi.check(fs._ffi.lib().fsgpu_synth_rows_device(0, 1, 1, 0, n, dim, 64, 0.30, slab.data_ptr(), None))
+    ix = fs.GpuVectorIndex.from_device_tensor(slab)
+    assert ix._L.fsgpu_index_int8_ready(ix._h) == 1
+    q = torch.from_numpy(np.stack([fo.clustered_query(i, dim) for i in range(1024)])).to(dev)
+    monkeypatch.setenv("FSGPU_MMA_MIN_BATCH", "3")
+    ix.profile_read(reset=True)
+    keys, hits, counts = ix.search_top_k_device(q, 10)
+    torch.cuda.synchronize()
+    p = ix.profile_read(reset=True)
+    monkeypatch.setenv("FSGPU_MMA_I8", "0")  # same index, f16 tensor-core form
+    fkeys, fhits, fcounts = ix.search_top_k_device(q, 10)
+    torch.cuda.synchronize()
+    assert torch.equal(keys, fkeys) and torch.equal(hits, fhits) and torch.equal(counts, fcounts)
+    monkeypatch.setenv("FSGPU_MMA_MIN_BATCH", "0")
+    ekeys, ehits, ecounts = ix.search_top_k_device(q[:16].contiguous(), 10)
+    torch.cuda.synchronize()
+    assert torch.equal(keys[:16], ekeys) and torch.equal(hits[:16], ehits)
+    assert p["redo_queries"] == 0, p
+    ix.close()
