@@ -517,8 +517,8 @@ static MmaCascade plan_cascade(uint64_t n_rows, uint32_t k, uint32_t tile_rows) 
 // which queries, if any, must be redone exactly).
 static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint32_t batch, uint32_t k,
                              uint64_t* d_out_keys, fsgpu_hit* d_out_hits, uint32_t* d_out_counts,
-                             cudaStream_t stream) {
-    const bool i8 = ix->i8_ok && env_int("FSGPU_MMA_I8", 0) != 0;
+                             cudaStream_t stream, bool allow_i8 = true) {
+    const bool i8 = allow_i8 && ix->i8_ok && env_int("FSGPU_MMA_I8", 0) != 0;
     const uint32_t n_kb = ix->dim / (i8 ? 128 : kMmaKBlock);  // 128-byte K-blocks
     const size_t smem_limit = 227 * 1024;
     const size_t fixed = mma_scan_smem_bytes(n_kb, 0);
@@ -710,6 +710,18 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
         CUDA_TRY(cudaMemcpyAsync(redo_host.data(), ix->ws_redo.p, (size_t)sub * 4, cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaStreamSynchronize(stream));
         CUDA_TRY(cudaMemsetAsync(ix->d_error + 1, 0, 4, stream));  // the next super-batch starts clean
+        if (i8) {
+            // the int8 bound is wide; when it overflows the candidate lists of more than a few
+            // queries the f16 form (100x tighter bound) serves this and the remaining super-batches
+            uint32_t overflowed = 0;
+            for (uint32_t b = 0; b < sub; ++b) overflowed += redo_host[b] == 2u ? 1u : 0u;
+            if (overflowed > 4) {
+                const size_t o = (size_t)done;
+                return search_mma_locked(ix, d_queries + o * ix->dim, batch - done, k,
+                                         d_out_keys ? d_out_keys + o * k : nullptr, d_out_hits ? d_out_hits + o * k : nullptr,
+                                         d_out_counts ? d_out_counts + o : nullptr, stream, false);
+            }
+        }
         for (uint32_t b = 0; b < sub; ++b) {
             if (!redo_host[b]) continue;
             ix->prof.redo_queries += 1;
