@@ -115,6 +115,9 @@ struct fsgpu_index {
     mutable const void* tm_qhat_i8_ptr = nullptr;
     mutable uint32_t tm_qhat_i8_rows = 0;
     mutable DevBuf ws_qscale;
+    // single-query int8 pass 1 (host API only: it needs the end-of-call synchronisation)
+    mutable bool use_i8_single = false;
+    mutable DevBuf ws_approx, ws_i8_top;
     // launch accounting (guarded by mu)
     mutable bool profiling = false;
     mutable fsgpu_profile prof{};
@@ -740,10 +743,117 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
 // FSGPU_MMA_MIN_BATCH (default 3) or more take the tensor-core pass (one pass of the slab for the
 // whole batch beats two CUDA-core passes from 3 queries on: profiles/r01_sweep_k.txt).  Both give
 // identical results.
+static int search_gather_locked(const fsgpu_index* ix, const float* d_queries, uint32_t batch, uint32_t k,
+                                uint64_t* d_out_keys, fsgpu_hit* d_out_hits, uint32_t* d_out_counts,
+                                cudaStream_t stream);
+
+// Positions the int8 pass may list per query before the call falls back to the f16 scan.
+constexpr uint32_t kI8ListCap = 1u << 13;
+
+// One or two queries, int8 pass 1 + exact re-score (scan_kernels.cuh "single-query int8 pass 1").
+// The caller (host API) has checked that the queries are finite and synchronises at the end:
+// word 1 of d_error reports a position list that overflowed.
+static int search_i8_single_locked(const fsgpu_index* ix, const float* d_queries, uint32_t batch, uint32_t k,
+                                   uint64_t* d_out_keys, fsgpu_hit* d_out_hits, uint32_t* d_out_counts,
+                                   cudaStream_t stream) {
+    const uint32_t cap = cand_capacity(k);
+    const size_t smem = (size_t)cap * 8 + 16;
+    CUDA_TRY(cudaFuncSetAttribute(scan_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_i8_kernel, kScanThreads, smem));
+    if (per_sm < 1) return fail(FSGPU_ERR_INVALID_CONFIG, "int8 scan kernel does not fit (k=%u)", k);
+    const uint64_t n_tiles = (ix->n_rows + kI8RowsPerIter - 1) / kI8RowsPerIter;
+    const uint32_t grid = (uint32_t)std::min<uint64_t>(n_tiles, (uint64_t)ix->num_sms * per_sm);
+    CUDA_TRY(ix->ws_qhat.reserve((size_t)ix->dim));
+    CUDA_TRY(ix->ws_margin.reserve(4));
+    CUDA_TRY(ix->ws_qscale.reserve(4));
+    CUDA_TRY(ix->ws_redo.reserve(4));
+    CUDA_TRY(ix->ws_gate.reserve(4));
+    CUDA_TRY(ix->ws_approx.reserve(ix->n_rows * 4));
+    CUDA_TRY(ix->ws_partial.reserve((size_t)grid * k * 8));
+    CUDA_TRY(ix->ws_i8_top.reserve((size_t)k * 8));
+    CUDA_TRY(ix->ws_gather_pos.reserve((size_t)kI8ListCap * 4));
+    CUDA_TRY(ix->ws_gather_count.reserve(4));
+    for (uint32_t b = 0; b < batch; ++b) {
+        const float* q = d_queries + (size_t)b * ix->dim;
+        mma_prep_queries_i8_kernel<<<1, 128, 0, stream>>>(q, 1, ix->dim, ix->max_row_norm, ix->i8_max_ex, ix->i8_sx,
+                                                          ix->ws_qhat.as<int8_t>(), ix->ws_margin.as<float>(),
+                                                          ix->ws_qscale.as<float>(), ix->ws_redo.as<uint32_t>());
+        CUDA_TRY(cudaGetLastError());
+        I8ScanArgs a{};
+        a.codes = ix->d_slab_i8.as<int8_t>();
+        a.tombstones = ix->d_excl ? ix->d_excl : ix->d_tomb;
+        a.q_codes = ix->ws_qhat.as<int8_t>();
+        a.qscale = ix->ws_qscale.as<float>();
+        a.n_rows = ix->n_rows;
+        a.row_base = ix->row_base;
+        a.dim = ix->dim;
+        a.k = k;
+        a.cap = cap;
+        a.sync_every = std::max<uint32_t>(1, std::min<uint32_t>(16, (cap - k) / (2 * kI8RowsPerIter)));
+        a.approx = ix->ws_approx.as<float>();
+        a.partial = ix->ws_partial.as<uint64_t>();
+        a.error_flag = ix->d_error;
+        std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+        if (ix->profiling) {
+            if (!ix->ev_free.empty()) {
+                ev = ix->ev_free.back();
+                ix->ev_free.pop_back();
+            } else {
+                CUDA_TRY(cudaEventCreate(&ev.first));
+                CUDA_TRY(cudaEventCreate(&ev.second));
+            }
+            CUDA_TRY(cudaEventRecord(ev.first, stream));
+        }
+        scan_i8_kernel<<<grid, kScanThreads, smem, stream>>>(a);
+        CUDA_TRY(cudaGetLastError());
+        if (ix->profiling) {
+            CUDA_TRY(cudaEventRecord(ev.second, stream));
+            ix->ev_pending.push_back(ev);
+        }
+        ix->prof.scan_launches += 1;
+        ix->prof.scan_bytes += ix->n_rows * ix->dim;  // int8 codes
+        MergeArgs m{};
+        m.keys = a.partial;
+        m.list_stride = k;
+        m.query_stride = 0;
+        m.n_lists = grid;
+        m.k_in = k;
+        m.k_out = k;
+        m.cap = cap;
+        m.out_keys = ix->ws_i8_top.as<uint64_t>();
+        m.error_flag = ix->d_error;
+        int rc = launch_merge(m, 1, stream);
+        if (rc) return rc;
+        i8_gate_kernel<<<1, kScanThreads, 0, stream>>>(ix->ws_i8_top.as<uint64_t>(), k, ix->d_slab, ix->row_base, ix->dim, q,
+                                                       ix->ws_margin.as<float>(), ix->reduce_order, ix->tail_fma,
+                                                       ix->ws_gate.as<float>(), ix->ws_gather_count.as<uint32_t>());
+        CUDA_TRY(cudaGetLastError());
+        i8_select_kernel<<<(unsigned)std::min<uint64_t>((ix->n_rows + 255) / 256, (uint64_t)ix->num_sms * 16), 256, 0, stream>>>(
+            ix->ws_approx.as<float>(), ix->n_rows, ix->ws_gate.as<float>(), ix->ws_gather_pos.as<uint32_t>(), kI8ListCap,
+            ix->ws_gather_count.as<uint32_t>(), ix->d_error + 1);
+        CUDA_TRY(cudaGetLastError());
+        ix->prof.merge_launches += 1;
+        ix->prof.other_launches += 3;
+        ix->d_gather_pos = ix->ws_gather_pos.as<uint32_t>();
+        ix->d_gather_count = ix->ws_gather_count.as<uint32_t>();
+        ix->gather_cap = kI8ListCap;
+        rc = search_gather_locked(ix, q, 1, k, d_out_keys ? d_out_keys + (size_t)b * k : nullptr,
+                                  d_out_hits ? d_out_hits + (size_t)b * k : nullptr, d_out_counts ? d_out_counts + b : nullptr,
+                                  stream);
+        ix->d_gather_pos = nullptr;
+        ix->d_gather_count = nullptr;
+        ix->gather_cap = 0;
+        if (rc) return rc;
+    }
+    return FSGPU_OK;
+}
+
 static int search_main_locked(const fsgpu_index* ix, const float* d_queries, uint32_t batch, uint32_t k,
                               uint64_t* d_out_keys, fsgpu_hit* d_out_hits, uint32_t* d_out_counts,
                               cudaStream_t stream) {
     if (batch == 0) return FSGPU_OK;
+    if (ix->use_i8_single) return search_i8_single_locked(ix, d_queries, batch, k, d_out_keys, d_out_hits, d_out_counts, stream);
     const int min_batch = env_int("FSGPU_MMA_MIN_BATCH", 3);
     const bool mma = ix->mma_ok && min_batch > 0 && batch >= (uint32_t)min_batch && k >= 1 && k <= kMmaMaxK &&
                      ix->n_rows > 0;
@@ -775,6 +885,7 @@ static int search_gather_locked(const fsgpu_index* ix, const float* d_queries, u
     m.query_stride = cap;
     m.n_lists = 1;
     m.k_in = cap;
+    m.k_in_used = ix->d_gather_count;  // skip the empty tail of the list
     m.k_out = k;
     m.cap = cand_capacity(k);
     m.out_keys = d_out_keys;
@@ -911,7 +1022,7 @@ extern "C" void fsgpu_index_destroy(fsgpu_index* ix) {
                           &ix->ws_present, &ix->ws_excl, &ix->ws_allow, &ix->ws_progress, &ix->ws_qhat, &ix->ws_margin, &ix->ws_gate, &ix->ws_redo, &ix->ws_cand,
                           &ix->ws_cand_count, &ix->d_wal, &ix->ws_wal_main, &ix->ws_wal_keys, &ix->d_hashes,
                           &ix->ws_allowed, &ix->ws_gather_pos, &ix->ws_gather_count, &ix->ws_gather_keys,
-                          &ix->d_slab_i8, &ix->ws_qscale})
+                          &ix->d_slab_i8, &ix->ws_qscale, &ix->ws_approx, &ix->ws_i8_top})
             b->release();
         if (ix->stream) cudaStreamDestroy(ix->stream);
     }
@@ -1139,30 +1250,13 @@ extern "C" int fsgpu_search_top_k_device(const fsgpu_index* ix, const float* d_q
     return FSGPU_OK;
 }
 
+extern "C" int fsgpu_search_top_k_filtered(const fsgpu_index* ix, const float* queries, uint32_t batch, uint32_t k,
+                                           uint32_t dim, const uint8_t* allow_bitmap, fsgpu_hit* out,
+                                           uint32_t* out_counts);
+
 extern "C" int fsgpu_search_top_k(const fsgpu_index* ix, const float* queries, uint32_t batch, uint32_t k,
                                   uint32_t dim, fsgpu_hit* out, uint32_t* out_counts) {
-    if (!ix) return fail(FSGPU_ERR_INVALID_CONFIG, "index is NULL");
-    if (dim != ix->dim)  // ensure_query_dimension (search.rs:1602-1610)
-        return fail(FSGPU_ERR_DIMENSION_MISMATCH, "expected %u, found %u", ix->dim, dim);
-    if (batch == 0) return FSGPU_OK;
-    if (!queries || !out_counts || (k && !out)) return fail(FSGPU_ERR_INVALID_CONFIG, "NULL argument");
-    if (k == 0 || (ix->n_rows == 0 && ix->n_wal == 0)) {
-        memset(out_counts, 0, (size_t)batch * 4);
-        return FSGPU_OK;
-    }
-    std::lock_guard<std::mutex> lock(ix->mu);
-    DeviceGuard g(ix->device);
-    cudaStream_t s = ix->stream;
-    CUDA_TRY(ix->ws_queries.reserve((size_t)batch * dim * 4));
-    CUDA_TRY(ix->ws_hits.reserve((size_t)batch * k * sizeof(fsgpu_hit)));
-    CUDA_TRY(ix->ws_counts.reserve((size_t)batch * 4));
-    CUDA_TRY(cudaMemcpyAsync(ix->ws_queries.p, queries, (size_t)batch * dim * 4, cudaMemcpyHostToDevice, s));
-    int rc = search_device_locked(ix, ix->ws_queries.as<float>(), batch, k, nullptr,
-                                  ix->ws_hits.as<fsgpu_hit>(), ix->ws_counts.as<uint32_t>(), s);
-    if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(out, ix->ws_hits.p, (size_t)batch * k * sizeof(fsgpu_hit), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(out_counts, ix->ws_counts.p, (size_t)batch * 4, cudaMemcpyDeviceToHost, s));
-    return check_error_flag(ix, s);
+    return fsgpu_search_top_k_filtered(ix, queries, batch, k, dim, nullptr, out, out_counts);
 }
 
 // ─── filtered search ────────────────────────────────────────────────────────────────────────
@@ -1234,12 +1328,29 @@ extern "C" int fsgpu_search_top_k_filtered(const fsgpu_index* ix, const float* q
         CUDA_TRY(cudaMemcpyAsync(ix->ws_allow.p, allow_bitmap, n_bytes, cudaMemcpyHostToDevice, s));
         d_allow = ix->ws_allow.as<uint8_t>();
     }
-    int rc = search_filtered_locked(ix, ix->ws_queries.as<float>(), batch, k, d_allow, nullptr,
-                                    ix->ws_hits.as<fsgpu_hit>(), ix->ws_counts.as<uint32_t>(), s);
-    if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(out, ix->ws_hits.p, (size_t)batch * k * sizeof(fsgpu_hit), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(out_counts, ix->ws_counts.p, (size_t)batch * 4, cudaMemcpyDeviceToHost, s));
-    return check_error_flag(ix, s);
+    // One or two finite queries on an index that holds int8 codes: int8 pass 1 + exact re-score
+    // (half the bytes of the f16 scan); a position list that overflows re-runs the call on the f16 scan.
+    const int min_batch = env_int("FSGPU_MMA_MIN_BATCH", 3);
+    bool i8_single = ix->i8_ok && env_int("FSGPU_MMA_I8", 0) != 0 && !(min_batch > 0 && batch >= (uint32_t)min_batch) &&
+                     k <= kFusedMaxK && ix->n_rows > 0;
+    for (size_t i = 0; i8_single && i < (size_t)batch * dim; ++i) i8_single = std::isfinite(queries[i]);
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        const bool i8_now = i8_single && attempt == 0;
+        if (i8_now) CUDA_TRY(cudaMemsetAsync(ix->d_error, 0, 8, s));
+        ix->use_i8_single = i8_now;
+        int rc = search_filtered_locked(ix, ix->ws_queries.as<float>(), batch, k, d_allow, nullptr,
+                                        ix->ws_hits.as<fsgpu_hit>(), ix->ws_counts.as<uint32_t>(), s);
+        ix->use_i8_single = false;
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(out, ix->ws_hits.p, (size_t)batch * k * sizeof(fsgpu_hit), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(out_counts, ix->ws_counts.p, (size_t)batch * 4, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(ix->h_flags, ix->d_error, 8, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        if (ix->h_flags[0]) return fail(FSGPU_ERR_SUBSYSTEM, "gpu: top-k candidate buffer contract violated");
+        if (!(i8_now && ix->h_flags[1])) break;
+        CUDA_TRY(cudaMemsetAsync(ix->d_error, 0, 8, s));
+    }
+    return FSGPU_OK;
 }
 
 // ─── doc-id-hash filters ────────────────────────────────────────────────────────────────────

@@ -341,6 +341,7 @@ struct MergeArgs {
     uint64_t query_stride;
     uint32_t n_lists;
     uint32_t k_in;
+    const uint32_t* k_in_used;  // optional (n_lists == 1): only the first min(*k_in_used, k_in) slots are filled
     uint32_t k_out;
     uint32_t cap;             // power of two, >= 2*k_out
     uint64_t* out_keys;       // [batch, k_out] (nullable)
@@ -367,7 +368,7 @@ __global__ void __launch_bounds__(kScanThreads) merge_topk_kernel(const MergeArg
     }
     __syncthreads();
     const CandBuf buf{cand, cnt, tau};
-    const uint64_t total = (uint64_t)args.n_lists * args.k_in;
+    const uint64_t total = args.k_in_used ? (uint64_t)min(*args.k_in_used, args.k_in) : (uint64_t)args.n_lists * args.k_in;
     const uint32_t step = blockDim.x;
     // between compaction checks at most `chunk` pushes can happen
     const uint32_t chunk = max(step, ((args.cap - args.k_out) / 2 / step) * step);
@@ -526,6 +527,168 @@ gather_keys_kernel(const uint16_t* __restrict__ slab, uint64_t row_base, uint32_
         key = make_key(s, (uint32_t)(row_base + row));
     }
     if (lane == 0) out[(size_t)b * cap + i] = key;
+}
+
+// ─── single-query int8 pass 1 ─────────────────────────────────────────────
+// The reference's int8 two-pass idea (search.rs:514-998: an int8 scan picks candidates, an exact
+// f16 re-score ranks them) made EXACT.  Pass 1 streams the int8 codes (half the bytes of the f16
+// slab: this is the HBM-bound regime), writes every row's approximate score and keeps the CTA's
+// best k of them.  The caller then (i8_gate_kernel) re-scores the approximate top-k exactly: their
+// k-th best exact score tau is a lower bound of the corpus' true k-th best, and every row of the
+// true top-k has approx >= tau - 2e (|approx - reference| <= e, mma_prep_queries_i8_kernel), so
+// i8_select_kernel lists exactly those rows and gather_keys_kernel + merge_topk_kernel rank them
+// with the reference arithmetic.  For one query the list is a few dozen rows.
+// Lane mapping: 8 adjacent lanes cover one row with 16-byte loads (4 rows per warp-level load,
+// 128 contiguous bytes each), dp4a against the query codes held in registers, 3 xor-shuffles.
+struct I8ScanArgs {
+    const int8_t* codes;        // [n_rows, dim]
+    const uint8_t* tombstones;  // packed bitmap or nullptr
+    const int8_t* q_codes;      // [dim]
+    const float* qscale;        // [1] score = acc * qscale
+    uint64_t n_rows, row_base;
+    uint32_t dim;               // multiple of 128, <= 512
+    uint32_t k, cap, sync_every;
+    float* approx;              // [n_rows] out; -inf for excluded rows
+    uint64_t* partial;          // [gridDim.x, k] approximate keys
+    uint32_t* error_flag;
+};
+
+constexpr int kI8RowsPerIter = kScanWarps * 4 * 2;  // 4 rows per warp-load, 2 loads in flight per lane
+
+__global__ void __launch_bounds__(kScanThreads) scan_i8_kernel(const I8ScanArgs args) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* cand = reinterpret_cast<uint64_t*>(smem_raw);
+    uint64_t* tau = cand + args.cap;
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(tau + 1);
+    if (threadIdx.x == 0) {
+        *cnt = 0u;
+        *tau = 0ull;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane & 7, rr = lane >> 3;
+    const uint32_t nj = args.dim >> 7;  // 128-byte segments per row
+    int y[4][4];
+#pragma unroll
+    for (uint32_t j = 0; j < 4; ++j) {
+        if (j < nj) {
+            const int4 v = *reinterpret_cast<const int4*>(args.q_codes + j * 128u + sub * 16u);
+            y[j][0] = v.x; y[j][1] = v.y; y[j][2] = v.z; y[j][3] = v.w;
+        } else {
+            y[j][0] = y[j][1] = y[j][2] = y[j][3] = 0;
+        }
+    }
+    const float qscale = *args.qscale;
+    __syncthreads();
+    const CandBuf buf{cand, cnt, tau};
+    const uint64_t n = args.n_rows;
+    const uint64_t n_tiles = (n + kI8RowsPerIter - 1) / kI8RowsPerIter;
+    const uint32_t trigger = args.cap - args.sync_every * kI8RowsPerIter;
+    float thr = -INFINITY;
+    uint32_t it = 0;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const uint64_t row0 = tile * kI8RowsPerIter + (uint64_t)warp * 8u + rr;  // this lane's rows: row0, row0 + 4
+        uint4 x[2][4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint64_t row = row0 + 4u * h;
+            const uint64_t rowc = row < n ? row : n - 1;
+            const uint4* p = reinterpret_cast<const uint4*>(args.codes + rowc * args.dim + sub * 16u);
+#pragma unroll
+            for (uint32_t j = 0; j < 4; ++j)
+                if (j < nj) x[h][j] = ld_stream_16(p + j * 8u);  // + j * 128 bytes
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            int acc = 0;
+#pragma unroll
+            for (uint32_t j = 0; j < 4; ++j)
+                if (j < nj) {
+                    acc = __dp4a((int)x[h][j].x, y[j][0], acc);
+                    acc = __dp4a((int)x[h][j].y, y[j][1], acc);
+                    acc = __dp4a((int)x[h][j].z, y[j][2], acc);
+                    acc = __dp4a((int)x[h][j].w, y[j][3], acc);
+                }
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+            const uint64_t row = row0 + 4u * h;
+            if (sub == 0 && row < n) {
+                const bool dead = tombstoned(args.tombstones, row);
+                const float s = __fmul_rn((float)acc, qscale);
+                args.approx[row] = dead ? -INFINITY : s;
+                if (!dead && !(s < thr)) {
+                    const uint64_t key = make_key(s, (uint32_t)(args.row_base + row));
+                    if (key > *tau && !cand_push(buf, args.cap, key)) atomicExch(args.error_flag, 1u);
+                }
+            }
+        }
+        if ((it + 1) % args.sync_every == 0) {
+            __syncthreads();
+            if (*cnt > trigger) cand_compact(buf, args.cap, args.k);
+            __syncthreads();
+            const uint64_t t = *tau;
+            thr = t ? key_score(t) : -INFINITY;
+        }
+    }
+    __syncthreads();
+    cand_compact(buf, args.cap, args.k);
+    __syncthreads();
+    const uint32_t c = min(*cnt, args.k);
+    uint64_t* out = args.partial + (size_t)blockIdx.x * args.k;
+    for (uint32_t i = threadIdx.x; i < args.k; i += blockDim.x) out[i] = i < c ? cand[i] : 0ull;
+}
+
+// One CTA: exact scores of the approximate top-k (`keys`, 0 = empty) -> gate = (k-th best exact) -
+// margin2 (= 2e, rounded down), or -inf when fewer than k rows exist.  Resets the position count.
+__global__ void __launch_bounds__(kScanThreads)
+i8_gate_kernel(const uint64_t* __restrict__ keys, uint32_t k, const uint16_t* __restrict__ slab, uint64_t row_base,
+               uint32_t dim, const float* __restrict__ query, const float* __restrict__ margin2, int reduce_order,
+               int tail_fma, float* __restrict__ gate_out, uint32_t* __restrict__ n_positions) {
+    __shared__ float s_min[kScanWarps];
+    __shared__ uint32_t s_cnt[kScanWarps];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float mn = INFINITY;
+    uint32_t cnt = 0;
+    for (uint32_t i = warp; i < k; i += kScanWarps) {
+        const uint64_t key = keys[i];
+        if (key == 0ull) continue;  // warp-uniform
+        const uint64_t local = (uint64_t)key_row(key) - row_base;
+        const float s = warp_exact_dot(slab + local * dim, query, dim, reduce_order, tail_fma);
+        mn = fminf(mn, s);
+        ++cnt;
+    }
+    if (lane == 0) {
+        s_min[warp] = mn;
+        s_cnt[warp] = cnt;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t total = 0;
+        for (int w = 0; w < kScanWarps; ++w) {
+            mn = fminf(mn, s_min[w]);
+            total += s_cnt[w];
+        }
+        *gate_out = total >= k ? __fsub_rd(mn, *margin2) : -INFINITY;
+        *n_positions = 0u;
+    }
+}
+
+// Rows whose approximate score clears the gate (excluded rows carry -inf and never do).
+__global__ void __launch_bounds__(256)
+i8_select_kernel(const float* __restrict__ approx, uint64_t n_rows, const float* __restrict__ gate,
+                 uint32_t* __restrict__ positions, uint32_t cap, uint32_t* __restrict__ n_positions,
+                 uint32_t* __restrict__ overflow) {
+    const float g = *gate;
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += (uint64_t)gridDim.x * blockDim.x) {
+        const float a = approx[r];
+        if (a >= g && a != -INFINITY) {
+            const uint32_t pos = atomicAdd(n_positions, 1u);
+            if (pos < cap)
+                positions[pos] = (uint32_t)r;
+            else
+                atomicExch(overflow, 1u);  // the caller re-runs the query on the f16 scan
+        }
+    }
 }
 
 // ─── gather-dot: quality_scores_for_hits (two_tier.rs:1566-1631, :1946-1973) ────────────────

@@ -143,3 +143,83 @@ def test_int8_one_million_rows_batch_1024(i8_env, fo, monkeypatch):
     assert torch.equal(keys[:16], ekeys) and torch.equal(hits[:16], ehits)
     assert p["redo_queries"] == 0, p
     ix.close()
+
+
+@pytest.mark.parametrize("n,dim", [(60000, 128), (25000, 384), (200, 256)])
+def test_int8_single_query_path_is_exact(i8_env, fo, n, dim, monkeypatch):
+    """One or two queries through the host API: int8 pass 1 (half the bytes), exact gate from the
+    re-scored approximate top-k, exact re-score of the listed rows.  Rows and score bits equal the
+    oracle, with tombstones, a filter, resident WAL rows, k up to 1000 and k > live rows."""
+    import frankensearch_b200 as fs
+
+    rng = np.random.default_rng(n)
+    slab, _ = fo.synth_rows(1, 13, 0, n, dim)
+    tomb = rng.random(n) < 0.1
+    ids = [f"doc-{i:06}" for i in range(n)]
+    ix = fs.GpuVectorIndex.from_f16_bits(ids, slab, tombstones=tomb)
+    assert ix._L.fsgpu_index_int8_ready(ix._h) == 1
+    allow = rng.random(n) < 0.5
+    for qi in range(6):
+        q = fo.clustered_query(qi, dim)
+        if qi == 4:
+            q = q * np.float32(250.0)
+        if qi == 5:
+            q = np.zeros(dim, dtype=np.float32)
+        for k in (1, 10, 100, 1000):
+            for mask in (None, allow):
+                ix.profile_read(reset=True)
+                rows, scores, counts = ix.search_top_k_batch(q, k, filter=mask)
+                p = ix.profile_read(reset=True)
+                if qi < 4 and k <= 100:  # the int8 codes were scanned, and nothing else
+                    assert p["scan_launches"] == 1 and p["scan_bytes"] == n * dim, p
+                else:  # a huge tie band (zero query) or k = 1000 may overflow the list: + one f16 scan
+                    assert p["scan_launches"] in (1, 2), p
+                excl = tomb if mask is None else (tomb | ~mask)
+                wr, ws = fo.search_top_k(slab, q, k, fo.pack_bitmap(excl))
+                c = int(counts[0])
+                assert c == len(wr), (qi, k)
+                assert np.array_equal(rows[0, :c].astype(np.uint64), wr), (qi, k)
+                assert np.array_equal(bits(scores[0, :c]), bits(ws)), (qi, k)
+    # two queries per call, and a non-finite query (served by the f16 scan)
+    q2 = np.stack([fo.clustered_query(7, dim), fo.clustered_query(8, dim)])
+    rows, scores, counts = ix.search_top_k_batch(q2, 10)
+    for b in range(2):
+        wr, ws = fo.search_top_k(slab, q2[b], 10, fo.pack_bitmap(tomb))
+        assert np.array_equal(rows[b, :int(counts[b])].astype(np.uint64), wr)
+    qn = fo.clustered_query(9, dim).copy()
+    qn[0] = np.float32("nan")
+    monkeypatch.setenv("FSGPU_MMA_I8", "0")
+    want = ix.search_top_k_batch(qn, 10)
+    monkeypatch.setenv("FSGPU_MMA_I8", "1")
+    got = ix.search_top_k_batch(qn, 10)
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[2], want[2])
+    # resident WAL rows ride along
+    from wal_model import OracleWalIndex
+
+    model = OracleWalIndex(ids, fo.decode_f16(slab), dim)
+    model.tomb = tomb.copy()
+    wal = [(f"new-{w}", fo.decode_f16(slab)[rng.integers(0, n)] * np.float32(1.01)) for w in range(5)]
+    ix.append_batch(wal)
+    model.append_batch(wal)
+    q = fo.clustered_query(3, dim)
+    rows, scores, counts = ix.search_top_k_batch(q, 10)
+    wr, ws = model.raw_search(q, 10)
+    assert np.array_equal(rows[0, :int(counts[0])].astype(np.uint64), wr) and np.array_equal(bits(scores[0, :int(counts[0])]), bits(ws))
+    ix.close()
+
+
+def test_int8_single_query_list_overflow_falls_back(i8_env, fo):
+    """A corpus of identical rows: every row clears the gate, the position list overflows, and the
+    call re-runs on the f16 scan — same hits."""
+    import frankensearch_b200 as fs
+
+    n, dim = 70000, 128
+    row = fo.clustered_query(1, dim)
+    slab = fo.encode_f16(np.repeat(row[None, :], n, axis=0))
+    ix = fs.GpuVectorIndex.from_f16_bits(None, slab)
+    assert ix._L.fsgpu_index_int8_ready(ix._h) == 1
+    rows, scores, counts = ix.search_top_k_batch(row, 10)
+    assert int(counts[0]) == 10 and list(rows[0]) == list(range(10))
+    wr, ws = fo.search_top_k(slab, row, 10)
+    assert np.array_equal(bits(scores[0]), bits(ws))
+    ix.close()
