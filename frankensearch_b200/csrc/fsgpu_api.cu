@@ -750,35 +750,42 @@ static int search_gather_locked(const fsgpu_index* ix, const float* d_queries, u
 // Positions the int8 pass may list per query before the call falls back to the f16 scan.
 constexpr uint32_t kI8ListCap = 1u << 13;
 
-// One or two queries, int8 pass 1 + exact re-score (scan_kernels.cuh "single-query int8 pass 1").
-// The caller (host API) has checked that the queries are finite and synchronises at the end:
-// word 1 of d_error reports a position list that overflowed.
+// A few queries, int8 pass 1 + exact re-score (scan_kernels.cuh "single-query int8 pass 1"); up to
+// four queries share one pass over the codes.  The caller (host API) has checked that the queries
+// are finite and synchronises at the end: word 1 of d_error reports a position list that overflowed.
 static int search_i8_single_locked(const fsgpu_index* ix, const float* d_queries, uint32_t batch, uint32_t k,
                                    uint64_t* d_out_keys, fsgpu_hit* d_out_hits, uint32_t* d_out_counts,
                                    cudaStream_t stream) {
     const uint32_t cap = cand_capacity(k);
-    const size_t smem = (size_t)cap * 8 + 16;
-    CUDA_TRY(cudaFuncSetAttribute(scan_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_i8_kernel, kScanThreads, smem));
-    if (per_sm < 1) return fail(FSGPU_ERR_INVALID_CONFIG, "int8 scan kernel does not fit (k=%u)", k);
     const uint64_t n_tiles = (ix->n_rows + kI8RowsPerIter - 1) / kI8RowsPerIter;
-    const uint32_t grid = (uint32_t)std::min<uint64_t>(n_tiles, (uint64_t)ix->num_sms * per_sm);
-    CUDA_TRY(ix->ws_qhat.reserve((size_t)ix->dim));
-    CUDA_TRY(ix->ws_margin.reserve(4));
-    CUDA_TRY(ix->ws_qscale.reserve(4));
-    CUDA_TRY(ix->ws_redo.reserve(4));
+    CUDA_TRY(ix->ws_qhat.reserve((size_t)4 * ix->dim));
+    CUDA_TRY(ix->ws_margin.reserve(16));
+    CUDA_TRY(ix->ws_qscale.reserve(16));
+    CUDA_TRY(ix->ws_redo.reserve(16));
     CUDA_TRY(ix->ws_gate.reserve(4));
-    CUDA_TRY(ix->ws_approx.reserve(ix->n_rows * 4));
-    CUDA_TRY(ix->ws_partial.reserve((size_t)grid * k * 8));
-    CUDA_TRY(ix->ws_i8_top.reserve((size_t)k * 8));
+    CUDA_TRY(ix->ws_i8_top.reserve((size_t)4 * k * 8));
     CUDA_TRY(ix->ws_gather_pos.reserve((size_t)kI8ListCap * 4));
     CUDA_TRY(ix->ws_gather_count.reserve(4));
-    for (uint32_t b = 0; b < batch; ++b) {
-        const float* q = d_queries + (size_t)b * ix->dim;
-        mma_prep_queries_i8_kernel<<<1, 128, 0, stream>>>(q, 1, ix->dim, ix->max_row_norm, ix->i8_max_ex, ix->i8_sx,
-                                                          ix->ws_qhat.as<int8_t>(), ix->ws_margin.as<float>(),
-                                                          ix->ws_qscale.as<float>(), ix->ws_redo.as<uint32_t>());
+    // more than one query per pass makes the dp4a pass ALU-bound (1.12 ms for 2, 1.38 ms for 4 queries at
+    // 10 M x 384, against 0.59 ms for one): off by default
+    const int qb_max = std::max(1, env_int("FSGPU_I8_QB", 1));
+    uint32_t done = 0;
+    while (done < batch) {
+        const uint32_t left = batch - done;
+        const uint32_t qb = (left >= 4 && qb_max >= 4) ? 4u : (left >= 2 && qb_max >= 2) ? 2u : 1u;
+        auto kernel = qb == 4 ? scan_i8_kernel<4> : qb == 2 ? scan_i8_kernel<2> : scan_i8_kernel<1>;
+        const size_t smem = (size_t)qb * cap * 8 + (size_t)qb * 12 + 16;
+        CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kScanThreads, smem));
+        if (per_sm < 1) return fail(FSGPU_ERR_INVALID_CONFIG, "int8 scan kernel does not fit (k=%u)", k);
+        const uint32_t grid = (uint32_t)std::min<uint64_t>(n_tiles, (uint64_t)ix->num_sms * per_sm);
+        CUDA_TRY(ix->ws_approx.reserve((size_t)qb * ix->n_rows * 4));
+        CUDA_TRY(ix->ws_partial.reserve((size_t)grid * qb * k * 8));
+        const float* q = d_queries + (size_t)done * ix->dim;
+        mma_prep_queries_i8_kernel<<<qb, 128, 0, stream>>>(q, qb, ix->dim, ix->max_row_norm, ix->i8_max_ex, ix->i8_sx,
+                                                           ix->ws_qhat.as<int8_t>(), ix->ws_margin.as<float>(),
+                                                           ix->ws_qscale.as<float>(), ix->ws_redo.as<uint32_t>());
         CUDA_TRY(cudaGetLastError());
         I8ScanArgs a{};
         a.codes = ix->d_slab_i8.as<int8_t>();
@@ -805,7 +812,7 @@ static int search_i8_single_locked(const fsgpu_index* ix, const float* d_queries
             }
             CUDA_TRY(cudaEventRecord(ev.first, stream));
         }
-        scan_i8_kernel<<<grid, kScanThreads, smem, stream>>>(a);
+        kernel<<<grid, kScanThreads, smem, stream>>>(a);
         CUDA_TRY(cudaGetLastError());
         if (ix->profiling) {
             CUDA_TRY(cudaEventRecord(ev.second, stream));
@@ -813,38 +820,46 @@ static int search_i8_single_locked(const fsgpu_index* ix, const float* d_queries
         }
         ix->prof.scan_launches += 1;
         ix->prof.scan_bytes += ix->n_rows * ix->dim;  // int8 codes
-        MergeArgs m{};
+        MergeArgs m{};  // approximate top-k of every query of the group
         m.keys = a.partial;
-        m.list_stride = k;
-        m.query_stride = 0;
+        m.list_stride = (uint64_t)qb * k;
+        m.query_stride = k;
         m.n_lists = grid;
         m.k_in = k;
         m.k_out = k;
         m.cap = cap;
         m.out_keys = ix->ws_i8_top.as<uint64_t>();
         m.error_flag = ix->d_error;
-        int rc = launch_merge(m, 1, stream);
+        int rc = launch_merge(m, qb, stream);
         if (rc) return rc;
-        i8_gate_kernel<<<1, kScanThreads, 0, stream>>>(ix->ws_i8_top.as<uint64_t>(), k, ix->d_slab, ix->row_base, ix->dim, q,
-                                                       ix->ws_margin.as<float>(), ix->reduce_order, ix->tail_fma,
-                                                       ix->ws_gate.as<float>(), ix->ws_gather_count.as<uint32_t>());
-        CUDA_TRY(cudaGetLastError());
-        i8_select_kernel<<<(unsigned)std::min<uint64_t>((ix->n_rows + 255) / 256, (uint64_t)ix->num_sms * 16), 256, 0, stream>>>(
-            ix->ws_approx.as<float>(), ix->n_rows, ix->ws_gate.as<float>(), ix->ws_gather_pos.as<uint32_t>(), kI8ListCap,
-            ix->ws_gather_count.as<uint32_t>(), ix->d_error + 1);
-        CUDA_TRY(cudaGetLastError());
         ix->prof.merge_launches += 1;
-        ix->prof.other_launches += 3;
-        ix->d_gather_pos = ix->ws_gather_pos.as<uint32_t>();
-        ix->d_gather_count = ix->ws_gather_count.as<uint32_t>();
-        ix->gather_cap = kI8ListCap;
-        rc = search_gather_locked(ix, q, 1, k, d_out_keys ? d_out_keys + (size_t)b * k : nullptr,
-                                  d_out_hits ? d_out_hits + (size_t)b * k : nullptr, d_out_counts ? d_out_counts + b : nullptr,
-                                  stream);
-        ix->d_gather_pos = nullptr;
-        ix->d_gather_count = nullptr;
-        ix->gather_cap = 0;
-        if (rc) return rc;
+        for (uint32_t qi = 0; qi < qb; ++qi) {
+            const size_t o = (size_t)done + qi;
+            const float* qq = d_queries + o * ix->dim;
+            const float* approx = ix->ws_approx.as<float>() + (size_t)qi * ix->n_rows;
+            i8_gate_kernel<<<1, kScanThreads, 0, stream>>>(ix->ws_i8_top.as<uint64_t>() + (size_t)qi * k, k, ix->d_slab,
+                                                           ix->row_base, ix->dim, qq, ix->ws_margin.as<float>() + qi,
+                                                           ix->reduce_order, ix->tail_fma, ix->ws_gate.as<float>(),
+                                                           ix->ws_gather_count.as<uint32_t>());
+            CUDA_TRY(cudaGetLastError());
+            i8_select_kernel<<<(unsigned)std::min<uint64_t>((ix->n_rows + 255) / 256, (uint64_t)ix->num_sms * 16), 256, 0,
+                               stream>>>(approx, ix->n_rows, ix->ws_gate.as<float>(), ix->ws_gather_pos.as<uint32_t>(),
+                                         kI8ListCap, ix->ws_gather_count.as<uint32_t>(), ix->d_error + 1);
+            CUDA_TRY(cudaGetLastError());
+            ix->prof.other_launches += 2;
+            ix->d_gather_pos = ix->ws_gather_pos.as<uint32_t>();
+            ix->d_gather_count = ix->ws_gather_count.as<uint32_t>();
+            ix->gather_cap = kI8ListCap;
+            rc = search_gather_locked(ix, qq, 1, k, d_out_keys ? d_out_keys + o * k : nullptr,
+                                      d_out_hits ? d_out_hits + o * k : nullptr, d_out_counts ? d_out_counts + o : nullptr,
+                                      stream);
+            ix->d_gather_pos = nullptr;
+            ix->d_gather_count = nullptr;
+            ix->gather_cap = 0;
+            if (rc) return rc;
+        }
+        ix->prof.other_launches += 1;  // prep
+        done += qb;
     }
     return FSGPU_OK;
 }
@@ -1331,7 +1346,9 @@ extern "C" int fsgpu_search_top_k_filtered(const fsgpu_index* ix, const float* q
     // One or two finite queries on an index that holds int8 codes: int8 pass 1 + exact re-score
     // (half the bytes of the f16 scan); a position list that overflows re-runs the call on the f16 scan.
     const int min_batch = env_int("FSGPU_MMA_MIN_BATCH", 3);
-    bool i8_single = ix->i8_ok && env_int("FSGPU_MMA_I8", 0) != 0 && !(min_batch > 0 && batch >= (uint32_t)min_batch) &&
+    const uint32_t i8_max_batch = (uint32_t)std::max(0, env_int("FSGPU_I8_MAX_BATCH", 2));
+    bool i8_single = ix->i8_ok && env_int("FSGPU_MMA_I8", 0) != 0 &&
+                     (batch <= i8_max_batch || !(min_batch > 0 && batch >= (uint32_t)min_batch)) && batch <= 64 &&
                      k <= kFusedMaxK && ix->n_rows > 0;
     for (size_t i = 0; i8_single && i < (size_t)batch * dim; ++i) i8_single = std::isfinite(queries[i]);
     for (int attempt = 0; attempt < 2; ++attempt) {

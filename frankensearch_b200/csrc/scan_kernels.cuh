@@ -543,47 +543,54 @@ gather_keys_kernel(const uint16_t* __restrict__ slab, uint64_t row_base, uint32_
 struct I8ScanArgs {
     const int8_t* codes;        // [n_rows, dim]
     const uint8_t* tombstones;  // packed bitmap or nullptr
-    const int8_t* q_codes;      // [dim]
-    const float* qscale;        // [1] score = acc * qscale
+    const int8_t* q_codes;      // [QB, dim]
+    const float* qscale;        // [QB] score = acc * qscale
     uint64_t n_rows, row_base;
     uint32_t dim;               // multiple of 128, <= 512
     uint32_t k, cap, sync_every;
-    float* approx;              // [n_rows] out; -inf for excluded rows
-    uint64_t* partial;          // [gridDim.x, k] approximate keys
+    float* approx;              // [QB, n_rows] out; -inf for excluded rows
+    uint64_t* partial;          // [gridDim.x, QB, k] approximate keys
     uint32_t* error_flag;
 };
 
 constexpr int kI8RowsPerIter = kScanWarps * 4 * 2;  // 4 rows per warp-load, 2 loads in flight per lane
 
+// QB queries share one pass over the codes (1, 2 or 4: the pass stays HBM-bound, dp4a work grows).
+template <int QB>
 __global__ void __launch_bounds__(kScanThreads) scan_i8_kernel(const I8ScanArgs args) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint64_t* cand = reinterpret_cast<uint64_t*>(smem_raw);
-    uint64_t* tau = cand + args.cap;
-    uint32_t* cnt = reinterpret_cast<uint32_t*>(tau + 1);
-    if (threadIdx.x == 0) {
-        *cnt = 0u;
-        *tau = 0ull;
+    uint64_t* cand = reinterpret_cast<uint64_t*>(smem_raw);          // [QB][cap]
+    uint64_t* tau = cand + (size_t)QB * args.cap;                      // [QB]
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(tau + QB);            // [QB]
+    if (threadIdx.x < QB) {
+        cnt[threadIdx.x] = 0u;
+        tau[threadIdx.x] = 0ull;
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sub = lane & 7, rr = lane >> 3;
     const uint32_t nj = args.dim >> 7;  // 128-byte segments per row
-    int y[4][4];
+    int y[QB][4][4];
+    float qscale[QB];
 #pragma unroll
-    for (uint32_t j = 0; j < 4; ++j) {
-        if (j < nj) {
-            const int4 v = *reinterpret_cast<const int4*>(args.q_codes + j * 128u + sub * 16u);
-            y[j][0] = v.x; y[j][1] = v.y; y[j][2] = v.z; y[j][3] = v.w;
-        } else {
-            y[j][0] = y[j][1] = y[j][2] = y[j][3] = 0;
+    for (int qi = 0; qi < QB; ++qi) {
+        qscale[qi] = args.qscale[qi];
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j) {
+            if (j < nj) {
+                const int4 v = *reinterpret_cast<const int4*>(args.q_codes + (size_t)qi * args.dim + j * 128u + sub * 16u);
+                y[qi][j][0] = v.x; y[qi][j][1] = v.y; y[qi][j][2] = v.z; y[qi][j][3] = v.w;
+            } else {
+                y[qi][j][0] = y[qi][j][1] = y[qi][j][2] = y[qi][j][3] = 0;
+            }
         }
     }
-    const float qscale = *args.qscale;
     __syncthreads();
-    const CandBuf buf{cand, cnt, tau};
     const uint64_t n = args.n_rows;
     const uint64_t n_tiles = (n + kI8RowsPerIter - 1) / kI8RowsPerIter;
     const uint32_t trigger = args.cap - args.sync_every * kI8RowsPerIter;
-    float thr = -INFINITY;
+    float thr[QB];
+#pragma unroll
+    for (int qi = 0; qi < QB; ++qi) thr[qi] = -INFINITY;
     uint32_t it = 0;
     for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const uint64_t row0 = tile * kI8RowsPerIter + (uint64_t)warp * 8u + rr;  // this lane's rows: row0, row0 + 4
@@ -599,43 +606,62 @@ __global__ void __launch_bounds__(kScanThreads) scan_i8_kernel(const I8ScanArgs 
         }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            int acc = 0;
-#pragma unroll
-            for (uint32_t j = 0; j < 4; ++j)
-                if (j < nj) {
-                    acc = __dp4a((int)x[h][j].x, y[j][0], acc);
-                    acc = __dp4a((int)x[h][j].y, y[j][1], acc);
-                    acc = __dp4a((int)x[h][j].z, y[j][2], acc);
-                    acc = __dp4a((int)x[h][j].w, y[j][3], acc);
-                }
-            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-            acc += __shfl_xor_sync(0xffffffffu, acc, 4);
             const uint64_t row = row0 + 4u * h;
-            if (sub == 0 && row < n) {
-                const bool dead = tombstoned(args.tombstones, row);
-                const float s = __fmul_rn((float)acc, qscale);
-                args.approx[row] = dead ? -INFINITY : s;
-                if (!dead && !(s < thr)) {
-                    const uint64_t key = make_key(s, (uint32_t)(args.row_base + row));
-                    if (key > *tau && !cand_push(buf, args.cap, key)) atomicExch(args.error_flag, 1u);
+            const bool mine = sub == 0 && row < n;
+            const bool dead = mine && tombstoned(args.tombstones, row);
+#pragma unroll
+            for (int qi = 0; qi < QB; ++qi) {
+                int acc = 0;
+#pragma unroll
+                for (uint32_t j = 0; j < 4; ++j)
+                    if (j < nj) {
+                        acc = __dp4a((int)x[h][j].x, y[qi][j][0], acc);
+                        acc = __dp4a((int)x[h][j].y, y[qi][j][1], acc);
+                        acc = __dp4a((int)x[h][j].z, y[qi][j][2], acc);
+                        acc = __dp4a((int)x[h][j].w, y[qi][j][3], acc);
+                    }
+                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+                if (mine) {
+                    const float s = __fmul_rn((float)acc, qscale[qi]);
+                    args.approx[(size_t)qi * n + row] = dead ? -INFINITY : s;
+                    if (!dead && !(s < thr[qi])) {
+                        const uint64_t key = make_key(s, (uint32_t)(args.row_base + row));
+                        const CandBuf buf{cand + (size_t)qi * args.cap, cnt + qi, tau + qi};
+                        if (key > tau[qi] && !cand_push(buf, args.cap, key)) atomicExch(args.error_flag, 1u);
+                    }
                 }
             }
         }
         if ((it + 1) % args.sync_every == 0) {
             __syncthreads();
-            if (*cnt > trigger) cand_compact(buf, args.cap, args.k);
+#pragma unroll
+            for (int qi = 0; qi < QB; ++qi) {
+                const CandBuf buf{cand + (size_t)qi * args.cap, cnt + qi, tau + qi};
+                if (cnt[qi] > trigger) cand_compact(buf, args.cap, args.k);  // CTA-uniform
+            }
             __syncthreads();
-            const uint64_t t = *tau;
-            thr = t ? key_score(t) : -INFINITY;
+#pragma unroll
+            for (int qi = 0; qi < QB; ++qi) {
+                const uint64_t t = tau[qi];
+                thr[qi] = t ? key_score(t) : -INFINITY;
+            }
         }
     }
     __syncthreads();
-    cand_compact(buf, args.cap, args.k);
+#pragma unroll
+    for (int qi = 0; qi < QB; ++qi) {
+        const CandBuf buf{cand + (size_t)qi * args.cap, cnt + qi, tau + qi};
+        cand_compact(buf, args.cap, args.k);
+    }
     __syncthreads();
-    const uint32_t c = min(*cnt, args.k);
-    uint64_t* out = args.partial + (size_t)blockIdx.x * args.k;
-    for (uint32_t i = threadIdx.x; i < args.k; i += blockDim.x) out[i] = i < c ? cand[i] : 0ull;
+    for (int qi = 0; qi < QB; ++qi) {
+        const uint32_t c = min(cnt[qi], args.k);
+        uint64_t* out = args.partial + ((size_t)blockIdx.x * QB + qi) * args.k;
+        const uint64_t* src = cand + (size_t)qi * args.cap;
+        for (uint32_t i = threadIdx.x; i < args.k; i += blockDim.x) out[i] = i < c ? src[i] : 0ull;
+    }
 }
 
 // One CTA: exact scores of the approximate top-k (`keys`, 0 = empty) -> gate = (k-th best exact) -

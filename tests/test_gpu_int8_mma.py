@@ -223,3 +223,32 @@ def test_int8_single_query_list_overflow_falls_back(i8_env, fo):
     wr, ws = fo.search_top_k(slab, row, 10)
     assert np.array_equal(bits(scores[0]), bits(ws))
     ix.close()
+
+
+def test_int8_small_batches_share_one_pass(i8_env, fo, monkeypatch):
+    """Batches of 2..7 through the host API with the multi-query pass switched on (FSGPU_I8_QB=4,
+    off by default: it is ALU-bound): groups of 4 / 2 / 1 queries per int8 pass; every query's hits
+    equal the oracle's."""
+    import frankensearch_b200 as fs
+
+    monkeypatch.setenv("FSGPU_I8_QB", "4")
+    monkeypatch.setenv("FSGPU_I8_MAX_BATCH", "8")
+
+    n, dim = 80000, 384
+    slab, _ = fo.synth_rows(1, 21, 0, n, dim)
+    tomb = np.arange(n) % 13 == 0
+    ix = fs.GpuVectorIndex.from_f16_bits(None, slab, tombstones=tomb)
+    assert ix._L.fsgpu_index_int8_ready(ix._h) == 1
+    queries = np.stack([fo.clustered_query(q, dim) for q in range(8)])
+    for batch, passes in ((2, 1), (3, 2), (4, 1), (5, 2), (7, 3)):
+        for k in (10, 100):
+            ix.profile_read(reset=True)
+            rows, scores, counts = ix.search_top_k_batch(queries[:batch], k)
+            p = ix.profile_read(reset=True)
+            assert p["scan_launches"] == passes and p["scan_bytes"] == passes * n * dim, (batch, p)
+            for b in range(batch):
+                wr, ws = fo.search_top_k(slab, queries[b], k, fo.pack_bitmap(tomb))
+                c = int(counts[b])
+                assert np.array_equal(rows[b, :c].astype(np.uint64), wr), (batch, k, b)
+                assert np.array_equal(bits(scores[b, :c]), bits(ws)), (batch, k, b)
+    ix.close()

@@ -17,27 +17,28 @@ def main():
     rows = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
     dim = int(sys.argv[2]) if len(sys.argv) > 2 else 384
     k = int(sys.argv[3]) if len(sys.argv) > 3 else 10
+    batch = int(sys.argv[4]) if len(sys.argv) > 4 else 1
     os.environ["FSGPU_MMA_I8"] = "1"
     dev = torch.device("cuda", 0)
     slab = torch.empty((rows, dim), dtype=torch.int16, device=dev)
     fs._ffi.check(fs._ffi.lib().fsgpu_synth_rows_device(0, 1, 1, 0, rows, dim, 64, 0.30, slab.data_ptr(), None))
     ix = fs.GpuVectorIndex.from_device_tensor(slab)
     rng = np.random.default_rng(1)
-    qs = rng.standard_normal((64, dim)).astype(np.float32)
+    qs = rng.standard_normal((64 * batch, dim)).astype(np.float32)
     qs /= np.linalg.norm(qs, axis=1, keepdims=True)
-    print(f"# rows={rows} dim={dim} k={k} int8_ready={ix._L.fsgpu_index_int8_ready(ix._h)}")
+    print(f"# rows={rows} dim={dim} k={k} batch={batch} int8_ready={ix._L.fsgpu_index_int8_ready(ix._h)}")
     ref = None
     for mode in ("0", "1"):
         os.environ["FSGPU_MMA_I8"] = mode
         for i in range(5):
-            ix.search_top_k_batch(qs[i], k)
+            ix.search_top_k_batch(qs[i * batch:(i + 1) * batch], k)
         ix.profile_read(reset=True)
         ix.profile_enable(True)
         lat = []
         out = []
         for i in range(64):
             t0 = time.perf_counter()
-            r = ix.search_top_k_batch(qs[i], k)
+            r = ix.search_top_k_batch(qs[i * batch:(i + 1) * batch], k)
             lat.append((time.perf_counter() - t0) * 1e3)
             out.append(r)
         p = ix.profile_read(reset=True)
