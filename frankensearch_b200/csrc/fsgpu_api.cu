@@ -449,11 +449,13 @@ static int search_exact_locked(const fsgpu_index* ix, const float* d_queries, ui
 struct MmaCascade {
     uint64_t n_tiles = 0, t0 = 0, t1 = 0;  // t1 == 0: two levels only; t0 == n_tiles: one level
     uint32_t k_sel = 16, tile_rows = kMmaN;
+    bool group_max = false;  // level 0 keeps the best score of every 8-row group of a sample 8x as large
     double slack = 6.0, random_part = 0.0;  // expected gate-clearing rows per query and level
     // capacity of one (CTA, query) list when `g` CTAs (or CTA pairs) share a query block
     // (each CTA keeps two lists per query, one per half of the tile's columns)
     uint32_t list_cap(uint32_t g) const {
-        const uint64_t dump = (t0 + g - 1) / g * (tile_rows / 2);  // level 0 keeps every score of its tiles
+        // level 0 keeps every score of its tiles (or one score per 8 rows: group_max)
+        const uint64_t dump = (t0 + g - 1) / g * (tile_rows / (group_max ? 16 : 2));
         const uint64_t rnd = (uint64_t)std::min(slack * random_part / (2.0 * g), 4194304.0) + 64;
         return (uint32_t)((std::max(dump, rnd) + 63) / 64 * 64);
     }
@@ -507,6 +509,17 @@ static MmaCascade plan_cascade(uint64_t n_rows, uint32_t k, uint32_t tile_rows) 
     if (c.n_tiles > 8 * c.t0) {
         c.t1 = (uint64_t)std::llround(std::sqrt((double)c.t0 * (double)c.n_tiles));
         c.t1 = std::min(c.n_tiles, std::max(c.t1, 2 * c.t0));
+        // the first level only feeds a k'-th-best selection: with one score per 8-row group it samples
+        // 8x as many tiles for the same number of appends, and its gate is ~8x tighter
+        if (env_int("FSGPU_MMA_GROUP_MAX", 1) != 0) {
+            // ... but the next level must still be >= 8x as large, or it too often catches fewer than
+            // k' rows above this gate (their count is ~ Poisson(k' * Gamma(k')/k' * t1/t0))
+            const uint64_t wide = std::min<uint64_t>(8 * c.t0, std::max<uint64_t>(c.t0, c.t1 / 8));
+            if (wide > c.t0) {
+                c.t0 = wide;
+                c.group_max = true;
+            }
+        }
         c.random_part = std::max((double)c.k_sel * (double)c.t1 / (double)c.t0,
                                  (double)c.k_sel * (double)c.n_tiles / (double)c.t1);
     } else if (c.t0 < c.n_tiles) {
@@ -546,7 +559,8 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
     auto stage_cap_for = [](double expected, uint32_t limit) {
         return std::min(limit, std::max(1024u, host_next_pow2((uint32_t)std::min(2.5 * expected + 256.0, 1.0e6))));
     };
-    const uint32_t gate0_cap = stage_cap_for((double)cas.t0 * cas.tile_rows / 2.5, kMmaStageScores);  // exact dump size
+    const uint32_t gate0_cap = stage_cap_for((double)cas.t0 * cas.tile_rows / (cas.group_max ? 8.0 : 1.0) / 2.5,
+                                             kMmaStageScores);  // exact dump size
     const uint32_t gate1_cap = stage_cap_for(cas.random_part, kMmaStageScores);
     const uint32_t refine_cap = stage_cap_for(cas.t0 < cas.n_tiles ? cas.random_part : (double)cas.t0 * cas.tile_rows / 2.5,
                                               kMmaStagePairs);
@@ -635,6 +649,7 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
             if (!level_tiles[lvl]) continue;
             a.tile_stride = env_int("FSGPU_MMA_SAMPLE_CONTIG", 0) ? 1 : cas.n_tiles / level_tiles[lvl];
             a.tile_count = level_tiles[lvl];
+            a.dump_group_max = (lvl == 0 && cas.group_max) ? 1u : 0u;
             a.gate = have_gate ? ix->ws_gate.as<float>() : nullptr;
             a.progress = paced ? ix->ws_progress.as<uint32_t>() : nullptr;
             if (paced) CUDA_TRY(cudaMemsetAsync(ix->ws_progress.p, 0, progress_bytes, stream));
@@ -643,12 +658,14 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
             CUDA_TRY(cudaGetLastError());
             trace.mark(lvl ? "scan1" : "scan0");
             ga.stage_cap = have_gate ? gate1_cap : gate0_cap;
+            ga.keep_prev = have_gate ? 1u : 0u;
             mma_gate_kernel<<<sub, 256, mma_stage_smem_bytes(ga.stage_cap, false), stream>>>(ga);
             CUDA_TRY(cudaGetLastError());
             ix->prof.other_launches += 2;
             have_gate = true;
         }
         // the full pass
+        a.dump_group_max = 0;
         a.tile_stride = 1;
         a.tile_count = cas.n_tiles;
         a.gate = have_gate ? ix->ws_gate.as<float>() : nullptr;

@@ -61,6 +61,7 @@ struct MmaScanArgs {
     // pseudo-random tile per stratum (a constant stride camps on a few HBM channels: a strided
     // sample pass ran at 140 GB/s, profiles/r01_mma_v3_L1_strided_ncu.json)
     uint64_t tile_stride, tile_count;
+    uint32_t dump_group_max;   // first sample level: append only the best score of every 8-row group
     const float* gate;         // [n_qblocks*128] static per-query gate (nullptr = -inf: keep everything)
     const float* qscale;       // int8 form only: [n_qblocks*128] score = accumulator * qscale[query]
     const uint32_t* redo;      // [n_qblocks*128] != 0: query is served by the exact path, skip it
@@ -420,6 +421,49 @@ __device__ __forceinline__ void mma_epilogue_tile(const MmaScanArgs& args, uint3
     }
 }
 
+// First sample level ("dump"): its list only feeds the k'-th-best selection that becomes the next
+// gate, so instead of every score of the sample it keeps the best live score of each 8-row group.
+// The k' largest group maxima belong to k' distinct live rows, hence the k'-th largest of them is
+// still a lower bound of the corpus' k'-th best — and a sample 8x as large costs the same number of
+// appends, which makes that gate ~8x tighter (the second level then runs at full speed instead
+// of on the epilogue's slow path).  The row stored with a group maximum is the group's first row.
+template <int COLS, bool I8>
+__device__ __forceinline__ void mma_epilogue_dump_max(const MmaScanArgs& args, uint32_t taddr, uint64_t tile_row0,
+                                                      bool live, float qscale, MmaCand* list, uint32_t& count) {
+    // every lane of the warp runs the TMEM loads (tcgen05.ld is warp-collective); `live` only
+    // predicates the appends
+    using D = MmaDom<I8>;
+    uint32_t v[32];
+#pragma unroll 1
+    for (int c = 0; c < COLS / 32; ++c) {
+        tmem_ld_x32(taddr + c * 32u, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const uint64_t row0 = tile_row0 + (uint32_t)(c * 32 + g * 8);
+            uint32_t dead = 0u;  // bit i: column i does not count (past the corpus, or tombstoned)
+            if (row0 >= args.n_rows)
+                dead = 0xFFu;
+            else if (row0 + 8u > args.n_rows)
+                dead = (0xFFu << (uint32_t)(args.n_rows - row0)) & 0xFFu;
+            if (args.tombstones && row0 < args.n_rows) dead |= __ldg(args.tombstones + (row0 >> 3));  // row0 % 8 == 0
+            float m = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (!((dead >> i) & 1u)) m = fmaxf(m, D::score(v[g * 8 + i], qscale));
+            if (live && (dead & 0xFFu) != 0xFFu) {
+                if (count < args.cap) {
+                    MmaCand e;
+                    e.score = m;
+                    e.row = (uint32_t)(args.row_base + row0);
+                    list[count] = e;
+                }
+                ++count;
+            }
+        }
+    }
+}
+
 // This thread's gate in the accumulator domain.  f32: the gate itself.  s32: the largest integer
 // bound that keeps every accumulator whose score (acc * qscale, rounded) reaches the gate.
 template <bool I8>
@@ -573,7 +617,11 @@ mma_scan_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * kMmaN + half * (kMmaN / 2);
-            mma_epilogue_tile<kMmaN / 2, I8>(args, taddr, tile * kMmaN + half * (kMmaN / 2), gate, qscale, list, count);
+            if (args.dump_group_max) {
+                mma_epilogue_dump_max<kMmaN / 2, I8>(args, taddr, tile * kMmaN + half * (kMmaN / 2), live, qscale, list, count);
+            } else {
+                mma_epilogue_tile<kMmaN / 2, I8>(args, taddr, tile * kMmaN + half * (kMmaN / 2), gate, qscale, list, count);
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));  // accumulator drained -> MMA may reuse it
@@ -756,7 +804,11 @@ mma_scan_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * kPairN + half * (kPairN / 2);
-            mma_epilogue_tile<kPairN / 2, I8>(args, taddr, tile * kPairN + half * (kPairN / 2), gate, qscale, list, count);
+            if (args.dump_group_max) {
+                mma_epilogue_dump_max<kPairN / 2, I8>(args, taddr, tile * kPairN + half * (kPairN / 2), live, qscale, list, count);
+            } else {
+                mma_epilogue_tile<kPairN / 2, I8>(args, taddr, tile * kPairN + half * (kPairN / 2), gate, qscale, list, count);
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(tempty_bar(acc), 0);  // leader may reuse the accumulator
@@ -949,6 +1001,7 @@ struct MmaGateArgs {
     float* gate;            // out
     uint32_t k_sel;
     uint32_t stage_cap;     // staged scores per CTA (sized by the host from the expected list lengths)
+    uint32_t keep_prev;     // `gate` already holds the previous level's (valid) gate: never go below it
 };
 
 __global__ void __launch_bounds__(256) mma_gate_kernel(const MmaGateArgs args) {
@@ -957,10 +1010,12 @@ __global__ void __launch_bounds__(256) mma_gate_kernel(const MmaGateArgs args) {
     if (args.redo[b] != 0u) return;
     const MmaStageSmem sm = carve_stage_smem(smem_raw, args.stage_cap, false);
     const uint32_t total = mma_stage_lists(sm, args.lists, b);
-    float gate = -INFINITY;
+    // a level that caught fewer than k' rows (its sample was unlucky) keeps the previous level's gate —
+    // also a lower bound of the corpus' k'-th best, just a looser one — instead of opening the gate
+    float gate = args.keep_prev ? args.gate[b] : -INFINITY;
     if (total >= args.k_sel) {  // CTA-uniform
         const uint32_t u = mma_kth_best(sm, args.lists, b, args.k_sel, total, total <= sm.cap);
-        gate = __fsub_rd(unordered_score(u), args.margin2[b]);
+        gate = fmaxf(gate, __fsub_rd(unordered_score(u), args.margin2[b]));
     }
     if (threadIdx.x == 0) args.gate[b] = gate;
 }
