@@ -54,7 +54,7 @@ def workload_config(a, n_gpus):
         "workload": f"configs[2]: {a.rows} docs x {a.dim}-dim f16, batch {a.batch} queries, exact cosine top-{a.k}",
         "rows": a.rows, "dim": a.dim, "batch": a.batch, "k": a.k,
         "corpus": "clustered (64 centroids, noise 0.30) — reference bench generator fsvi_int8_two_pass.rs:199-231",
-        "storage": "f16 slab, f32 query; tensor-core candidate pass (f16 x f16 -> f32) + exact re-scoring with the reference accumulation tree (bit-exact results)",
+        "storage": "f16 slab (+ int8 codes of it for the candidate pass), f32 query; tensor-core candidate pass (int8 x int8 -> s32, or f16 x f16 -> f32 with FSGPU_MMA_I8=0) + exact f16 re-scoring with the reference accumulation tree (bit-exact results)",
         "sharding": "single GPU" if n_gpus == 1 else f"rows sharded over {n_gpus} ranks, one all-gather of top-k keys",
         "l2": "inputs larger than L2 (slab per GPU >> 126 MB); no explicit flush",
     }
@@ -348,11 +348,21 @@ def run_ours(a):
             # a 1024-query batch is a dense [B,D]x[D,N] contraction: tensor-bound
             flops = prof["mma_flops"] / prof["mma_launches"]
             achieved_tf = flops / (avg_ms * 1e-3) / 1e12 if avg_ms > 0 else 0.0
+            i8 = prof.get("i8_launches", 0) > 0
+            if i8:
+                # the int8 form: kind::i8 MMAs retire twice the K per instruction of kind::f16/bf16 at the
+                # same instruction rate, so the tensor peak is 2x the measured bf16 figure (no int8 figure
+                # is in MEASURED_PEAKS.json); ops = 2 per int8 multiply-add
+                peak_tf, peak_tf_sus = 2.0 * peak_tf, 2.0 * peak_tf_sus
+                peak_src += "; int8 tensor peak = 2 x measured bf16"
+                traffic = None  # the stored traffic figure belongs to the f16 form
             roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                         "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic,
-                        "kernel": "mma_scan_pair_kernel (tcgen05.mma.cta_group::2 kind::f16, M=256 queries x N=256 rows per CTA pair, K=dim)",
+                        "kernel": ("mma_scan_pair_kernel<int8> (tcgen05.mma.cta_group::2 kind::i8, M=256 queries x N=256 "
+                                   "rows per CTA pair, K=dim; exact: f16 re-score of the candidate superset)") if i8 else
+                                  "mma_scan_pair_kernel (tcgen05.mma.cta_group::2 kind::f16, M=256 queries x N=256 rows per CTA pair, K=dim)",
                         "flops_per_launch": flops, "frac_of_sustained_peak": achieved_tf / peak_tf_sus,
-                        "peak_sustained": peak_tf_sus,
+                        "peak_sustained": peak_tf_sus, "ops": "int8 multiply-add = 2 ops" if i8 else "f16 multiply-add = 2 flops",
                         "hbm_gbs_same_launch": hbm_achieved, "hbm_frac_same_launch": hbm_achieved / peak_gbs}
         else:
             roofline = {"bound": "hbm", "achieved": hbm_achieved, "peak": peak_gbs, "unit": "GB/s",

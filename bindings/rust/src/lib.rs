@@ -28,6 +28,8 @@ pub struct fsgpu_index_options {
     pub tail_fma: i32,       // 1: bytes-kernel tail (simd.rs:440-444), 0: slice-kernel tail (simd.rs:298-300)
     pub slab_is_device: i32,
     pub row_base: u64,       // global row of local row 0 (row-sharded corpora)
+    pub int8_codes: i32,     // 1 (default): also keep int8 codes for the int8 forms of the scan (same results)
+    pub reserved: i32,
 }
 
 /// `RrfConfig` (crates/frankensearch-fusion/src/rrf.rs:25-48).

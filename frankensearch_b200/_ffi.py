@@ -57,13 +57,15 @@ class IndexOptions(C.Structure):
         ("tail_fma", C.c_int32),
         ("slab_is_device", C.c_int32),
         ("row_base", C.c_uint64),
+        ("int8_codes", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 
 class Profile(C.Structure):
     _fields_ = [("scan_launches", C.c_uint64), ("merge_launches", C.c_uint64), ("other_launches", C.c_uint64),
                 ("scan_bytes", C.c_uint64), ("scan_ms", C.c_double), ("mma_launches", C.c_uint64),
-                ("mma_flops", C.c_double), ("redo_queries", C.c_uint64)]
+                ("mma_flops", C.c_double), ("redo_queries", C.c_uint64), ("i8_launches", C.c_uint64)]
 
 
 class MiniLmLayerWeights(C.Structure):

@@ -58,6 +58,8 @@ extern "C" void fsgpu_index_options_default(fsgpu_index_options* o) {
     o->tail_fma = 1;
     o->slab_is_device = 0;
     o->row_base = 0;
+    o->int8_codes = 1;
+    o->reserved = 0;
 }
 
 // ─── the index handle ───────────────────────────────────────────────────────────────────────
@@ -109,6 +111,7 @@ struct fsgpu_index {
     // the per-row quantisation error
     DevBuf d_slab_i8;
     bool i8_ok = false;
+    bool want_i8 = true;  // fsgpu_index_options.int8_codes
     float i8_sx = 0.0f, i8_max_ex = 0.0f;
     CUtensorMap tm_slab_i8;
     mutable CUtensorMap tm_qhat_i8;
@@ -117,7 +120,7 @@ struct fsgpu_index {
     mutable DevBuf ws_qscale;
     // single-query int8 pass 1 (host API only: it needs the end-of-call synchronisation)
     mutable bool use_i8_single = false;
-    mutable DevBuf ws_approx, ws_i8_top;
+    mutable DevBuf ws_approx, ws_i8_top, ws_i8_cnt;
     // launch accounting (guarded by mu)
     mutable bool profiling = false;
     mutable fsgpu_profile prof{};
@@ -408,7 +411,7 @@ static int index_finish_setup(fsgpu_index* ix) {
 
     // int8 codes for the kind::i8 form (opt-in: half as many bytes again in HBM)
     ix->i8_ok = false;
-    if (ix->mma_ok && ix->dim % 128 == 0 && env_int("FSGPU_MMA_I8", 0) != 0) {
+    if (ix->mma_ok && ix->dim % 128 == 0 && ix->want_i8 && env_int("FSGPU_MMA_I8", 1) != 0) {
         // largest |element|: f16 magnitude bits -> f32
         const uint16_t hb = (uint16_t)stats[2];
         const uint32_t exp = (hb >> 10) & 0x1F, man = hb & 0x3FF;
@@ -417,6 +420,11 @@ static int index_finish_setup(fsgpu_index* ix) {
             const float scale = 127.0f / max_abs;  // simd.rs:1850
             ix->i8_sx = max_abs / 127.0f;
             e = ix->d_slab_i8.reserve(ix->n_rows * ix->dim);
+            if (e == cudaErrorMemoryAllocation) {  // no room for the codes: the f16 forms serve everything
+                cudaGetLastError();
+                cudaFree(d_stats);
+                return FSGPU_OK;
+            }
             if (e == cudaSuccess) e = cudaMemsetAsync(d_stats, 0, 16, ix->stream);
             if (e == cudaSuccess) {
                 quantize_slab_i8_kernel<<<grid, 256, 0, ix->stream>>>(ix->d_slab, ix->n_rows, ix->dim, scale, ix->i8_sx,
@@ -534,7 +542,9 @@ static MmaCascade plan_cascade(uint64_t n_rows, uint32_t k, uint32_t tile_rows) 
 static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint32_t batch, uint32_t k,
                              uint64_t* d_out_keys, fsgpu_hit* d_out_hits, uint32_t* d_out_counts,
                              cudaStream_t stream, bool allow_i8 = true) {
-    const bool i8 = allow_i8 && ix->i8_ok && env_int("FSGPU_MMA_I8", 0) != 0;
+    // the int8 form pays while the candidate volume stays small: k <= 32 (profiles/r01_sweep_i8_form.txt)
+    const bool i8 = allow_i8 && ix->i8_ok && env_int("FSGPU_MMA_I8", 1) != 0 &&
+                    k <= (uint32_t)std::max(0, env_int("FSGPU_I8_MAX_K", 32));
     const uint32_t n_kb = ix->dim / (i8 ? 128 : kMmaKBlock);  // 128-byte K-blocks
     const size_t smem_limit = 227 * 1024;
     const size_t fixed = mma_scan_smem_bytes(n_kb, 0);
@@ -552,7 +562,9 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
     CUDA_TRY(cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t units = pair ? (uint32_t)ix->num_sms / 2 : (uint32_t)ix->num_sms;  // CTAs or CTA pairs
     const uint32_t unit_queries = pair ? 2 * kMmaM : kMmaM;
-    const MmaCascade cas = plan_cascade(ix->n_rows, k, pair ? kPairN : kMmaN);
+    MmaCascade cas = plan_cascade(ix->n_rows, k, pair ? kPairN : kMmaN);
+    // the int8 bound lowers every gate by ~0.25-0.5 sigma of the score distribution: ~4x the rows clear it
+    if (i8) cas.random_part *= (double)std::max(1, env_int("FSGPU_I8_LIST_SCALE", 4));
     const uint32_t fin_cap = cand_capacity(k);
     // shared-memory staging of the candidate lists, sized from the expected list lengths (smaller
     // CTAs -> one wave of gate/refine CTAs); longer lists take the kernels' unstaged path
@@ -663,6 +675,38 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
             CUDA_TRY(cudaGetLastError());
             ix->prof.other_launches += 2;
             have_gate = true;
+            if (i8 && lvl == 1 && env_int("FSGPU_I8_EXACT_GATE", 1) != 0) {
+                // int8 form: tighten the gate of the full pass with an EXACT k-th best of this sample
+                CUDA_TRY(ix->ws_i8_top.reserve((size_t)slots * k * 8));
+                CUDA_TRY(ix->ws_i8_cnt.reserve((size_t)slots * 4));
+                CUDA_TRY(cudaMemsetAsync(ix->ws_i8_cnt.p, 0, (size_t)slots * 4, stream));
+                MmaRefineArgs ri{};
+                ri.lists = ga.lists;
+                ri.margin2 = ga.margin2;
+                ri.redo = ix->ws_redo.as<uint32_t>();
+                ri.k = k;
+                ri.buf_cap = fin_cap;
+                ri.stage_cap = refine_cap;
+                ri.slab = ix->d_slab;
+                ri.queries = q;
+                ri.n_rows = ix->n_rows;
+                ri.row_base = ix->row_base;
+                ri.dim = ix->dim;
+                ri.reduce_order = ix->reduce_order;
+                ri.tail_fma = ix->tail_fma;
+                ri.out_keys = ix->ws_i8_top.as<uint64_t>();
+                ri.out_counts = ix->ws_i8_cnt.as<uint32_t>();
+                ri.error_flag = ix->d_error;
+                ri.redo_any = ix->d_error + 1;
+                ri.intermediate = 1;
+                mma_refine_kernel<<<sub, 256, refine_smem, stream>>>(ri);
+                CUDA_TRY(cudaGetLastError());
+                mma_exact_gate_kernel<<<(sub + 255) / 256, 256, 0, stream>>>(ix->ws_i8_top.as<uint64_t>(),
+                                                                           ix->ws_i8_cnt.as<uint32_t>(), k, sub,
+                                                                           ix->ws_margin.as<float>(), ix->ws_gate.as<float>());
+                CUDA_TRY(cudaGetLastError());
+                ix->prof.other_launches += 2;
+            }
         }
         // the full pass
         a.dump_group_max = 0;
@@ -691,8 +735,9 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
             ix->ev_pending.push_back(ev);
         }
         ix->prof.scan_launches += 1;
-        ix->prof.scan_bytes += ix->n_rows * ix->dim * 2ull;
+        ix->prof.scan_bytes += ix->n_rows * ix->dim * (i8 ? 1ull : 2ull);
         ix->prof.mma_launches += 1;
+        ix->prof.i8_launches += i8 ? 1 : 0;
         ix->prof.mma_flops += 2.0 * (double)slots * (double)ix->n_rows * (double)ix->dim;
         ix->prof.merge_launches += 1;  // refine
 
@@ -837,6 +882,7 @@ static int search_i8_single_locked(const fsgpu_index* ix, const float* d_queries
         }
         ix->prof.scan_launches += 1;
         ix->prof.scan_bytes += ix->n_rows * ix->dim;  // int8 codes
+        ix->prof.i8_launches += 1;
         MergeArgs m{};  // approximate top-k of every query of the group
         m.keys = a.partial;
         m.list_stride = (uint64_t)qb * k;
@@ -1009,6 +1055,7 @@ static int index_alloc_common(fsgpu_index* ix, const fsgpu_index_options* o, uin
     ix->row_base = o->row_base;
     ix->reduce_order = o->reduce_order;
     ix->tail_fma = o->tail_fma ? 1 : 0;
+    ix->want_i8 = o->int8_codes != 0;
     CUDA_TRY(cudaSetDevice(ix->device));
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, ix->device));
@@ -1054,7 +1101,7 @@ extern "C" void fsgpu_index_destroy(fsgpu_index* ix) {
                           &ix->ws_present, &ix->ws_excl, &ix->ws_allow, &ix->ws_progress, &ix->ws_qhat, &ix->ws_margin, &ix->ws_gate, &ix->ws_redo, &ix->ws_cand,
                           &ix->ws_cand_count, &ix->d_wal, &ix->ws_wal_main, &ix->ws_wal_keys, &ix->d_hashes,
                           &ix->ws_allowed, &ix->ws_gather_pos, &ix->ws_gather_count, &ix->ws_gather_keys,
-                          &ix->d_slab_i8, &ix->ws_qscale, &ix->ws_approx, &ix->ws_i8_top})
+                          &ix->d_slab_i8, &ix->ws_qscale, &ix->ws_approx, &ix->ws_i8_top, &ix->ws_i8_cnt})
             b->release();
         if (ix->stream) cudaStreamDestroy(ix->stream);
     }
@@ -1364,7 +1411,7 @@ extern "C" int fsgpu_search_top_k_filtered(const fsgpu_index* ix, const float* q
     // (half the bytes of the f16 scan); a position list that overflows re-runs the call on the f16 scan.
     const int min_batch = env_int("FSGPU_MMA_MIN_BATCH", 3);
     const uint32_t i8_max_batch = (uint32_t)std::max(0, env_int("FSGPU_I8_MAX_BATCH", 2));
-    bool i8_single = ix->i8_ok && env_int("FSGPU_MMA_I8", 0) != 0 &&
+    bool i8_single = ix->i8_ok && env_int("FSGPU_MMA_I8", 1) != 0 && k <= 128 &&
                      (batch <= i8_max_batch || !(min_batch > 0 && batch >= (uint32_t)min_batch)) && batch <= 64 &&
                      k <= kFusedMaxK && ix->n_rows > 0;
     for (size_t i = 0; i8_single && i < (size_t)batch * dim; ++i) i8_single = std::isfinite(queries[i]);

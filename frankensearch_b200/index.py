@@ -22,7 +22,7 @@ REDUCE_ORDERS = {
 }
 
 
-def _options(device: int, reduce_order, tail_fma: bool, slab_is_device: bool, row_base: int):
+def _options(device: int, reduce_order, tail_fma: bool, slab_is_device: bool, row_base: int, int8_codes=None):
     o = _ffi.IndexOptions()
     _ffi.lib().fsgpu_index_options_default(C.byref(o))
     o.device = device
@@ -30,6 +30,8 @@ def _options(device: int, reduce_order, tail_fma: bool, slab_is_device: bool, ro
     o.tail_fma = 1 if tail_fma else 0
     o.slab_is_device = 1 if slab_is_device else 0
     o.row_base = row_base
+    if int8_codes is not None:
+        o.int8_codes = 1 if int8_codes else 0
     return o
 
 
@@ -187,7 +189,7 @@ class GpuVectorIndex:
         return dict(scan_launches=int(p.scan_launches), merge_launches=int(p.merge_launches),
                     other_launches=int(p.other_launches), scan_bytes=int(p.scan_bytes), scan_ms=float(p.scan_ms),
                     mma_launches=int(p.mma_launches), mma_flops=float(p.mma_flops),
-                    redo_queries=int(p.redo_queries))
+                    redo_queries=int(p.redo_queries), i8_launches=int(p.i8_launches))
 
     def set_tombstones(self, flags) -> None:
         """Soft-delete flags (record flag bit 0, lib.rs:172; honoured by the scan, search.rs:1281)."""

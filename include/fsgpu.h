@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FSGPU_ABI_VERSION 1
+#define FSGPU_ABI_VERSION 2
 
 typedef enum fsgpu_status {
     FSGPU_OK = 0,
@@ -71,8 +71,13 @@ typedef struct fsgpu_index_options {
                               0: in-memory slice kernel tail (`+= a*b`, simd.rs:298-300).
                               Only matters when dim % 8 != 0. */
     int32_t slab_is_device;/* 1: `slab` is already a device pointer on `device`; it is used in
-                              place (no copy) and must outlive the index */
+                              place (no copy), must outlive the index and must not change while
+                              the index exists (the index keeps statistics and codes of it) */
     uint64_t row_base;     /* global row number of local row 0 (row-sharded corpora) */
+    int32_t int8_codes;    /* 1 (default): when dim % 128 == 0 also keep the corpus as int8 codes
+                              (+ n_rows * dim bytes of HBM) for the int8 forms of the scan — same
+                              results, less time (see fsgpu_index_int8_ready); 0: f16 slab only */
+    int32_t reserved;
 } fsgpu_index_options;
 
 /* ---- library ------------------------------------------------------------------------------ */
@@ -119,11 +124,12 @@ int fsgpu_index_read_rows_f16(const fsgpu_index* index, uint64_t row_start, uint
                               uint16_t* out_bits);
 /* Replaces VectorIndex::soft_delete's effect on the scan (flag bit 0, search.rs:1281). */
 int fsgpu_index_set_tombstones(fsgpu_index* index, const uint8_t* bitmap_or_null);
-/* int8 form of the batched scan (opt-in: environment FSGPU_MMA_I8=1 when the index is created and
- * when it is searched; dim % 128 == 0).  The index then also holds the corpus as int8 codes made by
+/* int8 forms of the scan (fsgpu_index_options.int8_codes, on by default; dim % 128 == 0; the
+ * environment switch FSGPU_MMA_I8=0 turns them off at creation or per search).  The index also holds the corpus as int8 codes made by
  * the reference's corpus-wide quantiser (quantize_f16_slab_to_i8, crates/frankensearch-index/src/
- * simd.rs:1842-1859: scale = 127 / max|x|, code = clamp(round(x * scale), -127, 127)) and batches
- * run on tcgen05.mma kind::i8 — half the bytes and twice the MMA rate.  Results are unchanged (exact):
+ * simd.rs:1842-1859: scale = 127 / max|x|, code = clamp(round(x * scale), -127, 127)); batches with
+ * k <= 32 run on tcgen05.mma kind::i8 — half the bytes and twice the MMA rate — and one or two
+ * queries through the host API take a dp4a pass over the codes.  Results are unchanged (exact):
  * the int8 score only selects a candidate superset under a proven error bound, the winners are
  * re-scored with the reference's f16 arithmetic.  `fsgpu_index_read_codes_i8` copies codes back
  * (parity with the reference quantiser); `out_scale` receives max|x| / 127. */
@@ -160,6 +166,7 @@ typedef struct fsgpu_profile {
     uint64_t mma_launches; /* scan launches that ran on the tensor-core batched kernel */
     double mma_flops;      /* 2 * query slots * rows * dim summed over those launches */
     uint64_t redo_queries; /* queries of batched launches re-run on the exact CUDA-core kernel */
+    uint64_t i8_launches;  /* scan launches that read the int8 codes (kind::i8 MMAs or the dp4a pass) */
 } fsgpu_profile;
 int fsgpu_index_profile_enable(fsgpu_index* index, int on);
 int fsgpu_index_profile_read(fsgpu_index* index, fsgpu_profile* out, int reset);

@@ -25,7 +25,7 @@ def test_header_symbols_are_exported():
     for s in syms:
         assert hasattr(L, s), f"{s} declared in include/fsgpu.h but not exported by libfsgpu.so"
     assert sorted(_ffi.EXPORTS) == syms, "frankensearch_b200/_ffi.py EXPORTS is out of date"
-    assert L.fsgpu_abi_version() == 1
+    assert L.fsgpu_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
@@ -33,7 +33,7 @@ def test_struct_layouts_match_header():
 
     assert C.sizeof(_ffi.Hit) == 8
     assert C.sizeof(_ffi.FusedHitC) == 32
-    assert C.sizeof(_ffi.IndexOptions) == 24
+    assert C.sizeof(_ffi.IndexOptions) == 32
     assert C.sizeof(_ffi.RrfConfigC) == 32
 
 

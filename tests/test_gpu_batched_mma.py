@@ -174,7 +174,9 @@ def test_batched_unsafe_queries_are_redone_exactly(fs, cpu, fo):
     qs[7, 1::2] = 0.0
     ix = fs.GpuVectorIndex.from_f16_bits(None, slab)
     got, prof = search_with_profile(ix, qs, 10)
-    assert prof["mma_launches"] >= 1 and prof["redo_queries"] >= 3
+    # NaN and inf always go to the exact kernel; the f16 form also sends the 1e6-scaled query there
+    # (f16 overflow), the int8 form quantises it with its own scale
+    assert prof["mma_launches"] >= 1 and prof["redo_queries"] >= 2
     assert_batch_matches_oracle(cpu, slab, qs, 10, got)
     ix.close()
 

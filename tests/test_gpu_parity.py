@@ -463,11 +463,15 @@ def test_config3_10m_x_384_properties_and_full_oracle(gpu, cpu, fo):
     assert np.array_equal(slab_gpu[torch.from_numpy(sample).cuda()].cpu().numpy().view(np.uint16), ref_rows)
     q = fo.clustered_query(7, dim)
     # (d) plant needles: exact copies of one strong row at a tile edge, the first and the last row
+    # (an adopted slab is immutable while an index uses it — the index keeps statistics and int8
+    # codes of it — so the needles are planted between two indexes)
     ix = fs.GpuVectorIndex.from_device_tensor(slab_gpu)
     best = int(ix.search_top_k_batch(q, 1)[0][0, 0])
+    ix.close()
     for r in (0, 63, 64, 5_000_000, n - 1):
         slab_gpu[r] = slab_gpu[best]
     torch.cuda.synchronize()
+    ix = fs.GpuVectorIndex.from_device_tensor(slab_gpu)
     rows, scores, counts = ix.search_top_k_batch(np.stack([q, fo.clustered_query(8, dim)]), k)
     assert counts.tolist() == [k, k]
     planted = sorted({0, 63, 64, 5_000_000, n - 1, best})
