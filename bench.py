@@ -377,7 +377,8 @@ def run_ours(a):
             hbm["peak_gbs"] = peak_gbs
             hbm["frac"] = hbm["achieved_gbs"] / peak_gbs if peak_gbs else None
             hbm["note"] = ("same kernel, one 128-query block per corpus pass: the HBM-bound regime "
-                           "(algorithmic bytes = rows*dim*2 per launch)")
+                           "(algorithmic bytes per launch = rows*dim*2 for the f16 form, rows*dim for the int8 form: "
+                           "see bytes_per_launch)")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,

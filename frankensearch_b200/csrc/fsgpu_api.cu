@@ -547,21 +547,26 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
                     k <= (uint32_t)std::max(0, env_int("FSGPU_I8_MAX_K", 32));
     const uint32_t n_kb = ix->dim / (i8 ? 128 : kMmaKBlock);  // 128-byte K-blocks
     const size_t smem_limit = 227 * 1024;
-    const size_t fixed = mma_scan_smem_bytes(n_kb, 0);
+    // quad form (int8, more than 256 queries): two query blocks per CTA share every B stage
+    const bool quad = i8 && env_int("FSGPU_MMA_QUAD", 1) != 0 && env_int("FSGPU_MMA_PAIR", 1) != 0 && ix->num_sms >= 2 &&
+                      batch > 2 * kMmaM && mma_scan_smem_bytes(2 * n_kb, 4) <= smem_limit;
+    const uint32_t a_tiles = quad ? 2 * n_kb : n_kb;  // 16 KiB query tiles resident per CTA
+    const size_t fixed = mma_scan_smem_bytes(a_tiles, 0);
     uint32_t n_stages = (uint32_t)std::min<size_t>(kMmaMaxStages, (smem_limit - fixed) / kMmaTileBytes);
     const int stage_cap = env_int("FSGPU_MMA_STAGES", 0);
     if (stage_cap >= 2) n_stages = std::min<uint32_t>(n_stages, (uint32_t)stage_cap);
     if (n_stages < 2) return fail(FSGPU_ERR_INVALID_CONFIG, "batched scan does not fit in shared memory (dim=%u)", ix->dim);
-    const size_t smem = mma_scan_smem_bytes(n_kb, n_stages);
+    const size_t smem = mma_scan_smem_bytes(a_tiles, n_stages);
     // CTA-pair form (cta_group::2, 256 queries x 256 rows per MMA) unless FSGPU_MMA_PAIR=0
     // ... and unless the batch is a single 128-query block: that regime is HBM-bound and the
     // single-CTA form streams it faster (6.7 vs 5.8 TB/s at 10 M x 384, profiles/r01_sweep_mma_v6.txt)
     const bool pair = env_int("FSGPU_MMA_PAIR", 1) != 0 && ix->num_sms >= 2 && batch > kMmaM;
-    auto scan_kernel = pair ? (i8 ? mma_scan_pair_kernel<true> : mma_scan_pair_kernel<false>)
+    auto scan_kernel = quad ? mma_scan_quad_kernel
+                     : pair ? (i8 ? mma_scan_pair_kernel<true> : mma_scan_pair_kernel<false>)
                             : (i8 ? mma_scan_kernel<true> : mma_scan_kernel<false>);
     CUDA_TRY(cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t units = pair ? (uint32_t)ix->num_sms / 2 : (uint32_t)ix->num_sms;  // CTAs or CTA pairs
-    const uint32_t unit_queries = pair ? 2 * kMmaM : kMmaM;
+    const uint32_t unit_queries = quad ? 4 * kMmaM : pair ? 2 * kMmaM : kMmaM;
     MmaCascade cas = plan_cascade(ix->n_rows, k, pair ? kPairN : kMmaN);
     // the int8 bound lowers every gate by ~0.25-0.5 sigma of the score distribution: ~4x the rows clear it
     if (i8) cas.random_part *= (double)std::max(1, env_int("FSGPU_I8_LIST_SCALE", 4));
@@ -586,7 +591,7 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
     for (uint32_t done = 0; done < batch; done += max_queries) {
         const uint32_t sub = std::min(max_queries, batch - done);
         const uint32_t n_units = (sub + unit_queries - 1) / unit_queries;  // query blocks or query pairs
-        const uint32_t n_qb = pair ? 2 * n_units : n_units;                // 128-query blocks incl. padding
+        const uint32_t n_qb = quad ? 4 * n_units : pair ? 2 * n_units : n_units;  // 128-query blocks incl. padding
         const uint32_t g = units / n_units;
         const uint32_t grid = g * n_units * (pair ? 2 : 1);
         const uint32_t slots = n_qb * kMmaM;
@@ -595,8 +600,9 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
         CUDA_TRY(ix->ws_gate.reserve((size_t)slots * 4));
         CUDA_TRY(ix->ws_redo.reserve((size_t)slots * 4));
         const uint32_t cap = cas.list_cap(g);
-        CUDA_TRY(ix->ws_cand.reserve((size_t)grid * 2 * kMmaM * cap * sizeof(MmaCand)));
-        CUDA_TRY(ix->ws_cand_count.reserve((size_t)grid * 2 * kMmaM * 4));
+        const size_t lists_per_cta = quad ? 4 : 2;  // (sub-block x) column half
+        CUDA_TRY(ix->ws_cand.reserve((size_t)grid * lists_per_cta * kMmaM * cap * sizeof(MmaCand)));
+        CUDA_TRY(ix->ws_cand_count.reserve((size_t)grid * lists_per_cta * kMmaM * 4));
         if (i8) {
             CUDA_TRY(ix->ws_qscale.reserve((size_t)slots * 4));
             if (ix->tm_qhat_i8_ptr != ix->ws_qhat.p || ix->tm_qhat_i8_rows != slots) {
@@ -648,7 +654,7 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
         if (paced) CUDA_TRY(ix->ws_progress.reserve(progress_bytes));
         a.lead = lead;
         MmaGateArgs ga{};
-        ga.lists = MmaLists{a.cand, a.cand_count, n_qb, g, cap, pair ? 1u : 0u};
+        ga.lists = MmaLists{a.cand, a.cand_count, n_qb, g, cap, quad ? 2u : pair ? 1u : 0u};
         ga.margin2 = ix->ws_margin.as<float>();
         ga.redo = a.redo;
         ga.gate = ix->ws_gate.as<float>();

@@ -376,17 +376,29 @@ __device__ __forceinline__ void mma_epilogue_tile(const MmaScanArgs& args, uint3
                                                   typename MmaDom<I8>::Gate gate, float qscale, MmaCand* list,
                                                   uint32_t& count) {
     static_assert(COLS % 64 == 0 && COLS <= 256, "hot mask is 32 bits of 8-column groups");
-    uint32_t va[32], vb[32];
     uint32_t hot = 0;
-    tmem_ld_x32(taddr, va);
+    if constexpr (COLS <= 128) {
+        // all chunks of the tile in flight at once (tcgen05.wait::ld waits for every outstanding load,
+        // so a two-deep software pipeline serialises them: ~4 TMEM round trips per tile, which the
+        // int8 form's 1536-cycle tile period does not hide — tensor pipe 70 % active before this)
+        uint32_t v[COLS / 32][32];
 #pragma unroll
-    for (int c = 0; c < COLS / 32; c += 2) {
+        for (int c = 0; c < COLS / 32; ++c) tmem_ld_x32(taddr + c * 32u, v[c]);
         tmem_ld_wait();
-        tmem_ld_x32(taddr + (c + 1) * 32u, vb);  // in flight while the previous chunk is reduced
-        hot |= mma_hot_bits(va, gate, 4 * c);
-        tmem_ld_wait();
-        if (c + 2 < COLS / 32) tmem_ld_x32(taddr + (c + 2) * 32u, va);
-        hot |= mma_hot_bits(vb, gate, 4 * (c + 1));
+#pragma unroll
+        for (int c = 0; c < COLS / 32; ++c) hot |= mma_hot_bits(v[c], gate, 4 * c);
+    } else {
+        uint32_t va[32], vb[32];
+        tmem_ld_x32(taddr, va);
+#pragma unroll
+        for (int c = 0; c < COLS / 32; c += 2) {
+            tmem_ld_wait();
+            tmem_ld_x32(taddr + (c + 1) * 32u, vb);  // in flight while the previous chunk is reduced
+            hot |= mma_hot_bits(va, gate, 4 * c);
+            tmem_ld_wait();
+            if (c + 2 < COLS / 32) tmem_ld_x32(taddr + (c + 2) * 32u, va);
+            hot |= mma_hot_bits(vb, gate, 4 * (c + 1));
+        }
     }
     uint32_t hot_warp = __reduce_or_sync(0xffffffffu, hot);
     if (hot_warp == 0u) return;
@@ -828,12 +840,211 @@ mma_scan_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     }
 }
 
+// ─── the scan, CTA-pair form with TWO query blocks per CTA (int8 only) ───────────────────────
+// The int8 form of mma_scan_pair_kernel retires a 256-row tile in half the time, so at the same
+// bytes per tile it asks the L2->SM fabric for twice the bandwidth — and stalls on it (tensor pipe
+// 70 % active at 148 SMs x 32 B/clk x 1.9 GHz ~ 9 TB/s, profiles/r01_mma_pair_i8_b1024_ncu.json).
+// Here every B stage is used by two MMAs groups: the pair holds 512 queries (two 128-query blocks
+// per CTA, int8 so they fit: 2 x 48 KB at D = 384) and one accumulator per block; block 0's MMAs
+// over a tile are followed by block 1's over the same stages, and each block's epilogue overlaps the
+// other block's MMAs.  Half the L2->SM bytes per MMA.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMmaThreads, 1)
+mma_scan_quad_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_x,
+                     const MmaScanArgs args) {
+    extern __shared__ uint8_t smem_dyn[];
+    constexpr bool I8 = true;
+    constexpr uint32_t kElems = 128u;  // int8 codes per 128-byte K-block row
+    constexpr uint32_t kSub = 2;       // query blocks per CTA
+    const uint32_t raw = smem_u32(smem_dyn);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_dyn + (base - raw);
+    const uint32_t a_smem = base;
+    const uint32_t b_smem = a_smem + kSub * args.n_kblocks * kMmaTileBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base_ptr + (size_t)(kSub * args.n_kblocks + args.n_stages) * kMmaTileBytes);
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](uint32_t s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](uint32_t s) { return bar0 + 8u * (8u + s); };
+    auto tfull_bar = [&](uint32_t a) { return bar0 + 8u * (16u + a); };
+    auto tempty_bar = [&](uint32_t a) { return bar0 + 8u * (20u + a); };
+    const uint32_t afull_bar = bar0 + 8u * 24u;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const uint32_t pair = blockIdx.x >> 1;
+    const uint32_t n_qpairs = args.n_qblocks >> 2;  // query QUADS (4 blocks of 128): n_qblocks is a multiple of 4
+    const uint32_t quad = pair % n_qpairs;
+    const uint32_t j0 = pair / n_qpairs;
+    const uint32_t g = args.ctas_per_qblock;  // CTA pairs per query quad
+    // this CTA's query block of sub-block s: ((quad * 2 + s) * 2 + rank)
+    auto qb_of = [&](uint32_t sub) { return (quad * 2u + sub) * 2u + rank; };
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tm_q);
+        tma_prefetch_desc(&tm_x);
+        for (uint32_t s = 0; s < args.n_stages; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (uint32_t a = 0; a < kSub; ++a) {  // one accumulator per sub-block
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 2 * kMmaEpiWarps);  // one arrival per epilogue warp of BOTH CTAs
+        }
+        mbar_init(afull_bar, 1);
+        fence_barrier_init();
+    } else if (warp == 2) {
+        tmem_alloc_pair(smem_u32(tmem_slot), 512);
+    }
+    tc_fence_before();
+    cluster_sync_all();  // barrier inits and TMEM allocations of both CTAs are visible
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs; completion bytes land on the leader's barriers) =====
+        if (elect_one()) {
+            if (rank == 0) mbar_expect_tx(afull_bar, 2u * kSub * args.n_kblocks * kMmaTileBytes);
+            for (uint32_t sub = 0; sub < kSub; ++sub)
+                for (uint32_t kb = 0; kb < args.n_kblocks; ++kb)
+                    tma_load_2d_pair(a_smem + (sub * args.n_kblocks + kb) * kMmaTileBytes, &tm_q, afull_bar,
+                                     (int32_t)(kb * kElems), (int32_t)(qb_of(sub) * kMmaM));
+        }
+        __syncwarp();
+        uint32_t stage = 0, phase = 0, li = 0;
+        volatile uint32_t* prog = args.progress ? args.progress + (size_t)j0 * n_qpairs : nullptr;
+        for (uint64_t i = j0; i < args.tile_count; i += g, ++li) {
+            const int32_t row_coord = (int32_t)(mma_tile_of(args, i) * kPairN + rank * kMmaN);
+            // every 8th tile (an L2 round trip per tile would eat the TMA prefetch depth): wait for
+            // the slowest pair of this tile stream
+            if (prog && li > args.lead && (li & 7u) == 0u && lane == 0) {
+                const long long t0 = clock64();
+                for (uint32_t spins = 0;; ++spins) {
+                    uint32_t slowest = 0xFFFFFFFFu;
+                    for (uint32_t q = 0; q < n_qpairs; ++q) slowest = min(slowest, prog[q]);
+                    if (slowest + args.lead >= li) break;
+                    __nanosleep(200);
+                    if ((spins & 255u) == 255u && clock64() - t0 > 8000000000ll) __trap();
+                }
+            }
+            __syncwarp();
+            for (uint32_t kb = 0; kb < args.n_kblocks; ++kb) {
+                mbar_wait(empty_bar(stage), phase ^ 1u);
+                if (elect_one()) {
+                    if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * kMmaTileBytes);
+                    tma_load_2d_pair(b_smem + stage * kMmaTileBytes, &tm_x, full_bar(stage),
+                                     (int32_t)(kb * kElems), row_coord);
+                }
+                __syncwarp();
+                if (++stage == args.n_stages) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+            if (prog && rank == 0 && lane == 0 && (li & 3u) == 3u) prog[quad] = li + 1u;
+        }
+        if (prog && rank == 0 && lane == 0) prog[quad] = 0xFFFFFFF0u;  // done: never the slowest
+    } else if (warp == 1) {
+        if (rank == 0) {
+            // ===== MMA issuer (leader CTA only) =====
+            constexpr uint32_t idesc = I8 ? umma_idesc_i8(2 * kMmaM, kPairN) : umma_idesc_f16(2 * kMmaM, kPairN);
+            const uint64_t a_desc0 = umma_desc_sw128(a_smem);
+            const uint64_t b_desc0 = umma_desc_sw128(b_smem);
+            mbar_wait(afull_bar, 0);
+            tc_fence_after();
+            uint32_t stage = 0, phase = 0, acc_phase = 0;
+            for (uint64_t i = j0; i < args.tile_count; i += g) {
+                // sub-block 0 then sub-block 1 over the SAME B stages: the epilogue of one sub-block's
+                // accumulator overlaps the MMAs of the other (one accumulator each, 2 x 256 columns)
+                const uint32_t stage0 = stage, phase0 = phase;
+                for (uint32_t sub = 0; sub < kSub; ++sub) {
+                    mbar_wait(tempty_bar(sub), acc_phase ^ 1u);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + sub * kPairN;
+                    stage = stage0;
+                    phase = phase0;
+                    for (uint32_t kb = 0; kb < args.n_kblocks; ++kb) {
+                        if (sub == 0) {
+                            mbar_wait(full_bar(stage), phase);
+                            tc_fence_after();
+                        }
+                        if (elect_one()) {
+                            const uint64_t a_desc = a_desc0 + (uint64_t)((sub * args.n_kblocks + kb) * (kMmaTileBytes >> 4));
+                            const uint64_t b_desc = b_desc0 + (uint64_t)(stage * (kMmaTileBytes >> 4));
+#pragma unroll
+                            for (uint32_t k4 = 0; k4 < 4; ++k4)
+                                umma_i8_pair(d_tmem, a_desc + 2u * k4, b_desc + 2u * k4, idesc, (kb | k4) != 0u ? 1u : 0u);
+                            if (sub + 1 == kSub) umma_commit_pair(empty_bar(stage));  // both sub-blocks have read it
+                            if (kb + 1 == args.n_kblocks) umma_commit_pair(tfull_bar(sub));
+                        }
+                        __syncwarp();
+                        if (++stage == args.n_stages) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                    }
+                }
+                acc_phase ^= 1u;
+            }
+        }
+    } else {
+        // ===== epilogue (both CTAs): TMEM lane = query of this CTA, column = row of the pair tile =====
+        const uint32_t quarter = warp & 3u;
+        const uint32_t m = quarter * 32u + lane;
+        const uint32_t half = (warp - 2u) >> 2;
+        bool live[kSub];
+        float qscale[kSub];
+        int32_t gate[kSub];
+        MmaCand* list[kSub];
+        size_t list_id[kSub];
+        uint32_t count[kSub];
+#pragma unroll
+        for (uint32_t sub = 0; sub < kSub; ++sub) {
+            const uint32_t query = qb_of(sub) * kMmaM + m;
+            live[sub] = query < args.batch && args.redo[query] == 0u;
+            gate[sub] = mma_thread_gate<true>(args, query, live[sub], &qscale[sub]);
+            list_id[sub] = (((size_t)blockIdx.x * kSub + sub) * 2u + half) * kMmaM + m;
+            list[sub] = args.cand + list_id[sub] * args.cap;
+            count[sub] = 0;
+        }
+        uint32_t acc_phase = 0;
+        for (uint64_t i = j0; i < args.tile_count; i += g) {
+            const uint64_t tile = mma_tile_of(args, i);
+#pragma unroll
+            for (uint32_t sub = 0; sub < kSub; ++sub) {
+                mbar_wait(tfull_bar(sub), acc_phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + sub * kPairN + half * (kPairN / 2);
+                if (args.dump_group_max) {
+                    mma_epilogue_dump_max<kPairN / 2, true>(args, taddr, tile * kPairN + half * (kPairN / 2), live[sub],
+                                                            qscale[sub], list[sub], count[sub]);
+                } else {
+                    mma_epilogue_tile<kPairN / 2, true>(args, taddr, tile * kPairN + half * (kPairN / 2), gate[sub],
+                                                        qscale[sub], list[sub], count[sub]);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(tempty_bar(sub), 0);  // leader may reuse this accumulator
+            }
+            acc_phase ^= 1u;
+        }
+#pragma unroll
+        for (uint32_t sub = 0; sub < kSub; ++sub) args.cand_count[list_id[sub]] = count[sub];
+    }
+
+    tc_fence_before();
+    cluster_sync_all();  // neither CTA may leave while the other can still signal it
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, 512);
+    }
+}
+
 // ─── candidate lists as the gate / refine kernels see them ──────────────────────────────────
 struct MmaLists {
     const MmaCand* cand;         // [grid][128][cap]
     const uint32_t* cand_count;  // [grid][128]
     uint32_t n_qblocks, ctas_per_qblock, cap;
-    uint32_t pair;               // 1: lists were written by mma_scan_pair_kernel
+    uint32_t pair;               // 1: lists were written by mma_scan_pair_kernel, 2: by mma_scan_quad_kernel
 };
 // Query slot b has 2*ctas_per_qblock lists (two epilogue threads per CTA).  List j lives in CTA
 // c(j/2), half j%2, where c(i) = qb + n_qblocks*i (single-CTA form) or
@@ -841,6 +1052,10 @@ struct MmaLists {
 __device__ __forceinline__ uint32_t mma_list_count(const MmaLists& l) { return 2u * l.ctas_per_qblock; }
 __device__ __forceinline__ size_t mma_list_slot(const MmaLists& l, uint32_t b, uint32_t j) {
     const uint32_t qb = b / kMmaM, i = j >> 1;
+    if (l.pair == 2u) {  // quad form: blocks (quad*2 + sub)*2 + rank, lists [cta][sub][half][128]
+        const size_t cta = 2 * ((size_t)(qb >> 2) + (size_t)(l.n_qblocks >> 2) * i) + (qb & 1u);
+        return ((cta * 2u + ((qb >> 1) & 1u)) * 2u + (j & 1u)) * kMmaM + (b % kMmaM);
+    }
     const size_t cta = l.pair ? 2 * ((size_t)(qb >> 1) + (size_t)(l.n_qblocks >> 1) * i) + (qb & 1u)
                               : (size_t)qb + (size_t)l.n_qblocks * i;
     return (cta * 2u + (j & 1u)) * kMmaM + (b % kMmaM);
