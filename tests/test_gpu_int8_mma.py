@@ -17,6 +17,10 @@ def bits(x):
 @pytest.fixture()
 def i8_env(monkeypatch):
     monkeypatch.setenv("FSGPU_MMA_I8", "1")
+    # the defaults keep the batched int8 form for k <= 16 on shards of >= 2.5 M rows (where it pays);
+    # these tests exercise it on small corpora and large k too
+    monkeypatch.setenv("FSGPU_I8_MIN_ROWS", "0")
+    monkeypatch.setenv("FSGPU_I8_MAX_K", "1024")
     yield
 
 
@@ -252,3 +256,17 @@ def test_int8_small_batches_share_one_pass(i8_env, fo, monkeypatch):
                 assert np.array_equal(rows[b, :c].astype(np.uint64), wr), (batch, k, b)
                 assert np.array_equal(bits(scores[b, :c]), bits(ws)), (batch, k, b)
     ix.close()
+
+
+def test_randomised_soak_on_the_int8_form(i8_env):
+    """tools/soak_batched.py with the int8 batched form forced on for every size and k: adversarial
+    corpora (ascending-by-score order, duplicates, extreme norms, exact ties), tombstones, filters —
+    rows, order and f32 score bits must equal the per-query path."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "soak_batched.py"), "35", "11"],
+                       capture_output=True, text=True, timeout=600, env=dict(os.environ))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "soak ok" in r.stdout
