@@ -680,11 +680,15 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
             trace.mark(lvl ? "scan1" : "scan0");
             ga.stage_cap = have_gate ? gate1_cap : gate0_cap;
             ga.keep_prev = have_gate ? 1u : 0u;
-            mma_gate_kernel<<<sub, 256, mma_stage_smem_bytes(ga.stage_cap, false), stream>>>(ga);
-            CUDA_TRY(cudaGetLastError());
-            ix->prof.other_launches += 2;
+            const bool exact_gate = i8 && lvl == 1 && env_int("FSGPU_I8_EXACT_GATE", 1) != 0;
+            if (!exact_gate) {  // (the exact gate below supersedes this level's approximate one)
+                mma_gate_kernel<<<sub, 256, mma_stage_smem_bytes(ga.stage_cap, false), stream>>>(ga);
+                CUDA_TRY(cudaGetLastError());
+                ix->prof.other_launches += 1;
+            }
+            ix->prof.other_launches += 1;
             have_gate = true;
-            if (i8 && lvl == 1 && env_int("FSGPU_I8_EXACT_GATE", 1) != 0) {
+            if (exact_gate) {
                 // int8 form: tighten the gate of the full pass with an EXACT k-th best of this sample
                 CUDA_TRY(ix->ws_i8_top.reserve((size_t)slots * k * 8));
                 CUDA_TRY(ix->ws_i8_cnt.reserve((size_t)slots * 4));
