@@ -355,7 +355,13 @@ def run_ours(a):
                 # is in MEASURED_PEAKS.json); ops = 2 per int8 multiply-add
                 peak_tf, peak_tf_sus = 2.0 * peak_tf, 2.0 * peak_tf_sus
                 peak_src += "; int8 tensor peak = 2 x measured bf16"
-                traffic = None  # the stored traffic figure belongs to the f16 form
+                traffic = None  # the figure read above belongs to the f16 form
+                tp8 = os.path.join(ROOT, "profiles", "scan_kernel_traffic_i8.json")
+                if os.path.exists(tp8):
+                    try:
+                        traffic = json.load(open(tp8)).get("dram_bytes_per_launch")
+                    except (OSError, ValueError):
+                        traffic = None
             roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                         "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic,
                         "kernel": ("mma_scan_pair_kernel<int8> (tcgen05.mma.cta_group::2 kind::i8, M=256 queries x N=256 "
