@@ -542,11 +542,11 @@ static MmaCascade plan_cascade(uint64_t n_rows, uint32_t k, uint32_t tile_rows) 
 static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint32_t batch, uint32_t k,
                              uint64_t* d_out_keys, fsgpu_hit* d_out_hits, uint32_t* d_out_counts,
                              cudaStream_t stream, bool allow_i8 = true) {
-    // the int8 form pays while the candidate volume stays small (k <= 16: top-20/30 are erratic, top-50
-    // loses) and the pass is long enough to amortise its extra refine step (>= 2.5 M rows: at 1.25 M
-    // rows it breaks even) — profiles/r01_sweep_i8_form.txt
+    // the int8 form pays while the candidate volume stays small (k <= 32: top-50 loses) and the pass is
+    // long enough to amortise its extra refine step (>= 2.5 M rows: at 1.25 M rows it breaks even) —
+    // profiles/r01_sweep_i8_form.txt
     const bool i8 = allow_i8 && ix->i8_ok && env_int("FSGPU_MMA_I8", 1) != 0 &&
-                    k <= (uint32_t)std::max(0, env_int("FSGPU_I8_MAX_K", 16)) &&
+                    k <= (uint32_t)std::max(0, env_int("FSGPU_I8_MAX_K", 32)) &&
                     ix->n_rows >= (uint64_t)std::max(0, env_int("FSGPU_I8_MIN_ROWS", 2500000));
     const uint32_t n_kb = ix->dim / (i8 ? 128 : kMmaKBlock);  // 128-byte K-blocks
     const size_t smem_limit = 227 * 1024;

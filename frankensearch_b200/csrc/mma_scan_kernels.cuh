@@ -1068,7 +1068,7 @@ __device__ __forceinline__ size_t mma_list_slot(const MmaLists& l, uint32_t b, u
 // and the entries are flattened into shared memory once.
 constexpr uint32_t kMmaMaxLists = 2 * 160;      // >= 2 * SM count
 constexpr uint32_t kMmaStageScores = 16384;     // gate kernel: ordered scores only (64 KiB)
-constexpr uint32_t kMmaStagePairs = 8192;       // refine kernel: ordered score + row (64 KiB)
+constexpr uint32_t kMmaStagePairs = 16384;      // refine kernel: ordered score + row (128 KiB); <= 64 * 256 (flag word)
 
 struct MmaStageSmem {
     uint32_t* hist;   // [256]
@@ -1352,7 +1352,7 @@ __global__ void __launch_bounds__(256) mma_refine_kernel(const MmaRefineArgs arg
     __syncthreads();
     if (staged) {
         // (a) gather the rows of the band into a dense list (it reuses the score array: every thread
-        //     first folds the pass flags of its <= 32 entries into a register), (b) spread the exact
+        //     first folds the pass flags of its <= 64 entries into a register), (b) spread the exact
         //     dots evenly over the warps — no barrier per 256 entries, no warp idling while another
         //     re-scores (the first version spent half its time at those barriers).
         // Round 1: the approximate top-k (score >= tau_a) are re-scored first.  The k-th best of
@@ -1378,14 +1378,14 @@ __global__ void __launch_bounds__(256) mma_refine_kernel(const MmaRefineArgs arg
             }
             __syncthreads();
         }
-        uint32_t mine = 0;
+        uint64_t mine = 0;  // <= kMmaStagePairs / 256 = 64 entries per thread
         for (uint32_t r = 0, i = threadIdx.x; i < total; ++r, i += step)
-            if (sm.score[i] >= lo_u && sm.score[i] < top_u) mine |= 1u << r;
+            if (sm.score[i] >= lo_u && sm.score[i] < top_u) mine |= 1ull << r;
         if (threadIdx.x == 0) sm.ctl[2] = 0u;
         __syncthreads();
         uint32_t* band = sm.score;
         for (uint32_t r = 0, i = threadIdx.x; i < total; ++r, i += step)
-            if (mine & (1u << r)) band[atomicAdd(&sm.ctl[2], 1u)] = sm.row[i];
+            if (mine & (1ull << r)) band[atomicAdd(&sm.ctl[2], 1u)] = sm.row[i];
         __syncthreads();
         const uint32_t n_band = sm.ctl[2];
         const uint32_t warp = threadIdx.x >> 5, n_warps = step >> 5;
