@@ -1,4 +1,4 @@
-"""int8 form of the batched scan (tcgen05.mma kind::i8, FSGPU_MMA_I8=1): corpus codes equal the
+"""int8 forms of the scan (tcgen05.mma kind::i8 batches, dp4a single-query pass 1): corpus codes equal the
 reference's quantiser byte for byte, and search results stay EXACT — identical rows and score bits
 to the per-query path and the oracle — because the int8 score only selects a candidate superset
 under a proven error bound (mma_scan_kernels.cuh) and winners are re-scored in f16."""

@@ -1,5 +1,5 @@
 """Single-query latency through the host API (pinned-free numpy query in, hits out), f16 scan vs
-the int8 pass-1 form.  FSGPU_MMA_I8=1 python tools/bench_single_query.py [rows] [dim] [k]"""
+the int8 pass-1 form.  python tools/bench_single_query.py [rows] [dim] [k] [batch]"""
 import os
 import sys
 import time
