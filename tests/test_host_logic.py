@@ -194,3 +194,95 @@ def test_kendall_tau_matches_naive_for_deterministic_permutations():
             disc = sum(1 for i in range(n) for j in range(i + 1, n) if ranks[i] > ranks[j])
             total = n * (n - 1) // 2
             assert kendall_tau(initial, refined) == ((total - disc) - disc) / total
+
+
+# ── host half of the WAL / soft-delete / filter path (frankensearch_b200/index.py) on the CPU ─
+class _CpuWalIndex:
+    """GpuVectorIndex over tests/fake_lib.py behind the scenario interface of tests/wal_model.py."""
+
+    def __init__(self, doc_ids, vectors, dim):
+        from fake_lib import make_cpu_index
+
+        self.ix = make_cpu_index(doc_ids, vectors, dim)
+
+    def append(self, d, v):
+        self.ix.append(d, v)
+
+    def append_batch(self, e):
+        self.ix.append_batch(e)
+
+    def soft_delete(self, d):
+        return self.ix.soft_delete(d)
+
+    def wal_record_count(self):
+        return self.ix.wal_record_count()
+
+    def search_top_k(self, query, k, filter_ids=None):
+        f = None if filter_ids is None else (lambda d, ids=set(filter_ids): d in ids)
+        return [(h.index, np.float32(h.score), h.doc_id) for h in self.ix.search_top_k(query, k, filter=f)]
+
+
+def _wal_scenarios():
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import ref_cases as rc
+
+    return rc.WAL_SCENARIOS
+
+
+@pytest.mark.parametrize("scenario", _wal_scenarios(), ids=[s["name"] for s in _wal_scenarios()])
+def test_index_host_logic_replays_the_reference_wal_tests(scenario):
+    """The reference's own WAL / filter / soft-delete tests (tests/ref_cases.py WAL_SCENARIOS) through
+    the product's host code — append dedup and supersede, tombstoning of replaced main rows, filter
+    -> allow bitmap incl. the WAL bits, doc-id resolve with shadowing — with the device calls served
+    by the CPU oracle (tests/fake_lib.py).  Hits must also equal the oracle model's, bit for bit."""
+    from wal_model import OracleWalIndex, run_scenario
+
+    got, want = [], []
+    run_scenario(lambda ids, vecs, dim: _CpuWalIndex(ids, vecs, dim), scenario, on_search=lambda s, h: got.append(h))
+    run_scenario(lambda ids, vecs, dim: OracleWalIndex(ids, vecs, dim), scenario, on_search=lambda s, h: want.append(h))
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert [(r, d) for r, _, d in g] == [(r, d) for r, _, d in w]
+        assert np.array_equal(np.array([s for _, s, _ in g], dtype=np.float32).view(np.uint32),
+                              np.array([s for _, s, _ in w], dtype=np.float32).view(np.uint32))
+
+
+def test_index_host_logic_append_validation_and_bookkeeping():
+    """append_batch_impl (lib.rs:2581-2720) and soft_delete_batch (lib.rs:2314-2396) on the host:
+    validation order and error kinds, last-entry-wins inside a batch, superseding resident rows,
+    tombstones pushed to the device exactly when they change, WAL rows numbered after the slab."""
+    from fake_lib import make_cpu_index
+    from frankensearch_b200 import SearchError
+
+    ids = [f"doc-{i}" for i in range(6)]
+    vec = np.eye(6, 4, dtype=np.float32) + 0.1
+    ix = make_cpu_index(ids, vec, 4)
+    lib = ix._L
+    for bad, kind in (([1.0, 0.0], "DimensionMismatch"), ([float("nan"), 0, 0, 0], "InvalidConfig"),
+                      ([0.0, 0.0, 0.0, 0.0], "InvalidConfig"), ([float("inf"), 0, 0, 0], "InvalidConfig")):
+        with pytest.raises(SearchError) as e:
+            ix.append_batch([("ok", [1.0, 0, 0, 0]), ("bad", bad)])  # nothing is admitted when one entry is bad
+        assert e.value.kind == kind
+    assert ix.wal_record_count() == 0 and lib.calls == []
+    ix.append_batch([("new-a", [1, 0, 0, 0]), ("doc-2", [0, 1, 0, 0]), ("new-a", [0, 0, 1, 0])])
+    assert [d for d, _ in ix.wal_records()] == ["doc-2", "new-a"]            # last entry of new-a, batch order kept
+    assert np.array_equal(ix.wal_records()[1][1], np.array([0, 0, 1, 0], dtype=np.float32))
+    assert lib.calls == [("set_wal", 2, 6), "set_tombstones"] and lib.tomb.tolist() == [False, False, True, False, False, False]
+    assert ix.is_deleted(2) and not ix.is_deleted(3)
+    ix.append("new-a", [0, 0, 0, 2])                                          # supersedes the resident row
+    assert [d for d, _ in ix.wal_records()] == ["doc-2", "new-a"] and lib.calls[-1] == ("set_wal", 2, 6)
+    assert ix.doc_id_at(6) == "doc-2" and ix.doc_id_at(7) == "new-a" and ix.doc_id_at(1) == "doc-1"
+    hits = ix.search_top_k([0.0, 0.0, 0.0, 1.0], 3)
+    assert hits[0].doc_id == "new-a" and hits[0].index == 7                   # record_count + wal_idx
+    assert ix.soft_delete_batch(["doc-2", "doc-3", "missing"]) == 2           # doc-2: WAL row (main already dead), doc-3: main
+    assert ix.wal_record_count() == 1 and lib.tomb.tolist() == [False, False, True, True, False, False]
+    assert ix.soft_delete("doc-3") is False                                   # already tombstoned
+    n_calls = len(lib.calls)
+    assert ix.soft_delete("nobody") is False and len(lib.calls) == n_calls    # nothing changed, nothing uploaded
+    # a boolean-array filter over the main rows is extended with "allowed" for the WAL rows
+    mask = np.zeros(6, dtype=bool)
+    mask[0] = True
+    got = [h.doc_id for h in ix.search_top_k([1.0, 1.0, 1.0, 1.0], 10, filter=mask)]
+    assert sorted(got) == ["doc-0", "new-a"]
+    ix.close()
+    assert lib.calls[-1] == "destroy"
