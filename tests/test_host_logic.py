@@ -286,3 +286,25 @@ def test_index_host_logic_append_validation_and_bookkeeping():
     assert sorted(got) == ["doc-0", "new-a"]
     ix.close()
     assert lib.calls[-1] == "destroy"
+
+
+def test_bitset_and_predicate_filters_follow_the_reference_seam(fo):
+    """BitsetFilter / PredicateFilter (crates/frankensearch-core/src/filter.rs:330-383 and its tests):
+    a bitset filter decides on the FNV-1a hash of the doc id alone and can enumerate its hashes (the
+    gather arm needs that); a predicate filter decides on the doc id and cannot."""
+    from frankensearch_b200 import BitsetFilter, PredicateFilter
+
+    ids = ["doc-a", "doc-b", "ünïcode-id", ""]
+    f = BitsetFilter.from_doc_ids(ids[:2])
+    assert f.matches("doc-a") and f.matches("doc-b") and not f.matches("doc-c") and not f.matches("")
+    assert f.candidate_hashes() == frozenset(fo.fnv1a64(d.encode("utf-8")) for d in ids[:2])
+    for d in ids:
+        h = fo.fnv1a64(d.encode("utf-8"))
+        assert fnv1a_hash(d.encode("utf-8")) == h                      # host hash == oracle hash (lib.rs:6120-6127)
+        assert f.matches_doc_id_hash(h) == (d in ids[:2])              # Some(set.contains(hash))
+    g = BitsetFilter.from_hashes(f.candidate_hashes())
+    assert g.matches("doc-a") and not g.matches("nope") and g.name == "bitset_filter"
+    assert BitsetFilter.from_doc_ids([]).candidate_hashes() == frozenset()
+    p = PredicateFilter("only-b", lambda d: d == "doc-b")
+    assert p.matches("doc-b") and not p.matches("doc-a") and p("doc-b") and p.name == "only-b"
+    assert p.matches_doc_id_hash(123) is None and p.candidate_hashes() is None
