@@ -25,6 +25,9 @@ STATUS_NAMES = {
 }
 
 
+ABI_VERSION = 2  # FSGPU_ABI_VERSION of include/fsgpu.h this binding was written against
+
+
 class SearchError(Exception):
     """Mirror of `SearchError` (crates/frankensearch-core/src/error.rs:12)."""
 

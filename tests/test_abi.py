@@ -86,3 +86,19 @@ def test_rust_binding_source_lists_every_hot_path_symbol():
     for must in ("fsgpu_search_top_k", "fsgpu_search_top_k_filtered", "fsgpu_scores_for_rows", "fsgpu_rrf_fuse",
                  "fsgpu_blend_two_tier", "fsgpu_potion_embed", "fsgpu_minilm_embed", "fsgpu_index_open_fsvi"):
         assert must in bound, must
+
+
+def test_graft_entry_build_passes():
+    """`__graft_entry__.build()` is what the driver runs on the CPU box every round: the (incremental)
+    nvcc + gcc build must succeed and its own ABI check must agree with the library."""
+    import importlib
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    entry = importlib.import_module("__graft_entry__")
+    entry.build()
+    from frankensearch_b200 import _ffi
+
+    assert _ffi.lib().fsgpu_abi_version() == _ffi.ABI_VERSION
