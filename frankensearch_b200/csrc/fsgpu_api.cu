@@ -543,11 +543,11 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
                              uint64_t* d_out_keys, fsgpu_hit* d_out_hits, uint32_t* d_out_counts,
                              cudaStream_t stream, bool allow_i8 = true) {
     // the int8 form pays while the candidate volume stays small (k <= 32: top-50 loses) and the pass is
-    // long enough to amortise its extra refine step (>= 2.5 M rows: at 1.25 M rows it breaks even) —
-    // profiles/r01_sweep_i8_form.txt
+    // long enough to amortise its extra refine step (>= 1 M rows: at 1.25 M rows it is 5 % ahead, 0.82 vs
+    // 0.87 ms at batch 1024) — profiles/r01_sweep_i8_form.txt
     const bool i8 = allow_i8 && ix->i8_ok && env_int("FSGPU_MMA_I8", 1) != 0 &&
                     k <= (uint32_t)std::max(0, env_int("FSGPU_I8_MAX_K", 32)) &&
-                    ix->n_rows >= (uint64_t)std::max(0, env_int("FSGPU_I8_MIN_ROWS", 2500000));
+                    ix->n_rows >= (uint64_t)std::max(0, env_int("FSGPU_I8_MIN_ROWS", 1000000));
     const uint32_t n_kb = ix->dim / (i8 ? 128 : kMmaKBlock);  // 128-byte K-blocks
     const size_t smem_limit = 227 * 1024;
     // quad form (int8, more than 256 queries): two query blocks per CTA share every B stage

@@ -128,7 +128,7 @@ int fsgpu_index_set_tombstones(fsgpu_index* index, const uint8_t* bitmap_or_null
  * environment switch FSGPU_MMA_I8=0 turns them off at creation or per search).  The index also holds the corpus as int8 codes made by
  * the reference's corpus-wide quantiser (quantize_f16_slab_to_i8, crates/frankensearch-index/src/
  * simd.rs:1842-1859: scale = 127 / max|x|, code = clamp(round(x * scale), -127, 127)); batches with
- * k <= 32 (shards of >= 2.5 M rows) run on tcgen05.mma kind::i8 — half the bytes and twice the MMA rate — and one or two
+ * k <= 32 (shards of >= 1 M rows) run on tcgen05.mma kind::i8 — half the bytes and twice the MMA rate — and one or two
  * queries through the host API take a dp4a pass over the codes.  Results are unchanged (exact):
  * the int8 score only selects a candidate superset under a proven error bound, the winners are
  * re-scored with the reference's f16 arithmetic.  `fsgpu_index_read_codes_i8` copies codes back
