@@ -25,7 +25,7 @@ STATUS_NAMES = {
 }
 
 
-ABI_VERSION = 2  # FSGPU_ABI_VERSION of include/fsgpu.h this binding was written against
+ABI_VERSION = 3  # FSGPU_ABI_VERSION of include/fsgpu.h this binding was written against
 
 
 class SearchError(Exception):
@@ -113,7 +113,8 @@ EXPORTS = [
     "fsgpu_search_top_k_filtered", "fsgpu_search_top_k_filtered_device",
     "fsgpu_index_set_doc_hashes", "fsgpu_search_top_k_hashes",
     "fsgpu_merge_top_k_device", "fsgpu_merge_top_k_hits_device", "fsgpu_scores_for_rows", "fsgpu_scores_for_rows_device",
-    "fsgpu_rrf_fuse", "fsgpu_rrf_fuse_device", "fsgpu_blend_two_tier", "fsgpu_potion_create",
+    "fsgpu_scores_for_hits_device", "fsgpu_merge_payload_device",
+    "fsgpu_rrf_fuse", "fsgpu_rrf_fuse_device", "fsgpu_blend_two_tier", "fsgpu_blend_two_tier_device", "fsgpu_potion_create",
     "fsgpu_potion_destroy", "fsgpu_potion_embed", "fsgpu_potion_embed_device",
     "fsgpu_synth_rows_device",
     "fsgpu_minilm_create", "fsgpu_minilm_destroy", "fsgpu_minilm_embed", "fsgpu_minilm_embed_device",
@@ -186,6 +187,11 @@ def lib() -> C.CDLL:
                                         _vp, _vp]
     L.fsgpu_blend_two_tier.argtypes = [C.c_int, C.c_float, _vp, _vp, _vp, C.c_uint32, _vp, _vp, _vp, _vp,
                                        C.c_uint32, _vp, C.POINTER(C.c_uint32)]
+    L.fsgpu_blend_two_tier_device.argtypes = [C.c_int, C.c_float, C.c_uint32, _vp, _vp, _vp, C.c_uint32, _vp, _vp, _vp,
+                                              _vp, _vp, C.c_uint32, _vp, _vp, _vp]
+    L.fsgpu_scores_for_hits_device.argtypes = [_vp, _vp, C.c_uint32, _vp, C.c_uint32, _vp, _vp, _vp]
+    L.fsgpu_merge_payload_device.argtypes = [C.c_int, _vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64,
+                                             C.c_uint64, C.c_uint64, C.c_uint64, _vp, C.c_uint32, _vp, _vp, _vp]
     L.fsgpu_potion_create.argtypes = [_vp, C.c_uint64, C.c_uint32, C.c_int, C.POINTER(_vp)]
     L.fsgpu_potion_destroy.argtypes = [_vp]
     L.fsgpu_potion_destroy.restype = None

@@ -1627,8 +1627,45 @@ extern "C" int fsgpu_scores_for_rows_device(const fsgpu_index* ix, const float* 
     cudaStream_t s = stream ? (cudaStream_t)stream : ix->stream;
     dim3 grid((n_per_query + kScanWarps - 1) / kScanWarps, batch);
     scores_for_rows_kernel<<<grid, kScanThreads, 0, s>>>(ix->d_slab, ix->n_rows, ix->row_base, ix->dim,
-                                                         d_queries, d_rows, n_per_query, ix->reduce_order,
+                                                         d_queries, d_rows, 1u, n_per_query, ix->reduce_order,
                                                          ix->tail_fma, d_out_scores, d_out_present);
+    CUDA_TRY(cudaGetLastError());
+    if (!stream) CUDA_TRY(cudaStreamSynchronize(s));
+    return FSGPU_OK;
+}
+
+extern "C" int fsgpu_scores_for_hits_device(const fsgpu_index* ix, const float* d_queries, uint32_t batch,
+                                            const fsgpu_hit* d_hits, uint32_t n_per_query, float* d_out_scores,
+                                            uint8_t* d_out_present, void* stream) {
+    if (!ix) return fail(FSGPU_ERR_INVALID_CONFIG, "index is NULL");
+    if (batch == 0 || n_per_query == 0) return FSGPU_OK;
+    if (!d_queries || !d_hits || !d_out_scores) return fail(FSGPU_ERR_INVALID_CONFIG, "NULL argument");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t s = stream ? (cudaStream_t)stream : ix->stream;
+    dim3 grid((n_per_query + kScanWarps - 1) / kScanWarps, batch);
+    // the row of hit i is word 2i of the record array
+    scores_for_rows_kernel<<<grid, kScanThreads, 0, s>>>(ix->d_slab, ix->n_rows, ix->row_base, ix->dim, d_queries,
+                                                         reinterpret_cast<const uint32_t*>(d_hits), 2u, n_per_query,
+                                                         ix->reduce_order, ix->tail_fma, d_out_scores, d_out_present);
+    CUDA_TRY(cudaGetLastError());
+    if (!stream) CUDA_TRY(cudaStreamSynchronize(s));
+    return FSGPU_OK;
+}
+
+extern "C" int fsgpu_merge_payload_device(int device, const uint64_t* d_keys, const float* d_payload, uint32_t batch,
+                                          uint32_t n_lists, uint32_t k_in, uint64_t list_stride, uint64_t query_stride,
+                                          uint64_t payload_list_stride, uint64_t payload_query_stride,
+                                          const uint64_t* d_merged_keys, uint32_t k_out, float* d_out_payload,
+                                          uint8_t* d_out_present, void* stream) {
+    if (batch == 0 || k_out == 0) return FSGPU_OK;
+    if (!d_keys || !d_payload || !d_merged_keys || !d_out_payload) return fail(FSGPU_ERR_INVALID_CONFIG, "NULL argument");
+    DeviceGuard g(device);
+    cudaStream_t s = (cudaStream_t)stream;
+    dim3 grid((k_out + 255) / 256, batch);
+    merge_payload_kernel<<<grid, 256, 0, s>>>(d_keys, list_stride, query_stride, n_lists, k_in, d_payload,
+                                              payload_list_stride, payload_query_stride, d_merged_keys, k_out,
+                                              d_out_payload, d_out_present);
     CUDA_TRY(cudaGetLastError());
     if (!stream) CUDA_TRY(cudaStreamSynchronize(s));
     return FSGPU_OK;
@@ -1654,7 +1691,7 @@ extern "C" int fsgpu_scores_for_rows(const fsgpu_index* ix, const float* query, 
         dim3 grid((n + kScanWarps - 1) / kScanWarps, 1);
         scores_for_rows_kernel<<<grid, kScanThreads, 0, s>>>(
             ix->d_slab, ix->n_rows, ix->row_base, ix->dim, ix->ws_queries.as<float>(),
-            ix->ws_rows.as<uint32_t>(), n, ix->reduce_order, ix->tail_fma, ix->ws_scores.as<float>(),
+            ix->ws_rows.as<uint32_t>(), 1u, n, ix->reduce_order, ix->tail_fma, ix->ws_scores.as<float>(),
             ix->ws_present.as<uint8_t>());
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaMemcpyAsync(out_scores, ix->ws_scores.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));

@@ -125,6 +125,64 @@ extern "C" int fsgpu_rrf_fuse(int device, const fsgpu_rrf_config* config, uint32
     return FSGPU_OK;
 }
 
+static float sanitize_alpha(float blend_factor) {  // blend.rs:518-524
+    float alpha = blend_factor;
+    if (!std::isfinite(alpha)) alpha = 0.7f;
+    return std::min(1.0f, std::max(0.0f, alpha));
+}
+
+static int launch_blend(const BlendArgs& a, uint32_t batch, cudaStream_t s) {
+    const uint32_t m = a.n_fast_max + (a.union_form ? a.n_quality_max : 0);
+    if (m > kFusionMaxEntries)
+        return fail(FSGPU_ERR_INVALID_CONFIG, "blend: %u hits exceed the device window of %u", m, kFusionMaxEntries);
+    const size_t smem = (size_t)host_next_pow2(std::max(m, 1u)) * 20 + 16;
+    CUDA_TRY(cudaFuncSetAttribute(blend_two_tier_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    blend_two_tier_kernel<<<batch, kFusionThreads, smem, s>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    return FSGPU_OK;
+}
+
+extern "C" int fsgpu_blend_two_tier_device(int device, float blend_factor, uint32_t batch,
+                                           const fsgpu_hit* d_fast_hits, const uint32_t* d_fast_tie,
+                                           const uint32_t* d_fast_counts, uint32_t n_fast_max,
+                                           const fsgpu_hit* d_quality_hits, const float* d_quality_scores,
+                                           const uint8_t* d_quality_present, const uint32_t* d_quality_tie,
+                                           const uint32_t* d_quality_counts, uint32_t n_quality_max,
+                                           fsgpu_hit* d_out, uint32_t* d_out_counts, void* stream) {
+    if (batch == 0) return FSGPU_OK;
+    if (!d_out || !d_out_counts) return fail(FSGPU_ERR_INVALID_CONFIG, "blend: output is NULL");
+    if (n_fast_max && !d_fast_hits) return fail(FSGPU_ERR_INVALID_CONFIG, "blend: fast hits is NULL");
+    const bool union_form = d_quality_hits != nullptr;
+    if (!union_form && n_fast_max && !d_quality_scores)
+        return fail(FSGPU_ERR_INVALID_CONFIG, "blend: aligned form needs quality scores (or a retrieved quality list)");
+    DeviceGuard g(device);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n_fast_max + (union_form ? n_quality_max : 0) == 0) {
+        CUDA_TRY(cudaMemsetAsync(d_out_counts, 0, (size_t)batch * 4, s));
+        return FSGPU_OK;
+    }
+    BlendArgs a{};
+    a.alpha = sanitize_alpha(blend_factor);
+    a.fast_hits = d_fast_hits;
+    a.fast_tie = d_fast_tie;
+    a.fast_counts = d_fast_counts;
+    a.n_fast_max = n_fast_max;
+    a.union_form = union_form ? 1u : 0u;
+    a.quality_hits = d_quality_hits;
+    a.quality_scores = d_quality_scores;
+    a.quality_present = d_quality_present;
+    a.quality_tie = d_quality_tie;
+    a.quality_counts = d_quality_counts;
+    a.n_quality_max = union_form ? n_quality_max : n_fast_max;
+    a.out = d_out;
+    a.out_stride = n_fast_max + (union_form ? n_quality_max : 0);
+    a.out_counts = d_out_counts;
+    int rc = launch_blend(a, batch, s);
+    if (rc) return rc;
+    if (!stream) CUDA_TRY(cudaStreamSynchronize(s));
+    return FSGPU_OK;
+}
+
 extern "C" int fsgpu_blend_two_tier(int device, float blend_factor, const uint32_t* fast_rows,
                                     const float* fast_scores, const uint32_t* fast_tie, uint32_t n_fast,
                                     const uint32_t* quality_rows, const float* quality_scores,
@@ -148,10 +206,7 @@ extern "C" int fsgpu_blend_two_tier(int device, float blend_factor, const uint32
     DeviceGuard g(device);
     Staging st;
     BlendArgs a{};
-    float alpha = blend_factor;  // blend.rs:518-524
-    if (!std::isfinite(alpha)) alpha = 0.7f;
-    alpha = std::min(1.0f, std::max(0.0f, alpha));
-    a.alpha = alpha;
+    a.alpha = sanitize_alpha(blend_factor);
     uint32_t *d_fr, *d_ft, *d_qr, *d_qt; float *d_fs, *d_qs; uint8_t* d_qp; fsgpu_hit* d_out; uint32_t* d_cnt;
     std::vector<uint8_t> none;
     const uint32_t nq_eff = union_form ? n_quality : n_fast;
@@ -173,14 +228,13 @@ extern "C" int fsgpu_blend_two_tier(int device, float blend_factor, const uint32
     CUDA_TRY(st.up(quality_tie, union_form ? n_quality : 0, &d_qt));
     CUDA_TRY(st.alloc(m, &d_out));
     CUDA_TRY(st.alloc(1, &d_cnt));
-    a.fast_rows = d_fr; a.fast_scores = d_fs; a.fast_tie = d_ft; a.n_fast = n_fast;
+    a.fast_rows = d_fr; a.fast_scores = d_fs; a.fast_tie = d_ft; a.n_fast_max = n_fast;
+    a.union_form = union_form ? 1u : 0u;
     a.quality_rows = d_qr; a.quality_scores = d_qs; a.quality_present = d_qp; a.quality_tie = d_qt;
-    a.n_quality = nq_eff;
-    a.out = d_out; a.out_count = d_cnt;
-    const size_t smem = (size_t)host_next_pow2(m) * 20 + 16;
-    CUDA_TRY(cudaFuncSetAttribute(blend_two_tier_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    blend_two_tier_kernel<<<1, kFusionThreads, smem>>>(a);
-    CUDA_TRY(cudaGetLastError());
+    a.n_quality_max = nq_eff;
+    a.out = d_out; a.out_stride = m; a.out_counts = d_cnt;
+    rc = launch_blend(a, 1, nullptr);
+    if (rc) return rc;
     uint32_t cnt = 0;
     CUDA_TRY(cudaMemcpy(&cnt, d_cnt, 4, cudaMemcpyDeviceToHost));
     CUDA_TRY(cudaMemcpy(out, d_out, (size_t)cnt * sizeof(fsgpu_hit), cudaMemcpyDeviceToHost));

@@ -220,19 +220,28 @@ __global__ void __launch_bounds__(kFusionThreads) rrf_fuse_kernel(const RrfArgs 
 }
 
 // ─── blend ──────────────────────────────────────────────────────────────────────────────────
+// One CTA per query.  Every list is [batch, n_*_max] row-major; `*_counts[b]` (nullable = full) is
+// the filled prefix of query b's list.  Rows and scores come either from fsgpu_hit records
+// (`fast_hits`, `quality_hits`: what the device searches emit) or from split arrays.
 struct BlendArgs {
     float alpha;                 // sanitised (blend.rs:518-524)
-    const uint32_t* fast_rows;   // [n_fast]
+    const fsgpu_hit_t* fast_hits;   // [batch, n_fast_max] — either this ...
+    const uint32_t* fast_rows;      // ... or split arrays
     const float* fast_scores;
     const uint32_t* fast_tie;    // nullable
-    uint32_t n_fast;
-    const uint32_t* quality_rows;     // union form, else nullptr
-    const float* quality_scores;      // [n_quality] (aligned form: n_quality == n_fast)
+    const uint32_t* fast_counts; // nullable
+    uint32_t n_fast_max;
+    uint32_t union_form;              // 1: a separately retrieved quality list, joined by row
+    const fsgpu_hit_t* quality_hits;  // union form: [batch, n_quality_max] — either this ...
+    const uint32_t* quality_rows;     // ... or split arrays
+    const float* quality_scores;      // aligned form: [batch, n_fast_max], slot i belongs to fast hit i
     const uint8_t* quality_present;   // aligned form (nullable = all present)
     const uint32_t* quality_tie;      // union form, nullable
-    uint32_t n_quality;
-    fsgpu_hit_t* out;
-    uint32_t* out_count;
+    const uint32_t* quality_counts;   // union form, nullable
+    uint32_t n_quality_max;
+    fsgpu_hit_t* out;            // [batch, out_stride]
+    uint32_t out_stride;
+    uint32_t* out_counts;        // [batch]
 };
 
 __device__ __forceinline__ float block_min(float v, float* scratch, bool is_max) {
@@ -261,12 +270,13 @@ struct NormBounds {  // blend.rs:35-77
     }
 };
 
-__device__ __forceinline__ NormBounds fit_bounds(const float* s, const uint8_t* present, uint32_t n,
+template <class ScoreAt>
+__device__ __forceinline__ NormBounds fit_bounds(ScoreAt score_at, const uint8_t* present, uint32_t n,
                                                  float* scratch) {
     float mn = INFINITY, mx = -INFINITY;
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
         if (present && !present[i]) continue;
-        const float v = s[i];
+        const float v = score_at(i);
         if (isfinite(v)) {
             mn = fminf(mn, v);
             mx = fmaxf(mx, v);
@@ -285,24 +295,40 @@ __global__ void __launch_bounds__(kFusionThreads) blend_two_tier_kernel(const Bl
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ float scratch[kFusionThreads / 32];
     __shared__ uint32_t n_rec;
-    const bool union_form = args.quality_rows != nullptr;
-    const uint32_t n_fast = args.n_fast, n_q = union_form ? args.n_quality : 0;
+    const uint32_t b = blockIdx.x;
+    const bool union_form = args.union_form != 0;
+    const uint32_t n_fast = min(args.fast_counts ? args.fast_counts[b] : args.n_fast_max, args.n_fast_max);
+    const uint32_t n_q = union_form ? min(args.quality_counts ? args.quality_counts[b] : args.n_quality_max,
+                                          args.n_quality_max)
+                                    : 0;
     const uint32_t m = n_fast + n_q;
+    // the carve-up must not depend on the query: sized for the widest possible list
+    const uint32_t m2_max = next_pow2(max(args.n_fast_max + (union_form ? args.n_quality_max : 0), 1u));
     const uint32_t m2 = next_pow2(max(m, 1u));
     uint64_t* hi = reinterpret_cast<uint64_t*>(smem_raw);
-    uint64_t* lo = hi + m2;
-    uint32_t* pay = reinterpret_cast<uint32_t*>(lo + m2);
+    uint64_t* lo = hi + m2_max;
+    uint32_t* pay = reinterpret_cast<uint32_t*>(lo + m2_max);
 
-    const NormBounds fb = fit_bounds(args.fast_scores, nullptr, n_fast, scratch);
-    const NormBounds qb = fit_bounds(args.quality_scores, union_form ? nullptr : args.quality_present,
-                                     union_form ? n_q : n_fast, scratch);
+    const size_t f0 = (size_t)b * args.n_fast_max, q0 = (size_t)b * (union_form ? args.n_quality_max : args.n_fast_max);
+    auto fast_row = [&](uint32_t i) -> uint32_t { return args.fast_hits ? args.fast_hits[f0 + i].row : args.fast_rows[f0 + i]; };
+    auto fast_score = [&](uint32_t i) -> float { return args.fast_hits ? args.fast_hits[f0 + i].score : args.fast_scores[f0 + i]; };
+    auto q_row = [&](uint32_t i) -> uint32_t { return args.quality_hits ? args.quality_hits[q0 + i].row : args.quality_rows[q0 + i]; };
+    auto q_score = [&](uint32_t i) -> float {
+        return (union_form && args.quality_hits) ? args.quality_hits[q0 + i].score : args.quality_scores[q0 + i];
+    };
+    const uint8_t* q_present = (!union_form && args.quality_present) ? args.quality_present + q0 : nullptr;
+    const uint32_t* fast_tie = args.fast_tie ? args.fast_tie + f0 : nullptr;
+    const uint32_t* quality_tie = (union_form && args.quality_tie) ? args.quality_tie + q0 : nullptr;
+
+    const NormBounds fb = fit_bounds(fast_score, nullptr, n_fast, scratch);
+    const NormBounds qb = fit_bounds(q_score, q_present, union_form ? n_q : n_fast, scratch);
     // join by row: (row, source, position); fast entries first within a row
     for (uint32_t i = threadIdx.x; i < m2; i += blockDim.x) {
         uint64_t key = ~0ull;
         if (i < n_fast)
-            key = ((uint64_t)args.fast_rows[i] << 24) | i;
+            key = ((uint64_t)fast_row(i) << 24) | i;
         else if (i < m)
-            key = ((uint64_t)args.quality_rows[i - n_fast] << 24) | (1ull << 23) | (i - n_fast);
+            key = ((uint64_t)q_row(i - n_fast) << 24) | (1ull << 23) | (i - n_fast);
         hi[i] = key;
         lo[i] = 0;
         pay[i] = 0;
@@ -325,30 +351,30 @@ __global__ void __launch_bounds__(kFusionThreads) blend_two_tier_kernel(const Bl
         float f = 0.0f, q = 0.0f;
         uint32_t tie;
         if (has_fast) {
-            f = fb.apply(args.fast_scores[pos]);
-            tie = args.fast_tie ? args.fast_tie[pos] : (uint32_t)row;
+            f = fb.apply(fast_score(pos));
+            tie = fast_tie ? fast_tie[pos] : (uint32_t)row;
             if (union_form) {
                 uint32_t j = i + 1;
                 while (j < m && (hi[j] >> 24) == row && !((hi[j] >> 23) & 1)) ++j;
                 if (j < m && (hi[j] >> 24) == row) {
                     has_q = true;
-                    q = qb.apply(args.quality_scores[(uint32_t)(hi[j] & 0x7FFFFFu)]);
+                    q = qb.apply(q_score((uint32_t)(hi[j] & 0x7FFFFFu)));
                 }
             } else {
                 // aligned: first fast occurrence (in fast order) that carries a quality score
                 for (uint32_t j = i; j < m && (hi[j] >> 24) == row; ++j) {
                     const uint32_t p = (uint32_t)(hi[j] & 0x7FFFFFu);
-                    if (!args.quality_present || args.quality_present[p]) {
+                    if (!q_present || q_present[p]) {
                         has_q = true;
-                        q = qb.apply(args.quality_scores[p]);
+                        q = qb.apply(q_score(p));
                         break;
                     }
                 }
             }
         } else {
             has_q = true;
-            q = qb.apply(args.quality_scores[pos]);
-            tie = args.quality_tie ? args.quality_tie[pos] : (uint32_t)row;
+            q = qb.apply(q_score(pos));
+            tie = quality_tie ? quality_tie[pos] : (uint32_t)row;
         }
         float s;
         if (has_fast && has_q)  // alpha.mul_add(q, (1 - alpha) * f)   blend.rs:256-261
@@ -376,13 +402,14 @@ __global__ void __launch_bounds__(kFusionThreads) blend_two_tier_kernel(const Bl
     }
     __syncthreads();
     cta_sort_asc_pairs(hi, lo, pay, t2);  // score desc (total_cmp), then tie asc (blend.rs:272-276)
-    for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+    fsgpu_hit_t* out = args.out + (size_t)b * args.out_stride;
+    for (uint32_t i = threadIdx.x; i < args.out_stride; i += blockDim.x) {
         fsgpu_hit_t h;
-        h.row = pay[i];
-        h.score = unordered_f32_raw(~(uint32_t)(hi[i] >> 32));
-        args.out[i] = h;
+        h.row = i < total ? pay[i] : 0xFFFFFFFFu;
+        h.score = i < total ? unordered_f32_raw(~(uint32_t)(hi[i] >> 32)) : 0.0f;
+        out[i] = h;
     }
-    if (threadIdx.x == 0) *args.out_count = total;
+    if (threadIdx.x == 0) args.out_counts[b] = total;
 }
 
 // ─── potion / Model2Vec ─────────────────────────────────────────────────────────────────────

@@ -437,6 +437,40 @@ __global__ void __launch_bounds__(kScanThreads) merge_topk_kernel(const MergeArg
     }
 }
 
+// ─── payload of merged keys ─────────────────────────────────────────────────────────────────
+// After a cross-shard merge: the value that travelled with each surviving key (e.g. the quality-tier
+// score its owning rank computed before the all-gather, two_tier.rs:1566-1631).  The input lists are
+// the per-rank results — best first, i.e. DESCENDING keys, 0-padded — so the key is found by a binary
+// search per list; keys are unique across lists (distinct global rows).
+__global__ void __launch_bounds__(256)
+merge_payload_kernel(const uint64_t* __restrict__ keys, uint64_t list_stride, uint64_t query_stride,
+                     uint32_t n_lists, uint32_t k_in, const float* __restrict__ payload, uint64_t pl_list_stride,
+                     uint64_t pl_query_stride, const uint64_t* __restrict__ merged_keys, uint32_t k_out,
+                     float* __restrict__ out_payload, uint8_t* __restrict__ out_present) {
+    const uint32_t b = blockIdx.y;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= k_out) return;
+    const uint64_t key = merged_keys[(size_t)b * k_out + i];
+    float val = 0.0f;
+    bool found = false;
+    if (key != 0ull) {
+        for (uint32_t g = 0; g < n_lists && !found; ++g) {
+            const uint64_t* list = keys + g * list_stride + b * query_stride;
+            uint32_t lo = 0, hi = k_in;
+            while (lo < hi) {
+                const uint32_t mid = lo + ((hi - lo) >> 1);
+                if (list[mid] > key) lo = mid + 1; else hi = mid;
+            }
+            if (lo < k_in && list[lo] == key) {
+                val = payload[g * pl_list_stride + b * pl_query_stride + lo];
+                found = true;
+            }
+        }
+    }
+    out_payload[(size_t)b * k_out + i] = val;
+    if (out_present) out_present[(size_t)b * k_out + i] = found ? 1 : 0;
+}
+
 // ─── resident WAL rows: scan_wal (search.rs:1449-1475) ──────────────────────────────────────
 // One warp per (query, WAL row): exact f32 dot, non-finite scores skipped (search.rs:1466-1470),
 // optional allow bit (the filter evaluated by the host, search.rs:1457-1465).  WAL row w carries the
@@ -721,16 +755,17 @@ i8_select_kernel(const float* __restrict__ approx, uint64_t n_rows, const float*
 __global__ void __launch_bounds__(kScanThreads)
 scores_for_rows_kernel(const uint16_t* __restrict__ slab, uint64_t n_rows, uint64_t row_base,
                        uint32_t dim, const float* __restrict__ queries,
-                       const uint32_t* __restrict__ rows, uint32_t n_per_query, int reduce_order,
-                       int tail_fma, float* __restrict__ out_scores,
+                       const uint32_t* __restrict__ rows, uint32_t row_stride, uint32_t n_per_query,
+                       int reduce_order, int tail_fma, float* __restrict__ out_scores,
                        uint8_t* __restrict__ out_present) {
+    // `row_stride` = 1 for a plain row array, 2 when the rows are read out of fsgpu_hit records
     const uint32_t b = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const uint32_t i = blockIdx.x * kScanWarps + (threadIdx.x >> 5);
     if (i >= n_per_query) return;
     const size_t o = (size_t)b * n_per_query + i;
-    const uint64_t grow = rows[o];
-    const bool ok = rows[o] != 0xFFFFFFFFu && grow >= row_base && grow - row_base < n_rows;
+    const uint64_t grow = rows[o * row_stride];
+    const bool ok = grow != 0xFFFFFFFFull && grow >= row_base && grow - row_base < n_rows;
     float s = 0.0f;
     if (ok)
         s = warp_exact_dot(slab + (grow - row_base) * dim, queries + (size_t)b * dim, dim,

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FSGPU_ABI_VERSION 2
+#define FSGPU_ABI_VERSION 3
 
 typedef enum fsgpu_status {
     FSGPU_OK = 0,
@@ -254,6 +254,26 @@ int fsgpu_scores_for_rows_device(const fsgpu_index* index, const float* d_querie
                                  const uint32_t* d_rows, uint32_t n_per_query, float* d_out_scores,
                                  uint8_t* d_out_present, void* stream);
 
+/* Same re-scoring with the rows taken from the hit records a device search wrote
+ * (d_hits [batch, n_per_query]; row UINT32_MAX = empty slot -> present 0).  In a row-sharded two-tier
+ * index every rank re-scores its OWN fast-tier candidates on its quality-tier shard before the
+ * all-gather (both tiers share the row partition), so the quality score travels with
+ * the candidate. */
+int fsgpu_scores_for_hits_device(const fsgpu_index* index, const float* d_queries, uint32_t batch,
+                                 const fsgpu_hit* d_hits, uint32_t n_per_query, float* d_out_scores,
+                                 uint8_t* d_out_present, void* stream);
+
+/* The value that travelled with each key through a cross-shard merge: for every key of
+ * d_merged_keys [batch, k_out] (the output of fsgpu_merge_top_k*_device) the entry of `d_payload`
+ * stored beside that key in the per-shard lists (same [list, query, slot] addressing as d_keys, with
+ * its own strides in float units).  The per-shard lists must be best-first (descending keys,
+ * 0-padded) — what every search entry point writes.  d_out_present[i] = 0 for empty slots. */
+int fsgpu_merge_payload_device(int device, const uint64_t* d_keys, const float* d_payload, uint32_t batch,
+                               uint32_t n_lists, uint32_t k_in, uint64_t list_stride, uint64_t query_stride,
+                               uint64_t payload_list_stride, uint64_t payload_query_stride,
+                               const uint64_t* d_merged_keys, uint32_t k_out, float* d_out_payload,
+                               uint8_t* d_out_present, void* stream);
+
 /* ---- fusion -------------------------------------------------------------------------------- */
 typedef struct fsgpu_rrf_config { /* RrfConfig, crates/frankensearch-fusion/src/rrf.rs:25-48 */
     double k;               /* non-finite or < 0 -> 60 (rrf.rs:124-130) */
@@ -308,6 +328,23 @@ int fsgpu_blend_two_tier(int device, float blend_factor,
                          const uint32_t* quality_rows, const float* quality_scores,
                          const uint8_t* quality_present, const uint32_t* quality_tie,
                          uint32_t n_quality, fsgpu_hit* out, uint32_t* out_count);
+
+/* Batched, device-resident form (one CTA per query; phase 2 of SyncTwoTierSearcher::search_internal,
+ * crates/frankensearch-fusion/src/sync_searcher.rs:876-886, for a whole batch without leaving the
+ * GPU).  d_fast_hits [batch, n_fast_max] with d_fast_counts[b] filled slots (NULL = all).
+ *   aligned form (d_quality_hits == NULL): d_quality_scores / d_quality_present [batch, n_fast_max]
+ *     belong to the fast hits slot by slot (blend_two_tier_aligned, blend.rs:213-286);
+ *   union form: d_quality_hits [batch, n_quality_max] (+ d_quality_counts) is a separately retrieved
+ *     quality list joined by row (blend_two_tier, blend.rs:107-191).
+ * d_out [batch, n_fast_max (+ n_quality_max in the union form)], best first, empty slots row
+ * UINT32_MAX; d_out_counts [batch]. */
+int fsgpu_blend_two_tier_device(int device, float blend_factor, uint32_t batch,
+                                const fsgpu_hit* d_fast_hits, const uint32_t* d_fast_tie,
+                                const uint32_t* d_fast_counts, uint32_t n_fast_max,
+                                const fsgpu_hit* d_quality_hits, const float* d_quality_scores,
+                                const uint8_t* d_quality_present, const uint32_t* d_quality_tie,
+                                const uint32_t* d_quality_counts, uint32_t n_quality_max,
+                                fsgpu_hit* d_out, uint32_t* d_out_counts, void* stream);
 
 /* ---- query encoders ------------------------------------------------------------------------ */
 typedef struct fsgpu_potion fsgpu_potion;

@@ -149,6 +149,43 @@ def test_int8_one_million_rows_batch_1024(i8_env, fo, monkeypatch):
     ix.close()
 
 
+def test_int8_quad_10m_batch_1024_against_the_oracle(fo, monkeypatch):
+    """The headline configuration (BASELINE configs[2]: 10 M x 384, batch 1024, top-10) on the headline
+    kernel (mma_scan_quad_kernel, default switches), compared DIRECTLY with the CPU oracle for nine
+    queries spread over every 128-query block position of a quad (sub-block x CTA rank) and the
+    batch edges: rows equal, f32 score bits equal."""
+    import torch
+
+    import frankensearch_b200 as fs
+
+    for v in ("FSGPU_MMA_I8", "FSGPU_I8_MIN_ROWS", "FSGPU_I8_MAX_K", "FSGPU_MMA_MIN_BATCH", "FSGPU_MMA_QUAD"):
+        monkeypatch.delenv(v, raising=False)
+    n, dim, batch, k = 10_000_000, 384, 1024, 10
+    dev = torch.device("cuda", 0)
+    slab = torch.empty((n, dim), dtype=torch.int16, device=dev)
+    fs._ffi.check(fs._ffi.lib().fsgpu_synth_rows_device(0, 1, 1, 0, n, dim, 64, 0.30, slab.data_ptr(), None))
+    ix = fs.GpuVectorIndex.from_device_tensor(slab)
+    assert ix._L.fsgpu_index_int8_ready(ix._h) == 1
+    q_np = np.stack([fo.clustered_query(i, dim) for i in range(batch)])
+    q = torch.from_numpy(q_np).to(dev)
+    ix.profile_read(reset=True)
+    keys, hits, counts = ix.search_top_k_device(q, k)
+    torch.cuda.synchronize()
+    p = ix.profile_read(reset=True)
+    assert p["mma_launches"] == 1 and p["i8_launches"] == 1 and p["redo_queries"] == 0, p
+    h = hits.cpu().numpy()
+    rows, scores = h[..., 0].view(np.uint32), h[..., 1].view(np.float32)
+    assert counts.cpu().numpy().tolist() == [k] * batch
+    host, _ = fo.synth_rows(1, 1, 0, n, dim)  # the oracle's own copy of the corpus (same generator)
+    sample = np.r_[0:4096:97, n - 64:n]
+    assert np.array_equal(slab[torch.from_numpy(sample).to(dev)].cpu().numpy().view(np.uint16), host[sample])
+    for b in (0, 1, 127, 128, 300, 511, 512, 777, 1023):
+        o_rows, o_scores = fo.search_top_k(host, q_np[b], k)
+        assert rows[b].tolist() == [int(r) for r in o_rows], f"query {b}: rows differ from the oracle"
+        assert np.array_equal(bits(scores[b]), bits(o_scores)), f"query {b}: score bits differ from the oracle"
+    ix.close()
+
+
 @pytest.mark.parametrize("n,dim", [(60000, 128), (25000, 384), (200, 256)])
 def test_int8_single_query_path_is_exact(i8_env, fo, n, dim, monkeypatch):
     """One or two queries through the host API: int8 pass 1 (half the bytes), exact gate from the

@@ -24,6 +24,51 @@ def synth(dev_index, lo, n, dim):
     return slab
 
 
+def check_two_tier(rank, world, local, dev, rows):
+    """The sharded two-tier pipeline (256-d fast tier -> 384-d quality re-score -> blend -> RRF, one
+    all-gather of [keys | hits | quality]) must equal the same pipeline over ONE pair of indexes."""
+    from frankensearch_b200.pipeline import DeviceLexical, DeviceTwoTierSearcher
+
+    lo, hi = shard_bounds(rows, world, rank)
+    mk = lambda seed, a, n, dim: fs.GpuVectorIndex.from_device_tensor(synth_seed(local, seed, a, n, dim), row_base=a)  # noqa: E731
+    sharded = DeviceTwoTierSearcher(mk(21, lo, hi - lo, 256), mk(22, lo, hi - lo, 384))
+    whole = DeviceTwoTierSearcher(mk(21, 0, rows, 256), mk(22, 0, rows, 384))
+    whole._world = 1  # the reference arm of the comparison never exchanges anything
+    g = torch.Generator(device="cpu").manual_seed(11)
+    bad = 0
+    for k, batch in ((10, 1), (10, 33), (100, 7), (1000, 2)):
+        fq = torch.nn.functional.normalize(torch.randn((batch, 256), generator=g), dim=1).to(dev).contiguous()
+        qq = torch.nn.functional.normalize(torch.randn((batch, 384), generator=g), dim=1).to(dev).contiguous()
+        fetch = sharded.fetch_for(k)
+        ids = torch.randint(0, rows + rows // 8, (batch, fetch), generator=g).to(torch.int64)
+        ids = torch.where(ids < rows, ids, ids + (1 << 32)).to(dev)
+        sc = torch.arange(fetch, 0, -1, dtype=torch.float32).repeat(batch, 1).to(dev).contiguous()
+        for lex in (None, DeviceLexical(ids, sc)):
+            a = sharded.search_device(fq, qq, k, lex)
+            got = [x.clone() for x in (a.fast_hits, a.fast_counts, a.quality_scores, a.quality_present, a.initial,
+                                       a.initial_counts, a.blended, a.blended_counts, a.refined, a.refined_counts)]
+            w = whole.search_device(fq, qq, k, lex)
+            want = (w.fast_hits, w.fast_counts, w.quality_scores, w.quality_present, w.initial, w.initial_counts,
+                    w.blended, w.blended_counts, w.refined, w.refined_counts)
+            torch.cuda.synchronize()
+            names = "fast_hits fast_counts quality_scores quality_present initial initial_counts blended blended_counts refined refined_counts".split()
+            for nm, x, y in zip(names, got, want):
+                if nm == "quality_scores":  # slots past the count are unspecified in the single-index arm
+                    m = torch.arange(fetch, device=dev)[None, :] < a.fast_counts[:, None]
+                    x, y = torch.where(m, x, 0), torch.where(m, y, 0)
+                if not torch.equal(x.view(torch.uint8) if x.dtype == torch.float32 else x,
+                                   y.view(torch.uint8) if y.dtype == torch.float32 else y):
+                    bad += 1
+                    print(f"rank {rank}: TWO-TIER MISMATCH {nm} k={k} batch={batch} lexical={lex is not None}", flush=True)
+    return bad
+
+
+def synth_seed(dev_index, seed, lo, n, dim):
+    slab = torch.empty((n, dim), dtype=torch.int16, device=torch.device("cuda", dev_index))
+    fs._ffi.check(fs._ffi.lib().fsgpu_synth_rows_device(dev_index, 1, seed, lo, n, dim, 64, 0.30, slab.data_ptr(), None))
+    return slab
+
+
 def main():
     rows = int(sys.argv[1]) if len(sys.argv) > 1 else 400_000
     dim = int(sys.argv[2]) if len(sys.argv) > 2 else 128
@@ -50,6 +95,7 @@ def main():
                 if not ok:
                     bad += 1
                     print(f"rank {rank}: MISMATCH k={k} batch={batch} rep={rep}", flush=True)
+    bad += check_two_tier(rank, world, local, dev, rows)
     t = torch.tensor([bad], device=dev)
     dist.all_reduce(t)
     if rank == 0:
