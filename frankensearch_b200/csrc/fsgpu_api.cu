@@ -7,6 +7,7 @@
 #include <cerrno>
 #include <cmath>
 #include <cstdarg>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -19,6 +20,7 @@
 #include "fsgpu_host.cuh"
 #include "mma_scan_kernels.cuh"
 #include "scan_kernels.cuh"
+#include "select_kernels.cuh"
 #include "synth_kernels.cuh"
 
 using namespace fsgpu;
@@ -121,6 +123,8 @@ struct fsgpu_index {
     // single-query int8 pass 1 (host API only: it needs the end-of-call synchronisation)
     mutable bool use_i8_single = false;
     mutable DevBuf ws_approx, ws_i8_top, ws_i8_cnt;
+    // large-k radix select (select_kernels.cuh): position lists and the two select states
+    mutable DevBuf ws_sel_pos, ws_sel_pos2, ws_sel_state;
     // launch accounting (guarded by mu)
     mutable bool profiling = false;
     mutable fsgpu_profile prof{};
@@ -751,6 +755,8 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
         ix->prof.scan_bytes += ix->n_rows * ix->dim * (i8 ? 1ull : 2ull);
         ix->prof.mma_launches += 1;
         ix->prof.i8_launches += i8 ? 1 : 0;
+        ix->prof.quad_launches += quad ? 1 : 0;
+        ix->prof.pair_launches += (pair && !quad) ? 1 : 0;
         ix->prof.mma_flops += 2.0 * (double)slots * (double)ix->n_rows * (double)ix->dim;
         ix->prof.merge_launches += 1;  // refine
 
@@ -940,6 +946,103 @@ static int search_i8_single_locked(const fsgpu_index* ix, const float* d_queries
     return FSGPU_OK;
 }
 
+// Large k (FSGPU_SELECT_MIN_K <= k <= kSelMaxK), one query at a time: one pass that writes a score per
+// row + a grid-wide radix select (select_kernels.cuh).  Fully asynchronous, nothing can overflow,
+// works for any query (a query the int8 bound cannot cover sends every live row to the exact stage).
+static int search_select_locked(const fsgpu_index* ix, const float* d_queries, uint32_t batch, uint32_t k,
+                                uint64_t* d_out_keys, fsgpu_hit* d_out_hits, uint32_t* d_out_counts,
+                                cudaStream_t stream) {
+    using u64 = unsigned long long;
+    const uint64_t n = ix->n_rows;
+    const bool i8 = ix->i8_ok && env_int("FSGPU_MMA_I8", 1) != 0 && env_int("FSGPU_SELECT_I8", 1) != 0;
+    CUDA_TRY(ix->ws_sel_state.reserve(2 * sizeof(SelState)));
+    CUDA_TRY(ix->ws_sort_a.reserve(n * 8));
+    CUDA_TRY(ix->ws_sel_pos2.reserve((size_t)kSelMaxK * 4));
+    if (i8) {
+        CUDA_TRY(ix->ws_approx.reserve(n * 4));
+        CUDA_TRY(ix->ws_sel_pos.reserve(n * 4));
+        CUDA_TRY(ix->ws_qhat.reserve((size_t)ix->dim));
+        CUDA_TRY(ix->ws_margin.reserve(4));
+        CUDA_TRY(ix->ws_qscale.reserve(4));
+        CUDA_TRY(ix->ws_redo.reserve(4));
+    }
+    SelState* st0 = ix->ws_sel_state.as<SelState>();
+    SelState* st1 = st0 + 1;
+    uint32_t* n1 = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(st0) + offsetof(SelState, n_out));
+    uint32_t* n2 = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(st1) + offsetof(SelState, n_out));
+    u64* keys = ix->ws_sort_a.as<u64>();
+    const uint8_t* tomb = ix->d_excl ? ix->d_excl : ix->d_tomb;
+    const int wide_grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((n + 2047) / 2048, (uint64_t)ix->num_sms * 8));
+    const int small_grid = ix->num_sms;  // lists whose length only the device knows (a few k rows)
+    CUDA_TRY(cudaFuncSetAttribute(sel_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSelMaxK * 8)));
+    for (uint32_t b = 0; b < batch; ++b) {
+        const float* q = d_queries + (size_t)b * ix->dim;
+        CUDA_TRY(cudaMemsetAsync(st0, 0, 2 * sizeof(SelState), stream));
+        const uint32_t* n_exact = nullptr;  // length of `keys` (nullptr = n)
+        if (i8) {
+            mma_prep_queries_i8_kernel<<<1, 128, 0, stream>>>(q, 1, ix->dim, ix->max_row_norm, ix->i8_max_ex, ix->i8_sx,
+                                                              ix->ws_qhat.as<int8_t>(), ix->ws_margin.as<float>(),
+                                                              ix->ws_qscale.as<float>(), ix->ws_redo.as<uint32_t>());
+            CUDA_TRY(cudaGetLastError());
+            std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+            if (ix->profiling) {
+                if (!ix->ev_free.empty()) {
+                    ev = ix->ev_free.back();
+                    ix->ev_free.pop_back();
+                } else {
+                    CUDA_TRY(cudaEventCreate(&ev.first));
+                    CUDA_TRY(cudaEventCreate(&ev.second));
+                }
+                CUDA_TRY(cudaEventRecord(ev.first, stream));
+            }
+            const int scan_grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((n + 63) / 64, (uint64_t)ix->num_sms * 8));
+            scan_i8_all_kernel<<<scan_grid, 256, 0, stream>>>(ix->d_slab_i8.as<int8_t>(), tomb, ix->ws_qhat.as<int8_t>(),
+                                                              ix->ws_qscale.as<float>(), n, ix->dim,
+                                                              ix->ws_approx.as<uint32_t>());
+            CUDA_TRY(cudaGetLastError());
+            if (ix->profiling) {
+                CUDA_TRY(cudaEventRecord(ev.second, stream));
+                ix->ev_pending.push_back(ev);
+            }
+            ix->prof.scan_launches += 1;
+            ix->prof.i8_launches += 1;
+            ix->prof.scan_bytes += n * ix->dim;
+            for (int p = 0; p < SelTraits<uint32_t>::kPasses; ++p)
+                sel_hist_kernel<uint32_t><<<wide_grid, 256, 0, stream>>>(ix->ws_approx.as<uint32_t>(), n, nullptr, st0, p, k);
+            sel_compact_kernel<uint32_t><<<wide_grid, 256, 0, stream>>>(ix->ws_approx.as<uint32_t>(), n, nullptr, st0,
+                                                                        ix->ws_margin.as<float>(), ix->ws_redo.as<uint32_t>(),
+                                                                        ix->ws_sel_pos.as<uint32_t>(), (uint32_t)n, n1);
+            gather_list_keys_kernel<<<ix->num_sms * 4, 256, (size_t)ix->dim * 4, stream>>>(
+                ix->d_slab, ix->row_base, ix->dim, q, ix->ws_sel_pos.as<uint32_t>(), n1, ix->reduce_order, ix->tail_fma, keys);
+            CUDA_TRY(cudaGetLastError());
+            n_exact = n1;
+            ix->prof.other_launches += 6;
+        } else {
+            const int grid = (int)std::min<uint64_t>((n + kScanWarps - 1) / kScanWarps, (uint64_t)ix->num_sms * 8);
+            score_all_kernel<<<grid, kScanThreads, (size_t)ix->dim * 4, stream>>>(ix->d_slab, tomb, n, ix->row_base, ix->dim, q,
+                                                                                 ix->reduce_order, ix->tail_fma,
+                                                                                 reinterpret_cast<uint64_t*>(keys));
+            CUDA_TRY(cudaGetLastError());
+            ix->prof.scan_launches += 1;
+            ix->prof.scan_bytes += n * ix->dim * 2ull;
+        }
+        const int g2 = n_exact ? small_grid : wide_grid;
+        for (int p = 0; p < SelTraits<u64>::kPasses; ++p)
+            sel_hist_kernel<u64><<<g2, 256, 0, stream>>>(keys, n, n_exact, st1, p, k);
+        sel_compact_kernel<u64><<<g2, 256, 0, stream>>>(keys, n, n_exact, st1, nullptr, nullptr, ix->ws_sel_pos2.as<uint32_t>(),
+                                                        kSelMaxK, n2);
+        sel_emit_kernel<<<1, 1024, kSelMaxK * 8, stream>>>(keys, ix->ws_sel_pos2.as<uint32_t>(), n2, k, ix->d_slab, q, n,
+                                                           ix->row_base, ix->dim, ix->reduce_order, ix->tail_fma,
+                                                           d_out_keys ? d_out_keys + (size_t)b * k : nullptr,
+                                                           d_out_hits ? d_out_hits + (size_t)b * k : nullptr,
+                                                           d_out_counts ? d_out_counts + b : nullptr, ix->d_error);
+        CUDA_TRY(cudaGetLastError());
+        ix->prof.other_launches += 7;
+        ix->prof.merge_launches += 1;
+    }
+    return FSGPU_OK;
+}
+
 static int search_main_locked(const fsgpu_index* ix, const float* d_queries, uint32_t batch, uint32_t k,
                               uint64_t* d_out_keys, fsgpu_hit* d_out_hits, uint32_t* d_out_counts,
                               cudaStream_t stream) {
@@ -952,7 +1055,41 @@ static int search_main_locked(const fsgpu_index* ix, const float* d_queries, uin
         CUDA_TRY(cudaMemsetAsync(ix->d_error, 0, 8, stream));
         return search_mma_locked(ix, d_queries, batch, k, d_out_keys, d_out_hits, d_out_counts, stream);
     }
+    // large k off the tensor-core path (few queries, or k past its ceiling): radix select; it needs 16-byte
+    // rows for the int8 codes only, any dim otherwise
+    const uint32_t select_min_k = (uint32_t)std::max(1, env_int("FSGPU_SELECT_MIN_K", 129));
+    if (k >= select_min_k && k <= kSelMaxK && ix->n_rows > 0 && ix->n_rows <= 0xFFFFFFF0ull) {
+        CUDA_TRY(cudaMemsetAsync(ix->d_error, 0, 4, stream));
+        return search_select_locked(ix, d_queries, batch, k, d_out_keys, d_out_hits, d_out_counts, stream);
+    }
     return search_exact_locked(ix, d_queries, batch, k, d_out_keys, d_out_hits, d_out_counts, stream);
+}
+
+// Merge of ONE contiguous list per query (main top-k + WAL keys, or the keys of a selective gather) into
+// the best k_out.  The shared-memory merge holds cand_capacity(k_out) keys; past that (k_out > 8192:
+// `limit >= record_count` searches on an index with WAL rows, search.rs:449-493) the list is sorted
+// whole, like the score-all arm.
+static int merge_single_list_locked(const fsgpu_index* ix, const MergeArgs& m, uint32_t batch, cudaStream_t stream) {
+    if ((size_t)m.cap * 8 + 16 <= 200 * 1024) return launch_merge(m, batch, stream);
+    const uint64_t n = m.k_in;
+    CUDA_TRY(ix->ws_sort_b.reserve(n * 8));
+    size_t cub_bytes = 0;
+    CUDA_TRY(cub::DeviceRadixSort::SortKeysDescending(nullptr, cub_bytes, m.keys, ix->ws_sort_b.as<uint64_t>(), n, 0, 64, stream));
+    CUDA_TRY(ix->ws_cub.reserve(cub_bytes));
+    const uint32_t k_eff = (uint32_t)std::min<uint64_t>(m.k_out, n);
+    for (uint32_t b = 0; b < batch; ++b) {
+        CUDA_TRY(cub::DeviceRadixSort::SortKeysDescending(ix->ws_cub.p, cub_bytes, m.keys + (size_t)b * m.query_stride,
+                                                         ix->ws_sort_b.as<uint64_t>(), n, 0, 64, stream));
+        emit_sorted_prefix_kernel<<<std::max(1u, std::min(1024u, (m.k_out + kScanWarps - 1) / kScanWarps)), kScanThreads, 0,
+                                    stream>>>(ix->ws_sort_b.as<uint64_t>(), k_eff, m.k_out, m.slab,
+                                              m.queries + (size_t)b * m.dim, m.n_rows, m.row_base, m.dim, m.reduce_order,
+                                              m.tail_fma, m.out_keys ? m.out_keys + (size_t)b * m.k_out : nullptr,
+                                              m.out_hits ? m.out_hits + (size_t)b * m.k_out : nullptr,
+                                              m.out_counts ? m.out_counts + b : nullptr);
+        CUDA_TRY(cudaGetLastError());
+        ix->prof.other_launches += 4;
+    }
+    return FSGPU_OK;
 }
 
 // The selective arm of a filtered search: score only the listed rows (scan_gather_positions,
@@ -990,7 +1127,7 @@ static int search_gather_locked(const fsgpu_index* ix, const float* d_queries, u
     m.reduce_order = ix->reduce_order;
     m.tail_fma = ix->tail_fma;
     m.error_flag = ix->d_error;
-    return launch_merge(m, batch, stream);
+    return merge_single_list_locked(ix, m, batch, stream);
 }
 
 // Main slab + resident WAL rows (VectorIndex::search_top_k_internal, search.rs:476-493): the slab's
@@ -1038,7 +1175,7 @@ static int search_device_locked(const fsgpu_index* ix, const float* d_queries, u
     m.tail_fma = ix->tail_fma;
     m.error_flag = ix->d_error;
     ix->prof.merge_launches += 1;
-    return launch_merge(m, batch, stream);
+    return merge_single_list_locked(ix, m, batch, stream);
 }
 
 static int check_error_flag(const fsgpu_index* ix, cudaStream_t stream) {
@@ -1114,7 +1251,8 @@ extern "C" void fsgpu_index_destroy(fsgpu_index* ix) {
                           &ix->ws_present, &ix->ws_excl, &ix->ws_allow, &ix->ws_progress, &ix->ws_qhat, &ix->ws_margin, &ix->ws_gate, &ix->ws_redo, &ix->ws_cand,
                           &ix->ws_cand_count, &ix->d_wal, &ix->ws_wal_main, &ix->ws_wal_keys, &ix->d_hashes,
                           &ix->ws_allowed, &ix->ws_gather_pos, &ix->ws_gather_count, &ix->ws_gather_keys,
-                          &ix->d_slab_i8, &ix->ws_qscale, &ix->ws_approx, &ix->ws_i8_top, &ix->ws_i8_cnt})
+                          &ix->d_slab_i8, &ix->ws_qscale, &ix->ws_approx, &ix->ws_i8_top, &ix->ws_i8_cnt,
+                          &ix->ws_sel_pos, &ix->ws_sel_pos2, &ix->ws_sel_state})
             b->release();
         if (ix->stream) cudaStreamDestroy(ix->stream);
     }

@@ -145,23 +145,28 @@ __device__ __forceinline__ float warp_exact_dot_f32(const float* __restrict__ ro
 }
 
 // ─── CTA-wide bitonic sort, descending, n a power of two, keys in shared memory ─────────────
+// Every thread owns compare-exchange PAIRS (t -> i with bit j clear, i | j), so no thread idles, and
+// the stages with j <= 16 only touch the 64 consecutive keys a warp owns (for every t of that warp,
+// in every such stage): they need a warp barrier, not a CTA barrier — 15 CTA barriers instead of 55
+// for 1024 keys.  All threads of the CTA must call.
 __device__ __forceinline__ void cta_sort_desc(uint64_t* keys, uint32_t n) {
     for (uint32_t k = 2; k <= n; k <<= 1) {
+        if ((k >> 1) > 16u) __syncthreads();  // the warp-local stages of the previous phase are complete
         for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-                const uint32_t ixj = i ^ j;
-                if (ixj > i) {
-                    const uint64_t a = keys[i], b = keys[ixj];
-                    const bool desc = (i & k) == 0;
-                    if (desc ? (a < b) : (a > b)) {
-                        keys[i] = b;
-                        keys[ixj] = a;
-                    }
+            for (uint32_t t = threadIdx.x; t < (n >> 1); t += blockDim.x) {
+                const uint32_t i = ((t & ~(j - 1u)) << 1) | (t & (j - 1u));
+                const uint32_t ixj = i | j;
+                const uint64_t a = keys[i], b = keys[ixj];
+                const bool desc = (i & k) == 0;
+                if (desc ? (a < b) : (a > b)) {
+                    keys[i] = b;
+                    keys[ixj] = a;
                 }
             }
-            __syncthreads();
+            if (j > 16u) __syncthreads(); else __syncwarp();
         }
     }
+    __syncthreads();
 }
 
 __device__ __forceinline__ uint32_t next_pow2(uint32_t x) {

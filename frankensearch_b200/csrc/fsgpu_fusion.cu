@@ -30,8 +30,13 @@ static int launch_rrf(RrfArgs& a, uint32_t batch, cudaStream_t s) {
         return fail(FSGPU_ERR_INVALID_CONFIG, "rrf: %u candidates exceed the device window of %u", m,
                     kFusionMaxEntries);
     const size_t smem = (size_t)host_next_pow2(std::max(m, 1u)) * 20 + 16;
-    CUDA_TRY(cudaFuncSetAttribute(rrf_fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    rrf_fuse_kernel<<<batch, kFusionThreads, smem, s>>>(a);
+    if (m > kFusionWideFrom) {
+        CUDA_TRY(cudaFuncSetAttribute(rrf_fuse_kernel<kFusionWideThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rrf_fuse_kernel<kFusionWideThreads><<<batch, kFusionWideThreads, smem, s>>>(a);
+    } else {
+        CUDA_TRY(cudaFuncSetAttribute(rrf_fuse_kernel<kFusionThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rrf_fuse_kernel<kFusionThreads><<<batch, kFusionThreads, smem, s>>>(a);
+    }
     CUDA_TRY(cudaGetLastError());
     return FSGPU_OK;
 }
@@ -136,8 +141,13 @@ static int launch_blend(const BlendArgs& a, uint32_t batch, cudaStream_t s) {
     if (m > kFusionMaxEntries)
         return fail(FSGPU_ERR_INVALID_CONFIG, "blend: %u hits exceed the device window of %u", m, kFusionMaxEntries);
     const size_t smem = (size_t)host_next_pow2(std::max(m, 1u)) * 20 + 16;
-    CUDA_TRY(cudaFuncSetAttribute(blend_two_tier_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    blend_two_tier_kernel<<<batch, kFusionThreads, smem, s>>>(a);
+    if (m > kFusionWideFrom) {
+        CUDA_TRY(cudaFuncSetAttribute(blend_two_tier_kernel<kFusionWideThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        blend_two_tier_kernel<kFusionWideThreads><<<batch, kFusionWideThreads, smem, s>>>(a);
+    } else {
+        CUDA_TRY(cudaFuncSetAttribute(blend_two_tier_kernel<kFusionThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        blend_two_tier_kernel<kFusionThreads><<<batch, kFusionThreads, smem, s>>>(a);
+    }
     CUDA_TRY(cudaGetLastError());
     return FSGPU_OK;
 }

@@ -9,7 +9,10 @@
 
 namespace fsgpu {
 
-constexpr int kFusionThreads = 256;
+constexpr int kFusionThreads = 256;       // lists up to kFusionWideFrom entries
+constexpr int kFusionWideThreads = 1024;  // longer lists: the sorts are the whole cost (0.88 ms for 6000
+                                          // entries with 256 threads, profiles/r02_launches_select.md)
+constexpr uint32_t kFusionWideFrom = 1024;
 constexpr uint32_t kFusionMaxEntries = 8192;  // n_sem_max + n_lex_max (160 KB of shared memory)
 constexpr uint32_t kTieBits = 18;             // tie ranks are ranks inside one candidate union
 
@@ -27,18 +30,28 @@ __device__ __forceinline__ float unordered_f32_raw(uint32_t o) {
     return __uint_as_float((o >> 31) ? (o ^ 0x80000000u) : ~o);
 }
 
-// Bitonic sort ascending over (hi, lo) with a u32 payload; n a power of two.
-__device__ __forceinline__ void cta_sort_asc_pairs(uint64_t* hi, uint64_t* lo, uint32_t* pay,
-                                                   uint32_t n) {
+// Bitonic sort ascending over (hi, lo) with a u32 payload; n a power of two.  Pair-indexed (no idle
+// threads); stages with j <= 16 stay inside the 64 entries a warp owns and use a warp barrier
+// (fsgpu_common.cuh, cta_sort_desc).  KEYS_ONLY sorts `hi` alone (the join passes carry nothing else).
+template <bool KEYS_ONLY>
+__device__ __forceinline__ void cta_sort_asc_impl(uint64_t* hi, uint64_t* lo, uint32_t* pay, uint32_t n) {
     for (uint32_t k = 2; k <= n; k <<= 1) {
+        if ((k >> 1) > 16u) __syncthreads();
         for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-                const uint32_t ixj = i ^ j;
-                if (ixj > i) {
-                    const uint64_t ah = hi[i], bh = hi[ixj], al = lo[i], bl = lo[ixj];
+            for (uint32_t t = threadIdx.x; t < (n >> 1); t += blockDim.x) {
+                const uint32_t i = ((t & ~(j - 1u)) << 1) | (t & (j - 1u));
+                const uint32_t ixj = i | j;
+                const uint64_t ah = hi[i], bh = hi[ixj];
+                const bool asc = (i & k) == 0;
+                if constexpr (KEYS_ONLY) {
+                    if (asc ? (ah > bh) : (ah < bh)) {
+                        hi[i] = bh;
+                        hi[ixj] = ah;
+                    }
+                } else {
+                    const uint64_t al = lo[i], bl = lo[ixj];
                     const bool a_gt_b = ah > bh || (ah == bh && al > bl);
                     const bool a_lt_b = ah < bh || (ah == bh && al < bl);
-                    const bool asc = (i & k) == 0;
                     if (asc ? a_gt_b : a_lt_b) {
                         hi[i] = bh; hi[ixj] = ah;
                         lo[i] = bl; lo[ixj] = al;
@@ -48,9 +61,16 @@ __device__ __forceinline__ void cta_sort_asc_pairs(uint64_t* hi, uint64_t* lo, u
                     }
                 }
             }
-            __syncthreads();
+            if (j > 16u) __syncthreads(); else __syncwarp();
         }
     }
+    __syncthreads();
+}
+__device__ __forceinline__ void cta_sort_asc_pairs(uint64_t* hi, uint64_t* lo, uint32_t* pay, uint32_t n) {
+    cta_sort_asc_impl<false>(hi, lo, pay, n);
+}
+__device__ __forceinline__ void cta_sort_asc_keys(uint64_t* hi, uint32_t n) {
+    cta_sort_asc_impl<true>(hi, nullptr, nullptr, n);
 }
 
 // rrf.rs:118-121 — 1.0 / (k + f64::from(rank as u32) + 1.0), each op one IEEE rounding.
@@ -79,7 +99,8 @@ struct RrfArgs {
 
 constexpr uint32_t kNone16 = 0xFFFFu;
 
-__global__ void __launch_bounds__(kFusionThreads) rrf_fuse_kernel(const RrfArgs args) {
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) rrf_fuse_kernel(const RrfArgs args) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t b = blockIdx.x;
     const uint32_t n_lex = min(args.lex_counts ? args.lex_counts[b] : args.n_lex_max, args.n_lex_max);
@@ -117,13 +138,14 @@ __global__ void __launch_bounds__(kFusionThreads) rrf_fuse_kernel(const RrfArgs 
     }
     if (threadIdx.x == 0) n_rec = 0;
     __syncthreads();
-    cta_sort_asc_pairs(hi, lo, pay, m2);
+    cta_sort_asc_keys(hi, m2);  // the join only orders the keys
 
     // 2) one record per distinct id: first semantic occurrence (+ first lexical occurrence), or
     //    a lexical-only record.  Records are staged in registers, written after a barrier
     //    because they overwrite the join keys.
-    uint64_t rec_hi[kFusionMaxEntries / kFusionThreads], rec_lo[kFusionMaxEntries / kFusionThreads];
-    uint32_t rec_pay[kFusionMaxEntries / kFusionThreads];
+    constexpr uint32_t kPerThread = (THREADS == kFusionThreads ? kFusionWideFrom : kFusionMaxEntries) / THREADS;
+    uint64_t rec_hi[kPerThread], rec_lo[kPerThread];
+    uint32_t rec_pay[kPerThread];
     uint32_t n_mine = 0;
     for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
         const uint64_t key = hi[i];
@@ -291,9 +313,10 @@ __device__ __forceinline__ NormBounds fit_bounds(ScoreAt score_at, const uint8_t
     return b;
 }
 
-__global__ void __launch_bounds__(kFusionThreads) blend_two_tier_kernel(const BlendArgs args) {
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) blend_two_tier_kernel(const BlendArgs args) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ float scratch[kFusionThreads / 32];
+    __shared__ float scratch[THREADS / 32];
     __shared__ uint32_t n_rec;
     const uint32_t b = blockIdx.x;
     const bool union_form = args.union_form != 0;
@@ -335,10 +358,11 @@ __global__ void __launch_bounds__(kFusionThreads) blend_two_tier_kernel(const Bl
     }
     if (threadIdx.x == 0) n_rec = 0;
     __syncthreads();
-    cta_sort_asc_pairs(hi, lo, pay, m2);
+    cta_sort_asc_keys(hi, m2);  // the join only orders the keys
 
-    uint64_t rec_hi[kFusionMaxEntries / kFusionThreads];
-    uint32_t rec_pay[kFusionMaxEntries / kFusionThreads];
+    constexpr uint32_t kPerThread = (THREADS == kFusionThreads ? kFusionWideFrom : kFusionMaxEntries) / THREADS;
+    uint64_t rec_hi[kPerThread];
+    uint32_t rec_pay[kPerThread];
     uint32_t n_mine = 0;
     for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {
         const uint64_t key = hi[i];

@@ -189,7 +189,8 @@ class GpuVectorIndex:
         return dict(scan_launches=int(p.scan_launches), merge_launches=int(p.merge_launches),
                     other_launches=int(p.other_launches), scan_bytes=int(p.scan_bytes), scan_ms=float(p.scan_ms),
                     mma_launches=int(p.mma_launches), mma_flops=float(p.mma_flops),
-                    redo_queries=int(p.redo_queries), i8_launches=int(p.i8_launches))
+                    redo_queries=int(p.redo_queries), i8_launches=int(p.i8_launches),
+                    pair_launches=int(p.pair_launches), quad_launches=int(p.quad_launches))
 
     def set_tombstones(self, flags) -> None:
         """Soft-delete flags (record flag bit 0, lib.rs:172; honoured by the scan, search.rs:1281)."""

@@ -167,9 +167,17 @@ typedef struct fsgpu_profile {
     double mma_flops;      /* 2 * query slots * rows * dim summed over those launches */
     uint64_t redo_queries; /* queries of batched launches re-run on the exact CUDA-core kernel */
     uint64_t i8_launches;  /* scan launches that read the int8 codes (kind::i8 MMAs or the dp4a pass) */
+    uint64_t pair_launches; /* tensor-core scan launches of the CTA-pair form (mma_scan_pair_kernel) */
+    uint64_t quad_launches; /* ... of the two-blocks-per-CTA int8 form (mma_scan_quad_kernel) */
 } fsgpu_profile;
 int fsgpu_index_profile_enable(fsgpu_index* index, int on);
 int fsgpu_index_profile_read(fsgpu_index* index, fsgpu_profile* out, int reset);
+
+/* Tensor-pipe issue ceiling of this GPU for the MMA shape of the batched scan (tcgen05.mma
+ * cta_group::2, M = 256 x N = 256; kind 0 = f16 -> f32, 1 = int8 -> s32): a bare issue loop, operands
+ * in shared memory, no loads, no epilogue, timed with CUDA events for about `target_ms`.  Writes
+ * operations per second (2 per multiply-add).  bench.py quotes the scan kernel against this figure. */
+int fsgpu_measure_tensor_peak(int device, int kind, uint32_t target_ms, double* out_ops_per_s);
 
 /* ---- exact scan + top-k -------------------------------------------------------------------- */
 /* Replaces VectorIndex::search_top_k / InMemoryVectorIndex::search_top_k

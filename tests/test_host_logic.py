@@ -129,6 +129,78 @@ def test_sharded_search_equals_single_index_over_gloo():
         assert np.array_equal(ret[0][b], want)
 
 
+# ── sharded two-tier pipeline plumbing over gloo, world_size 2 ───────────────────────────────
+def _pipeline_worker(rank, world, port, fast_slab, quality_slab, fq, qq, k, lex_ids, lex_scores, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        from fake_pipeline_lib import FakePipelineLib, FakeShard
+        from frankensearch_b200.pipeline import DeviceLexical, DeviceTwoTierSearcher
+
+        lo, hi = sharded.shard_bounds(fast_slab.shape[0], world, rank)
+        fast, quality = FakeShard(1, fast_slab[lo:hi], lo), FakeShard(2, quality_slab[lo:hi], lo)
+        s = DeviceTwoTierSearcher(fast, quality)
+        s._L = FakePipelineLib([fast, quality])
+        lex = DeviceLexical(torch.from_numpy(lex_ids.view(np.int64)), torch.from_numpy(lex_scores)) if lex_ids is not None else None
+        r = s.search_device(torch.from_numpy(fq), torch.from_numpy(qq), k, lex)
+        ret[rank] = {n: getattr(r, n).numpy().copy() for n in
+                     ("fast_hits", "fast_counts", "quality_scores", "quality_present", "initial", "initial_counts",
+                      "blended", "blended_counts", "refined", "refined_counts")}
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("with_lexical", [True, False])
+def test_sharded_two_tier_pipeline_equals_single_process_flow_over_gloo(with_lexical):
+    """SURVEY 8e "Two-tier": per-rank fast top-fetch + local quality re-score, ONE all-gather of
+    [keys | hits | quality], merge + payload pickup, blend, RRF == the unsharded oracle flow
+    (sync_searcher.rs:616-1009); both ranks hold the same answer."""
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import flows
+    from fake_pipeline_lib import FUSED, HIT
+    from oracle import fs_oracle as fo
+
+    n, k, batch = 3001, 7, 3
+    fast_slab, _ = fo.synth_rows(1, 21, 0, n, 128)
+    quality_slab, _ = fo.synth_rows(1, 22, 0, n, 64)
+    fast_slab[700] = fast_slab[2400]  # an exact cross-shard tie: the lower global row wins
+    fq = np.stack([fo.clustered_query(q, 128) for q in range(batch)])
+    qq = np.stack([fo.clustered_query(50 + q, 64) for q in range(batch)])
+    fetch = 3 * k
+    lex_ids = lex_scores = None
+    lists = []
+    if with_lexical:
+        for b in range(batch):
+            rows, _ = fo.search_top_k(fast_slab, fq[b], fetch)
+            lists.append(flows.synthetic_lexical(rows, n, fetch, seed=b))
+        lex_ids = np.stack([i for i, _ in lists])
+        lex_scores = np.stack([s for _, s in lists])
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 31500 + os.getpid() % 2000 + (1 if with_lexical else 0)
+    mp.spawn(_pipeline_worker, args=(2, port, fast_slab, quality_slab, fq, qq, k, lex_ids, lex_scores, ret), nprocs=2, join=True)
+    for name in ret[0]:
+        assert np.array_equal(ret[0][name], ret[1][name]), name
+    got = ret[0]
+    fast = np.ascontiguousarray(got["fast_hits"]).view(HIT).reshape(batch, fetch)
+    blended = np.ascontiguousarray(got["blended"]).view(HIT).reshape(batch, fetch)
+    for b in range(batch):
+        want = flows.oracle_two_tier(fast_slab, quality_slab, fq[b], qq[b], k, lists[b] if with_lexical else None)
+        assert fast["row"][b].tolist() == [int(r) for r in want["fast"][0]]
+        assert np.array_equal(got["quality_scores"][b].view(np.uint32), want["quality"].view(np.uint32))
+        flows.assert_hits_equal(blended[b, :int(got["blended_counts"][b])], want["blended"], f"blended {b}")
+        if with_lexical:
+            for phase in ("initial", "refined"):
+                f = np.ascontiguousarray(got[phase]).view(FUSED).reshape(batch, k)
+                flows.assert_fused_equal(f[b, :int(got[phase + "_counts"][b])], want[phase], f"{phase} {b}")
+        else:
+            for phase in ("initial", "refined"):
+                h = np.ascontiguousarray(got[phase]).view(HIT).reshape(batch, k)
+                flows.assert_hits_equal(h[b, :int(got[phase + "_counts"][b])], want[phase], f"{phase} {b}")
+
+
 # ── phase-2 diagnostics (crates/frankensearch-fusion/src/blend.rs:365-544 and its tests) ─────
 def _hit(doc, score, index):
     from frankensearch_b200.types import VectorHit
