@@ -110,7 +110,7 @@ EXPORTS = [
     "fsgpu_index_set_tombstones", "fsgpu_index_read_tombstones", "fsgpu_index_int8_ready",
     "fsgpu_index_read_codes_i8",
     "fsgpu_index_set_wal", "fsgpu_index_wal_rows", "fsgpu_index_read_rows_f16", "fsgpu_index_profile_enable",
-    "fsgpu_index_profile_read", "fsgpu_measure_tensor_peak", "fsgpu_search_top_k", "fsgpu_search_top_k_device",
+    "fsgpu_index_profile_read", "fsgpu_index_last_status", "fsgpu_measure_tensor_peak", "fsgpu_search_top_k", "fsgpu_search_top_k_device",
     "fsgpu_search_top_k_filtered", "fsgpu_search_top_k_filtered_device",
     "fsgpu_index_set_doc_hashes", "fsgpu_search_top_k_hashes",
     "fsgpu_merge_top_k_device", "fsgpu_merge_top_k_hits_device", "fsgpu_scores_for_rows", "fsgpu_scores_for_rows_device",
@@ -171,6 +171,7 @@ def lib() -> C.CDLL:
     L.fsgpu_index_read_rows_f16.argtypes = [_vp, C.c_uint64, C.c_uint64, _vp]
     L.fsgpu_index_profile_enable.argtypes = [_vp, C.c_int]
     L.fsgpu_index_profile_read.argtypes = [_vp, C.POINTER(Profile), C.c_int]
+    L.fsgpu_index_last_status.argtypes = [_vp, _vp]
     L.fsgpu_measure_tensor_peak.argtypes = [C.c_int, C.c_int, C.c_uint32, C.POINTER(C.c_double)]
     L.fsgpu_search_top_k.argtypes = [_vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, _vp, _vp]
     L.fsgpu_search_top_k_device.argtypes = [_vp, _vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp, _vp]

@@ -97,8 +97,25 @@ struct fsgpu_index {
     // workspaces (grow-only, guarded by mu)
     mutable DevBuf ws_partial, ws_queries, ws_keys, ws_hits, ws_counts, ws_sort_a, ws_sort_b,
         ws_cub, ws_rows, ws_scores, ws_present;
-    uint32_t* d_error = nullptr;    // [2]: {contract-violation flag, "some query needs the exact path"}
-    uint32_t* h_flags = nullptr;    // pinned mirror of d_error[0..2): one small D2H per batched search
+    // d_error[4]: {0: contract-violation flag, 1: "some query needs the exact path" (set by the refine
+    // kernel, cleared per sub-batch), 2: bails (a redo launch found more flagged queries than its limit),
+    // 3: flagged queries served by device-side redo launches since the call began}
+    uint32_t* d_error = nullptr;
+    uint32_t* h_flags = nullptr;    // pinned mirror of d_error[0..4): copied at the end of every batched search
+    // device-side redo (scan_kernels.cuh RedoArgs): slot -> query table and per-launch count
+    mutable DevBuf ws_redo_slots, ws_redo_partial;
+    // calls may arrive on different streams; the workspaces above are shared, so every call first waits
+    // for the previous one (cudaStreamWaitEvent: device-side ordering, the host never blocks)
+    cudaEvent_t ev_last = nullptr;
+    mutable cudaStream_t last_stream = nullptr;
+    mutable bool have_last = false;
+    // adaptive form choice for stream-asynchronous callers: when the int8 form's candidate lists
+    // overflowed for more than a few queries of a call, the next calls use the f16 form
+    mutable cudaEvent_t ev_flags = nullptr;
+    mutable bool flags_pending = false;
+    mutable int i8_penalty = 0;
+    mutable bool force_f16 = false;  // set by a synchronous caller's retry
+    mutable bool sync_caller = true;  // the entry point synchronises before returning (it may retry)
     // batched tensor-core path (mma_scan_kernels.cuh): slab statistics for the error bound, the
     // slab's TMA descriptor, workspaces
     bool mma_ok = false;            // dim % 64 == 0, dim <= 512, every element finite, TMA usable
@@ -232,7 +249,6 @@ static int search_exact_locked(const fsgpu_index* ix, const float* d_queries, ui
         if (d_out_counts) CUDA_TRY(cudaMemsetAsync(d_out_counts, 0, (size_t)batch * 4, stream));
         return FSGPU_OK;
     }
-    CUDA_TRY(cudaMemsetAsync(ix->d_error, 0, 4, stream));
     if (k > kFusedMaxK) {
         // `limit >= n` / very large k arm (search.rs:449-473): score every row, radix sort.
         const uint64_t n = ix->n_rows;
@@ -456,6 +472,136 @@ static int search_exact_locked(const fsgpu_index* ix, const float* d_queries, ui
                                uint64_t* d_out_keys, fsgpu_hit* d_out_hits, uint32_t* d_out_counts,
                                cudaStream_t stream);
 
+// Device-side redo of the queries a batched search flagged (ws_redo[b] != 0; d_error[1] != 0 iff any):
+// exact CUDA-core scan + merge launches on the same stream that exit at once when nothing is flagged —
+// the call needs no host round trip.  `limit`: with more flagged queries than this the launches do
+// nothing and count a bail in d_error[2] (a synchronous caller then re-runs the batch in the f16 form).
+static int enqueue_redo_locked(const fsgpu_index* ix, const float* d_queries, uint32_t sub, uint32_t k,
+                               uint64_t* d_out_keys, fsgpu_hit* d_out_hits, uint32_t* d_out_counts,
+                               cudaStream_t stream, uint32_t limit) {
+    ScanPlan plan;
+    int rc = make_plan(ix, k, 1, &plan);
+    if (rc) return rc;
+    const int grid = std::min(plan.grid, ix->num_sms * 2);
+    const size_t slot_bytes = (size_t)grid * k * 8;
+    const uint32_t per = (uint32_t)std::max<size_t>(1, std::min<size_t>({(size_t)kRedoMaxPerLaunch, (size_t)sub,
+                                                                         ((size_t)128 << 20) / slot_bytes}));
+    const uint32_t worst = std::min(sub, limit);
+    const uint32_t rounds = std::max(1u, (worst + per - 1) / per);
+    CUDA_TRY(ix->ws_redo_partial.reserve((size_t)per * slot_bytes));
+    CUDA_TRY(ix->ws_redo_slots.reserve((size_t)(per + 1) * 4));
+    for (uint32_t r = 0; r < rounds; ++r) {
+        ScanArgs a{};
+        a.redo.flags = ix->ws_redo.as<uint32_t>();
+        a.redo.any = ix->d_error + 1;
+        a.redo.n = sub;
+        a.redo.first = r * per;
+        a.redo.max = per;
+        a.redo.limit = limit;
+        a.redo.bail = ix->d_error + 2;
+        a.redo.slots = ix->ws_redo_slots.as<uint32_t>();
+        a.redo.round_n = ix->ws_redo_slots.as<uint32_t>() + per;
+        a.redo.served = ix->d_error + 3;
+        a.slab = ix->d_slab;
+        a.tombstones = ix->d_excl ? ix->d_excl : ix->d_tomb;
+        a.queries = d_queries;
+        a.n_rows = ix->n_rows;
+        a.row_base = ix->row_base;
+        a.dim = ix->dim;
+        a.k = k;
+        a.cap = plan.cap;
+        a.sync_every = plan.sync_every;
+        a.reduce_order = ix->reduce_order;
+        a.tail_fma = ix->tail_fma;
+        a.allow_packed = env_int("FSGPU_SCAN_PACKED", 1);
+        a.partial = ix->ws_redo_partial.as<uint64_t>();
+        a.error_flag = ix->d_error;
+        plan.kernel<<<grid, kScanThreads, plan.smem, stream>>>(a);
+        CUDA_TRY(cudaGetLastError());
+        MergeArgs m{};
+        m.keys = a.partial;
+        m.list_stride = k;
+        m.query_stride = (uint64_t)grid * k;
+        m.n_lists = (uint32_t)grid;
+        m.k_in = k;
+        m.k_out = k;
+        m.cap = plan.cap;
+        m.out_keys = d_out_keys;
+        m.out_hits = d_out_hits;
+        m.out_counts = d_out_counts;
+        m.slab = ix->d_slab;
+        m.queries = d_queries;
+        m.n_rows = ix->n_rows;
+        m.row_base = ix->row_base;
+        m.dim = ix->dim;
+        m.reduce_order = ix->reduce_order;
+        m.tail_fma = ix->tail_fma;
+        m.error_flag = ix->d_error;
+        m.redo_slots = a.redo.slots;
+        m.redo_round_n = a.redo.round_n;
+        rc = launch_merge(m, per, stream);
+        if (rc) return rc;
+        ix->prof.other_launches += 2;
+    }
+    return FSGPU_OK;
+}
+
+// Flags of the call in flight -> pinned host words.  A synchronous entry point reads them after its own
+// synchronisation; a stream-asynchronous one leaves them for the next call (consume_flags_locked).
+static int copy_flags_locked(const fsgpu_index* ix, cudaStream_t stream) {
+    CUDA_TRY(cudaMemcpyAsync(ix->h_flags, ix->d_error, 16, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaEventRecord(ix->ev_flags, stream));
+    ix->flags_pending = true;
+    return FSGPU_OK;
+}
+
+// Book-keeping from the flags of a finished call: redo accounting, and the adaptive choice of form —
+// when the int8 form sent more than a few queries to the exact path (its candidate lists overflowed:
+// a corpus whose score spread is narrower than the int8 bound), the next calls take the f16 form.
+static void consume_flags_locked(const fsgpu_index* ix, bool wait) {
+    if (!ix->flags_pending) return;
+    if (wait) {
+        if (cudaEventSynchronize(ix->ev_flags) != cudaSuccess) return;
+    } else if (cudaEventQuery(ix->ev_flags) != cudaSuccess) {
+        cudaGetLastError();  // not ready: look again at the next call
+        return;
+    }
+    ix->flags_pending = false;
+    ix->prof.redo_queries += ix->h_flags[3];
+    if (ix->h_flags[3] > 4u || ix->h_flags[2] != 0u) ix->i8_penalty = 32;
+}
+
+// Start of every entry point that touches the index's workspaces (ix->mu held): take in the flags of the
+// last asynchronous call, order this call's stream after the previous call's work (the workspaces and
+// flag words are shared between streams), clear the flag words.
+static int begin_call_locked(const fsgpu_index* ix, cudaStream_t s, bool sync_caller) {
+    consume_flags_locked(ix, false);
+    if (ix->have_last && ix->last_stream != s) CUDA_TRY(cudaStreamWaitEvent(s, ix->ev_last, 0));
+    ix->sync_caller = sync_caller;
+    CUDA_TRY(cudaMemsetAsync(ix->d_error, 0, 16, s));
+    return FSGPU_OK;
+}
+// End of the enqueue: flags -> pinned host words, and the event the next call (on any stream) waits on.
+static int end_call_locked(const fsgpu_index* ix, cudaStream_t s) {
+    int rc = copy_flags_locked(ix, s);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(ix->ev_last, s));
+    ix->last_stream = s;
+    ix->have_last = true;
+    if (ix->i8_penalty > 0) --ix->i8_penalty;
+    return FSGPU_OK;
+}
+// A synchronous entry point after end_call_locked: wait, then read the verdict of the call.
+// *retry_f16 = the int8 form bailed (too many overflowed lists): run the call again in the f16 form.
+static int finish_sync_call_locked(const fsgpu_index* ix, cudaStream_t s, bool* retry_f16) {
+    CUDA_TRY(cudaStreamSynchronize(s));
+    const uint32_t violated = ix->h_flags[0], bails = ix->h_flags[2];
+    consume_flags_locked(ix, true);
+    if (violated) return fail(FSGPU_ERR_SUBSYSTEM, "gpu: top-k candidate buffer contract violated");
+    if (retry_f16) *retry_f16 = bails != 0u;
+    return FSGPU_OK;
+}
+
 // The sample cascade of one batched search (mma_scan_kernels.cuh header): tiles per level, the
 // selection rank k' used for intermediate gates, and the per-query list capacity.
 struct MmaCascade {
@@ -545,11 +691,11 @@ static MmaCascade plan_cascade(uint64_t n_rows, uint32_t k, uint32_t tile_rows) 
 // which queries, if any, must be redone exactly).
 static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint32_t batch, uint32_t k,
                              uint64_t* d_out_keys, fsgpu_hit* d_out_hits, uint32_t* d_out_counts,
-                             cudaStream_t stream, bool allow_i8 = true) {
+                             cudaStream_t stream) {
     // the int8 form pays while the candidate volume stays small (k <= 32: top-50 loses) and the pass is
     // long enough to amortise its extra refine step (>= 1 M rows: at 1.25 M rows it is 5 % ahead, 0.82 vs
     // 0.87 ms at batch 1024) — profiles/r01_sweep_i8_form.txt
-    const bool i8 = allow_i8 && ix->i8_ok && env_int("FSGPU_MMA_I8", 1) != 0 &&
+    const bool i8 = !ix->force_f16 && ix->i8_penalty == 0 && ix->i8_ok && env_int("FSGPU_MMA_I8", 1) != 0 &&
                     k <= (uint32_t)std::max(0, env_int("FSGPU_I8_MAX_K", 32)) &&
                     ix->n_rows >= (uint64_t)std::max(0, env_int("FSGPU_I8_MIN_ROWS", 1000000));
     const uint32_t n_kb = ix->dim / (i8 ? 128 : kMmaKBlock);  // 128-byte K-blocks
@@ -589,14 +735,18 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
     const uint32_t refine_cap = stage_cap_for(cas.t0 < cas.n_tiles ? cas.random_part : (double)cas.t0 * cas.tile_rows / 2.5,
                                               kMmaStagePairs);
     const size_t gate_smem_max = mma_stage_smem_bytes(kMmaStageScores, false);
-    const size_t refine_smem = (size_t)fin_cap * 8 + 16 + mma_stage_smem_bytes(refine_cap, true) + (size_t)ix->dim * 4;
+    const size_t refine_smem = (size_t)fin_cap * 8 + 16 + mma_stage_smem_bytes(refine_cap, true) + (size_t)ix->dim * 4 +
+                               (size_t)kMmaTopListCap * 4;
     CUDA_TRY(cudaFuncSetAttribute(mma_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gate_smem_max));
     CUDA_TRY(cudaFuncSetAttribute(mma_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)refine_smem));
 
     const uint32_t max_queries = units * unit_queries;
-    std::vector<uint32_t> redo_host;
+    // a synchronous caller can re-run the batch in the f16 form when the int8 lists overflow for more than
+    // a few queries (100x tighter bound); a stream-asynchronous one has the device redo everything flagged
+    const uint32_t redo_limit = (i8 && ix->sync_caller) ? 4u : 0xFFFFFFFFu;
     for (uint32_t done = 0; done < batch; done += max_queries) {
         const uint32_t sub = std::min(max_queries, batch - done);
+        if (done) CUDA_TRY(cudaMemsetAsync(ix->d_error + 1, 0, 4, stream));  // redo_any of this sub-batch (begin_call cleared the first)
         const uint32_t n_units = (sub + unit_queries - 1) / unit_queries;  // query blocks or query pairs
         const uint32_t n_qb = quad ? 4 * n_units : pair ? 2 * n_units : n_units;  // 128-query blocks incl. padding
         const uint32_t g = units / n_units;
@@ -657,8 +807,14 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
         // pacing of the pairs that share a tile stream (only meaningful with several query pairs)
         const uint32_t lead = (uint32_t)std::max(0, env_int("FSGPU_MMA_LEAD", 16));
         const bool paced = pair && n_units > 1 && lead > 0;
-        const size_t progress_bytes = (size_t)g * n_units * 4;
-        if (paced) CUDA_TRY(ix->ws_progress.reserve(progress_bytes));
+        // one zeroed block per sub-batch, ONE memset: [pacing counters of the three passes | the exact-gate
+        // refine's per-query counts] (every separate memset is ~2 us of stream time)
+        const size_t progress_bytes = (((size_t)g * n_units * 4) + 15) & ~(size_t)15;
+        const size_t zero_bytes = 3 * progress_bytes + (size_t)slots * 4;
+        CUDA_TRY(ix->ws_progress.reserve(zero_bytes));
+        CUDA_TRY(cudaMemsetAsync(ix->ws_progress.p, 0, zero_bytes, stream));
+        auto progress_of = [&](int pass) { return reinterpret_cast<uint32_t*>(static_cast<char*>(ix->ws_progress.p) + pass * progress_bytes); };
+        uint32_t* i8_cnt = reinterpret_cast<uint32_t*>(static_cast<char*>(ix->ws_progress.p) + 3 * progress_bytes);
         a.lead = lead;
         MmaGateArgs ga{};
         ga.lists = MmaLists{a.cand, a.cand_count, n_qb, g, cap, quad ? 2u : pair ? 1u : 0u};
@@ -676,8 +832,7 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
             a.tile_count = level_tiles[lvl];
             a.dump_group_max = (lvl == 0 && cas.group_max) ? 1u : 0u;
             a.gate = have_gate ? ix->ws_gate.as<float>() : nullptr;
-            a.progress = paced ? ix->ws_progress.as<uint32_t>() : nullptr;
-            if (paced) CUDA_TRY(cudaMemsetAsync(ix->ws_progress.p, 0, progress_bytes, stream));
+            a.progress = paced ? progress_of(lvl) : nullptr;
             trace.mark(lvl ? "gate0" : "prep");
             scan_kernel<<<grid, kMmaThreads, smem, stream>>>(i8 ? ix->tm_qhat_i8 : ix->tm_qhat, i8 ? ix->tm_slab_i8 : ix->tm_slab, a);
             CUDA_TRY(cudaGetLastError());
@@ -695,8 +850,7 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
             if (exact_gate) {
                 // int8 form: tighten the gate of the full pass with an EXACT k-th best of this sample
                 CUDA_TRY(ix->ws_i8_top.reserve((size_t)slots * k * 8));
-                CUDA_TRY(ix->ws_i8_cnt.reserve((size_t)slots * 4));
-                CUDA_TRY(cudaMemsetAsync(ix->ws_i8_cnt.p, 0, (size_t)slots * 4, stream));
+
                 MmaRefineArgs ri{};
                 ri.lists = ga.lists;
                 ri.margin2 = ga.margin2;
@@ -712,14 +866,14 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
                 ri.reduce_order = ix->reduce_order;
                 ri.tail_fma = ix->tail_fma;
                 ri.out_keys = ix->ws_i8_top.as<uint64_t>();
-                ri.out_counts = ix->ws_i8_cnt.as<uint32_t>();
+                ri.out_counts = i8_cnt;
                 ri.error_flag = ix->d_error;
                 ri.redo_any = ix->d_error + 1;
                 ri.intermediate = 1;
                 mma_refine_kernel<<<sub, 256, refine_smem, stream>>>(ri);
                 CUDA_TRY(cudaGetLastError());
                 mma_exact_gate_kernel<<<(sub + 255) / 256, 256, 0, stream>>>(ix->ws_i8_top.as<uint64_t>(),
-                                                                           ix->ws_i8_cnt.as<uint32_t>(), k, sub,
+                                                                           i8_cnt, k, sub,
                                                                            ix->ws_margin.as<float>(), ix->ws_gate.as<float>());
                 CUDA_TRY(cudaGetLastError());
                 ix->prof.other_launches += 2;
@@ -730,8 +884,7 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
         a.tile_stride = 1;
         a.tile_count = cas.n_tiles;
         a.gate = have_gate ? ix->ws_gate.as<float>() : nullptr;
-        a.progress = paced ? ix->ws_progress.as<uint32_t>() : nullptr;
-        if (paced) CUDA_TRY(cudaMemsetAsync(ix->ws_progress.p, 0, progress_bytes, stream));
+        a.progress = paced ? progress_of(2) : nullptr;
         std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
         if (ix->profiling) {
             if (!ix->ev_free.empty()) {
@@ -783,37 +936,19 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
         CUDA_TRY(cudaGetLastError());
         trace.mark("refine");
 
-        // one 8-byte read-back into pinned memory tells whether anything is left to do
-        CUDA_TRY(cudaMemcpyAsync(ix->h_flags, ix->d_error, 8, cudaMemcpyDeviceToHost, stream));
-        trace.mark("flags_d2h");
-        CUDA_TRY(cudaStreamSynchronize(stream));
-        trace.report(sub, ix->n_rows);
-        if (ix->h_flags[0]) return fail(FSGPU_ERR_SUBSYSTEM, "gpu: top-k candidate buffer contract violated (refine)");
-        if (!ix->h_flags[1]) continue;
-        redo_host.resize(sub);
-        CUDA_TRY(cudaMemcpyAsync(redo_host.data(), ix->ws_redo.p, (size_t)sub * 4, cudaMemcpyDeviceToHost, stream));
-        CUDA_TRY(cudaStreamSynchronize(stream));
-        CUDA_TRY(cudaMemsetAsync(ix->d_error + 1, 0, 4, stream));  // the next super-batch starts clean
-        if (i8) {
-            // the int8 bound is wide; when it overflows the candidate lists of more than a few
-            // queries the f16 form (100x tighter bound) serves this and the remaining super-batches
-            uint32_t overflowed = 0;
-            for (uint32_t b = 0; b < sub; ++b) overflowed += redo_host[b] == 2u ? 1u : 0u;
-            if (overflowed > 4) {
-                const size_t o = (size_t)done;
-                return search_mma_locked(ix, d_queries + o * ix->dim, batch - done, k,
-                                         d_out_keys ? d_out_keys + o * k : nullptr, d_out_hits ? d_out_hits + o * k : nullptr,
-                                         d_out_counts ? d_out_counts + o : nullptr, stream, false);
-            }
-        }
-        for (uint32_t b = 0; b < sub; ++b) {
-            if (!redo_host[b]) continue;
-            ix->prof.redo_queries += 1;
-            const size_t o = (size_t)done + b;
-            int rc = search_exact_locked(ix, d_queries + o * ix->dim, 1, k, d_out_keys ? d_out_keys + o * k : nullptr,
-                                         d_out_hits ? d_out_hits + o * k : nullptr,
-                                         d_out_counts ? d_out_counts + o : nullptr, stream);
+        // flagged queries (non-finite / overflowing components, overflowed candidate lists) are re-run by
+        // the exact kernels on the same stream; those launches exit at once when nothing is flagged
+        {
+            const size_t o = (size_t)done;
+            int rc = enqueue_redo_locked(ix, q, sub, k, d_out_keys ? d_out_keys + o * k : nullptr,
+                                         d_out_hits ? d_out_hits + o * k : nullptr, d_out_counts ? d_out_counts + o : nullptr,
+                                         stream, redo_limit);
             if (rc) return rc;
+        }
+        trace.mark("redo");
+        if (trace.on) {
+            CUDA_TRY(cudaStreamSynchronize(stream));
+            trace.report(sub, ix->n_rows);
         }
     }
     return FSGPU_OK;
@@ -1051,17 +1186,12 @@ static int search_main_locked(const fsgpu_index* ix, const float* d_queries, uin
     const int min_batch = env_int("FSGPU_MMA_MIN_BATCH", 3);
     const bool mma = ix->mma_ok && min_batch > 0 && batch >= (uint32_t)min_batch && k >= 1 && k <= kMmaMaxK &&
                      ix->n_rows > 0;
-    if (mma) {
-        CUDA_TRY(cudaMemsetAsync(ix->d_error, 0, 8, stream));
-        return search_mma_locked(ix, d_queries, batch, k, d_out_keys, d_out_hits, d_out_counts, stream);
-    }
+    if (mma) return search_mma_locked(ix, d_queries, batch, k, d_out_keys, d_out_hits, d_out_counts, stream);
     // large k off the tensor-core path (few queries, or k past its ceiling): radix select; it needs 16-byte
     // rows for the int8 codes only, any dim otherwise
     const uint32_t select_min_k = (uint32_t)std::max(1, env_int("FSGPU_SELECT_MIN_K", 129));
-    if (k >= select_min_k && k <= kSelMaxK && ix->n_rows > 0 && ix->n_rows <= 0xFFFFFFF0ull) {
-        CUDA_TRY(cudaMemsetAsync(ix->d_error, 0, 4, stream));
+    if (k >= select_min_k && k <= kSelMaxK && ix->n_rows > 0 && ix->n_rows <= 0xFFFFFFF0ull)
         return search_select_locked(ix, d_queries, batch, k, d_out_keys, d_out_hits, d_out_counts, stream);
-    }
     return search_exact_locked(ix, d_queries, batch, k, d_out_keys, d_out_hits, d_out_counts, stream);
 }
 
@@ -1178,14 +1308,6 @@ static int search_device_locked(const fsgpu_index* ix, const float* d_queries, u
     return merge_single_list_locked(ix, m, batch, stream);
 }
 
-static int check_error_flag(const fsgpu_index* ix, cudaStream_t stream) {
-    uint32_t flag = 0;
-    CUDA_TRY(cudaMemcpyAsync(&flag, ix->d_error, 4, cudaMemcpyDeviceToHost, stream));
-    CUDA_TRY(cudaStreamSynchronize(stream));
-    if (flag) return fail(FSGPU_ERR_SUBSYSTEM, "gpu: top-k candidate buffer contract violated");
-    return FSGPU_OK;
-}
-
 // ─── index creation ─────────────────────────────────────────────────────────────────────────
 static int index_alloc_common(fsgpu_index* ix, const fsgpu_index_options* o, uint64_t n_rows,
                               uint32_t dim) {
@@ -1214,9 +1336,12 @@ static int index_alloc_common(fsgpu_index* ix, const fsgpu_index_options* o, uin
                     ix->device, prop.major, prop.minor);
     ix->num_sms = prop.multiProcessorCount;
     CUDA_TRY(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
-    CUDA_TRY(cudaMalloc(&ix->d_error, 8));
-    CUDA_TRY(cudaMemset(ix->d_error, 0, 8));
-    CUDA_TRY(cudaHostAlloc(&ix->h_flags, 8, cudaHostAllocDefault));
+    CUDA_TRY(cudaMalloc(&ix->d_error, 16));
+    CUDA_TRY(cudaMemset(ix->d_error, 0, 16));
+    CUDA_TRY(cudaHostAlloc(&ix->h_flags, 16, cudaHostAllocDefault));
+    memset(ix->h_flags, 0, 16);
+    CUDA_TRY(cudaEventCreateWithFlags(&ix->ev_last, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&ix->ev_flags, cudaEventDisableTiming));
     return FSGPU_OK;
 }
 
@@ -1241,6 +1366,8 @@ extern "C" void fsgpu_index_destroy(fsgpu_index* ix) {
         if (ix->d_tomb) cudaFree(ix->d_tomb);
         if (ix->d_error) cudaFree(ix->d_error);
         if (ix->h_flags) cudaFreeHost(ix->h_flags);
+        if (ix->ev_last) cudaEventDestroy(ix->ev_last);
+        if (ix->ev_flags) cudaEventDestroy(ix->ev_flags);
         for (auto* v : {&ix->ev_pending, &ix->ev_free})
             for (auto& ev : *v) {
                 cudaEventDestroy(ev.first);
@@ -1252,7 +1379,7 @@ extern "C" void fsgpu_index_destroy(fsgpu_index* ix) {
                           &ix->ws_cand_count, &ix->d_wal, &ix->ws_wal_main, &ix->ws_wal_keys, &ix->d_hashes,
                           &ix->ws_allowed, &ix->ws_gather_pos, &ix->ws_gather_count, &ix->ws_gather_keys,
                           &ix->d_slab_i8, &ix->ws_qscale, &ix->ws_approx, &ix->ws_i8_top, &ix->ws_i8_cnt,
-                          &ix->ws_sel_pos, &ix->ws_sel_pos2, &ix->ws_sel_state})
+                          &ix->ws_sel_pos, &ix->ws_sel_pos2, &ix->ws_sel_state, &ix->ws_redo_slots, &ix->ws_redo_partial})
             b->release();
         if (ix->stream) cudaStreamDestroy(ix->stream);
     }
@@ -1451,6 +1578,7 @@ extern "C" int fsgpu_index_profile_read(fsgpu_index* ix, fsgpu_profile* out, int
     if (!ix || !out) return fail(FSGPU_ERR_INVALID_CONFIG, "NULL argument");
     std::lock_guard<std::mutex> lock(ix->mu);
     DeviceGuard g(ix->device);
+    consume_flags_locked(ix, true);
     for (auto& ev : ix->ev_pending) {
         CUDA_TRY(cudaEventSynchronize(ev.second));
         float ms = 0.0f;
@@ -1473,10 +1601,31 @@ extern "C" int fsgpu_search_top_k_device(const fsgpu_index* ix, const float* d_q
     std::lock_guard<std::mutex> lock(ix->mu);
     DeviceGuard g(ix->device);
     cudaStream_t s = stream ? (cudaStream_t)stream : ix->stream;
-    if (k && d_out_keys) CUDA_TRY(cudaMemsetAsync(d_out_keys, 0, (size_t)batch * k * 8, s));
-    int rc = search_device_locked(ix, d_queries, batch, k, d_out_keys, d_out_hits, d_out_counts, s);
-    if (rc) return rc;
-    if (!stream) return check_error_flag(ix, s);
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        int rc = begin_call_locked(ix, s, stream == nullptr);
+        if (rc) return rc;
+        if (k && d_out_keys) CUDA_TRY(cudaMemsetAsync(d_out_keys, 0, (size_t)batch * k * 8, s));
+        ix->force_f16 = attempt == 1;
+        rc = search_device_locked(ix, d_queries, batch, k, d_out_keys, d_out_hits, d_out_counts, s);
+        ix->force_f16 = false;
+        if (!rc) rc = end_call_locked(ix, s);
+        if (rc) return rc;
+        if (stream) return FSGPU_OK;  // asynchronous: fsgpu_index_last_status reports once the stream is done
+        bool retry = false;
+        rc = finish_sync_call_locked(ix, s, &retry);
+        if (rc || !retry) return rc;
+    }
+    return FSGPU_OK;
+}
+
+extern "C" int fsgpu_index_last_status(const fsgpu_index* ix, uint32_t* out_flags) {
+    if (!ix || !out_flags) return fail(FSGPU_ERR_INVALID_CONFIG, "NULL argument");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    DeviceGuard g(ix->device);
+    if (ix->flags_pending) CUDA_TRY(cudaEventSynchronize(ix->ev_flags));
+    memcpy(out_flags, ix->h_flags, 16);
+    consume_flags_locked(ix, true);
+    if (out_flags[0]) return fail(FSGPU_ERR_SUBSYSTEM, "gpu: top-k candidate buffer contract violated");
     return FSGPU_OK;
 }
 
@@ -1526,10 +1675,20 @@ extern "C" int fsgpu_search_top_k_filtered_device(const fsgpu_index* ix, const f
     std::lock_guard<std::mutex> lock(ix->mu);
     DeviceGuard g(ix->device);
     cudaStream_t s = stream ? (cudaStream_t)stream : ix->stream;
-    if (k && d_out_keys) CUDA_TRY(cudaMemsetAsync(d_out_keys, 0, (size_t)batch * k * 8, s));
-    int rc = search_filtered_locked(ix, d_queries, batch, k, d_allow_bitmap, d_out_keys, d_out_hits, d_out_counts, s);
-    if (rc) return rc;
-    if (!stream) return check_error_flag(ix, s);
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        int rc = begin_call_locked(ix, s, stream == nullptr);
+        if (rc) return rc;
+        if (k && d_out_keys) CUDA_TRY(cudaMemsetAsync(d_out_keys, 0, (size_t)batch * k * 8, s));
+        ix->force_f16 = attempt == 1;
+        rc = search_filtered_locked(ix, d_queries, batch, k, d_allow_bitmap, d_out_keys, d_out_hits, d_out_counts, s);
+        ix->force_f16 = false;
+        if (!rc) rc = end_call_locked(ix, s);
+        if (rc) return rc;
+        if (stream) return FSGPU_OK;
+        bool retry = false;
+        rc = finish_sync_call_locked(ix, s, &retry);
+        if (rc || !retry) return rc;
+    }
     return FSGPU_OK;
 }
 
@@ -1550,12 +1709,10 @@ extern "C" int fsgpu_search_top_k_filtered(const fsgpu_index* ix, const float* q
     CUDA_TRY(ix->ws_queries.reserve((size_t)batch * dim * 4));
     CUDA_TRY(ix->ws_hits.reserve((size_t)batch * k * sizeof(fsgpu_hit)));
     CUDA_TRY(ix->ws_counts.reserve((size_t)batch * 4));
-    CUDA_TRY(cudaMemcpyAsync(ix->ws_queries.p, queries, (size_t)batch * dim * 4, cudaMemcpyHostToDevice, s));
     const uint8_t* d_allow = nullptr;
     if (allow_bitmap) {
         const size_t n_bytes = (ix->n_rows + ix->n_wal + 7) / 8;
         CUDA_TRY(ix->ws_allow.reserve(n_bytes));
-        CUDA_TRY(cudaMemcpyAsync(ix->ws_allow.p, allow_bitmap, n_bytes, cudaMemcpyHostToDevice, s));
         d_allow = ix->ws_allow.as<uint8_t>();
     }
     // One or two finite queries on an index that holds int8 codes: int8 pass 1 + exact re-score
@@ -1568,19 +1725,30 @@ extern "C" int fsgpu_search_top_k_filtered(const fsgpu_index* ix, const float* q
     for (size_t i = 0; i8_single && i < (size_t)batch * dim; ++i) i8_single = std::isfinite(queries[i]);
     for (int attempt = 0; attempt < 2; ++attempt) {
         const bool i8_now = i8_single && attempt == 0;
-        if (i8_now) CUDA_TRY(cudaMemsetAsync(ix->d_error, 0, 8, s));
+        int rc = begin_call_locked(ix, s, true);
+        if (rc) return rc;
+        if (attempt == 0) {  // (the uploads above were enqueued before the wait: repeat them behind it)
+            CUDA_TRY(cudaMemcpyAsync(ix->ws_queries.p, queries, (size_t)batch * dim * 4, cudaMemcpyHostToDevice, s));
+            if (allow_bitmap)
+                CUDA_TRY(cudaMemcpyAsync(ix->ws_allow.p, allow_bitmap, (ix->n_rows + ix->n_wal + 7) / 8, cudaMemcpyHostToDevice, s));
+        }
         ix->use_i8_single = i8_now;
-        int rc = search_filtered_locked(ix, ix->ws_queries.as<float>(), batch, k, d_allow, nullptr,
-                                        ix->ws_hits.as<fsgpu_hit>(), ix->ws_counts.as<uint32_t>(), s);
+        ix->force_f16 = attempt == 1;
+        rc = search_filtered_locked(ix, ix->ws_queries.as<float>(), batch, k, d_allow, nullptr,
+                                    ix->ws_hits.as<fsgpu_hit>(), ix->ws_counts.as<uint32_t>(), s);
         ix->use_i8_single = false;
+        ix->force_f16 = false;
         if (rc) return rc;
         CUDA_TRY(cudaMemcpyAsync(out, ix->ws_hits.p, (size_t)batch * k * sizeof(fsgpu_hit), cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaMemcpyAsync(out_counts, ix->ws_counts.p, (size_t)batch * 4, cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(cudaMemcpyAsync(ix->h_flags, ix->d_error, 8, cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(cudaStreamSynchronize(s));
-        if (ix->h_flags[0]) return fail(FSGPU_ERR_SUBSYSTEM, "gpu: top-k candidate buffer contract violated");
-        if (!(i8_now && ix->h_flags[1])) break;
-        CUDA_TRY(cudaMemsetAsync(ix->d_error, 0, 8, s));
+        rc = end_call_locked(ix, s);
+        if (rc) return rc;
+        const uint32_t* hf = ix->h_flags;
+        bool retry = false;
+        rc = finish_sync_call_locked(ix, s, &retry);
+        if (rc) return rc;
+        // int8 pass 1: word 1 = its position list overflowed; batched int8 form: bails -> f16 forms
+        if (!((i8_now && hf[1]) || retry)) break;
     }
     return FSGPU_OK;
 }
@@ -1624,21 +1792,24 @@ extern "C" int fsgpu_search_top_k_hashes(const fsgpu_index* ix, const float* que
     CUDA_TRY(ix->ws_queries.reserve((size_t)batch * dim * 4));
     CUDA_TRY(ix->ws_hits.reserve((size_t)batch * k * sizeof(fsgpu_hit)));
     CUDA_TRY(ix->ws_counts.reserve((size_t)batch * 4));
-    CUDA_TRY(cudaMemcpyAsync(ix->ws_queries.p, queries, (size_t)batch * dim * 4, cudaMemcpyHostToDevice, s));
-    if (ix->n_wal) {
-        // WAL rows: the host evaluated the filter on their doc ids (search.rs:1457-1465); bit w = WAL row w
-        const size_t wal_bytes = (ix->n_wal + 7) / 8;
-        CUDA_TRY(ix->ws_allow.reserve(wal_bytes));
-        if (wal_allow_bitmap)
-            CUDA_TRY(cudaMemcpyAsync(ix->ws_allow.p, wal_allow_bitmap, wal_bytes, cudaMemcpyHostToDevice, s));
-        else
-            CUDA_TRY(cudaMemsetAsync(ix->ws_allow.p, 0xFF, wal_bytes, s));
-    }
+    const size_t wal_bytes = (ix->n_wal + 7) / 8;
+    if (ix->n_wal) CUDA_TRY(ix->ws_allow.reserve(wal_bytes));
     // try_gather_filtered (search.rs:1114-1131): the selective arm when allowed * 50 < record_count
     constexpr uint64_t kGatherSelectivityDivisor = 50;  // search.rs:33
     bool gather = ix->n_rows > 0 && (uint64_t)n_allowed * kGatherSelectivityDivisor < ix->n_rows;
+    bool force_f16 = false;
     const uint32_t cap = std::max(64u, 2 * n_allowed);  // rows sharing a hash (collisions, duplicate doc ids)
-    for (int attempt = 0; attempt < 2; ++attempt) {
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        int rc0 = begin_call_locked(ix, s, true);
+        if (rc0) return rc0;
+        CUDA_TRY(cudaMemcpyAsync(ix->ws_queries.p, queries, (size_t)batch * dim * 4, cudaMemcpyHostToDevice, s));
+        if (ix->n_wal) {
+            // WAL rows: the host evaluated the filter on their doc ids (search.rs:1457-1465); bit w = WAL row w
+            if (wal_allow_bitmap)
+                CUDA_TRY(cudaMemcpyAsync(ix->ws_allow.p, wal_allow_bitmap, wal_bytes, cudaMemcpyHostToDevice, s));
+            else
+                CUDA_TRY(cudaMemsetAsync(ix->ws_allow.p, 0xFF, wal_bytes, s));
+        }
         if (ix->n_rows > 0) {
             const size_t n_bytes = (ix->n_rows + 7) / 8;
             CUDA_TRY(ix->ws_excl.reserve(n_bytes));
@@ -1666,8 +1837,10 @@ extern "C" int fsgpu_search_top_k_hashes(const fsgpu_index* ix, const float* que
         // WAL allow bits live at bit n_rows + w of d_wal_allow: point it so that bit 0 of ws_allow lands there
         ix->d_wal_allow = ix->n_wal ? ix->ws_allow.as<uint8_t>() : nullptr;
         ix->wal_allow_bit0_is_zero = true;
+        ix->force_f16 = force_f16;
         int rc = search_device_locked(ix, ix->ws_queries.as<float>(), batch, k, nullptr,
                                       ix->ws_hits.as<fsgpu_hit>(), ix->ws_counts.as<uint32_t>(), s);
+        ix->force_f16 = false;
         ix->d_excl = nullptr;
         ix->d_wal_allow = nullptr;
         ix->wal_allow_bit0_is_zero = false;
@@ -1680,8 +1853,15 @@ extern "C" int fsgpu_search_top_k_hashes(const fsgpu_index* ix, const float* que
             CUDA_TRY(cudaMemcpyAsync(&listed, ix->ws_gather_count.p, 4, cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaMemcpyAsync(out, ix->ws_hits.p, (size_t)batch * k * sizeof(fsgpu_hit), cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaMemcpyAsync(out_counts, ix->ws_counts.p, (size_t)batch * 4, cudaMemcpyDeviceToHost, s));
-        rc = check_error_flag(ix, s);
+        rc = end_call_locked(ix, s);
         if (rc) return rc;
+        bool retry = false;
+        rc = finish_sync_call_locked(ix, s, &retry);
+        if (rc) return rc;
+        if (retry && !force_f16) {  // the batched int8 form bailed: same call in the f16 form
+            force_f16 = true;
+            continue;
+        }
         if (!gather || listed <= cap) {
             if (out_used_gather) *out_used_gather = gather ? 1 : 0;
             return FSGPU_OK;
@@ -1824,6 +2004,8 @@ extern "C" int fsgpu_scores_for_rows(const fsgpu_index* ix, const float* query, 
         CUDA_TRY(ix->ws_rows.reserve((size_t)n * 4));
         CUDA_TRY(ix->ws_scores.reserve((size_t)n * 4));
         CUDA_TRY(ix->ws_present.reserve(n));
+        int rc = begin_call_locked(ix, s, true);
+        if (rc) return rc;
         CUDA_TRY(cudaMemcpyAsync(ix->ws_queries.p, query, (size_t)dim * 4, cudaMemcpyHostToDevice, s));
         CUDA_TRY(cudaMemcpyAsync(ix->ws_rows.p, rows, (size_t)n * 4, cudaMemcpyHostToDevice, s));
         dim3 grid((n + kScanWarps - 1) / kScanWarps, 1);
@@ -1835,7 +2017,10 @@ extern "C" int fsgpu_scores_for_rows(const fsgpu_index* ix, const float* query, 
         CUDA_TRY(cudaMemcpyAsync(out_scores, ix->ws_scores.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
         if (out_present)
             CUDA_TRY(cudaMemcpyAsync(out_present, ix->ws_present.p, n, cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(cudaStreamSynchronize(s));
+        rc = end_call_locked(ix, s);
+        if (rc) return rc;
+        rc = finish_sync_call_locked(ix, s, nullptr);
+        if (rc) return rc;
     }
     return FSGPU_OK;
 }

@@ -111,6 +111,53 @@ __device__ __forceinline__ float warp_exact_dot(const uint16_t* __restrict__ row
     return result;
 }
 
+// ─── exact dot of EIGHT gathered rows per warp (dim % 32 == 0) ──────────────────────────────
+// Lane 4r + a owns accumulator a of row r — the lane mapping of scan_topk_fast_kernel — so a warp
+// re-scores eight candidate rows with 16-byte loads all in flight at once instead of eight dependent
+// one-row gathers (the refine kernel's exact dots were latency-bound: 37 % of its stall samples,
+// profiles/r02_refine_hot_lines.txt).  `row` points at THIS lane's row (lanes of a group agree), `q`
+// at the query in shared memory (16-byte aligned).  Chunk 4j + a goes to accumulator a in order of j
+// starting from 0.0, `(s0+s1)+(s2+s3)` is two xor-shuffles, then the configured 8-lane reduce: bit for
+// bit simd.rs:418-439.  Every lane of group r returns row r's score.
+__device__ __forceinline__ float warp_exact_dot8(const uint16_t* __restrict__ row, const float* __restrict__ q,
+                                                 uint32_t dim, int reduce_order) {
+    const uint32_t a = threadIdx.x & 3u;
+    const uint4* p = reinterpret_cast<const uint4*>(row) + a;
+    const uint32_t nj = dim >> 5;
+    float v[8];
+#pragma unroll
+    for (int l = 0; l < 8; ++l) v[l] = 0.0f;
+#pragma unroll 4
+    for (uint32_t j = 0; j < nj; ++j) {
+        uint4 x;
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w)
+                     : "l"(p + 4u * j));
+        const float2 x0 = __half22float2(*reinterpret_cast<const __half2*>(&x.x));
+        const float2 x1 = __half22float2(*reinterpret_cast<const __half2*>(&x.y));
+        const float2 x2 = __half22float2(*reinterpret_cast<const __half2*>(&x.z));
+        const float2 x3 = __half22float2(*reinterpret_cast<const __half2*>(&x.w));
+        const float4* qp = reinterpret_cast<const float4*>(q + (4u * j + a) * 8u);
+        const float4 q0 = qp[0], q1 = qp[1];
+        v[0] = add_rn(v[0], mul_rn(x0.x, q0.x));
+        v[1] = add_rn(v[1], mul_rn(x0.y, q0.y));
+        v[2] = add_rn(v[2], mul_rn(x1.x, q0.z));
+        v[3] = add_rn(v[3], mul_rn(x1.y, q0.w));
+        v[4] = add_rn(v[4], mul_rn(x2.x, q1.x));
+        v[5] = add_rn(v[5], mul_rn(x2.y, q1.y));
+        v[6] = add_rn(v[6], mul_rn(x3.x, q1.z));
+        v[7] = add_rn(v[7], mul_rn(x3.y, q1.w));
+    }
+#pragma unroll
+    for (int l = 0; l < 8; ++l) {
+        float sacc = v[l];
+        sacc = add_rn(sacc, __shfl_xor_sync(0xffffffffu, sacc, 1));  // s0+s1 | s2+s3
+        sacc = add_rn(sacc, __shfl_xor_sync(0xffffffffu, sacc, 2));  // (s0+s1)+(s2+s3)
+        v[l] = sacc;
+    }
+    return reduce8(v, reduce_order);
+}
+
 // ─── exact f32·f32 dot for resident WAL rows: one warp per row, any dim ─────────────────────
 // dot_product_f32_f32 (crates/frankensearch-index/src/simd.rs:161-222 AVX2, :1559-1587 generic):
 // four 8-lane accumulators over whole groups of 32 elements, `(acc0+acc1)+(acc2+acc3)` FIRST, then

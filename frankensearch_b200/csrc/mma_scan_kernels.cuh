@@ -1116,15 +1116,18 @@ __device__ __forceinline__ uint32_t mma_stage_lists(const MmaStageSmem& sm, cons
     __syncthreads();
     const uint32_t total = sm.offs[n_lists];
     if (total > sm.cap) return total;
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
-    for (uint32_t j = warp; j < n_lists; j += n_warps) {
-        const uint32_t off = sm.offs[j], n = sm.offs[j + 1] - off;
-        const MmaCand* list = l.cand + mma_list_slot(l, b, j) * l.cap;
-        for (uint32_t i = lane; i < n; i += 32) {
-            const MmaCand c = list[i];
-            sm.score[off + i] = ordered_score(c.score);
-            if (sm.row) sm.row[off + i] = c.row;
+    // one thread per flattened entry: its list is found by a binary search of the offsets, so every
+    // global load of the copy is in flight at once (a warp walking whole lists paid a dependent L2 round
+    // trip per list: 9-37 of them in a row)
+    for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+        uint32_t lo = 0, hi = n_lists;  // last j with offs[j] <= i
+        while (hi - lo > 1u) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (sm.offs[mid] <= i) lo = mid; else hi = mid;
         }
+        const MmaCand c = l.cand[mma_list_slot(l, b, lo) * l.cap + (i - sm.offs[lo])];
+        sm.score[i] = ordered_score(c.score);
+        if (sm.row) sm.row[i] = c.row;
     }
     __syncthreads();
     return total;
@@ -1291,6 +1294,46 @@ __device__ __forceinline__ void mma_rescore_round(const MmaRefineArgs& args, con
     }
 }
 
+// CTA-collective: exact reference scores of the `n` rows listed in `rows` (shared memory, GLOBAL row
+// numbers), offered to the bounded top-k buffer.  Eight rows per warp step (warp_exact_dot8) when
+// dim % 32 == 0, compaction whenever the buffer could fill.
+__device__ __forceinline__ void mma_rescore_list(const MmaRefineArgs& args, const CandBuf& buf, const float* q,
+                                                 const uint32_t* rows, uint32_t n) {
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u, n_warps = blockDim.x >> 5;
+    const uint32_t chunk = (args.buf_cap - args.k) & ~7u;  // pushes the buffer absorbs between compactions
+    const bool wide = (args.dim & 31u) == 0u;
+    for (uint32_t c0 = 0; c0 < n; c0 += chunk) {
+        const uint32_t c1 = min(n, c0 + chunk);
+        if (wide) {
+            for (uint32_t e0 = c0 + warp * 8u; e0 < c1; e0 += n_warps * 8u) {
+                const uint32_t e = e0 + (lane >> 2);
+                const bool valid = e < c1;
+                const uint32_t grow = rows[valid ? e : c1 - 1u];
+                const float sx = warp_exact_dot8(args.slab + ((uint64_t)grow - args.row_base) * args.dim, q, args.dim,
+                                                 args.reduce_order);
+                if (valid && (lane & 3u) == 0u) {
+                    const uint64_t exact = make_key(sx, grow);
+                    if (exact > *buf.tau && !cand_push(buf, args.buf_cap, exact)) atomicExch(args.error_flag, 1u);
+                }
+            }
+        } else {
+            for (uint32_t e = c0 + warp; e < c1; e += n_warps) {
+                const uint32_t grow = rows[e];
+                const float sx = warp_exact_dot(args.slab + ((uint64_t)grow - args.row_base) * args.dim, q, args.dim,
+                                                args.reduce_order, args.tail_fma);
+                if (lane == 0u) {
+                    const uint64_t exact = make_key(sx, grow);
+                    if (exact > *buf.tau && !cand_push(buf, args.buf_cap, exact)) atomicExch(args.error_flag, 1u);
+                }
+            }
+        }
+        __syncthreads();
+        if (c1 < n) cand_compact(buf, args.buf_cap, args.k);
+    }
+}
+
+constexpr uint32_t kMmaTopListCap = 2048;  // dense list of the approximate top-k (ties included) in the refine
+
 __global__ void __launch_bounds__(256) mma_refine_kernel(const MmaRefineArgs args) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* cand = reinterpret_cast<uint64_t*>(smem_raw);
@@ -1362,13 +1405,29 @@ __global__ void __launch_bounds__(256) mma_refine_kernel(const MmaRefineArgs arg
         // (tau_x >= tau_a - e).  With the int8 bound that is ~4x fewer exact dots in round 2.
         uint32_t lo_u = gate_u;
         if (top_u != 0xFFFFFFFFu) {
-            for (uint32_t i0 = 0; i0 < total; i0 += step) {  // CTA-uniform trip count
-                const uint32_t i = i0 + threadIdx.x;
-                const bool pass = i < total && sm.score[i] >= top_u;
-                mma_rescore_round(args, buf, q, pass, pass ? sm.row[i] : 0u);
-                __syncthreads();
-                if (*cnt > trigger) cand_compact(buf, args.buf_cap, args.k);
-                __syncthreads();
+            // the approximate top-k as a dense list (normally exactly k rows; a tie band at tau_a can make
+            // it longer than the list: then the flattened array is walked with a barrier per 256 entries)
+            uint32_t* top_list = reinterpret_cast<uint32_t*>(q + args.dim);
+            if (threadIdx.x == 0) sm.ctl[2] = 0u;
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < total; i += step)
+                if (sm.score[i] >= top_u) {
+                    const uint32_t slot = atomicAdd(&sm.ctl[2], 1u);
+                    if (slot < kMmaTopListCap) top_list[slot] = sm.row[i];
+                }
+            __syncthreads();
+            const uint32_t n_top = sm.ctl[2];
+            if (n_top <= kMmaTopListCap) {
+                mma_rescore_list(args, buf, q, top_list, n_top);
+            } else {
+                for (uint32_t i0 = 0; i0 < total; i0 += step) {  // CTA-uniform trip count
+                    const uint32_t i = i0 + threadIdx.x;
+                    const bool pass = i < total && sm.score[i] >= top_u;
+                    mma_rescore_round(args, buf, q, pass, pass ? sm.row[i] : 0u);
+                    __syncthreads();
+                    if (*cnt > trigger) cand_compact(buf, args.buf_cap, args.k);
+                    __syncthreads();
+                }
             }
             cand_compact(buf, args.buf_cap, args.k);
             if (*cnt >= args.k) {
@@ -1387,24 +1446,7 @@ __global__ void __launch_bounds__(256) mma_refine_kernel(const MmaRefineArgs arg
         for (uint32_t r = 0, i = threadIdx.x; i < total; ++r, i += step)
             if (mine & (1ull << r)) band[atomicAdd(&sm.ctl[2], 1u)] = sm.row[i];
         __syncthreads();
-        const uint32_t n_band = sm.ctl[2];
-        const uint32_t warp = threadIdx.x >> 5, n_warps = step >> 5;
-        const uint32_t chunk = (args.buf_cap - args.k) & ~7u;  // pushes the buffer absorbs between compactions
-        for (uint32_t c0 = 0; c0 < n_band; c0 += chunk) {
-            const uint32_t c1 = min(n_band, c0 + chunk);
-            for (uint32_t e = c0 + warp; e < c1; e += n_warps) {
-                const uint32_t grow = band[e];
-                const uint64_t local = (uint64_t)grow - args.row_base;
-                const float sx = warp_exact_dot(args.slab + local * args.dim, q, args.dim, args.reduce_order,
-                                                args.tail_fma);
-                if ((threadIdx.x & 31u) == 0u) {
-                    const uint64_t exact = make_key(sx, grow);
-                    if (exact > *tau && !cand_push(buf, args.buf_cap, exact)) atomicExch(args.error_flag, 1u);
-                }
-            }
-            __syncthreads();
-            if (c1 < n_band) cand_compact(buf, args.buf_cap, args.k);
-        }
+        mma_rescore_list(args, buf, q, band, sm.ctl[2]);
     } else {
         for (uint32_t j = 0; j < mma_list_count(l); ++j) {
             const uint32_t n = sm.offs[j + 1] - sm.offs[j];

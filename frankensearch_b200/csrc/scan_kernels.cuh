@@ -16,7 +16,27 @@ namespace fsgpu {
 constexpr int kScanThreads = 256;
 constexpr int kScanWarps = kScanThreads / 32;
 
+// Device-side "redo" launches: the batched tensor-core search flags the queries its bound cannot
+// cover (non-finite / overflowing components, a candidate list that overflowed) and the SAME stream
+// then runs the exact kernels below over just those queries — no host round trip.  A launch with
+// `flags` set serves the flagged queries of ranks [first, first + max) (rank = position among the
+// flagged, ascending query index), one after another, partial slot i = rank - first.
+constexpr uint32_t kRedoMaxPerLaunch = 1024;
+struct RedoArgs {
+    const uint32_t* flags;  // [n] != 0: the query needs the exact path; nullptr = a normal launch
+    const uint32_t* any;    // nullable: nothing is flagged when *any == 0 (the common case: exit at once)
+    uint32_t n;             // queries of the (sub-)batch
+    uint32_t first, max;    // flagged ranks served by this launch (max <= kRedoMaxPerLaunch)
+    uint32_t limit;         // more flagged queries than this: serve none and count a bail (the caller
+                            // re-runs the batch another way)
+    uint32_t* bail;         // bail counter
+    uint32_t* slots;        // [max] out: query index whose partials sit in slot i (written by CTA 0)
+    uint32_t* round_n;      // out: slots filled by this launch
+    uint32_t* served;       // nullable: += flagged queries (CTA 0 of the first launch)
+};
+
 struct ScanArgs {
+    RedoArgs redo;
     const uint16_t* slab;      // [n_rows, dim] f16 bits
     const uint8_t* tombstones; // packed bitmap or nullptr
     const float* queries;      // [QB, dim] f32 (device)
@@ -48,6 +68,56 @@ __device__ __forceinline__ void unpack8(const uint4& x, float f[8]) {
     const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&x.w));
     f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
     f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+
+// CTA-collective: collects the flagged queries of ranks [first, first + max) into `list` (shared,
+// kRedoMaxPerLaunch entries) and returns how many this launch serves (0: nothing to do).  Every CTA of
+// the launch computes the same list; CTA 0 publishes it for the merge launch that follows.
+__device__ __forceinline__ uint32_t redo_collect(const RedoArgs& r, uint32_t* list) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_running;
+    if (r.any && *r.any == 0u) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) *r.round_n = 0u;
+        return 0u;
+    }
+    if (threadIdx.x == 0) s_running = 0u;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    for (uint32_t base = 0; base < r.n; base += blockDim.x) {  // CTA-uniform trip count
+        const uint32_t b = base + threadIdx.x;
+        const bool f = b < r.n && r.flags[b] != 0u;
+        const uint32_t m = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) s_warp[warp] = __popc(m);
+        __syncthreads();
+        uint32_t before = s_running;
+        for (uint32_t w = 0; w < warp; ++w) before += s_warp[w];
+        const uint32_t rank = before + __popc(m & ((1u << lane) - 1u));
+        if (f && rank >= r.first && rank - r.first < r.max) list[rank - r.first] = b;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t t = 0;
+            for (uint32_t w = 0; w < n_warps; ++w) t += s_warp[w];
+            s_running += t;
+        }
+        __syncthreads();
+    }
+    const uint32_t total = s_running;
+    if (total > r.limit) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            if (r.first == 0u) atomicAdd(r.bail, 1u);
+            *r.round_n = 0u;
+        }
+        return 0u;
+    }
+    const uint32_t mine = total > r.first ? min(r.max, total - r.first) : 0u;
+    if (blockIdx.x == 0) {
+        for (uint32_t i = threadIdx.x; i < mine; i += blockDim.x) r.slots[i] = list[i];
+        if (threadIdx.x == 0) {
+            *r.round_n = mine;
+            if (r.served && r.first == 0u) atomicAdd(r.served, total);
+        }
+    }
+    return mine;
 }
 
 // Shared-memory carve-up shared by the scan kernels.
@@ -103,10 +173,10 @@ __device__ __forceinline__ void scan_offer(const ScanSmem& sm, const ScanArgs& a
 }
 
 template <int QB>
-__device__ __forceinline__ void scan_write_partials(const ScanSmem& sm, const ScanArgs& args) {
+__device__ __forceinline__ void scan_write_partials(const ScanSmem& sm, const ScanArgs& args, uint32_t slot = 0) {
     for (int qi = 0; qi < QB; ++qi) {
         const uint32_t c = min(sm.cnt[qi], args.k);
-        uint64_t* out = args.partial + ((size_t)blockIdx.x * QB + qi) * args.k;
+        uint64_t* out = args.partial + (((size_t)slot * gridDim.x + blockIdx.x) * QB + qi) * args.k;
         const uint64_t* src = sm.cand + (size_t)qi * args.cap;
         for (uint32_t i = threadIdx.x; i < args.k; i += blockDim.x) out[i] = i < c ? src[i] : 0ull;
     }
@@ -279,24 +349,30 @@ scan_topk_fast_kernel(const ScanArgs args) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t dim = NJ * 32;
     const ScanSmem sm = carve_scan_smem(smem_raw, QB, args.cap, dim);
-
-    bool q_ok = true;  // packed-path precondition: every non-zero |q_i| >= 2^-76
-    for (uint32_t i = threadIdx.x; i < QB * dim; i += blockDim.x) {
-        const float qv = args.queries[i];
-        sm.q[i] = qv;
-        const uint32_t mag = __float_as_uint(qv) & 0x7FFFFFFFu;
-        q_ok = q_ok && (mag == 0u || mag >= 0x19800000u);
+    __shared__ uint32_t s_redo[QB == 1 ? kRedoMaxPerLaunch : 1];
+    uint32_t n_serve = 1;
+    if (QB == 1 && args.redo.flags) n_serve = redo_collect(args.redo, s_redo);  // a redo launch (QB == 1 only)
+    for (uint32_t slot = 0; slot < n_serve; ++slot) {
+        const float* queries = (QB == 1 && args.redo.flags) ? args.queries + (size_t)s_redo[slot] * dim : args.queries;
+        bool q_ok = true;  // packed-path precondition: every non-zero |q_i| >= 2^-76
+        for (uint32_t i = threadIdx.x; i < QB * dim; i += blockDim.x) {
+            const float qv = queries[i];
+            sm.q[i] = qv;
+            const uint32_t mag = __float_as_uint(qv) & 0x7FFFFFFFu;
+            q_ok = q_ok && (mag == 0u || mag >= 0x19800000u);
+        }
+        if (threadIdx.x < QB) {
+            sm.cnt[threadIdx.x] = 0u;
+            sm.tau[threadIdx.x] = 0ull;
+        }
+        const bool packed = __syncthreads_and(q_ok ? 1 : 0) != 0 && args.allow_packed != 0;
+        if (packed)
+            scan_loop<NJ, QB, R, true>(args, sm);
+        else
+            scan_loop<NJ, QB, R, false>(args, sm);
+        scan_write_partials<QB>(sm, args, slot);
+        __syncthreads();  // the next query re-uses the shared buffers
     }
-    if (threadIdx.x < QB) {
-        sm.cnt[threadIdx.x] = 0u;
-        sm.tau[threadIdx.x] = 0ull;
-    }
-    const bool packed = __syncthreads_and(q_ok ? 1 : 0) != 0 && args.allow_packed != 0;
-    if (packed)
-        scan_loop<NJ, QB, R, true>(args, sm);
-    else
-        scan_loop<NJ, QB, R, false>(args, sm);
-    scan_write_partials<QB>(sm, args);
 }
 
 // ─── generic path: any dim (tails included), one warp per row, one query per pass ───────────
@@ -304,30 +380,37 @@ __global__ void __launch_bounds__(kScanThreads)
 scan_topk_generic_kernel(const ScanArgs args) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const ScanSmem sm = carve_scan_smem(smem_raw, 1, args.cap, args.dim);
-    for (uint32_t i = threadIdx.x; i < args.dim; i += blockDim.x) sm.q[i] = args.queries[i];
-    if (threadIdx.x == 0) {
-        sm.cnt[0] = 0u;
-        sm.tau[0] = 0ull;
+    __shared__ uint32_t s_redo[kRedoMaxPerLaunch];
+    uint32_t n_serve = 1;
+    if (args.redo.flags) n_serve = redo_collect(args.redo, s_redo);
+    for (uint32_t slot = 0; slot < n_serve; ++slot) {
+        const float* query = args.redo.flags ? args.queries + (size_t)s_redo[slot] * args.dim : args.queries;
+        for (uint32_t i = threadIdx.x; i < args.dim; i += blockDim.x) sm.q[i] = query[i];
+        if (threadIdx.x == 0) {
+            sm.cnt[0] = 0u;
+            sm.tau[0] = 0ull;
+        }
+        __syncthreads();
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        constexpr int kTileRows = kScanWarps;  // one row per warp per iteration
+        const uint64_t n = args.n_rows;
+        const uint64_t n_tiles = (n + kTileRows - 1) / kTileRows;
+        const uint32_t trigger = args.cap - args.sync_every * kTileRows;
+        float thr[1] = {-INFINITY};
+        uint32_t it = 0;
+        for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const uint64_t row = tile * kTileRows + warp;
+            const uint64_t rowc = row < n ? row : n - 1;
+            const float score = warp_exact_dot(args.slab + rowc * args.dim, sm.q, args.dim,
+                                               args.reduce_order, args.tail_fma);
+            if (!(score < thr[0]) && lane == 0 && row < n) scan_offer<1>(sm, args, 0, score, row);
+            if ((it + 1) % args.sync_every == 0)
+                scan_sync_point<1>(sm, args.cap, args.k, trigger, false, thr);
+        }
+        scan_sync_point<1>(sm, args.cap, args.k, trigger, true, thr);
+        scan_write_partials<1>(sm, args, slot);
+        __syncthreads();
     }
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    constexpr int kTileRows = kScanWarps;  // one row per warp per iteration
-    const uint64_t n = args.n_rows;
-    const uint64_t n_tiles = (n + kTileRows - 1) / kTileRows;
-    const uint32_t trigger = args.cap - args.sync_every * kTileRows;
-    float thr[1] = {-INFINITY};
-    uint32_t it = 0;
-    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        const uint64_t row = tile * kTileRows + warp;
-        const uint64_t rowc = row < n ? row : n - 1;
-        const float score = warp_exact_dot(args.slab + rowc * args.dim, sm.q, args.dim,
-                                           args.reduce_order, args.tail_fma);
-        if (!(score < thr[0]) && lane == 0 && row < n) scan_offer<1>(sm, args, 0, score, row);
-        if ((it + 1) % args.sync_every == 0)
-            scan_sync_point<1>(sm, args.cap, args.k, trigger, false, thr);
-    }
-    scan_sync_point<1>(sm, args.cap, args.k, trigger, true, thr);
-    scan_write_partials<1>(sm, args);
 }
 
 // ─── merge: one CTA per query over `n_lists` lists of `k_in` keys ───────────────────────────
@@ -354,6 +437,10 @@ struct MergeArgs {
     uint32_t dim;
     int reduce_order, tail_fma;
     uint32_t* error_flag;
+    // merge of a redo launch: CTA i reads the lists of slot i and writes the result of query
+    // redo_slots[i]; CTAs at or past *redo_round_n have nothing to do
+    const uint32_t* redo_slots;
+    const uint32_t* redo_round_n;
 };
 
 __global__ void __launch_bounds__(kScanThreads) merge_topk_kernel(const MergeArgs args) {
@@ -361,7 +448,12 @@ __global__ void __launch_bounds__(kScanThreads) merge_topk_kernel(const MergeArg
     uint64_t* cand = reinterpret_cast<uint64_t*>(smem_raw);
     uint64_t* tau = cand + args.cap;
     uint32_t* cnt = reinterpret_cast<uint32_t*>(tau + 1);
-    const uint32_t b = blockIdx.x;
+    const uint32_t b_in = blockIdx.x;
+    uint32_t b = blockIdx.x;  // the query whose outputs this CTA writes
+    if (args.redo_slots) {
+        if (b_in >= *args.redo_round_n) return;
+        b = args.redo_slots[b_in];
+    }
     if (threadIdx.x == 0) {
         *cnt = 0u;
         *tau = 0ull;
@@ -379,7 +471,7 @@ __global__ void __launch_bounds__(kScanThreads) merge_topk_kernel(const MergeArg
             const uint64_t idx = base + o;
             if (idx < total) {
                 const uint64_t g = idx / args.k_in, i = idx % args.k_in;
-                const uint64_t key = args.keys[g * args.list_stride + b * args.query_stride + i];
+                const uint64_t key = args.keys[g * args.list_stride + b_in * args.query_stride + i];
                 if (key > t) {
                     if (!cand_push(buf, args.cap, key)) atomicExch(args.error_flag, 1u);
                 }
@@ -414,7 +506,7 @@ __global__ void __launch_bounds__(kScanThreads) merge_topk_kernel(const MergeArg
             if (args.scores || args.hits_in) {
                 for (uint64_t idx = lane; idx < total && !have; idx += 32) {
                     const uint64_t g = idx / args.k_in, j = idx % args.k_in;
-                    const uint64_t off = g * args.list_stride + b * args.query_stride + j;
+                    const uint64_t off = g * args.list_stride + b_in * args.query_stride + j;
                     if (args.keys[off] == key) {
                         raw = args.scores ? args.scores[off] : args.hits_in[off].score;
                         have = true;

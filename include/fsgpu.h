@@ -14,7 +14,10 @@
  *   - "host" entry points take host pointers and copy; "_device" entry points take device
  *     pointers on the index's GPU and enqueue on `stream` (a cudaStream_t passed as void*;
  *     NULL = the index's own stream, in which case the call synchronises before returning).
- *   - every entry point is thread-safe; calls on one index are serialised internally.
+ *   - every entry point is thread-safe; calls on one index are serialised internally, and calls
+ *     that arrive on DIFFERENT streams are ordered on the device (each waits for the previous call's
+ *     work: the per-index workspaces are shared).  A `_device` call with a caller stream never blocks
+ *     the host: queries the batched path cannot cover are re-run by the exact kernels on that stream.
  *   - there is no CPU fallback: without a usable CUDA device every call fails with
  *     FSGPU_ERR_SUBSYSTEM.
  *   - rows are GLOBAL row numbers: `row_base + local row`, so per-shard results from a
@@ -192,7 +195,7 @@ int fsgpu_measure_tensor_peak(int device, int kind, uint32_t target_ms, double* 
  * Batches of >= 3 queries (FSGPU_MMA_MIN_BATCH) with k <= 1024 on an all-finite slab whose dim is
  * a multiple of 64 take ONE tensor-core pass over the slab (tcgen05/TMA, mma_scan_kernels.cuh)
  * followed by an exact re-scoring of a provable superset of the top-k; results are identical
- * to the per-query path.  That path synchronises the stream once per call. */
+ * to the per-query path. */
 int fsgpu_search_top_k(const fsgpu_index* index, const float* queries, uint32_t batch, uint32_t k,
                        uint32_t dim, fsgpu_hit* out, uint32_t* out_counts);
 
@@ -203,6 +206,13 @@ int fsgpu_search_top_k(const fsgpu_index* index, const float* queries, uint32_t 
 int fsgpu_search_top_k_device(const fsgpu_index* index, const float* d_queries, uint32_t batch,
                               uint32_t k, uint64_t* d_out_keys, fsgpu_hit* d_out_hits,
                               uint32_t* d_out_counts, void* stream);
+
+/* Status words of the most recent search on this index, for callers of the stream-asynchronous
+ * `_device` entry points (they return before the GPU has run; the synchronous ones report through
+ * their return value).  Waits for that call's flag read-back, then writes out_flags[4] =
+ * {contract violation (also returned as FSGPU_ERR_SUBSYSTEM), reserved, reserved, queries that were
+ * re-run by the exact kernels on the device (non-finite / overflowing queries, overflowed lists)}. */
+int fsgpu_index_last_status(const fsgpu_index* index, uint32_t* out_flags);
 
 /* The `filter: Option<&dyn SearchFilter>` argument of VectorIndex::search_top_k
  * (crates/frankensearch-index/src/search.rs:192-206; applied before heap admission,

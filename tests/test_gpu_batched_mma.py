@@ -319,3 +319,73 @@ def test_batched_f16_subnormal_rows(fs, cpu, fo):
     assert_batch_matches_oracle(cpu, slab, qs, 10, got)
     assert prof["redo_queries"] == 0, "subnormal f16 inputs were not handled exactly by the MMA path"
     ix.close()
+
+
+def test_async_device_calls_redo_on_the_device(fs, cpu, fo, monkeypatch):
+    """The stream-asynchronous `_device` entry point never blocks the host: queries the batched path
+    cannot cover (NaN / inf / f16-overflow, and an overflowing tie band) are re-run by the exact kernels
+    on the caller's stream.  Results equal the oracle, `fsgpu_index_last_status` reports how many were
+    redone, and a call on ANOTHER stream right behind it is ordered after it (shared workspaces)."""
+    import ctypes as C
+
+    import torch
+
+    rng = np.random.default_rng(5)
+    base = rng.normal(size=(60000, 64)).astype(np.float32)
+    base /= np.linalg.norm(base, axis=1, keepdims=True)
+    base[1000:50000] = base[7]
+    slab = fo.encode_f16(base)
+    qs = rng.normal(size=(40, 64)).astype(np.float32)
+    qs[0] = base[7]
+    qs[5] = base[7] * 0.5
+    qs[9, 3] = np.nan
+    qs[17, 0] = np.inf
+    qs[33, :] *= np.float32(1e6)
+    ix = fs.GpuVectorIndex.from_f16_bits(None, slab)
+    d_q = torch.from_numpy(qs).cuda()
+    side = torch.cuda.Stream()
+    for k in (20, 300):
+        keys, hits, counts = ix.search_top_k_device(d_q, k)  # torch's current stream, asynchronous
+        with torch.cuda.stream(side):  # a second call on another stream, enqueued at once
+            keys2, hits2, counts2 = ix.search_top_k_device(d_q[:7].contiguous(), k)
+        torch.cuda.synchronize()
+        flags = (C.c_uint32 * 4)()
+        fs._ffi.check(ix._L.fsgpu_index_last_status(ix._h, flags))
+        h = hits.cpu().numpy()
+        got = (h[..., 0].view(np.uint32), h[..., 1].view(np.float32), counts.cpu().numpy())
+        assert_batch_matches_oracle(cpu, slab, qs, k, got, ctx=f"async k={k}")
+        h2 = hits2.cpu().numpy()
+        got2 = (h2[..., 0].view(np.uint32), h2[..., 1].view(np.float32), counts2.cpu().numpy())
+        assert_batch_matches_oracle(cpu, slab, qs[:7], k, got2, ctx=f"async side stream k={k}")
+        assert flags[0] == 0
+    p = ix.profile_read(reset=True)
+    assert p["mma_launches"] >= 2 and p["redo_queries"] >= 4, p
+    ix.close()
+
+
+def test_int8_overflow_falls_back_to_f16_form_sync_and_async(fs, cpu, fo, monkeypatch):
+    """A corpus whose score spread is far narrower than the int8 bound (every row a small perturbation
+    of one vector): the int8 lists overflow for every query.  A synchronous caller re-runs the batch in
+    the f16 form; an asynchronous one gets the device redo, then the following calls avoid the int8 form."""
+    import torch
+
+    monkeypatch.setenv("FSGPU_I8_MIN_ROWS", "0")
+    rng = np.random.default_rng(3)
+    n, dim = 40000, 128
+    centre = rng.normal(size=dim).astype(np.float32)
+    centre /= np.linalg.norm(centre)
+    rows = centre[None, :] + 1e-3 * rng.normal(size=(n, dim)).astype(np.float32)
+    slab = fo.encode_f16(rows)
+    qs = (centre[None, :] + 0.05 * rng.normal(size=(8, dim))).astype(np.float32)
+    ix = fs.GpuVectorIndex.from_f16_bits(None, slab)
+    assert ix._L.fsgpu_index_int8_ready(ix._h) == 1
+    got = ix.search_top_k_batch(qs, 10)  # synchronous host API
+    assert_batch_matches_oracle(cpu, slab, qs, 10, got, ctx="sync")
+    d_q = torch.from_numpy(qs).cuda()
+    for rep in range(3):
+        keys, hits, counts = ix.search_top_k_device(d_q, 10)
+        torch.cuda.synchronize()
+        h = hits.cpu().numpy()
+        assert_batch_matches_oracle(cpu, slab, qs, 10, (h[..., 0].view(np.uint32), h[..., 1].view(np.float32),
+                                                        counts.cpu().numpy()), ctx=f"async rep={rep}")
+    ix.close()
