@@ -61,7 +61,7 @@ class IndexOptions(C.Structure):
         ("slab_is_device", C.c_int32),
         ("row_base", C.c_uint64),
         ("int8_codes", C.c_int32),
-        ("reserved", C.c_int32),
+        ("flags", C.c_int32),
     ]
 
 

@@ -61,7 +61,7 @@ extern "C" void fsgpu_index_options_default(fsgpu_index_options* o) {
     o->slab_is_device = 0;
     o->row_base = 0;
     o->int8_codes = 1;
-    o->reserved = 0;
+    o->flags = 0;
 }
 
 // ─── the index handle ───────────────────────────────────────────────────────────────────────
@@ -73,6 +73,12 @@ struct fsgpu_index {
     int reduce_order = 0, tail_fma = 1;
     uint16_t* d_slab = nullptr;
     bool owns_slab = false;
+    // an f32-quantised FSVI file (quantization 0, lib.rs:6-43) keeps its slab as f32 and is scored with the
+    // reference's f32 kernel (dot_product_f32_bytes_f32, search.rs:1300-1321): exact score of every row +
+    // radix select; the f16 / int8 scan forms do not apply
+    float* d_slab_f32 = nullptr;
+    const void* slab_any() const { return d_slab_f32 ? static_cast<const void*>(d_slab_f32) : static_cast<const void*>(d_slab); }
+    int is_f32() const { return d_slab_f32 ? 1 : 0; }
     uint8_t* d_tomb = nullptr;
     mutable const uint8_t* d_excl = nullptr;  // per-call exclusion bitmap (tombstones | !filter), else nullptr
     mutable DevBuf ws_excl, ws_allow;
@@ -249,7 +255,7 @@ static int search_exact_locked(const fsgpu_index* ix, const float* d_queries, ui
         if (d_out_counts) CUDA_TRY(cudaMemsetAsync(d_out_counts, 0, (size_t)batch * 4, stream));
         return FSGPU_OK;
     }
-    if (k > kFusedMaxK) {
+    if (k > kFusedMaxK || ix->d_slab_f32) {
         // `limit >= n` / very large k arm (search.rs:449-473): score every row, radix sort.
         const uint64_t n = ix->n_rows;
         CUDA_TRY(ix->ws_sort_a.reserve(n * 8));
@@ -262,7 +268,7 @@ static int search_exact_locked(const fsgpu_index* ix, const float* d_queries, ui
         const int grid = (int)std::min<uint64_t>((n + kScanWarps - 1) / kScanWarps, (uint64_t)ix->num_sms * 8);
         for (uint32_t b = 0; b < batch; ++b) {
             score_all_kernel<<<grid, kScanThreads, (size_t)ix->dim * 4, stream>>>(
-                ix->d_slab, ix->d_excl ? ix->d_excl : ix->d_tomb, n, ix->row_base, ix->dim, d_queries + (size_t)b * ix->dim,
+                ix->slab_any(), ix->is_f32(), ix->d_excl ? ix->d_excl : ix->d_tomb, n, ix->row_base, ix->dim, d_queries + (size_t)b * ix->dim,
                 ix->reduce_order, ix->tail_fma, ix->ws_sort_a.as<uint64_t>());
             CUDA_TRY(cudaGetLastError());
             CUDA_TRY(cub::DeviceRadixSort::SortKeysDescending(
@@ -270,7 +276,7 @@ static int search_exact_locked(const fsgpu_index* ix, const float* d_queries, ui
                 64, stream));
             emit_sorted_prefix_kernel<<<std::max(1u, std::min(1024u, (k + kScanWarps - 1) / kScanWarps)),
                                         kScanThreads, 0, stream>>>(
-                ix->ws_sort_b.as<uint64_t>(), k_eff, k, ix->d_slab, d_queries + (size_t)b * ix->dim,
+                ix->ws_sort_b.as<uint64_t>(), k_eff, k, ix->slab_any(), ix->is_f32(), d_queries + (size_t)b * ix->dim,
                 ix->n_rows, ix->row_base, ix->dim, ix->reduce_order, ix->tail_fma,
                 d_out_keys ? d_out_keys + (size_t)b * k : nullptr,
                 d_out_hits ? d_out_hits + (size_t)b * k : nullptr, d_out_counts ? d_out_counts + b : nullptr);
@@ -342,7 +348,8 @@ static int search_exact_locked(const fsgpu_index* ix, const float* d_queries, ui
         m.out_keys = d_out_keys ? d_out_keys + (size_t)done * k : nullptr;
         m.out_hits = d_out_hits ? d_out_hits + (size_t)done * k : nullptr;
         m.out_counts = d_out_counts ? d_out_counts + done : nullptr;
-        m.slab = ix->d_slab;
+        m.slab = ix->slab_any();
+        m.slab_is_f32 = ix->is_f32();
         m.queries = a.queries;
         m.n_rows = ix->n_rows;
         m.row_base = ix->row_base;
@@ -407,6 +414,7 @@ static bool make_u8_tile_map(CUtensorMap* tm, const void* base, uint64_t rows, u
 // index (otherwise every batch runs on the exact CUDA-core kernels).
 static int index_finish_setup(fsgpu_index* ix) {
     ix->mma_ok = false;
+    if (ix->d_slab_f32) return FSGPU_OK;  // f32-quantised slab: scored exactly row by row, no tensor-core forms
     if (ix->n_rows == 0 || ix->dim % kMmaKBlock != 0 || ix->dim > kMmaMaxDim ||
         ix->n_rows > 0x7FFFFF00ull || (reinterpret_cast<uintptr_t>(ix->d_slab) & 15u) != 0)
         return FSGPU_OK;
@@ -529,7 +537,8 @@ static int enqueue_redo_locked(const fsgpu_index* ix, const float* d_queries, ui
         m.out_keys = d_out_keys;
         m.out_hits = d_out_hits;
         m.out_counts = d_out_counts;
-        m.slab = ix->d_slab;
+        m.slab = ix->slab_any();
+        m.slab_is_f32 = ix->is_f32();
         m.queries = d_queries;
         m.n_rows = ix->n_rows;
         m.row_base = ix->row_base;
@@ -1089,7 +1098,7 @@ static int search_select_locked(const fsgpu_index* ix, const float* d_queries, u
                                 cudaStream_t stream) {
     using u64 = unsigned long long;
     const uint64_t n = ix->n_rows;
-    const bool i8 = ix->i8_ok && env_int("FSGPU_MMA_I8", 1) != 0 && env_int("FSGPU_SELECT_I8", 1) != 0;
+    const bool i8 = ix->i8_ok && !ix->d_slab_f32 && env_int("FSGPU_MMA_I8", 1) != 0 && env_int("FSGPU_SELECT_I8", 1) != 0;
     CUDA_TRY(ix->ws_sel_state.reserve(2 * sizeof(SelState)));
     CUDA_TRY(ix->ws_sort_a.reserve(n * 8));
     CUDA_TRY(ix->ws_sel_pos2.reserve((size_t)kSelMaxK * 4));
@@ -1154,7 +1163,7 @@ static int search_select_locked(const fsgpu_index* ix, const float* d_queries, u
             ix->prof.other_launches += 6;
         } else {
             const int grid = (int)std::min<uint64_t>((n + kScanWarps - 1) / kScanWarps, (uint64_t)ix->num_sms * 8);
-            score_all_kernel<<<grid, kScanThreads, (size_t)ix->dim * 4, stream>>>(ix->d_slab, tomb, n, ix->row_base, ix->dim, q,
+            score_all_kernel<<<grid, kScanThreads, (size_t)ix->dim * 4, stream>>>(ix->slab_any(), ix->is_f32(), tomb, n, ix->row_base, ix->dim, q,
                                                                                  ix->reduce_order, ix->tail_fma,
                                                                                  reinterpret_cast<uint64_t*>(keys));
             CUDA_TRY(cudaGetLastError());
@@ -1166,7 +1175,7 @@ static int search_select_locked(const fsgpu_index* ix, const float* d_queries, u
             sel_hist_kernel<u64><<<g2, 256, 0, stream>>>(keys, n, n_exact, st1, p, k);
         sel_compact_kernel<u64><<<g2, 256, 0, stream>>>(keys, n, n_exact, st1, nullptr, nullptr, ix->ws_sel_pos2.as<uint32_t>(),
                                                         kSelMaxK, n2);
-        sel_emit_kernel<<<1, 1024, kSelMaxK * 8, stream>>>(keys, ix->ws_sel_pos2.as<uint32_t>(), n2, k, ix->d_slab, q, n,
+        sel_emit_kernel<<<1, 1024, kSelMaxK * 8, stream>>>(keys, ix->ws_sel_pos2.as<uint32_t>(), n2, k, ix->slab_any(), ix->is_f32(), q, n,
                                                            ix->row_base, ix->dim, ix->reduce_order, ix->tail_fma,
                                                            d_out_keys ? d_out_keys + (size_t)b * k : nullptr,
                                                            d_out_hits ? d_out_hits + (size_t)b * k : nullptr,
@@ -1182,6 +1191,11 @@ static int search_main_locked(const fsgpu_index* ix, const float* d_queries, uin
                               uint64_t* d_out_keys, fsgpu_hit* d_out_hits, uint32_t* d_out_counts,
                               cudaStream_t stream) {
     if (batch == 0) return FSGPU_OK;
+    if (ix->d_slab_f32) {  // f32-quantised slab: exact score of every row, then radix select (or the sort arm)
+        if (k >= 1 && k <= kSelMaxK && ix->n_rows > 0 && ix->n_rows <= 0xFFFFFFF0ull)
+            return search_select_locked(ix, d_queries, batch, k, d_out_keys, d_out_hits, d_out_counts, stream);
+        return search_exact_locked(ix, d_queries, batch, k, d_out_keys, d_out_hits, d_out_counts, stream);
+    }
     if (ix->use_i8_single) return search_i8_single_locked(ix, d_queries, batch, k, d_out_keys, d_out_hits, d_out_counts, stream);
     const int min_batch = env_int("FSGPU_MMA_MIN_BATCH", 3);
     const bool mma = ix->mma_ok && min_batch > 0 && batch >= (uint32_t)min_batch && k >= 1 && k <= kMmaMaxK &&
@@ -1211,7 +1225,7 @@ static int merge_single_list_locked(const fsgpu_index* ix, const MergeArgs& m, u
         CUDA_TRY(cub::DeviceRadixSort::SortKeysDescending(ix->ws_cub.p, cub_bytes, m.keys + (size_t)b * m.query_stride,
                                                          ix->ws_sort_b.as<uint64_t>(), n, 0, 64, stream));
         emit_sorted_prefix_kernel<<<std::max(1u, std::min(1024u, (m.k_out + kScanWarps - 1) / kScanWarps)), kScanThreads, 0,
-                                    stream>>>(ix->ws_sort_b.as<uint64_t>(), k_eff, m.k_out, m.slab,
+                                    stream>>>(ix->ws_sort_b.as<uint64_t>(), k_eff, m.k_out, m.slab, m.slab_is_f32,
                                               m.queries + (size_t)b * m.dim, m.n_rows, m.row_base, m.dim, m.reduce_order,
                                               m.tail_fma, m.out_keys ? m.out_keys + (size_t)b * m.k_out : nullptr,
                                               m.out_hits ? m.out_hits + (size_t)b * m.k_out : nullptr,
@@ -1249,7 +1263,8 @@ static int search_gather_locked(const fsgpu_index* ix, const float* d_queries, u
     m.out_keys = d_out_keys;
     m.out_hits = d_out_hits;
     m.out_counts = d_out_counts;
-    m.slab = ix->d_slab;
+    m.slab = ix->slab_any();
+        m.slab_is_f32 = ix->is_f32();
     m.queries = d_queries;
     m.n_rows = ix->n_rows;
     m.row_base = ix->row_base;
@@ -1296,7 +1311,8 @@ static int search_device_locked(const fsgpu_index* ix, const float* d_queries, u
     m.out_keys = d_out_keys;
     m.out_hits = d_out_hits;
     m.out_counts = d_out_counts;
-    m.slab = ix->d_slab;  // raw NaN scores of main rows (WAL rows are always finite)
+    m.slab = ix->slab_any();
+        m.slab_is_f32 = ix->is_f32();  // raw NaN scores of main rows (WAL rows are always finite)
     m.queries = d_queries;
     m.n_rows = ix->n_rows;
     m.row_base = ix->row_base;
@@ -1363,6 +1379,7 @@ extern "C" void fsgpu_index_destroy(fsgpu_index* ix) {
         DeviceGuard g(ix->device);
         if (ix->stream) cudaStreamSynchronize(ix->stream);
         if (ix->owns_slab && ix->d_slab) cudaFree(ix->d_slab);
+        if (ix->d_slab_f32) cudaFree(ix->d_slab_f32);
         if (ix->d_tomb) cudaFree(ix->d_tomb);
         if (ix->d_error) cudaFree(ix->d_error);
         if (ix->h_flags) cudaFreeHost(ix->h_flags);
@@ -1498,6 +1515,7 @@ extern "C" int fsgpu_index_read_rows_f16(const fsgpu_index* ix, uint64_t row_sta
     if (row_start > ix->n_rows || n > ix->n_rows - row_start)
         return fail(FSGPU_ERR_INVALID_CONFIG, "row range outside the index");
     if (n == 0) return FSGPU_OK;
+    if (ix->d_slab_f32) return fail(FSGPU_ERR_INVALID_CONFIG, "index holds an f32-quantised slab: no f16 rows to read");
     std::lock_guard<std::mutex> lock(ix->mu);
     DeviceGuard g(ix->device);
     CUDA_TRY(cudaMemcpy(out_bits, ix->d_slab + row_start * ix->dim, (size_t)n * ix->dim * 2,
@@ -1719,7 +1737,7 @@ extern "C" int fsgpu_search_top_k_filtered(const fsgpu_index* ix, const float* q
     // (half the bytes of the f16 scan); a position list that overflows re-runs the call on the f16 scan.
     const int min_batch = env_int("FSGPU_MMA_MIN_BATCH", 3);
     const uint32_t i8_max_batch = (uint32_t)std::max(0, env_int("FSGPU_I8_MAX_BATCH", 2));
-    bool i8_single = ix->i8_ok && env_int("FSGPU_MMA_I8", 1) != 0 && k <= 128 &&
+    bool i8_single = ix->i8_ok && !ix->d_slab_f32 && env_int("FSGPU_MMA_I8", 1) != 0 && k <= 128 &&
                      (batch <= i8_max_batch || !(min_batch > 0 && batch >= (uint32_t)min_batch)) && batch <= 64 &&
                      k <= kFusedMaxK && ix->n_rows > 0;
     for (size_t i = 0; i8_single && i < (size_t)batch * dim; ++i) i8_single = std::isfinite(queries[i]);
@@ -1796,7 +1814,7 @@ extern "C" int fsgpu_search_top_k_hashes(const fsgpu_index* ix, const float* que
     if (ix->n_wal) CUDA_TRY(ix->ws_allow.reserve(wal_bytes));
     // try_gather_filtered (search.rs:1114-1131): the selective arm when allowed * 50 < record_count
     constexpr uint64_t kGatherSelectivityDivisor = 50;  // search.rs:33
-    bool gather = ix->n_rows > 0 && (uint64_t)n_allowed * kGatherSelectivityDivisor < ix->n_rows;
+    bool gather = ix->n_rows > 0 && (uint64_t)n_allowed * kGatherSelectivityDivisor < ix->n_rows && !ix->d_slab_f32;
     bool force_f16 = false;
     const uint32_t cap = std::max(64u, 2 * n_allowed);  // rows sharing a hash (collisions, duplicate doc ids)
     for (int attempt = 0; attempt < 3; ++attempt) {
@@ -1944,7 +1962,7 @@ extern "C" int fsgpu_scores_for_rows_device(const fsgpu_index* ix, const float* 
     DeviceGuard g(ix->device);
     cudaStream_t s = stream ? (cudaStream_t)stream : ix->stream;
     dim3 grid((n_per_query + kScanWarps - 1) / kScanWarps, batch);
-    scores_for_rows_kernel<<<grid, kScanThreads, 0, s>>>(ix->d_slab, ix->n_rows, ix->row_base, ix->dim,
+    scores_for_rows_kernel<<<grid, kScanThreads, 0, s>>>(ix->slab_any(), ix->is_f32(), ix->n_rows, ix->row_base, ix->dim,
                                                          d_queries, d_rows, 1u, n_per_query, ix->reduce_order,
                                                          ix->tail_fma, d_out_scores, d_out_present);
     CUDA_TRY(cudaGetLastError());
@@ -1963,7 +1981,7 @@ extern "C" int fsgpu_scores_for_hits_device(const fsgpu_index* ix, const float* 
     cudaStream_t s = stream ? (cudaStream_t)stream : ix->stream;
     dim3 grid((n_per_query + kScanWarps - 1) / kScanWarps, batch);
     // the row of hit i is word 2i of the record array
-    scores_for_rows_kernel<<<grid, kScanThreads, 0, s>>>(ix->d_slab, ix->n_rows, ix->row_base, ix->dim, d_queries,
+    scores_for_rows_kernel<<<grid, kScanThreads, 0, s>>>(ix->slab_any(), ix->is_f32(), ix->n_rows, ix->row_base, ix->dim, d_queries,
                                                          reinterpret_cast<const uint32_t*>(d_hits), 2u, n_per_query,
                                                          ix->reduce_order, ix->tail_fma, d_out_scores, d_out_present);
     CUDA_TRY(cudaGetLastError());
@@ -2010,7 +2028,7 @@ extern "C" int fsgpu_scores_for_rows(const fsgpu_index* ix, const float* query, 
         CUDA_TRY(cudaMemcpyAsync(ix->ws_rows.p, rows, (size_t)n * 4, cudaMemcpyHostToDevice, s));
         dim3 grid((n + kScanWarps - 1) / kScanWarps, 1);
         scores_for_rows_kernel<<<grid, kScanThreads, 0, s>>>(
-            ix->d_slab, ix->n_rows, ix->row_base, ix->dim, ix->ws_queries.as<float>(),
+            ix->slab_any(), ix->is_f32(), ix->n_rows, ix->row_base, ix->dim, ix->ws_queries.as<float>(),
             ix->ws_rows.as<uint32_t>(), 1u, n, ix->reduce_order, ix->tail_fma, ix->ws_scores.as<float>(),
             ix->ws_present.as<uint8_t>());
         CUDA_TRY(cudaGetLastError());
@@ -2078,13 +2096,30 @@ extern "C" int fsgpu_index_open_fsvi(const char* path, uint64_t row_start, uint6
     if (!out) return fail(FSGPU_ERR_INVALID_CONFIG, "out is NULL");
     *out = nullptr;
     if (!path) return fail(FSGPU_ERR_INVALID_CONFIG, "path is NULL");
+    fsgpu_index_options o;
+    if (opts) o = *opts; else fsgpu_index_options_default(&o);
+    // Pending appends live in the `<path>.wal` sidecar (wal.rs:575-579); VectorIndex::open replays it
+    // (lib.rs:1833-1878).  The doc ids of WAL rows are host state, so the replay is the host's job
+    // (fsgpu_index_set_wal): a host that has not said it does so must not silently lose those rows.
+    if (!(o.flags & FSGPU_OPEN_HOST_REPLAYS_WAL)) {
+        const std::string wal = std::string(path) + ".wal";
+        if (FILE* w = fopen(wal.c_str(), "rb")) {
+            fseeko(w, 0, SEEK_END);
+            const off_t wlen = ftello(w);
+            fclose(w);
+            if (wlen >= 20)  // WAL_HEADER_SIZE: anything shorter is ignored by the reference too (wal.rs:861-864)
+                return fail(FSGPU_ERR_INVALID_CONFIG,
+                            "%s has a WAL sidecar with pending appends: replay it on the host (fsgpu_index_set_wal) and pass "
+                            "FSGPU_OPEN_HOST_REPLAYS_WAL, or compact the index first", path);
+        }
+    }
     FILE* f = fopen(path, "rb");
     if (!f) return fail(FSGPU_ERR_IO, "cannot open %s: %s", path, strerror(errno));
-    fseek(f, 0, SEEK_END);
-    const long fsize = ftell(f);
-    fseek(f, 0, SEEK_SET);
-    // header + record table + string table are read whole; the slab is read by row range
-    std::vector<uint8_t> head((size_t)std::min<long>(fsize, 4 + 2 + 2 + 65535 + 2 + 65535 + 4 + 1 + 3 + 8 + 8 + 4));
+    fseeko(f, 0, SEEK_END);
+    const uint64_t fsize = (uint64_t)ftello(f);  // 64-bit: a 50 M x 384 slab is 38 GB
+    fseeko(f, 0, SEEK_SET);
+    // header + record table + string table are read whole; the slab is streamed by row range
+    std::vector<uint8_t> head((size_t)std::min<uint64_t>(fsize, 4 + 2 + 2 + 65535 + 2 + 65535 + 4 + 1 + 3 + 8 + 8 + 4));
     if (fread(head.data(), 1, head.size(), f) != head.size()) {
         fclose(f);
         return fail(FSGPU_ERR_IO, "short read on %s", path);
@@ -2101,7 +2136,7 @@ extern "C" int fsgpu_index_open_fsvi(const char* path, uint64_t row_start, uint6
     cur = 4;
     if (memcmp(magic, "FSVI", 4) != 0) return corrupt("bad magic");
     if (!rd(head, &cur, &version)) return corrupt("truncated header");
-    if (version != 1) return corrupt("unsupported FSVI version (only v1 is read here)");
+    if (version != 1) return corrupt("unsupported FSVI version (only v1 is read here; v2 identity headers are out of scope)");
     if (!rd(head, &cur, &len16) || cur + len16 > head.size()) return corrupt("truncated embedder_id");
     cur += len16;
     if (!rd(head, &cur, &len16) || cur + len16 > head.size()) return corrupt("truncated embedder_revision");
@@ -2116,18 +2151,12 @@ extern "C" int fsgpu_index_open_fsvi(const char* path, uint64_t row_start, uint6
     if (!rd(head, &cur, &crc_stored)) return corrupt("truncated header crc");
     if (crc32_ieee(head.data(), crc_end) != crc_stored) return corrupt("header CRC mismatch");
     if (quant > 1) return corrupt("unknown quantization");
-    if (quant == 0) {
-        // an f32 slab is scored by dot_product_f32_bytes_f32 in the reference (search.rs:1300-1321);
-        // re-encoding it to f16 here would silently change scores.
-        fclose(f);
-        return fail(FSGPU_ERR_INVALID_CONFIG, "%s: f32-quantised FSVI is not supported on the device path (f16 only)", path);
-    }
     if (dim == 0) return corrupt("zero dimension");
     const size_t records_offset = cur;
     const uint64_t elem = quant == 1 ? 2 : 4;
     if (vectors_offset % 64 != 0) return corrupt("vector slab is not 64-byte aligned");
     if (records_offset + record_count * 16 > vectors_offset ||
-        vectors_offset + record_count * dim * elem > (uint64_t)fsize)
+        vectors_offset + record_count * dim * elem > fsize)
         return corrupt("section offsets exceed file size");
     if (row_start > record_count) {
         fclose(f);
@@ -2136,7 +2165,7 @@ extern "C" int fsgpu_index_open_fsvi(const char* path, uint64_t row_start, uint6
     const uint64_t n = n_rows_or_0 ? std::min(n_rows_or_0, record_count - row_start) : record_count - row_start;
 
     std::vector<uint8_t> meta(vectors_offset - records_offset);
-    fseek(f, (long)records_offset, SEEK_SET);
+    fseeko(f, (off_t)records_offset, SEEK_SET);
     if (!meta.empty() && fread(meta.data(), 1, meta.size(), f) != meta.size()) return corrupt("short read (records)");
     const uint8_t* strings = meta.data() + record_count * 16;
     const size_t strings_len = meta.size() - record_count * 16;
@@ -2161,20 +2190,76 @@ extern "C" int fsgpu_index_open_fsvi(const char* path, uint64_t row_start, uint6
             any_tomb = true;
         }
     }
-    std::vector<uint8_t> slab((size_t)(n * dim * elem));
-    fseek(f, (long)(vectors_offset + row_start * dim * elem), SEEK_SET);
-    if (!slab.empty() && fread(slab.data(), 1, slab.size(), f) != slab.size()) return corrupt("short read (slab)");
-    fclose(f);
+    meta.clear();
+    meta.shrink_to_fit();
 
-    fsgpu_index_options o;
-    if (opts) o = *opts; else fsgpu_index_options_default(&o);
     o.slab_is_device = 0;
-    o.tail_fma = 1;  // file-backed index scores with the bytes kernel (search.rs:1283)
+    o.tail_fma = 1;  // file-backed index scores with the bytes kernels (search.rs:1283, :1310)
     if (o.row_base == 0) o.row_base = row_start;
-    fsgpu_index* ix = nullptr;
-    int rc = fsgpu_index_create_f16(reinterpret_cast<const uint16_t*>(slab.data()), n, dim,
-                                    any_tomb ? tomb.data() : nullptr, &o, &ix);
-    if (rc) return rc;
+    DeviceGuard g(o.device);
+    fsgpu_index* ix = new fsgpu_index();
+    int rc = index_alloc_common(ix, &o, n, dim);
+    if (rc) {
+        fclose(f);
+        fsgpu_index_destroy(ix);
+        return rc;
+    }
+    // the slab goes file -> pinned staging -> device in 32 MiB pieces (two buffers in flight): no host copy
+    // of the whole slab, no pageable memcpy
+    const uint64_t slab_bytes = n * dim * elem;
+    cudaError_t e = cudaSuccess;
+    void* d_dst = nullptr;
+    if (slab_bytes) {
+        e = cudaMalloc(&d_dst, slab_bytes);
+        if (e == cudaSuccess) {
+            if (quant == 1) {
+                ix->d_slab = static_cast<uint16_t*>(d_dst);
+                ix->owns_slab = true;
+            } else {
+                ix->d_slab_f32 = static_cast<float*>(d_dst);
+            }
+        }
+    }
+    constexpr size_t kPiece = (size_t)32 << 20;
+    uint8_t* stage[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    for (int i = 0; i < 2 && e == cudaSuccess && slab_bytes; ++i) {
+        e = cudaHostAlloc(reinterpret_cast<void**>(&stage[i]), (size_t)std::min<uint64_t>(kPiece, slab_bytes), cudaHostAllocDefault);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming);
+    }
+    bool short_read = false;
+    if (e == cudaSuccess && slab_bytes) {
+        fseeko(f, (off_t)(vectors_offset + row_start * dim * elem), SEEK_SET);
+        int which = 0;
+        for (uint64_t off = 0; off < slab_bytes && e == cudaSuccess; off += kPiece, which ^= 1) {
+            const size_t len = (size_t)std::min<uint64_t>(kPiece, slab_bytes - off);
+            if (off >= 2 * kPiece) e = cudaEventSynchronize(done[which]);  // the buffer's previous copy has landed
+            if (e != cudaSuccess) break;
+            if (fread(stage[which], 1, len, f) != len) {
+                short_read = true;
+                break;
+            }
+            e = cudaMemcpyAsync(static_cast<uint8_t*>(d_dst) + off, stage[which], len, cudaMemcpyHostToDevice, ix->stream);
+            if (e == cudaSuccess) e = cudaEventRecord(done[which], ix->stream);
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ix->stream);
+    }
+    fclose(f);
+    for (int i = 0; i < 2; ++i) {
+        if (stage[i]) cudaFreeHost(stage[i]);
+        if (done[i]) cudaEventDestroy(done[i]);
+    }
+    if (short_read || e != cudaSuccess) {
+        fsgpu_index_destroy(ix);
+        if (short_read) return fail(FSGPU_ERR_INDEX_CORRUPTED, "%s: short read (slab)", path);
+        return fail(FSGPU_ERR_SUBSYSTEM, "gpu: slab upload failed: %s", cudaGetErrorString(e));
+    }
+    rc = upload_tombstones(ix, any_tomb ? tomb.data() : nullptr);
+    if (!rc) rc = index_finish_setup(ix);
+    if (rc) {
+        fsgpu_index_destroy(ix);
+        return rc;
+    }
     ix->doc_bytes.swap(doc_bytes);
     ix->doc_off.swap(doc_off);
     if (n) {  // record-table hashes (FNV-1a of the doc id, lib.rs:6120-6127) for device-side hash filters

@@ -165,7 +165,7 @@ __device__ __forceinline__ float warp_exact_dot8(const uint16_t* __restrict__ ro
 // accumulator 0 before combining), 8-lane reduce, scalar tail `result += a*b` (mul, then add).
 __device__ __forceinline__ float warp_exact_dot_f32(const float* __restrict__ row,
                                                     const float* __restrict__ q, uint32_t dim,
-                                                    int reduce_order) {
+                                                    int reduce_order, int tail_fma = 0) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t chunks = dim >> 3;
     const uint32_t groups = chunks >> 2;
@@ -187,8 +187,20 @@ __device__ __forceinline__ float warp_exact_dot_f32(const float* __restrict__ ro
 #pragma unroll
     for (int l = 0; l < 8; ++l) v[l] = __shfl_sync(0xffffffffu, acc, l);
     float result = reduce8(v, reduce_order);
-    for (uint32_t e = chunks * 8u; e < dim; ++e) result = add_rn(result, mul_rn(row[e], q[e]));
+    // scalar tail: `result += a*b` in the slice kernel (simd.rs:218-221), `mul_add` in the bytes kernel of
+    // an f32-quantised FSVI slab (dot_product_f32_bytes_f32, simd.rs:581-760)
+    for (uint32_t e = chunks * 8u; e < dim; ++e)
+        result = tail_fma ? __fmaf_rn(row[e], q[e], result) : add_rn(result, mul_rn(row[e], q[e]));
     return result;
+}
+
+// Exact reference score of one slab row, whichever quantisation the slab has (f16: simd.rs:398-446;
+// f32: simd.rs:581-760).  `slab` points at the start of the slab, `local_row` indexes it.
+__device__ __forceinline__ float warp_exact_row(const void* __restrict__ slab, int slab_is_f32, uint64_t local_row,
+                                                const float* __restrict__ q, uint32_t dim, int reduce_order,
+                                                int tail_fma) {
+    return slab_is_f32 ? warp_exact_dot_f32(static_cast<const float*>(slab) + local_row * dim, q, dim, reduce_order, 1)
+                       : warp_exact_dot(static_cast<const uint16_t*>(slab) + local_row * dim, q, dim, reduce_order, tail_fma);
 }
 
 // ─── CTA-wide bitonic sort, descending, n a power of two, keys in shared memory ─────────────

@@ -268,10 +268,13 @@ mma_prep_queries_i8_kernel(const float* __restrict__ queries, uint32_t batch, ui
         const double e = ((R + Ex) * ey + Ex * nq + (d / 32.0 + 8.0) * (1.0 / 8388608.0) * R * nq +
                           (1.0 / 2097152.0) * (R + Ex) * (nq + ey)) * 1.01;
         float m2 = __double2float_ru(2.0 * e);
-        if (!(m2 >= 0.0f) || !(m2 <= 3.0e38f) || is_bad) m2 = 0.0f;
+        // a finite query so large that the bound itself overflows cannot be covered: it is flagged BEFORE
+        // the margin is clamped (flagging after the clamp could never fire)
+        const bool overflow = !(m2 >= 0.0f) || !(m2 <= 3.0e38f);
+        if (overflow || is_bad) m2 = 0.0f;
         margin2[b] = m2;
         qscale[b] = __fmul_rn(sx, sy);
-        redo[b] = (b < batch && (is_bad || !(m2 <= 3.0e38f))) ? 1u : 0u;
+        redo[b] = (b < batch && (is_bad || overflow)) ? 1u : 0u;
     }
 }
 

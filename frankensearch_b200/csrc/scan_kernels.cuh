@@ -431,7 +431,8 @@ struct MergeArgs {
     fsgpu_hit_t* out_hits;    // [batch, k_out] (nullable)
     uint32_t* out_counts;     // [batch] (nullable)
     // optional exact re-computation of -inf/NaN class scores from the local slab
-    const uint16_t* slab;
+    const void* slab;         // f16 slab, or f32 when slab_is_f32 (an f32-quantised FSVI file)
+    int slab_is_f32;
     const float* queries;     // [batch, dim]
     uint64_t n_rows, row_base;
     uint32_t dim;
@@ -519,9 +520,8 @@ __global__ void __launch_bounds__(kScanThreads) merge_topk_kernel(const MergeArg
             if (!have && args.slab) {
                 const uint64_t grow = key_row(key);
                 if (grow >= args.row_base && grow - args.row_base < args.n_rows) {
-                    raw = warp_exact_dot(args.slab + (grow - args.row_base) * args.dim,
-                                         args.queries + (size_t)b * args.dim, args.dim,
-                                         args.reduce_order, args.tail_fma);
+                    raw = warp_exact_row(args.slab, args.slab_is_f32, grow - args.row_base,
+                                         args.queries + (size_t)b * args.dim, args.dim, args.reduce_order, args.tail_fma);
                 }
             }
             if (lane == 0) args.out_hits[(size_t)b * args.k_out + i].score = raw;
@@ -845,7 +845,7 @@ i8_select_kernel(const float* __restrict__ approx, uint64_t n_rows, const float*
 
 // ─── gather-dot: quality_scores_for_hits (two_tier.rs:1566-1631, :1946-1973) ────────────────
 __global__ void __launch_bounds__(kScanThreads)
-scores_for_rows_kernel(const uint16_t* __restrict__ slab, uint64_t n_rows, uint64_t row_base,
+scores_for_rows_kernel(const void* __restrict__ slab, int slab_is_f32, uint64_t n_rows, uint64_t row_base,
                        uint32_t dim, const float* __restrict__ queries,
                        const uint32_t* __restrict__ rows, uint32_t row_stride, uint32_t n_per_query,
                        int reduce_order, int tail_fma, float* __restrict__ out_scores,
@@ -860,8 +860,7 @@ scores_for_rows_kernel(const uint16_t* __restrict__ slab, uint64_t n_rows, uint6
     const bool ok = grow != 0xFFFFFFFFull && grow >= row_base && grow - row_base < n_rows;
     float s = 0.0f;
     if (ok)
-        s = warp_exact_dot(slab + (grow - row_base) * dim, queries + (size_t)b * dim, dim,
-                           reduce_order, tail_fma);
+        s = warp_exact_row(slab, slab_is_f32, grow - row_base, queries + (size_t)b * dim, dim, reduce_order, tail_fma);
     if (lane == 0) {
         out_scores[o] = s;
         if (out_present) out_present[o] = ok ? 1 : 0;
@@ -871,7 +870,7 @@ scores_for_rows_kernel(const uint16_t* __restrict__ slab, uint64_t n_rows, uint6
 // ─── score-all: the `limit >= n` / very large k arm (search.rs:449-473) ─────────────────────
 // Writes one order key per live row (0 for tombstoned rows); the caller sorts descending.
 __global__ void __launch_bounds__(kScanThreads)
-score_all_kernel(const uint16_t* __restrict__ slab, const uint8_t* __restrict__ tombstones,
+score_all_kernel(const void* __restrict__ slab, int slab_is_f32, const uint8_t* __restrict__ tombstones,
                  uint64_t n_rows, uint64_t row_base, uint32_t dim,
                  const float* __restrict__ query, int reduce_order, int tail_fma,
                  uint64_t* __restrict__ out_keys) {
@@ -882,7 +881,7 @@ score_all_kernel(const uint16_t* __restrict__ slab, const uint8_t* __restrict__ 
     const int lane = threadIdx.x & 31;
     for (uint64_t row = (uint64_t)blockIdx.x * kScanWarps + (threadIdx.x >> 5); row < n_rows;
          row += (uint64_t)gridDim.x * kScanWarps) {
-        const float s = warp_exact_dot(slab + row * dim, q, dim, reduce_order, tail_fma);
+        const float s = warp_exact_row(slab, slab_is_f32, row, q, dim, reduce_order, tail_fma);
         if (lane == 0)
             out_keys[row] = tombstoned(tombstones, row) ? 0ull
                                                         : make_key(s, (uint32_t)(row_base + row));
@@ -893,7 +892,7 @@ score_all_kernel(const uint16_t* __restrict__ slab, const uint8_t* __restrict__ 
 // count = number of live (non-zero) keys, raw scores restored for the -inf/NaN class.
 __global__ void __launch_bounds__(kScanThreads)
 emit_sorted_prefix_kernel(const uint64_t* __restrict__ sorted, uint32_t k_eff, uint32_t k_out,
-                          const uint16_t* __restrict__ slab, const float* __restrict__ query,
+                          const void* __restrict__ slab, int slab_is_f32, const float* __restrict__ query,
                           uint64_t n_rows, uint64_t row_base, uint32_t dim, int reduce_order,
                           int tail_fma, uint64_t* __restrict__ out_keys,
                           fsgpu_hit_t* __restrict__ out_hits, uint32_t* __restrict__ out_count) {
@@ -914,8 +913,7 @@ emit_sorted_prefix_kernel(const uint64_t* __restrict__ sorted, uint32_t k_eff, u
             if (key && (uint32_t)(key >> 32) == kNegInfOrdered) {
                 const uint64_t grow = key_row(key);
                 if (grow >= row_base && grow - row_base < n_rows)
-                    score = warp_exact_dot(slab + (grow - row_base) * dim, query, dim, reduce_order,
-                                           tail_fma);
+                    score = warp_exact_row(slab, slab_is_f32, grow - row_base, query, dim, reduce_order, tail_fma);
             }
             if (lane == 0) {
                 fsgpu_hit_t h;

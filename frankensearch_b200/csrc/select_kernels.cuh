@@ -263,7 +263,7 @@ gather_list_keys_kernel(const uint16_t* __restrict__ slab, uint64_t row_base, ui
 // search.rs:1549-1553).  One CTA of 1024 threads; dynamic shared memory: kSelMaxK keys.
 __global__ void __launch_bounds__(1024)
 sel_emit_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ positions,
-                const uint32_t* __restrict__ n_sel, uint32_t k, const uint16_t* __restrict__ slab,
+                const uint32_t* __restrict__ n_sel, uint32_t k, const void* __restrict__ slab, int slab_is_f32,
                 const float* __restrict__ query, uint64_t n_rows, uint64_t row_base, uint32_t dim, int reduce_order,
                 int tail_fma, uint64_t* __restrict__ out_keys, fsgpu_hit_t* __restrict__ out_hits,
                 uint32_t* __restrict__ out_count, uint32_t* __restrict__ error_flag) {
@@ -287,7 +287,7 @@ sel_emit_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __r
         if (key && (uint32_t)(key >> 32) == kNegInfOrdered) {
             const uint64_t grow = key_row(key);
             if (grow >= row_base && grow - row_base < n_rows)
-                score = warp_exact_dot(slab + (grow - row_base) * dim, query, dim, reduce_order, tail_fma);
+                score = warp_exact_row(slab, slab_is_f32, grow - row_base, query, dim, reduce_order, tail_fma);
         }
         if (lane == 0) {
             if (out_keys) out_keys[i] = key;

@@ -118,8 +118,11 @@ class GpuVectorIndex:
     def open(cls, path: str, *, device: int = 0, reduce_order="halves_pairwise", row_start: int = 0,
              n_rows: int = 0) -> "GpuVectorIndex":
         """VectorIndex::open (lib.rs:819) for an FSVI v1 / f16 file; doc ids come from the file."""
+        from . import fsvi
+
         h = C.c_void_p()
         o = _options(device, reduce_order, True, False, row_start)
+        o.flags = 1  # FSGPU_OPEN_HOST_REPLAYS_WAL: this host replays the WAL sidecar itself (below); without the flag a pending sidecar is an error
         check(_ffi.lib().fsgpu_index_open_fsvi(path.encode(), row_start, n_rows, C.byref(o), C.byref(h)))
         ix = cls(h.value, None, dedup_doc_ids=True)
         ix._doc_ids_from_handle = True
@@ -130,6 +133,21 @@ class GpuVectorIndex:
             check(ix._L.fsgpu_index_read_tombstones(ix._h, ptr(bm)))
             flags = np.unpackbits(bm, bitorder="little")[:n].astype(bool)
             ix._tomb = flags if flags.any() else None
+        # pending appends: the sidecar's rows become resident WAL rows again (VectorIndex::open,
+        # lib.rs:1833-1878: last entry of a doc id wins, a stale sidecar is ignored).  append_batch already
+        # tombstoned the main rows they supersede in the record table, and resolve_hits shadows the rest.
+        # A row-range shard only takes the sidecar when it holds the END of the file (WAL rows are numbered
+        # after record_count).
+        header = fsvi.read_fsvi_header(path)
+        if row_start + n == header["record_count"]:
+            try:
+                pending = fsvi.replay_wal_for(path, header)
+            except SearchError:
+                ix.close()
+                raise
+            if pending:
+                ix._wal = [(d, np.ascontiguousarray(v, dtype=np.float32)) for d, v in pending]
+                ix._upload_wal()
         return ix
 
     def close(self) -> None:

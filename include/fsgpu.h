@@ -80,8 +80,14 @@ typedef struct fsgpu_index_options {
     int32_t int8_codes;    /* 1 (default): when dim % 128 == 0 also keep the corpus as int8 codes
                               (+ n_rows * dim bytes of HBM) for the int8 forms of the scan — same
                               results, less time (see fsgpu_index_int8_ready); 0: f16 slab only */
-    int32_t reserved;
+    int32_t flags;         /* FSGPU_OPEN_* bits (0 by default) */
 } fsgpu_index_options;
+
+/* fsgpu_index_open_fsvi: the caller replays the `<path>.wal` sidecar itself (reads it, keeps the last
+ * entry of each doc id, drops a stale one — VectorIndex::open, lib.rs:1833-1878 — and hands the rows to
+ * fsgpu_index_set_wal).  Without this bit a sidecar with pending appends makes the open FAIL rather
+ * than silently drop documents (their superseded main rows are already tombstoned in the file). */
+#define FSGPU_OPEN_HOST_REPLAYS_WAL 1
 
 /* ---- library ------------------------------------------------------------------------------ */
 int fsgpu_abi_version(void);
@@ -104,9 +110,11 @@ int fsgpu_index_create_f32(const float* rows, uint64_t n_rows, uint32_t dim,
                            const uint8_t* tombstones, const fsgpu_index_options* opts,
                            fsgpu_index** out);
 /* Opens a reference-written FSVI v1 file (layout: crates/frankensearch-index/src/lib.rs:6-43;
- * header CRC lib.rs:6114; f16 or f32 quantisation) and uploads rows [row_start, row_start+n)
- * (n_rows_or_0 == 0: to the end).  Tombstone flags and the doc-id string table are kept on the
- * host side of the handle (fsgpu_index_doc_id). */
+ * header CRC lib.rs:6114) and uploads rows [row_start, row_start+n) (n_rows_or_0 == 0: to the end),
+ * streaming the slab through pinned memory.  f16 slabs (quantization 1) get every scan form; f32 slabs
+ * (quantization 0) are scored exactly with the reference's f32 kernel (search.rs:1300-1321) through the
+ * score-every-row + select path.  Tombstone flags and the doc-id string table are kept on the host
+ * side of the handle (fsgpu_index_doc_id).  v2 identity headers are not read (IndexCorrupted). */
 int fsgpu_index_open_fsvi(const char* path, uint64_t row_start, uint64_t n_rows_or_0,
                           const fsgpu_index_options* opts, fsgpu_index** out);
 void fsgpu_index_destroy(fsgpu_index* index);

@@ -155,6 +155,28 @@ def dot_f32_f32(a: np.ndarray, b: np.ndarray, reduce_order: int = 0) -> np.float
     return F32(result)
 
 
+def dot_f32_bytes_f32(a: np.ndarray, b: np.ndarray, reduce_order: int = 0) -> np.float32:
+    """dot_product_f32_bytes_f32 (simd.rs:581-760), the score of a row of an f32-quantised FSVI slab
+    (search.rs:1300-1321): the tree of dot_f32_f32 with a `mul_add` scalar tail."""
+    a = np.asarray(a, dtype=np.float32)
+    b = np.asarray(b, dtype=np.float32)
+    dim = a.size
+    chunks, groups = dim // 8, dim // 32
+    s = np.zeros((4, 8), dtype=np.float32)
+    with np.errstate(all="ignore"):
+        for g in range(groups):
+            for acc in range(4):
+                lo = g * 32 + acc * 8
+                s[acc] = s[acc] + a[lo:lo + 8] * b[lo:lo + 8]
+        v = (s[0] + s[1]) + (s[2] + s[3])
+        for c in range(groups * 4, chunks):
+            v = v + a[c * 8:c * 8 + 8] * b[c * 8:c * 8 + 8]
+        result = _reduce8(v, reduce_order)
+        for e in range(chunks * 8, dim):
+            result = _fma_f32(a[e], b[e], result)
+    return F32(result)
+
+
 def resolve_sorted_entries(rows, scores, main_doc_ids, wal_doc_ids, tombstones=None):
     """The doc-id half of resolve_sorted_entries (search.rs:1503-1558) over best-first winners:
     a WAL winner (row >= len(main_doc_ids)) is dropped if its doc id was already emitted; a main

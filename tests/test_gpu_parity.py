@@ -560,3 +560,36 @@ def test_concurrent_callers_share_one_index(gpu, cpu, fo):
             for a, b in zip(results[i][rep], want):
                 assert np.array_equal(a, b), (i, rep)
     ix.close()
+
+
+@pytest.mark.parametrize("dim", [128, 100])
+def test_fsvi_f32_quantised_file(gpu, fo, tmp_path, dim):
+    """An f32-quantised FSVI v1 file (quantization byte 0, lib.rs:6-43) is scored with the reference's f32
+    kernel (dot_product_f32_bytes_f32, simd.rs:581-760 — `mul_add` scalar tail — search.rs:1300-1321):
+    rows and score bits equal a NumPy restatement of that kernel for small, large and all-rows limits,
+    with tombstones; re-scoring (dot_query_at) uses the same kernel."""
+    import frankensearch_b200 as fs
+    from frankensearch_b200.fsvi import QUANT_F32, write_fsvi_v1
+
+    n = 2500
+    _, vec = fo.synth_rows(1, 71, 0, n, dim, want_f32=True)
+    ids = [f"doc-{i:06}" for i in range(n)]
+    tomb = [i % 53 == 7 for i in range(n)]
+    path = str(tmp_path / "f32.fsvi")
+    perm = write_fsvi_v1(path, "bench-f32", dim, ids, vec, tombstones=tomb, quantization=QUANT_F32)
+    ix = fs.GpuVectorIndex.open(path)
+    rows_f32 = vec[perm]
+    live = ~np.array(tomb)[perm]
+    for qi in (0, 5):
+        q = fo.clustered_query(qi, dim)
+        exact = np.array([no.dot_f32_bytes_f32(rows_f32[r], q) for r in range(n)], dtype=np.float32)
+        for k in (10, 300, 5000):
+            want_rows, want_scores = no.top_k(exact, k, live)
+            hits = ix.search_top_k(q, k)
+            assert [h.index for h in hits] == [int(r) for r in want_rows], (dim, qi, k)
+            assert np.array_equal(bits([h.score for h in hits]), bits(want_scores)), (dim, qi, k)
+        got, present = ix.scores_for_rows(q, np.arange(0, n, 97, dtype=np.uint32))
+        assert present.all() and np.array_equal(bits(got), bits(exact[::97]))
+    with pytest.raises(fs.SearchError):
+        ix.read_rows_f16(0, 1)
+    ix.close()

@@ -2,6 +2,8 @@
 merged on the device (search.rs:476-493, :1449-1475), doc-id shadowing / dedup on the host
 (search.rs:1503-1558).  Checked against the reference's own WAL tests (tests/ref_cases.py
 WAL_SCENARIOS) and bit-for-bit against the oracle model (tests/wal_model.py)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -151,5 +153,56 @@ def test_wal_errors():
     with pytest.raises(fs.SearchError) as e:
         ix.append("b", [0.0, 0.0, 0.0, 0.0])
     assert e.value.kind == "InvalidConfig"
+    assert ix.wal_record_count() == 0
+    ix.close()
+
+
+def test_open_replays_the_wal_sidecar(fo, tmp_path):
+    """VectorIndex::open (lib.rs:1833-1878): pending appends in `<index>.wal` are searchable after a
+    reopen — updated documents (their main rows were tombstoned by append_batch, lib.rs:2546-2720), new
+    documents, last-entry-wins inside the sidecar, a torn tail ignored.  The C entry point refuses to
+    open such a file for a host that has not declared it replays the sidecar."""
+    import ctypes as C
+
+    import frankensearch_b200 as fs
+    from frankensearch_b200 import fsvi
+
+    n, dim = 600, 128
+    _, vec = fo.synth_rows(1, 61, 0, n, dim, want_f32=True)
+    ids = [f"doc-{i:06}" for i in range(n)]
+    rng = np.random.default_rng(2)
+    fresh = fo.normalize(rng.standard_normal(dim).astype(np.float32))
+    upd = fo.normalize((vec[10] + 0.5 * rng.standard_normal(dim)).astype(np.float32))
+    upd2 = fo.normalize((vec[10] + 0.1 * rng.standard_normal(dim)).astype(np.float32))
+    path = str(tmp_path / "idx.fsvi")
+    tomb = [d in ("doc-000010", "doc-000333") for d in ids]  # rows superseded by the pending appends
+    perm = fsvi.write_fsvi_v1(path, "bench-128", dim, ids, vec, tombstones=tomb)
+    wal = fsvi.wal_path_for(path)
+    fsvi.append_wal_batch(wal, [("doc-000010", upd), ("new-a", fresh)], dim, compaction_gen=1)
+    fsvi.append_wal_batch(wal, [("doc-000333", vec[5]), ("doc-000010", upd2)], dim, compaction_gen=1)
+    with open(wal, "ab") as f:
+        f.write(b"FWB1\x09\x00\x00\x00torn")
+    # a host that does not replay the sidecar must not get a silently incomplete index
+    h, o = C.c_void_p(), fs._ffi.IndexOptions()
+    fs._ffi.lib().fsgpu_index_options_default(C.byref(o))
+    rc = fs._ffi.lib().fsgpu_index_open_fsvi(path.encode(), 0, 0, C.byref(o), C.byref(h))
+    assert rc == 2 and b"WAL sidecar" in fs._ffi.lib().fsgpu_last_error()
+    ix = fs.GpuVectorIndex.open(path)
+    assert [d for d, _ in ix.wal_records()] == ["new-a", "doc-000333", "doc-000010"]
+    slab = fo.encode_f16(vec[perm])
+    wal_rows = np.stack([v for _, v in ix.wal_records()])
+    # WAL vectors are stored in the index quantisation (f16) and widened back exactly (wal.rs:1132-1160)
+    assert np.array_equal(wal_rows[0], fo.decode_f16(fo.encode_f16(fresh)))
+    for q in (fresh, upd2, fo.clustered_query(3, dim)):
+        hits = ix.search_top_k(q, 20)
+        rows, scores = fo.search_top_k_wal(slab, wal_rows, q, 20, fo.pack_bitmap(np.array(tomb)[perm]))
+        assert [h.index for h in hits] == [int(r) for r in rows]
+        assert np.array_equal(bits([h.score for h in hits]), bits(scores))
+    assert ix.search_top_k(fresh, 1)[0].doc_id == "new-a"
+    assert ix.search_top_k(upd2, 1)[0].doc_id == "doc-000010"
+    ix.close()
+    os.remove(wal)
+    fsvi.append_wal_batch(wal, [("new-b", fresh)], dim, compaction_gen=9)  # stale generation: ignored (lib.rs:1856-1878)
+    ix = fs.GpuVectorIndex.open(path)
     assert ix.wal_record_count() == 0
     ix.close()

@@ -380,3 +380,64 @@ def test_bitset_and_predicate_filters_follow_the_reference_seam(fo):
     p = PredicateFilter("only-b", lambda d: d == "doc-b")
     assert p.matches("doc-b") and not p.matches("doc-a") and p("doc-b") and p.name == "only-b"
     assert p.matches_doc_id_hash(123) is None and p.candidate_hashes() is None
+
+
+# ── WAL sidecar (crates/frankensearch-index/src/wal.rs) and the WAL half of VectorIndex::open ──
+def test_wal_sidecar_layout_roundtrip_and_crash_tolerance(tmp_path):
+    """wal.rs:1-27 layout, :852-866 read_wal, :980-1130 parse: header CRC, batch CRC, a corrupt or
+    truncated final batch ends the replay without an error, a bad header IS an error."""
+    from frankensearch_b200 import fsvi
+    from frankensearch_b200._ffi import SearchError
+
+    p = str(tmp_path / "x.fsvi.wal")
+    assert fsvi.wal_path_for("/a/b/data.fsvi") == "/a/b/data.fsvi.wal"  # wal.rs:2493-2499
+    assert fsvi.read_wal(p, 4) == ([], 0, 0)
+    v = lambda *x: np.array(x, dtype=np.float32)  # noqa: E731
+    fsvi.append_wal_batch(p, [("a", v(1, 0, 0, 0)), ("b", v(0, 1, 0, 0))], 4, compaction_gen=1)
+    fsvi.append_wal_batch(p, [("a", v(0, 0, 1, 0))], 4, compaction_gen=1)
+    data = open(p, "rb").read()
+    assert data[:4] == b"FWAL" and struct.unpack_from("<HIBB", data, 4) == (1, 4, 1, 1)
+    assert struct.unpack_from("<I", data, 16)[0] == zlib.crc32(data[:16]) & 0xFFFFFFFF
+    assert data[20:24] == b"FWB1" and struct.unpack_from("<I", data, 24)[0] == 2
+    entries, gen, valid = fsvi.read_wal(p, 4)
+    assert [d for d, _ in entries] == ["a", "b", "a"] and gen == 1 and valid == len(data)
+    assert entries[2][1].tolist() == [0, 0, 1, 0]
+    with open(p, "ab") as f:  # a torn third batch: replay stops before it
+        f.write(b"FWB1" + struct.pack("<I", 5) + b"\x01\x00z")
+    entries2, _, valid2 = fsvi.read_wal(p, 4)
+    assert len(entries2) == 3 and valid2 == valid
+    with pytest.raises(SearchError) as e:  # dimension mismatch in the header
+        fsvi.read_wal(p, 8)
+    assert e.value.kind == "IndexCorrupted"
+    bad = bytearray(data)
+    bad[7] ^= 1
+    open(p, "wb").write(bytes(bad))
+    with pytest.raises(SearchError):  # header CRC
+        fsvi.read_wal(p, 4)
+    open(p, "wb").write(b"FWAL\x01")  # shorter than the header: ignored (wal.rs:861-864)
+    assert fsvi.read_wal(p, 4) == ([], 0, 0)
+
+
+def test_wal_replay_last_wins_and_stale_generation(tmp_path):
+    """VectorIndex::open, lib.rs:1845-1878: the last entry of a doc id wins (order of the last entries);
+    a sidecar whose generation is not the successor of the main file's is discarded."""
+    from frankensearch_b200 import fsvi
+
+    path = str(tmp_path / "idx.fsvi")
+    vec = np.eye(4, dtype=np.float32)
+    fsvi.write_fsvi_v1(path, "e", 4, ["m0", "m1", "m2", "m3"], vec)
+    h = fsvi.read_fsvi_header(path)
+    assert (h["dimension"], h["quantization"], h["record_count"], h["compaction_gen"]) == (4, 1, 4, 0)
+    wal = fsvi.wal_path_for(path)
+    fsvi.append_wal_batch(wal, [("x", vec[0]), ("y", vec[1]), ("x", vec[2])], 4, compaction_gen=1)
+    fsvi.append_wal_batch(wal, [("z", vec[3]), ("y", vec[0])], 4, compaction_gen=1)
+    kept = fsvi.replay_wal_for(path)
+    assert [d for d, _ in kept] == ["x", "z", "y"]
+    assert kept[0][1].tolist() == vec[2].tolist() and kept[2][1].tolist() == vec[0].tolist()
+    os.remove(wal)
+    fsvi.append_wal_batch(wal, [("x", vec[0])], 4, compaction_gen=3)  # not next_generation(0) == 1: stale
+    assert fsvi.replay_wal_for(path) == []
+    os.remove(wal)
+    fsvi.append_wal_batch(wal, [("x", vec[0])], 4, compaction_gen=0)  # legacy generation 0 on a generation-0 file
+    assert [d for d, _ in fsvi.replay_wal_for(path)] == ["x"]
+    assert fsvi.next_generation(255) == 1 and fsvi.next_generation(7) == 8
