@@ -109,7 +109,7 @@ EXPORTS = [
     "fsgpu_index_device_slab", "fsgpu_index_set_doc_ids", "fsgpu_index_doc_id",
     "fsgpu_index_set_tombstones", "fsgpu_index_read_tombstones", "fsgpu_index_int8_ready",
     "fsgpu_index_read_codes_i8",
-    "fsgpu_index_set_wal", "fsgpu_index_wal_rows", "fsgpu_index_read_rows_f16", "fsgpu_index_profile_enable",
+    "fsgpu_index_set_wal", "fsgpu_index_wal_rows", "fsgpu_index_zero_signal_state", "fsgpu_index_read_rows_f16", "fsgpu_index_profile_enable",
     "fsgpu_index_profile_read", "fsgpu_index_last_status", "fsgpu_measure_tensor_peak", "fsgpu_search_top_k", "fsgpu_search_top_k_device",
     "fsgpu_search_top_k_filtered", "fsgpu_search_top_k_filtered_device",
     "fsgpu_index_set_doc_hashes", "fsgpu_search_top_k_hashes",
@@ -165,6 +165,7 @@ def lib() -> C.CDLL:
     L.fsgpu_index_set_doc_hashes.argtypes = [_vp, _vp]
     L.fsgpu_search_top_k_hashes.argtypes = [_vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, _vp, C.c_uint32, _vp,
                                             _vp, _vp, C.POINTER(C.c_int)]
+    L.fsgpu_index_zero_signal_state.argtypes = [_vp, _vp]
     L.fsgpu_index_set_wal.argtypes = [_vp, _vp, C.c_uint32, C.c_uint64]
     L.fsgpu_index_wal_rows.argtypes = [_vp]
     L.fsgpu_index_wal_rows.restype = C.c_uint32

@@ -1563,6 +1563,37 @@ extern "C" int fsgpu_index_read_tombstones(const fsgpu_index* ix, uint8_t* out_b
     return FSGPU_OK;
 }
 
+extern "C" int fsgpu_index_zero_signal_state(const fsgpu_index* ix, uint64_t* out_state) {
+    if (!ix || !out_state) return fail(FSGPU_ERR_INVALID_CONFIG, "NULL argument");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    DeviceGuard g(ix->device);
+    unsigned long long counts[2] = {0, 0};
+    if (ix->n_rows) {
+        int rc = begin_call_locked(ix, ix->stream, true);
+        if (rc) return rc;
+        unsigned long long* d_counts = nullptr;
+        CUDA_TRY(cudaMalloc(&d_counts, 16));
+        cudaError_t e = cudaMemsetAsync(d_counts, 0, 16, ix->stream);
+        if (e == cudaSuccess) {
+            const int grid = (int)std::min<uint64_t>((ix->n_rows + 255) / 256, (uint64_t)ix->num_sms * 8);
+            census_kernel<<<grid, 256, 0, ix->stream>>>(ix->slab_any(), ix->is_f32(), ix->n_rows, ix->dim, ix->d_tomb, d_counts);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(counts, d_counts, 16, cudaMemcpyDeviceToHost, ix->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ix->stream);
+        cudaFree(d_counts);
+        if (e != cudaSuccess) return fail(FSGPU_ERR_SUBSYSTEM, "gpu: census failed: %s", cudaGetErrorString(e));
+        rc = end_call_locked(ix, ix->stream);
+        if (rc) return rc;
+    }
+    out_state[0] = ix->n_rows;               // record_count
+    out_state[1] = ix->n_rows - counts[0];   // live_count
+    out_state[2] = counts[0];                // tombstone_count
+    out_state[3] = ix->n_wal;                // wal_count
+    out_state[4] = counts[1];                // usable_vector_count
+    return FSGPU_OK;
+}
+
 extern "C" int fsgpu_index_set_wal(fsgpu_index* ix, const float* embeddings, uint32_t n_wal, uint64_t virtual_base) {
     if (!ix) return fail(FSGPU_ERR_INVALID_CONFIG, "index is NULL");
     if (n_wal && !embeddings) return fail(FSGPU_ERR_INVALID_CONFIG, "embeddings is NULL");

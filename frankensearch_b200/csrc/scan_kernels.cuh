@@ -867,6 +867,40 @@ scores_for_rows_kernel(const void* __restrict__ slab, int slab_is_f32, uint64_t 
     }
 }
 
+// ─── zero-signal census (VectorIndex::zero_signal_state, lib.rs:2441-2459) ──────────────────
+// counts[0] = tombstoned rows, counts[1] = live rows whose stored vector is usable: every element
+// finite and the SEQUENTIAL f32 sum of squares positive and finite (vector_signal_usable,
+// lib.rs:6133-6142).  One thread per row, elements in order: a lazy pass that only runs to classify an
+// EMPTY result (search.rs:206-260), so simplicity beats coalescing.
+__global__ void __launch_bounds__(256)
+census_kernel(const void* __restrict__ slab, int slab_is_f32, uint64_t n_rows, uint32_t dim,
+              const uint8_t* __restrict__ tombstones, unsigned long long* __restrict__ counts) {
+    unsigned long long dead = 0, usable = 0;
+    for (uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n_rows; row += (uint64_t)gridDim.x * blockDim.x) {
+        if (tombstoned(tombstones, row)) {
+            ++dead;
+            continue;
+        }
+        float norm_sq = 0.0f;
+        bool finite = true;
+        for (uint32_t i = 0; i < dim && finite; ++i) {
+            const float v = slab_is_f32 ? static_cast<const float*>(slab)[row * dim + i]
+                                        : h2f(static_cast<const uint16_t*>(slab)[row * dim + i]);
+            if (!isfinite(v)) finite = false;
+            norm_sq = add_rn(norm_sq, mul_rn(v, v));
+        }
+        if (finite && norm_sq > 0.0f && isfinite(norm_sq)) ++usable;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        dead += __shfl_xor_sync(0xffffffffu, dead, o);
+        usable += __shfl_xor_sync(0xffffffffu, usable, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (dead) atomicAdd(counts, dead);
+        if (usable) atomicAdd(counts + 1, usable);
+    }
+}
+
 // ─── score-all: the `limit >= n` / very large k arm (search.rs:449-473) ─────────────────────
 // Writes one order key per live row (0 for tombstoned rows); the caller sorts descending.
 __global__ void __launch_bounds__(kScanThreads)

@@ -15,7 +15,7 @@ import numpy as np
 
 from . import _ffi
 from ._ffi import SearchError, check, ptr
-from .types import VectorHit, fnv1a_hash
+from .types import ClassifiedHits, VectorHit, ZeroSignalReason, ZeroSignalState, fnv1a_hash
 
 REDUCE_ORDERS = {
     "halves_pairwise": 0, "avx_tree": 1, "halves_sequential": 2, "halves_stride2": 3, "sequential": 4,
@@ -399,6 +399,29 @@ class GpuVectorIndex:
                 out.append(h)
             hits = out
         return hits
+
+    def zero_signal_state(self) -> ZeroSignalState:
+        """VectorIndex::zero_signal_state (lib.rs:2441-2459): one census pass on the device."""
+        out = np.zeros(5, dtype=np.uint64)
+        check(self._L.fsgpu_index_zero_signal_state(self._h, ptr(out)))
+        return ZeroSignalState(*(int(x) for x in out))
+
+    def search_top_k_classified(self, query, limit: int, filter=None) -> ClassifiedHits:
+        """VectorIndex::search_top_k_classified (search.rs:206-260): like search_top_k, but a non-finite
+        query is rejected (InvalidConfig on `query`) and an empty result always says why."""
+        q = np.ascontiguousarray(query, dtype=np.float32).reshape(-1)
+        if q.size != self.dimension():  # ensure_query_dimension comes first (search.rs:233)
+            raise SearchError("DimensionMismatch", f"expected {self.dimension()}, found {q.size}")
+        if limit == 0:
+            return ClassifiedHits([], ZeroSignalReason.CALLER_REQUESTED_ZERO_K)
+        if not np.isfinite(q).all():
+            raise SearchError("InvalidConfig", "query: <contains non-finite values>: query vector must be finite")
+        if not q.any():
+            return ClassifiedHits([], ZeroSignalReason.ZERO_NORM_QUERY)
+        hits = self.search_top_k(q, limit, filter=filter)
+        if not hits:
+            return ClassifiedHits(hits, self.zero_signal_state().empty_result_reason(filter is not None))
+        return ClassifiedHits(hits, None)
 
     def search_top_k_device(self, d_queries, limit: int, *, want_hits: bool = True, stream=None):
         """Device-resident form: `d_queries` is a CUDA float32 tensor [B, dim].  Returns torch

@@ -150,6 +150,13 @@ int fsgpu_index_read_codes_i8(const fsgpu_index* index, uint64_t row_start, uint
 /* VectorIndex::is_deleted (lib.rs:2401-2406) in bulk: the current soft-delete bitmap over local rows
  * ((n_rows + 7) / 8 bytes; for an FSVI file, flag bit 0 of each record as read at open). */
 int fsgpu_index_read_tombstones(const fsgpu_index* index, uint8_t* out_bitmap);
+/* VectorIndex::zero_signal_state (crates/frankensearch-index/src/lib.rs:2441-2459): the census that
+ * classifies an EMPTY result (ZeroSignalState, crates/frankensearch-core/src/config.rs:682-741).
+ * out_state[5] = {record_count, live_count, tombstone_count, wal_count, usable_vector_count}, where a
+ * usable vector is finite with a positive finite squared norm (vector_signal_usable, lib.rs:6133-6142).
+ * One pass over the slab; only called when a well-formed search came back empty. */
+int fsgpu_index_zero_signal_state(const fsgpu_index* index, uint64_t* out_state);
+
 /* Replaces the resident WAL rows of VectorIndex (`wal_entries`: f32 embeddings appended since the
  * last compaction, crates/frankensearch-index/src/lib.rs:2532-2720, wal.rs:101-107).  `embeddings`
  * is host memory, [n_wal, dim] f32 in WAL order; n_wal = 0 clears.  Every search then also scores

@@ -593,3 +593,66 @@ def test_fsvi_f32_quantised_file(gpu, fo, tmp_path, dim):
     with pytest.raises(fs.SearchError):
         ix.read_rows_f16(0, 1)
     ix.close()
+
+
+def test_classified_lane_replays_reference_cases(gpu, fo):
+    """search.rs:2430-2600 (classified_*): k = 0 vs a never-populated index, non-finite query rejected
+    (the unclassified lane keeps scoring it), zero-norm query, a filter that rejects everything, an
+    all-tombstoned index, a non-empty result carries no reason; plus the census itself."""
+    import frankensearch_b200 as fs
+    from frankensearch_b200.types import ZeroSignalReason as R
+
+    e0 = [1.0, 0.0, 0.0, 0.0]
+    empty = fs.GpuVectorIndex.from_vectors([], np.zeros((0, 4), dtype=np.float32))
+    c = empty.search_top_k_classified(e0, 0)
+    assert c.hits == [] and c.zero_signal == R.CALLER_REQUESTED_ZERO_K
+    c = empty.search_top_k_classified(e0, 5)
+    assert c.hits == [] and c.zero_signal == R.NEWLY_CREATED_EMPTY
+    empty.close()
+
+    one = fs.GpuVectorIndex.from_vectors(["doc-a"], np.array([[0.1, 0, 0, 0]], dtype=np.float32))
+    with pytest.raises(fs.SearchError) as err:
+        one.search_top_k_classified([float("nan"), 0, 0, 0], 5)
+    assert err.value.kind == "InvalidConfig" and "query" in err.value.message
+    with pytest.raises(fs.SearchError):
+        one.search_top_k_classified([float("inf"), 0, 0, 0], 5)
+    assert len(one.search_top_k([float("nan"), 0, 0, 0], 5)) == 1  # legacy lane is unchanged (search.rs:2474)
+    c = one.search_top_k_classified([0.0, 0, 0, 0], 5)
+    assert c.hits == [] and c.zero_signal == R.ZERO_NORM_QUERY
+    c = one.search_top_k_classified(e0, 5)
+    assert len(c.hits) == 1 and c.zero_signal is None
+    with pytest.raises(fs.SearchError) as err:
+        one.search_top_k_classified([1.0, 0, 0], 5)
+    assert err.value.kind == "DimensionMismatch"
+    one.close()
+
+    two = fs.GpuVectorIndex.from_vectors(["doc-a", "doc-b"], np.array([[0.1, 0, 0, 0], [0.2, 0, 0, 0]], dtype=np.float32))
+    c = two.search_top_k_classified(e0, 5, filter=fs.PredicateFilter("reject-all", lambda _d: False))
+    assert c.hits == [] and c.zero_signal == R.FILTER_ELIMINATED_ALL
+    st = two.zero_signal_state()
+    assert (st.record_count, st.live_count, st.tombstone_count, st.wal_count, st.usable_vector_count) == (2, 2, 0, 0, 2)
+    two.soft_delete("doc-a")
+    two.soft_delete("doc-b")
+    c = two.search_top_k_classified(e0, 5)
+    assert c.hits == [] and c.zero_signal == R.ALL_TOMBSTONED
+    two.close()
+
+    # TwoTierIndex::search_fast_classified (two_tier.rs:1358-1390) + quality re-scoring through the pair
+    slab, vec = fo.synth_rows(1, 81, 0, 500, 128, want_f32=True)
+    ids = [f"doc-{i:06}" for i in range(500)]
+    fast = fs.GpuVectorIndex.from_vectors(ids, vec)
+    quality = fs.GpuVectorIndex.from_vectors(ids, vec[:, ::-1].copy())
+    tt = fs.GpuTwoTierIndex(fast, quality)
+    q = fo.clustered_query(1, 128)
+    c = tt.search_fast_classified(q, 7)
+    assert c.zero_signal is None and [h.index for h in c.hits] == [h.index for h in tt.search_fast(q, 7)]
+    assert tt.search_fast_classified(q, 0).zero_signal == R.CALLER_REQUESTED_ZERO_K
+    assert tt.search_fast_classified(np.zeros(128, dtype=np.float32), 7).zero_signal == R.ZERO_NORM_QUERY
+    with pytest.raises(fs.SearchError):
+        tt.search_fast_classified(np.full(128, np.nan, dtype=np.float32), 7)
+    qs = tt.quality_scores_for_hits(q, c.hits)
+    want, _ = fo.scores_for_rows(fo.encode_f16(vec[:, ::-1].copy()), q, [h.index for h in c.hits], tail_fma=False)
+    assert np.array_equal(bits(qs), bits(want))
+    assert tt.has_quality_index() and tt.doc_count() == 500
+    fast.close()
+    quality.close()

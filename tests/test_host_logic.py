@@ -441,3 +441,61 @@ def test_wal_replay_last_wins_and_stale_generation(tmp_path):
     fsvi.append_wal_batch(wal, [("x", vec[0])], 4, compaction_gen=0)  # legacy generation 0 on a generation-0 file
     assert [d for d, _ in fsvi.replay_wal_for(path)] == ["x"]
     assert fsvi.next_generation(255) == 1 and fsvi.next_generation(7) == 8
+
+
+# ── budgets, query classes, zero-signal classification (host arithmetic of the searcher) ─────
+def test_scaled_budget_and_class_multipliers():
+    """searcher.rs:120-126, :1599-1608 and query_class.rs:197-215 (identifier_leans_lexical :375,
+    natural_language_leans_semantic :383, short_keyword_is_balanced :391, empty_has_zero_budgets :401)."""
+    from frankensearch_b200.types import QueryClass, phase1_budgets, scaled_budget
+
+    assert scaled_budget(30, 0.5) == 15 and scaled_budget(30, 2.0) == 60 and scaled_budget(30, 1.0) == 30
+    assert scaled_budget(3, 0.5) == 2 and scaled_budget(1, 0.5) == 1  # ceil, at least 1
+    assert scaled_budget(0, 2.0) == 0 and scaled_budget(30, 0.0) == 0 and scaled_budget(30, float("nan")) == 0
+    assert scaled_budget(30, float("inf")) == 0 and scaled_budget(30, -1.0) == 0
+    qc = QueryClass
+    assert qc.lexical_budget_multiplier(qc.IDENTIFIER) > qc.semantic_budget_multiplier(qc.IDENTIFIER)
+    assert qc.semantic_budget_multiplier(qc.NATURAL_LANGUAGE) > qc.lexical_budget_multiplier(qc.NATURAL_LANGUAGE)
+    assert qc.lexical_budget_multiplier(qc.SHORT_KEYWORD) == qc.semantic_budget_multiplier(qc.SHORT_KEYWORD) == 1.0
+    assert qc.lexical_budget_multiplier(qc.EMPTY) == qc.semantic_budget_multiplier(qc.EMPTY) == 0.0
+    assert phase1_budgets(10, 3, qc.IDENTIFIER) == (30, 15, 60)
+    assert phase1_budgets(10, 3, qc.NATURAL_LANGUAGE) == (30, 60, 15)
+    assert phase1_budgets(10, 0, qc.SHORT_KEYWORD) == (10, 10, 10)  # multiplier.max(1)
+
+
+def test_query_class_classify_reference_cases():
+    """query_class.rs:238-372, literal for literal."""
+    from frankensearch_b200.types import QueryClass as Q
+
+    table = {
+        "": Q.EMPTY, "   ": Q.EMPTY, "\\t\\n".encode().decode("unicode_escape"): Q.EMPTY,
+        "src/main.rs": Q.IDENTIFIER, "path/to/file.txt": Q.IDENTIFIER,
+        "how should we handle HTTP status 404/500 errors": Q.NATURAL_LANGUAGE,
+        "http 404/500": Q.SHORT_KEYWORD, "bd-123": Q.IDENTIFIER, "JIRA-456": Q.IDENTIFIER,
+        "my-project-123": Q.IDENTIFIER, "repo_name-789": Q.IDENTIFIER,
+        "error-handling": Q.SHORT_KEYWORD, "load-balancer": Q.SHORT_KEYWORD, "bd-ab": Q.SHORT_KEYWORD,
+        "std::collections::HashMap": Q.IDENTIFIER, "config.toml": Q.IDENTIFIER,
+        "fn search_query": Q.IDENTIFIER, "struct TwoTierConfig": Q.IDENTIFIER,
+        "search": Q.SHORT_KEYWORD, "error handling": Q.SHORT_KEYWORD, "vector index search": Q.SHORT_KEYWORD,
+        "how does the search pipeline work?": Q.NATURAL_LANGUAGE,
+        "find all documents about distributed consensus": Q.NATURAL_LANGUAGE,
+    }
+    for text, want in table.items():
+        assert Q.classify(text) == want, text
+        assert Q.classify("  " + text + " ") == want, text  # classify_is_trim_invariant (:436)
+
+
+def test_zero_signal_state_classification_table():
+    """config.rs:1080-1153 zero_signal_state_classification_table + empty_result_reason (:729-740)."""
+    from frankensearch_b200.types import ZeroSignalReason as R
+    from frankensearch_b200.types import ZeroSignalState as S
+
+    cases = [(S(), R.NEWLY_CREATED_EMPTY), (S(5, 0, 5, 0, 0), R.ALL_TOMBSTONED), (S(5, 3, 2, 0, 0), R.NO_USABLE_VECTORS),
+             (S(0, 0, 0, 4, 0), None), (S(5, 0, 5, 2, 0), None), (S(5, 5, 0, 0, 5), None)]
+    for state, want in cases:
+        assert state.state_reason() == want, state
+    assert S(0, 0, 0, 4, 0).is_wal_only()
+    assert S(5, 5, 0, 0, 5).empty_result_reason(True) == R.FILTER_ELIMINATED_ALL
+    assert S(5, 0, 5, 2, 0).empty_result_reason(False) == R.WAL_ONLY_NO_LIVE_RECORDS
+    assert S(5, 5, 0, 0, 5).empty_result_reason(False) == R.NO_USABLE_VECTORS
+    assert S(5, 0, 5, 0, 0).empty_result_reason(True) == R.ALL_TOMBSTONED  # state reasons take precedence
