@@ -2167,23 +2167,70 @@ extern "C" int fsgpu_index_open_fsvi(const char* path, uint64_t row_start, uint6
     cur = 4;
     if (memcmp(magic, "FSVI", 4) != 0) return corrupt("bad magic");
     if (!rd(head, &cur, &version)) return corrupt("truncated header");
-    if (version != 1) return corrupt("unsupported FSVI version (only v1 is read here; v2 identity headers are out of scope)");
-    if (!rd(head, &cur, &len16) || cur + len16 > head.size()) return corrupt("truncated embedder_id");
-    cur += len16;
-    if (!rd(head, &cur, &len16) || cur + len16 > head.size()) return corrupt("truncated embedder_revision");
-    cur += len16;
     uint32_t dim = 0, crc_stored = 0;
     uint8_t quant = 0, reserved[3];
     uint64_t record_count = 0, vectors_offset = 0;
-    if (!rd(head, &cur, &dim) || !rd(head, &cur, &quant) || !rd(head, &cur, &reserved) ||
-        !rd(head, &cur, &record_count) || !rd(head, &cur, &vectors_offset))
-        return corrupt("truncated header");
-    const size_t crc_end = cur;
-    if (!rd(head, &cur, &crc_stored)) return corrupt("truncated header crc");
-    if (crc32_ieee(head.data(), crc_end) != crc_stored) return corrupt("header CRC mismatch");
+    size_t records_offset = 0;
+    if (version == 1) {
+        if (!rd(head, &cur, &len16) || cur + len16 > head.size()) return corrupt("truncated embedder_id");
+        cur += len16;
+        if (!rd(head, &cur, &len16) || cur + len16 > head.size()) return corrupt("truncated embedder_revision");
+        cur += len16;
+        if (!rd(head, &cur, &dim) || !rd(head, &cur, &quant) || !rd(head, &cur, &reserved) ||
+            !rd(head, &cur, &record_count) || !rd(head, &cur, &vectors_offset))
+            return corrupt("truncated header");
+        const size_t crc_end = cur;
+        if (!rd(head, &cur, &crc_stored)) return corrupt("truncated header crc");
+        if (crc32_ieee(head.data(), crc_end) != crc_stored) return corrupt("header CRC mismatch");
+        records_offset = cur;
+    } else if (version == 2) {
+        // FSVI v2 (identity-complete immutable artifact, lib.rs:4229-4520): a 332-byte fixed prefix —
+        // header_size u32, binding schema u16 (= 1), quantization u8, flags u8 (= 0), publication nonce
+        // u16, dimension u32, record_count u64, vectors_offset u64, generation {schema u16, reserved u16
+        // (= 0), sequence u64, nonce [16]}, three canonical-identity lengths u32, eight SHA-256
+        // fingerprints — then the three canonical identity documents and a CRC-32 of everything before it;
+        // the record table starts at header_size.  The LAYOUT is read and checked here; admitting the
+        // identity (fingerprint / bundle validation, lib.rs:4448-4500) is the host's decision before it
+        // hands the file to the GPU.
+        uint32_t header_size = 0, bundle_len = 0, space_len = 0, storage_len = 0;
+        uint16_t schema = 0, nonce = 0, gen_schema = 0, gen_reserved = 0;
+        uint8_t flags8 = 0, gen_nonce[16], fp[32];
+        uint64_t gen_seq = 0;
+        if (!rd(head, &cur, &header_size) || !rd(head, &cur, &schema) || !rd(head, &cur, &quant) || !rd(head, &cur, &flags8) ||
+            !rd(head, &cur, &nonce) || !rd(head, &cur, &dim) || !rd(head, &cur, &record_count) ||
+            !rd(head, &cur, &vectors_offset) || !rd(head, &cur, &gen_schema) || !rd(head, &cur, &gen_reserved) ||
+            !rd(head, &cur, &gen_seq) || !rd(head, &cur, &gen_nonce) || !rd(head, &cur, &bundle_len) ||
+            !rd(head, &cur, &space_len) || !rd(head, &cur, &storage_len))
+            return corrupt("truncated v2 header");
+        if (header_size < 336 || header_size > fsize) return corrupt("v2 header_size out of range");
+        if (schema != 1) return corrupt("unsupported v2 identity binding schema");
+        if (flags8 != 0) return corrupt("v2 header flags must be zero");
+        if (gen_reserved != 0) return corrupt("v2 generation reserved field must be zero");
+        for (uint32_t len : {bundle_len, space_len, storage_len})
+            if (len == 0 || len > (1u << 20)) return corrupt("v2 canonical identity length must be non-zero and at most 1 MiB");
+        for (int i = 0; i < 8; ++i) {
+            if (!rd(head, &cur, &fp)) return corrupt("truncated v2 fingerprints");
+            bool zero = true;
+            for (uint8_t b : fp) zero = zero && b == 0;
+            if (zero) return corrupt("v2 fingerprint must not be all zero");
+        }
+        if (cur != 332) return corrupt("v2 fixed header layout disagreement");
+        if ((uint64_t)332 + bundle_len + space_len + storage_len + 4 != header_size)
+            return corrupt("v2 canonical identity lengths do not end at the header CRC");
+        if (head.size() < header_size) {  // identity documents can push the header past the v1-sized first read
+            head.resize(header_size);
+            fseeko(f, 0, SEEK_SET);
+            if (fread(head.data(), 1, head.size(), f) != head.size()) return corrupt("short read (v2 header)");
+        }
+        memcpy(&crc_stored, head.data() + header_size - 4, 4);
+        if (crc32_ieee(head.data(), header_size - 4) != crc_stored) return corrupt("v2 header CRC mismatch");
+        records_offset = header_size;
+        memset(reserved, 0, sizeof reserved);
+    } else {
+        return corrupt("unsupported FSVI version (v1 and v2 are read)");
+    }
     if (quant > 1) return corrupt("unknown quantization");
     if (dim == 0) return corrupt("zero dimension");
-    const size_t records_offset = cur;
     const uint64_t elem = quant == 1 ? 2 : 4;
     if (vectors_offset % 64 != 0) return corrupt("vector slab is not 64-byte aligned");
     if (records_offset + record_count * 16 > vectors_offset ||

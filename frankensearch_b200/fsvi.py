@@ -79,7 +79,24 @@ def read_fsvi_header(path: str) -> dict:
         data = f.read(4 + 2 + 2 + 65535 + 2 + 65535 + 4 + 1 + 3 + 8 + 8 + 4)
     if len(data) < 8 or data[:4] != FSVI_MAGIC:
         raise SearchError("IndexCorrupted", f"{path}: bad magic")
-    version, n = struct.unpack_from("<HH", data, 4)
+    (version,) = struct.unpack_from("<H", data, 4)
+    if version == 2:  # identity-complete artifact (lib.rs:4229-4447): fixed 332-byte prefix, CRC at header_size - 4
+        header_size, schema, quant, flags, nonce, dim, count, voff = struct.unpack_from("<IHBBHIQQ", data, 6)
+        if header_size < 336:
+            raise SearchError("IndexCorrupted", f"{path}: v2 header_size out of range")
+        if len(data) < header_size:
+            with open(path, "rb") as f:
+                data = f.read(header_size)
+        if len(data) < header_size:
+            raise SearchError("IndexCorrupted", f"{path}: v2 header is truncated")
+        (crc,) = struct.unpack_from("<I", data, header_size - 4)
+        if zlib.crc32(data[:header_size - 4]) & 0xFFFFFFFF != crc:
+            raise SearchError("IndexCorrupted", f"{path}: v2 header CRC mismatch")
+        return dict(version=2, embedder_id="", embedder_revision="", dimension=dim, quantization=quant,
+                    compaction_gen=0, publication_nonce=nonce, record_count=count, vectors_offset=voff)
+    if version != FSVI_VERSION or len(data) < 8:
+        raise SearchError("IndexCorrupted", f"{path}: unsupported FSVI version {version}")
+    (n,) = struct.unpack_from("<H", data, 6)
     cur = 8
     embedder_id = data[cur:cur + n].decode("utf-8", "replace")
     cur += n

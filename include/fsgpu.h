@@ -109,12 +109,14 @@ int fsgpu_index_create_f16(const uint16_t* slab, uint64_t n_rows, uint32_t dim,
 int fsgpu_index_create_f32(const float* rows, uint64_t n_rows, uint32_t dim,
                            const uint8_t* tombstones, const fsgpu_index_options* opts,
                            fsgpu_index** out);
-/* Opens a reference-written FSVI v1 file (layout: crates/frankensearch-index/src/lib.rs:6-43;
+/* Opens a reference-written FSVI file (v1 layout: crates/frankensearch-index/src/lib.rs:6-43;
  * header CRC lib.rs:6114) and uploads rows [row_start, row_start+n) (n_rows_or_0 == 0: to the end),
  * streaming the slab through pinned memory.  f16 slabs (quantization 1) get every scan form; f32 slabs
  * (quantization 0) are scored exactly with the reference's f32 kernel (search.rs:1300-1321) through the
  * score-every-row + select path.  Tombstone flags and the doc-id string table are kept on the host
- * side of the handle (fsgpu_index_doc_id).  v2 identity headers are not read (IndexCorrupted). */
+ * side of the handle (fsgpu_index_doc_id).  FSVI v2 files (identity-complete artifacts,
+ * lib.rs:4229-4520) are read too: the header LAYOUT and CRC are checked, the identity documents are
+ * not interpreted — admitting an artifact's identity is the host's decision before it uploads it. */
 int fsgpu_index_open_fsvi(const char* path, uint64_t row_start, uint64_t n_rows_or_0,
                           const fsgpu_index_options* opts, fsgpu_index** out);
 void fsgpu_index_destroy(fsgpu_index* index);

@@ -231,3 +231,19 @@ def wal_full_recall_case():
 
 # avx2_f32slicedot_matches_generic (simd.rs:2512): xorshift seed and dims of the f32 x f32 dot
 DOT_F32_XORSHIFT = dict(seed=0x7C6D5E4F3A2B1908, dims=[1, 7, 8, 9, 16, 31, 32, 33, 64, 100, 256, 384, 512])
+
+
+# ── `wide::f32x8::reduce_add` probe (SURVEY.md section 7 "hard parts") ─────────────────
+# One 8-lane vector whose five candidate summation orders give five DIFFERENT f32 results.  A row of
+# eight f16 ones dotted with it is exactly reduce_add(probe) (products are exact, the four-accumulator
+# tree only adds zeros), so `dot_product_f16_f32(&[f16::ONE; 8], &REDUCE_PROBE).to_bits()` in the
+# reference build names the order `fsgpu_index_options.reduce_order` must be set to.
+REDUCE_PROBE = [-95027.75, -1704061.0, -10354.58203125, -14751.4765625, 35482.0, -4012.865234375, 2076639.5,
+                237570.6875]
+REDUCE_PROBE_BITS = {
+    0: 0x48FEA198,  # FSGPU_REDUCE_HALVES_PAIRWISE    ((v0+v1)+(v2+v3)) + ((v4+v5)+(v6+v7))   521484.75
+    1: 0x48FEA190,  # FSGPU_REDUCE_AVX_TREE           ((v0+v4)+(v2+v6)) + ((v1+v5)+(v3+v7))   521484.5
+    2: 0x48FEA194,  # FSGPU_REDUCE_HALVES_SEQUENTIAL  (((v0+v1)+v2)+v3) + (((v4+v5)+v6)+v7)   521484.625
+    3: 0x48FEA18C,  # FSGPU_REDUCE_HALVES_STRIDE2     ((v0+v2)+(v1+v3)) + ((v4+v6)+(v5+v7))   521484.375
+    4: 0x48FEA18E,  # FSGPU_REDUCE_SEQUENTIAL         ((((((v0+v1)+v2)+v3)+v4)+v5)+v6)+v7     521484.4375
+}

@@ -656,3 +656,100 @@ def test_classified_lane_replays_reference_cases(gpu, fo):
     assert tt.has_quality_index() and tt.doc_count() == 500
     fast.close()
     quality.close()
+
+
+def test_reduce_order_probe_on_the_device(gpu):
+    """The probe of INTEGRATION.md: a row of eight f16 ones against REDUCE_PROBE returns, for each
+    `reduce_order`, exactly the bits listed for that order (every kernel family that scores a row:
+    per-query scan, re-scoring)."""
+    import frankensearch_b200 as fs
+
+    q = np.array(rc.REDUCE_PROBE, dtype=np.float32)
+    for order, name in enumerate(("halves_pairwise", "avx_tree", "halves_sequential", "halves_stride2", "sequential")):
+        ix = fs.GpuVectorIndex.from_vectors(None, np.ones((3, 8), dtype=np.float32), reduce_order=name)
+        rows, scores, counts = ix.search_top_k_batch(q, 1)
+        assert int(scores[0, 0].view(np.uint32)) == rc.REDUCE_PROBE_BITS[order], name
+        s, _ = ix.scores_for_rows(q, np.array([2], dtype=np.uint32))
+        assert int(s[0].view(np.uint32)) == rc.REDUCE_PROBE_BITS[order], name
+        ix.close()
+
+
+def _hand_assembled_fsvi(version, dim, docs, quant=1, flags=None):
+    """An FSVI file assembled BYTE BY BYTE from the layout comment of the reference (lib.rs:6-43 for v1,
+    parse_v2_header lib.rs:4229-4447 for v2) — independently of frankensearch_b200/fsvi.py's writer — so
+    the device reader is pinned by a second, literal statement of the format."""
+    import struct
+    import zlib
+
+    from frankensearch_b200.types import fnv1a_hash
+
+    order = sorted(range(len(docs)), key=lambda i: (fnv1a_hash(docs[i][0].encode()), docs[i][0].encode()))
+    strings = b"".join(docs[i][0].encode() for i in order)
+    n = len(docs)
+    if version == 1:
+        eid, rev = b"hand-made", b"r1"
+        fixed = 4 + 2 + 2 + len(eid) + 2 + len(rev) + 4 + 1 + 3 + 8 + 8 + 4
+    else:
+        blobs = [b'{"bundle":1}', b'{"space":"x"}', b'{"storage":"f16"}']
+        fixed = 332 + sum(len(b) for b in blobs) + 4
+    voff = (fixed + 16 * n + len(strings) + 63) // 64 * 64
+    if version == 1:
+        head = (b"FSVI" + struct.pack("<H", 1) + struct.pack("<H", len(eid)) + eid + struct.pack("<H", len(rev)) + rev +
+                struct.pack("<I", dim) + bytes([quant]) + bytes(3) + struct.pack("<Q", n) + struct.pack("<Q", voff))
+    else:
+        head = b"FSVI" + struct.pack("<H", 2) + struct.pack("<I", fixed) + struct.pack("<H", 1) + bytes([quant, 0])
+        head += struct.pack("<H", 7) + struct.pack("<I", dim) + struct.pack("<Q", n) + struct.pack("<Q", voff)
+        head += struct.pack("<HHQ", 1, 0, 42) + bytes(range(1, 17))
+        head += struct.pack("<III", *(len(b) for b in blobs))
+        head += b"".join(bytes([i + 1]) * 32 for i in range(8))
+        assert len(head) == 332
+        head += b"".join(blobs)
+    head += struct.pack("<I", zlib.crc32(head) & 0xFFFFFFFF)
+    assert len(head) == fixed
+    records, off = b"", 0
+    for rank, i in enumerate(order):
+        b = docs[i][0].encode()
+        records += struct.pack("<QIHH", fnv1a_hash(b), off, len(b), (flags or [0] * n)[i])
+        off += len(b)
+    body = np.stack([np.asarray(docs[i][1], dtype=np.float32) for i in order])
+    slab = body.astype(np.float16).tobytes() if quant == 1 else body.tobytes()
+    pad = bytes(voff - fixed - len(records) - len(strings))
+    return head + records + strings + pad + slab, order
+
+
+@pytest.mark.parametrize("version", [1, 2])
+def test_reader_against_hand_assembled_fsvi_bytes(gpu, tmp_path, version):
+    """index/tests/fsvi_roundtrip.rs replayed against literal bytes: single f16 record round trip (:35),
+    multiple records found by doc id in hash order (:96), search_returns_closest_vector (:401),
+    search_respects_limit (:443), tombstone flag honoured, corrupted header (:543: byte 6 flipped) and
+    truncated file (:574: 8 bytes) detected — for the v1 layout and the v2 identity-header layout."""
+    import frankensearch_b200 as fs
+
+    def norm(v):
+        v = np.asarray(v, dtype=np.float32)
+        return v / np.float32(np.sqrt((v * v).sum()))
+
+    docs = [("north", norm([1, 0, 0, 0])), ("east", norm([0, 1, 0, 0])), ("northeast", norm([1, 1, 0, 0])),
+            ("gone", norm([0.9, 0.1, 0, 0]))]
+    data, order = _hand_assembled_fsvi(version, 4, docs, flags=[0, 0, 0, 1])
+    path = str(tmp_path / f"v{version}.fsvi")
+    open(path, "wb").write(data)
+    ix = fs.GpuVectorIndex.open(path)
+    assert ix.record_count() == 4 and ix.dimension() == 4
+    assert sorted(ix.doc_id_at(r) for r in range(4)) == sorted(d for d, _ in docs)
+    assert [ix.doc_id_at(r) for r in range(4)] == [docs[i][0] for i in order]
+    got = ix.read_rows_f16(0, 4).view(np.float16).astype(np.float32)
+    assert np.abs(got - np.stack([docs[i][1] for i in order])).max() < 0.01
+    assert ix.search_top_k(norm([0.9, 0.1, 0, 0]), 3)[0].doc_id == "north"  # "gone" is tombstoned
+    assert ix.search_top_k(norm([0.1, 0.9, 0, 0]), 3)[0].doc_id == "east"
+    assert len(ix.search_top_k([1.0, 0, 0, 0], 2)) == 2 and len(ix.search_top_k([1.0, 0, 0, 0], 100)) == 3
+    ix.close()
+    bad = bytearray(data)
+    bad[6] ^= 0xFF
+    open(path, "wb").write(bytes(bad))
+    with pytest.raises(fs.SearchError) as e:
+        fs.GpuVectorIndex.open(path)
+    assert e.value.kind == "IndexCorrupted"
+    open(path, "wb").write(data[:8])
+    with pytest.raises(fs.SearchError):
+        fs.GpuVectorIndex.open(path)

@@ -282,3 +282,17 @@ def test_wal_nonfinite_scores_are_skipped(fo):
     wal = np.array([[3.0e38, 3.0e38, 0.0, 0.0], [0.5, 0.0, 0.0, 0.0]], dtype=np.float32)
     rows, scores = fo.search_top_k_wal(slab, wal, np.array([2.0, 2.0, 0.0, 0.0], dtype=np.float32), 10)
     assert list(rows) == [0, 2] and np.isfinite(scores).all()
+
+
+def test_reduce_order_probe_separates_all_five_orders(fo):
+    """INTEGRATION.md "which reduce_add order does your build use": the probe vector gives five distinct
+    bit patterns, one per candidate order, in the C++ oracle and in the NumPy restatement."""
+    from oracle import np_oracle as no
+
+    ones = fo.encode_f16(np.ones(8, dtype=np.float32))
+    q = np.array(rc.REDUCE_PROBE, dtype=np.float32)
+    got = {o: int(np.float32(fo.dot_f16_f32(ones, q, o, True)).view(np.uint32)) for o in range(5)}
+    assert got == rc.REDUCE_PROBE_BITS
+    assert len(set(got.values())) == 5
+    for o in range(5):
+        assert int(np.float32(no.dot_f16_f32(ones, q, o)).view(np.uint32)) == rc.REDUCE_PROBE_BITS[o]
