@@ -753,3 +753,40 @@ def test_reader_against_hand_assembled_fsvi_bytes(gpu, tmp_path, version):
     open(path, "wb").write(data[:8])
     with pytest.raises(fs.SearchError):
         fs.GpuVectorIndex.open(path)
+
+
+@pytest.mark.parametrize("dim", [1, 255, 256, 257])
+def test_potion_reference_edge_inputs(gpu, fo, dim):
+    """The edge inputs of the reference's own potion tests (model2vec_embedder.rs:1255-1330): a token row
+    of signed zeros, rows below (1e-20) and above (1e-4) the normalisation guard, a NaN row, the guard
+    boundary [MIN_POSITIVE, +/-sqrt(EPSILON)], non-finite sums, token counts 1, 2, 3, 4, 511, 512, 513,
+    OOV ids dropped, the empty text — bit for bit against the oracle (NaN positions equal)."""
+    import frankensearch_b200 as fs
+
+    rng = np.random.default_rng(dim)
+    table = rng.standard_normal((12, dim)).astype(np.float32)
+    eps, tiny = np.float32(np.finfo(np.float32).eps), np.float32(np.finfo(np.float32).tiny)
+    table[1] = np.float32(-0.0)
+    table[2] = np.float32(1.0e-20)
+    table[3] = np.float32(1.0e-4)
+    table[4] = np.float32("nan")
+    table[5, : min(3, dim)] = [tiny, np.sqrt(eps), -np.sqrt(eps)][: min(3, dim)]
+    table[5, 3:] = 0
+    table[6, : min(4, dim)] = [np.float32("nan"), np.float32("inf"), np.float32("-inf"), np.finfo(np.float32).max][: min(4, dim)]
+    table[7] = np.finfo(np.float32).max  # sums overflow to +inf for counts > 1
+    for d in range(dim):  # arbitrary finite values with alternating sign and consecutive bit patterns
+        table[8, d] = np.uint32(0x3F800000 + (d % 256)).view(np.float32) * (1 if d % 2 == 0 else -1)
+    cases = [[], [0, 9999, 0]]
+    for count in (1, 2, 3, 4, 511, 512, 513):
+        cases.append([0] * count)
+        cases.append([8] * count)
+        cases.append([5] * count)
+    cases += [[1, 1], [2], [3], [0, 4, 0], [6], [6, 6, 0], [7], [7, 7], [1, 9, 1, 10], [11, 10, 9, 8, 3, 2]]
+    enc = fs.Model2VecEmbedder(table)
+    got = enc.embed_token_ids_batch(cases)
+    for i, ids in enumerate(cases):
+        want = fo.potion_embed(table, np.asarray(ids, dtype=np.uint32))
+        nan = np.isnan(want)
+        assert np.array_equal(np.isnan(got[i]), nan), (dim, ids[:4], len(ids))
+        assert np.array_equal(bits(got[i])[~nan], bits(want)[~nan]), (dim, ids[:4], len(ids))
+    enc.close()
