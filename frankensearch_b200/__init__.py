@@ -13,7 +13,7 @@ from .filter import BitsetFilter, PredicateFilter  # noqa: F401
 from .fusion import (RankChanges, blend_two_tier, blend_two_tier_aligned, compute_rank_changes,  # noqa: F401
                      kendall_tau, rrf_fuse)
 from .embed import MiniLmEmbedder, Model2VecEmbedder  # noqa: F401
-from .sharded import ShardedGpuIndex, shard_bounds  # noqa: F401
+from .sharded import GpuShardedIndex, ShardedGpuIndex, shard_bounds  # noqa: F401
 from .searcher import GpuSyncTwoTierSearcher, SyncSearchOutcome, TwoTierConfig  # noqa: F401
 from .two_tier import GpuTwoTierIndex  # noqa: F401
 from .pipeline import DeviceLexical, DeviceTwoTierSearcher  # noqa: F401

@@ -118,6 +118,8 @@ EXPORTS = [
     "fsgpu_rrf_fuse", "fsgpu_rrf_fuse_device", "fsgpu_blend_two_tier", "fsgpu_blend_two_tier_device", "fsgpu_potion_create",
     "fsgpu_potion_destroy", "fsgpu_potion_embed", "fsgpu_potion_embed_device",
     "fsgpu_synth_rows_device",
+    "fsgpu_sharded_create_f16", "fsgpu_sharded_from_shards", "fsgpu_sharded_destroy", "fsgpu_sharded_shard_count",
+    "fsgpu_sharded_rows", "fsgpu_sharded_shard", "fsgpu_sharded_is_direct", "fsgpu_sharded_search_top_k",
     "fsgpu_minilm_create", "fsgpu_minilm_destroy", "fsgpu_minilm_embed", "fsgpu_minilm_embed_device",
     "fsgpu_minilm_profile_enable", "fsgpu_minilm_profile_read",
 ]
@@ -203,6 +205,17 @@ def lib() -> C.CDLL:
     L.fsgpu_potion_embed_device.argtypes = [_vp, _vp, _vp, C.c_uint32, _vp, _vp]
     L.fsgpu_synth_rows_device.argtypes = [C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32,
                                           C.c_uint32, C.c_float, _vp, _vp]
+    L.fsgpu_sharded_create_f16.argtypes = [_vp, C.c_uint64, C.c_uint32, _vp, _vp, C.c_int, C.POINTER(IndexOptions), C.POINTER(_vp)]
+    L.fsgpu_sharded_from_shards.argtypes = [_vp, C.c_int, C.c_int, C.POINTER(_vp)]
+    L.fsgpu_sharded_destroy.argtypes = [_vp]
+    L.fsgpu_sharded_destroy.restype = None
+    L.fsgpu_sharded_shard_count.argtypes = [_vp]
+    L.fsgpu_sharded_rows.argtypes = [_vp]
+    L.fsgpu_sharded_rows.restype = C.c_uint64
+    L.fsgpu_sharded_shard.argtypes = [_vp, C.c_int]
+    L.fsgpu_sharded_shard.restype = _vp
+    L.fsgpu_sharded_is_direct.argtypes = [_vp, C.c_int]
+    L.fsgpu_sharded_search_top_k.argtypes = [_vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, _vp, _vp]
     L.fsgpu_minilm_create.argtypes = [C.POINTER(MiniLmWeights), C.c_int, C.POINTER(_vp)]
     L.fsgpu_minilm_destroy.argtypes = [_vp]
     L.fsgpu_minilm_destroy.restype = None

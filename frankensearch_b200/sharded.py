@@ -118,3 +118,78 @@ class ShardedGpuIndex:
         all_keys.copy_(gathered[:, :nk].contiguous().view(torch.int64).view(all_keys.shape))
         all_scores.copy_(gathered[:, nk:].contiguous().view(torch.float32).view(all_scores.shape))
         return self._merge(all_keys, all_scores, k)
+
+
+class GpuShardedIndex:
+    """Single-process form (no torch.distributed, no NCCL): one `fsgpu_sharded` handle over several GPUs
+    of the box — what a Rust host binds (`fsgpu_sharded_*`, include/fsgpu.h).  Shard i holds the contiguous
+    rows [i*N/G, (i+1)*N/G) on `devices[i]`; a search runs on every shard concurrently (one host thread
+    each) and, with peer access, the shards' kernels store their top-k straight into the merge device's
+    buffer over NVLink.  The result is byte-identical to one index over all rows."""
+
+    def __init__(self, handle, keepalive=None):
+        import ctypes as C
+
+        self._h = C.c_void_p(handle)
+        self._L = _ffi.lib()
+        self._keepalive = keepalive
+
+    @classmethod
+    def from_f16_bits(cls, slab_bits, devices, *, tombstones=None, reduce_order=0, tail_fma=True):
+        import ctypes as C
+
+        import numpy as np
+
+        s = np.ascontiguousarray(slab_bits, dtype=np.uint16)
+        o = _ffi.IndexOptions()
+        _ffi.lib().fsgpu_index_options_default(C.byref(o))
+        o.reduce_order, o.tail_fma = int(reduce_order), 1 if tail_fma else 0
+        dev = (C.c_int * len(devices))(*devices)
+        bm = None if tombstones is None else np.packbits(np.asarray(tombstones, dtype=bool), bitorder="little")
+        h = C.c_void_p()
+        check(_ffi.lib().fsgpu_sharded_create_f16(_ffi.ptr(s), s.shape[0], s.shape[1], _ffi.ptr(bm), dev, len(devices),
+                                                  C.byref(o), C.byref(h)))
+        return cls(h.value)
+
+    @classmethod
+    def from_indexes(cls, indexes):
+        """Adopt per-device GpuVectorIndex shards (contiguous row ranges, in order); they stay owned by the caller."""
+        import ctypes as C
+
+        arr = (C.c_void_p * len(indexes))(*[ix.handle for ix in indexes])
+        h = C.c_void_p()
+        check(_ffi.lib().fsgpu_sharded_from_shards(arr, len(indexes), 0, C.byref(h)))
+        return cls(h.value, keepalive=list(indexes))
+
+    def close(self):
+        if self._h:
+            self._L.fsgpu_sharded_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def shard_count(self) -> int:
+        return int(self._L.fsgpu_sharded_shard_count(self._h))
+
+    def record_count(self) -> int:
+        return int(self._L.fsgpu_sharded_rows(self._h))
+
+    def direct_shards(self):
+        return [bool(self._L.fsgpu_sharded_is_direct(self._h, i)) for i in range(self.shard_count())]
+
+    def search_top_k_batch(self, queries, limit: int):
+        import numpy as np
+
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        if q.ndim == 1:
+            q = q[None, :]
+        b, dim = q.shape
+        k = int(limit)
+        hits = np.zeros((b, max(k, 1)), dtype=np.dtype([("row", np.uint32), ("score", np.float32)]))
+        counts = np.zeros(b, dtype=np.uint32)
+        check(self._L.fsgpu_sharded_search_top_k(self._h, _ffi.ptr(q), b, k, dim, _ffi.ptr(hits), _ffi.ptr(counts)))
+        return hits["row"][:, :k].copy(), hits["score"][:, :k].copy(), counts

@@ -309,6 +309,31 @@ int fsgpu_merge_payload_device(int device, const uint64_t* d_keys, const float* 
                                const uint64_t* d_merged_keys, uint32_t k_out, float* d_out_payload,
                                uint8_t* d_out_present, void* stream);
 
+/* ---- row-sharded index over several GPUs, one process --------------------------------------- */
+/* contiguous row shards [i*N/G, (i+1)*N/G), one per device, the exact search on every
+ * shard and merge_partial_heaps (crates/frankensearch-index/src/search.rs:1704-1720) across them.
+ * Because the key order is a strict total order on (score_key, global row) (search.rs:1669-1686) the
+ * result is byte-identical to one index over all rows.  No NCCL, no second process: with peer access
+ * every shard's search kernels store their top-k straight into the merge device's buffer over NVLink
+ * (fsgpu_sharded_is_direct), otherwise one cudaMemcpyPeerAsync per shard carries it; each shard is
+ * driven by its own host thread.  `devices` may name a device more than once (several shards on one GPU).
+ * The two-tier pipeline and process-per-GPU deployments use the per-shard entry points above instead. */
+typedef struct fsgpu_sharded fsgpu_sharded;
+int fsgpu_sharded_create_f16(const uint16_t* slab, uint64_t n_rows, uint32_t dim, const uint8_t* tombstones,
+                             const int* devices, int n_devices, const fsgpu_index_options* opts,
+                             fsgpu_sharded** out);
+/* Adopts existing shard indexes (contiguous row ranges, in order; e.g. each built from a device-resident
+ * slab or opened from a row range of an FSVI file).  take_ownership != 0: destroy them with the handle. */
+int fsgpu_sharded_from_shards(fsgpu_index* const* shards, int n_shards, int take_ownership, fsgpu_sharded** out);
+void fsgpu_sharded_destroy(fsgpu_sharded* sharded);
+int fsgpu_sharded_shard_count(const fsgpu_sharded* sharded);
+uint64_t fsgpu_sharded_rows(const fsgpu_sharded* sharded);
+fsgpu_index* fsgpu_sharded_shard(const fsgpu_sharded* sharded, int i);
+int fsgpu_sharded_is_direct(const fsgpu_sharded* sharded, int i);
+/* VectorIndex::search_top_k over the whole corpus: host queries [batch, dim], host hits [batch, k]. */
+int fsgpu_sharded_search_top_k(fsgpu_sharded* sharded, const float* queries, uint32_t batch, uint32_t k,
+                               uint32_t dim, fsgpu_hit* out, uint32_t* out_counts);
+
 /* ---- fusion -------------------------------------------------------------------------------- */
 typedef struct fsgpu_rrf_config { /* RrfConfig, crates/frankensearch-fusion/src/rrf.rs:25-48 */
     double k;               /* non-finite or < 0 -> 60 (rrf.rs:124-130) */

@@ -160,3 +160,40 @@ def test_merge_payload_follows_the_keys(fo):
         assert np.array_equal(mk[b, :len(allk)], allk)
         assert np.array_equal(out_pl[b, :len(allk)].cpu().numpy(), (allk & np.uint64(0xFFFF)).astype(np.float32))
         assert out_pr[b, :len(allk)].cpu().numpy().all()
+
+
+@pytest.mark.parametrize("shards", [1, 3, 8])
+def test_single_process_sharded_index_equals_one_index(fo, shards):
+    """fsgpu_sharded_* (the multi-GPU path behind the C ABI, one process): per-shard exact search with the
+    results stored into the merge device's buffer, merge == merge_partial_heaps across shards
+    (search.rs:1704-1720).  Rows and score bits equal the oracle over the whole corpus, ties across a shard
+    boundary go to the lower global row, tombstones are re-packed per shard, k above the live row count
+    returns everything.  On a one-GPU box every shard lives on device 0; on a multi-GPU box they spread out."""
+    import torch
+
+    import frankensearch_b200 as fs
+
+    n, dim = 90_001, 128
+    slab, _ = fo.synth_rows(1, 91, 0, n, dim)
+    lo = n // shards if shards > 1 else 100
+    slab[lo] = slab[lo - 1]            # an exact tie across the first shard boundary
+    slab[n - 1] = slab[3]
+    tomb = np.arange(n) % 17 == 3
+    devices = [i % torch.cuda.device_count() for i in range(shards)]
+    sh = fs.GpuShardedIndex.from_f16_bits(slab, devices, tombstones=tomb)
+    assert sh.shard_count() == shards and sh.record_count() == n
+    queries = np.stack([fo.clustered_query(q, dim) for q in range(9)] + [slab[lo].view(np.float16).astype(np.float32)])
+    bm = fo.pack_bitmap(tomb)
+    for k in (1, 10, 300):
+        for batch in (1, 2, 10):
+            rows, scores, counts = sh.search_top_k_batch(queries[-batch:], k)
+            for b in range(batch):
+                o_rows, o_scores = fo.search_top_k(slab, queries[-batch:][b], k, bm)
+                c = int(counts[b])
+                assert c == len(o_rows) and rows[b, :c].tolist() == [int(r) for r in o_rows], (shards, k, batch, b)
+                assert np.array_equal(bits(scores[b, :c]), bits(o_scores)), (shards, k, batch, b)
+    small = fs.GpuShardedIndex.from_f16_bits(slab[:50], devices[: min(shards, 3)])
+    rows, scores, counts = small.search_top_k_batch(queries[:2], 200)
+    assert counts.tolist() == [50, 50]
+    small.close()
+    sh.close()
