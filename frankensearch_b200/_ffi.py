@@ -120,7 +120,7 @@ EXPORTS = [
     "fsgpu_synth_rows_device",
     "fsgpu_sharded_create_f16", "fsgpu_sharded_from_shards", "fsgpu_sharded_destroy", "fsgpu_sharded_shard_count",
     "fsgpu_sharded_rows", "fsgpu_sharded_shard", "fsgpu_sharded_is_direct", "fsgpu_sharded_search_top_k",
-    "fsgpu_minilm_create", "fsgpu_minilm_destroy", "fsgpu_minilm_embed", "fsgpu_minilm_embed_device",
+    "fsgpu_minilm_create", "fsgpu_minilm_load", "fsgpu_minilm_destroy", "fsgpu_minilm_embed", "fsgpu_minilm_embed_device",
     "fsgpu_minilm_profile_enable", "fsgpu_minilm_profile_read",
 ]
 
@@ -217,6 +217,7 @@ def lib() -> C.CDLL:
     L.fsgpu_sharded_is_direct.argtypes = [_vp, C.c_int]
     L.fsgpu_sharded_search_top_k.argtypes = [_vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, _vp, _vp]
     L.fsgpu_minilm_create.argtypes = [C.POINTER(MiniLmWeights), C.c_int, C.POINTER(_vp)]
+    L.fsgpu_minilm_load.argtypes = [C.c_char_p, C.c_int, C.POINTER(_vp)]
     L.fsgpu_minilm_destroy.argtypes = [_vp]
     L.fsgpu_minilm_destroy.restype = None
     L.fsgpu_minilm_embed.argtypes = [_vp, _vp, _vp, C.c_uint32, C.c_uint32, _vp]

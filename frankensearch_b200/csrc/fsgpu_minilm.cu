@@ -2,7 +2,9 @@
 // activation workspaces, the per-layer launch sequence).  No CPU compute path.
 #include <cmath>
 #include <cstring>
+#include <cstdio>
 #include <mutex>
+#include <string>
 #include <vector>
 
 #include "fsgpu.h"
@@ -356,4 +358,278 @@ extern "C" int fsgpu_minilm_profile_read(fsgpu_minilm* e, fsgpu_minilm_profile* 
     *out = e->prof;
     if (reset) e->prof = fsgpu_minilm_profile{};
     return FSGPU_OK;
+}
+
+// ─── safetensors loader (fsgpu_minilm_load) ───────────────────────────────────────
+// `model.safetensors` of sentence-transformers/all-MiniLM-L6-v2 (sha256 53aa5117...d9db, 90 868 376 B,
+// crates/frankensearch-embed/src/model_manifest.rs:343-349): an 8-byte little-endian header length, a
+// JSON object {tensor name: {"dtype", "shape", "data_offsets": [begin, end]}, "__metadata__": {...}},
+// then the tensor bytes.  Names are those of a Hugging Face BertModel, optionally prefixed with "bert."
+// or "0.auto_model."; F32, F16 and BF16 tensors are accepted (widened on the host).
+namespace {
+struct StTensor {
+    std::string dtype;
+    std::vector<uint64_t> shape;
+    uint64_t begin = 0, end = 0;
+};
+
+// A minimal parser for the flat two-level JSON of a safetensors header.
+struct StParser {
+    const char* p;
+    const char* end;
+    bool ok = true;
+    void ws() {
+        while (p < end && (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) ++p;
+    }
+    bool eat(char c) {
+        ws();
+        if (p < end && *p == c) {
+            ++p;
+            return true;
+        }
+        return false;
+    }
+    std::string str() {
+        ws();
+        std::string s;
+        if (p >= end || *p != '"') {
+            ok = false;
+            return s;
+        }
+        ++p;
+        while (p < end && *p != '"') {
+            if (*p == '\\' && p + 1 < end) ++p;  // escapes do not occur in tensor names; keep the next byte
+            s.push_back(*p++);
+        }
+        if (p >= end) ok = false;
+        ++p;
+        return s;
+    }
+    uint64_t num() {
+        ws();
+        uint64_t v = 0;
+        bool any = false;
+        while (p < end && *p >= '0' && *p <= '9') {
+            v = v * 10 + (uint64_t)(*p++ - '0');
+            any = true;
+        }
+        if (!any) ok = false;
+        return v;
+    }
+    void skip_value() {  // strings, numbers, nested objects / arrays (the __metadata__ entry)
+        ws();
+        if (p >= end) {
+            ok = false;
+            return;
+        }
+        if (*p == '"') {
+            str();
+        } else if (*p == '{' || *p == '[') {
+            const char open = *p, close = open == '{' ? '}' : ']';
+            int depth = 0;
+            bool in_str = false;
+            for (; p < end; ++p) {
+                if (in_str) {
+                    if (*p == '\\') ++p;
+                    else if (*p == '"') in_str = false;
+                } else if (*p == '"') in_str = true;
+                else if (*p == open) ++depth;
+                else if (*p == close && --depth == 0) {
+                    ++p;
+                    return;
+                }
+            }
+            ok = false;
+        } else {
+            while (p < end && *p != ',' && *p != '}' && *p != ']') ++p;
+        }
+    }
+};
+
+static bool st_parse_header(const char* json, size_t len, std::vector<std::pair<std::string, StTensor>>* out) {
+    StParser ps{json, json + len};
+    if (!ps.eat('{')) return false;
+    if (ps.eat('}')) return true;
+    do {
+        const std::string name = ps.str();
+        if (!ps.ok || !ps.eat(':')) return false;
+        if (name == "__metadata__") {
+            ps.skip_value();
+        } else {
+            StTensor t;
+            if (!ps.eat('{')) return false;
+            do {
+                const std::string key = ps.str();
+                if (!ps.ok || !ps.eat(':')) return false;
+                if (key == "dtype") {
+                    t.dtype = ps.str();
+                } else if (key == "shape") {
+                    if (!ps.eat('[')) return false;
+                    if (!ps.eat(']')) {
+                        do t.shape.push_back(ps.num()); while (ps.eat(','));
+                        if (!ps.eat(']')) return false;
+                    }
+                } else if (key == "data_offsets") {
+                    if (!ps.eat('[')) return false;
+                    t.begin = ps.num();
+                    if (!ps.eat(',')) return false;
+                    t.end = ps.num();
+                    if (!ps.eat(']')) return false;
+                } else {
+                    ps.skip_value();
+                }
+            } while (ps.ok && ps.eat(','));
+            if (!ps.ok || !ps.eat('}')) return false;
+            out->emplace_back(name, t);
+        }
+    } while (ps.ok && ps.eat(','));
+    return ps.ok && ps.eat('}');
+}
+
+static float st_widen16(uint16_t bits, bool bf16) {
+    uint32_t u;
+    if (bf16) {
+        u = (uint32_t)bits << 16;
+    } else {  // IEEE f16 -> f32
+        const uint32_t sign = (uint32_t)(bits & 0x8000u) << 16, exp = (bits >> 10) & 0x1Fu, man = bits & 0x3FFu;
+        if (exp == 0) {
+            if (man == 0) u = sign;
+            else {
+                int e = -1;
+                uint32_t m = man;
+                do { ++e; m <<= 1; } while (!(m & 0x400u));
+                u = sign | ((uint32_t)(127 - 15 - e) << 23) | ((m & 0x3FFu) << 13);
+            }
+        } else if (exp == 31) {
+            u = sign | 0x7F800000u | (man << 13);
+        } else {
+            u = sign | ((exp + 112u) << 23) | (man << 13);
+        }
+    }
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+}  // namespace
+
+extern "C" int fsgpu_minilm_load(const char* safetensors_path, int device, fsgpu_minilm** out) {
+    if (!out) return fail(FSGPU_ERR_INVALID_CONFIG, "out is NULL");
+    *out = nullptr;
+    if (!safetensors_path) return fail(FSGPU_ERR_INVALID_CONFIG, "path is NULL");
+    FILE* f = fopen(safetensors_path, "rb");
+    if (!f) return fail(FSGPU_ERR_IO, "cannot open %s", safetensors_path);
+    fseeko(f, 0, SEEK_END);
+    const uint64_t fsize = (uint64_t)ftello(f);
+    fseeko(f, 0, SEEK_SET);
+    uint64_t hlen = 0;
+    if (fsize < 8 || fread(&hlen, 1, 8, f) != 8 || hlen == 0 || hlen > fsize - 8 || hlen > (100u << 20)) {
+        fclose(f);
+        return fail(FSGPU_ERR_EMBEDDING_FAILED, "%s: not a safetensors file (bad header length)", safetensors_path);
+    }
+    std::vector<char> header(hlen);
+    std::vector<uint8_t> data(fsize - 8 - hlen);
+    const bool read_ok = fread(header.data(), 1, hlen, f) == hlen && (data.empty() || fread(data.data(), 1, data.size(), f) == data.size());
+    fclose(f);
+    if (!read_ok) return fail(FSGPU_ERR_IO, "%s: short read", safetensors_path);
+    std::vector<std::pair<std::string, StTensor>> tensors;
+    if (!st_parse_header(header.data(), hlen, &tensors))
+        return fail(FSGPU_ERR_EMBEDDING_FAILED, "%s: malformed safetensors header", safetensors_path);
+
+    std::vector<std::vector<float>> keep;  // widened / concatenated tensors the weight struct points into
+    std::string missing;
+    auto find = [&](const std::string& key, std::vector<uint64_t>* shape) -> const float* {
+        for (const char* prefix : {"", "bert.", "0.auto_model."}) {
+            const std::string full = std::string(prefix) + key;
+            for (auto& kv : tensors) {
+                if (kv.first != full) continue;
+                const StTensor& t = kv.second;
+                uint64_t count = 1;
+                for (uint64_t d : t.shape) count *= d;
+                const uint64_t esz = t.dtype == "F32" ? 4 : (t.dtype == "F16" || t.dtype == "BF16") ? 2 : 0;
+                if (!esz || t.end < t.begin || t.end > data.size() || t.end - t.begin != count * esz) {
+                    missing = full + " (unsupported dtype or bad offsets)";
+                    return nullptr;
+                }
+                if (shape) *shape = t.shape;
+                if (esz == 4 && (reinterpret_cast<uintptr_t>(data.data() + t.begin) & 3u) == 0)
+                    return reinterpret_cast<const float*>(data.data() + t.begin);
+                keep.emplace_back(count);
+                if (esz == 4) {
+                    memcpy(keep.back().data(), data.data() + t.begin, count * 4);
+                } else {
+                    const bool bf = t.dtype == "BF16";
+                    for (uint64_t i = 0; i < count; ++i) {
+                        uint16_t b;
+                        memcpy(&b, data.data() + t.begin + 2 * i, 2);
+                        keep.back()[i] = st_widen16(b, bf);
+                    }
+                }
+                return keep.back().data();
+            }
+        }
+        if (missing.empty()) missing = key;
+        return nullptr;
+    };
+    std::vector<uint64_t> shp;
+    fsgpu_minilm_weights w{};
+    w.word_emb = find("embeddings.word_embeddings.weight", &shp);
+    if (!w.word_emb || shp.size() != 2) return fail(FSGPU_ERR_EMBEDDING_FAILED, "%s: tensor %s is missing", safetensors_path, missing.c_str());
+    w.vocab_size = (uint32_t)shp[0];
+    w.hidden = (uint32_t)shp[1];
+    w.pos_emb = find("embeddings.position_embeddings.weight", &shp);
+    if (w.pos_emb && shp.size() == 2) w.max_positions = (uint32_t)shp[0];
+    w.type_emb = find("embeddings.token_type_embeddings.weight", nullptr);
+    w.emb_ln_g = find("embeddings.LayerNorm.weight", nullptr);
+    w.emb_ln_b = find("embeddings.LayerNorm.bias", nullptr);
+    uint32_t n_layers = 0;
+    for (;; ++n_layers) {
+        const std::string key = "encoder.layer." + std::to_string(n_layers) + ".attention.self.query.weight";
+        bool have = false;
+        for (auto& kv : tensors)
+            for (const char* prefix : {"", "bert.", "0.auto_model."}) have = have || kv.first == std::string(prefix) + key;
+        if (!have) break;
+    }
+    std::vector<fsgpu_minilm_layer_weights> layers(n_layers);
+    const uint64_t H = w.hidden;
+    for (uint32_t i = 0; i < n_layers && missing.empty(); ++i) {
+        const std::string p = "encoder.layer." + std::to_string(i) + ".";
+        fsgpu_minilm_layer_weights& L = layers[i];
+        const float* qkv_w[3];
+        const float* qkv_b[3];
+        const char* names[3] = {"query", "key", "value"};
+        for (int j = 0; j < 3; ++j) {
+            qkv_w[j] = find(p + "attention.self." + names[j] + ".weight", nullptr);
+            qkv_b[j] = find(p + "attention.self." + names[j] + ".bias", nullptr);
+        }
+        if (!missing.empty()) break;
+        keep.emplace_back(3 * H * H);  // query | key | value rows (fsgpu_minilm_layer_weights.qkv_w)
+        float* cw = keep.back().data();
+        keep.emplace_back(3 * H);
+        float* cb = keep.back().data();
+        for (int j = 0; j < 3; ++j) {
+            memcpy(cw + j * H * H, qkv_w[j], H * H * 4);
+            memcpy(cb + j * H, qkv_b[j], H * 4);
+        }
+        L.qkv_w = cw;
+        L.qkv_b = cb;
+        L.attn_out_w = find(p + "attention.output.dense.weight", nullptr);
+        L.attn_out_b = find(p + "attention.output.dense.bias", nullptr);
+        L.attn_ln_g = find(p + "attention.output.LayerNorm.weight", nullptr);
+        L.attn_ln_b = find(p + "attention.output.LayerNorm.bias", nullptr);
+        L.ffn_in_w = find(p + "intermediate.dense.weight", &shp);
+        if (L.ffn_in_w && shp.size() == 2) w.intermediate = (uint32_t)shp[0];
+        L.ffn_in_b = find(p + "intermediate.dense.bias", nullptr);
+        L.ffn_out_w = find(p + "output.dense.weight", nullptr);
+        L.ffn_out_b = find(p + "output.dense.bias", nullptr);
+        L.ffn_ln_g = find(p + "output.LayerNorm.weight", nullptr);
+        L.ffn_ln_b = find(p + "output.LayerNorm.bias", nullptr);
+    }
+    if (!missing.empty() || n_layers == 0)
+        return fail(FSGPU_ERR_EMBEDDING_FAILED, "%s: tensor %s is missing", safetensors_path,
+                    missing.empty() ? "encoder.layer.0.attention.self.query.weight" : missing.c_str());
+    w.n_layers = n_layers;
+    w.heads = kHeads;       // config.json num_attention_heads of all-MiniLM-L6-v2 (native.rs:36-45)
+    w.ln_eps = 1e-12f;      // layer_norm_eps
+    w.layers = layers.data();
+    return fsgpu_minilm_create(&w, device, out);
 }

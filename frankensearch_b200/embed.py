@@ -156,6 +156,34 @@ class MiniLmEmbedder:
         check(self._L.fsgpu_minilm_create(C.byref(w), device, C.byref(h)))
         self._h = h
 
+    @classmethod
+    def from_safetensors(cls, path: str, tokenizer: Optional[Callable[[str], Sequence[int]]] = None, *, device: int = 0,
+                         max_positions: int = 512, name: str = "all-MiniLM-L6-v2") -> "MiniLmEmbedder":
+        """Weights straight from `model.safetensors` through the C ABI (fsgpu_minilm_load): the file the
+        reference pins for all-MiniLM-L6-v2 (model_manifest.rs:343-349)."""
+        self = cls.__new__(cls)
+        self._L = _ffi.lib()
+        self._tokenizer = tokenizer
+        self._name = name
+        self._max_positions = int(max_positions)
+        h = C.c_void_p()
+        check(self._L.fsgpu_minilm_load(path.encode(), device, C.byref(h)))
+        self._h = h
+        return self
+
+    @classmethod
+    def from_model_dir(cls, model_dir: str, *, device: int = 0) -> "MiniLmEmbedder":
+        """A model directory as the reference downloads it (`model.safetensors` + `tokenizer.json`,
+        model_manifest.rs:327-349): weights through fsgpu_minilm_load, tokenisation by the Hugging Face
+        `tokenizers` library under the adapter's sequence policy (minilm_token_ids)."""
+        import os
+
+        from tokenizers import Tokenizer
+
+        tok = Tokenizer.from_file(os.path.join(model_dir, "tokenizer.json"))
+        return cls.from_safetensors(os.path.join(model_dir, "model.safetensors"),
+                                    tokenizer=lambda text: minilm_token_ids(tok, text), device=device)
+
     def close(self) -> None:
         if self._h:
             self._L.fsgpu_minilm_destroy(self._h)
@@ -225,3 +253,41 @@ class MiniLmEmbedder:
         check(self._L.fsgpu_minilm_profile_read(self._h, C.byref(p), 1 if reset else 0))
         return dict(gemm_launches=int(p.gemm_launches), other_launches=int(p.other_launches),
                     gemm_flops=float(p.gemm_flops), gemm_ms=float(p.gemm_ms))
+
+
+# ─── the host half of the MiniLM input contract ───────────────────────────────────────────────
+MINILM_MAX_LENGTH = 512  # FASTEMBED_MAX_LENGTH_V1 (crates/frankensearch-embed/src/model_manifest.rs:74)
+MINILM_CLS, MINILM_SEP = 101, 102  # [CLS] / [SEP] of the bert-base-uncased vocabulary the model ships
+
+
+def minilm_sequence(wordpiece_ids: Sequence[int], *, cls_id: int = MINILM_CLS, sep_id: int = MINILM_SEP,
+                    max_length: int = MINILM_MAX_LENGTH) -> List[int]:
+    """`bert-tokenizer-special-tokens=true` + `max-length=512;longest-first` (model_manifest.rs:74-80,
+    :300-304): `[CLS] w_1 .. w_n [SEP]`, truncated so that the whole sequence — specials included — fits
+    `max_length` (a single sequence loses its LAST word pieces, the specials stay)."""
+    room = max(max_length - 2, 0)
+    return [cls_id] + [int(t) for t in wordpiece_ids[:room]] + [sep_id]
+
+
+def minilm_token_ids(tokenizer, text: str) -> List[int]:
+    """Token ids of `text` for MiniLmEmbedder under the adapter's policy, from a Hugging Face
+    `tokenizers.Tokenizer` (the reference's tokenizer family: huggingface-tokenizers-json-v1).  The empty
+    string is answered before tokenisation (zero vector, fastembed_embedder.rs:432-434)."""
+    if text == "":
+        return []
+    enc = tokenizer.encode(text, add_special_tokens=False)
+    cls_id = tokenizer.token_to_id("[CLS]")
+    sep_id = tokenizer.token_to_id("[SEP]")
+    return minilm_sequence(enc.ids, cls_id=MINILM_CLS if cls_id is None else cls_id,
+                           sep_id=MINILM_SEP if sep_id is None else sep_id)
+
+
+def minilm_pad_batch(sequences: Sequence[Sequence[int]], pad_id: int = 0):
+    """`batch-longest-padding`: int32 ids [B, longest] padded with `pad_id`, int32 lens [B]; the attention
+    mask is `position < len` (fsgpu_minilm_embed ignores slots at or past len)."""
+    lens = np.array([len(s) for s in sequences], dtype=np.int32)
+    t = max(int(lens.max()) if len(sequences) else 0, 1)
+    ids = np.full((len(sequences), t), pad_id, dtype=np.int32)
+    for i, srow in enumerate(sequences):
+        ids[i, :len(srow)] = np.asarray(srow, dtype=np.int32)
+    return ids, lens

@@ -453,6 +453,12 @@ typedef struct fsgpu_minilm_profile {
     double gemm_ms;        /* event-timed GEMM durations (0 unless enabled) */
 } fsgpu_minilm_profile;
 int fsgpu_minilm_create(const fsgpu_minilm_weights* weights, int device, fsgpu_minilm** out);
+/* Same from a `model.safetensors` file (Hugging Face BertModel tensor names, optionally prefixed
+ * "bert." / "0.auto_model."; F32, F16 or BF16): the weights file of sentence-transformers/
+ * all-MiniLM-L6-v2 that the reference pins (crates/frankensearch-embed/src/model_manifest.rs:343-349).
+ * heads = 12 and layer_norm_eps = 1e-12 are the architecture's (crates/frankensearch-rerank/src/
+ * native.rs:36-45). */
+int fsgpu_minilm_load(const char* safetensors_path, int device, fsgpu_minilm** out);
 void fsgpu_minilm_destroy(fsgpu_minilm* enc);
 /* ids [batch, max_len] int32 (slots >= lens[b] ignored), lens [batch] (0 = empty text -> zero
  * vector, fastembed_embedder.rs:432-434); out [batch, hidden] f32, L2-normalised. */

@@ -137,3 +137,70 @@ def test_minilm_errors(fs, bert):
         fs.MiniLmEmbedder(bad)
     with pytest.raises(fs.SearchError):
         fs.MiniLmEmbedder(sd, heads=8)
+
+
+def test_minilm_loads_from_safetensors_file(fs, bert, tmp_path):
+    """fsgpu_minilm_load: a `model.safetensors` written by the safetensors library (F32, then F16 and a
+    "bert."-prefixed variant) gives bit-identical embeddings to the same weights passed as arrays."""
+    from safetensors.numpy import save_file
+
+    sd = mr.state_dict_numpy(bert)
+    sd = {k: v for k, v in sd.items() if "position_ids" not in k}
+    p32 = str(tmp_path / "model.safetensors")
+    save_file(sd, p32, metadata={"format": "pt"})
+    toks = [[101, 7, 8, 9, 102], [101, 44, 102], [], list(range(20, 60))]
+    base = fs.MiniLmEmbedder(sd)
+    want = base.embed_token_ids_batch(toks)
+    base.close()
+    enc = fs.MiniLmEmbedder.from_safetensors(p32)
+    assert np.array_equal(enc.embed_token_ids_batch(toks).view(np.uint32), want.view(np.uint32))
+    enc.close()
+    ppre = str(tmp_path / "prefixed.safetensors")
+    save_file({"bert." + k: v for k, v in sd.items()}, ppre)
+    enc = fs.MiniLmEmbedder.from_safetensors(ppre)
+    assert np.array_equal(enc.embed_token_ids_batch(toks).view(np.uint32), want.view(np.uint32))
+    enc.close()
+    p16 = str(tmp_path / "f16.safetensors")
+    save_file({k: v.astype(np.float16) for k, v in sd.items()}, p16)
+    enc = fs.MiniLmEmbedder.from_safetensors(p16)
+    half = fs.MiniLmEmbedder({k: v.astype(np.float16).astype(np.float32) for k, v in sd.items()})
+    assert np.array_equal(enc.embed_token_ids_batch(toks).view(np.uint32), half.embed_token_ids_batch(toks).view(np.uint32))
+    enc.close()
+    half.close()
+    with pytest.raises(fs.SearchError):
+        fs.MiniLmEmbedder.from_safetensors(str(tmp_path / "missing.safetensors"))
+    open(str(tmp_path / "junk.safetensors"), "wb").write((16).to_bytes(8, "little") + b'{"a":1}')
+    with pytest.raises(fs.SearchError):
+        fs.MiniLmEmbedder.from_safetensors(str(tmp_path / "junk.safetensors"))
+
+
+@pytest.mark.skipif(not os.environ.get("FSGPU_MINILM_MODEL_DIR"), reason="needs the real all-MiniLM-L6-v2 files "
+                    "(model.safetensors + tokenizer.json) via FSGPU_MINILM_MODEL_DIR — the counterpart of the reference's "
+                    "#[ignore] minilm_conformance_certificate_matches_fixture (fastembed_embedder.rs:904-912)")
+def test_minilm_real_weights_conformance_texts(fs):
+    """With the real model files: the four conformance texts of the reference (MODEL_CONFORMANCE_TEXTS_V1,
+    model_manifest.rs:65-70) through tokenizer.json + fsgpu_minilm_load against a PyTorch f32 BertModel with
+    the same weights (the reference pins these vectors only as a SHA-256 of ONNX Runtime's exact bits, which
+    no other implementation can reproduce)."""
+    import torch
+    from safetensors.torch import load_file
+    from transformers import BertConfig, BertModel
+
+    d = os.environ["FSGPU_MINILM_MODEL_DIR"]
+    texts = ["hello world", "semantic search finds related ideas", "identifier fsvi_v2", "naive cafe Tokyo"]
+    enc = fs.MiniLmEmbedder.from_model_dir(d)
+    got = np.stack(enc.embed_batch(texts))
+    enc.close()
+    cfg = BertConfig(vocab_size=30522, hidden_size=384, num_hidden_layers=6, num_attention_heads=12,
+                     intermediate_size=1536, max_position_embeddings=512, type_vocab_size=2, layer_norm_eps=1e-12)
+    model = BertModel(cfg, add_pooling_layer=False).eval()
+    sd = {k.removeprefix("bert."): v for k, v in load_file(os.path.join(d, "model.safetensors")).items()}
+    model.load_state_dict(sd, strict=False)
+    from tokenizers import Tokenizer
+
+    from frankensearch_b200.embed import minilm_token_ids
+
+    tok = Tokenizer.from_file(os.path.join(d, "tokenizer.json"))
+    want = mr.reference_embed(model, [minilm_token_ids(tok, t) for t in texts])
+    assert np.abs(got - want).max() < 2e-4
+    assert np.allclose(np.linalg.norm(got, axis=1), 1.0, atol=1e-5)

@@ -499,3 +499,25 @@ def test_zero_signal_state_classification_table():
     assert S(5, 0, 5, 2, 0).empty_result_reason(False) == R.WAL_ONLY_NO_LIVE_RECORDS
     assert S(5, 5, 0, 0, 5).empty_result_reason(False) == R.NO_USABLE_VECTORS
     assert S(5, 0, 5, 0, 0).empty_result_reason(True) == R.ALL_TOMBSTONED  # state reasons take precedence
+
+
+def test_minilm_host_sequence_policy():
+    """model_manifest.rs:74-80, :300-304: special tokens added, truncation to 512 INCLUDING them,
+    batch-longest padding, the empty text never reaches the tokenizer."""
+    from frankensearch_b200.embed import minilm_pad_batch, minilm_sequence, minilm_token_ids
+
+    assert minilm_sequence([7, 8, 9]) == [101, 7, 8, 9, 102]
+    assert minilm_sequence([]) == [101, 102]
+    long = list(range(1000, 1700))
+    s = minilm_sequence(long)
+    assert len(s) == 512 and s[0] == 101 and s[-1] == 102 and s[1:-1] == long[:510]
+    ids, lens = minilm_pad_batch([[101, 5, 102], [101, 102], []])
+    assert ids.tolist() == [[101, 5, 102], [101, 102, 0], [0, 0, 0]] and lens.tolist() == [3, 2, 0]
+
+    from tokenizers import Tokenizer, models, pre_tokenizers
+
+    vocab = {"[PAD]": 0, "[UNK]": 1, "[CLS]": 2, "[SEP]": 3, "hello": 4, "world": 5, "##s": 6}
+    tok = Tokenizer(models.WordPiece(vocab, unk_token="[UNK]"))
+    tok.pre_tokenizer = pre_tokenizers.Whitespace()
+    assert minilm_token_ids(tok, "hello worlds") == [2, 4, 5, 6, 3]  # this tokenizer's own [CLS]/[SEP] ids
+    assert minilm_token_ids(tok, "") == []
