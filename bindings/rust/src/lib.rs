@@ -1,4 +1,4 @@
-//! Raw `extern "C"` bindings of `include/fsgpu.h` (ABI version 1) — the B200 semantic-tier hot
+//! Raw `extern "C"` bindings of `include/fsgpu.h` (ABI version 3) — the B200 semantic-tier hot
 //! path behind frankensearch's own seams.  Each item names the reference interface it replaces;
 //! see INTEGRATION.md for the safe wrapper (`GpuVectorIndex`) and the error mapping.
 #![allow(non_camel_case_types)]
@@ -7,6 +7,12 @@ use std::os::raw::{c_char, c_int, c_void};
 #[repr(C)] pub struct fsgpu_index { _private: [u8; 0] }
 #[repr(C)] pub struct fsgpu_potion { _private: [u8; 0] }
 #[repr(C)] pub struct fsgpu_minilm { _private: [u8; 0] }
+#[repr(C)] pub struct fsgpu_sharded { _private: [u8; 0] }
+
+pub const FSGPU_ABI_VERSION: c_int = 3;
+/// `fsgpu_index_options.flags`: this host replays the `<index>.wal` sidecar itself (VectorIndex::open,
+/// lib.rs:1833-1878) and hands the rows to `fsgpu_index_set_wal`.
+pub const FSGPU_OPEN_HOST_REPLAYS_WAL: i32 = 1;
 
 pub const FSGPU_OK: c_int = 0;
 pub const FSGPU_ERR_DIMENSION_MISMATCH: c_int = 1; // SearchError::DimensionMismatch
@@ -29,7 +35,7 @@ pub struct fsgpu_index_options {
     pub slab_is_device: i32,
     pub row_base: u64,       // global row of local row 0 (row-sharded corpora)
     pub int8_codes: i32,     // 1 (default): also keep int8 codes for the int8 forms of the scan (same results)
-    pub reserved: i32,
+    pub flags: i32,          // FSGPU_OPEN_* bits
 }
 
 /// `RrfConfig` (crates/frankensearch-fusion/src/rrf.rs:25-48).
@@ -128,4 +134,46 @@ extern "C" {
     pub fn fsgpu_minilm_destroy(enc: *mut fsgpu_minilm);
     pub fn fsgpu_minilm_embed(enc: *const fsgpu_minilm, ids: *const i32, lens: *const i32, batch: u32,
                               max_len: u32, out: *mut f32) -> c_int;
+    // weights straight from model.safetensors (model_manifest.rs:343-349)
+    pub fn fsgpu_minilm_load(safetensors_path: *const c_char, device: c_int, out: *mut *mut fsgpu_minilm) -> c_int;
+
+    // VectorIndex::zero_signal_state (lib.rs:2441-2459): [records, live, tombstoned, wal, usable]
+    pub fn fsgpu_index_zero_signal_state(index: *const fsgpu_index, out_state: *mut u64) -> c_int;
+    // status words of the last (stream-asynchronous) search on an index
+    pub fn fsgpu_index_last_status(index: *const fsgpu_index, out_flags: *mut u32) -> c_int;
+
+    // the two-tier pipeline on the device (sync_searcher.rs:616-1009): re-score a shard's own candidates,
+    // pick the quality score that travelled through the cross-shard merge, blend, fuse
+    pub fn fsgpu_scores_for_hits_device(index: *const fsgpu_index, d_queries: *const f32, batch: u32,
+                                        d_hits: *const fsgpu_hit, n_per_query: u32, d_out_scores: *mut f32,
+                                        d_out_present: *mut u8, stream: *mut c_void) -> c_int;
+    pub fn fsgpu_merge_payload_device(device: c_int, d_keys: *const u64, d_payload: *const f32, batch: u32,
+                                      n_lists: u32, k_in: u32, list_stride: u64, query_stride: u64,
+                                      payload_list_stride: u64, payload_query_stride: u64,
+                                      d_merged_keys: *const u64, k_out: u32, d_out_payload: *mut f32,
+                                      d_out_present: *mut u8, stream: *mut c_void) -> c_int;
+    pub fn fsgpu_blend_two_tier_device(device: c_int, blend_factor: f32, batch: u32, d_fast_hits: *const fsgpu_hit,
+                                       d_fast_tie: *const u32, d_fast_counts: *const u32, n_fast_max: u32,
+                                       d_quality_hits: *const fsgpu_hit, d_quality_scores: *const f32,
+                                       d_quality_present: *const u8, d_quality_tie: *const u32,
+                                       d_quality_counts: *const u32, n_quality_max: u32, d_out: *mut fsgpu_hit,
+                                       d_out_counts: *mut u32, stream: *mut c_void) -> c_int;
+    pub fn fsgpu_rrf_fuse_device(device: c_int, config: *const fsgpu_rrf_config, batch: u32, d_lex_ids: *const u64,
+                                 d_lex_scores: *const f32, d_lex_tie: *const u32, d_lex_counts: *const u32,
+                                 n_lex_max: u32, d_sem_hits: *const fsgpu_hit, d_sem_tie: *const u32,
+                                 d_sem_counts: *const u32, n_sem_max: u32, limit: u32, offset: u32,
+                                 d_out: *mut fsgpu_fused_hit, d_out_counts: *mut u32, stream: *mut c_void) -> c_int;
+
+    // row-sharded index over the GPUs of one box, one process, no NCCL
+    pub fn fsgpu_sharded_create_f16(slab: *const u16, n_rows: u64, dim: u32, tombstones: *const u8,
+                                    devices: *const c_int, n_devices: c_int, opts: *const fsgpu_index_options,
+                                    out: *mut *mut fsgpu_sharded) -> c_int;
+    pub fn fsgpu_sharded_from_shards(shards: *const *mut fsgpu_index, n_shards: c_int, take_ownership: c_int,
+                                     out: *mut *mut fsgpu_sharded) -> c_int;
+    pub fn fsgpu_sharded_destroy(sharded: *mut fsgpu_sharded);
+    pub fn fsgpu_sharded_shard_count(sharded: *const fsgpu_sharded) -> c_int;
+    pub fn fsgpu_sharded_rows(sharded: *const fsgpu_sharded) -> u64;
+    pub fn fsgpu_sharded_shard(sharded: *const fsgpu_sharded, i: c_int) -> *mut fsgpu_index;
+    pub fn fsgpu_sharded_search_top_k(sharded: *mut fsgpu_sharded, queries: *const f32, batch: u32, k: u32, dim: u32,
+                                      out: *mut fsgpu_hit, out_counts: *mut u32) -> c_int;
 }

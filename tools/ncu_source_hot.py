@@ -1,5 +1,5 @@
 """Hot source lines of one kernel from an ncu report (needs -lineinfo and --import-source on):
-  python tools/ncu_source_hot.py gpurun_out/x.ncu-rep regex:kernel_name [top_n]
+  python tools/ncu_source_hot.py gpurun_out/x.ncu-rep regex:kernel_name [top_n] [launch_skip]
 Aggregates warp-stall samples per CUDA source line (file:line) and prints the dominant stall reason."""
 import csv
 import io
@@ -11,8 +11,9 @@ from collections import defaultdict
 def main():
     rep, kern = sys.argv[1], sys.argv[2]
     top = int(sys.argv[3]) if len(sys.argv) > 3 else 30
+    skip = sys.argv[4] if len(sys.argv) > 4 else "0"
     raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "--kernel-name",
-                          kern, "--launch-count", "1"], capture_output=True, text=True).stdout
+                          kern, "--launch-skip", skip, "--launch-count", "1"], capture_output=True, text=True).stdout
     cur_file = None
     hdr = None
     agg = defaultdict(lambda: [0, defaultdict(int), ""])
