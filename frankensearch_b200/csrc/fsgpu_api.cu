@@ -619,11 +619,11 @@ struct MmaCascade {
     bool group_max = false;  // level 0 keeps the best score of every 8-row group of a sample 8x as large
     double slack = 6.0, random_part = 0.0;  // expected gate-clearing rows per query and level
     // capacity of one (CTA, query) list when `g` CTAs (or CTA pairs) share a query block
-    // (each CTA keeps two lists per query, one per half of the tile's columns)
-    uint32_t list_cap(uint32_t g) const {
+    // (each CTA keeps `parts` lists per query, one per epilogue warp of a lane quarter: equal shares of a tile's columns)
+    uint32_t list_cap(uint32_t g, uint32_t parts) const {
         // level 0 keeps every score of its tiles (or one score per 8 rows: group_max)
-        const uint64_t dump = (t0 + g - 1) / g * (tile_rows / (group_max ? 16 : 2));
-        const uint64_t rnd = (uint64_t)std::min(slack * random_part / (2.0 * g), 4194304.0) + 64;
+        const uint64_t dump = (t0 + g - 1) / g * (tile_rows / (group_max ? 8 * parts : parts));
+        const uint64_t rnd = (uint64_t)std::min(slack * random_part / ((double)parts * g), 4194304.0) + 64;
         return (uint32_t)((std::max(dump, rnd) + 63) / 64 * 64);
     }
 };
@@ -723,7 +723,11 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
     // ... and unless the batch is a single 128-query block: that regime is HBM-bound and the
     // single-CTA form streams it faster (6.7 vs 5.8 TB/s at 10 M x 384, profiles/r01_sweep_mma_v6.txt)
     const bool pair = env_int("FSGPU_MMA_PAIR", 1) != 0 && ix->num_sms >= 2 && batch > kMmaM;
-    auto scan_kernel = quad ? mma_scan_quad_kernel
+    // quad form: 16 epilogue warps (FSGPU_MMA_QUAD_WARPS=8: the first form, two per TMEM lane quarter)
+    const uint32_t quad_warps = quad && env_int("FSGPU_MMA_QUAD_WARPS", 16) >= 16 ? 16u : 8u;
+    const uint32_t parts = quad ? quad_warps / 4 : 2;  // private candidate lists per (CTA, query)
+    const uint32_t scan_threads = quad ? 64 + 32 * quad_warps : kMmaThreads;
+    auto scan_kernel = quad ? (quad_warps == 16 ? mma_scan_quad_kernel<16> : mma_scan_quad_kernel<8>)
                      : pair ? (i8 ? mma_scan_pair_kernel<true> : mma_scan_pair_kernel<false>)
                             : (i8 ? mma_scan_kernel<true> : mma_scan_kernel<false>);
     CUDA_TRY(cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -765,8 +769,8 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
         CUDA_TRY(ix->ws_margin.reserve((size_t)slots * 4));
         CUDA_TRY(ix->ws_gate.reserve((size_t)slots * 4));
         CUDA_TRY(ix->ws_redo.reserve((size_t)slots * 4));
-        const uint32_t cap = cas.list_cap(g);
-        const size_t lists_per_cta = quad ? 4 : 2;  // (sub-block x) column half
+        const uint32_t cap = cas.list_cap(g, parts);
+        const size_t lists_per_cta = quad ? 2 * parts : 2;  // (sub-block x) column part
         CUDA_TRY(ix->ws_cand.reserve((size_t)grid * lists_per_cta * kMmaM * cap * sizeof(MmaCand)));
         CUDA_TRY(ix->ws_cand_count.reserve((size_t)grid * lists_per_cta * kMmaM * 4));
         if (i8) {
@@ -826,7 +830,7 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
         uint32_t* i8_cnt = reinterpret_cast<uint32_t*>(static_cast<char*>(ix->ws_progress.p) + 3 * progress_bytes);
         a.lead = lead;
         MmaGateArgs ga{};
-        ga.lists = MmaLists{a.cand, a.cand_count, n_qb, g, cap, quad ? 2u : pair ? 1u : 0u};
+        ga.lists = MmaLists{a.cand, a.cand_count, n_qb, g, cap, quad ? 2u : pair ? 1u : 0u, parts};
         ga.margin2 = ix->ws_margin.as<float>();
         ga.redo = a.redo;
         ga.gate = ix->ws_gate.as<float>();
@@ -843,7 +847,7 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
             a.gate = have_gate ? ix->ws_gate.as<float>() : nullptr;
             a.progress = paced ? progress_of(lvl) : nullptr;
             trace.mark(lvl ? "gate0" : "prep");
-            scan_kernel<<<grid, kMmaThreads, smem, stream>>>(i8 ? ix->tm_qhat_i8 : ix->tm_qhat, i8 ? ix->tm_slab_i8 : ix->tm_slab, a);
+            scan_kernel<<<grid, scan_threads, smem, stream>>>(i8 ? ix->tm_qhat_i8 : ix->tm_qhat, i8 ? ix->tm_slab_i8 : ix->tm_slab, a);
             CUDA_TRY(cudaGetLastError());
             trace.mark(lvl ? "scan1" : "scan0");
             ga.stage_cap = have_gate ? gate1_cap : gate0_cap;
@@ -892,6 +896,13 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
         a.dump_group_max = 0;
         a.tile_stride = 1;
         a.tile_count = cas.n_tiles;
+        a.dbg = (uint32_t)env_int("FSGPU_MMA_DBG", 0);  // timing experiments on the full pass (wrong results)
+        long long* d_ts = nullptr;
+        if (trace.on && quad && env_int("FSGPU_MMA_TS", 0) != 0) {  // debugging aid: pipeline timestamps of CTA 0
+            CUDA_TRY(cudaMalloc(&d_ts, (8 + 64 * 2 * 72) * sizeof(long long)));
+            CUDA_TRY(cudaMemsetAsync(d_ts, 0, (8 + 64 * 2 * 72) * sizeof(long long), stream));
+            a.ts = d_ts;
+        }
         a.gate = have_gate ? ix->ws_gate.as<float>() : nullptr;
         a.progress = paced ? progress_of(2) : nullptr;
         std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
@@ -906,7 +917,7 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
             CUDA_TRY(cudaEventRecord(ev.first, stream));
         }
         trace.mark("gate_last");
-        scan_kernel<<<grid, kMmaThreads, smem, stream>>>(i8 ? ix->tm_qhat_i8 : ix->tm_qhat, i8 ? ix->tm_slab_i8 : ix->tm_slab, a);
+        scan_kernel<<<grid, scan_threads, smem, stream>>>(i8 ? ix->tm_qhat_i8 : ix->tm_qhat, i8 ? ix->tm_slab_i8 : ix->tm_slab, a);
         CUDA_TRY(cudaGetLastError());
         trace.mark("scan_full");
         if (ix->profiling) {
@@ -958,6 +969,22 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
         if (trace.on) {
             CUDA_TRY(cudaStreamSynchronize(stream));
             trace.report(sub, ix->n_rows);
+            if (d_ts) {
+                std::vector<long long> ts(8 + 64 * 2 * 72);
+                CUDA_TRY(cudaMemcpy(ts.data(), d_ts, ts.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+                cudaFree(d_ts);
+                const long long t0 = ts[8], off1 = ts[1] - ts[0];  // CTA 1's clock minus CTA 0's at the cluster barrier
+                fprintf(stderr, "[fsgpu ts] unit: issuer(wait_tempty got issued) | per epilogue warp (CTA 0's, then CTA 1's): tfull_seen hotbits released done  [CTA 0 SM clocks since the first stamp]\n");
+                for (int u = 0; u < 128; ++u) {
+                    fprintf(stderr, "[fsgpu ts] %3d.%d:", u / 2, u % 2);
+                    for (int k = 0; k < 68; ++k) {
+                        if (k == 3) continue;
+                        const long long v = ts[8 + u * 72 + k];
+                        fprintf(stderr, "%s%7lld", (k >= 4 && k % 4 == 0) ? " |" : "", v ? v - t0 - (k >= 36 ? off1 : 0) : -1);
+                    }
+                    fprintf(stderr, "\n");
+                }
+            }
         }
     }
     return FSGPU_OK;

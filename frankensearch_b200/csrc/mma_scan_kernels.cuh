@@ -73,6 +73,9 @@ struct MmaScanArgs {
     MmaCand* cand;             // [gridDim.x][2][128][cap]: one private list per epilogue thread
     uint32_t* cand_count;      // [gridDim.x][2][128] appended entries (may exceed cap = overflow)
     uint32_t cap;
+    long long* ts;             // FSGPU_MMA_TS: clock64 stamps of CTA 0's issuer / epilogue warps, tiles 64..127 of its stream
+    uint32_t dbg;              // timing experiments only (FSGPU_MMA_DBG; results are wrong): 1 = epilogue skips its
+                               // work, 2 = hot bits are computed but nothing is appended (quad kernel)
 };
 
 // ─── prep: q -> q_hat (f16), error bound, safety flags ──────────────────────────────────────
@@ -289,10 +292,12 @@ __device__ __forceinline__ uint64_t mma_tile_of(const MmaScanArgs& args, uint64_
     return i * args.tile_stride + jitter;
 }
 
-// Appends the rows of one 8-column group that clear the gate to this thread's private list: plain
-// predicated stores, no atomics, no returned value to wait for and (in the common case: no
-// tombstones, tile inside the corpus) no branches — the branchy per-row form cost ~135 cycles of
-// warp time per appended row, which is what the sample levels and large-k passes are made of.
+// Appends the rows of one 8-column group that clear the gate to this thread's private list (plain
+// stores, no atomics, no returned value to wait for).  The common case (no tombstones, group inside the
+// corpus) is STRAIGHT-LINE code: eight predicated 8-byte stores written in PTX, because from the C++
+// form `if (p && c < cap) list[c] = e;` the compiler builds eight divergent branch regions
+// (BSSY / BRA / BSYNC per column, ~190 instructions per group: 19 % of the int8 full pass went there,
+// FSGPU_MMA_DBG=2).  The capacity test is made once per group (8 free slots, else the per-row form).
 // The count keeps growing past `cap` so the consumer sees overflow.
 // Value domain of the accumulators: f32 (kind::f16) or s32 (kind::i8; score = acc * qscale, the
 // gate is compared in the integer domain).
@@ -311,6 +316,22 @@ struct MmaDom<true> {
     }
 };
 
+// one column: `if (hit) { list[c] = {score, row}; ++c; }` with a predicated store
+__device__ __forceinline__ void mma_store_if(MmaCand* list, uint32_t& c, bool hit, float score, uint32_t row) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 a;\n"
+        "setp.ne.u32 p, %2, 0;\n"
+        "mad.wide.u32 a, %0, 8, %1;\n"
+        "@p st.global.v2.b32 [a], {%3, %4};\n"
+        "@p add.u32 %0, %0, 1;\n"
+        "}\n"
+        : "+r"(c)
+        : "l"(list), "r"((uint32_t)hit), "r"(__float_as_uint(score)), "r"(row)
+        : "memory");
+}
+
 template <bool I8>
 __device__ __forceinline__ void mma_append8(const MmaScanArgs& args, MmaCand* list, uint32_t& count,
                                             const uint32_t (&w)[8], typename MmaDom<I8>::Gate gate, float qscale,
@@ -319,20 +340,24 @@ __device__ __forceinline__ void mma_append8(const MmaScanArgs& args, MmaCand* li
     const bool interior = row0 + 8u <= args.n_rows && args.tombstones == nullptr;
     const uint32_t grow0 = (uint32_t)(args.row_base + row0);
     uint32_t c = count;
-    if (interior) {
+    if (interior && c + 8u <= args.cap) {
+        // a hot group nearly always holds exactly one row above the gate: pick it with selects and store once
+        uint32_t m = 0u, one = w[0];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const bool p = D::val(w[i]) >= gate;
-            if (p && c < args.cap) {
-                MmaCand e;
-                e.score = D::score(w[i], qscale);
-                e.row = grow0 + (uint32_t)i;
-                list[c] = e;
-            }
-            c += p ? 1u : 0u;
+            m |= p ? (1u << i) : 0u;
+            one = p ? w[i] : one;
         }
-    } else {
+        if ((m & (m - 1u)) == 0u) {
+            mma_store_if(list, c, m != 0u, D::score(one, qscale), grow0 + (uint32_t)__ffs(m) - 1u);
+        } else {
 #pragma unroll
+            for (int i = 0; i < 8; ++i)
+                mma_store_if(list, c, ((m >> i) & 1u) != 0u, D::score(w[i], qscale), grow0 + (uint32_t)i);
+        }
+    } else {  // tombstones, the corpus' last rows, or a list about to overflow: per-row tests
+#pragma unroll  // (static indices: a rolled loop would move w[] to local memory for every caller)
         for (int i = 0; i < 8; ++i) {
             const uint64_t row = row0 + (uint32_t)i;
             if (D::val(w[i]) >= gate && row < args.n_rows && !tombstoned(args.tombstones, row)) {
@@ -405,6 +430,10 @@ __device__ __forceinline__ void mma_epilogue_tile(const MmaScanArgs& args, uint3
     }
     uint32_t hot_warp = __reduce_or_sync(0xffffffffu, hot);
     if (hot_warp == 0u) return;
+    if (args.dbg & 2u) {
+        count += __popc(hot);
+        return;
+    }
     // two groups in flight: the TMEM read of the next hot group overlaps the appends of this one
     auto check8 = [&](const uint32_t (&w)[8], uint32_t grp) {
         if (hot & (1u << grp)) mma_append8<I8>(args, list, count, w, gate, qscale, tile_row0 + grp * 8u);
@@ -851,13 +880,22 @@ mma_scan_pair_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 // per CTA, int8 so they fit: 2 x 48 KB at D = 384) and one accumulator per block; block 0's MMAs
 // over a tile are followed by block 1's over the same stages, and each block's epilogue overlaps the
 // other block's MMAs.  Half the L2->SM bytes per MMA.
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMmaThreads, 1)
+// kEpiWarps = 16 (default; 8 = the first form): four epilogue warps per TMEM lane quarter, each takes a
+// quarter (64) of an accumulator's columns.  A sub-block's epilogue must fit inside the other sub-block's
+// 1536-cycle MMA group, and with two warps per scheduler it did not: ~330 cycles of TMEM reads
+// (~100 B/clk per scheduler, tools/ubench_tmem.cu) that nothing overlapped, ~440 of gate tests on the
+// half-rate integer pipe and ~350 of appends (half of all warp tiles hold a candidate) — tensor pipe 72-80 %
+// active, epilogue warps busy 60-80 % of the time at an IPC of 0.15 (profiles/r02_mma_quad_i8_b1024_ncu.json).
+template <uint32_t kEpiWarps>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * kEpiWarps, 1)
 mma_scan_quad_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_x,
                      const MmaScanArgs args) {
     extern __shared__ uint8_t smem_dyn[];
-    constexpr bool I8 = true;
     constexpr uint32_t kElems = 128u;  // int8 codes per 128-byte K-block row
     constexpr uint32_t kSub = 2;       // query blocks per CTA
+    constexpr uint32_t kParts = kEpiWarps / 4;      // column parts of an accumulator (one epilogue warp each per lane quarter)
+    constexpr uint32_t kCols = kPairN / kParts;     // columns per epilogue warp and accumulator
+    static_assert(kEpiWarps == 8 || kEpiWarps == 16, "two or four epilogue warps per TMEM lane quarter");
     const uint32_t raw = smem_u32(smem_dyn);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* base_ptr = smem_dyn + (base - raw);
@@ -891,7 +929,7 @@ mma_scan_quad_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         }
         for (uint32_t a = 0; a < kSub; ++a) {  // one accumulator per sub-block
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), 2 * kMmaEpiWarps);  // one arrival per epilogue warp of BOTH CTAs
+            mbar_init(tempty_bar(a), 2 * kEpiWarps);  // one arrival per epilogue warp of BOTH CTAs
         }
         mbar_init(afull_bar, 1);
         fence_barrier_init();
@@ -902,8 +940,12 @@ mma_scan_quad_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     cluster_sync_all();  // barrier inits and TMEM allocations of both CTAs are visible
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (args.ts && blockIdx.x < 2 && threadIdx.x == 0) args.ts[blockIdx.x] = clock64();  // clock offset between the two SMs
 
-    if (warp == 0) {
+    // Roles by warp id: the scheduler of an SM sub-partition prefers its eligible warp with the HIGHEST id, so the
+    // two latency-critical single-warp roles take the top ids (as warps 0 and 1 they lost every issue slot the
+    // epilogue warps of their sub-partitions wanted).
+    if (warp == kEpiWarps) {
         // ===== TMA producer (both CTAs; completion bytes land on the leader's barriers) =====
         if (elect_one()) {
             if (rank == 0) mbar_expect_tx(afull_bar, 2u * kSub * args.n_kblocks * kMmaTileBytes);
@@ -946,45 +988,58 @@ mma_scan_quad_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             if (prog && rank == 0 && lane == 0 && (li & 3u) == 3u) prog[quad] = li + 1u;
         }
         if (prog && rank == 0 && lane == 0) prog[quad] = 0xFFFFFFF0u;  // done: never the slowest
-    } else if (warp == 1) {
+    } else if (warp == kEpiWarps + 1) {
         if (rank == 0) {
             // ===== MMA issuer (leader CTA only) =====
-            constexpr uint32_t idesc = I8 ? umma_idesc_i8(2 * kMmaM, kPairN) : umma_idesc_f16(2 * kMmaM, kPairN);
+            constexpr uint32_t idesc = umma_idesc_i8(2 * kMmaM, kPairN);
             const uint64_t a_desc0 = umma_desc_sw128(a_smem);
             const uint64_t b_desc0 = umma_desc_sw128(b_smem);
             mbar_wait(afull_bar, 0);
             tc_fence_after();
             uint32_t stage = 0, phase = 0, acc_phase = 0;
+            const uint32_t n_kb = args.n_kblocks, n_st = args.n_stages;
             for (uint64_t i = j0; i < args.tile_count; i += g) {
                 // sub-block 0 then sub-block 1 over the SAME B stages: the epilogue of one sub-block's
-                // accumulator overlaps the MMAs of the other (one accumulator each, 2 x 256 columns)
-                const uint32_t stage0 = stage, phase0 = phase;
-                for (uint32_t sub = 0; sub < kSub; ++sub) {
-                    mbar_wait(tempty_bar(sub), acc_phase ^ 1u);
-                    tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + sub * kPairN;
-                    stage = stage0;
-                    phase = phase0;
-                    for (uint32_t kb = 0; kb < args.n_kblocks; ++kb) {
-                        if (sub == 0) {
-                            mbar_wait(full_bar(stage), phase);
-                            tc_fence_after();
-                        }
-                        if (elect_one()) {
-                            const uint64_t a_desc = a_desc0 + (uint64_t)((sub * args.n_kblocks + kb) * (kMmaTileBytes >> 4));
-                            const uint64_t b_desc = b_desc0 + (uint64_t)(stage * (kMmaTileBytes >> 4));
-#pragma unroll
-                            for (uint32_t k4 = 0; k4 < 4; ++k4)
-                                umma_i8_pair(d_tmem, a_desc + 2u * k4, b_desc + 2u * k4, idesc, (kb | k4) != 0u ? 1u : 0u);
-                            if (sub + 1 == kSub) umma_commit_pair(empty_bar(stage));  // both sub-blocks have read it
-                            if (kb + 1 == args.n_kblocks) umma_commit_pair(tfull_bar(sub));
-                        }
-                        __syncwarp();
-                        if (++stage == args.n_stages) {
-                            stage = 0;
-                            phase ^= 1u;
-                        }
+                // accumulator overlaps the MMAs of the other (one accumulator each, 2 x 256 columns).
+                // ONE elected block per MMA group (all of a group's K-blocks, <= 16 MMAs, and its commits): with an
+                // elect + reconvergence + eight vector->uniform register moves per K-block the issuer needed
+                // 700-1200 cycles per group (timestamps, FSGPU_MMA_TS), and a group whose last four MMAs (512
+                // cycles) are issued that late cannot finish inside its 1536-cycle slot.
+                const uint32_t stage0 = stage;
+                for (uint32_t kb = 0; kb < n_kb; ++kb) {  // the tile's stages have landed (they are requested together)
+                    mbar_wait(full_bar(stage), phase);
+                    if (++stage == n_st) {
+                        stage = 0;
+                        phase ^= 1u;
                     }
+                }
+#pragma unroll
+                for (uint32_t sub = 0; sub < kSub; ++sub) {
+                    const uint64_t tsi = (i - j0) / g - 64u;
+                    long long* ts = (args.ts && blockIdx.x == 0 && tsi < 64u && lane == 0) ? args.ts + 8 + (tsi * 2u + sub) * 72u : nullptr;
+                    if (ts) ts[0] = clock64();
+                    mbar_wait(tempty_bar(sub), acc_phase ^ 1u);
+                    if (ts) ts[1] = clock64();
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t d_tmem = tmem_base + sub * kPairN;
+                        const uint64_t a_desc = a_desc0 + (uint64_t)(sub * n_kb * (kMmaTileBytes >> 4));
+#pragma unroll
+                        for (uint32_t kb = 0; kb < kMmaMaxDim / 128u; ++kb) {
+                            if (kb < n_kb) {
+                                const uint32_t st = stage0 + kb >= n_st ? stage0 + kb - n_st : stage0 + kb;
+                                const uint64_t b_desc = b_desc0 + (uint64_t)(st * (kMmaTileBytes >> 4));
+#pragma unroll
+                                for (uint32_t k4 = 0; k4 < 4; ++k4)
+                                    umma_i8_pair(d_tmem, a_desc + (uint64_t)(kb * (kMmaTileBytes >> 4) + 2u * k4), b_desc + 2u * k4,
+                                                 idesc, (kb | k4) != 0u ? 1u : 0u);
+                                if (sub + 1 == kSub) umma_commit_pair(empty_bar(st));  // both sub-blocks have read it
+                            }
+                        }
+                        umma_commit_pair(tfull_bar(sub));
+                    }
+                    __syncwarp();
+                    if (ts) ts[2] = clock64();
                 }
                 acc_phase ^= 1u;
             }
@@ -993,7 +1048,7 @@ mma_scan_quad_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         // ===== epilogue (both CTAs): TMEM lane = query of this CTA, column = row of the pair tile =====
         const uint32_t quarter = warp & 3u;
         const uint32_t m = quarter * 32u + lane;
-        const uint32_t half = (warp - 2u) >> 2;
+        const uint32_t part = warp >> 2;  // columns [part * kCols, +kCols) of the pair tile = its rows
         bool live[kSub];
         float qscale[kSub];
         int32_t gate[kSub];
@@ -1005,7 +1060,7 @@ mma_scan_quad_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             const uint32_t query = qb_of(sub) * kMmaM + m;
             live[sub] = query < args.batch && args.redo[query] == 0u;
             gate[sub] = mma_thread_gate<true>(args, query, live[sub], &qscale[sub]);
-            list_id[sub] = (((size_t)blockIdx.x * kSub + sub) * 2u + half) * kMmaM + m;
+            list_id[sub] = (((size_t)blockIdx.x * kSub + sub) * kParts + part) * kMmaM + m;
             list[sub] = args.cand + list_id[sub] * args.cap;
             count[sub] = 0;
         }
@@ -1014,19 +1069,30 @@ mma_scan_quad_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             const uint64_t tile = mma_tile_of(args, i);
 #pragma unroll
             for (uint32_t sub = 0; sub < kSub; ++sub) {
+                const uint64_t tsi = (i - j0) / g - 64u;
+                long long* ts = (args.ts && blockIdx.x < 2 && tsi < 64u && lane == 0)
+                                    ? args.ts + 8 + (tsi * 2u + sub) * 72u + 4 + (blockIdx.x * 8 + warp) * 4 : nullptr;
                 mbar_wait(tfull_bar(sub), acc_phase);
+                if (ts) ts[0] = clock64();
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + sub * kPairN + half * (kPairN / 2);
-                if (args.dump_group_max) {
-                    mma_epilogue_dump_max<kPairN / 2, true>(args, taddr, tile * kPairN + half * (kPairN / 2), live[sub],
-                                                            qscale[sub], list[sub], count[sub]);
+                const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + sub * kPairN + part * kCols;
+                const uint64_t row0 = tile * kPairN + part * kCols;
+                auto release = [&]() {  // leader may reuse this accumulator
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(tempty_bar(sub), 0);
+                    if (ts) ts[2] = clock64();
+                };
+                if (args.dbg & 1u) {
+                    release();
+                } else if (args.dump_group_max) {
+                    mma_epilogue_dump_max<kCols, true>(args, taddr, row0, live[sub], qscale[sub], list[sub], count[sub]);
+                    release();
                 } else {
-                    mma_epilogue_tile<kPairN / 2, true>(args, taddr, tile * kPairN + half * (kPairN / 2), gate[sub],
-                                                        qscale[sub], list[sub], count[sub]);
+                    mma_epilogue_tile<kCols, true>(args, taddr, row0, gate[sub], qscale[sub], list[sub], count[sub]);
+                    release();
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(tempty_bar(sub), 0);  // leader may reuse this accumulator
+                if (ts) ts[3] = clock64();
             }
             acc_phase ^= 1u;
         }
@@ -1044,24 +1110,24 @@ mma_scan_quad_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 
 // ─── candidate lists as the gate / refine kernels see them ──────────────────────────────────
 struct MmaLists {
-    const MmaCand* cand;         // [grid][128][cap]
-    const uint32_t* cand_count;  // [grid][128]
+    const MmaCand* cand;         // [grid][lists per CTA][128][cap]
+    const uint32_t* cand_count;  // [grid][lists per CTA][128]
     uint32_t n_qblocks, ctas_per_qblock, cap;
     uint32_t pair;               // 1: lists were written by mma_scan_pair_kernel, 2: by mma_scan_quad_kernel
+    uint32_t parts;              // lists per (CTA, query): one per epilogue warp of a lane quarter (2, quad form: 2 or 4)
 };
-// Query slot b has 2*ctas_per_qblock lists (two epilogue threads per CTA).  List j lives in CTA
-// c(j/2), half j%2, where c(i) = qb + n_qblocks*i (single-CTA form) or
-// 2*(qb/2 + (n_qblocks/2)*i) + qb%2 (pair form).
-__device__ __forceinline__ uint32_t mma_list_count(const MmaLists& l) { return 2u * l.ctas_per_qblock; }
+// Query slot b has parts*ctas_per_qblock lists.  List j lives in CTA c(j/parts), part j%parts, where
+// c(i) = qb + n_qblocks*i (single-CTA form) or 2*(qb/2 + (n_qblocks/2)*i) + qb%2 (pair form).
+__device__ __forceinline__ uint32_t mma_list_count(const MmaLists& l) { return l.parts * l.ctas_per_qblock; }
 __device__ __forceinline__ size_t mma_list_slot(const MmaLists& l, uint32_t b, uint32_t j) {
-    const uint32_t qb = b / kMmaM, i = j >> 1;
-    if (l.pair == 2u) {  // quad form: blocks (quad*2 + sub)*2 + rank, lists [cta][sub][half][128]
+    const uint32_t qb = b / kMmaM, i = j / l.parts, part = j % l.parts;
+    if (l.pair == 2u) {  // quad form: blocks (quad*2 + sub)*2 + rank, lists [cta][sub][part][128]
         const size_t cta = 2 * ((size_t)(qb >> 2) + (size_t)(l.n_qblocks >> 2) * i) + (qb & 1u);
-        return ((cta * 2u + ((qb >> 1) & 1u)) * 2u + (j & 1u)) * kMmaM + (b % kMmaM);
+        return ((cta * 2u + ((qb >> 1) & 1u)) * l.parts + part) * kMmaM + (b % kMmaM);
     }
     const size_t cta = l.pair ? 2 * ((size_t)(qb >> 1) + (size_t)(l.n_qblocks >> 1) * i) + (qb & 1u)
                               : (size_t)qb + (size_t)l.n_qblocks * i;
-    return (cta * 2u + (j & 1u)) * kMmaM + (b % kMmaM);
+    return (cta * l.parts + part) * kMmaM + (b % kMmaM);
 }
 
 // ─── staging + radix select ─────────────────────────────────────────────────────────────────
@@ -1069,7 +1135,7 @@ __device__ __forceinline__ size_t mma_list_slot(const MmaLists& l, uint32_t b, u
 // another costs two dependent L2 round trips per list (36-296 lists): the first versions of the
 // gate/refine kernels spent 100-500 us there.  Instead every warp takes whole lists in parallel
 // and the entries are flattened into shared memory once.
-constexpr uint32_t kMmaMaxLists = 2 * 160;      // >= 2 * SM count
+constexpr uint32_t kMmaMaxLists = 2 * 160;      // >= 2 * SM count (quad form with 4 parts: 4 * 74 CTA pairs)
 constexpr uint32_t kMmaStageScores = 16384;     // gate kernel: ordered scores only (64 KiB)
 constexpr uint32_t kMmaStagePairs = 16384;      // refine kernel: ordered score + row (128 KiB); <= 64 * 256 (flag word)
 
