@@ -657,7 +657,7 @@ struct MmaTrace {
     }
 };
 
-static MmaCascade plan_cascade(uint64_t n_rows, uint32_t k, uint32_t tile_rows) {
+static MmaCascade plan_cascade(uint64_t n_rows, uint32_t k, uint32_t tile_rows, bool i8) {
     // Appends per query: level 0 keeps all t0*tile_rows sample scores (deterministic); level 1
     // expects k' * t1/t0 and level 2 k' * n_tiles/t1, both minimised by t1 = sqrt(t0 * n_tiles) at
     // L = k' * sqrt(n_tiles/t0).
@@ -675,6 +675,13 @@ static MmaCascade plan_cascade(uint64_t n_rows, uint32_t k, uint32_t tile_rows) 
     c.t0 = std::min<uint64_t>(c.n_tiles, std::max<uint64_t>({(uint64_t)2048 / tile_rows, t0_min, (uint64_t)std::ceil(t0_bal)}));
     if (c.n_tiles > 8 * c.t0) {
         c.t1 = (uint64_t)std::llround(std::sqrt((double)c.t0 * (double)c.n_tiles));
+        // int8 form: ~3x the rows clear a gate lowered by its wider bound, and every appended row costs the full pass's
+        // epilogue and both refine steps — a second sample up to twice as large pays from ~5 M rows on (10 M x 384,
+        // batch 1024: sample pass +70 us, exact-gate step -27, full pass -95, refine -70; neutral at 1.25 M rows;
+        // four times as large overflows the gate kernel's staging).  FSGPU_MMA_T1_PCT overrides (100 = the f16 rule).
+        int t1_pct = env_int("FSGPU_MMA_T1_PCT", 0);
+        if (t1_pct <= 0) t1_pct = i8 ? (int)(100.0 * std::min(2.0, std::max(1.0, std::cbrt((double)c.n_tiles / 4883.0)))) : 100;
+        c.t1 = c.t1 * (uint64_t)t1_pct / 100;
         c.t1 = std::min(c.n_tiles, std::max(c.t1, 2 * c.t0));
         // the first level only feeds a k'-th-best selection: with one score per 8-row group it samples
         // 8x as many tiles for the same number of appends, and its gate is ~8x tighter
@@ -733,7 +740,7 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
     CUDA_TRY(cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t units = pair ? (uint32_t)ix->num_sms / 2 : (uint32_t)ix->num_sms;  // CTAs or CTA pairs
     const uint32_t unit_queries = quad ? 4 * kMmaM : pair ? 2 * kMmaM : kMmaM;
-    MmaCascade cas = plan_cascade(ix->n_rows, k, pair ? kPairN : kMmaN);
+    MmaCascade cas = plan_cascade(ix->n_rows, k, pair ? kPairN : kMmaN, i8);
     // the int8 bound lowers every gate by ~0.25-0.5 sigma of the score distribution: ~4x the rows clear it
     if (i8) cas.random_part *= (double)std::max(1, env_int("FSGPU_I8_LIST_SCALE", 4));
     const uint32_t fin_cap = cand_capacity(k);
