@@ -397,6 +397,20 @@ bool make_f16_tile_map(CUtensorMap* tm, const void* base, uint64_t rows, uint32_
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+bool make_tile_map_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint32_t cols, uint32_t elem_bytes,
+                      uint32_t box_cols, uint32_t box_rows) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc || rows == 0 || (elem_bytes != 2 && elem_bytes != 4) || box_cols * elem_bytes != 128) return false;
+    const cuuint64_t gdim[2] = {cols, rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)cols * elem_bytes};
+    const cuuint32_t box[2] = {box_cols, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(tm, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+               const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // The same boxes over a row-major [rows, dim] matrix of 8-bit codes: 128 codes per 128-byte row.
 static bool make_u8_tile_map(CUtensorMap* tm, const void* base, uint64_t rows, uint32_t dim) {
     EncodeTiledFn enc = encode_tiled_fn();

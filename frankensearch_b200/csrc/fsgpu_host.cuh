@@ -110,3 +110,7 @@ inline uint32_t host_next_pow2(uint32_t x) {
 // the 128-byte swizzle the UMMA shared-memory descriptors expect (defined in fsgpu_api.cu).
 bool fsgpu_tma_available();
 bool make_f16_tile_map(CUtensorMap* tm, const void* base, uint64_t rows, uint32_t dim, uint32_t box_rows = 128);
+// The same for any 2- or 4-byte element type and box: row-major [rows, cols], box [box_cols x box_rows] with
+// box_cols * elem_bytes == 128 (the 128-byte swizzle).  Used for TMA stores of GEMM outputs.
+bool make_tile_map_2d(CUtensorMap* tm, const void* base, uint64_t rows, uint32_t cols, uint32_t elem_bytes,
+                      uint32_t box_cols, uint32_t box_rows);

@@ -10,7 +10,7 @@
 #include "fsgpu.h"
 #include "fsgpu_common.cuh"
 #include "fsgpu_host.cuh"
-#include "minilm_kernels.cuh"
+#include "minilm_fast_kernels.cuh"
 
 using namespace fsgpu;
 
@@ -43,6 +43,12 @@ struct fsgpu_minilm {
     mutable DevBuf ws_h32, ws_pre32, ws_qkv32, ws_ids, ws_lens, ws_out;
     mutable SplitMat act_h, act_ctx, act_ffn;
     mutable uint64_t act_rows = 0;
+    // f16 form (minilm_fast_kernels.cuh): one f16 copy of every activation + the descriptors of its GEMMs
+    mutable DevBuf f_h, f_qkv, f_ctx, f_ffn;
+    mutable CUtensorMap f_tm_h, f_tm_ctx, f_tm_ffn;             // A operands: [128 rows x 64] boxes
+    mutable CUtensorMap f_tm_qkv_out, f_tm_ffn_out, f_tm_pre;  // stores: f16 [64 x 32] boxes, f32 [32 x 32] boxes
+    mutable uint64_t f_rows = 0;
+    mutable float* f_pre_ptr = nullptr;
     mutable bool profiling = false;
     mutable fsgpu_minilm_profile prof{};
     mutable std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pending, ev_free;
@@ -244,6 +250,99 @@ static int minilm_gemm(const fsgpu_minilm* e, const SplitMat& a, const SplitMat&
     return FSGPU_OK;
 }
 
+// One linear of the f16 form: out = A W^T + bias (mode 0: f16, 1: f16 after erf-GELU, 2: f32).
+static int minilm_fast_gemm(const fsgpu_minilm* e, const CUtensorMap& tm_a, const SplitMat& w, const CUtensorMap& tm_out,
+                            uint32_t m, const float* bias, int mode, cudaStream_t stream) {
+    FastGemmArgs ga{};
+    ga.m = m;
+    ga.n = (uint32_t)w.rows;
+    ga.k = w.cols;
+    ga.bias = bias;
+    ga.mode = mode;
+    const uint32_t tiles = ((m + 127u) / 128u) * (ga.n / 128u);
+    const uint32_t grid = std::min<uint32_t>(tiles, (uint32_t)e->num_sms);
+    std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+    if (e->profiling) {
+        if (!e->ev_free.empty()) {
+            ev = e->ev_free.back();
+            e->ev_free.pop_back();
+        } else {
+            CUDA_TRY(cudaEventCreate(&ev.first));
+            CUDA_TRY(cudaEventCreate(&ev.second));
+        }
+        CUDA_TRY(cudaEventRecord(ev.first, stream));
+    }
+    gemm_f16_fast_kernel<<<grid, kFastThreads, fast_gemm_smem_bytes(), stream>>>(tm_a, w.tm_hi, tm_out, ga);
+    CUDA_TRY(cudaGetLastError());
+    if (e->profiling) {
+        CUDA_TRY(cudaEventRecord(ev.second, stream));
+        e->ev_pending.push_back(ev);
+    }
+    e->prof.gemm_launches += 1;
+    e->prof.gemm_flops += 2.0 * (double)m * ga.n * ga.k;
+    return FSGPU_OK;
+}
+
+// The f16 form of the forward (max_len <= 32).  Caller holds e->mu and has selected the device.
+static int minilm_embed_fast_locked(const fsgpu_minilm* e, const int32_t* d_ids, const int32_t* d_lens, uint32_t batch,
+                                    uint32_t max_len, float* d_out, cudaStream_t s, bool sync) {
+    const uint64_t rows = (uint64_t)batch * max_len;
+    const uint32_t m = (uint32_t)rows, H = kHidden, I = e->inter;
+    CUDA_TRY(e->ws_h32.reserve(rows * H * 4));
+    CUDA_TRY(e->ws_pre32.reserve(rows * H * 4));
+    void* before[4] = {e->f_h.p, e->f_qkv.p, e->f_ctx.p, e->f_ffn.p};
+    float* pre_before = e->ws_pre32.as<float>();
+    CUDA_TRY(e->f_h.reserve(rows * H * 2));
+    CUDA_TRY(e->f_qkv.reserve(rows * 3 * H * 2));
+    CUDA_TRY(e->f_ctx.reserve(rows * H * 2));
+    CUDA_TRY(e->f_ffn.reserve(rows * I * 2));
+    if (rows != e->f_rows || before[0] != e->f_h.p || before[1] != e->f_qkv.p || before[2] != e->f_ctx.p ||
+        before[3] != e->f_ffn.p || pre_before != e->f_pre_ptr) {  // descriptors carry base and row count
+        const bool ok = make_f16_tile_map(&e->f_tm_h, e->f_h.p, rows, H) && make_f16_tile_map(&e->f_tm_ctx, e->f_ctx.p, rows, H) &&
+                        make_f16_tile_map(&e->f_tm_ffn, e->f_ffn.p, rows, I) &&
+                        make_tile_map_2d(&e->f_tm_qkv_out, e->f_qkv.p, rows, 3 * H, 2, 64, 32) &&
+                        make_tile_map_2d(&e->f_tm_ffn_out, e->f_ffn.p, rows, I, 2, 64, 32) &&
+                        make_tile_map_2d(&e->f_tm_pre, e->ws_pre32.p, rows, H, 4, 32, 32);
+        if (!ok) return fail(FSGPU_ERR_SUBSYSTEM, "gpu: cuTensorMapEncodeTiled failed for a minilm activation");
+        e->f_rows = rows;
+        e->f_pre_ptr = e->ws_pre32.as<float>();
+    }
+    CUDA_TRY(cudaFuncSetAttribute(gemm_f16_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_gemm_smem_bytes()));
+    const unsigned row_blocks = (unsigned)((rows + 7) / 8);
+    __half* h16 = e->f_h.as<__half>();
+    __half* qkv16 = e->f_qkv.as<__half>();
+    __half* ctx16 = e->f_ctx.as<__half>();
+    float* pre32 = e->ws_pre32.as<float>();
+    float* h32 = e->ws_h32.as<float>();
+    minilm_fast_embed_kernel<<<row_blocks, 256, 0, s>>>(d_ids, batch, max_len, e->vocab, e->word, e->pos, e->type0, e->emb_g,
+                                                        e->emb_b, e->eps, h16);
+    CUDA_TRY(cudaGetLastError());
+    for (uint32_t li = 0; li < e->n_layers; ++li) {
+        const MiniLmLayer& L = e->layers[li];
+        const bool last = li + 1 == e->n_layers;
+        int rc = minilm_fast_gemm(e, e->f_tm_h, L.qkv, e->f_tm_qkv_out, m, L.qkv_b, 0, s);
+        if (rc) return rc;
+        minilm_fast_attention_kernel<<<(batch * kHeads + 3) / 4, 128, 0, s>>>(qkv16, d_lens, batch, max_len, ctx16);
+        CUDA_TRY(cudaGetLastError());
+        rc = minilm_fast_gemm(e, e->f_tm_ctx, L.attn_out, e->f_tm_pre, m, L.attn_out_b, 2, s);
+        if (rc) return rc;
+        minilm_fast_ln_kernel<<<row_blocks, 256, 0, s>>>(pre32, h16, rows, L.attn_ln_g, L.attn_ln_b, e->eps, nullptr);
+        CUDA_TRY(cudaGetLastError());
+        rc = minilm_fast_gemm(e, e->f_tm_h, L.ffn_in, e->f_tm_ffn_out, m, L.ffn_in_b, 1, s);
+        if (rc) return rc;
+        rc = minilm_fast_gemm(e, e->f_tm_ffn, L.ffn_out, e->f_tm_pre, m, L.ffn_out_b, 2, s);
+        if (rc) return rc;
+        minilm_fast_ln_kernel<<<row_blocks, 256, 0, s>>>(pre32, h16, rows, L.ffn_ln_g, L.ffn_ln_b, e->eps, last ? h32 : nullptr);
+        CUDA_TRY(cudaGetLastError());
+        e->prof.other_launches += 3;
+    }
+    minilm_pool_kernel<<<batch, 128, 0, s>>>(h32, d_lens, max_len, d_out);
+    CUDA_TRY(cudaGetLastError());
+    e->prof.other_launches += 2;
+    if (sync) CUDA_TRY(cudaStreamSynchronize(s));
+    return FSGPU_OK;
+}
+
 // Caller holds e->mu and has selected the device.
 static int minilm_embed_locked(const fsgpu_minilm* e, const int32_t* d_ids, const int32_t* d_lens, uint32_t batch,
                                uint32_t max_len, float* d_out, cudaStream_t s, bool sync) {
@@ -251,6 +350,11 @@ static int minilm_embed_locked(const fsgpu_minilm* e, const int32_t* d_ids, cons
         return fail(FSGPU_ERR_EMBEDDING_FAILED, "minilm: max_len %u outside 1..%u", max_len, e->max_pos);
     const uint64_t rows = (uint64_t)batch * max_len;
     if (rows > 0x7FFFFF00ull) return fail(FSGPU_ERR_INVALID_CONFIG, "minilm: batch * max_len too large");
+    // FSGPU_MINILM_PRODUCTS: 0 (default) = the f16 form for query lengths <= 32 (minilm_fast_kernels.cuh),
+    // 3 = split-f16 operands, three products (an f32 forward to ~2e-6), 1 = the split form's hi halves only
+    const int products_env = env_int("FSGPU_MINILM_PRODUCTS", 0);
+    if (products_env == 0 && max_len <= 32 && e->hidden == kHidden && e->inter % 128 == 0)
+        return minilm_embed_fast_locked(e, d_ids, d_lens, batch, max_len, d_out, s, sync);
     const uint32_t m = (uint32_t)rows, H = kHidden, I = e->inter;
     if (rows != e->act_rows) {  // descriptors carry the row count: (re)build on a shape change
         CUDA_TRY(cudaStreamSynchronize(s));
@@ -263,7 +367,7 @@ static int minilm_embed_locked(const fsgpu_minilm* e, const int32_t* d_ids, cons
     CUDA_TRY(e->ws_h32.reserve(rows * H * 4));
     CUDA_TRY(e->ws_pre32.reserve(rows * H * 4));
     CUDA_TRY(e->ws_qkv32.reserve(rows * 3 * H * 4));
-    const uint32_t products = env_int("FSGPU_MINILM_PRODUCTS", 3) == 1 ? 1 : 3;
+    const uint32_t products = products_env == 1 ? 1 : 3;
     const unsigned row_blocks = (unsigned)((rows + 7) / 8);
     float* h32 = e->ws_h32.as<float>();
     float* pre32 = e->ws_pre32.as<float>();

@@ -1,0 +1,420 @@
+// minilm_fast_kernels.cuh — the f16 form of the MiniLM-L6-v2 encoder (the default for query lengths <= 32).
+//
+// The split-f16 form (minilm_kernels.cuh) reproduces an f32 forward to ~2e-6, but it moves every activation
+// three times (f32 + hi + lo halves) and issues every product three times: at 1024 x 32 tokens the encoder
+// spent 3.5 ms, ~1.5 ms of it as plain HBM traffic (8.7 GB per batch), against 2.6 ms for the exact scan of
+// 10 M rows it feeds.  The contract is "within 1e-3 relative on cosine scores", which f16 OPERANDS with f32
+// accumulation meet with two orders of magnitude to spare (tests/test_gpu_minilm.py: cosine to the f32
+// reference >= 1 - 1e-6, score error <= 1e-4), so this form carries activations as ONE f16 copy:
+//
+//   h (f16) --QKV GEMM--> qkv (f16) --attention (mma.sync, one warp per (sequence, head))--> ctx (f16)
+//     --out-proj GEMM (+bias)--> pre (f32) --(+ residual h) LayerNorm--> h (f16)
+//     --FFN-in GEMM (+bias, erf-GELU)--> ffn (f16) --FFN-out GEMM (+bias)--> pre (f32) --(+h) LayerNorm--> h (f16)
+//
+// The two pre-LayerNorm sums stay f32 (LayerNorm subtracts a mean: its input is the one place where an f16
+// rounding would be amplified).  One GEMM kernel serves all four linears: persistent, warp-specialised
+// (TMA -> mbarrier ring -> tcgen05.mma kind::f16, M = 128 x N = 128, f32 accumulators double-buffered in
+// TMEM), epilogue warps read their TMEM rows, apply bias / GELU, write the 32 x 64 sub-tile into a swizzled
+// shared-memory box and hand it to a TMA STORE — full 128-byte row segments leave the SM without a transpose
+// (the row-per-thread global stores of the first epilogue were what bound those GEMMs).
+#pragma once
+
+#include <mma.h>
+
+#include "minilm_kernels.cuh"
+
+namespace fsgpu {
+
+constexpr int kFastThreads = 320;  // warps 0-7 epilogue (lane quarter = warp % 4, column half = warp / 4), 8 TMA, 9 MMA
+constexpr int kFastStages = 5;     // 5 x (A 16 KiB + W 16 KiB)
+constexpr int kFastAcc = 2;        // 2 x 128 TMEM columns
+
+struct FastGemmArgs {
+    uint32_t m, n, k;     // n % 128 == 0, k % 64 == 0
+    const float* bias;    // [n]
+    int mode;             // 0: f16 out = acc + bias   1: f16 out = gelu(acc + bias)   2: f32 out = acc + bias
+};
+
+__host__ __device__ inline size_t fast_gemm_smem_bytes() {
+    // ring | 8 warps x 8 KiB staging (f32 mode: two [32 x 32] boxes; f16 modes use the first 4 KiB) | barriers
+    return 1024 + (size_t)kFastStages * 2 * kMmaTileBytes + 8 * 8192 + 256;
+}
+
+// tm_out: f16 modes: [M, N] f16, box [64 cols x 32 rows]; f32 mode: [M, N] f32, box [32 cols x 32 rows]; both
+// 128-byte swizzled (row r of a box at r * 128 B, its 16-byte chunk c at position c ^ (r & 7)).
+__global__ void __launch_bounds__(kFastThreads, 1)
+gemm_f16_fast_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
+                     const __grid_constant__ CUtensorMap tm_out, const FastGemmArgs args) {
+    extern __shared__ uint8_t smem_dyn[];
+    const uint32_t raw = smem_u32(smem_dyn);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_dyn + (base - raw);
+    constexpr uint32_t per_stage = 2u * kMmaTileBytes;
+    const uint32_t stage_smem = base + kFastStages * per_stage;  // 8 x 8 KiB, 1024-byte aligned
+    uint8_t* stage_ptr = base_ptr + (size_t)kFastStages * per_stage;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stage_ptr + 8 * 8192);
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](uint32_t s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](uint32_t s) { return bar0 + 8u * (8u + s); };
+    auto tfull_bar = [&](uint32_t a) { return bar0 + 8u * (16u + a); };
+    auto tempty_bar = [&](uint32_t a) { return bar0 + 8u * (20u + a); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t tiles_m = (args.m + 127u) / 128u, tiles_n = args.n / 128u;
+    const uint32_t n_tiles = tiles_m * tiles_n, n_kb = args.k / kMmaKBlock;
+
+    if (warp == 8 && lane == 0) {
+        tma_prefetch_desc(&tm_a);
+        tma_prefetch_desc(&tm_w);
+        tma_prefetch_desc(&tm_out);
+        for (uint32_t s = 0; s < kFastStages; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (uint32_t a = 0; a < kFastAcc; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 8);
+        }
+        fence_barrier_init();
+    } else if (warp == 0) {
+        tmem_alloc(smem_u32(tmem_slot), kFastAcc * 128);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 8) {
+        // ===== TMA producer: tile t = (m tile t / tiles_n, n tile t % tiles_n): CTAs that run together share the A rows
+        uint32_t stage = 0, phase = 0;
+        for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const int32_t row_a = (int32_t)((t / tiles_n) * 128u), row_w = (int32_t)((t % tiles_n) * 128u);
+            for (uint32_t kb = 0; kb < n_kb; ++kb) {
+                mbar_wait(empty_bar(stage), phase ^ 1u);
+                if (elect_one()) {
+                    const uint32_t s0 = base + stage * per_stage;
+                    const int32_t kc = (int32_t)(kb * kMmaKBlock);
+                    mbar_expect_tx(full_bar(stage), per_stage);
+                    tma_load_2d(s0, &tm_a, full_bar(stage), kc, row_a);
+                    tma_load_2d(s0 + kMmaTileBytes, &tm_w, full_bar(stage), kc, row_w);
+                }
+                __syncwarp();
+                if (++stage == kFastStages) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+        }
+    } else if (warp == 9) {
+        // ===== MMA issuer =====
+        constexpr uint32_t idesc = umma_idesc_f16(128, 128);
+        uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+        for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * 128u;
+            for (uint32_t kb = 0; kb < n_kb; ++kb) {
+                mbar_wait(full_bar(stage), phase);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t s0 = base + stage * per_stage;
+                    const uint64_t a_desc = umma_desc_sw128(s0), w_desc = umma_desc_sw128(s0 + kMmaTileBytes);
+#pragma unroll
+                    for (uint32_t k4 = 0; k4 < kMmaKBlock / 16; ++k4)
+                        umma_f16(d_tmem, a_desc + 2u * k4, w_desc + 2u * k4, idesc, (kb | k4) != 0u ? 1u : 0u);
+                    umma_commit(empty_bar(stage));
+                    if (kb + 1 == n_kb) umma_commit(tfull_bar(acc));
+                }
+                __syncwarp();
+                if (++stage == kFastStages) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+            if (++acc == kFastAcc) {
+                acc = 0;
+                acc_phase ^= 1u;
+            }
+        }
+    } else {
+        // ===== epilogue: TMEM lane = output row, column = output feature; warp = 32 rows x 64 columns =====
+        const uint32_t quarter = warp & 3u, half = warp >> 2;
+        const uint32_t my_stage = stage_smem + warp * 8192u;
+        uint8_t* my_ptr = stage_ptr + (size_t)warp * 8192u;
+        const uint32_t sw = lane & 7u;  // this row's swizzle phase
+        uint32_t acc = 0, acc_phase = 0;
+        for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const uint32_t row0 = (t / tiles_n) * 128u + quarter * 32u;
+            const uint32_t col0 = (t % tiles_n) * 128u + half * 64u;
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * 128u + half * 64u;
+            uint32_t v[2][32];
+            tmem_ld_x32(taddr, v[0]);
+            tmem_ld_x32(taddr + 32u, v[1]);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));  // the accumulator is in registers: hand it back
+            if (++acc == kFastAcc) {
+                acc = 0;
+                acc_phase ^= 1u;
+            }
+            if (row0 >= args.m) continue;  // (whole warp: a tile past the last row stores nothing)
+            // the previous store of this warp must have finished reading the staging box
+            if (lane == 0) tma_store_wait_read();
+            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    float x[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        x[i] = __uint_as_float(v[c][j + i]) + __ldg(args.bias + col0 + c * 32 + j + i);
+                        if (args.mode == 1) x[i] = gelu_erf(x[i]);
+                    }
+                    if (args.mode == 2) {  // f32: box c = columns [32c, 32c+32): 8 chunks of 4 floats per row
+                        const uint32_t ch = (uint32_t)j / 4u;
+                        float4* d0 = reinterpret_cast<float4*>(my_ptr + c * 4096 + lane * 128u + ((ch ^ sw) << 4));
+                        float4* d1 = reinterpret_cast<float4*>(my_ptr + c * 4096 + lane * 128u + (((ch + 1u) ^ sw) << 4));
+                        *d0 = make_float4(x[0], x[1], x[2], x[3]);
+                        *d1 = make_float4(x[4], x[5], x[6], x[7]);
+                    } else {  // f16: one box of 64 columns: 8 chunks of 8 halves per row
+                        const uint32_t ch = (uint32_t)(c * 32 + j) / 8u;
+                        __half2 h[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+                        *reinterpret_cast<uint4*>(my_ptr + lane * 128u + ((ch ^ sw) << 4)) = *reinterpret_cast<uint4*>(h);
+                    }
+                }
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                if (args.mode == 2) {
+                    tma_store_2d(&tm_out, my_stage, (int32_t)col0, (int32_t)row0);
+                    tma_store_2d(&tm_out, my_stage + 4096u, (int32_t)col0 + 32, (int32_t)row0);
+                } else {
+                    tma_store_2d(&tm_out, my_stage, (int32_t)col0, (int32_t)row0);
+                }
+                tma_store_commit();
+            }
+        }
+        if (lane == 0) tma_store_wait_all();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kFastAcc * 128);
+    }
+}
+
+// ─── h = LayerNorm(pre + residual): one warp per token row of H = 384 ───────────────────────
+// pre f32 (linear + bias), residual f16 (the layer input); h f16 in place of the residual, and an f32 copy on
+// request (the last layer: the pooling kernel reads f32).
+__global__ void __launch_bounds__(256)
+minilm_fast_ln_kernel(const float* __restrict__ pre, __half* __restrict__ h, size_t rows, const float* __restrict__ g,
+                      const float* __restrict__ b, float eps, float* __restrict__ out_f32) {
+    const uint32_t lane = threadIdx.x & 31;
+    const size_t row = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    float x[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        const size_t o = row * kHidden + lane + 32u * i;
+        x[i] = pre[o] + __half2float(h[o]);
+    }
+    layernorm_row(x, g, b, eps, lane);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        const size_t o = row * kHidden + lane + 32u * i;
+        h[o] = __float2half_rn(x[i]);
+        if (out_f32) out_f32[o] = x[i];
+    }
+}
+
+// embeddings -> LayerNorm -> h f16 (BertEmbeddings; the f32 sums are those of minilm_embed_kernel)
+__global__ void __launch_bounds__(256)
+minilm_fast_embed_kernel(const int32_t* __restrict__ ids, uint32_t batch, uint32_t t_pad, uint32_t vocab,
+                         const float* __restrict__ word, const float* __restrict__ pos, const float* __restrict__ type0,
+                         const float* __restrict__ g, const float* __restrict__ b, float eps, __half* __restrict__ h) {
+    const uint32_t lane = threadIdx.x & 31;
+    const size_t row = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= (size_t)batch * t_pad) return;
+    const uint32_t t = (uint32_t)(row % t_pad);
+    int32_t id = ids[row];
+    if (id < 0 || (uint32_t)id >= vocab) id = 0;
+    float x[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        const uint32_t d = lane + 32u * i;
+        x[i] = word[(size_t)id * kHidden + d] + pos[(size_t)t * kHidden + d] + type0[d];
+    }
+    layernorm_row(x, g, b, eps, lane);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) h[row * kHidden + lane + 32u * i] = __float2half_rn(x[i]);
+}
+
+// ─── attention for t_pad <= 32 on mma.sync: one warp per (sequence, head) ───────────────────
+// qkv [M, 1152] f16 = [q | k | v], head h at columns h * 32.  S = Q K^T / sqrt(32) (2 x 4 m16n8k16 tiles, K = 32),
+// keys >= len masked, soft-max in f32 on the accumulator fragments, O = P V with P re-used from the
+// accumulator registers as the A operand (f16), O / row sum -> ctx [M, 384] f16.  Tiles are staged in shared
+// memory with an 80-byte row pitch (conflict-free ldmatrix).
+constexpr int kAttPitch = 40;  // halves per staged row (32 + 8 padding)
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(addr));
+}
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(128)
+minilm_fast_attention_kernel(const __half* __restrict__ qkv, const int32_t* __restrict__ lens, uint32_t batch,
+                             uint32_t t_pad, __half* __restrict__ ctx) {
+    __shared__ __align__(16) __half tiles[4][3][32 * kAttPitch];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t item = blockIdx.x * 4u + warp;
+    if (item >= batch * kHeads) return;
+    const uint32_t b = item / kHeads, h = item % kHeads;
+    const uint32_t len = min((uint32_t)max(lens[b], 0), t_pad);
+    const size_t row0 = (size_t)b * t_pad;
+    __half* qs = tiles[warp][0];
+    __half* ks = tiles[warp][1];
+    __half* vs = tiles[warp][2];
+    // stage: 3 matrices x 32 rows x 4 chunks of 16 bytes; rows >= t_pad are zero
+#pragma unroll
+    for (int it = 0; it < 12; ++it) {
+        const uint32_t idx = (uint32_t)it * 32u + lane;  // 0 .. 383
+        const uint32_t mat = idx / 128u, r = (idx % 128u) / 4u, ch = idx % 4u;
+        uint4 val = make_uint4(0u, 0u, 0u, 0u);
+        if (r < t_pad)
+            val = *reinterpret_cast<const uint4*>(qkv + (row0 + r) * (3 * kHidden) + mat * kHidden + h * kHeadDim + ch * 8u);
+        *reinterpret_cast<uint4*>(tiles[warp][mat] + r * kAttPitch + ch * 8u) = val;
+    }
+    __syncwarp();
+    const uint32_t g = lane >> 2, tig = lane & 3u;
+    // S = Q K^T
+    float s[2][4][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) s[mt][nt][i] = 0.0f;
+    uint32_t kf[4][4];  // per key tile nt: b0/b1 of k-step 0, b0/b1 of k-step 1
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+        ldmatrix_x4(kf[nt], smem_u32(ks + (nt * 8 + (lane & 7u)) * kAttPitch + (lane >> 3) * 8u));
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+        for (int kstep = 0; kstep < 2; ++kstep) {
+            uint32_t a[4];
+            ldmatrix_x4(a, smem_u32(qs + (mt * 16 + (lane & 7u) + ((lane >> 3) & 1u) * 8u) * kAttPitch + kstep * 16 + (lane >> 4) * 8u));
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) mma_16816(s[mt][nt], a, kf[nt][2 * kstep], kf[nt][2 * kstep + 1]);
+        }
+    }
+    // soft-max over the keys (columns): thread holds rows g (c0, c1) and g + 8 (c2, c3) of each m tile
+    const float scale = 0.17677669529663687f;  // 1 / sqrt(32)
+    uint32_t p[2][2][4];                         // P as A fragments: [m tile][key step of 16][a0..a3]
+    float inv_sum[2][2];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {  // row g (hh = 0) or g + 8 (hh = 1)
+            float mx = -INFINITY;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const uint32_t key = (uint32_t)nt * 8u + 2u * tig + (uint32_t)i;
+                    float x = s[mt][nt][2 * hh + i] * scale;
+                    x = key < len ? x : -INFINITY;
+                    s[mt][nt][2 * hh + i] = x;
+                    mx = fmaxf(mx, x);
+                }
+            }
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+            float sum = 0.0f;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const float e = __expf(s[mt][nt][2 * hh + i] - mx);  // len >= 1: mx is finite
+                    s[mt][nt][2 * hh + i] = e;
+                    sum += e;
+                }
+            }
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            inv_sum[mt][hh] = 1.0f / sum;
+        }
+#pragma unroll
+        for (int kt = 0; kt < 2; ++kt) {
+            p[mt][kt][0] = pack_half2(s[mt][2 * kt][0], s[mt][2 * kt][1]);
+            p[mt][kt][1] = pack_half2(s[mt][2 * kt][2], s[mt][2 * kt][3]);
+            p[mt][kt][2] = pack_half2(s[mt][2 * kt + 1][0], s[mt][2 * kt + 1][1]);
+            p[mt][kt][3] = pack_half2(s[mt][2 * kt + 1][2], s[mt][2 * kt + 1][3]);
+        }
+    }
+    // O = P V
+    float o[2][4][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[mt][nt][i] = 0.0f;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {  // 8 output dims per tile
+        uint32_t vf[4];                // b0/b1 of key step 0, b0/b1 of key step 1 (transposed 8 x 8 blocks of V)
+        ldmatrix_x4_trans(vf, smem_u32(vs + lane * kAttPitch + nt * 8));
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            mma_16816(o[mt][nt], p[mt][0], vf[0], vf[1]);
+            mma_16816(o[mt][nt], p[mt][1], vf[2], vf[3]);
+        }
+    }
+    // O / sum -> staged rows (over the Q tile) -> 64-byte row segments of ctx
+    __syncwarp();
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            const uint32_t d = (uint32_t)nt * 8u + 2u * tig;
+            *reinterpret_cast<uint32_t*>(qs + (mt * 16 + g) * kAttPitch + d) =
+                pack_half2(o[mt][nt][0] * inv_sum[mt][0], o[mt][nt][1] * inv_sum[mt][0]);
+            *reinterpret_cast<uint32_t*>(qs + (mt * 16 + g + 8) * kAttPitch + d) =
+                pack_half2(o[mt][nt][2] * inv_sum[mt][1], o[mt][nt][3] * inv_sum[mt][1]);
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const uint32_t idx = (uint32_t)it * 32u + lane, r = idx / 4u, ch = idx % 4u;
+        if (r < t_pad)
+            *reinterpret_cast<uint4*>(ctx + (row0 + r) * kHidden + h * kHeadDim + ch * 8u) =
+                *reinterpret_cast<const uint4*>(qs + r * kAttPitch + ch * 8u);
+    }
+}
+
+}  // namespace fsgpu
