@@ -283,6 +283,44 @@ static int minilm_fast_gemm(const fsgpu_minilm* e, const CUtensorMap& tm_a, cons
     return FSGPU_OK;
 }
 
+// The same linear for K <= 384 on CTA pairs with the activation tile resident (gemm_f16_ares_pair_kernel).
+static int minilm_ares_gemm(const fsgpu_minilm* e, const CUtensorMap& tm_a, const SplitMat& w, const CUtensorMap& tm_out,
+                            uint32_t m, const float* bias, int mode, cudaStream_t stream) {
+    AresGemmArgs ga{};
+    ga.m = m;
+    ga.n = (uint32_t)w.rows;
+    ga.k = w.cols;
+    ga.bias = bias;
+    ga.mode = mode | (env_int("FSGPU_MINILM_DBG", 0) << 4);
+    const uint32_t n_kb = ga.k / kMmaKBlock;
+    if (ga.n > kAresMaxN || n_kb > kAresMaxKb) return fail(FSGPU_ERR_INVALID_CONFIG, "minilm: linear %u x %u outside the pair GEMM's range", ga.n, ga.k);
+    ga.n_stages = (uint32_t)std::min<size_t>(8, (227 * 1024 - ares_gemm_smem_bytes(n_kb, 0)) / kMmaTileBytes);
+    const size_t smem = ares_gemm_smem_bytes(n_kb, ga.n_stages);
+    CUDA_TRY(cudaFuncSetAttribute(gemm_f16_ares_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const uint32_t items = ((m + 255u) / 256u) * ((ga.n + 255u) / 256u);
+    const uint32_t grid = 2 * std::min<uint32_t>(items, (uint32_t)e->num_sms / 2);
+    std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+    if (e->profiling) {
+        if (!e->ev_free.empty()) {
+            ev = e->ev_free.back();
+            e->ev_free.pop_back();
+        } else {
+            CUDA_TRY(cudaEventCreate(&ev.first));
+            CUDA_TRY(cudaEventCreate(&ev.second));
+        }
+        CUDA_TRY(cudaEventRecord(ev.first, stream));
+    }
+    gemm_f16_ares_pair_kernel<<<grid, kAresThreads, smem, stream>>>(tm_a, w.tm_hi, w.tm64_hi, tm_out, ga);
+    CUDA_TRY(cudaGetLastError());
+    if (e->profiling) {
+        CUDA_TRY(cudaEventRecord(ev.second, stream));
+        e->ev_pending.push_back(ev);
+    }
+    e->prof.gemm_launches += 1;
+    e->prof.gemm_flops += 2.0 * (double)m * ga.n * ga.k;
+    return FSGPU_OK;
+}
+
 // The f16 form of the forward (max_len <= 32).  Caller holds e->mu and has selected the device.
 static int minilm_embed_fast_locked(const fsgpu_minilm* e, const int32_t* d_ids, const int32_t* d_lens, uint32_t batch,
                                     uint32_t max_len, float* d_out, cudaStream_t s, bool sync) {
@@ -309,6 +347,7 @@ static int minilm_embed_fast_locked(const fsgpu_minilm* e, const int32_t* d_ids,
     }
     CUDA_TRY(cudaFuncSetAttribute(gemm_f16_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_gemm_smem_bytes()));
     const unsigned row_blocks = (unsigned)((rows + 7) / 8);
+    const bool ares = env_int("FSGPU_MINILM_ARES", 1) != 0 && e->num_sms >= 2 && m >= 256;
     __half* h16 = e->f_h.as<__half>();
     __half* qkv16 = e->f_qkv.as<__half>();
     __half* ctx16 = e->f_ctx.as<__half>();
@@ -320,15 +359,17 @@ static int minilm_embed_fast_locked(const fsgpu_minilm* e, const int32_t* d_ids,
     for (uint32_t li = 0; li < e->n_layers; ++li) {
         const MiniLmLayer& L = e->layers[li];
         const bool last = li + 1 == e->n_layers;
-        int rc = minilm_fast_gemm(e, e->f_tm_h, L.qkv, e->f_tm_qkv_out, m, L.qkv_b, 0, s);
+        // K = 384 linears: CTA pairs with the activation tile resident (FSGPU_MINILM_ARES=0: 128 x 128 tiles)
+        auto lin384 = ares ? minilm_ares_gemm : minilm_fast_gemm;
+        int rc = lin384(e, e->f_tm_h, L.qkv, e->f_tm_qkv_out, m, L.qkv_b, 0, s);
         if (rc) return rc;
         minilm_fast_attention_kernel<<<(batch * kHeads + 3) / 4, 128, 0, s>>>(qkv16, d_lens, batch, max_len, ctx16);
         CUDA_TRY(cudaGetLastError());
-        rc = minilm_fast_gemm(e, e->f_tm_ctx, L.attn_out, e->f_tm_pre, m, L.attn_out_b, 2, s);
+        rc = lin384(e, e->f_tm_ctx, L.attn_out, e->f_tm_pre, m, L.attn_out_b, 2, s);
         if (rc) return rc;
         minilm_fast_ln_kernel<<<row_blocks, 256, 0, s>>>(pre32, h16, rows, L.attn_ln_g, L.attn_ln_b, e->eps, nullptr);
         CUDA_TRY(cudaGetLastError());
-        rc = minilm_fast_gemm(e, e->f_tm_h, L.ffn_in, e->f_tm_ffn_out, m, L.ffn_in_b, 1, s);
+        rc = lin384(e, e->f_tm_h, L.ffn_in, e->f_tm_ffn_out, m, L.ffn_in_b, 1, s);
         if (rc) return rc;
         rc = minilm_fast_gemm(e, e->f_tm_ffn, L.ffn_out, e->f_tm_pre, m, L.ffn_out_b, 2, s);
         if (rc) return rc;

@@ -29,6 +29,21 @@ constexpr int kFastThreads = 320;  // warps 0-7 epilogue (lane quarter = warp % 
 constexpr int kFastStages = 5;     // 5 x (A 16 KiB + W 16 KiB)
 constexpr int kFastAcc = 2;        // 2 x 128 TMEM columns
 
+// erf-GELU for the f16 form: 0.5 x (1 + tanh(y(x))) with y = x (a + b x^2 + c x^4) fitted so that tanh(y) follows
+// erf(x / sqrt 2) to 3.7e-5 on the whole axis (|x| clamped to 8 inside y: beyond it tanh is 1 to f32 precision
+// and the fitted polynomial would turn over), i.e. |GELU error| <= 5.5e-5 + 2.4e-4 |x| from tanh.approx.f32's
+// 2^-11 — below the f16 rounding of the result it feeds.  9 instructions and one MUFU instead of ~18 and two:
+// the FFN-in epilogue evaluates 50 M of these per layer and was bound by them (131 of the layer's 323 us).
+__device__ __forceinline__ float gelu_tanh_fit(float x) {
+    const float xc = fminf(fmaxf(x, -8.0f), 8.0f);
+    const float x2 = xc * xc;
+    float p = fmaf(-0.00031580769466f, x2, 0.036798259397f);
+    p = fmaf(p, x2, 0.79771783151f);
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(xc * p));
+    return x * fmaf(0.5f, t, 0.5f);
+}
+
 struct FastGemmArgs {
     uint32_t m, n, k;     // n % 128 == 0, k % 64 == 0
     const float* bias;    // [n]
@@ -37,7 +52,7 @@ struct FastGemmArgs {
 
 __host__ __device__ inline size_t fast_gemm_smem_bytes() {
     // ring | 8 warps x 8 KiB staging (f32 mode: two [32 x 32] boxes; f16 modes use the first 4 KiB) | barriers
-    return 1024 + (size_t)kFastStages * 2 * kMmaTileBytes + 8 * 8192 + 256;
+    return 1024 + (size_t)kFastStages * 2 * kMmaTileBytes + 8 * 8192 + 256 + 384 * 4;
 }
 
 // tm_out: f16 modes: [M, N] f16, box [64 cols x 32 rows]; f32 mode: [M, N] f32, box [32 cols x 32 rows]; both
@@ -59,6 +74,12 @@ gemm_f16_fast_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
     auto tfull_bar = [&](uint32_t a) { return bar0 + 8u * (16u + a); };
     auto tempty_bar = [&](uint32_t a) { return bar0 + 8u * (20u + a); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
+    // bias of the whole layer in shared memory when it fits (n <= 384: this kernel's FFN-out / out-projection use);
+    // with the L1 carved down to a few KiB every global bias load was an L2 round trip in the epilogue
+    float* bias_s = reinterpret_cast<float*>(bars + 32);
+    const bool bias_in_smem = args.n <= 384u;
+    if (bias_in_smem)
+        for (uint32_t i = threadIdx.x; i < args.n; i += blockDim.x) bias_s[i] = args.bias[i];
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t tiles_m = (args.m + 127u) / 128u, tiles_n = args.n / 128u;
@@ -172,8 +193,9 @@ gemm_f16_fast_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
                     float x[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        x[i] = __uint_as_float(v[c][j + i]) + __ldg(args.bias + col0 + c * 32 + j + i);
-                        if (args.mode == 1) x[i] = gelu_erf(x[i]);
+                        const uint32_t col = col0 + c * 32 + j + i;
+                        x[i] = __uint_as_float(v[c][j + i]) + (bias_in_smem ? bias_s[col] : __ldg(args.bias + col));
+                        if (args.mode == 1) x[i] = gelu_tanh_fit(x[i]);
                     }
                     if (args.mode == 2) {  // f32: box c = columns [32c, 32c+32): 8 chunks of 4 floats per row
                         const uint32_t ch = (uint32_t)j / 4u;
@@ -209,6 +231,251 @@ gemm_f16_fast_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
     if (warp == 0) {
         tc_fence_after();
         tmem_dealloc(tmem_base, kFastAcc * 128);
+    }
+}
+
+// ─── the K <= 384 linears (QKV, out-projection, FFN-in) on CTA pairs with the activation tile RESIDENT ──────
+// A 128 x 128 tile with both operands streamed asks the L2->SM fabric for 128 B per MMA clock and gets ~25: the
+// single-CTA kernel above runs the tensor pipe at ~20 % (1.64 of the f16 form's 2.17 ms were GEMMs).  Here the
+// two CTAs of a cluster share tcgen05.mma.cta_group::2 instructions of M = 256 rows (128 per CTA) x N = 256
+// features (each CTA loads 128 weight rows), and a CTA's [128 x K] activation tile stays in shared memory while
+// the pair walks over the feature blocks of its work items — only weights stream: 32 B per MMA clock, the ratio
+// of the corpus scan's pair kernels.  Work items (256-row tile, 256-feature block) are dealt in contiguous
+// m-major ranges, so a pair reloads its activation tile once or twice per GEMM; the reload is K-block by
+// K-block behind per-block barriers, as soon as the last item of the old tile has consumed that block.
+// N % 256 == 128 leaves a 128-wide block: the N = 128 instruction shape with 64 weight rows per CTA.
+constexpr int kAresThreads = 320;
+constexpr uint32_t kAresMaxKb = 6;  // K <= 384
+constexpr uint32_t kAresMaxN = 1536;  // the layer's bias vector is staged in shared memory
+
+struct AresGemmArgs {
+    uint32_t m, n, k;
+    uint32_t n_stages;   // W ring depth (16 KiB stages)
+    const float* bias;
+    int mode;            // as FastGemmArgs
+};
+
+__host__ __device__ inline size_t ares_gemm_smem_bytes(uint32_t n_kb, uint32_t n_stages) {
+    return 1024 + (size_t)(n_kb + n_stages) * kMmaTileBytes + 8 * 4096 + 512 + kAresMaxN * 4;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kAresThreads, 1)
+gemm_f16_ares_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
+                          const __grid_constant__ CUtensorMap tm_w64, const __grid_constant__ CUtensorMap tm_out,
+                          const AresGemmArgs args) {
+    extern __shared__ uint8_t smem_dyn[];
+    const uint32_t raw = smem_u32(smem_dyn);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_dyn + (base - raw);
+    const uint32_t n_kb = args.k / kMmaKBlock;
+    const uint32_t a_smem = base, w_smem = base + n_kb * kMmaTileBytes;
+    const uint32_t stage_smem = w_smem + args.n_stages * kMmaTileBytes;  // 8 x 4 KiB
+    uint8_t* stage_ptr = base_ptr + (size_t)(n_kb + args.n_stages) * kMmaTileBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stage_ptr + 8 * 4096);
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](uint32_t s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](uint32_t s) { return bar0 + 8u * (8u + s); };
+    auto tfull_bar = [&](uint32_t a) { return bar0 + 8u * (16u + a); };
+    auto tempty_bar = [&](uint32_t a) { return bar0 + 8u * (18u + a); };
+    auto afull_bar = [&](uint32_t kb) { return bar0 + 8u * (20u + kb); };
+    auto aempty_bar = [&](uint32_t kb) { return bar0 + 8u * (26u + kb); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
+    // the bias vector in shared memory: with the L1 carved down to a few KiB every global bias load was an L2 round
+    // trip inside the epilogue — 54 % of this kernel's stall samples (profiles/r02_minilm_ares_qkv_ncu.md)
+    float* bias_s = reinterpret_cast<float*>(bars + 40);
+    for (uint32_t i = threadIdx.x; i < args.n; i += blockDim.x) bias_s[i] = args.bias[i];
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const uint32_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const uint32_t m_tiles = (args.m + 255u) / 256u, n_blocks = (args.n + 255u) / 256u;
+    const uint32_t items = m_tiles * n_blocks;
+    const uint32_t item0 = (uint32_t)((uint64_t)items * pair / n_pairs), item1 = (uint32_t)((uint64_t)items * (pair + 1) / n_pairs);
+
+    if (warp == 8 && lane == 0) {
+        tma_prefetch_desc(&tm_a);
+        tma_prefetch_desc(&tm_w);
+        tma_prefetch_desc(&tm_out);
+        for (uint32_t s = 0; s < args.n_stages; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (uint32_t a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 16);  // one arrival per epilogue warp of BOTH CTAs
+        }
+        for (uint32_t kb = 0; kb < kAresMaxKb; ++kb) {
+            mbar_init(afull_bar(kb), 1);
+            mbar_init(aempty_bar(kb), 1);
+        }
+        fence_barrier_init();
+    } else if (warp == 0) {
+        tmem_alloc_pair(smem_u32(tmem_slot), 512);
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 8) {
+        // ===== TMA producer (both CTAs; completion bytes land on the leader's barriers) =====
+        uint32_t stage = 0, phase = 0, a_gen = 0;
+        uint32_t cur_mt = 0xFFFFFFFFu;
+        for (uint32_t item = item0; item < item1; ++item) {
+            const uint32_t mt = item / n_blocks, nb = item % n_blocks;
+            const bool tail = args.n - nb * 256u < 256u;  // 128-wide block: 64 weight rows per CTA
+            const bool new_a = mt != cur_mt;
+            cur_mt = mt;
+            for (uint32_t kb = 0; kb < n_kb; ++kb) {
+                if (new_a) {
+                    if (a_gen) mbar_wait(aempty_bar(kb), (a_gen - 1u) & 1u);  // the old tile's last item has read this block
+                    if (elect_one()) {
+                        if (rank == 0) mbar_expect_tx(afull_bar(kb), 2u * kMmaTileBytes);
+                        tma_load_2d_pair(a_smem + kb * kMmaTileBytes, &tm_a, afull_bar(kb), (int32_t)(kb * kMmaKBlock),
+                                         (int32_t)(mt * 256u + rank * 128u));
+                    }
+                    __syncwarp();
+                }
+                mbar_wait(empty_bar(stage), phase ^ 1u);
+                if (elect_one()) {
+                    if (rank == 0) mbar_expect_tx(full_bar(stage), tail ? kMmaTileBytes : 2u * kMmaTileBytes);
+                    if (tail)
+                        tma_load_2d_pair(w_smem + stage * kMmaTileBytes, &tm_w64, full_bar(stage), (int32_t)(kb * kMmaKBlock),
+                                         (int32_t)(nb * 256u + rank * 64u));
+                    else
+                        tma_load_2d_pair(w_smem + stage * kMmaTileBytes, &tm_w, full_bar(stage), (int32_t)(kb * kMmaKBlock),
+                                         (int32_t)(nb * 256u + rank * 128u));
+                }
+                __syncwarp();
+                if (++stage == args.n_stages) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+            if (new_a) ++a_gen;
+        }
+    } else if (warp == 9) {
+        if (rank == 0) {
+            // ===== MMA issuer (leader CTA only) =====
+            constexpr uint32_t idesc256 = umma_idesc_f16(256, 256), idesc128 = umma_idesc_f16(256, 128);
+            const uint64_t a_desc0 = umma_desc_sw128(a_smem), w_desc0 = umma_desc_sw128(w_smem);
+            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, a_gen = 0;
+            uint32_t cur_mt = 0xFFFFFFFFu;
+            for (uint32_t item = item0; item < item1; ++item) {
+                const uint32_t mt = item / n_blocks, nb = item % n_blocks;
+                const bool tail = args.n - nb * 256u < 256u;
+                const bool new_a = mt != cur_mt;
+                const bool last_of_a = item + 1 == item1 || (item + 1) / n_blocks != mt;
+                cur_mt = mt;
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * 256u;
+                for (uint32_t kb = 0; kb < n_kb; ++kb) {
+                    if (new_a) mbar_wait(afull_bar(kb), a_gen & 1u);
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint64_t a_desc = a_desc0 + (uint64_t)(kb * (kMmaTileBytes >> 4));
+                        const uint64_t w_desc = w_desc0 + (uint64_t)(stage * (kMmaTileBytes >> 4));
+#pragma unroll
+                        for (uint32_t k4 = 0; k4 < 4; ++k4)
+                            umma_f16_pair(d_tmem, a_desc + 2u * k4, w_desc + 2u * k4, tail ? idesc128 : idesc256,
+                                          (kb | k4) != 0u ? 1u : 0u);
+                        umma_commit_pair(empty_bar(stage));
+                        if (last_of_a) umma_commit_pair(aempty_bar(kb));
+                        if (kb + 1 == n_kb) umma_commit_pair(tfull_bar(acc));
+                    }
+                    __syncwarp();
+                    if (++stage == args.n_stages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                if (new_a) ++a_gen;
+                acc ^= 1u;
+                if (acc == 0u) acc_phase ^= 1u;
+            }
+        }
+    } else {
+        // ===== epilogue (both CTAs): TMEM lane = output row of this CTA, column = feature of the block =====
+        const uint32_t quarter = warp & 3u, half = warp >> 2;
+        const uint32_t my_stage = stage_smem + warp * 4096u;
+        uint8_t* my_ptr = stage_ptr + (size_t)warp * 4096u;
+        const uint32_t sw = lane & 7u;
+        const int mode = args.mode & 15, dbg = args.mode >> 4;  // dbg: timing experiments (FSGPU_MINILM_DBG)
+        uint32_t acc = 0, acc_phase = 0;
+        for (uint32_t item = item0; item < item1; ++item) {
+            const uint32_t mt = item / n_blocks, nb = item % n_blocks;
+            const bool tail = args.n - nb * 256u < 256u;
+            const uint32_t row0 = mt * 256u + rank * 128u + quarter * 32u;
+            const uint32_t width = tail ? 64u : 128u;  // columns of this warp: [half * width, +width)
+            const uint32_t col0 = nb * 256u + half * width;
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * 256u + half * width;
+            uint32_t v[4][32];
+            tmem_ld_x32(taddr, v[0]);
+            tmem_ld_x32(taddr + 32u, v[1]);
+            if (!tail) {
+                tmem_ld_x32(taddr + 64u, v[2]);
+                tmem_ld_x32(taddr + 96u, v[3]);
+            }
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tempty_bar(acc), 0);  // the accumulator is in registers
+            acc ^= 1u;
+            if (acc == 0u) acc_phase ^= 1u;
+            if (row0 >= args.m) continue;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {  // 32-column chunks; a staging box = 64 f16 columns or 32 f32 columns
+                if (c * 32u >= width) break;
+                const bool new_box = mode == 2 || (c & 1) == 0;
+                if (new_box && !(dbg & 2)) {
+                    if (lane == 0) tma_store_wait_read();
+                    __syncwarp();
+                }
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    float x[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        x[i] = __uint_as_float(v[c][j + i]) + ((dbg & 1) ? 0.f : bias_s[col0 + c * 32 + j + i]);
+                        if (mode == 1) x[i] = gelu_tanh_fit(x[i]);
+                    }
+                    if (dbg & 4) {
+                        if (x[0] + x[1] + x[2] + x[3] + x[4] + x[5] + x[6] + x[7] == 12345.678f) my_ptr[0] = 1;
+                    } else if (mode == 2) {
+                        const uint32_t ch = (uint32_t)j / 4u;
+                        *reinterpret_cast<float4*>(my_ptr + lane * 128u + ((ch ^ sw) << 4)) = make_float4(x[0], x[1], x[2], x[3]);
+                        *reinterpret_cast<float4*>(my_ptr + lane * 128u + (((ch + 1u) ^ sw) << 4)) = make_float4(x[4], x[5], x[6], x[7]);
+                    } else {
+                        const uint32_t ch = (uint32_t)((c & 1) * 32 + j) / 8u;
+                        __half2 hh[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) hh[i] = __floats2half2_rn(x[2 * i], x[2 * i + 1]);
+                        *reinterpret_cast<uint4*>(my_ptr + lane * 128u + ((ch ^ sw) << 4)) = *reinterpret_cast<uint4*>(hh);
+                    }
+                }
+                const bool box_done = mode == 2 || (c & 1) == 1;
+                if (box_done && !(dbg & 2)) {
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        const int32_t bc = (int32_t)(col0 + (mode == 2 ? c * 32 : (c & ~1) * 32));
+                        tma_store_2d(&tm_out, my_stage, bc, (int32_t)row0);
+                        tma_store_commit();
+                    }
+                }
+            }
+        }
+        if (lane == 0) tma_store_wait_all();
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, 512);
     }
 }
 
