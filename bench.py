@@ -761,6 +761,38 @@ def bench_config4(ctx):
         torch.cuda.synchronize(dev)
 
     enc_ms = _time_wall(ctx, with_encoders, max(3, a.steps // 2), 2)
+
+    # the encoder alone (device-resident token ids): ms per batch, GEMM time and useful TFLOP/s from the library's own
+    # events, for the default f16 form and the split-f16 form (FSGPU_MINILM_PRODUCTS=3)
+    encoder = None
+    if ctx.rank == 0:
+        d_ids, d_lens = ids_h.to(dev), lens_h.to(dev)
+        encoder = {"batch": batch, "tokens_per_query": "4-32 (t_pad 32)", "weights": "synthetic (seeded), all-MiniLM-L6-v2 geometry"}
+        useful_flop = 2.0 * batch * 32 * 6 * (4 * 384 * 384 + 2 * 384 * 1536)
+        for name, mode in (("f16_form", "0"), ("split_f16_form", "3")):
+            os.environ["FSGPU_MINILM_PRODUCTS"] = mode
+            for _ in range(3):
+                minilm.embed_device(d_ids, d_lens)
+            torch.cuda.synchronize(dev)
+            minilm.profile_read(reset=True)
+            minilm.profile_enable(True)
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            for _ in range(10):
+                minilm.embed_device(d_ids, d_lens)
+            t1.record()
+            torch.cuda.synchronize(dev)
+            pr = minilm.profile_read(reset=True)
+            minilm.profile_enable(False)
+            enc_only = t0.elapsed_time(t1) / 10
+            encoder[name] = {"ms_per_batch": enc_only, "queries_per_s": batch / enc_only * 1e3, "gemm_ms": pr["gemm_ms"] / 10,
+                             "gemm_launches_per_batch": pr["gemm_launches"] // 10,
+                             "useful_tflops_whole_encoder": useful_flop / (enc_only * 1e-3) / 1e12,
+                             "useful_tflops_in_gemms": useful_flop / (pr["gemm_ms"] / 10 * 1e-3) / 1e12}
+        del os.environ["FSGPU_MINILM_PRODUCTS"]
+        encoder["accuracy"] = ("f16 form: |component error| <= 5e-4, cosine >= 1 - 2e-6 vs PyTorch f32 (tests/test_gpu_minilm.py); "
+                               "split form: <= 2e-4 (measured ~2e-6)")
+        encoder["ncu"] = "profiles/r02_minilm_f16_form.md"
     rec = None
     if ctx.rank == 0:
         rec = {"workload": f"configs[3]: {n} docs, 256-d fast tier + 384-d quality tier, f16, row-sharded over {ctx.world} "
@@ -772,6 +804,7 @@ def bench_config4(ctx):
                "with_encoders": {"ms_per_step": enc_ms, "queries_per_s": batch / enc_ms * 1e3,
                                  "what": "host token ids -> potion gather-pool + MiniLM-L6 forward (synthetic weights, "
                                          "4-32 tokens) -> the same search -> host results"},
+               "encoder": encoder,
                "flow": "SyncTwoTierSearcher::search_internal, sync_searcher.rs:616-1009, pre-embedded queries"}
         if not a.no_cpu_baseline:
             fused_i, fused_r = snap["initial"], snap["refined"]

@@ -292,12 +292,15 @@ static int minilm_ares_gemm(const fsgpu_minilm* e, const CUtensorMap& tm_a, cons
     ga.k = w.cols;
     ga.bias = bias;
     ga.mode = mode | (env_int("FSGPU_MINILM_DBG", 0) << 4);
-    const uint32_t n_kb = ga.k / kMmaKBlock;
+    ga.k_chunks = ga.k > kAresMaxKb * kMmaKBlock ? ga.k / (kAresMaxKb * kMmaKBlock) : 1;
+    if (ga.k % ga.k_chunks != 0 || (ga.k / ga.k_chunks) % kMmaKBlock != 0 || (ga.k_chunks > 1 && ga.n > 512))
+        return fail(FSGPU_ERR_INVALID_CONFIG, "minilm: linear %u x %u outside the pair GEMM's range", ga.n, ga.k);
+    const uint32_t n_kb = ga.k / ga.k_chunks / kMmaKBlock;
     if (ga.n > kAresMaxN || n_kb > kAresMaxKb) return fail(FSGPU_ERR_INVALID_CONFIG, "minilm: linear %u x %u outside the pair GEMM's range", ga.n, ga.k);
     ga.n_stages = (uint32_t)std::min<size_t>(8, (227 * 1024 - ares_gemm_smem_bytes(n_kb, 0)) / kMmaTileBytes);
     const size_t smem = ares_gemm_smem_bytes(n_kb, ga.n_stages);
     CUDA_TRY(cudaFuncSetAttribute(gemm_f16_ares_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const uint32_t items = ((m + 255u) / 256u) * ((ga.n + 255u) / 256u);
+    const uint32_t items = ((m + 255u) / 256u) * (ga.k_chunks > 1 ? 1u : (ga.n + 255u) / 256u);  // units a pair can own
     const uint32_t grid = 2 * std::min<uint32_t>(items, (uint32_t)e->num_sms / 2);
     std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
     if (e->profiling) {
@@ -371,7 +374,10 @@ static int minilm_embed_fast_locked(const fsgpu_minilm* e, const int32_t* d_ids,
         CUDA_TRY(cudaGetLastError());
         rc = lin384(e, e->f_tm_h, L.ffn_in, e->f_tm_ffn_out, m, L.ffn_in_b, 1, s);
         if (rc) return rc;
-        rc = minilm_fast_gemm(e, e->f_tm_ffn, L.ffn_out, e->f_tm_pre, m, L.ffn_out_b, 2, s);
+        // FFN-out (K = 1536): 128 x 128 tiles with both operands streamed; the pair kernel's K-chunked mode
+        // (FSGPU_MINILM_ARES_FFN_OUT=1) measures the same 54 us per layer — two waves of whole 256-row tiles
+        const bool ffn_out_pair = ares && I % (kAresMaxKb * kMmaKBlock) == 0 && env_int("FSGPU_MINILM_ARES_FFN_OUT", 0) != 0;
+        rc = (ffn_out_pair ? minilm_ares_gemm : minilm_fast_gemm)(e, e->f_tm_ffn, L.ffn_out, e->f_tm_pre, m, L.ffn_out_b, 2, s);
         if (rc) return rc;
         minilm_fast_ln_kernel<<<row_blocks, 256, 0, s>>>(pre32, h16, rows, L.ffn_ln_g, L.ffn_ln_b, e->eps, last ? h32 : nullptr);
         CUDA_TRY(cudaGetLastError());

@@ -244,19 +244,24 @@ gemm_f16_fast_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
 // m-major ranges, so a pair reloads its activation tile once or twice per GEMM; the reload is K-block by
 // K-block behind per-block barriers, as soon as the last item of the old tile has consumed that block.
 // N % 256 == 128 leaves a 128-wide block: the N = 128 instruction shape with 64 weight rows per CTA.
-constexpr int kAresThreads = 320;
+constexpr int kAresEpiWarps = 16;  // four per TMEM lane quarter, 64 columns each: the epilogue (bias, GELU, f16 pack) is
+                                   // instruction-latency-bound — eight warps ran it at an IPC of ~0.35 per scheduler
+constexpr int kAresThreads = 32 * (kAresEpiWarps + 2);  // + TMA producer, MMA issuer (highest warp ids)
 constexpr uint32_t kAresMaxKb = 6;  // K <= 384
 constexpr uint32_t kAresMaxN = 1536;  // the layer's bias vector is staged in shared memory
 
 struct AresGemmArgs {
-    uint32_t m, n, k;
+    uint32_t m, n, k;    // k = k_chunks * (<= 384)
+    uint32_t k_chunks;   // > 1 (FFN-out, K = 1536): the pair owns whole 256-row tiles and walks (K chunk, feature block)
+                         // with the activation tile of the chunk resident; a block's accumulator lives through all
+                         // chunks, so n <= 512 (the two TMEM accumulators = the tile's two feature blocks)
     uint32_t n_stages;   // W ring depth (16 KiB stages)
     const float* bias;
     int mode;            // as FastGemmArgs
 };
 
 __host__ __device__ inline size_t ares_gemm_smem_bytes(uint32_t n_kb, uint32_t n_stages) {
-    return 1024 + (size_t)(n_kb + n_stages) * kMmaTileBytes + 8 * 4096 + 512 + kAresMaxN * 4;
+    return 1024 + (size_t)(n_kb + n_stages) * kMmaTileBytes + kAresEpiWarps * 4096 + 512 + kAresMaxN * 4;
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kAresThreads, 1)
@@ -267,11 +272,11 @@ gemm_f16_ares_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid
     const uint32_t raw = smem_u32(smem_dyn);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* base_ptr = smem_dyn + (base - raw);
-    const uint32_t n_kb = args.k / kMmaKBlock;
+    const uint32_t n_kb = args.k / args.k_chunks / kMmaKBlock;  // K-blocks of one chunk
     const uint32_t a_smem = base, w_smem = base + n_kb * kMmaTileBytes;
-    const uint32_t stage_smem = w_smem + args.n_stages * kMmaTileBytes;  // 8 x 4 KiB
+    const uint32_t stage_smem = w_smem + args.n_stages * kMmaTileBytes;  // one 4 KiB box per epilogue warp
     uint8_t* stage_ptr = base_ptr + (size_t)(n_kb + args.n_stages) * kMmaTileBytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(stage_ptr + 8 * 4096);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stage_ptr + kAresEpiWarps * 4096);
     const uint32_t bar0 = smem_u32(bars);
     auto full_bar = [&](uint32_t s) { return bar0 + 8u * s; };
     auto empty_bar = [&](uint32_t s) { return bar0 + 8u * (8u + s); };
@@ -289,10 +294,14 @@ gemm_f16_ares_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid
     const uint32_t rank = cluster_ctarank();
     const uint32_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
     const uint32_t m_tiles = (args.m + 255u) / 256u, n_blocks = (args.n + 255u) / 256u;
-    const uint32_t items = m_tiles * n_blocks;
-    const uint32_t item0 = (uint32_t)((uint64_t)items * pair / n_pairs), item1 = (uint32_t)((uint64_t)items * (pair + 1) / n_pairs);
+    const uint32_t kch = args.k_chunks, per_mt = kch * n_blocks;  // items of one 256-row tile: (K chunk, feature block)
+    // contiguous m-major item ranges; with K chunks a pair owns whole tiles (its accumulators live across the chunks)
+    const uint32_t item0 = kch > 1 ? (uint32_t)((uint64_t)m_tiles * pair / n_pairs) * per_mt
+                                   : (uint32_t)((uint64_t)m_tiles * n_blocks * pair / n_pairs);
+    const uint32_t item1 = kch > 1 ? (uint32_t)((uint64_t)m_tiles * (pair + 1) / n_pairs) * per_mt
+                                   : (uint32_t)((uint64_t)m_tiles * n_blocks * (pair + 1) / n_pairs);
 
-    if (warp == 8 && lane == 0) {
+    if (warp == kAresEpiWarps && lane == 0) {
         tma_prefetch_desc(&tm_a);
         tma_prefetch_desc(&tm_w);
         tma_prefetch_desc(&tm_out);
@@ -302,7 +311,7 @@ gemm_f16_ares_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid
         }
         for (uint32_t a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), 16);  // one arrival per epilogue warp of BOTH CTAs
+            mbar_init(tempty_bar(a), 2 * kAresEpiWarps);  // one arrival per epilogue warp of BOTH CTAs
         }
         for (uint32_t kb = 0; kb < kAresMaxKb; ++kb) {
             mbar_init(afull_bar(kb), 1);
@@ -317,21 +326,22 @@ gemm_f16_ares_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 8) {
+    if (warp == kAresEpiWarps) {
         // ===== TMA producer (both CTAs; completion bytes land on the leader's barriers) =====
         uint32_t stage = 0, phase = 0, a_gen = 0;
-        uint32_t cur_mt = 0xFFFFFFFFu;
+        uint32_t cur_a = 0xFFFFFFFFu;
         for (uint32_t item = item0; item < item1; ++item) {
-            const uint32_t mt = item / n_blocks, nb = item % n_blocks;
+            const uint32_t mt = item / per_mt, kc = (item % per_mt) / n_blocks, nb = item % n_blocks;
             const bool tail = args.n - nb * 256u < 256u;  // 128-wide block: 64 weight rows per CTA
-            const bool new_a = mt != cur_mt;
-            cur_mt = mt;
+            const bool new_a = item / n_blocks != cur_a;  // a new (tile, K chunk)
+            cur_a = item / n_blocks;
+            const uint32_t k0 = kc * n_kb * kMmaKBlock;
             for (uint32_t kb = 0; kb < n_kb; ++kb) {
                 if (new_a) {
                     if (a_gen) mbar_wait(aempty_bar(kb), (a_gen - 1u) & 1u);  // the old tile's last item has read this block
                     if (elect_one()) {
                         if (rank == 0) mbar_expect_tx(afull_bar(kb), 2u * kMmaTileBytes);
-                        tma_load_2d_pair(a_smem + kb * kMmaTileBytes, &tm_a, afull_bar(kb), (int32_t)(kb * kMmaKBlock),
+                        tma_load_2d_pair(a_smem + kb * kMmaTileBytes, &tm_a, afull_bar(kb), (int32_t)(k0 + kb * kMmaKBlock),
                                          (int32_t)(mt * 256u + rank * 128u));
                     }
                     __syncwarp();
@@ -340,10 +350,10 @@ gemm_f16_ares_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid
                 if (elect_one()) {
                     if (rank == 0) mbar_expect_tx(full_bar(stage), tail ? kMmaTileBytes : 2u * kMmaTileBytes);
                     if (tail)
-                        tma_load_2d_pair(w_smem + stage * kMmaTileBytes, &tm_w64, full_bar(stage), (int32_t)(kb * kMmaKBlock),
+                        tma_load_2d_pair(w_smem + stage * kMmaTileBytes, &tm_w64, full_bar(stage), (int32_t)(k0 + kb * kMmaKBlock),
                                          (int32_t)(nb * 256u + rank * 64u));
                     else
-                        tma_load_2d_pair(w_smem + stage * kMmaTileBytes, &tm_w, full_bar(stage), (int32_t)(kb * kMmaKBlock),
+                        tma_load_2d_pair(w_smem + stage * kMmaTileBytes, &tm_w, full_bar(stage), (int32_t)(k0 + kb * kMmaKBlock),
                                          (int32_t)(nb * 256u + rank * 128u));
                 }
                 __syncwarp();
@@ -354,21 +364,27 @@ gemm_f16_ares_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid
             }
             if (new_a) ++a_gen;
         }
-    } else if (warp == 9) {
+    } else if (warp == kAresEpiWarps + 1) {
         if (rank == 0) {
             // ===== MMA issuer (leader CTA only) =====
             constexpr uint32_t idesc256 = umma_idesc_f16(256, 256), idesc128 = umma_idesc_f16(256, 128);
             const uint64_t a_desc0 = umma_desc_sw128(a_smem), w_desc0 = umma_desc_sw128(w_smem);
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, a_gen = 0;
-            uint32_t cur_mt = 0xFFFFFFFFu;
+            uint32_t cur_a = 0xFFFFFFFFu;
             for (uint32_t item = item0; item < item1; ++item) {
-                const uint32_t mt = item / n_blocks, nb = item % n_blocks;
+                const uint32_t kc = (item % per_mt) / n_blocks, nb = item % n_blocks;
                 const bool tail = args.n - nb * 256u < 256u;
-                const bool new_a = mt != cur_mt;
-                const bool last_of_a = item + 1 == item1 || (item + 1) / n_blocks != mt;
-                cur_mt = mt;
-                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
-                tc_fence_after();
+                const bool new_a = item / n_blocks != cur_a;
+                const bool last_of_a = item + 1 == item1 || (item + 1) / n_blocks != item / n_blocks;
+                cur_a = item / n_blocks;
+                if (kch > 1) {  // the block's accumulator, through every K chunk of the tile
+                    acc = nb;
+                    acc_phase = ((item - item0) / per_mt) & 1u;
+                }
+                if (kc == 0) {
+                    mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                    tc_fence_after();
+                }
                 const uint32_t d_tmem = tmem_base + acc * 256u;
                 for (uint32_t kb = 0; kb < n_kb; ++kb) {
                     if (new_a) mbar_wait(afull_bar(kb), a_gen & 1u);
@@ -380,10 +396,10 @@ gemm_f16_ares_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid
 #pragma unroll
                         for (uint32_t k4 = 0; k4 < 4; ++k4)
                             umma_f16_pair(d_tmem, a_desc + 2u * k4, w_desc + 2u * k4, tail ? idesc128 : idesc256,
-                                          (kb | k4) != 0u ? 1u : 0u);
+                                          (kc | kb | k4) != 0u ? 1u : 0u);
                         umma_commit_pair(empty_bar(stage));
                         if (last_of_a) umma_commit_pair(aempty_bar(kb));
-                        if (kb + 1 == n_kb) umma_commit_pair(tfull_bar(acc));
+                        if (kb + 1 == n_kb && kc + 1 == kch) umma_commit_pair(tfull_bar(acc));
                     }
                     __syncwarp();
                     if (++stage == args.n_stages) {
@@ -392,44 +408,51 @@ gemm_f16_ares_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid
                     }
                 }
                 if (new_a) ++a_gen;
-                acc ^= 1u;
-                if (acc == 0u) acc_phase ^= 1u;
+                if (kch == 1) {
+                    acc ^= 1u;
+                    if (acc == 0u) acc_phase ^= 1u;
+                }
             }
         }
     } else {
         // ===== epilogue (both CTAs): TMEM lane = output row of this CTA, column = feature of the block =====
-        const uint32_t quarter = warp & 3u, half = warp >> 2;
+        const uint32_t quarter = warp & 3u, part = warp >> 2;  // columns [part * 64, +64) of the block
         const uint32_t my_stage = stage_smem + warp * 4096u;
         uint8_t* my_ptr = stage_ptr + (size_t)warp * 4096u;
         const uint32_t sw = lane & 7u;
         const int mode = args.mode & 15, dbg = args.mode >> 4;  // dbg: timing experiments (FSGPU_MINILM_DBG)
         uint32_t acc = 0, acc_phase = 0;
         for (uint32_t item = item0; item < item1; ++item) {
-            const uint32_t mt = item / n_blocks, nb = item % n_blocks;
+            const uint32_t mt = item / per_mt, kc = (item % per_mt) / n_blocks, nb = item % n_blocks;
+            if (kc + 1 != kch) continue;  // the block is complete after the tile's last K chunk
+            if (kch > 1) {
+                acc = nb;
+                acc_phase = ((item - item0) / per_mt) & 1u;
+            }
             const bool tail = args.n - nb * 256u < 256u;
             const uint32_t row0 = mt * 256u + rank * 128u + quarter * 32u;
-            const uint32_t width = tail ? 64u : 128u;  // columns of this warp: [half * width, +width)
-            const uint32_t col0 = nb * 256u + half * width;
+            const bool idle = tail && part * 64u >= 128u;  // a 128-wide block has columns for two of the four parts
+            const uint32_t col0 = nb * 256u + part * 64u;
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * 256u + half * width;
-            uint32_t v[4][32];
-            tmem_ld_x32(taddr, v[0]);
-            tmem_ld_x32(taddr + 32u, v[1]);
-            if (!tail) {
-                tmem_ld_x32(taddr + 64u, v[2]);
-                tmem_ld_x32(taddr + 96u, v[3]);
+            const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * 256u + part * 64u;
+            uint32_t v[2][32];
+            if (!idle) {
+                tmem_ld_x32(taddr, v[0]);
+                tmem_ld_x32(taddr + 32u, v[1]);
+                tmem_ld_wait();
             }
-            tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(tempty_bar(acc), 0);  // the accumulator is in registers
-            acc ^= 1u;
-            if (acc == 0u) acc_phase ^= 1u;
+            if (kch == 1) {
+                acc ^= 1u;
+                if (acc == 0u) acc_phase ^= 1u;
+            }
+            if (idle) continue;
             if (row0 >= args.m) continue;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {  // 32-column chunks; a staging box = 64 f16 columns or 32 f32 columns
-                if (c * 32u >= width) break;
+            for (int c = 0; c < 2; ++c) {  // 32-column chunks; a staging box = 64 f16 columns or 32 f32 columns
                 const bool new_box = mode == 2 || (c & 1) == 0;
                 if (new_box && !(dbg & 2)) {
                     if (lane == 0) tma_store_wait_read();
