@@ -839,7 +839,10 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
         a.cand_count = ix->ws_cand_count.as<uint32_t>();
         a.cap = cap;
         // pacing of the pairs that share a tile stream (only meaningful with several query pairs)
-        const uint32_t lead = (uint32_t)std::max(0, env_int("FSGPU_MMA_LEAD", 16));
+        // (int8 quad form at 10 M x 384, batch 1024: lead 32 / 16 / 8 / 4 / 2 -> 4.24 / 4.16 / 3.90 / 3.87 / 3.87 GB read from
+        // DRAM for 3.84 GB of codes, the same 2.35 ms)
+        // f16 pair form: lead 16 -> 4: 12.08 -> 7.70 GB for 7.68 GB of slab and 5.12 -> 4.92 ms (less DRAM power, higher clock)
+        const uint32_t lead = (uint32_t)std::max(0, env_int("FSGPU_MMA_LEAD", 4));
         const bool paced = pair && n_units > 1 && lead > 0;
         // one zeroed block per sub-batch, ONE memset: [pacing counters of the three passes | the exact-gate
         // refine's per-query counts] (every separate memset is ~2 us of stream time)

@@ -288,7 +288,8 @@ __host__ __device__ inline size_t mma_scan_smem_bytes(uint32_t n_kblocks, uint32
 }
 
 __device__ __forceinline__ uint64_t mma_tile_of(const MmaScanArgs& args, uint64_t i) {
-    const uint64_t jitter = args.tile_stride > 1 ? (uint64_t)(((uint32_t)i * 0x9E3779B1u) >> 8) % args.tile_stride : 0;
+    if (args.tile_stride <= 1) return i;  // the full pass: no 64-bit modulo in the tile loop
+    const uint64_t jitter = (uint64_t)(((uint32_t)i * 0x9E3779B1u) >> 8) % args.tile_stride;
     return i * args.tile_stride + jitter;
 }
 
@@ -998,7 +999,8 @@ mma_scan_quad_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             tc_fence_after();
             uint32_t stage = 0, phase = 0, acc_phase = 0;
             const uint32_t n_kb = args.n_kblocks, n_st = args.n_stages;
-            for (uint64_t i = j0; i < args.tile_count; i += g) {
+            uint32_t li = 0;
+            for (uint64_t i = j0; i < args.tile_count; i += g, ++li) {
                 // sub-block 0 then sub-block 1 over the SAME B stages: the epilogue of one sub-block's
                 // accumulator overlaps the MMAs of the other (one accumulator each, 2 x 256 columns).
                 // ONE elected block per MMA group (all of a group's K-blocks, <= 16 MMAs, and its commits): with an
@@ -1015,7 +1017,7 @@ mma_scan_quad_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                 }
 #pragma unroll
                 for (uint32_t sub = 0; sub < kSub; ++sub) {
-                    const uint64_t tsi = (i - j0) / g - 64u;
+                    const uint32_t tsi = li - 64u;  // (li = tiles of this stream so far: the stamps cover tiles 64..127)
                     long long* ts = (args.ts && blockIdx.x == 0 && tsi < 64u && lane == 0) ? args.ts + 8 + (tsi * 2u + sub) * 72u : nullptr;
                     if (ts) ts[0] = clock64();
                     mbar_wait(tempty_bar(sub), acc_phase ^ 1u);
@@ -1064,12 +1066,12 @@ mma_scan_quad_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             list[sub] = args.cand + list_id[sub] * args.cap;
             count[sub] = 0;
         }
-        uint32_t acc_phase = 0;
-        for (uint64_t i = j0; i < args.tile_count; i += g) {
+        uint32_t acc_phase = 0, li = 0;
+        for (uint64_t i = j0; i < args.tile_count; i += g, ++li) {
             const uint64_t tile = mma_tile_of(args, i);
 #pragma unroll
             for (uint32_t sub = 0; sub < kSub; ++sub) {
-                const uint64_t tsi = (i - j0) / g - 64u;
+                const uint32_t tsi = li - 64u;
                 long long* ts = (args.ts && blockIdx.x < 2 && tsi < 64u && lane == 0)
                                     ? args.ts + 8 + (tsi * 2u + sub) * 72u + 4 + (blockIdx.x * 8 + warp) * 4 : nullptr;
                 mbar_wait(tfull_bar(sub), acc_phase);
