@@ -702,7 +702,8 @@ static MmaCascade plan_cascade(uint64_t n_rows, uint32_t k, uint32_t tile_rows, 
         if (env_int("FSGPU_MMA_GROUP_MAX", 1) != 0) {
             // ... but the next level must still be >= 8x as large, or it too often catches fewer than
             // k' rows above this gate (their count is ~ Poisson(k' * Gamma(k')/k' * t1/t0))
-            const uint64_t wide = std::min<uint64_t>(8 * c.t0, std::max<uint64_t>(c.t0, c.t1 / 8));
+            const uint64_t cap0 = (uint64_t)std::max(1, env_int("FSGPU_MMA_T0_CAP", 8));
+            const uint64_t wide = std::min<uint64_t>(cap0 * c.t0, std::max<uint64_t>(c.t0, c.t1 / 8));
             if (wide > c.t0) {
                 c.t0 = wide;
                 c.group_max = true;

@@ -2,6 +2,7 @@
 // activation workspaces, the per-layer launch sequence).  No CPU compute path.
 #include <cmath>
 #include <cstring>
+#include <map>
 #include <cstdio>
 #include <mutex>
 #include <string>
@@ -49,6 +50,14 @@ struct fsgpu_minilm {
     mutable CUtensorMap f_tm_qkv_out, f_tm_ffn_out, f_tm_pre;  // stores: f16 [64 x 32] boxes, f32 [32 x 32] boxes
     mutable uint64_t f_rows = 0;
     mutable float* f_pre_ptr = nullptr;
+    // small batches replay a captured CUDA graph of the forward (44 launches of a few microseconds each are bound by
+    // the host's launch calls): one graph per (batch, max_len, variant), inputs / outputs staged in fixed buffers
+    struct FastGraph {
+        cudaGraphExec_t exec = nullptr;
+        const void* bufs[9] = {};
+    };
+    mutable std::map<uint64_t, FastGraph> f_graphs;
+    mutable DevBuf g_ids, g_lens, g_out;
     mutable bool profiling = false;
     mutable fsgpu_minilm_profile prof{};
     mutable std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pending, ev_free;
@@ -98,7 +107,11 @@ extern "C" void fsgpu_minilm_destroy(fsgpu_minilm* e) {
             if (m->hi) cudaFree(m->hi);
             if (m->lo) cudaFree(m->lo);
         }
-        for (DevBuf* b : {&e->ws_h32, &e->ws_pre32, &e->ws_qkv32, &e->ws_ids, &e->ws_lens, &e->ws_out}) b->release();
+        for (DevBuf* b : {&e->ws_h32, &e->ws_pre32, &e->ws_qkv32, &e->ws_ids, &e->ws_lens, &e->ws_out, &e->f_h, &e->f_qkv, &e->f_ctx,
+                          &e->f_ffn, &e->g_ids, &e->g_lens, &e->g_out})
+            b->release();
+        for (auto& kv : e->f_graphs)
+            if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
         for (auto* v : {&e->ev_pending, &e->ev_free})
             for (auto& ev : *v) {
                 cudaEventDestroy(ev.first);
@@ -299,7 +312,6 @@ static int minilm_ares_gemm(const fsgpu_minilm* e, const CUtensorMap& tm_a, cons
     if (ga.n > kAresMaxN || n_kb > kAresMaxKb) return fail(FSGPU_ERR_INVALID_CONFIG, "minilm: linear %u x %u outside the pair GEMM's range", ga.n, ga.k);
     ga.n_stages = (uint32_t)std::min<size_t>(8, (227 * 1024 - ares_gemm_smem_bytes(n_kb, 0)) / kMmaTileBytes);
     const size_t smem = ares_gemm_smem_bytes(n_kb, ga.n_stages);
-    CUDA_TRY(cudaFuncSetAttribute(gemm_f16_ares_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint32_t items = ((m + 255u) / 256u) * (ga.k_chunks > 1 ? 1u : (ga.n + 255u) / 256u);  // units a pair can own
     const uint32_t grid = 2 * std::min<uint32_t>(items, (uint32_t)e->num_sms / 2);
     std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
@@ -324,33 +336,12 @@ static int minilm_ares_gemm(const fsgpu_minilm* e, const CUtensorMap& tm_a, cons
     return FSGPU_OK;
 }
 
-// The f16 form of the forward (max_len <= 32).  Caller holds e->mu and has selected the device.
-static int minilm_embed_fast_locked(const fsgpu_minilm* e, const int32_t* d_ids, const int32_t* d_lens, uint32_t batch,
-                                    uint32_t max_len, float* d_out, cudaStream_t s, bool sync) {
+// The launch sequence of the f16 form (buffers reserved and descriptors built by the caller): also what a graph captures.
+static int minilm_fast_enqueue(const fsgpu_minilm* e, const int32_t* d_ids, const int32_t* d_lens, uint32_t batch,
+                               uint32_t max_len, float* d_out, cudaStream_t s, bool ares, bool ffn_out_pair) {
     const uint64_t rows = (uint64_t)batch * max_len;
-    const uint32_t m = (uint32_t)rows, H = kHidden, I = e->inter;
-    CUDA_TRY(e->ws_h32.reserve(rows * H * 4));
-    CUDA_TRY(e->ws_pre32.reserve(rows * H * 4));
-    void* before[4] = {e->f_h.p, e->f_qkv.p, e->f_ctx.p, e->f_ffn.p};
-    float* pre_before = e->ws_pre32.as<float>();
-    CUDA_TRY(e->f_h.reserve(rows * H * 2));
-    CUDA_TRY(e->f_qkv.reserve(rows * 3 * H * 2));
-    CUDA_TRY(e->f_ctx.reserve(rows * H * 2));
-    CUDA_TRY(e->f_ffn.reserve(rows * I * 2));
-    if (rows != e->f_rows || before[0] != e->f_h.p || before[1] != e->f_qkv.p || before[2] != e->f_ctx.p ||
-        before[3] != e->f_ffn.p || pre_before != e->f_pre_ptr) {  // descriptors carry base and row count
-        const bool ok = make_f16_tile_map(&e->f_tm_h, e->f_h.p, rows, H) && make_f16_tile_map(&e->f_tm_ctx, e->f_ctx.p, rows, H) &&
-                        make_f16_tile_map(&e->f_tm_ffn, e->f_ffn.p, rows, I) &&
-                        make_tile_map_2d(&e->f_tm_qkv_out, e->f_qkv.p, rows, 3 * H, 2, 64, 32) &&
-                        make_tile_map_2d(&e->f_tm_ffn_out, e->f_ffn.p, rows, I, 2, 64, 32) &&
-                        make_tile_map_2d(&e->f_tm_pre, e->ws_pre32.p, rows, H, 4, 32, 32);
-        if (!ok) return fail(FSGPU_ERR_SUBSYSTEM, "gpu: cuTensorMapEncodeTiled failed for a minilm activation");
-        e->f_rows = rows;
-        e->f_pre_ptr = e->ws_pre32.as<float>();
-    }
-    CUDA_TRY(cudaFuncSetAttribute(gemm_f16_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_gemm_smem_bytes()));
+    const uint32_t m = (uint32_t)rows;
     const unsigned row_blocks = (unsigned)((rows + 7) / 8);
-    const bool ares = env_int("FSGPU_MINILM_ARES", 1) != 0 && e->num_sms >= 2 && m >= 256;
     __half* h16 = e->f_h.as<__half>();
     __half* qkv16 = e->f_qkv.as<__half>();
     __half* ctx16 = e->f_ctx.as<__half>();
@@ -376,7 +367,6 @@ static int minilm_embed_fast_locked(const fsgpu_minilm* e, const int32_t* d_ids,
         if (rc) return rc;
         // FFN-out (K = 1536): 128 x 128 tiles with both operands streamed; the pair kernel's K-chunked mode
         // (FSGPU_MINILM_ARES_FFN_OUT=1) measures the same 54 us per layer — two waves of whole 256-row tiles
-        const bool ffn_out_pair = ares && I % (kAresMaxKb * kMmaKBlock) == 0 && env_int("FSGPU_MINILM_ARES_FFN_OUT", 0) != 0;
         rc = (ffn_out_pair ? minilm_ares_gemm : minilm_fast_gemm)(e, e->f_tm_ffn, L.ffn_out, e->f_tm_pre, m, L.ffn_out_b, 2, s);
         if (rc) return rc;
         minilm_fast_ln_kernel<<<row_blocks, 256, 0, s>>>(pre32, h16, rows, L.ffn_ln_g, L.ffn_ln_b, e->eps, last ? h32 : nullptr);
@@ -386,6 +376,97 @@ static int minilm_embed_fast_locked(const fsgpu_minilm* e, const int32_t* d_ids,
     minilm_pool_kernel<<<batch, 128, 0, s>>>(h32, d_lens, max_len, d_out);
     CUDA_TRY(cudaGetLastError());
     e->prof.other_launches += 2;
+    return FSGPU_OK;
+}
+
+// The f16 form of the forward (max_len <= 32).  Caller holds e->mu and has selected the device.
+static int minilm_embed_fast_locked(const fsgpu_minilm* e, const int32_t* d_ids, const int32_t* d_lens, uint32_t batch,
+                                    uint32_t max_len, float* d_out, cudaStream_t s, bool sync) {
+    const uint64_t rows = (uint64_t)batch * max_len;
+    const uint32_t m = (uint32_t)rows, H = kHidden, I = e->inter;
+    CUDA_TRY(e->ws_h32.reserve(rows * H * 4));
+    CUDA_TRY(e->ws_pre32.reserve(rows * H * 4));
+    void* before[4] = {e->f_h.p, e->f_qkv.p, e->f_ctx.p, e->f_ffn.p};
+    CUDA_TRY(e->f_h.reserve(rows * H * 2));
+    CUDA_TRY(e->f_qkv.reserve(rows * 3 * H * 2));
+    CUDA_TRY(e->f_ctx.reserve(rows * H * 2));
+    CUDA_TRY(e->f_ffn.reserve(rows * I * 2));
+    if (rows != e->f_rows || before[0] != e->f_h.p || before[1] != e->f_qkv.p || before[2] != e->f_ctx.p ||
+        before[3] != e->f_ffn.p || e->ws_pre32.as<float>() != e->f_pre_ptr) {  // descriptors carry base and row count
+        const bool ok = make_f16_tile_map(&e->f_tm_h, e->f_h.p, rows, H) && make_f16_tile_map(&e->f_tm_ctx, e->f_ctx.p, rows, H) &&
+                        make_f16_tile_map(&e->f_tm_ffn, e->f_ffn.p, rows, I) &&
+                        make_tile_map_2d(&e->f_tm_qkv_out, e->f_qkv.p, rows, 3 * H, 2, 64, 32) &&
+                        make_tile_map_2d(&e->f_tm_ffn_out, e->f_ffn.p, rows, I, 2, 64, 32) &&
+                        make_tile_map_2d(&e->f_tm_pre, e->ws_pre32.p, rows, H, 4, 32, 32);
+        if (!ok) return fail(FSGPU_ERR_SUBSYSTEM, "gpu: cuTensorMapEncodeTiled failed for a minilm activation");
+        e->f_rows = rows;
+        e->f_pre_ptr = e->ws_pre32.as<float>();
+    }
+    CUDA_TRY(cudaFuncSetAttribute(gemm_f16_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_gemm_smem_bytes()));
+    CUDA_TRY(cudaFuncSetAttribute(gemm_f16_ares_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    const bool ares = env_int("FSGPU_MINILM_ARES", 1) != 0 && e->num_sms >= 2 && m >= 256;
+    const bool ffn_out_pair = ares && I % (kAresMaxKb * kMmaKBlock) == 0 && env_int("FSGPU_MINILM_ARES_FFN_OUT", 0) != 0;
+
+    // Small batches (a query or a handful: <= 4096 token rows): the forward is bound by the host's 44 launch calls, so a
+    // captured graph of it is replayed; ids / lens / output go through fixed staging buffers.  FSGPU_MINILM_GRAPH=0: off.
+    bool use_graph = !e->profiling && rows <= 4096 && env_int("FSGPU_MINILM_GRAPH", 1) != 0;
+    if (use_graph) {  // a caller that is itself capturing this stream gets the plain launches in its graph
+        cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(s, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) {
+            cudaGetLastError();
+            use_graph = false;
+        }
+    }
+    if (!use_graph) {
+        int rc = minilm_fast_enqueue(e, d_ids, d_lens, batch, max_len, d_out, s, ares, ffn_out_pair);
+        if (rc) return rc;
+        if (sync) CUDA_TRY(cudaStreamSynchronize(s));
+        return FSGPU_OK;
+    }
+    CUDA_TRY(e->g_ids.reserve(4096 * 4));
+    CUDA_TRY(e->g_lens.reserve(4096 * 4));
+    CUDA_TRY(e->g_out.reserve((size_t)4096 * H * 4));
+    const uint64_t key = ((uint64_t)batch << 32) | ((uint64_t)max_len << 8) | (ares ? 1u : 0u) | (ffn_out_pair ? 2u : 0u);
+    const void* bufs[9] = {e->f_h.p, e->f_qkv.p, e->f_ctx.p, e->f_ffn.p, e->ws_pre32.p, e->ws_h32.p, e->g_ids.p, e->g_lens.p, e->g_out.p};
+    if (e->f_graphs.size() >= 64 && !e->f_graphs.count(key)) {  // bounded cache: shapes are few in practice
+        for (auto& kv : e->f_graphs)
+            if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+        e->f_graphs.clear();
+    }
+    fsgpu_minilm::FastGraph& fg = e->f_graphs[key];
+    if (fg.exec && memcmp(fg.bufs, bufs, sizeof(bufs)) != 0) {  // a buffer moved (grew): the captured pointers are stale
+        cudaGraphExecDestroy(fg.exec);
+        fg.exec = nullptr;
+    }
+    bool captured_now = false;
+    if (!fg.exec) {
+        captured_now = true;  // (the capture ran the launch sequence once: its counters already cover this call)
+        cudaGraph_t graph = nullptr;
+        CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        int rc = minilm_fast_enqueue(e, e->g_ids.as<int32_t>(), e->g_lens.as<int32_t>(), batch, max_len, e->g_out.as<float>(), s,
+                                     ares, ffn_out_pair);
+        cudaError_t ce = cudaStreamEndCapture(s, &graph);
+        if (rc || ce != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            return rc ? rc : fail(FSGPU_ERR_SUBSYSTEM, "gpu: minilm graph capture failed: %s", cudaGetErrorString(ce));
+        }
+        ce = cudaGraphInstantiate(&fg.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) {
+            fg.exec = nullptr;
+            return fail(FSGPU_ERR_SUBSYSTEM, "gpu: minilm graph instantiation failed: %s", cudaGetErrorString(ce));
+        }
+        memcpy(fg.bufs, bufs, sizeof(bufs));
+    }
+    CUDA_TRY(cudaMemcpyAsync(e->g_ids.p, d_ids, rows * 4, cudaMemcpyDeviceToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(e->g_lens.p, d_lens, (size_t)batch * 4, cudaMemcpyDeviceToDevice, s));
+    CUDA_TRY(cudaGraphLaunch(fg.exec, s));
+    CUDA_TRY(cudaMemcpyAsync(d_out, e->g_out.p, (size_t)batch * H * 4, cudaMemcpyDeviceToDevice, s));
+    if (!captured_now) {
+        e->prof.gemm_launches += 4 * e->n_layers;
+        e->prof.other_launches += 3 * e->n_layers + 2;
+    }
     if (sync) CUDA_TRY(cudaStreamSynchronize(s));
     return FSGPU_OK;
 }
