@@ -1,4 +1,4 @@
-//! Raw `extern "C"` bindings of `include/fsgpu.h` (ABI version 3) — the B200 semantic-tier hot
+//! Raw `extern "C"` bindings of `include/fsgpu.h` (ABI version 4) — the B200 semantic-tier hot
 //! path behind frankensearch's own seams.  Each item names the reference interface it replaces;
 //! see INTEGRATION.md for the safe wrapper (`GpuVectorIndex`) and the error mapping.
 #![allow(non_camel_case_types)]
@@ -9,7 +9,7 @@ use std::os::raw::{c_char, c_int, c_void};
 #[repr(C)] pub struct fsgpu_minilm { _private: [u8; 0] }
 #[repr(C)] pub struct fsgpu_sharded { _private: [u8; 0] }
 
-pub const FSGPU_ABI_VERSION: c_int = 3;
+pub const FSGPU_ABI_VERSION: c_int = 4;
 /// `fsgpu_index_options.flags`: this host replays the `<index>.wal` sidecar itself (VectorIndex::open,
 /// lib.rs:1833-1878) and hands the rows to `fsgpu_index_set_wal`.
 pub const FSGPU_OPEN_HOST_REPLAYS_WAL: i32 = 1;
@@ -163,6 +163,12 @@ extern "C" {
                                  n_lex_max: u32, d_sem_hits: *const fsgpu_hit, d_sem_tie: *const u32,
                                  d_sem_counts: *const u32, n_sem_max: u32, limit: u32, offset: u32,
                                  d_out: *mut fsgpu_fused_hit, d_out_counts: *mut u32, stream: *mut c_void) -> c_int;
+
+    // VectorIndex::search_top_k_int8_two_pass / search_top_k_4bit_two_pass with the reference's semantics
+    // (search.rs:514-650, :876-946): bits = 8 or 4
+    pub fn fsgpu_search_top_k_two_pass(index: *const fsgpu_index, query: *const f32, k: u32, candidate_multiplier: u32,
+                                       bits: c_int, dim: u32, out: *mut fsgpu_hit, out_count: *mut u32) -> c_int;
+    pub fn fsgpu_index_read_two_pass_codes(index: *const fsgpu_index, bits: c_int, out: *mut u8) -> c_int;
 
     // row-sharded index over the GPUs of one box, one process, no NCCL
     pub fn fsgpu_sharded_create_f16(slab: *const u16, n_rows: u64, dim: u32, tombstones: *const u8,

@@ -25,7 +25,7 @@ STATUS_NAMES = {
 }
 
 
-ABI_VERSION = 3  # FSGPU_ABI_VERSION of include/fsgpu.h this binding was written against
+ABI_VERSION = 4  # FSGPU_ABI_VERSION of include/fsgpu.h this binding was written against
 
 
 class SearchError(Exception):
@@ -113,6 +113,7 @@ EXPORTS = [
     "fsgpu_index_profile_read", "fsgpu_index_last_status", "fsgpu_measure_tensor_peak", "fsgpu_search_top_k", "fsgpu_search_top_k_device",
     "fsgpu_search_top_k_filtered", "fsgpu_search_top_k_filtered_device",
     "fsgpu_index_set_doc_hashes", "fsgpu_search_top_k_hashes",
+    "fsgpu_search_top_k_two_pass", "fsgpu_index_read_two_pass_codes",
     "fsgpu_merge_top_k_device", "fsgpu_merge_top_k_hits_device", "fsgpu_scores_for_rows", "fsgpu_scores_for_rows_device",
     "fsgpu_scores_for_hits_device", "fsgpu_merge_payload_device",
     "fsgpu_rrf_fuse", "fsgpu_rrf_fuse_device", "fsgpu_blend_two_tier", "fsgpu_blend_two_tier_device", "fsgpu_potion_create",
@@ -168,6 +169,8 @@ def lib() -> C.CDLL:
     L.fsgpu_search_top_k_hashes.argtypes = [_vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, _vp, C.c_uint32, _vp,
                                             _vp, _vp, C.POINTER(C.c_int)]
     L.fsgpu_index_zero_signal_state.argtypes = [_vp, _vp]
+    L.fsgpu_search_top_k_two_pass.argtypes = [_vp, _vp, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, _vp, _vp]
+    L.fsgpu_index_read_two_pass_codes.argtypes = [_vp, C.c_int, _vp]
     L.fsgpu_index_set_wal.argtypes = [_vp, _vp, C.c_uint32, C.c_uint64]
     L.fsgpu_index_wal_rows.argtypes = [_vp]
     L.fsgpu_index_wal_rows.restype = C.c_uint32

@@ -21,6 +21,7 @@
 #include "mma_scan_kernels.cuh"
 #include "scan_kernels.cuh"
 #include "select_kernels.cuh"
+#include "two_pass_kernels.cuh"
 #include "synth_kernels.cuh"
 
 using namespace fsgpu;
@@ -148,6 +149,10 @@ struct fsgpu_index {
     mutable DevBuf ws_approx, ws_i8_top, ws_i8_cnt;
     // large-k radix select (select_kernels.cuh): position lists and the two select states
     mutable DevBuf ws_sel_pos, ws_sel_pos2, ws_sel_state;
+    // the reference's quantised two-pass searches (two_pass_kernels.cuh): lazily built code slabs
+    mutable DevBuf d_tp_codes8, d_tp_codes4;
+    mutable bool tp8_ready = false, tp4_ready = false;
+    mutable float tp_max_abs = -1.0f;  // corpus-wide max |element| (ignoring NaN), -1 = not computed yet
     // launch accounting (guarded by mu)
     mutable bool profiling = false;
     mutable fsgpu_profile prof{};
@@ -1448,7 +1453,8 @@ extern "C" void fsgpu_index_destroy(fsgpu_index* ix) {
                           &ix->ws_cand_count, &ix->d_wal, &ix->ws_wal_main, &ix->ws_wal_keys, &ix->d_hashes,
                           &ix->ws_allowed, &ix->ws_gather_pos, &ix->ws_gather_count, &ix->ws_gather_keys,
                           &ix->d_slab_i8, &ix->ws_qscale, &ix->ws_approx, &ix->ws_i8_top, &ix->ws_i8_cnt,
-                          &ix->ws_sel_pos, &ix->ws_sel_pos2, &ix->ws_sel_state, &ix->ws_redo_slots, &ix->ws_redo_partial})
+                          &ix->ws_sel_pos, &ix->ws_sel_pos2, &ix->ws_sel_state, &ix->ws_redo_slots, &ix->ws_redo_partial,
+                          &ix->d_tp_codes8, &ix->d_tp_codes4})
             b->release();
         if (ix->stream) cudaStreamDestroy(ix->stream);
     }
@@ -1737,6 +1743,180 @@ extern "C" int fsgpu_search_top_k_filtered(const fsgpu_index* ix, const float* q
 extern "C" int fsgpu_search_top_k(const fsgpu_index* ix, const float* queries, uint32_t batch, uint32_t k,
                                   uint32_t dim, fsgpu_hit* out, uint32_t* out_counts) {
     return fsgpu_search_top_k_filtered(ix, queries, batch, k, dim, nullptr, out, out_counts);
+}
+
+// ─── the reference's quantised two-pass searches ────────────────────────────────────────────
+// largest |element| of the slab as f16 magnitude bits, NaN ignored (f32::max ignores NaN: simd.rs:1842-1846)
+__global__ void slab_max_abs_kernel(const uint16_t* __restrict__ slab, uint64_t n, uint32_t* __restrict__ out) {
+    uint32_t m = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t b = slab[i] & 0x7FFFu;
+        if (b <= 0x7C00u) m = max(m, b);
+    }
+    m = __reduce_max_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+static float f16_magnitude_to_f32(uint32_t hb) {
+    const uint32_t exp = (hb >> 10) & 0x1F, man = hb & 0x3FF;
+    if (exp == 31) return INFINITY;
+    return exp == 0 ? std::ldexp((float)man, -24) : std::ldexp((float)(man | 0x400), (int)exp - 25);
+}
+
+extern "C" int fsgpu_search_top_k_two_pass(const fsgpu_index* ix, const float* query, uint32_t k, uint32_t candidate_multiplier,
+                                           int bits, uint32_t dim, fsgpu_hit* out, uint32_t* out_count) {
+    using u64 = unsigned long long;
+    if (!ix) return fail(FSGPU_ERR_INVALID_CONFIG, "index is NULL");
+    if (bits != 8 && bits != 4) return fail(FSGPU_ERR_INVALID_CONFIG, "bits must be 8 or 4, got %d", bits);
+    if (!out_count) return fail(FSGPU_ERR_INVALID_CONFIG, "out_count is NULL");
+    // the reference's gate (search.rs:578-586, :882-890): k == 0, an empty index, resident WAL rows or a slab that is
+    // not f16 take the exact search (which also reports the dimension mismatch); so does a k the select cannot hold
+    if (k == 0 || ix->n_rows == 0 || ix->n_wal > 0 || ix->d_slab_f32 || k > kSelMaxK || ix->n_rows >= 0xFFFFFFFFull)
+        return fsgpu_search_top_k(ix, query, 1, k, dim, out, out_count);
+    if (dim != ix->dim) return fail(FSGPU_ERR_DIMENSION_MISMATCH, "expected %u, found %u", ix->dim, dim);
+    if (!query || !out) return fail(FSGPU_ERR_INVALID_CONFIG, "NULL argument");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t s = ix->stream;
+    int rc = begin_call_locked(ix, s, true);
+    if (rc) return rc;
+    const uint64_t n = ix->n_rows;
+    // corpus-wide scale (once per index)
+    if (ix->tp_max_abs < 0.0f) {
+        CUDA_TRY(ix->ws_sel_state.reserve(2 * sizeof(SelState)));
+        CUDA_TRY(cudaMemsetAsync(ix->ws_sel_state.p, 0, 4, s));
+        slab_max_abs_kernel<<<ix->num_sms * 8, 256, 0, s>>>(ix->d_slab, n * dim, ix->ws_sel_state.as<uint32_t>());
+        CUDA_TRY(cudaGetLastError());
+        uint32_t hb = 0;
+        CUDA_TRY(cudaMemcpyAsync(&hb, ix->ws_sel_state.p, 4, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        ix->tp_max_abs = f16_magnitude_to_f32(hb);
+    }
+    const float max_abs = ix->tp_max_abs;
+    const uint32_t row_bytes = bits == 8 ? dim : (dim + 1u) / 2u;
+    const uint8_t* codes = nullptr;
+    if (bits == 8) {
+        if (ix->i8_ok) {
+            codes = ix->d_slab_i8.as<uint8_t>();  // the index's resident codes are the same quantiser's (simd.rs:1842-1859)
+        } else {
+            if (!ix->tp8_ready) {
+                CUDA_TRY(ix->d_tp_codes8.reserve(n * dim));
+                if (max_abs <= 0.0f) {
+                    CUDA_TRY(cudaMemsetAsync(ix->d_tp_codes8.p, 0, n * dim, s));
+                } else {
+                    quantize_slab_i8_any_kernel<<<ix->num_sms * 8, 256, 0, s>>>(ix->d_slab, n * dim, 127.0f / max_abs,
+                                                                               ix->d_tp_codes8.as<int8_t>());
+                    CUDA_TRY(cudaGetLastError());
+                }
+                ix->tp8_ready = true;
+            }
+            codes = ix->d_tp_codes8.as<uint8_t>();
+        }
+    } else {
+        if (!ix->tp4_ready) {
+            CUDA_TRY(ix->d_tp_codes4.reserve(n * row_bytes));
+            const float scale = max_abs > 1e-9f ? 7.0f / max_abs : 0.0f;  // simd.rs:2211
+            pack_slab_4bit_kernel<<<ix->num_sms * 8, 256, 0, s>>>(ix->d_slab, n, dim, scale, ix->d_tp_codes4.as<uint8_t>());
+            CUDA_TRY(cudaGetLastError());
+            ix->tp4_ready = true;
+        }
+        codes = ix->d_tp_codes4.as<uint8_t>();
+    }
+    // the query's own codes (search.rs:1610-1655), on the host: `dim` values
+    const uint32_t pad = (row_bytes + 15u) & ~15u;
+    std::vector<int8_t> qc(2 * (size_t)pad, 0);
+    float q_max = 0.0f;
+    for (uint32_t i = 0; i < dim; ++i) q_max = std::fmax(q_max, std::fabs(query[i]));  // f32::max: NaN is ignored
+    if (bits == 8) {
+        if (q_max > 0.0f) {
+            const float scale = 127.0f / q_max;
+            for (uint32_t i = 0; i < dim; ++i) {
+                const float v = std::fmin(std::fmax(std::round(query[i] * scale), -127.0f), 127.0f);
+                qc[i] = (int8_t)(std::isnan(v) ? 0 : (int)v);  // `NaN as i8` is 0 in Rust
+            }
+        }
+    } else {
+        const float scale = q_max > 1e-9f ? 7.0f / q_max : 0.0f;
+        for (uint32_t i = 0; i < dim; ++i) {
+            const float v = std::fmin(std::fmax(std::round(query[i] * scale), -7.0f), 7.0f);
+            const int8_t c = (int8_t)(std::isnan(v) ? 0 : (int)v);
+            (i % 2 == 0 ? qc[i / 2] : qc[pad + i / 2]) = c;
+        }
+    }
+    CUDA_TRY(ix->ws_queries.reserve((size_t)dim * 4));
+    CUDA_TRY(ix->ws_qhat.reserve(2 * (size_t)pad));
+    CUDA_TRY(ix->ws_hits.reserve((size_t)k * sizeof(fsgpu_hit)));
+    CUDA_TRY(ix->ws_counts.reserve(4));
+    CUDA_TRY(ix->ws_sel_state.reserve(2 * sizeof(SelState)));
+    CUDA_TRY(ix->ws_sort_a.reserve(n * 8));
+    CUDA_TRY(ix->ws_sel_pos.reserve(n * 4));
+    CUDA_TRY(ix->ws_sel_pos2.reserve((size_t)kSelMaxK * 4));
+    CUDA_TRY(cudaMemcpyAsync(ix->ws_queries.p, query, (size_t)dim * 4, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(ix->ws_qhat.p, qc.data(), qc.size(), cudaMemcpyHostToDevice, s));
+    SelState* st0 = ix->ws_sel_state.as<SelState>();
+    SelState* st1 = st0 + 1;
+    uint32_t* n1 = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(st0) + offsetof(SelState, n_out));
+    uint32_t* n2 = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(st1) + offsetof(SelState, n_out));
+    CUDA_TRY(cudaMemsetAsync(st0, 0, 2 * sizeof(SelState), s));
+    u64* keys = ix->ws_sort_a.as<u64>();
+    const float* q = ix->ws_queries.as<float>();
+    // candidate_count (search.rs:596-599): k * max(multiplier, 1), at most the record count, at least min(k, count)
+    const uint64_t want = (uint64_t)k * std::max<uint32_t>(candidate_multiplier, 1u);
+    const uint32_t cand = (uint32_t)std::max<uint64_t>(std::min<uint64_t>(want, n), std::min<uint64_t>(k, n));
+    // pass 1: integer score of every live row as an order key, then the best `cand` of them
+    const int scan_grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((n + 31) / 32, (uint64_t)ix->num_sms * 8));
+    const int8_t* qa = ix->ws_qhat.as<int8_t>();
+    if (bits == 8)
+        two_pass_scan_kernel<8><<<scan_grid, 256, 2 * pad, s>>>(codes, row_bytes, ix->d_tomb, qa, qa + pad, n, ix->row_base, keys);
+    else
+        two_pass_scan_kernel<4><<<scan_grid, 256, 2 * pad, s>>>(codes, row_bytes, ix->d_tomb, qa, qa + pad, n, ix->row_base, keys);
+    CUDA_TRY(cudaGetLastError());
+    ix->prof.scan_launches += 1;
+    ix->prof.scan_bytes += n * row_bytes;
+    const int wide_grid = (int)std::max<uint64_t>(1, std::min<uint64_t>((n + 2047) / 2048, (uint64_t)ix->num_sms * 8));
+    for (int p = 0; p < SelTraits<u64>::kPasses; ++p) sel_hist_kernel<u64><<<wide_grid, 256, 0, s>>>(keys, n, nullptr, st0, p, cand);
+    sel_compact_kernel<u64><<<wide_grid, 256, 0, s>>>(keys, n, nullptr, st0, nullptr, nullptr, ix->ws_sel_pos.as<uint32_t>(),
+                                                      (uint32_t)n, n1);
+    // pass 2: exact f16 re-score of exactly those rows (search.rs:629-640), top k by the reference's total order
+    gather_list_keys_kernel<<<ix->num_sms * 4, 256, (size_t)dim * 4, s>>>(ix->d_slab, ix->row_base, dim, q, ix->ws_sel_pos.as<uint32_t>(),
+                                                                         n1, ix->reduce_order, ix->tail_fma, keys);
+    CUDA_TRY(cudaGetLastError());
+    for (int p = 0; p < SelTraits<u64>::kPasses; ++p) sel_hist_kernel<u64><<<ix->num_sms, 256, 0, s>>>(keys, n, n1, st1, p, k);
+    sel_compact_kernel<u64><<<ix->num_sms, 256, 0, s>>>(keys, n, n1, st1, nullptr, nullptr, ix->ws_sel_pos2.as<uint32_t>(), kSelMaxK, n2);
+    CUDA_TRY(cudaFuncSetAttribute(sel_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSelMaxK * 8)));
+    sel_emit_kernel<<<1, 1024, kSelMaxK * 8, s>>>(keys, ix->ws_sel_pos2.as<uint32_t>(), n2, k, ix->slab_any(), ix->is_f32(), q, n, ix->row_base,
+                                                  dim, ix->reduce_order, ix->tail_fma, nullptr, ix->ws_hits.as<fsgpu_hit>(),
+                                                  ix->ws_counts.as<uint32_t>(), ix->d_error);
+    CUDA_TRY(cudaGetLastError());
+    ix->prof.other_launches += 17;
+    CUDA_TRY(cudaMemcpyAsync(out, ix->ws_hits.p, (size_t)k * sizeof(fsgpu_hit), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(out_count, ix->ws_counts.p, 4, cudaMemcpyDeviceToHost, s));
+    rc = end_call_locked(ix, s);
+    if (rc) return rc;
+    return finish_sync_call_locked(ix, s, nullptr);
+}
+
+// code slabs of the two-pass searches, for parity tests against the reference quantisers (host buffer of
+// n_rows * dim bytes for bits = 8, n_rows * ceil(dim / 2) for bits = 4); builds them if needed
+extern "C" int fsgpu_index_read_two_pass_codes(const fsgpu_index* ix, int bits, uint8_t* out) {
+    if (!ix || !out || (bits != 8 && bits != 4)) return fail(FSGPU_ERR_INVALID_CONFIG, "bad argument");
+    if (ix->n_rows == 0) return FSGPU_OK;
+    if (ix->d_slab_f32) return fail(FSGPU_ERR_INVALID_CONFIG, "f32-quantised slab: no two-pass codes");
+    std::vector<float> q(ix->dim, 0.0f);
+    fsgpu_hit h;
+    uint32_t c = 0;
+    if (ix->n_wal == 0) {
+        int rc = fsgpu_search_top_k_two_pass(ix, q.data(), 1, 1, bits, ix->dim, &h, &c);  // builds the slab as a side effect
+        if (rc) return rc;
+    }
+    std::lock_guard<std::mutex> lock(ix->mu);
+    DeviceGuard g(ix->device);
+    const size_t bytes = ix->n_rows * (bits == 8 ? (size_t)ix->dim : ((size_t)ix->dim + 1) / 2);
+    const void* src = bits == 8 ? (ix->i8_ok ? ix->d_slab_i8.p : (ix->tp8_ready ? ix->d_tp_codes8.p : nullptr))
+                                : (ix->tp4_ready ? ix->d_tp_codes4.p : nullptr);
+    if (!src) return fail(FSGPU_ERR_INVALID_CONFIG, "two-pass codes are not built (resident WAL rows?)");
+    CUDA_TRY(cudaMemcpy(out, src, bytes, cudaMemcpyDeviceToHost));
+    return FSGPU_OK;
 }
 
 // ─── filtered search ────────────────────────────────────────────────────────────────────────

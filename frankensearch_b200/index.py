@@ -400,6 +400,34 @@ class GpuVectorIndex:
             hits = out
         return hits
 
+    def _search_two_pass(self, query, k: int, candidate_multiplier: int, bits: int) -> List[VectorHit]:
+        q = np.ascontiguousarray(query, dtype=np.float32).reshape(-1)
+        if self._wal:  # the reference's gate (search.rs:578-586): resident WAL rows take the exact search
+            return self.search_top_k(q, k)
+        hits = np.zeros((max(int(k), 1), 2), dtype=np.uint32)
+        count = np.zeros(1, dtype=np.uint32)
+        check(self._L.fsgpu_search_top_k_two_pass(self._h, ptr(q), int(k), int(candidate_multiplier), bits, q.size, ptr(hits),
+                                                 ptr(count)))
+        n = int(count[0])
+        scores = hits[:, 1].view(np.float32)
+        return [VectorHit(int(hits[i, 0]), float(scores[i]), self.doc_id_at(int(hits[i, 0]))) for i in range(n)]
+
+    def search_top_k_int8_two_pass(self, query, k: int, candidate_multiplier: int) -> List[VectorHit]:
+        """VectorIndex::search_top_k_int8_two_pass (search.rs:514-650): integer pass 1 over the corpus-wide int8 codes keeps
+        `k * candidate_multiplier` rows, exact f16 pass 2 keeps k — the reference's result for every multiplier."""
+        return self._search_two_pass(query, k, candidate_multiplier, 8)
+
+    def search_top_k_4bit_two_pass(self, query, k: int, candidate_multiplier: int) -> List[VectorHit]:
+        """VectorIndex::search_top_k_4bit_two_pass (search.rs:876-946): the same over signed 4-bit nibbles."""
+        return self._search_two_pass(query, k, candidate_multiplier, 4)
+
+    def two_pass_codes(self, bits: int) -> np.ndarray:
+        """The code slab those searches scan: [rows, dim] int8 or [rows, ceil(dim / 2)] packed nibbles."""
+        n, d = self.record_count(), self.dimension()
+        out = np.zeros((n, d if bits == 8 else (d + 1) // 2), dtype=np.uint8)
+        check(self._L.fsgpu_index_read_two_pass_codes(self._h, bits, ptr(out)))
+        return out.view(np.int8) if bits == 8 else out
+
     def zero_signal_state(self) -> ZeroSignalState:
         """VectorIndex::zero_signal_state (lib.rs:2441-2459): one census pass on the device."""
         out = np.zeros(5, dtype=np.uint64)

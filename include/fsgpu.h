@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define FSGPU_ABI_VERSION 3
+#define FSGPU_ABI_VERSION 4
 
 typedef enum fsgpu_status {
     FSGPU_OK = 0,
@@ -244,6 +244,23 @@ int fsgpu_search_top_k_filtered(const fsgpu_index* index, const float* queries, 
 int fsgpu_search_top_k_filtered_device(const fsgpu_index* index, const float* d_queries, uint32_t batch,
                                        uint32_t k, const uint8_t* d_allow_bitmap, uint64_t* d_out_keys,
                                        fsgpu_hit* d_out_hits, uint32_t* d_out_counts, void* stream);
+
+/* The reference's QUANTISED TWO-PASS searches with their own semantics — VectorIndex::search_top_k_int8_two_pass
+ * (crates/frankensearch-index/src/search.rs:514-650; TwoTierIndex::search_fast calls it with multiplier 3,
+ * two_tier.rs:1323-1342) and search_top_k_4bit_two_pass (search.rs:876-946).  `bits` = 8 or 4.  Pass 1 ranks every
+ * live row by the INTEGER dot of corpus-wide-scaled codes (simd.rs:1842-1859 / :2201-2233) with the query's own codes
+ * (search.rs:1610-1655) and keeps the best max(min(k * max(multiplier, 1), rows), min(k, rows)) by (score, lower
+ * row); pass 2 re-scores exactly those rows with the f16 kernel and returns the top k.  A row outside the candidate
+ * set is lost, as in the reference — the result is bit-identical to the reference's for every multiplier (all pass-1
+ * quantities are exact integers), and equal to fsgpu_search_top_k whenever the reference's own recall is 1.  k == 0, an
+ * empty index, resident WAL rows or an f32-quantised slab take the exact search (search.rs:578-586); so does
+ * k > 4096.  One query, host pointers, synchronous.  The code slab of the chosen width is built on first use
+ * (nibbles_slab / int8_slab, search.rs:840-858, :986-998); an index created with int8_codes = 1 and dim % 128 == 0
+ * shares its resident int8 codes. */
+int fsgpu_search_top_k_two_pass(const fsgpu_index* index, const float* query, uint32_t k, uint32_t candidate_multiplier,
+                                int bits, uint32_t dim, fsgpu_hit* out, uint32_t* out_count);
+/* The code slab those searches scan (tests: byte-identical to the reference quantisers). */
+int fsgpu_index_read_two_pass_codes(const fsgpu_index* index, int bits, uint8_t* out);
 
 /* Doc-id-hash filters evaluated on the device.  `fsgpu_index_set_doc_hashes` gives the index the
  * 8-byte FNV-1a doc-id hash of every local row (record-table field 0, lib.rs:130-174, :6120-6127);

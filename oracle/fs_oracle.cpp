@@ -439,6 +439,115 @@ FSO_API uint64_t fso_search_top_k(const uint16_t* slab, uint64_t n, uint32_t dim
     return out_n;
 }
 
+// ─── quantised two-pass searches ────────────────────────────────────────────────────────────
+// quantize_f16_slab_to_i8_generic (crates/frankensearch-index/src/simd.rs:1842-1859): one corpus-wide scale
+// 127 / max|x| (f32::max ignores NaN), round half away, clamp, `as i8`.
+FSO_API void fso_quantize_slab_i8(const uint16_t* slab, uint64_t n_elems, int8_t* out) {
+    float max_abs = 0.0f;
+    for (uint64_t i = 0; i < n_elems; ++i) {
+        const float a = std::fabs(f16_bits_to_f32(slab[i]));
+        if (a > max_abs) max_abs = a;  // NaN compares false: ignored, as f32::max does
+    }
+    if (max_abs <= 0.0f) {
+        memset(out, 0, n_elems);
+        return;
+    }
+    const float scale = 127.0f / max_abs;
+    for (uint64_t i = 0; i < n_elems; ++i) {
+        const float v = std::fmin(std::fmax(std::round(f16_bits_to_f32(slab[i]) * scale), -127.0f), 127.0f);
+        out[i] = (int8_t)(std::isnan(v) ? 0 : (int)v);
+    }
+}
+// pack_f16_slab_to_4bit_generic (simd.rs:2201-2233): scale 7 / max|x| (0 when max|x| <= 1e-9), nibble_of_4bit
+// (simd.rs:1892-1896), byte j = dims 2j (low nibble) | 2j + 1 (high nibble), ceil(dim / 2) bytes per vector.
+static inline uint8_t nibble_of(float value, float scale) {
+    const float v = std::fmin(std::fmax(std::round(value * scale), -7.0f), 7.0f);
+    return (uint8_t)((int8_t)(std::isnan(v) ? 0 : (int)v)) & 0x0F;
+}
+FSO_API void fso_pack_slab_4bit(const uint16_t* slab, uint64_t n_rows, uint32_t dim, uint8_t* out) {
+    if (dim == 0) return;
+    float max_abs = 0.0f;
+    for (uint64_t i = 0; i < n_rows * dim; ++i) {
+        const float a = std::fabs(f16_bits_to_f32(slab[i]));
+        if (a > max_abs) max_abs = a;
+    }
+    const float scale = max_abs > 1e-9f ? 7.0f / max_abs : 0.0f;
+    const uint32_t bpv = (dim + 1) / 2;
+    memset(out, 0, n_rows * bpv);
+    for (uint64_t v = 0; v < n_rows; ++v)
+        for (uint32_t d = 0; d < dim; ++d) {
+            const uint8_t nib = nibble_of(f16_bits_to_f32(slab[v * dim + d]), scale);
+            out[v * bpv + d / 2] |= (d % 2 == 0) ? nib : (uint8_t)(nib << 4);
+        }
+}
+// VectorIndex::search_top_k_int8_two_pass / search_top_k_4bit_two_pass (search.rs:571-650, :876-946) on a slab without
+// WAL rows: candidate_count = max(min(k * max(mult, 1), n), min(k, n)); pass 1 = integer dot of the codes with the
+// query's own codes (quantize_i8_query search.rs:1610-1622, pack_4bit_query :1640-1655; dot_i8_i8 / dot_4bit_prepared are
+// exact integers), ranked by (score as f32 under score_key, lower index) — the heap keys of search.rs:141-156 and
+// HeapEntry order agree (int8_heap_keys_match_legacy_score_and_index_order, search.rs:3112); pass 2 = exact f16 dot of
+// the candidates, top k by the same total order.  Returns the number of hits.
+FSO_API uint64_t fso_search_two_pass(const uint16_t* slab, uint64_t n, uint32_t dim, const uint8_t* tombstones,
+                                     const float* query, uint64_t k, uint64_t mult, int bits, int reduce_order,
+                                     int tail_fma, uint64_t* out_rows, float* out_scores) {
+    if (k == 0 || n == 0) return 0;
+    const uint64_t want = k * std::max<uint64_t>(mult, 1);
+    const uint64_t cand = std::max(std::min(want, n), std::min(k, n));
+    float q_max = 0.0f;
+    for (uint32_t i = 0; i < dim; ++i) {
+        const float a = std::fabs(query[i]);
+        if (a > q_max) q_max = a;
+    }
+    std::vector<int> qc(dim, 0);
+    std::vector<Entry> all;
+    all.reserve(n);
+    if (bits == 8) {
+        std::vector<int8_t> codes(n * dim);
+        fso_quantize_slab_i8(slab, n * dim, codes.data());
+        if (q_max > 0.0f) {
+            const float scale = 127.0f / q_max;
+            for (uint32_t i = 0; i < dim; ++i) {
+                const float v = std::fmin(std::fmax(std::round(query[i] * scale), -127.0f), 127.0f);
+                qc[i] = std::isnan(v) ? 0 : (int)v;
+            }
+        }
+        for (uint64_t r = 0; r < n; ++r) {
+            if (tombstoned(tombstones, r)) continue;
+            int32_t acc = 0;
+            for (uint32_t i = 0; i < dim; ++i) acc += (int32_t)codes[r * dim + i] * qc[i];
+            all.push_back(Entry{r, (float)acc});
+        }
+    } else {
+        const uint32_t bpv = (dim + 1) / 2;
+        std::vector<uint8_t> codes(n * bpv);
+        fso_pack_slab_4bit(slab, n, dim, codes.data());
+        const float scale = q_max > 1e-9f ? 7.0f / q_max : 0.0f;
+        for (uint32_t i = 0; i < dim; ++i) {
+            const uint8_t nib = nibble_of(query[i], scale);
+            qc[i] = (int)(int8_t)(nib << 4) >> 4;  // sign-extended nibble
+        }
+        for (uint64_t r = 0; r < n; ++r) {
+            if (tombstoned(tombstones, r)) continue;
+            int32_t acc = 0;
+            for (uint32_t i = 0; i < dim; ++i) {
+                const uint8_t b = codes[r * bpv + i / 2];
+                const int x = (i % 2 == 0) ? ((int)(int8_t)(b << 4) >> 4) : ((int)(int8_t)(b & 0xF0) >> 4);
+                acc += x * qc[i];
+            }
+            all.push_back(Entry{r, (float)acc});
+        }
+    }
+    std::sort(all.begin(), all.end(), best_first_less);
+    if (all.size() > cand) all.resize(cand);
+    for (Entry& e : all) e.score = dot_fast(slab + e.index * dim, query, dim, reduce_order, tail_fma);
+    std::sort(all.begin(), all.end(), best_first_less);
+    const uint64_t out_n = std::min<uint64_t>(all.size(), k);
+    for (uint64_t i = 0; i < out_n; ++i) {
+        out_rows[i] = all[i].index;
+        out_scores[i] = all[i].score;
+    }
+    return out_n;
+}
+
 FSO_API float fso_dot_f32_f32(const float* a, const float* b, uint32_t dim, int reduce_order) {
     return dot_f32_f32_scalar(a, b, dim, reduce_order);
 }

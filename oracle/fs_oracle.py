@@ -70,6 +70,11 @@ def _declare(L: C.CDLL) -> None:
     L.fso_search_top_k.argtypes = [_u16p, C.c_uint64, C.c_uint32, _u8p, _f32p, C.c_uint64, C.c_int,
                                    C.c_int, C.c_int, _u64p, _f32p]
     L.fso_search_top_k.restype = C.c_uint64
+    L.fso_quantize_slab_i8.argtypes = [_u16p, C.c_uint64, C.c_void_p]
+    L.fso_pack_slab_4bit.argtypes = [_u16p, C.c_uint64, C.c_uint32, _u8p]
+    L.fso_search_two_pass.argtypes = [_u16p, C.c_uint64, C.c_uint32, _u8p, _f32p, C.c_uint64, C.c_uint64, C.c_int,
+                                      C.c_int, C.c_int, _u64p, _f32p]
+    L.fso_search_two_pass.restype = C.c_uint64
     L.fso_scores_for_rows.argtypes = [_u16p, C.c_uint64, C.c_uint32, _f32p, _u64p, C.c_uint64,
                                       C.c_int, C.c_int, _f32p, _u8p]
     L.fso_fnv1a64.argtypes = [_u8p, C.c_uint64]
@@ -152,6 +157,38 @@ def search_top_k(slab_bits, query, limit: int, tombstones: Optional[np.ndarray] 
                                  int(limit), threads or host_threads(), reduce_order, int(tail_fma),
                                  _p(rows, _u64p), _p(scores, _f32p))
     return rows[:got].copy(), scores[:got].copy()
+
+
+def quantize_slab_i8(slab_bits) -> np.ndarray:
+    """quantize_f16_slab_to_i8_generic (simd.rs:1842-1859): [rows, dim] f16 bits -> int8 codes of the same shape."""
+    s = _c(slab_bits, np.uint16)
+    out = np.zeros(s.shape, dtype=np.int8)
+    lib().fso_quantize_slab_i8(_p(s, _u16p), s.size, out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def pack_slab_4bit(slab_bits) -> np.ndarray:
+    """pack_f16_slab_to_4bit_generic (simd.rs:2201-2233): [rows, dim] f16 bits -> [rows, ceil(dim / 2)] nibble bytes."""
+    s = _c(slab_bits, np.uint16)
+    n, dim = s.shape
+    out = np.zeros((n, (dim + 1) // 2), dtype=np.uint8)
+    lib().fso_pack_slab_4bit(_p(s, _u16p), n, dim, _p(out, _u8p))
+    return out
+
+
+def search_two_pass(slab_bits, query, k: int, candidate_multiplier: int, bits: int, tombstones: Optional[np.ndarray] = None,
+                    reduce_order: int = DEFAULT_REDUCE, tail_fma: bool = True):
+    """search_top_k_int8_two_pass (bits = 8, search.rs:571-650) / search_top_k_4bit_two_pass (bits = 4, :876-946) on a
+    slab without WAL rows.  Returns (rows u64, scores f32)."""
+    s = _c(slab_bits, np.uint16)
+    n, dim = s.shape
+    q = _c(query, np.float32)
+    rows = np.zeros(max(min(k, n), 1), dtype=np.uint64)
+    scores = np.zeros(max(min(k, n), 1), dtype=np.float32)
+    tb = pack_bitmap(tombstones) if tombstones is not None else None
+    got = lib().fso_search_two_pass(_p(s, _u16p), n, dim, _p(tb, _u8p), _p(q, _f32p), k, candidate_multiplier, bits,
+                                    reduce_order, 1 if tail_fma else 0, _p(rows, _u64p), _p(scores, _f32p))
+    return rows[:got], scores[:got]
 
 
 def dot_f32_f32(a, b, reduce_order: int = DEFAULT_REDUCE) -> np.float32:

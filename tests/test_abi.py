@@ -25,7 +25,7 @@ def test_header_symbols_are_exported():
     for s in syms:
         assert hasattr(L, s), f"{s} declared in include/fsgpu.h but not exported by libfsgpu.so"
     assert sorted(_ffi.EXPORTS) == syms, "frankensearch_b200/_ffi.py EXPORTS is out of date"
-    assert L.fsgpu_abi_version() == _ffi.ABI_VERSION == 3
+    assert L.fsgpu_abi_version() == _ffi.ABI_VERSION == 4
 
 
 def test_struct_layouts_match_header():
