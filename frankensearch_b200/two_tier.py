@@ -5,9 +5,10 @@ an optional quality tier over the same documents, with the method set the search
 
 The reference's default `search_fast` is `search_top_k_int8_two_pass(query, k, 3)` — an int8 pass that
 nominates `3k` rows for an exact f16 re-score — "candidate-lossless" by measurement
-(two_tier.rs:1323-1342).  The GPU fast tier returns the EXACT top-k (its own int8 forms are exact by a
+(two_tier.rs:1323-1342).  By default the GPU fast tier returns the EXACT top-k (its own int8 forms are exact by a
 proven bound), i.e. what that two-pass returns whenever its recall is 1, and what an
-explicit `SearchParams` (exact scan) returns always.  ANN and MRL dispatch are out of scope.
+explicit `SearchParams` (exact scan) returns always; `reference_two_pass=True` runs the reference's two-pass itself
+(fsgpu_search_top_k_two_pass).  ANN and MRL dispatch are out of scope.
 """
 from __future__ import annotations
 
@@ -21,9 +22,14 @@ from .types import ClassifiedHits, VectorHit, ZeroSignalReason
 
 
 class GpuTwoTierIndex:
-    def __init__(self, fast: GpuVectorIndex, quality: Optional[GpuVectorIndex] = None, *, alignment=None):
+    def __init__(self, fast: GpuVectorIndex, quality: Optional[GpuVectorIndex] = None, *, alignment=None,
+                 reference_two_pass: bool = False):
         self._fast = fast
         self._quality = quality
+        # True: `search_fast` without params is the reference's literal default, the int8 two-pass with multiplier 3
+        # (two_tier.rs:1323-1342) — its candidate set bit for bit, rows lost to the multiplier included.  False
+        # (default): the exact top-k, i.e. what that two-pass returns whenever its recall is 1.
+        self._reference_two_pass = reference_two_pass
         self._alignment = alignment  # fast row -> quality row (two_tier.rs:404-409); None = `Aligned`
         self._last_zero_signal: Optional[str] = None
 
@@ -39,12 +45,17 @@ class GpuTwoTierIndex:
     def doc_count(self) -> int:
         return self._fast.record_count()
 
+    FAST_TIER_MULT = 3  # two_tier.rs:1333
+
     def search_fast(self, query_vec, k: int) -> List[VectorHit]:
         """two_tier.rs:1262-1264."""
-        return self._fast.search_top_k(query_vec, k)
+        return self.search_fast_with_params(query_vec, k, None)
 
     def search_fast_with_params(self, query_vec, k: int, params=None) -> List[VectorHit]:
-        """two_tier.rs:1275-1343: `params` selects the exact scan on the CPU; here every form is exact."""
+        """two_tier.rs:1275-1343: explicit `params` select the exact scan; without them the reference runs
+        `search_top_k_int8_two_pass(query, k, 3)` — reproduced literally when `reference_two_pass` is set."""
+        if params is None and self._reference_two_pass:
+            return self._fast.search_top_k_int8_two_pass(query_vec, k, self.FAST_TIER_MULT)
         return self._fast.search_top_k(query_vec, k)
 
     def search_fast_classified(self, query_vec, k: int) -> ClassifiedHits:

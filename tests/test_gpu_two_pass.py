@@ -97,3 +97,20 @@ def test_two_pass_one_million_rows(fs):
         for bits, mult in ((8, 3), (4, 5)):
             same(run(ix, q, 10, mult, bits), fo.search_two_pass(slab, q, 10, mult, bits))
     ix.close()
+
+
+def test_two_tier_search_fast_reference_default(fs):
+    """TwoTierIndex::search_fast without params = search_top_k_int8_two_pass(query, k, 3) (two_tier.rs:1323-1342):
+    reproduced literally with reference_two_pass=True; the default mirror returns the exact top-k."""
+    rng = np.random.default_rng(21)
+    x = rng.standard_normal((5000, 64)).astype(np.float32)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    slab = fo.encode_f16(x)
+    fast = fs.GpuVectorIndex.from_f16_bits(None, slab)
+    q = rng.standard_normal(64).astype(np.float32)
+    lit = fs.GpuTwoTierIndex(fast, reference_two_pass=True).search_fast(q, 10)
+    want = fo.search_two_pass(slab, q, 10, 3, 8)
+    assert [h.index for h in lit] == [int(r) for r in want[0]]
+    exact = fs.GpuTwoTierIndex(fast).search_fast(q, 10)
+    assert [h.index for h in exact] == [int(r) for r in fo.search_top_k(slab, q, 10)[0]]
+    fast.close()
