@@ -162,6 +162,11 @@ struct fsgpu_index {
     std::vector<uint64_t> doc_off;
 };
 
+// Dynamic shared memory of the kernels that stage one f32 query: rounded up with a spare vector, because the
+// compiler may fetch the scalar tail of warp_exact_dot (dim % 8 != 0) as one 12- or 16-byte load that reaches a few
+// bytes past element dim - 1 (compute-sanitizer: benign but out of bounds at dim = 70).
+static inline size_t query_smem_bytes(uint32_t dim) { return (((size_t)dim * 4 + 15) & ~(size_t)15) + 16; }
+
 // ─── launch planning ────────────────────────────────────────────────────────────────────────
 constexpr uint32_t kFusedMaxK = 1024;
 
@@ -272,7 +277,7 @@ static int search_exact_locked(const fsgpu_index* ix, const float* d_queries, ui
         const uint32_t k_eff = (uint32_t)std::min<uint64_t>(k, n);
         const int grid = (int)std::min<uint64_t>((n + kScanWarps - 1) / kScanWarps, (uint64_t)ix->num_sms * 8);
         for (uint32_t b = 0; b < batch; ++b) {
-            score_all_kernel<<<grid, kScanThreads, (size_t)ix->dim * 4, stream>>>(
+            score_all_kernel<<<grid, kScanThreads, query_smem_bytes(ix->dim), stream>>>(
                 ix->slab_any(), ix->is_f32(), ix->d_excl ? ix->d_excl : ix->d_tomb, n, ix->row_base, ix->dim, d_queries + (size_t)b * ix->dim,
                 ix->reduce_order, ix->tail_fma, ix->ws_sort_a.as<uint64_t>());
             CUDA_TRY(cudaGetLastError());
@@ -1213,14 +1218,14 @@ static int search_select_locked(const fsgpu_index* ix, const float* d_queries, u
             sel_compact_kernel<uint32_t><<<wide_grid, 256, 0, stream>>>(ix->ws_approx.as<uint32_t>(), n, nullptr, st0,
                                                                         ix->ws_margin.as<float>(), ix->ws_redo.as<uint32_t>(),
                                                                         ix->ws_sel_pos.as<uint32_t>(), (uint32_t)n, n1);
-            gather_list_keys_kernel<<<ix->num_sms * 4, 256, (size_t)ix->dim * 4, stream>>>(
+            gather_list_keys_kernel<<<ix->num_sms * 4, 256, query_smem_bytes(ix->dim), stream>>>(
                 ix->d_slab, ix->row_base, ix->dim, q, ix->ws_sel_pos.as<uint32_t>(), n1, ix->reduce_order, ix->tail_fma, keys);
             CUDA_TRY(cudaGetLastError());
             n_exact = n1;
             ix->prof.other_launches += 6;
         } else {
             const int grid = (int)std::min<uint64_t>((n + kScanWarps - 1) / kScanWarps, (uint64_t)ix->num_sms * 8);
-            score_all_kernel<<<grid, kScanThreads, (size_t)ix->dim * 4, stream>>>(ix->slab_any(), ix->is_f32(), tomb, n, ix->row_base, ix->dim, q,
+            score_all_kernel<<<grid, kScanThreads, query_smem_bytes(ix->dim), stream>>>(ix->slab_any(), ix->is_f32(), tomb, n, ix->row_base, ix->dim, q,
                                                                                  ix->reduce_order, ix->tail_fma,
                                                                                  reinterpret_cast<uint64_t*>(keys));
             CUDA_TRY(cudaGetLastError());
@@ -1878,7 +1883,7 @@ extern "C" int fsgpu_search_top_k_two_pass(const fsgpu_index* ix, const float* q
     sel_compact_kernel<u64><<<wide_grid, 256, 0, s>>>(keys, n, nullptr, st0, nullptr, nullptr, ix->ws_sel_pos.as<uint32_t>(),
                                                       (uint32_t)n, n1);
     // pass 2: exact f16 re-score of exactly those rows (search.rs:629-640), top k by the reference's total order
-    gather_list_keys_kernel<<<ix->num_sms * 4, 256, (size_t)dim * 4, s>>>(ix->d_slab, ix->row_base, dim, q, ix->ws_sel_pos.as<uint32_t>(),
+    gather_list_keys_kernel<<<ix->num_sms * 4, 256, query_smem_bytes(dim), s>>>(ix->d_slab, ix->row_base, dim, q, ix->ws_sel_pos.as<uint32_t>(),
                                                                          n1, ix->reduce_order, ix->tail_fma, keys);
     CUDA_TRY(cudaGetLastError());
     for (int p = 0; p < SelTraits<u64>::kPasses; ++p) sel_hist_kernel<u64><<<ix->num_sms, 256, 0, s>>>(keys, n, n1, st1, p, k);
