@@ -196,6 +196,7 @@ class ClockSampler:
         reasons = sorted(name for name, bit in self.REASONS.items() if self.mask & bit)
         return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_min_mhz": min(self.sm) if self.sm else None,
                 "sm_max_mhz": self.max_mhz, "samples": len(self.sm), "reasons": reasons,
+                "reasons_mask": hex(self.mask),  # raw NVML event-reason bits OR-ed over the samples (0x1 idle, 0x2 app clocks, 0x4 sw power cap)
                 "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 

@@ -342,6 +342,7 @@ static int minilm_fast_enqueue(const fsgpu_minilm* e, const int32_t* d_ids, cons
     const uint64_t rows = (uint64_t)batch * max_len;
     const uint32_t m = (uint32_t)rows;
     const unsigned row_blocks = (unsigned)((rows + 7) / 8);
+    const bool ffn_fused = ares && e->inter == 1536 && env_int("FSGPU_MINILM_FFN_FUSED", 1) != 0;
     __half* h16 = e->f_h.as<__half>();
     __half* qkv16 = e->f_qkv.as<__half>();
     __half* ctx16 = e->f_ctx.as<__half>();
@@ -363,6 +364,38 @@ static int minilm_fast_enqueue(const fsgpu_minilm* e, const int32_t* d_ids, cons
         if (rc) return rc;
         minilm_fast_ln_kernel<<<row_blocks, 256, 0, s>>>(pre32, h16, rows, L.attn_ln_g, L.attn_ln_b, e->eps, nullptr);
         CUDA_TRY(cudaGetLastError());
+        if (ffn_fused) {  // FFN-in -> GELU -> FFN-out in one kernel: the [rows x 1536] intermediate stays on the SM
+            FfnArgs fa{};
+            fa.m = m;
+            fa.bias1 = L.ffn_in_b;
+            fa.bias2 = L.ffn_out_b;
+            const uint32_t m_tiles = (m + 255u) / 256u;
+            const uint32_t grid = 2 * std::min<uint32_t>(m_tiles, (uint32_t)e->num_sms / 2);
+            std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+            if (e->profiling) {
+                if (!e->ev_free.empty()) {
+                    ev = e->ev_free.back();
+                    e->ev_free.pop_back();
+                } else {
+                    CUDA_TRY(cudaEventCreate(&ev.first));
+                    CUDA_TRY(cudaEventCreate(&ev.second));
+                }
+                CUDA_TRY(cudaEventRecord(ev.first, s));
+            }
+            ffn_fused_pair_kernel<<<grid, kFfnThreads, ffn_fused_smem_bytes(), s>>>(e->f_tm_h, L.ffn_in.tm64_hi, L.ffn_out.tm64_hi,
+                                                                                    e->f_tm_pre, fa);
+            CUDA_TRY(cudaGetLastError());
+            if (e->profiling) {
+                CUDA_TRY(cudaEventRecord(ev.second, s));
+                e->ev_pending.push_back(ev);
+            }
+            e->prof.gemm_launches += 2;  // two linears
+            e->prof.gemm_flops += 2.0 * 2.0 * (double)m * kHidden * e->inter;
+            minilm_fast_ln_kernel<<<row_blocks, 256, 0, s>>>(pre32, h16, rows, L.ffn_ln_g, L.ffn_ln_b, e->eps, last ? h32 : nullptr);
+            CUDA_TRY(cudaGetLastError());
+            e->prof.other_launches += 3;
+            continue;
+        }
         rc = lin384(e, e->f_tm_h, L.ffn_in, e->f_tm_ffn_out, m, L.ffn_in_b, 1, s);
         if (rc) return rc;
         // FFN-out (K = 1536): 128 x 128 tiles with both operands streamed; the pair kernel's K-chunked mode
@@ -404,6 +437,7 @@ static int minilm_embed_fast_locked(const fsgpu_minilm* e, const int32_t* d_ids,
     }
     CUDA_TRY(cudaFuncSetAttribute(gemm_f16_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_gemm_smem_bytes()));
     CUDA_TRY(cudaFuncSetAttribute(gemm_f16_ares_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(ffn_fused_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ffn_fused_smem_bytes()));
     const bool ares = env_int("FSGPU_MINILM_ARES", 1) != 0 && e->num_sms >= 2 && m >= 256;
     const bool ffn_out_pair = ares && I % (kAresMaxKb * kMmaKBlock) == 0 && env_int("FSGPU_MINILM_ARES_FFN_OUT", 0) != 0;
 
@@ -426,7 +460,8 @@ static int minilm_embed_fast_locked(const fsgpu_minilm* e, const int32_t* d_ids,
     CUDA_TRY(e->g_ids.reserve(4096 * 4));
     CUDA_TRY(e->g_lens.reserve(4096 * 4));
     CUDA_TRY(e->g_out.reserve((size_t)4096 * H * 4));
-    const uint64_t key = ((uint64_t)batch << 32) | ((uint64_t)max_len << 8) | (ares ? 1u : 0u) | (ffn_out_pair ? 2u : 0u);
+    const uint64_t key = ((uint64_t)batch << 32) | ((uint64_t)max_len << 8) | (ares ? 1u : 0u) | (ffn_out_pair ? 2u : 0u) |
+                         (env_int("FSGPU_MINILM_FFN_FUSED", 1) != 0 ? 4u : 0u);
     const void* bufs[9] = {e->f_h.p, e->f_qkv.p, e->f_ctx.p, e->f_ffn.p, e->ws_pre32.p, e->ws_h32.p, e->g_ids.p, e->g_lens.p, e->g_out.p};
     if (e->f_graphs.size() >= 64 && !e->f_graphs.count(key)) {  // bounded cache: shapes are few in practice
         for (auto& kv : e->f_graphs)

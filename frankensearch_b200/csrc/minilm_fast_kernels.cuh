@@ -502,6 +502,301 @@ gemm_f16_ares_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid
     }
 }
 
+// ─── FFN-in -> erf-GELU -> FFN-out in ONE kernel (H = 384, I = 1536) ─────────────────────────────────────────
+// The [rows x 1536] intermediate never leaves the SM.  A CTA pair owns 256-row tiles (128 rows per CTA: its h tile,
+// 96 KiB, resident as the A operand of the first GEMM).  The 1536 intermediate features are walked in 12 chunks of
+// 128: G1(c): acc1 [128 x 128] = h . W1[chunk c]^T  (K = 384; cta_group::2, M = 256, N = 128: 64 weight rows per CTA),
+// epilogue(c): + bias, GELU, f16, written as the NEXT GEMM's A operand — straight into the 128-byte-swizzled K-major
+// layout tcgen05 reads (two [128 x 64] K-blocks per chunk, double-buffered) —, G2(c): acc2 [128 x 384] += g_c . W2[:, chunk c]^T
+// (K = 128; three N = 128 instructions per K-block).  The issuer interleaves G1(c+1) before G2(c), so the tensor pipe
+// works on one while the sixteen epilogue warps finish the other; acc1 is handed back as soon as it is in registers.
+// TMEM: 128 + 384 = 512 columns.  Only weights stream (32 B per MMA clock): every weight box of either matrix is
+// [64 rows x 64 K] = 8 KiB per CTA, so one ring of seven 8 KiB slots serves both.  After the last chunk the epilogue
+// adds the FFN-out bias and stores acc2 as f32 through TMA (staging = the two g buffers).
+constexpr int kFfnEpiWarps = 16;
+constexpr int kFfnThreads = 32 * (kFfnEpiWarps + 2);
+constexpr uint32_t kFfnStages = 7;                     // weight ring slots
+constexpr uint32_t kFfnSlotBytes = kMmaTileBytes / 2;  // [64 x 64] f16
+constexpr uint32_t kFfnChunks = 12;                    // 1536 / 128
+constexpr uint32_t kFfnHKb = 6;                        // 384 / 64
+
+struct FfnArgs {
+    uint32_t m;
+    const float* bias1;  // [1536]
+    const float* bias2;  // [384]
+};
+
+__host__ __device__ inline size_t ffn_fused_smem_bytes() {
+    return 1024 + (size_t)(kFfnHKb + 4) * kMmaTileBytes + (size_t)kFfnStages * kFfnSlotBytes + 512 + (1536 + 384) * 4;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFfnThreads, 1)
+ffn_fused_pair_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_w1_64,
+                      const __grid_constant__ CUtensorMap tm_w2_64, const __grid_constant__ CUtensorMap tm_out,
+                      const FfnArgs args) {
+    extern __shared__ uint8_t smem_dyn[];
+    const uint32_t raw = smem_u32(smem_dyn);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_dyn + (base - raw);
+    const uint32_t h_smem = base;                            // 6 x 16 KiB
+    const uint32_t g_smem = base + kFfnHKb * kMmaTileBytes;  // 2 buffers x 2 K-blocks x 16 KiB
+    const uint32_t w_smem = g_smem + 4u * kMmaTileBytes;     // ring
+    uint8_t* g_ptr = base_ptr + (size_t)kFfnHKb * kMmaTileBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base_ptr + (size_t)(kFfnHKb + 4) * kMmaTileBytes + (size_t)kFfnStages * kFfnSlotBytes);
+    const uint32_t bar0 = smem_u32(bars);
+    auto w_full = [&](uint32_t s) { return bar0 + 8u * s; };
+    auto w_empty = [&](uint32_t s) { return bar0 + 8u * (8u + s); };
+    auto h_full = [&](uint32_t kb) { return bar0 + 8u * (16u + kb); };
+    auto h_empty = [&](uint32_t kb) { return bar0 + 8u * (22u + kb); };
+    const uint32_t acc1_full = bar0 + 8u * 28u, acc1_empty = bar0 + 8u * 29u;
+    auto g_full = [&](uint32_t b) { return bar0 + 8u * (30u + b); };
+    auto g_empty = [&](uint32_t b) { return bar0 + 8u * (32u + b); };
+    const uint32_t acc2_full = bar0 + 8u * 34u, acc2_empty = bar0 + 8u * 35u;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 40);
+    float* bias1_s = reinterpret_cast<float*>(bars + 64);
+    float* bias2_s = bias1_s + 1536;
+    for (uint32_t i = threadIdx.x; i < 1536u; i += blockDim.x) bias1_s[i] = args.bias1[i];
+    for (uint32_t i = threadIdx.x; i < 384u; i += blockDim.x) bias2_s[i] = args.bias2[i];
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const uint32_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const uint32_t m_tiles = (args.m + 255u) / 256u;
+
+    if (warp == kFfnEpiWarps && lane == 0) {
+        tma_prefetch_desc(&tm_h);
+        tma_prefetch_desc(&tm_w1_64);
+        tma_prefetch_desc(&tm_w2_64);
+        tma_prefetch_desc(&tm_out);
+        for (uint32_t s = 0; s < kFfnStages; ++s) {
+            mbar_init(w_full(s), 1);
+            mbar_init(w_empty(s), 1);
+        }
+        for (uint32_t kb = 0; kb < kFfnHKb; ++kb) {
+            mbar_init(h_full(kb), 1);
+            mbar_init(h_empty(kb), 1);
+        }
+        mbar_init(acc1_full, 1);
+        mbar_init(acc1_empty, 2 * kFfnEpiWarps);
+        for (uint32_t b = 0; b < 2; ++b) {
+            mbar_init(g_full(b), 2 * kFfnEpiWarps);
+            mbar_init(g_empty(b), 1);
+        }
+        mbar_init(acc2_full, 1);
+        mbar_init(acc2_empty, 2 * kFfnEpiWarps);
+        fence_barrier_init();
+    } else if (warp == 0) {
+        tmem_alloc_pair(smem_u32(tmem_slot), 512);
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t acc2_col = 0u, acc1_col = 384u;
+
+    if (warp == kFfnEpiWarps) {
+        // ===== TMA producer (both CTAs): h tile per 256-row tile, then the weight sequence G1(0), G1(1), G2(0), G1(2), G2(1), ...
+        uint32_t stage = 0, phase = 0, tiles_done = 0;
+        auto load_w = [&](const CUtensorMap* tm, int32_t kcol, int32_t wrow) {  // one [64 x 64] box per CTA
+            mbar_wait(w_empty(stage), phase ^ 1u);
+            if (elect_one()) {
+                if (rank == 0) mbar_expect_tx(w_full(stage), 2u * kFfnSlotBytes);
+                tma_load_2d_pair(w_smem + stage * kFfnSlotBytes, tm, w_full(stage), kcol, wrow);
+            }
+            __syncwarp();
+            if (++stage == kFfnStages) {
+                stage = 0;
+                phase ^= 1u;
+            }
+        };
+        auto load_g1 = [&](uint32_t c) {  // W1 rows [128c, +128): 64 per CTA, K-blocks 0..5
+            for (uint32_t kb = 0; kb < kFfnHKb; ++kb)
+                load_w(&tm_w1_64, (int32_t)(kb * kMmaKBlock), (int32_t)(c * 128u + rank * 64u));
+        };
+        auto load_g2 = [&](uint32_t c) {  // W2 columns [128c, +128) as two K-blocks x three blocks of 128 output features
+            for (uint32_t j = 0; j < 2; ++j)
+                for (uint32_t part = 0; part < 3; ++part)
+                    load_w(&tm_w2_64, (int32_t)(c * 128u + j * 64u), (int32_t)(part * 128u + rank * 64u));
+        };
+        for (uint32_t mt = pair; mt < m_tiles; mt += n_pairs, ++tiles_done) {
+            for (uint32_t kb = 0; kb < kFfnHKb; ++kb) {
+                if (tiles_done) mbar_wait(h_empty(kb), (tiles_done - 1u) & 1u);
+                if (elect_one()) {
+                    if (rank == 0) mbar_expect_tx(h_full(kb), 2u * kMmaTileBytes);
+                    tma_load_2d_pair(h_smem + kb * kMmaTileBytes, &tm_h, h_full(kb), (int32_t)(kb * kMmaKBlock),
+                                     (int32_t)(mt * 256u + rank * 128u));
+                }
+                __syncwarp();
+            }
+            for (uint32_t c = 0; c < kFfnChunks; ++c) {
+                load_g1(c);
+                if (c) load_g2(c - 1u);
+            }
+            load_g2(kFfnChunks - 1u);
+        }
+    } else if (warp == kFfnEpiWarps + 1) {
+        if (rank == 0) {
+            // ===== MMA issuer (leader CTA only) =====
+            constexpr uint32_t idesc128 = umma_idesc_f16(256, 128);
+            const uint64_t h_desc0 = umma_desc_sw128(h_smem), g_desc0 = umma_desc_sw128(g_smem), w_desc0 = umma_desc_sw128(w_smem);
+            uint32_t stage = 0, phase = 0, tiles_done = 0;
+            uint32_t n_g1 = 0;          // G1 groups issued so far (acc1 generation)
+            uint32_t n_g2[2] = {0, 0};  // G2 groups issued per g buffer
+            auto next_stage = [&]() {
+                if (++stage == kFfnStages) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            };
+            auto issue_g1 = [&](uint32_t c, bool first_of_tile) {
+                mbar_wait(acc1_empty, (n_g1 & 1u) ^ 1u);
+                tc_fence_after();
+                for (uint32_t kb = 0; kb < kFfnHKb; ++kb) {
+                    if (first_of_tile) mbar_wait(h_full(kb), tiles_done & 1u);
+                    mbar_wait(w_full(stage), phase);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint64_t a = h_desc0 + (uint64_t)(kb * (kMmaTileBytes >> 4));
+                        const uint64_t b = w_desc0 + (uint64_t)(stage * (kFfnSlotBytes >> 4));
+#pragma unroll
+                        for (uint32_t k4 = 0; k4 < 4; ++k4)
+                            umma_f16_pair(tmem_base + acc1_col, a + 2u * k4, b + 2u * k4, idesc128, (kb | k4) != 0u ? 1u : 0u);
+                        umma_commit_pair(w_empty(stage));
+                        if (c + 1 == kFfnChunks) umma_commit_pair(h_empty(kb));  // the tile's last use of this h block
+                        if (kb + 1 == kFfnHKb) umma_commit_pair(acc1_full);
+                    }
+                    __syncwarp();
+                    next_stage();
+                }
+                ++n_g1;
+            };
+            auto issue_g2 = [&](uint32_t c) {
+                const uint32_t buf = c & 1u;
+                mbar_wait(g_full(buf), n_g2[buf] & 1u);
+                tc_fence_after();
+                if (c == 0) {
+                    mbar_wait(acc2_empty, (tiles_done & 1u) ^ 1u);
+                    tc_fence_after();
+                }
+                for (uint32_t j = 0; j < 2; ++j) {
+                    const uint64_t a = g_desc0 + (uint64_t)((buf * 2u + j) * (kMmaTileBytes >> 4));
+                    for (uint32_t part = 0; part < 3; ++part) {  // output features [128 part, +128)
+                        mbar_wait(w_full(stage), phase);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint64_t b = w_desc0 + (uint64_t)(stage * (kFfnSlotBytes >> 4));
+                            const uint32_t d = tmem_base + acc2_col + part * 128u;
+#pragma unroll
+                            for (uint32_t k4 = 0; k4 < 4; ++k4)
+                                umma_f16_pair(d, a + 2u * k4, b + 2u * k4, idesc128, (c | j | k4) != 0u ? 1u : 0u);
+                            umma_commit_pair(w_empty(stage));
+                            if (j == 1 && part == 2) {
+                                umma_commit_pair(g_empty(buf));
+                                if (c + 1 == kFfnChunks) umma_commit_pair(acc2_full);
+                            }
+                        }
+                        __syncwarp();
+                        next_stage();
+                    }
+                }
+                ++n_g2[buf];
+            };
+            for (uint32_t mt = pair; mt < m_tiles; mt += n_pairs, ++tiles_done) {
+                for (uint32_t c = 0; c < kFfnChunks; ++c) {
+                    issue_g1(c, c == 0);
+                    if (c) issue_g2(c - 1u);
+                }
+                issue_g2(kFfnChunks - 1u);
+            }
+        }
+    } else {
+        // ===== epilogue (both CTAs): TMEM lane = row of this CTA =====
+        const uint32_t quarter = warp & 3u, part = warp >> 2;  // acc1: columns [32 part, +32); acc2: [96 part, +96)
+        const uint32_t row_l = quarter * 32u + lane;           // local row 0..127
+        const uint32_t sw = row_l & 7u;
+        uint32_t n_acc1 = 0, n_g[2] = {0, 0}, tiles_done = 0;
+        for (uint32_t mt = pair; mt < m_tiles; mt += n_pairs, ++tiles_done) {
+            for (uint32_t c = 0; c < kFfnChunks; ++c) {
+                const uint32_t buf = c & 1u;
+                mbar_wait(acc1_full, n_acc1 & 1u);
+                tc_fence_after();
+                uint32_t v[32];
+                tmem_ld_x32(tmem_base + ((quarter * 32u) << 16) + acc1_col + part * 32u, v);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(acc1_empty, 0);
+                ++n_acc1;
+                // the g buffer is free once G2 of the chunk that used it last has completed
+                if (n_g[buf]) mbar_wait(g_empty(buf), (n_g[buf] - 1u) & 1u);
+                uint8_t* gk = g_ptr + (size_t)(buf * 2u + (part >> 1)) * kMmaTileBytes + row_l * 128u;
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    __half2 hh[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint32_t col = c * 128u + part * 32u + (uint32_t)j + 2u * (uint32_t)i;
+                        const float x0 = gelu_tanh_fit(__uint_as_float(v[j + 2 * i]) + bias1_s[col]);
+                        const float x1 = gelu_tanh_fit(__uint_as_float(v[j + 2 * i + 1]) + bias1_s[col + 1u]);
+                        hh[i] = __floats2half2_rn(x0, x1);
+                    }
+                    const uint32_t ch = (part & 1u) * 4u + (uint32_t)j / 8u;
+                    *reinterpret_cast<uint4*>(gk + ((ch ^ sw) << 4)) = *reinterpret_cast<uint4*>(hh);
+                }
+                fence_proxy_async_smem();  // generic-proxy writes -> tcgen05 operand reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(g_full(buf), 0);
+                ++n_g[buf];
+            }
+            // final: acc2 + bias2 -> f32 pre, 96 columns per warp as three [32 x 32] boxes through this warp's 4 KiB of
+            // the g buffers (free: acc2_full implies every G2 of the tile has completed)
+            mbar_wait(acc2_full, tiles_done & 1u);
+            tc_fence_after();
+            const uint32_t row0 = mt * 256u + rank * 128u + quarter * 32u;
+            uint8_t* st_ptr = g_ptr + (size_t)warp * 4096u;
+            const uint32_t st_smem = g_smem + warp * 4096u;
+            const uint32_t swl = lane & 7u;
+#pragma unroll 1
+            for (uint32_t b = 0; b < 3; ++b) {  // one [32 x 32] box at a time (32 accumulator registers, not 96)
+                uint32_t w2[32];
+                tmem_ld_x32(tmem_base + ((quarter * 32u) << 16) + acc2_col + part * 96u + b * 32u, w2);
+                tmem_ld_wait();
+                if (b == 2) {  // the accumulator is in registers / already stored: hand it back
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(acc2_empty, 0);
+                }
+                if (row0 >= args.m) continue;
+                if (lane == 0) tma_store_wait_read();
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const uint32_t col = part * 96u + b * 32u + (uint32_t)j;
+                    const float4 x = make_float4(__uint_as_float(w2[j]) + bias2_s[col], __uint_as_float(w2[j + 1]) + bias2_s[col + 1],
+                                                 __uint_as_float(w2[j + 2]) + bias2_s[col + 2], __uint_as_float(w2[j + 3]) + bias2_s[col + 3]);
+                    *reinterpret_cast<float4*>(st_ptr + lane * 128u + ((((uint32_t)j / 4u) ^ swl) << 4)) = x;
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&tm_out, st_smem, (int32_t)(part * 96u + b * 32u), (int32_t)row0);
+                    tma_store_commit();
+                }
+            }
+            if (lane == 0) tma_store_wait_read();
+            // every warp's staging must have been read before any warp writes g values of the next tile over it
+            asm volatile("bar.sync 1, %0;" ::"r"(kFfnEpiWarps * 32) : "memory");
+        }
+        if (lane == 0) tma_store_wait_all();
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, 512);
+    }
+}
+
 // ─── h = LayerNorm(pre + residual): one warp per token row of H = 384 ───────────────────────
 // pre f32 (linear + bias), residual f16 (the layer input); h f16 in place of the residual, and an f32 copy on
 // request (the last layer: the pooling kernel reads f32).

@@ -147,6 +147,31 @@ def test_minilm_large_batch_1024_queries(enc, bert):
     check(got[idx], want)
 
 
+def test_minilm_fused_ffn_kernel_matches_the_two_gemm_form(fs, bert):
+    """FSGPU_MINILM_FFN_FUSED (default 1): FFN-in -> GELU -> FFN-out in one kernel, the [rows x 1536] intermediate
+    kept on the SM.  Same operands, same f16 rounding of the intermediate, same f32 accumulation: it must agree with
+    the two-GEMM form to f16 accumulation-order noise, on a ragged last tile, on pairs that own several tiles
+    (1024 x 32 rows = 128 tiles on 74 CTA pairs), and both forms stay inside the tolerance against torch f32."""
+    rng = np.random.default_rng(11)
+    for n in (9, 300, 1024):  # 288 rows (one ragged 256-row tile + tail), 9600 rows, 32768 rows
+        batches = random_batches(rng, n, 1, 32)
+        batches[0] = rng.integers(1, 2000, 32).tolist()  # t_pad = 32
+        out = {}
+        for fused in (1, 0):
+            e = fs.MiniLmEmbedder(mr.state_dict_numpy(bert))
+            os.environ["FSGPU_MINILM_FFN_FUSED"] = str(fused)
+            try:
+                out[fused] = e.embed_token_ids_batch(batches)
+            finally:
+                del os.environ["FSGPU_MINILM_FFN_FUSED"]
+                e.close()
+        assert np.abs(out[1] - out[0]).max() <= 1e-4, np.abs(out[1] - out[0]).max()
+        idx = list(range(0, n, max(1, n // 16)))
+        want = mr.reference_embed(bert, [batches[i] for i in idx])
+        check(out[1][idx], want, tol=5e-4)
+        check(out[0][idx], want, tol=5e-4)
+
+
 def test_minilm_single_product_mode_is_within_tolerance(fs, bert):
     """FSGPU_MINILM_PRODUCTS=1 (plain f16 operands, a third of the tensor work): still inside the
     1e-3 budget on cosine, reported beside the default in the bench."""
