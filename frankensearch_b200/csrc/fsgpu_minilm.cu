@@ -369,6 +369,13 @@ static int minilm_fast_enqueue(const fsgpu_minilm* e, const int32_t* d_ids, cons
             fa.m = m;
             fa.bias1 = L.ffn_in_b;
             fa.bias2 = L.ffn_out_b;
+            fa.dbg = (uint32_t)env_int("FSGPU_MINILM_FFN_DBG", 0);
+            long long* d_ts = nullptr;
+            if (li == 0 && env_int("FSGPU_MINILM_FFN_TS", 0) != 0) {  // debugging aid (never with a captured graph)
+                CUDA_TRY(cudaMalloc(&d_ts, 24 * 8 * sizeof(long long)));
+                CUDA_TRY(cudaMemsetAsync(d_ts, 0, 24 * 8 * sizeof(long long), s));
+                fa.ts = d_ts;
+            }
             const uint32_t m_tiles = (m + 255u) / 256u;
             const uint32_t grid = 2 * std::min<uint32_t>(m_tiles, (uint32_t)e->num_sms / 2);
             std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
@@ -388,6 +395,19 @@ static int minilm_fast_enqueue(const fsgpu_minilm* e, const int32_t* d_ids, cons
             if (e->profiling) {
                 CUDA_TRY(cudaEventRecord(ev.second, s));
                 e->ev_pending.push_back(ev);
+            }
+            if (d_ts) {
+                long long t[24 * 8];
+                CUDA_TRY(cudaStreamSynchronize(s));
+                CUDA_TRY(cudaMemcpy(t, d_ts, sizeof(t), cudaMemcpyDeviceToHost));
+                cudaFree(d_ts);
+                const long long t0 = t[0];
+                fprintf(stderr, "[ffn ts] chunk: issuer acc1_empty g1_issued g_full g2_issued | epilogue acc1_full ld_done g_empty g_written (cycles)\n");
+                for (int c = 0; c < 24; ++c) {
+                    fprintf(stderr, "[ffn ts] %2d:", c);
+                    for (int i = 0; i < 8; ++i) fprintf(stderr, " %7lld%s", t[c * 8 + i] ? t[c * 8 + i] - t0 : -1, i == 3 ? " |" : "");
+                    fprintf(stderr, "\n");
+                }
             }
             e->prof.gemm_launches += 2;  // two linears
             e->prof.gemm_flops += 2.0 * 2.0 * (double)m * kHidden * e->inter;

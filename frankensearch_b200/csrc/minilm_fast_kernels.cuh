@@ -511,12 +511,17 @@ gemm_f16_ares_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid
 // (K = 128; three N = 128 instructions per K-block).  The issuer interleaves G1(c+1) before G2(c), so the tensor pipe
 // works on one while the sixteen epilogue warps finish the other; acc1 is handed back as soon as it is in registers.
 // TMEM: 128 + 384 = 512 columns.  Only weights stream (32 B per MMA clock): every weight box of either matrix is
-// [64 rows x 64 K] = 8 KiB per CTA, so one ring of seven 8 KiB slots serves both.  After the last chunk the epilogue
-// adds the FFN-out bias and stores acc2 as f32 through TMA (staging = the two g buffers).
+// [64 rows x 64 K] = 8 KiB per CTA, and one ring slot holds TWO of them behind one barrier (the two K-blocks that
+// feed the same accumulator columns), i.e. eight MMAs = 512 tensor clocks per barrier round.  In-kernel timestamps
+// (FSGPU_MINILM_FFN_TS) showed why: with one box per barrier the single issuing thread needed ~380 clocks per round
+// (wait, fence, election, four MMAs, commits) for 256 clocks of tensor work — the ISSUER, not the epilogue or the
+// weight stream, set the pace (tensor pipe 49 % active).  The whole issue loop now runs in one elected thread.
+// After the last chunk the epilogue adds the FFN-out bias and stores acc2 as f32 through TMA (staging = the two g buffers).
 constexpr int kFfnEpiWarps = 16;
 constexpr int kFfnThreads = 32 * (kFfnEpiWarps + 2);
-constexpr uint32_t kFfnStages = 7;                     // weight ring slots
-constexpr uint32_t kFfnSlotBytes = kMmaTileBytes / 2;  // [64 x 64] f16
+constexpr uint32_t kFfnStages = 4;                     // weight ring slots (three held one GEMM group: every refill waited for L2)
+constexpr uint32_t kFfnBoxBytes = kMmaTileBytes / 2;   // [64 x 64] f16
+constexpr uint32_t kFfnSlotBytes = 2 * kFfnBoxBytes;   // two boxes per slot
 constexpr uint32_t kFfnChunks = 12;                    // 1536 / 128
 constexpr uint32_t kFfnHKb = 6;                        // 384 / 64
 
@@ -524,10 +529,14 @@ struct FfnArgs {
     uint32_t m;
     const float* bias1;  // [1536]
     const float* bias2;  // [384]
+    uint32_t dbg;        // timing experiments (FSGPU_MINILM_FFN_DBG; results are wrong with any bit set): 1 no GELU math,
+                         // 2 issuer ignores g_full, 4 G2 MMAs not issued, 8 weight boxes loaded once (no TMA after the
+                         // first ring fill), 16 G1 MMAs not issued
+    long long* ts;       // FSGPU_MINILM_FFN_TS: clock64 stamps of pair 0's issuer and first epilogue warp, 8 per chunk, 24 chunks
 };
 
 __host__ __device__ inline size_t ffn_fused_smem_bytes() {
-    return 1024 + (size_t)(kFfnHKb + 4) * kMmaTileBytes + (size_t)kFfnStages * kFfnSlotBytes + 512 + (1536 + 384) * 4;
+    return 1024 + (size_t)(kFfnHKb + 4) * kMmaTileBytes + (size_t)kFfnStages * kFfnSlotBytes + 512 + 384 * 4;  // = 227 KiB exactly
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFfnThreads, 1)
@@ -553,9 +562,7 @@ ffn_fused_pair_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_con
     auto g_empty = [&](uint32_t b) { return bar0 + 8u * (32u + b); };
     const uint32_t acc2_full = bar0 + 8u * 34u, acc2_empty = bar0 + 8u * 35u;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 40);
-    float* bias1_s = reinterpret_cast<float*>(bars + 64);
-    float* bias2_s = bias1_s + 1536;
-    for (uint32_t i = threadIdx.x; i < 1536u; i += blockDim.x) bias1_s[i] = args.bias1[i];
+    float* bias2_s = reinterpret_cast<float*>(bars + 64);  // the FFN-in bias has no room here: see the epilogue
     for (uint32_t i = threadIdx.x; i < 384u; i += blockDim.x) bias2_s[i] = args.bias2[i];
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -596,29 +603,34 @@ ffn_fused_pair_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_con
 
     if (warp == kFfnEpiWarps) {
         // ===== TMA producer (both CTAs): h tile per 256-row tile, then the weight sequence G1(0), G1(1), G2(0), G1(2), G2(1), ...
-        uint32_t stage = 0, phase = 0, tiles_done = 0;
-        auto load_w = [&](const CUtensorMap* tm, int32_t kcol, int32_t wrow) {  // one [64 x 64] box per CTA
+        uint32_t stage = 0, phase = 0, tiles_done = 0, n_loads = 0;
+        auto load_w = [&](const CUtensorMap* tm, int32_t kcol, int32_t wrow) {  // two [64 x 64] boxes per CTA: K-columns kcol, kcol + 64
             mbar_wait(w_empty(stage), phase ^ 1u);
             if (elect_one()) {
-                if (rank == 0) mbar_expect_tx(w_full(stage), 2u * kFfnSlotBytes);
-                tma_load_2d_pair(w_smem + stage * kFfnSlotBytes, tm, w_full(stage), kcol, wrow);
+                if ((args.dbg & 8u) && n_loads >= kFfnStages) {
+                    if (rank == 0) mbar_arrive(w_full(stage));
+                } else {
+                    if (rank == 0) mbar_expect_tx(w_full(stage), 2u * kFfnSlotBytes);
+                    tma_load_2d_pair(w_smem + stage * kFfnSlotBytes, tm, w_full(stage), kcol, wrow);
+                    tma_load_2d_pair(w_smem + stage * kFfnSlotBytes + kFfnBoxBytes, tm, w_full(stage), kcol + (int32_t)kMmaKBlock, wrow);
+                }
             }
+            ++n_loads;
             __syncwarp();
             if (++stage == kFfnStages) {
                 stage = 0;
                 phase ^= 1u;
             }
         };
-        auto load_g1 = [&](uint32_t c) {  // W1 rows [128c, +128): 64 per CTA, K-blocks 0..5
-            for (uint32_t kb = 0; kb < kFfnHKb; ++kb)
-                load_w(&tm_w1_64, (int32_t)(kb * kMmaKBlock), (int32_t)(c * 128u + rank * 64u));
+        auto load_g1 = [&](uint32_t c) {  // W1 rows [128c, +128): 64 per CTA, K-blocks (0,1) (2,3) (4,5)
+            for (uint32_t i = 0; i < kFfnHKb / 2; ++i)
+                load_w(&tm_w1_64, (int32_t)(2u * i * kMmaKBlock), (int32_t)(c * 128u + rank * 64u));
         };
-        auto load_g2 = [&](uint32_t c) {  // W2 columns [128c, +128) as two K-blocks x three blocks of 128 output features
-            for (uint32_t j = 0; j < 2; ++j)
-                for (uint32_t part = 0; part < 3; ++part)
-                    load_w(&tm_w2_64, (int32_t)(c * 128u + j * 64u), (int32_t)(part * 128u + rank * 64u));
+        auto load_g2 = [&](uint32_t c) {  // W2 columns [128c, +128) (two K-blocks) for each block of 128 output features
+            for (uint32_t part = 0; part < 3; ++part)
+                load_w(&tm_w2_64, (int32_t)(c * 128u), (int32_t)(part * 128u + rank * 64u));
         };
-        for (uint32_t mt = pair; mt < m_tiles; mt += n_pairs, ++tiles_done) {
+        auto load_h = [&](uint32_t mt) {  // the tile's h blocks, each as soon as the previous tile's last G1 has read it
             for (uint32_t kb = 0; kb < kFfnHKb; ++kb) {
                 if (tiles_done) mbar_wait(h_empty(kb), (tiles_done - 1u) & 1u);
                 if (elect_one()) {
@@ -628,17 +640,23 @@ ffn_fused_pair_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_con
                 }
                 __syncwarp();
             }
+        };
+        if (pair < m_tiles) load_h(pair);
+        for (uint32_t mt = pair; mt < m_tiles; mt += n_pairs) {
             for (uint32_t c = 0; c < kFfnChunks; ++c) {
                 load_g1(c);
                 if (c) load_g2(c - 1u);
             }
+            ++tiles_done;
+            if (mt + n_pairs < m_tiles) load_h(mt + n_pairs);  // before the last G2's weights: lands under G2(10), G2(11)
             load_g2(kFfnChunks - 1u);
         }
     } else if (warp == kFfnEpiWarps + 1) {
-        if (rank == 0) {
-            // ===== MMA issuer (leader CTA only) =====
+        if (rank == 0 && elect_one()) {
+            // ===== MMA issuer (one thread of the leader CTA) =====
             constexpr uint32_t idesc128 = umma_idesc_f16(256, 128);
             const uint64_t h_desc0 = umma_desc_sw128(h_smem), g_desc0 = umma_desc_sw128(g_smem), w_desc0 = umma_desc_sw128(w_smem);
+            const bool ts_on = args.ts != nullptr && blockIdx.x == 0;
             uint32_t stage = 0, phase = 0, tiles_done = 0;
             uint32_t n_g1 = 0;          // G1 groups issued so far (acc1 generation)
             uint32_t n_g2[2] = {0, 0};  // G2 groups issued per g buffer
@@ -651,54 +669,67 @@ ffn_fused_pair_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_con
             auto issue_g1 = [&](uint32_t c, bool first_of_tile) {
                 mbar_wait(acc1_empty, (n_g1 & 1u) ^ 1u);
                 tc_fence_after();
-                for (uint32_t kb = 0; kb < kFfnHKb; ++kb) {
-                    if (first_of_tile) mbar_wait(h_full(kb), tiles_done & 1u);
+                if (ts_on && n_g1 < 24) args.ts[n_g1 * 8 + 0] = clock64();
+                for (uint32_t i = 0; i < kFfnHKb / 2; ++i) {
+                    if (first_of_tile) {
+                        mbar_wait(h_full(2u * i), tiles_done & 1u);
+                        mbar_wait(h_full(2u * i + 1u), tiles_done & 1u);
+                    }
                     mbar_wait(w_full(stage), phase);
                     tc_fence_after();
-                    if (elect_one()) {
-                        const uint64_t a = h_desc0 + (uint64_t)(kb * (kMmaTileBytes >> 4));
-                        const uint64_t b = w_desc0 + (uint64_t)(stage * (kFfnSlotBytes >> 4));
+                    const uint64_t a = h_desc0 + (uint64_t)(2u * i * (kMmaTileBytes >> 4));
+                    const uint64_t b = w_desc0 + (uint64_t)(stage * (kFfnSlotBytes >> 4));
+                    if (!(args.dbg & 16u)) {
 #pragma unroll
-                        for (uint32_t k4 = 0; k4 < 4; ++k4)
-                            umma_f16_pair(tmem_base + acc1_col, a + 2u * k4, b + 2u * k4, idesc128, (kb | k4) != 0u ? 1u : 0u);
-                        umma_commit_pair(w_empty(stage));
-                        if (c + 1 == kFfnChunks) umma_commit_pair(h_empty(kb));  // the tile's last use of this h block
-                        if (kb + 1 == kFfnHKb) umma_commit_pair(acc1_full);
+                        for (uint32_t half = 0; half < 2; ++half)
+#pragma unroll
+                            for (uint32_t k4 = 0; k4 < 4; ++k4)
+                                umma_f16_pair(tmem_base + acc1_col, a + half * (kMmaTileBytes >> 4) + 2u * k4,
+                                              b + half * (kFfnBoxBytes >> 4) + 2u * k4, idesc128, (i | half | k4) != 0u ? 1u : 0u);
                     }
-                    __syncwarp();
+                    umma_commit_pair(w_empty(stage));
+                    if (c + 1 == kFfnChunks) {  // the tile's last use of these h blocks
+                        umma_commit_pair(h_empty(2u * i));
+                        umma_commit_pair(h_empty(2u * i + 1u));
+                    }
+                    if (i + 1 == kFfnHKb / 2) umma_commit_pair(acc1_full);
                     next_stage();
                 }
+                if (ts_on && n_g1 < 24) args.ts[n_g1 * 8 + 1] = clock64();
                 ++n_g1;
             };
             auto issue_g2 = [&](uint32_t c) {
                 const uint32_t buf = c & 1u;
-                mbar_wait(g_full(buf), n_g2[buf] & 1u);
+                if (!(args.dbg & 2u)) mbar_wait(g_full(buf), n_g2[buf] & 1u);
                 tc_fence_after();
+                const uint32_t gi = tiles_done * kFfnChunks + c;
+                if (ts_on && gi < 24) args.ts[gi * 8 + 2] = clock64();
                 if (c == 0) {
                     mbar_wait(acc2_empty, (tiles_done & 1u) ^ 1u);
                     tc_fence_after();
                 }
-                for (uint32_t j = 0; j < 2; ++j) {
-                    const uint64_t a = g_desc0 + (uint64_t)((buf * 2u + j) * (kMmaTileBytes >> 4));
-                    for (uint32_t part = 0; part < 3; ++part) {  // output features [128 part, +128)
-                        mbar_wait(w_full(stage), phase);
-                        tc_fence_after();
-                        if (elect_one()) {
-                            const uint64_t b = w_desc0 + (uint64_t)(stage * (kFfnSlotBytes >> 4));
-                            const uint32_t d = tmem_base + acc2_col + part * 128u;
+                const uint64_t a = g_desc0 + (uint64_t)(buf * 2u * (kMmaTileBytes >> 4));
+                for (uint32_t part = 0; part < 3; ++part) {  // output features [128 part, +128)
+                    mbar_wait(w_full(stage), phase);
+                    tc_fence_after();
+                    const uint64_t b = w_desc0 + (uint64_t)(stage * (kFfnSlotBytes >> 4));
+                    const uint32_t d = tmem_base + acc2_col + part * 128u;
+                    if (!(args.dbg & 4u)) {
+#pragma unroll
+                        for (uint32_t j = 0; j < 2; ++j)
 #pragma unroll
                             for (uint32_t k4 = 0; k4 < 4; ++k4)
-                                umma_f16_pair(d, a + 2u * k4, b + 2u * k4, idesc128, (c | j | k4) != 0u ? 1u : 0u);
-                            umma_commit_pair(w_empty(stage));
-                            if (j == 1 && part == 2) {
-                                umma_commit_pair(g_empty(buf));
-                                if (c + 1 == kFfnChunks) umma_commit_pair(acc2_full);
-                            }
-                        }
-                        __syncwarp();
-                        next_stage();
+                                umma_f16_pair(d, a + j * (kMmaTileBytes >> 4) + 2u * k4, b + j * (kFfnBoxBytes >> 4) + 2u * k4, idesc128,
+                                              (c | j | k4) != 0u ? 1u : 0u);
                     }
+                    umma_commit_pair(w_empty(stage));
+                    if (part == 2) {
+                        umma_commit_pair(g_empty(buf));
+                        if (c + 1 == kFfnChunks) umma_commit_pair(acc2_full);
+                    }
+                    next_stage();
                 }
+                if (ts_on && gi < 24) args.ts[gi * 8 + 3] = clock64();
                 ++n_g2[buf];
             };
             for (uint32_t mt = pair; mt < m_tiles; mt += n_pairs, ++tiles_done) {
@@ -709,35 +740,49 @@ ffn_fused_pair_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_con
                 issue_g2(kFfnChunks - 1u);
             }
         }
+        __syncwarp();
     } else {
         // ===== epilogue (both CTAs): TMEM lane = row of this CTA =====
         const uint32_t quarter = warp & 3u, part = warp >> 2;  // acc1: columns [32 part, +32); acc2: [96 part, +96)
         const uint32_t row_l = quarter * 32u + lane;           // local row 0..127
         const uint32_t sw = row_l & 7u;
         uint32_t n_acc1 = 0, n_g[2] = {0, 0}, tiles_done = 0;
+        const bool ts_on = args.ts != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
         for (uint32_t mt = pair; mt < m_tiles; mt += n_pairs, ++tiles_done) {
             for (uint32_t c = 0; c < kFfnChunks; ++c) {
                 const uint32_t buf = c & 1u;
+                // this warp's 32 FFN-in bias values of the chunk (warp-uniform addresses), fetched ahead of the wait
+                float4 bq[8];
+                const float4* bsrc = reinterpret_cast<const float4*>(args.bias1 + c * 128u + part * 32u);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) bq[i] = __ldg(bsrc + i);
+                const float* bias1_r = reinterpret_cast<const float*>(bq);
                 mbar_wait(acc1_full, n_acc1 & 1u);
                 tc_fence_after();
+                if (ts_on && n_acc1 < 24) args.ts[n_acc1 * 8 + 4] = clock64();
                 uint32_t v[32];
                 tmem_ld_x32(tmem_base + ((quarter * 32u) << 16) + acc1_col + part * 32u, v);
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(acc1_empty, 0);
+                if (ts_on && n_acc1 < 24) args.ts[n_acc1 * 8 + 5] = clock64();
                 ++n_acc1;
                 // the g buffer is free once G2 of the chunk that used it last has completed
                 if (n_g[buf]) mbar_wait(g_empty(buf), (n_g[buf] - 1u) & 1u);
+                if (ts_on && n_acc1 <= 24) args.ts[(n_acc1 - 1) * 8 + 6] = clock64();
                 uint8_t* gk = g_ptr + (size_t)(buf * 2u + (part >> 1)) * kMmaTileBytes + row_l * 128u;
 #pragma unroll
                 for (int j = 0; j < 32; j += 8) {
                     __half2 hh[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        const uint32_t col = c * 128u + part * 32u + (uint32_t)j + 2u * (uint32_t)i;
-                        const float x0 = gelu_tanh_fit(__uint_as_float(v[j + 2 * i]) + bias1_s[col]);
-                        const float x1 = gelu_tanh_fit(__uint_as_float(v[j + 2 * i + 1]) + bias1_s[col + 1u]);
+                        float x0 = __uint_as_float(v[j + 2 * i]) + bias1_r[j + 2 * i];
+                        float x1 = __uint_as_float(v[j + 2 * i + 1]) + bias1_r[j + 2 * i + 1];
+                        if (!(args.dbg & 1u)) {
+                            x0 = gelu_tanh_fit(x0);
+                            x1 = gelu_tanh_fit(x1);
+                        }
                         hh[i] = __floats2half2_rn(x0, x1);
                     }
                     const uint32_t ch = (part & 1u) * 4u + (uint32_t)j / 8u;
@@ -746,6 +791,7 @@ ffn_fused_pair_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_con
                 fence_proxy_async_smem();  // generic-proxy writes -> tcgen05 operand reads
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(g_full(buf), 0);
+                if (ts_on && n_acc1 <= 24) args.ts[(n_acc1 - 1) * 8 + 7] = clock64();
                 ++n_g[buf];
             }
             // final: acc2 + bias2 -> f32 pre, 96 columns per warp as three [32 x 32] boxes through this warp's 4 KiB of
