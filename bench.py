@@ -48,18 +48,34 @@ def parse_args():
                    help="3 = the headline only (configs[2]); all = headline + sub-records for configs[1], [3], [4]")
     p.add_argument("--rows5", type=int, default=50_000_000, help="rows of configs[4] (50 M)")
     p.add_argument("--queries5", type=int, default=1000, help="queries of the configs[4] latency run")
+    p.add_argument("--query-groups", type=int, default=0,
+                   help="N > 1: ranks = (N / Q) row shards x Q query groups (frankensearch_b200/sharded.py); default 1 = "
+                        "plain row shards: at 8 GPUs 2 x 4 measured 0.658 ms per step against 0.640 for 8 row shards "
+                        "(profiles/r02_layout_rows_x_query_groups.md)")
     p.add_argument("--hbm-batch", type=int, default=128,
                    help="also time the HBM-bound regime with this many queries per pass (0 = skip)")
     return p.parse_args()
 
 
+def query_groups_for(a, n_gpus):
+    if n_gpus < 2:
+        return 1
+    q = a.query_groups if a.query_groups > 0 else 1
+    return q if n_gpus % q == 0 else 1
+
+
 def workload_config(a, n_gpus):
+    qg = query_groups_for(a, n_gpus)
     return {
         "workload": f"configs[2]: {a.rows} docs x {a.dim}-dim f16, batch {a.batch} queries, exact cosine top-{a.k}",
         "rows": a.rows, "dim": a.dim, "batch": a.batch, "k": a.k,
         "corpus": "clustered (64 centroids, noise 0.30) — reference bench generator fsvi_int8_two_pass.rs:199-231",
         "storage": "f16 slab (+ int8 codes of it for the candidate pass), f32 query; tensor-core candidate pass (int8 x int8 -> s32, or f16 x f16 -> f32 with FSGPU_MMA_I8=0) + exact f16 re-scoring with the reference accumulation tree (bit-exact results)",
-        "sharding": "single GPU" if n_gpus == 1 else f"rows sharded over {n_gpus} ranks, one all-gather of top-k keys",
+        "sharding": ("single GPU" if n_gpus == 1 else
+                     f"rows sharded over {n_gpus} ranks, one all-gather of top-k keys" if qg == 1 else
+                     f"{n_gpus // qg} row shards x {qg} query groups (rank g*R + r: rows [r*N/R, (r+1)*N/R), queries "
+                     f"[g*B/Q, (g+1)*B/Q)), one all-gather of top-k keys, one merge per group; the HBM-regime "
+                     f"sub-records and `row_shards_only` use {n_gpus} plain row shards"),
         "l2": "inputs larger than L2 (slab per GPU >> 126 MB); no explicit flush",
     }
 
@@ -241,13 +257,13 @@ class Ctx:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
-    def synth_shard(self, seed, rows, dim):
-        """This rank's contiguous row shard of a clustered corpus, generated on the device by the
-        reference's bench generator (bit-identical to the oracle's fso_synth_rows)."""
+    def synth_shard(self, seed, rows, dim, shards=None, shard=None):
+        """This rank's contiguous row shard (default: shard `rank` of `world`) of a clustered corpus, generated
+        on the device by the reference's bench generator (bit-identical to the oracle's fso_synth_rows)."""
         import frankensearch_b200 as fs
         from frankensearch_b200.sharded import shard_bounds
 
-        lo, hi = shard_bounds(rows, self.world, self.rank)
+        lo, hi = shard_bounds(rows, self.world if shards is None else shards, self.rank if shard is None else shard)
         slab = self.torch.empty((hi - lo, dim), dtype=self.torch.int16, device=self.dev)
         fs._ffi.check(fs._ffi.lib().fsgpu_synth_rows_device(self.local_rank, 1, seed, lo, hi - lo, dim, 64, 0.30,
                                                             slab.data_ptr(), None))
@@ -323,8 +339,12 @@ def run_ours(a):
 def run_headline(ctx):
     a, torch, dev, world, rank, local_rank = ctx.a, ctx.torch, ctx.dev, ctx.world, ctx.rank, ctx.local_rank
     import frankensearch_b200 as fs
-    from frankensearch_b200.sharded import ShardedGpuIndex
+    from frankensearch_b200.sharded import ShardedGpuIndex, grid_position, query_block
 
+    # layout at N > 1: R row shards x Q query groups for the headline batch (frankensearch_b200/sharded.py); the
+    # HBM-bound sub-records (1 and 128 queries per pass) run on N plain row shards
+    qg = query_groups_for(a, world)
+    r_shards, r_shard, q_group = grid_position(world, rank, qg)
     ix, lo, hi = ctx.synth_shard(1, a.rows, a.dim)
     sharded = ShardedGpuIndex(ix) if world > 1 else None
 
@@ -385,6 +405,17 @@ def run_headline(ctx):
         for rec in hbm.values():
             rec["algorithmic_bytes"] = "rows*dim*2 (f16 slab)" if "int8" not in rec["kernel"] else "rows*dim (int8 codes)"
 
+    row_shards_only = None
+    if qg > 1:
+        # the same batch on N plain row shards, for the record; then the R x Q layout takes over
+        for _ in range(3):
+            search(d_queries)
+        ms_rows, _ = _time_steps(ctx, lambda: search(d_queries), a.steps, 0)
+        row_shards_only = {"layout": f"{world} row shards", "ms_per_step": ms_rows, "queries_per_s": a.batch / (ms_rows / 1e3)}
+        ix.close()
+        ix, lo, hi = ctx.synth_shard(1, a.rows, a.dim, shards=r_shards, shard=r_shard)
+        sharded = ShardedGpuIndex(ix, query_groups=qg)
+    my_q = query_block(a.batch, qg, q_group)
     for _ in range(max(a.warmup, 3)):
         search(d_queries)
     ctx.barrier()
@@ -476,7 +507,7 @@ def run_headline(ctx):
                         "traffic_source": traffic_src, "kernel": "scan_topk_fast_kernel", "peak_source": peak_src}
         roofline.update({"launches_timed": prof["scan_launches"], "avg_launch_ms": avg_ms,
                          "bytes_per_launch": bytes_per_launch,
-                         "queries_per_launch": a.batch * a.steps / scan_launches,
+                         "queries_per_launch": (my_q[1] - my_q[0]) * a.steps / scan_launches,
                          "scan_share_of_step": prof["scan_ms"] / elapsed_ms if elapsed_ms else None,
                          "redo_queries": prof["redo_queries"]})
         line = {
@@ -491,24 +522,28 @@ def run_headline(ctx):
             "gpu_launches": prof["scan_launches"] + prof["merge_launches"] + prof["other_launches"],
             "clocks": clocks,
         }
+        if row_shards_only is not None:
+            line["row_shards_only"] = row_shards_only
     # CPU leg + oracle parity of the timed result.  The CPU leg scans the SAME corpus with the SAME first
     # queries, so the comparison is free at N = 1; at N > 1 rank 0 runs the oracle once for the parity alone.
     if rank == 0 and not a.no_cpu_baseline:
         from oracle import fs_oracle as fo
 
         nq = max(1, min(a.cpu_queries, a.batch))
+        # the first and the last queries of the batch: both query groups of the R x Q layout are checked
+        par_idx = sorted(set(list(range((nq + 1) // 2)) + [a.batch - 1 - i for i in range(nq // 2)]))
         host = ctx.host_slab(1, a.rows, a.dim)
         if world == 1:
-            r = cpu_arm(a, steps=2, warmup=1, slab=host, queries=[q_np[i] for i in range(nq)])
+            r = cpu_arm(a, steps=2, warmup=1, slab=host, queries=[q_np[i] for i in par_idx])
             line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "port",
                                     "sample": r["sample"], "cpu": cpu_model(), "per_query_ms": r["per_query_ms"]}
         rows_ok = bits_ok = e2e_ok = True
-        for b in range(nq):
+        for b in par_idx:
             o_rows, o_scores = fo.search_top_k(host, q_np[b], a.k, threads=fo.host_threads())
             re_, be_ = _hits_parity(got_hits[b, :, 0].view(np.uint32), got_hits[b, :, 1].view(np.float32), o_rows, o_scores)
             r2, b2 = _hits_parity(e2e_hits[b, :, 0].view(np.uint32), e2e_hits[b, :, 1].view(np.float32), o_rows, o_scores)
             rows_ok, bits_ok, e2e_ok = rows_ok and re_, bits_ok and be_, e2e_ok and r2 and b2
-        line["parity"] = {"queries": nq, "rows_equal": rows_ok, "score_bits_equal": bits_ok,
+        line["parity"] = {"queries": len(par_idx), "query_indices": par_idx, "rows_equal": rows_ok, "score_bits_equal": bits_ok,
                           "e2e_result_equal": e2e_ok, "against": "oracle fs_oracle.search_top_k on the identical corpus",
                           "checked": "the merged result of the last timed step" if world > 1 else "the result of the last timed step"}
     ctx.barrier()

@@ -874,9 +874,11 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
         // sample levels: strided tiles, each level's k'-th best gates the next
         const uint64_t level_tiles[2] = {cas.t0 < cas.n_tiles ? cas.t0 : 0, cas.t1};
         bool have_gate = false;
+        uint64_t stride1 = 0;  // tile stride of the second sample level (its lists can be carried into the full pass)
         for (int lvl = 0; lvl < 2; ++lvl) {
             if (!level_tiles[lvl]) continue;
             a.tile_stride = env_int("FSGPU_MMA_SAMPLE_CONTIG", 0) ? 1 : cas.n_tiles / level_tiles[lvl];
+            if (lvl == 1) stride1 = a.tile_stride;
             a.tile_count = level_tiles[lvl];
             a.dump_group_max = (lvl == 0 && cas.group_max) ? 1u : 0u;
             a.gate = have_gate ? ix->ws_gate.as<float>() : nullptr;
@@ -940,6 +942,16 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
         }
         a.gate = have_gate ? ix->ws_gate.as<float>() : nullptr;
         a.progress = paced ? progress_of(2) : nullptr;
+        // quad form: the second sample level's tiles are not scanned twice — its lists stay in place, every thread
+        // compacts its list against the final gate and the full pass appends behind it (FSGPU_MMA_CARRY=0: off)
+        const bool carry = quad && level_tiles[1] && stride1 >= 1 && cas.n_tiles < (1ull << 31) && level_tiles[1] < cas.n_tiles &&
+                           env_int("FSGPU_MMA_CARRY", 1) != 0;
+        if (carry) {
+            a.skip_stride = (uint32_t)stride1;
+            a.skip_count = (uint32_t)level_tiles[1];
+            a.carry = 1;
+        }
+        const double scanned = carry ? (double)(cas.n_tiles - level_tiles[1]) / (double)cas.n_tiles : 1.0;
         std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
         if (ix->profiling) {
             if (!ix->ev_free.empty()) {
@@ -960,12 +972,12 @@ static int search_mma_locked(const fsgpu_index* ix, const float* d_queries, uint
             ix->ev_pending.push_back(ev);
         }
         ix->prof.scan_launches += 1;
-        ix->prof.scan_bytes += ix->n_rows * ix->dim * (i8 ? 1ull : 2ull);
+        ix->prof.scan_bytes += (uint64_t)((double)(ix->n_rows * ix->dim * (i8 ? 1ull : 2ull)) * scanned);
         ix->prof.mma_launches += 1;
         ix->prof.i8_launches += i8 ? 1 : 0;
         ix->prof.quad_launches += quad ? 1 : 0;
         ix->prof.pair_launches += (pair && !quad) ? 1 : 0;
-        ix->prof.mma_flops += 2.0 * (double)slots * (double)ix->n_rows * (double)ix->dim;
+        ix->prof.mma_flops += 2.0 * (double)slots * (double)ix->n_rows * (double)ix->dim * scanned;
         ix->prof.merge_launches += 1;  // refine
 
         MmaRefineArgs r{};

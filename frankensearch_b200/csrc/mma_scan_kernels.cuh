@@ -61,6 +61,11 @@ struct MmaScanArgs {
     // pseudo-random tile per stratum (a constant stride camps on a few HBM channels: a strided
     // sample pass ran at 140 GB/s, profiles/r01_mma_v3_L1_strided_ncu.json)
     uint64_t tile_stride, tile_count;
+    // full pass of the quad kernel after a sample level whose lists are still in place: the tiles that level
+    // scanned (tile_of(i) for i < skip_count under stride skip_stride) are not scanned again — their rows above
+    // this pass's gate are already in the lists (`carry`: every thread first compacts its list against its gate
+    // and appends behind it).  Sound because every level's gate is a lower bound of the next one's.
+    uint32_t skip_stride, skip_count, carry;
     uint32_t dump_group_max;   // first sample level: append only the best score of every 8-row group
     const float* gate;         // [n_qblocks*128] static per-query gate (nullptr = -inf: keep everything)
     const float* qscale;       // int8 form only: [n_qblocks*128] score = accumulator * qscale[query]
@@ -920,6 +925,15 @@ mma_scan_quad_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     const uint32_t g = args.ctas_per_qblock;  // CTA pairs per query quad
     // this CTA's query block of sub-block s: ((quad * 2 + s) * 2 + rank)
     auto qb_of = [&](uint32_t sub) { return (quad * 2u + sub) * 2u + rank; };
+    // tile i of the full pass was scanned by the carried sample level (32-bit restatement of mma_tile_of)
+    const uint32_t skip_s = args.skip_stride, skip_c = args.skip_count;
+    auto skipped = [&](uint64_t i) -> bool {
+        if (!skip_c) return false;
+        const uint32_t t = (uint32_t)i, idx = t / skip_s;
+        if (idx >= skip_c) return false;
+        const uint32_t jitter = skip_s > 1u ? ((idx * 0x9E3779B1u) >> 8) % skip_s : 0u;
+        return t == idx * skip_s + jitter;
+    };
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_q);
@@ -973,7 +987,7 @@ mma_scan_quad_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                 }
             }
             __syncwarp();
-            for (uint32_t kb = 0; kb < args.n_kblocks; ++kb) {
+            for (uint32_t kb = 0; kb < (skipped(i) ? 0u : args.n_kblocks); ++kb) {
                 mbar_wait(empty_bar(stage), phase ^ 1u);
                 if (elect_one()) {
                     if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * kMmaTileBytes);
@@ -1007,6 +1021,7 @@ mma_scan_quad_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
                 // elect + reconvergence + eight vector->uniform register moves per K-block the issuer needed
                 // 700-1200 cycles per group (timestamps, FSGPU_MMA_TS), and a group whose last four MMAs (512
                 // cycles) are issued that late cannot finish inside its 1536-cycle slot.
+                if (skipped(i)) continue;
                 const uint32_t stage0 = stage;
                 for (uint32_t kb = 0; kb < n_kb; ++kb) {  // the tile's stages have landed (they are requested together)
                     mbar_wait(full_bar(stage), phase);
@@ -1065,9 +1080,25 @@ mma_scan_quad_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             list_id[sub] = (((size_t)blockIdx.x * kSub + sub) * kParts + part) * kMmaM + m;
             list[sub] = args.cand + list_id[sub] * args.cap;
             count[sub] = 0;
+            if (args.carry) {
+                const uint32_t old = args.cand_count[list_id[sub]];
+                if (old > args.cap) {
+                    count[sub] = old;  // the sample level overflowed this list: it stays flagged (the query is redone)
+                } else if (live[sub]) {
+                    // keep what clears this pass's gate (four accumulator units of slack: a superset is always safe)
+                    const float gf = args.gate ? args.gate[query] - 4.0f * fabsf(qscale[sub]) : -INFINITY;
+                    uint32_t n = 0;
+                    for (uint32_t e = 0; e < old; ++e) {
+                        const MmaCand c = list[sub][e];
+                        if (c.score >= gf) list[sub][n++] = c;
+                    }
+                    count[sub] = n;
+                }
+            }
         }
         uint32_t acc_phase = 0, li = 0;
         for (uint64_t i = j0; i < args.tile_count; i += g, ++li) {
+            if (skipped(i)) continue;
             const uint64_t tile = mma_tile_of(args, i);
 #pragma unroll
             for (uint32_t sub = 0; sub < kSub; ++sub) {

@@ -129,6 +129,57 @@ def test_sharded_search_equals_single_index_over_gloo():
         assert np.array_equal(ret[0][b], want)
 
 
+def _grid_worker(rank, world, port, slab, queries, k, query_groups, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        r_shards, r, _g = sharded.grid_position(world, rank, query_groups)
+        lo, hi = sharded.shard_bounds(slab.shape[0], r_shards, r)
+        ix = sharded.ShardedGpuIndex(None, local_search=_np_local_search(slab[lo:hi], lo), merge=_np_merge,
+                                     query_groups=query_groups)
+        out = []
+        for b in (queries.shape[0], 1):  # a ragged split, then a batch that leaves the second group empty
+            keys, _, _ = ix.search_top_k_device(torch.from_numpy(queries[:b]), k)
+            out.append(keys.numpy().view(np.uint64).copy())
+        ret[rank] = out
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,query_groups", [(2, 2), (4, 2)])
+def test_row_shards_x_query_groups_equal_single_index_over_gloo(world, query_groups):
+    """R row shards x Q query groups (rank = g*R + r searches its query block over its row shard): one all-gather,
+    one merge per group == the unsharded answer, for a ragged and for a one-query batch."""
+    from oracle import fs_oracle as fo
+
+    slab, _ = fo.synth_rows(1, 1, 0, 3001, 128)
+    slab[700] = slab[2500]  # an exact cross-shard tie
+    queries = np.stack([fo.clustered_query(q, 128) for q in range(5)])
+    k = 12
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 31500 + (os.getpid() + 7 * world) % 2000
+    mp.spawn(_grid_worker, args=(world, port, slab, queries, k, query_groups, ret), nprocs=world, join=True)
+    for i, b in enumerate((5, 1)):
+        for r in range(1, world):
+            assert np.array_equal(ret[0][i], ret[r][i])
+        assert ret[0][i].shape == (b, k)
+        for q in range(b):
+            rows, scores = fo.search_top_k(slab, queries[q], k)
+            assert np.array_equal(ret[0][i][q], ~no.order_keys(scores, rows))
+
+
+def test_grid_position_and_query_blocks():
+    assert [sharded.grid_position(8, r, 2) for r in (0, 3, 4, 7)] == [(4, 0, 0), (4, 3, 0), (4, 0, 1), (4, 3, 1)]
+    assert sharded.grid_position(2, 1, 2) == (1, 0, 1) and sharded.grid_position(4, 3, 1) == (4, 3, 0)
+    with pytest.raises(Exception):
+        sharded.grid_position(6, 0, 4)
+    assert [sharded.query_block(1024, 2, g) for g in range(2)] == [(0, 512), (512, 1024)]
+    assert [sharded.query_block(5, 2, g) for g in range(2)] == [(0, 3), (3, 5)]
+    assert [sharded.query_block(1, 2, g) for g in range(2)] == [(0, 1), (1, 1)]
+
+
 # ── sharded two-tier pipeline plumbing over gloo, world_size 2 ───────────────────────────────
 def _pipeline_worker(rank, world, port, fast_slab, quality_slab, fq, qq, k, lex_ids, lex_scores, ret):
     os.environ["MASTER_ADDR"] = "127.0.0.1"

@@ -95,6 +95,24 @@ def main():
                 if not ok:
                     bad += 1
                     print(f"rank {rank}: MISMATCH k={k} batch={batch} rep={rep}", flush=True)
+    # R row shards x 2 query groups (rank = g*R + r): same answer, ragged and one-query batches included
+    if world % 2 == 0:
+        from frankensearch_b200.sharded import grid_position
+
+        r_shards, r, _g = grid_position(world, rank, 2)
+        glo, ghi = shard_bounds(rows, r_shards, r)
+        gshard = fs.GpuVectorIndex.from_device_tensor(synth(local, glo, ghi - glo, dim), row_base=glo)
+        grid = ShardedGpuIndex(gshard, query_groups=2)
+        for k in (1, 10, 100):
+            for batch in (1, 2, 5, 64, 300):
+                q = q_all[:batch].contiguous()
+                for rep in range(2):
+                    keys, hits, counts = grid.search_top_k_device(q, k)
+                    wkeys, whits, wcounts = whole.search_top_k_device(q, k)
+                    torch.cuda.synchronize()
+                    if not (torch.equal(keys, wkeys) and torch.equal(hits, whits) and torch.equal(counts, wcounts)):
+                        bad += 1
+                        print(f"rank {rank}: GRID MISMATCH k={k} batch={batch} rep={rep}", flush=True)
     bad += check_two_tier(rank, world, local, dev, rows)
     t = torch.tensor([bad], device=dev)
     dist.all_reduce(t)
