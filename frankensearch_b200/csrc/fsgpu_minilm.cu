@@ -370,6 +370,14 @@ static int minilm_fast_enqueue(const fsgpu_minilm* e, const int32_t* d_ids, cons
             fa.bias1 = L.ffn_in_b;
             fa.bias2 = L.ffn_out_b;
             fa.dbg = (uint32_t)env_int("FSGPU_MINILM_FFN_DBG", 0);
+            const bool ln_fused = env_int("FSGPU_MINILM_FFN_LN", 1) != 0;  // residual + LayerNorm in the kernel's final epilogue
+            if (ln_fused) {
+                fa.h16 = h16;
+                fa.ln_g = L.ffn_ln_g;
+                fa.ln_b = L.ffn_ln_b;
+                fa.h32 = last ? h32 : nullptr;
+                fa.eps = e->eps;
+            }
             long long* d_ts = nullptr;
             if (li == 0 && env_int("FSGPU_MINILM_FFN_TS", 0) != 0) {  // debugging aid (never with a captured graph)
                 CUDA_TRY(cudaMalloc(&d_ts, 24 * 8 * sizeof(long long)));
@@ -411,9 +419,11 @@ static int minilm_fast_enqueue(const fsgpu_minilm* e, const int32_t* d_ids, cons
             }
             e->prof.gemm_launches += 2;  // two linears
             e->prof.gemm_flops += 2.0 * 2.0 * (double)m * kHidden * e->inter;
-            minilm_fast_ln_kernel<<<row_blocks, 256, 0, s>>>(pre32, h16, rows, L.ffn_ln_g, L.ffn_ln_b, e->eps, last ? h32 : nullptr);
-            CUDA_TRY(cudaGetLastError());
-            e->prof.other_launches += 3;
+            if (!ln_fused) {
+                minilm_fast_ln_kernel<<<row_blocks, 256, 0, s>>>(pre32, h16, rows, L.ffn_ln_g, L.ffn_ln_b, e->eps, last ? h32 : nullptr);
+                CUDA_TRY(cudaGetLastError());
+            }
+            e->prof.other_launches += ln_fused ? 2 : 3;
             continue;
         }
         rc = lin384(e, e->f_tm_h, L.ffn_in, e->f_tm_ffn_out, m, L.ffn_in_b, 1, s);
@@ -481,7 +491,7 @@ static int minilm_embed_fast_locked(const fsgpu_minilm* e, const int32_t* d_ids,
     CUDA_TRY(e->g_lens.reserve(4096 * 4));
     CUDA_TRY(e->g_out.reserve((size_t)4096 * H * 4));
     const uint64_t key = ((uint64_t)batch << 32) | ((uint64_t)max_len << 8) | (ares ? 1u : 0u) | (ffn_out_pair ? 2u : 0u) |
-                         (env_int("FSGPU_MINILM_FFN_FUSED", 1) != 0 ? 4u : 0u);
+                         (env_int("FSGPU_MINILM_FFN_FUSED", 1) != 0 ? 4u : 0u) | (env_int("FSGPU_MINILM_FFN_LN", 1) != 0 ? 8u : 0u);
     const void* bufs[9] = {e->f_h.p, e->f_qkv.p, e->f_ctx.p, e->f_ffn.p, e->ws_pre32.p, e->ws_h32.p, e->g_ids.p, e->g_lens.p, e->g_out.p};
     if (e->f_graphs.size() >= 64 && !e->f_graphs.count(key)) {  // bounded cache: shapes are few in practice
         for (auto& kv : e->f_graphs)

@@ -533,6 +533,13 @@ struct FfnArgs {
                          // 2 issuer ignores g_full, 4 G2 MMAs not issued, 8 weight boxes loaded once (no TMA after the
                          // first ring fill), 16 G1 MMAs not issued
     long long* ts;       // FSGPU_MINILM_FFN_TS: clock64 stamps of pair 0's issuer and first epilogue warp, 8 per chunk, 24 chunks
+    // residual + LayerNorm in the final epilogue (ln_g != nullptr): h = LayerNorm(acc2 + bias2 + h) written in place as
+    // f16 (and as f32 to h32 when given: the last layer feeds the pooling kernel); nothing goes to tm_out then
+    __half* h16;         // [m x 384] the layer input = the residual; overwritten with the layer output
+    const float* ln_g;   // [384]
+    const float* ln_b;   // [384]
+    float* h32;          // [m x 384] or nullptr
+    float eps;
 };
 
 __host__ __device__ inline size_t ffn_fused_smem_bytes() {
@@ -561,6 +568,7 @@ ffn_fused_pair_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_con
     auto g_full = [&](uint32_t b) { return bar0 + 8u * (30u + b); };
     auto g_empty = [&](uint32_t b) { return bar0 + 8u * (32u + b); };
     const uint32_t acc2_full = bar0 + 8u * 34u, acc2_empty = bar0 + 8u * 35u;
+    const uint32_t res_done = bar0 + 8u * 36u;  // fused LayerNorm: this CTA's epilogue warps have read the residual out of the h tile
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 40);
     float* bias2_s = reinterpret_cast<float*>(bars + 64);  // the FFN-in bias has no room here: see the epilogue
     for (uint32_t i = threadIdx.x; i < 384u; i += blockDim.x) bias2_s[i] = args.bias2[i];
@@ -591,6 +599,7 @@ ffn_fused_pair_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_con
         }
         mbar_init(acc2_full, 1);
         mbar_init(acc2_empty, 2 * kFfnEpiWarps);
+        mbar_init(res_done, kFfnEpiWarps);
         fence_barrier_init();
     } else if (warp == 0) {
         tmem_alloc_pair(smem_u32(tmem_slot), 512);
@@ -631,6 +640,7 @@ ffn_fused_pair_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_con
                 load_w(&tm_w2_64, (int32_t)(c * 128u), (int32_t)(part * 128u + rank * 64u));
         };
         auto load_h = [&](uint32_t mt) {  // the tile's h blocks, each as soon as the previous tile's last G1 has read it
+            if (tiles_done && args.ln_g) mbar_wait(res_done, (tiles_done - 1u) & 1u);
             for (uint32_t kb = 0; kb < kFfnHKb; ++kb) {
                 if (tiles_done) mbar_wait(h_empty(kb), (tiles_done - 1u) & 1u);
                 if (elect_one()) {
@@ -648,8 +658,11 @@ ffn_fused_pair_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_con
                 if (c) load_g2(c - 1u);
             }
             ++tiles_done;
-            if (mt + n_pairs < m_tiles) load_h(mt + n_pairs);  // before the last G2's weights: lands under G2(10), G2(11)
+            // unfused: before the last G2's weights, so that it lands under G2(10), G2(11); fused LayerNorm: the final
+            // epilogue still reads the residual out of the tile (res_done), and that epilogue needs G2(11)'s weights first
+            if (!args.ln_g && mt + n_pairs < m_tiles) load_h(mt + n_pairs);
             load_g2(kFfnChunks - 1u);
+            if (args.ln_g && mt + n_pairs < m_tiles) load_h(mt + n_pairs);
         }
     } else if (warp == kFfnEpiWarps + 1) {
         if (rank == 0 && elect_one()) {
@@ -794,10 +807,110 @@ ffn_fused_pair_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_con
                 if (ts_on && n_acc1 <= 24) args.ts[(n_acc1 - 1) * 8 + 7] = clock64();
                 ++n_g[buf];
             }
-            // final: acc2 + bias2 -> f32 pre, 96 columns per warp as three [32 x 32] boxes through this warp's 4 KiB of
-            // the g buffers (free: acc2_full implies every G2 of the tile has completed)
             mbar_wait(acc2_full, tiles_done & 1u);
             tc_fence_after();
+            if (args.ln_g) {
+                // final, fused form: x = acc2 + bias2 + residual, LayerNorm over the row's 384 features (two-pass statistics
+                // in f32 as the stand-alone kernel computes them), h written in place.  A row's features sit in four threads
+                // (same lane, the four column parts): partial sums meet in shared memory (the g buffers are free: acc2_full
+                // implies every G2 of the tile has completed).  Pass 1 reads the residual out of the resident h tile (the
+                // swizzled A operand), writes x BACK into the accumulator's TMEM columns and sums it; the h tile is then
+                // released to the producer (res_done); passes 2 (variance) and 3 (output) read x from TMEM only — 96 values
+                // per thread never sit in registers.  (Residual reads from global memory instead: 36 us per launch, latency.)
+                float* red = reinterpret_cast<float*>(g_ptr);  // [2][128 rows][4 parts]
+                float* gb_s = red + 1024;                      // gamma [384] | beta [384]
+                const uint32_t et = threadIdx.x;               // 0 .. 511 (the epilogue warps are warps 0 .. 15)
+                if (et < 384u) gb_s[et] = args.ln_g[et];  // 512 threads stage the 768 values in two steps
+                else gb_s[et] = args.ln_b[et - 384u];
+                if (et < 256u) gb_s[512u + et] = args.ln_b[128u + et];
+                const uint32_t row = mt * 256u + rank * 128u + row_l;
+                const bool row_ok = row < args.m;
+                const size_t off = (size_t)row * 384u + part * 96u;
+                const uint32_t tcol = tmem_base + ((quarter * 32u) << 16) + acc2_col + part * 96u;
+                const uint8_t* h_row = base_ptr + row_l * 128u;  // this row inside every [128 x 64] K-block of the h tile
+                float acc = 0.0f;
+#pragma unroll 1
+                for (uint32_t b = 0; b < 3; ++b) {
+                    uint32_t w2[32];
+                    tmem_ld_x32(tcol + b * 32u, w2);
+                    uint4 r4[4];
+#pragma unroll
+                    for (uint32_t i = 0; i < 4; ++i) {
+                        const uint32_t col0 = part * 96u + b * 32u + i * 8u;
+                        r4[i] = *reinterpret_cast<const uint4*>(h_row + (size_t)(col0 >> 6) * kMmaTileBytes + ((((col0 >> 3) & 7u) ^ sw) << 4));
+                    }
+                    tmem_ld_wait();
+                    const __half2* rh = reinterpret_cast<const __half2*>(r4);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {
+                        const float2 r = __half22float2(rh[j / 2]);
+                        const uint32_t col = part * 96u + b * 32u + (uint32_t)j;
+                        const float x0 = __uint_as_float(w2[j]) + bias2_s[col] + r.x;
+                        const float x1 = __uint_as_float(w2[j + 1]) + bias2_s[col + 1u] + r.y;
+                        acc += x0;
+                        acc += x1;
+                        w2[j] = __float_as_uint(x0);
+                        w2[j + 1] = __float_as_uint(x1);
+                    }
+                    tmem_st_x32(tcol + b * 32u, w2);
+                }
+                tmem_st_wait();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(res_done);  // the residual has been read: the producer may load the next h tile
+                red[row_l * 4u + part] = acc;
+                asm volatile("bar.sync 1, %0;" ::"r"(kFfnEpiWarps * 32) : "memory");
+                const float mean = ((red[row_l * 4u] + red[row_l * 4u + 1u]) + (red[row_l * 4u + 2u] + red[row_l * 4u + 3u])) * (1.0f / 384.0f);
+                acc = 0.0f;
+#pragma unroll 1
+                for (uint32_t b = 0; b < 3; ++b) {
+                    uint32_t w2[32];
+                    tmem_ld_x32(tcol + b * 32u, w2);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float d = __uint_as_float(w2[j]) - mean;
+                        acc = fmaf(d, d, acc);
+                    }
+                }
+                red[512u + row_l * 4u + part] = acc;
+                asm volatile("bar.sync 1, %0;" ::"r"(kFfnEpiWarps * 32) : "memory");
+                const float var_eps = ((red[512u + row_l * 4u] + red[512u + row_l * 4u + 1u]) + (red[512u + row_l * 4u + 2u] + red[512u + row_l * 4u + 3u])) *
+                                          (1.0f / 384.0f) + args.eps;
+                const float inv = rsqrtf(var_eps);
+                const float inv2 = inv * (1.5f - 0.5f * var_eps * inv * inv);  // one Newton step (as layernorm_row)
+#pragma unroll 1
+                for (uint32_t b = 0; b < 3; ++b) {
+                    uint32_t w2[32];
+                    tmem_ld_x32(tcol + b * 32u, w2);
+                    tmem_ld_wait();
+                    if (b == 2) {  // last read of the accumulator: hand it back
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(acc2_empty, 0);
+                    }
+                    if (!row_ok) continue;
+                    const float* gs = gb_s + part * 96u + b * 32u;
+                    float x[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) x[j] = (__uint_as_float(w2[j]) - mean) * inv2 * gs[j] + gs[384 + j];
+                    __half2 hh[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) hh[j] = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        *reinterpret_cast<uint4*>(args.h16 + off + b * 32u + (uint32_t)i * 8u) = reinterpret_cast<const uint4*>(hh)[i];
+                    if (args.h32) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            *reinterpret_cast<float4*>(args.h32 + off + b * 32u + (uint32_t)i * 4u) = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+                    }
+                }
+                // every warp's reads of the statistics must be over before any warp writes g values of the next tile over them
+                asm volatile("bar.sync 1, %0;" ::"r"(kFfnEpiWarps * 32) : "memory");
+                continue;
+            }
+            // final, unfused form: acc2 + bias2 -> f32 pre, 96 columns per warp as three [32 x 32] boxes through this warp's 4 KiB of
+            // the g buffers (free: acc2_full implies every G2 of the tile has completed)
             const uint32_t row0 = mt * 256u + rank * 128u + quarter * 32u;
             uint8_t* st_ptr = g_ptr + (size_t)warp * 4096u;
             const uint32_t st_smem = g_smem + warp * 4096u;
