@@ -48,6 +48,7 @@ struct fsgpu_minilm {
     mutable DevBuf f_h, f_qkv, f_ctx, f_ffn;
     mutable CUtensorMap f_tm_h, f_tm_ctx, f_tm_ffn;             // A operands: [128 rows x 64] boxes
     mutable CUtensorMap f_tm_qkv_out, f_tm_ffn_out, f_tm_pre;  // stores: f16 [64 x 32] boxes, f32 [32 x 32] boxes
+    mutable CUtensorMap f_tm_h_out;                             // store: f16 [64 x 32] boxes over h (fused FFN + LayerNorm)
     mutable uint64_t f_rows = 0;
     mutable float* f_pre_ptr = nullptr;
     // small batches replay a captured CUDA graph of the forward (44 launches of a few microseconds each are bound by
@@ -398,7 +399,7 @@ static int minilm_fast_enqueue(const fsgpu_minilm* e, const int32_t* d_ids, cons
                 CUDA_TRY(cudaEventRecord(ev.first, s));
             }
             ffn_fused_pair_kernel<<<grid, kFfnThreads, ffn_fused_smem_bytes(), s>>>(e->f_tm_h, L.ffn_in.tm64_hi, L.ffn_out.tm64_hi,
-                                                                                    e->f_tm_pre, fa);
+                                                                                    e->f_tm_pre, e->f_tm_h_out, fa);
             CUDA_TRY(cudaGetLastError());
             if (e->profiling) {
                 CUDA_TRY(cudaEventRecord(ev.second, s));
@@ -460,7 +461,8 @@ static int minilm_embed_fast_locked(const fsgpu_minilm* e, const int32_t* d_ids,
                         make_f16_tile_map(&e->f_tm_ffn, e->f_ffn.p, rows, I) &&
                         make_tile_map_2d(&e->f_tm_qkv_out, e->f_qkv.p, rows, 3 * H, 2, 64, 32) &&
                         make_tile_map_2d(&e->f_tm_ffn_out, e->f_ffn.p, rows, I, 2, 64, 32) &&
-                        make_tile_map_2d(&e->f_tm_pre, e->ws_pre32.p, rows, H, 4, 32, 32);
+                        make_tile_map_2d(&e->f_tm_pre, e->ws_pre32.p, rows, H, 4, 32, 32) &&
+                        make_tile_map_2d(&e->f_tm_h_out, e->f_h.p, rows, H, 2, 64, 32);
         if (!ok) return fail(FSGPU_ERR_SUBSYSTEM, "gpu: cuTensorMapEncodeTiled failed for a minilm activation");
         e->f_rows = rows;
         e->f_pre_ptr = e->ws_pre32.as<float>();

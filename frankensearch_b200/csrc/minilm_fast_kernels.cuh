@@ -534,8 +534,8 @@ struct FfnArgs {
                          // first ring fill), 16 G1 MMAs not issued
     long long* ts;       // FSGPU_MINILM_FFN_TS: clock64 stamps of pair 0's issuer and first epilogue warp, 8 per chunk, 24 chunks
     // residual + LayerNorm in the final epilogue (ln_g != nullptr): h = LayerNorm(acc2 + bias2 + h) written in place as
-    // f16 (and as f32 to h32 when given: the last layer feeds the pooling kernel); nothing goes to tm_out then
-    __half* h16;         // [m x 384] the layer input = the residual; overwritten with the layer output
+    // f16 through tm_h_out (and as f32 to h32 when given: the last layer feeds the pooling kernel); nothing goes to tm_out then
+    __half* h16;         // [m x 384] the layer input = the residual (read from the resident tile); tm_h_out stores over it
     const float* ln_g;   // [384]
     const float* ln_b;   // [384]
     float* h32;          // [m x 384] or nullptr
@@ -549,7 +549,7 @@ __host__ __device__ inline size_t ffn_fused_smem_bytes() {
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFfnThreads, 1)
 ffn_fused_pair_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_constant__ CUtensorMap tm_w1_64,
                       const __grid_constant__ CUtensorMap tm_w2_64, const __grid_constant__ CUtensorMap tm_out,
-                      const FfnArgs args) {
+                      const __grid_constant__ CUtensorMap tm_h_out, const FfnArgs args) {
     extern __shared__ uint8_t smem_dyn[];
     const uint32_t raw = smem_u32(smem_dyn);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -583,6 +583,7 @@ ffn_fused_pair_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_con
         tma_prefetch_desc(&tm_w1_64);
         tma_prefetch_desc(&tm_w2_64);
         tma_prefetch_desc(&tm_out);
+        tma_prefetch_desc(&tm_h_out);
         for (uint32_t s = 0; s < kFfnStages; ++s) {
             mbar_init(w_full(s), 1);
             mbar_init(w_empty(s), 1);
@@ -825,7 +826,6 @@ ffn_fused_pair_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_con
                 if (et < 256u) gb_s[512u + et] = args.ln_b[128u + et];
                 const uint32_t row = mt * 256u + rank * 128u + row_l;
                 const bool row_ok = row < args.m;
-                const size_t off = (size_t)row * 384u + part * 96u;
                 const uint32_t tcol = tmem_base + ((quarter * 32u) << 16) + acc2_col + part * 96u;
                 const uint8_t* h_row = base_ptr + row_l * 128u;  // this row inside every [128 x 64] K-block of the h tile
                 float acc = 0.0f;
@@ -878,32 +878,59 @@ ffn_fused_pair_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_con
                                           (1.0f / 384.0f) + args.eps;
                 const float inv = rsqrtf(var_eps);
                 const float inv2 = inv * (1.5f - 0.5f * var_eps * inv * inv);  // one Newton step (as layernorm_row)
+                // output: twelve warps (column parts 0..2) take two [32 rows x 64 features] boxes each — f16 rows of 128 bytes,
+                // written swizzled into 4 KiB of the g buffers and stored by TMA (full row segments; 16-byte stores of one
+                // row per lane cost 6 k LSU cycles per tile); part 3 only hands the accumulator back
+                const uint32_t trow = tmem_base + ((quarter * 32u) << 16) + acc2_col;
+                if (part == 3u) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(acc2_empty, 0);
+                } else {
+                    uint8_t* st_ptr = g_ptr + 8192u + (size_t)(quarter * 3u + part) * 4096u;
+                    const uint32_t st_smem = g_smem + 8192u + (quarter * 3u + part) * 4096u;
+                    const uint32_t row0 = mt * 256u + rank * 128u + quarter * 32u;
 #pragma unroll 1
-                for (uint32_t b = 0; b < 3; ++b) {
-                    uint32_t w2[32];
-                    tmem_ld_x32(tcol + b * 32u, w2);
-                    tmem_ld_wait();
-                    if (b == 2) {  // last read of the accumulator: hand it back
-                        tc_fence_before();
+                    for (uint32_t bi = 0; bi < 2; ++bi) {
+                        const uint32_t c0 = (2u * part + bi) * 64u;  // first feature of the box
+                        if (lane == 0) tma_store_wait_read();       // the previous box has left the staging buffer
                         __syncwarp();
-                        if (lane == 0) mbar_arrive_cluster(acc2_empty, 0);
+#pragma unroll 1
+                        for (uint32_t hf = 0; hf < 2; ++hf) {
+                            uint32_t w2[32];
+                            tmem_ld_x32(trow + c0 + hf * 32u, w2);
+                            tmem_ld_wait();
+                            if (bi == 1 && hf == 1) {  // last read of the accumulator: hand it back
+                                tc_fence_before();
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive_cluster(acc2_empty, 0);
+                            }
+                            const float* gs = gb_s + c0 + hf * 32u;
+                            float x[32];
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) x[j] = (__uint_as_float(w2[j]) - mean) * inv2 * gs[j] + gs[384 + j];
+#pragma unroll
+                            for (uint32_t i = 0; i < 4; ++i) {
+                                __half2 hh[4];
+#pragma unroll
+                                for (uint32_t q = 0; q < 4; ++q) hh[q] = __floats2half2_rn(x[8 * i + 2 * q], x[8 * i + 2 * q + 1]);
+                                *reinterpret_cast<uint4*>(st_ptr + lane * 128u + (((hf * 4u + i) ^ (lane & 7u)) << 4)) = *reinterpret_cast<const uint4*>(hh);
+                            }
+                            if (args.h32 && row_ok) {
+                                float* o32 = args.h32 + (size_t)row * 384u + c0 + hf * 32u;
+#pragma unroll
+                                for (int i = 0; i < 8; ++i)
+                                    *reinterpret_cast<float4*>(o32 + 4 * i) = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+                            }
+                        }
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0 && row0 < args.m) {
+                            tma_store_2d(&tm_h_out, st_smem, (int32_t)c0, (int32_t)row0);  // rows past m are clipped by the map
+                            tma_store_commit();
+                        }
                     }
-                    if (!row_ok) continue;
-                    const float* gs = gb_s + part * 96u + b * 32u;
-                    float x[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) x[j] = (__uint_as_float(w2[j]) - mean) * inv2 * gs[j] + gs[384 + j];
-                    __half2 hh[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) hh[j] = __floats2half2_rn(x[2 * j], x[2 * j + 1]);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        *reinterpret_cast<uint4*>(args.h16 + off + b * 32u + (uint32_t)i * 8u) = reinterpret_cast<const uint4*>(hh)[i];
-                    if (args.h32) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            *reinterpret_cast<float4*>(args.h32 + off + b * 32u + (uint32_t)i * 4u) = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
-                    }
+                    if (lane == 0) tma_store_wait_read();
                 }
                 // every warp's reads of the statistics must be over before any warp writes g values of the next tile over them
                 asm volatile("bar.sync 1, %0;" ::"r"(kFfnEpiWarps * 32) : "memory");
