@@ -2,6 +2,8 @@
 (both through the C ABI; the per-query path is itself oracle-pinned by tests/).  Adversarial corpora:
 ascending-by-score row order, heavy duplicates, tiny / huge / mixed norms, tombstones, filters.
     python tools/soak_batched.py [n_cases] [seed]   -> exit 1 on the first mismatch
+SOAK_I8=1: the int8 forms instead (FSGPU_I8_MIN_ROWS=0, k <= 32, batches up to 1024 so that the quad kernel, its
+carried sample lists and skipped tiles are exercised on every corpus kind; larger corpora).
 """
 import os
 import sys
@@ -47,12 +49,21 @@ def main():
     rng = np.random.default_rng(seed)
     kinds = ["unit", "clustered", "dups", "tiny", "huge", "mixed", "quantised"]
     redo_total = 0
+    i8 = os.environ.get("SOAK_I8", "0") != "0"
+    if i8:
+        os.environ["FSGPU_I8_MIN_ROWS"] = "0"
+    quad_total = 0
     for case in range(n_cases):
         kind = kinds[case % len(kinds)]
         dim = int(rng.choice([64, 128, 192, 256, 384, 512]))
         n = int(rng.choice([50, 300, 1000, 5000, 20000, 70000, 200000]))
         batch = int(rng.choice([3, 5, 17, 64, 129, 300, 700]))
         k = int(rng.choice([1, 3, 10, 16, 17, 50, 100, 200, 600]))
+        if i8:
+            dim = int(rng.choice([128, 256, 384, 512]))
+            n = int(rng.choice([20000, 70000, 200000, 600000, 1500000]))
+            batch = int(rng.choice([64, 257, 300, 512, 700, 1024]))
+            k = int(rng.choice([1, 3, 10, 17, 32]))
         x = make_corpus(rng, kind, n, dim)
         q = rng.normal(size=(batch, dim)).astype(np.float32)
         if case % 3 == 0:
@@ -78,14 +89,15 @@ def main():
             ok = ok and np.array_equal(r1[b, :m], r2[b, :m]) and \
                 np.array_equal(s1[b, :m].view(np.uint32), s2[b, :m].view(np.uint32))
         redo_total += prof["redo_queries"]
+        quad_total += prof.get("quad_launches", 0)
         tag = f"case {case:3d} {kind:9s} n={n:6d} dim={dim:3d} batch={batch:3d} k={k:3d} " \
-              f"mma={prof['mma_launches']} redo={prof['redo_queries']}"
+              f"mma={prof['mma_launches']} i8={prof.get('i8_launches', 0)} quad={prof.get('quad_launches', 0)} redo={prof['redo_queries']}"
         if not ok or prof["mma_launches"] < 1:
             print("MISMATCH", tag, flush=True)
             sys.exit(1)
-        if case % 10 == 0:
+        if case % 10 == 0 or i8:
             print("ok", tag, flush=True)
-    print(f"soak ok: {n_cases} cases, {redo_total} queries re-run on the exact path")
+    print(f"soak ok: {n_cases} cases, {redo_total} queries re-run on the exact path, {quad_total} quad-kernel full passes")
 
 
 if __name__ == "__main__":
