@@ -554,7 +554,7 @@ def run_headline(ctx):
 def _ncu_tensor_active(i8):
     """sm__pipe_tensor_cycles_active of the committed ncu capture of the headline kernel (context for
     `frac`: a profiler number is never a bench value)."""
-    for name in (("r02_mma_quad_i8_b1024_v2_ncu.json", "r01_mma_quad_i8_b1024_ncu.json") if i8 else
+    for name in (("r02_mma_quad_i8_b1024_v3_carry_ncu.json", "r02_mma_quad_i8_b1024_v2_ncu.json") if i8 else
                  ("r02_mma_pair_f16_b1024_paced_ncu.json", "r01_mma_pair_b1024_ncu.json")):
         try:
             j = json.load(open(os.path.join(ROOT, "profiles", name)))
