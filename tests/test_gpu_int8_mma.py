@@ -146,6 +146,21 @@ def test_int8_one_million_rows_batch_1024(i8_env, fo, monkeypatch):
     torch.cuda.synchronize()
     assert torch.equal(keys[:16], ekeys) and torch.equal(hits[:16], ehits)
     assert p["redo_queries"] == 0, p
+    # the quad full pass keeps the second sample level's lists and skips its tiles (FSGPU_MMA_CARRY, default on): the
+    # same answer as scanning every tile again, and fewer bytes in the full pass's record
+    monkeypatch.setenv("FSGPU_MMA_MIN_BATCH", "3")
+    monkeypatch.setenv("FSGPU_MMA_I8", "1")
+    bytes_of = {}
+    for carry in ("1", "0"):
+        monkeypatch.setenv("FSGPU_MMA_CARRY", carry)
+        ix.profile_read(reset=True)
+        ckeys, chits, ccounts = ix.search_top_k_device(q, 10)
+        torch.cuda.synchronize()
+        pc = ix.profile_read(reset=True)
+        assert pc["quad_launches"] == 1 and pc["redo_queries"] == 0, pc
+        assert torch.equal(keys, ckeys) and torch.equal(hits, chits) and torch.equal(counts, ccounts)
+        bytes_of[carry] = pc["scan_bytes"]
+    assert bytes_of["1"] < bytes_of["0"] == n * dim
     ix.close()
 
 
