@@ -804,8 +804,11 @@ def bench_config4(ctx):
     if ctx.rank == 0:
         d_ids, d_lens = ids_h.to(dev), lens_h.to(dev)
         encoder = {"batch": batch, "tokens_per_query": "4-32 (t_pad 32)", "weights": "synthetic (seeded), all-MiniLM-L6-v2 geometry"}
-        useful_flop = 2.0 * batch * 32 * 6 * (4 * 384 * 384 + 2 * 384 * 1536)
+        flop_per_row = 2.0 * 6 * (4 * 384 * 384 + 2 * 384 * 1536)
+        token_rows = int(lens_h.sum().item())  # the f16 form packs rows (no padding rows); the split form pads to 32
+        encoder["token_rows"] = {"packed (f16 form)": token_rows, "padded (split form)": batch * 32}
         for name, mode in (("f16_form", "0"), ("split_f16_form", "3")):
+            useful_flop = flop_per_row * (token_rows if mode == "0" and os.environ.get("FSGPU_MINILM_PACKED", "1") != "0" else batch * 32)
             os.environ["FSGPU_MINILM_PRODUCTS"] = mode
             for _ in range(3):
                 minilm.embed_device(d_ids, d_lens)

@@ -49,13 +49,15 @@ struct fsgpu_minilm {
     mutable CUtensorMap f_tm_h, f_tm_ctx, f_tm_ffn;             // A operands: [128 rows x 64] boxes
     mutable CUtensorMap f_tm_qkv_out, f_tm_ffn_out, f_tm_pre;  // stores: f16 [64 x 32] boxes, f32 [32 x 32] boxes
     mutable CUtensorMap f_tm_h_out;                             // store: f16 [64 x 32] boxes over h (fused FFN + LayerNorm)
+    mutable DevBuf f_offs;                                   // packed rows: [batch + 1] prefix sums of the lengths
+    mutable const uint32_t* f_m_ptr = nullptr;                  // != nullptr while a packed forward is being enqueued: &offs[batch]
     mutable uint64_t f_rows = 0;
     mutable float* f_pre_ptr = nullptr;
     // small batches replay a captured CUDA graph of the forward (44 launches of a few microseconds each are bound by
     // the host's launch calls): one graph per (batch, max_len, variant), inputs / outputs staged in fixed buffers
     struct FastGraph {
         cudaGraphExec_t exec = nullptr;
-        const void* bufs[9] = {};
+        const void* bufs[10] = {};
     };
     mutable std::map<uint64_t, FastGraph> f_graphs;
     mutable DevBuf g_ids, g_lens, g_out;
@@ -109,7 +111,7 @@ extern "C" void fsgpu_minilm_destroy(fsgpu_minilm* e) {
             if (m->lo) cudaFree(m->lo);
         }
         for (DevBuf* b : {&e->ws_h32, &e->ws_pre32, &e->ws_qkv32, &e->ws_ids, &e->ws_lens, &e->ws_out, &e->f_h, &e->f_qkv, &e->f_ctx,
-                          &e->f_ffn, &e->g_ids, &e->g_lens, &e->g_out})
+                          &e->f_ffn, &e->g_ids, &e->g_lens, &e->g_out, &e->f_offs})
             b->release();
         for (auto& kv : e->f_graphs)
             if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
@@ -273,6 +275,7 @@ static int minilm_fast_gemm(const fsgpu_minilm* e, const CUtensorMap& tm_a, cons
     ga.k = w.cols;
     ga.bias = bias;
     ga.mode = mode;
+    ga.m_ptr = e->f_m_ptr;
     const uint32_t tiles = ((m + 127u) / 128u) * (ga.n / 128u);
     const uint32_t grid = std::min<uint32_t>(tiles, (uint32_t)e->num_sms);
     std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
@@ -305,6 +308,7 @@ static int minilm_ares_gemm(const fsgpu_minilm* e, const CUtensorMap& tm_a, cons
     ga.n = (uint32_t)w.rows;
     ga.k = w.cols;
     ga.bias = bias;
+    ga.m_ptr = e->f_m_ptr;
     ga.mode = mode | (env_int("FSGPU_MINILM_DBG", 0) << 4);
     ga.k_chunks = ga.k > kAresMaxKb * kMmaKBlock ? ga.k / (kAresMaxKb * kMmaKBlock) : 1;
     if (ga.k % ga.k_chunks != 0 || (ga.k / ga.k_chunks) % kMmaKBlock != 0 || (ga.k_chunks > 1 && ga.n > 512))
@@ -339,7 +343,7 @@ static int minilm_ares_gemm(const fsgpu_minilm* e, const CUtensorMap& tm_a, cons
 
 // The launch sequence of the f16 form (buffers reserved and descriptors built by the caller): also what a graph captures.
 static int minilm_fast_enqueue(const fsgpu_minilm* e, const int32_t* d_ids, const int32_t* d_lens, uint32_t batch,
-                               uint32_t max_len, float* d_out, cudaStream_t s, bool ares, bool ffn_out_pair) {
+                               uint32_t max_len, float* d_out, cudaStream_t s, bool ares, bool ffn_out_pair, bool packed) {
     const uint64_t rows = (uint64_t)batch * max_len;
     const uint32_t m = (uint32_t)rows;
     const unsigned row_blocks = (unsigned)((rows + 7) / 8);
@@ -349,8 +353,20 @@ static int minilm_fast_enqueue(const fsgpu_minilm* e, const int32_t* d_ids, cons
     __half* ctx16 = e->f_ctx.as<__half>();
     float* pre32 = e->ws_pre32.as<float>();
     float* h32 = e->ws_h32.as<float>();
+    // packed rows (FSGPU_MINILM_PACKED, with the pair GEMMs): sequence b owns rows [offs[b], offs[b] + len_b); every kernel
+    // below reads the row count offs[batch] on the device — the grids stay sized for batch * max_len
+    uint32_t* offs = packed ? e->f_offs.as<uint32_t>() : nullptr;
+    struct MPtrScope {  // the launchers read e->f_m_ptr
+        const fsgpu_minilm* e;
+        ~MPtrScope() { e->f_m_ptr = nullptr; }
+    } m_scope{e};
+    e->f_m_ptr = packed ? offs + batch : nullptr;
+    if (packed) {
+        minilm_offsets_kernel<<<1, 1024, 0, s>>>(d_lens, batch, max_len, offs);
+        CUDA_TRY(cudaGetLastError());
+    }
     minilm_fast_embed_kernel<<<row_blocks, 256, 0, s>>>(d_ids, batch, max_len, e->vocab, e->word, e->pos, e->type0, e->emb_g,
-                                                        e->emb_b, e->eps, h16);
+                                                        e->emb_b, e->eps, h16, offs);
     CUDA_TRY(cudaGetLastError());
     for (uint32_t li = 0; li < e->n_layers; ++li) {
         const MiniLmLayer& L = e->layers[li];
@@ -359,15 +375,16 @@ static int minilm_fast_enqueue(const fsgpu_minilm* e, const int32_t* d_ids, cons
         auto lin384 = ares ? minilm_ares_gemm : minilm_fast_gemm;
         int rc = lin384(e, e->f_tm_h, L.qkv, e->f_tm_qkv_out, m, L.qkv_b, 0, s);
         if (rc) return rc;
-        minilm_fast_attention_kernel<<<(batch * kHeads + 3) / 4, 128, 0, s>>>(qkv16, d_lens, batch, max_len, ctx16);
+        minilm_fast_attention_kernel<<<(batch * kHeads + 3) / 4, 128, 0, s>>>(qkv16, d_lens, batch, max_len, ctx16, offs);
         CUDA_TRY(cudaGetLastError());
         rc = lin384(e, e->f_tm_ctx, L.attn_out, e->f_tm_pre, m, L.attn_out_b, 2, s);
         if (rc) return rc;
-        minilm_fast_ln_kernel<<<row_blocks, 256, 0, s>>>(pre32, h16, rows, L.attn_ln_g, L.attn_ln_b, e->eps, nullptr);
+        minilm_fast_ln_kernel<<<row_blocks, 256, 0, s>>>(pre32, h16, rows, L.attn_ln_g, L.attn_ln_b, e->eps, nullptr, e->f_m_ptr);
         CUDA_TRY(cudaGetLastError());
         if (ffn_fused) {  // FFN-in -> GELU -> FFN-out in one kernel: the [rows x 1536] intermediate stays on the SM
             FfnArgs fa{};
             fa.m = m;
+            fa.m_ptr = e->f_m_ptr;
             fa.bias1 = L.ffn_in_b;
             fa.bias2 = L.ffn_out_b;
             fa.dbg = (uint32_t)env_int("FSGPU_MINILM_FFN_DBG", 0);
@@ -421,7 +438,7 @@ static int minilm_fast_enqueue(const fsgpu_minilm* e, const int32_t* d_ids, cons
             e->prof.gemm_launches += 2;  // two linears
             e->prof.gemm_flops += 2.0 * 2.0 * (double)m * kHidden * e->inter;
             if (!ln_fused) {
-                minilm_fast_ln_kernel<<<row_blocks, 256, 0, s>>>(pre32, h16, rows, L.ffn_ln_g, L.ffn_ln_b, e->eps, last ? h32 : nullptr);
+                minilm_fast_ln_kernel<<<row_blocks, 256, 0, s>>>(pre32, h16, rows, L.ffn_ln_g, L.ffn_ln_b, e->eps, last ? h32 : nullptr, e->f_m_ptr);
                 CUDA_TRY(cudaGetLastError());
             }
             e->prof.other_launches += ln_fused ? 2 : 3;
@@ -433,11 +450,11 @@ static int minilm_fast_enqueue(const fsgpu_minilm* e, const int32_t* d_ids, cons
         // (FSGPU_MINILM_ARES_FFN_OUT=1) measures the same 54 us per layer — two waves of whole 256-row tiles
         rc = (ffn_out_pair ? minilm_ares_gemm : minilm_fast_gemm)(e, e->f_tm_ffn, L.ffn_out, e->f_tm_pre, m, L.ffn_out_b, 2, s);
         if (rc) return rc;
-        minilm_fast_ln_kernel<<<row_blocks, 256, 0, s>>>(pre32, h16, rows, L.ffn_ln_g, L.ffn_ln_b, e->eps, last ? h32 : nullptr);
+        minilm_fast_ln_kernel<<<row_blocks, 256, 0, s>>>(pre32, h16, rows, L.ffn_ln_g, L.ffn_ln_b, e->eps, last ? h32 : nullptr, e->f_m_ptr);
         CUDA_TRY(cudaGetLastError());
         e->prof.other_launches += 3;
     }
-    minilm_pool_kernel<<<batch, 128, 0, s>>>(h32, d_lens, max_len, d_out);
+    minilm_pool_kernel<<<batch, 128, 0, s>>>(h32, d_lens, max_len, d_out, offs);
     CUDA_TRY(cudaGetLastError());
     e->prof.other_launches += 2;
     return FSGPU_OK;
@@ -472,6 +489,8 @@ static int minilm_embed_fast_locked(const fsgpu_minilm* e, const int32_t* d_ids,
     CUDA_TRY(cudaFuncSetAttribute(ffn_fused_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ffn_fused_smem_bytes()));
     const bool ares = env_int("FSGPU_MINILM_ARES", 1) != 0 && e->num_sms >= 2 && m >= 256;
     const bool ffn_out_pair = ares && I % (kAresMaxKb * kMmaKBlock) == 0 && env_int("FSGPU_MINILM_ARES_FFN_OUT", 0) != 0;
+    const bool packed = ares && env_int("FSGPU_MINILM_PACKED", 1) != 0;  // no padding rows (see minilm_offsets_kernel)
+    CUDA_TRY(e->f_offs.reserve(((size_t)batch + 1) * 4));
 
     // Small batches (a query or a handful: <= 4096 token rows): the forward is bound by the host's 44 launch calls, so a
     // captured graph of it is replayed; ids / lens / output go through fixed staging buffers.  FSGPU_MINILM_GRAPH=0: off.
@@ -484,7 +503,7 @@ static int minilm_embed_fast_locked(const fsgpu_minilm* e, const int32_t* d_ids,
         }
     }
     if (!use_graph) {
-        int rc = minilm_fast_enqueue(e, d_ids, d_lens, batch, max_len, d_out, s, ares, ffn_out_pair);
+        int rc = minilm_fast_enqueue(e, d_ids, d_lens, batch, max_len, d_out, s, ares, ffn_out_pair, packed);
         if (rc) return rc;
         if (sync) CUDA_TRY(cudaStreamSynchronize(s));
         return FSGPU_OK;
@@ -493,8 +512,9 @@ static int minilm_embed_fast_locked(const fsgpu_minilm* e, const int32_t* d_ids,
     CUDA_TRY(e->g_lens.reserve(4096 * 4));
     CUDA_TRY(e->g_out.reserve((size_t)4096 * H * 4));
     const uint64_t key = ((uint64_t)batch << 32) | ((uint64_t)max_len << 8) | (ares ? 1u : 0u) | (ffn_out_pair ? 2u : 0u) |
-                         (env_int("FSGPU_MINILM_FFN_FUSED", 1) != 0 ? 4u : 0u) | (env_int("FSGPU_MINILM_FFN_LN", 1) != 0 ? 8u : 0u);
-    const void* bufs[9] = {e->f_h.p, e->f_qkv.p, e->f_ctx.p, e->f_ffn.p, e->ws_pre32.p, e->ws_h32.p, e->g_ids.p, e->g_lens.p, e->g_out.p};
+                         (env_int("FSGPU_MINILM_FFN_FUSED", 1) != 0 ? 4u : 0u) | (env_int("FSGPU_MINILM_FFN_LN", 1) != 0 ? 8u : 0u) |
+                         (packed ? 16u : 0u);
+    const void* bufs[10] = {e->f_h.p, e->f_qkv.p, e->f_ctx.p, e->f_ffn.p, e->ws_pre32.p, e->ws_h32.p, e->g_ids.p, e->g_lens.p, e->g_out.p, e->f_offs.p};
     if (e->f_graphs.size() >= 64 && !e->f_graphs.count(key)) {  // bounded cache: shapes are few in practice
         for (auto& kv : e->f_graphs)
             if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
@@ -511,7 +531,7 @@ static int minilm_embed_fast_locked(const fsgpu_minilm* e, const int32_t* d_ids,
         cudaGraph_t graph = nullptr;
         CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
         int rc = minilm_fast_enqueue(e, e->g_ids.as<int32_t>(), e->g_lens.as<int32_t>(), batch, max_len, e->g_out.as<float>(), s,
-                                     ares, ffn_out_pair);
+                                     ares, ffn_out_pair, packed);
         cudaError_t ce = cudaStreamEndCapture(s, &graph);
         if (rc || ce != cudaSuccess || !graph) {
             if (graph) cudaGraphDestroy(graph);

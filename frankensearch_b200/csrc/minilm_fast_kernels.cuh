@@ -46,6 +46,7 @@ __device__ __forceinline__ float gelu_tanh_fit(float x) {
 
 struct FastGemmArgs {
     uint32_t m, n, k;     // n % 128 == 0, k % 64 == 0
+    const uint32_t* m_ptr;  // packed rows: the row count lives on the device (m is then the upper bound the grid was sized for)
     const float* bias;    // [n]
     int mode;             // 0: f16 out = acc + bias   1: f16 out = gelu(acc + bias)   2: f32 out = acc + bias
 };
@@ -82,7 +83,8 @@ gemm_f16_fast_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
         for (uint32_t i = threadIdx.x; i < args.n; i += blockDim.x) bias_s[i] = args.bias[i];
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t tiles_m = (args.m + 127u) / 128u, tiles_n = args.n / 128u;
+    const uint32_t m_rows = args.m_ptr ? min(*args.m_ptr, args.m) : args.m;
+    const uint32_t tiles_m = (m_rows + 127u) / 128u, tiles_n = args.n / 128u;
     const uint32_t n_tiles = tiles_m * tiles_n, n_kb = args.k / kMmaKBlock;
 
     if (warp == 8 && lane == 0) {
@@ -182,7 +184,7 @@ gemm_f16_fast_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
                 acc = 0;
                 acc_phase ^= 1u;
             }
-            if (row0 >= args.m) continue;  // (whole warp: a tile past the last row stores nothing)
+            if (row0 >= m_rows) continue;  // (whole warp: a tile past the last row stores nothing)
             // the previous store of this warp must have finished reading the staging box
             if (lane == 0) tma_store_wait_read();
             __syncwarp();
@@ -252,6 +254,7 @@ constexpr uint32_t kAresMaxN = 1536;  // the layer's bias vector is staged in sh
 
 struct AresGemmArgs {
     uint32_t m, n, k;    // k = k_chunks * (<= 384)
+    const uint32_t* m_ptr;  // packed rows: the row count lives on the device (m is then the upper bound the grid was sized for)
     uint32_t k_chunks;   // > 1 (FFN-out, K = 1536): the pair owns whole 256-row tiles and walks (K chunk, feature block)
                          // with the activation tile of the chunk resident; a block's accumulator lives through all
                          // chunks, so n <= 512 (the two TMEM accumulators = the tile's two feature blocks)
@@ -293,7 +296,8 @@ gemm_f16_ares_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const uint32_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
-    const uint32_t m_tiles = (args.m + 255u) / 256u, n_blocks = (args.n + 255u) / 256u;
+    const uint32_t m_rows = args.m_ptr ? min(*args.m_ptr, args.m) : args.m;
+    const uint32_t m_tiles = (m_rows + 255u) / 256u, n_blocks = (args.n + 255u) / 256u;
     const uint32_t kch = args.k_chunks, per_mt = kch * n_blocks;  // items of one 256-row tile: (K chunk, feature block)
     // contiguous m-major item ranges; with K chunks a pair owns whole tiles (its accumulators live across the chunks)
     const uint32_t item0 = kch > 1 ? (uint32_t)((uint64_t)m_tiles * pair / n_pairs) * per_mt
@@ -450,7 +454,7 @@ gemm_f16_ares_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid
                 if (acc == 0u) acc_phase ^= 1u;
             }
             if (idle) continue;
-            if (row0 >= args.m) continue;
+            if (row0 >= m_rows) continue;
 #pragma unroll
             for (int c = 0; c < 2; ++c) {  // 32-column chunks; a staging box = 64 f16 columns or 32 f32 columns
                 const bool new_box = mode == 2 || (c & 1) == 0;
@@ -527,6 +531,7 @@ constexpr uint32_t kFfnHKb = 6;                        // 384 / 64
 
 struct FfnArgs {
     uint32_t m;
+    const uint32_t* m_ptr;  // packed rows: the row count lives on the device (m is then the upper bound the grid was sized for)
     const float* bias1;  // [1536]
     const float* bias2;  // [384]
     uint32_t dbg;        // timing experiments (FSGPU_MINILM_FFN_DBG; results are wrong with any bit set): 1 no GELU math,
@@ -576,7 +581,8 @@ ffn_fused_pair_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_con
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const uint32_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
-    const uint32_t m_tiles = (args.m + 255u) / 256u;
+    const uint32_t m_rows = args.m_ptr ? min(*args.m_ptr, args.m) : args.m;
+    const uint32_t m_tiles = (m_rows + 255u) / 256u;
 
     if (warp == kFfnEpiWarps && lane == 0) {
         tma_prefetch_desc(&tm_h);
@@ -825,7 +831,7 @@ ffn_fused_pair_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_con
                 else gb_s[et] = args.ln_b[et - 384u];
                 if (et < 256u) gb_s[512u + et] = args.ln_b[128u + et];
                 const uint32_t row = mt * 256u + rank * 128u + row_l;
-                const bool row_ok = row < args.m;
+                const bool row_ok = row < m_rows;
                 const uint32_t tcol = tmem_base + ((quarter * 32u) << 16) + acc2_col + part * 96u;
                 const uint8_t* h_row = base_ptr + row_l * 128u;  // this row inside every [128 x 64] K-block of the h tile
                 float acc = 0.0f;
@@ -925,7 +931,7 @@ ffn_fused_pair_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_con
                         }
                         fence_proxy_async_smem();
                         __syncwarp();
-                        if (lane == 0 && row0 < args.m) {
+                        if (lane == 0 && row0 < m_rows) {
                             tma_store_2d(&tm_h_out, st_smem, (int32_t)c0, (int32_t)row0);  // rows past m are clipped by the map
                             tma_store_commit();
                         }
@@ -952,7 +958,7 @@ ffn_fused_pair_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_con
                     __syncwarp();
                     if (lane == 0) mbar_arrive_cluster(acc2_empty, 0);
                 }
-                if (row0 >= args.m) continue;
+                if (row0 >= m_rows) continue;
                 if (lane == 0) tma_store_wait_read();
                 __syncwarp();
 #pragma unroll
@@ -988,10 +994,10 @@ ffn_fused_pair_kernel(const __grid_constant__ CUtensorMap tm_h, const __grid_con
 // request (the last layer: the pooling kernel reads f32).
 __global__ void __launch_bounds__(256)
 minilm_fast_ln_kernel(const float* __restrict__ pre, __half* __restrict__ h, size_t rows, const float* __restrict__ g,
-                      const float* __restrict__ b, float eps, float* __restrict__ out_f32) {
+                      const float* __restrict__ b, float eps, float* __restrict__ out_f32, const uint32_t* __restrict__ m_ptr) {
     const uint32_t lane = threadIdx.x & 31;
     const size_t row = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (row >= rows) return;
+    if (row >= rows || (m_ptr && row >= *m_ptr)) return;
     float x[12];
 #pragma unroll
     for (int i = 0; i < 12; ++i) {
@@ -1007,16 +1013,67 @@ minilm_fast_ln_kernel(const float* __restrict__ pre, __half* __restrict__ h, siz
     }
 }
 
+// Packed rows (f16 form): sequence b owns rows [offs[b], offs[b] + len_b) — no padding rows exist, so every row-wise
+// kernel and GEMM of the forward works on sum(len) rows instead of batch * t_pad (queries are short and ragged).
+// offs[b] = sum of min(max(lens[i], 0), t_pad) for i < b; offs[batch] = the row count every later kernel reads.
+__global__ void __launch_bounds__(1024) minilm_offsets_kernel(const int32_t* __restrict__ lens, uint32_t batch, uint32_t t_pad,
+                                                              uint32_t* __restrict__ offs) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < batch; base += 1024u) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < batch ? min((uint32_t)max(lens[i], 0), t_pad) : 0u;
+        uint32_t x = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if ((int)lane >= o) x += y;
+        }
+        if (lane == 31) warp_sums[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = warp_sums[lane];
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, w, o);
+                if ((int)lane >= o) w += y;
+            }
+            warp_sums[lane] = w;  // inclusive over warps
+        }
+        __syncthreads();
+        const uint32_t before = carry + (warp ? warp_sums[warp - 1] : 0u) + x - v;  // exclusive prefix
+        if (i < batch) offs[i] = before;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = before + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) offs[batch] = carry;
+}
+
 // embeddings -> LayerNorm -> h f16 (BertEmbeddings; the f32 sums are those of minilm_embed_kernel)
 __global__ void __launch_bounds__(256)
 minilm_fast_embed_kernel(const int32_t* __restrict__ ids, uint32_t batch, uint32_t t_pad, uint32_t vocab,
                          const float* __restrict__ word, const float* __restrict__ pos, const float* __restrict__ type0,
-                         const float* __restrict__ g, const float* __restrict__ b, float eps, __half* __restrict__ h) {
+                         const float* __restrict__ g, const float* __restrict__ b, float eps, __half* __restrict__ h,
+                         const uint32_t* __restrict__ offs) {
     const uint32_t lane = threadIdx.x & 31;
     const size_t row = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= (size_t)batch * t_pad) return;
-    const uint32_t t = (uint32_t)(row % t_pad);
-    int32_t id = ids[row];
+    uint32_t t = (uint32_t)(row % t_pad);
+    size_t src = row;
+    if (offs) {  // packed rows: row -> (sequence, token) through the prefix sums of the lengths
+        if (row >= offs[batch]) return;
+        uint32_t lo = 0, hi = batch;  // the last sequence with offs[seq] <= row (empty sequences share an offset: take the last)
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (offs[mid] <= row) lo = mid;
+            else hi = mid;
+        }
+        t = (uint32_t)row - offs[lo];
+        src = (size_t)lo * t_pad + t;
+    }
+    int32_t id = ids[src];
     if (id < 0 || (uint32_t)id >= vocab) id = 0;
     float x[12];
 #pragma unroll
@@ -1058,14 +1115,15 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 
 __global__ void __launch_bounds__(128)
 minilm_fast_attention_kernel(const __half* __restrict__ qkv, const int32_t* __restrict__ lens, uint32_t batch,
-                             uint32_t t_pad, __half* __restrict__ ctx) {
+                             uint32_t t_pad, __half* __restrict__ ctx, const uint32_t* __restrict__ offs) {
     __shared__ __align__(16) __half tiles[4][3][32 * kAttPitch];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t item = blockIdx.x * 4u + warp;
     if (item >= batch * kHeads) return;
     const uint32_t b = item / kHeads, h = item % kHeads;
     const uint32_t len = min((uint32_t)max(lens[b], 0), t_pad);
-    const size_t row0 = (size_t)b * t_pad;
+    const size_t row0 = offs ? (size_t)offs[b] : (size_t)b * t_pad;
+    const uint32_t t_rows = offs ? len : t_pad;  // packed rows: the sequence owns exactly len rows (the next ones are another sequence's)
     __half* qs = tiles[warp][0];
     __half* ks = tiles[warp][1];
     __half* vs = tiles[warp][2];
@@ -1075,7 +1133,7 @@ minilm_fast_attention_kernel(const __half* __restrict__ qkv, const int32_t* __re
         const uint32_t idx = (uint32_t)it * 32u + lane;  // 0 .. 383
         const uint32_t mat = idx / 128u, r = (idx % 128u) / 4u, ch = idx % 4u;
         uint4 val = make_uint4(0u, 0u, 0u, 0u);
-        if (r < t_pad)
+        if (r < t_rows)
             val = *reinterpret_cast<const uint4*>(qkv + (row0 + r) * (3 * kHidden) + mat * kHidden + h * kHeadDim + ch * 8u);
         *reinterpret_cast<uint4*>(tiles[warp][mat] + r * kAttPitch + ch * 8u) = val;
     }
@@ -1182,7 +1240,7 @@ minilm_fast_attention_kernel(const __half* __restrict__ qkv, const int32_t* __re
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
         const uint32_t idx = (uint32_t)it * 32u + lane, r = idx / 4u, ch = idx % 4u;
-        if (r < t_pad)
+        if (r < t_rows)
             *reinterpret_cast<uint4*>(ctx + (row0 + r) * kHidden + h * kHeadDim + ch * 8u) =
                 *reinterpret_cast<const uint4*>(qs + r * kAttPitch + ch * 8u);
     }

@@ -678,9 +678,10 @@ minilm_attention_short_kernel(const float* __restrict__ qkv, const int32_t* __re
 // ─── pooling: masked mean -> L2 (eps 1e-12) -> adapter L2 with zero-vector guard ─────────────
 __global__ void __launch_bounds__(128)
 minilm_pool_kernel(const float* __restrict__ hidden, const int32_t* __restrict__ lens, uint32_t t_pad,
-                   float* __restrict__ out) {
+                   float* __restrict__ out, const uint32_t* __restrict__ offs = nullptr) {
     const uint32_t b = blockIdx.x;
     const uint32_t len = min((uint32_t)max(lens[b], 0), t_pad);
+    const size_t row0 = offs ? (size_t)offs[b] : (size_t)b * t_pad;  // packed rows (f16 form) or batch-longest padding
     __shared__ float red[4];
     float v[3];
     float part = 0.0f;
@@ -688,7 +689,7 @@ minilm_pool_kernel(const float* __restrict__ hidden, const int32_t* __restrict__
     for (int i = 0; i < 3; ++i) {
         const uint32_t d = threadIdx.x + 128u * i;
         float s = 0.0f;
-        for (uint32_t t = 0; t < len; ++t) s += hidden[((size_t)b * t_pad + t) * kHidden + d];
+        for (uint32_t t = 0; t < len; ++t) s += hidden[(row0 + t) * kHidden + d];
         v[i] = len ? s / (float)len : 0.0f;  // sum(mask * h) / clamp(sum(mask), 1e-9)
         part = fmaf(v[i], v[i], part);
     }

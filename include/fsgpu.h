@@ -466,7 +466,8 @@ typedef struct fsgpu_minilm_weights {
 } fsgpu_minilm_weights;
 typedef struct fsgpu_minilm_profile {
     uint64_t gemm_launches, other_launches;
-    double gemm_flops;     /* 2*M*N*K per tensor-core product actually issued, summed */
+    double gemm_flops;     /* 2*M*N*K per tensor-core product issued, summed; M = batch * max_len (the f16 form packs
+                              its rows on the device, sum(len) of them: scale by sum(len) / (batch * max_len)) */
     double gemm_ms;        /* event-timed GEMM durations (0 unless enabled) */
 } fsgpu_minilm_profile;
 int fsgpu_minilm_create(const fsgpu_minilm_weights* weights, int device, fsgpu_minilm** out);

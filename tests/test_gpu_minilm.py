@@ -176,6 +176,38 @@ def test_minilm_fused_ffn_kernel_matches_the_two_gemm_form(fs, bert):
             assert errs[form] <= errs["two-gemm"] + 1e-4, errs
 
 
+def test_minilm_packed_rows_equal_the_padded_layout(fs, bert):
+    """FSGPU_MINILM_PACKED (default 1, f16 form with >= 256 padded token rows): sequence b owns rows [offs[b], offs[b] +
+    len_b) — no padding rows — and every kernel reads the row count from the device.  A row's arithmetic does not depend
+    on its neighbours, so the embeddings must equal the padded layout's: ragged batches, empty texts between others, a
+    batch whose packed row count is far below one 256-row tile, lengths of exactly t_pad."""
+    rng = np.random.default_rng(21)
+    cases = [
+        random_batches(rng, 300, 1, 32),
+        [rng.integers(1, 2000, 32).tolist()] + [[int(t)] for t in rng.integers(1, 2000, 40)],  # 72 packed rows of 1312
+        [rng.integers(1, 2000, 32).tolist() for _ in range(24)],                                  # nothing to pack
+        [[], rng.integers(1, 2000, 32).tolist(), [], []] + random_batches(rng, 60, 1, 9) + [[]],
+        random_batches(rng, 1500, 1, 32),                                                          # 1500 > 1024: two scan chunks of the offsets kernel
+    ]
+    for batches in cases:
+        out = {}
+        for packed in ("1", "0"):
+            e = fs.MiniLmEmbedder(mr.state_dict_numpy(bert))
+            os.environ["FSGPU_MINILM_PACKED"] = packed
+            try:
+                out[packed] = e.embed_token_ids_batch(batches)
+            finally:
+                del os.environ["FSGPU_MINILM_PACKED"]
+                e.close()
+        assert np.isfinite(out["1"]).all()
+        assert np.abs(out["1"] - out["0"]).max() <= 2e-6, np.abs(out["1"] - out["0"]).max()
+        idx = list(range(0, len(batches), max(1, len(batches) // 12)))
+        check(out["1"][idx], mr.reference_embed(bert, [batches[i] for i in idx]), tol=5e-4)
+        for i, b in enumerate(batches):
+            if not b:
+                assert not out["1"][i].any()
+
+
 def test_minilm_single_product_mode_is_within_tolerance(fs, bert):
     """FSGPU_MINILM_PRODUCTS=1 (plain f16 operands, a third of the tensor work): still inside the
     1e-3 budget on cosine, reported beside the default in the bench."""

@@ -45,7 +45,9 @@ def main():
         enc.profile_enable(False)
         ms = t0.elapsed_time(t1) / iters
         gemm_ms = p["gemm_ms"] / iters
-        issued = p["gemm_flops"] / iters / (gemm_ms * 1e-3) / 1e12
+        # the library counts flops on batch * t_pad rows; the f16 form (products 0) works on the packed rows only
+        packed = products == 0 and os.environ.get("FSGPU_MINILM_PACKED", "1") != "0" and batch * tokens >= 256
+        issued = p["gemm_flops"] / iters / (gemm_ms * 1e-3) / 1e12 * (float(lens.sum()) / (batch * tokens) if packed else 1.0)
         print(f"{products:8d} {ms:9.3f} {batch / (ms * 1e-3):11.0f} {gemm_ms:9.3f} {gemm_ms / ms:10.2f} "
               f"{issued:16.1f} {issued / max(products, 1):16.1f}", flush=True)
     # single-query latency (the reference quotes ~128 ms per query on one CPU core, README.md:527)
