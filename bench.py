@@ -396,7 +396,10 @@ def run_headline(ctx):
     # the north-star's HBM-bound regimes, every N: exact f16 scan of one query (CUDA cores), f16 and int8
     # forms of the batched kernel with one 128-query block per corpus pass
     hbm = {}
-    if a.hbm_batch > 0:
+
+    def run_hbm():
+        if a.hbm_batch <= 0:
+            return
         q1 = d_queries[:1].contiguous()
         qb = d_queries[: min(a.hbm_batch, a.batch)].contiguous()
         hbm["f16_single_query"] = profiled(q1)
@@ -404,6 +407,11 @@ def run_headline(ctx):
         hbm["int8_batch128"] = profiled(qb)
         for rec in hbm.values():
             rec["algorithmic_bytes"] = "rows*dim*2 (f16 slab)" if "int8" not in rec["kernel"] else "rows*dim (int8 codes)"
+
+    # the sub-records run AFTER the headline's timed region (the headline is measured first, from the state the index
+    # build leaves the GPU in); only the rows x query-groups layout needs them before its index replaces the row shards
+    if qg > 1:
+        run_hbm()
 
     row_shards_only = None
     if qg > 1:
@@ -453,6 +461,8 @@ def run_headline(ctx):
     assert bool((keys[:, :-1] > keys[:, 1:]).all().item()) if a.k > 1 else True, "result keys are not sorted"
     got_hits = out[1].cpu().numpy()
     e2e_hits = hits_host.numpy().copy()
+    if qg == 1:
+        run_hbm()  # (after the timed results have been copied out)
 
     line = None
     if rank == 0:
