@@ -784,8 +784,9 @@ def bench_config4(ctx):
         torch.cuda.synchronize(dev)
 
     e2e_ms = _time_wall(ctx, e2e, a.steps, 2)
-    # with the query encoders inside the step: potion (static table gather) for the fast tier, MiniLM-L6 for
-    # the quality tier, replicas on every rank, synthetic weights and token ids
+    # with the query encoders inside the step: potion (static table gather) for the fast tier (a replica on every rank:
+    # it costs microseconds), MiniLM-L6 for the quality tier — at N > 1 every rank encodes its block of B/N queries and
+    # ONE all-gather hands every rank all B embeddings (1.5 MB); synthetic weights and token ids
     rng = np.random.default_rng(5)
     potion = fs.Model2VecEmbedder((rng.standard_normal((65536, 256)) * 0.1).astype(np.float32), device=ctx.local_rank)
     minilm = fs.MiniLmEmbedder(_synthetic_minilm_weights(), device=ctx.local_rank)
@@ -794,6 +795,10 @@ def bench_config4(ctx):
     off_h = torch.from_numpy(np.concatenate([[0], np.cumsum(lens64)]).astype(np.int64)).pin_memory()
     flat_h = torch.from_numpy(np.concatenate([ids_h.numpy()[i, :l] for i, l in enumerate(lens_h.numpy())]).astype(np.int32)).pin_memory()
     pf = torch.empty((batch, 256), dtype=torch.float32, device=dev)
+    bq = (batch + ctx.world - 1) // ctx.world           # queries per rank (equal blocks for the all-gather)
+    q_lo, q_hi = min(batch, ctx.rank * bq), min(batch, (ctx.rank + 1) * bq)
+    q_block = torch.zeros((bq, 384), dtype=torch.float32, device=dev)
+    q_all = torch.empty((ctx.world * bq, 384), dtype=torch.float32, device=dev)
 
     def with_encoders():
         d_ids, d_lens = ids_h.to(dev, non_blocking=True), lens_h.to(dev, non_blocking=True)
@@ -801,7 +806,13 @@ def bench_config4(ctx):
         s = torch.cuda.current_stream(dev).cuda_stream
         fs._ffi.check(fs._ffi.lib().fsgpu_potion_embed_device(potion._h, d_flat.data_ptr(), d_off.data_ptr(), batch,
                                                               pf.data_ptr(), s))
-        q = minilm.embed_device(d_ids, d_lens)
+        if ctx.world == 1:
+            q = minilm.embed_device(d_ids, d_lens)
+        else:
+            if q_hi > q_lo:
+                q_block[: q_hi - q_lo] = minilm.embed_device(d_ids[q_lo:q_hi].contiguous(), d_lens[q_lo:q_hi].contiguous())
+            ctx.dist.all_gather_into_tensor(q_all, q_block)
+            q = q_all[:batch]
         r = searcher.search_device(pf, q, k, lex)
         out_host.copy_(r.refined, non_blocking=True)
         torch.cuda.synchronize(dev)
@@ -852,7 +863,8 @@ def bench_config4(ctx):
                "h2d_bytes_per_step": batch * (256 + 384) * 4, "d2h_bytes_per_step": batch * k * 32,
                "with_encoders": {"ms_per_step": enc_ms, "queries_per_s": batch / enc_ms * 1e3,
                                  "what": "host token ids -> potion gather-pool + MiniLM-L6 forward (synthetic weights, "
-                                         "4-32 tokens) -> the same search -> host results"},
+                                         "4-32 tokens; N > 1: each rank encodes B/N queries, one all-gather of the embeddings) -> the same "
+                                         "search -> host results"},
                "encoder": encoder,
                "flow": "SyncTwoTierSearcher::search_internal, sync_searcher.rs:616-1009, pre-embedded queries"}
         if not a.no_cpu_baseline:
