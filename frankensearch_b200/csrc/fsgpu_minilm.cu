@@ -53,6 +53,10 @@ struct fsgpu_minilm {
     mutable const uint32_t* f_m_ptr = nullptr;                  // != nullptr while a packed forward is being enqueued: &offs[batch]
     mutable uint64_t f_rows = 0;
     mutable float* f_pre_ptr = nullptr;
+    // the activation buffers are shared by every call: a call on another stream waits for the previous call's work
+    mutable cudaEvent_t ev_last = nullptr;
+    mutable cudaStream_t last_stream = nullptr;
+    mutable bool have_last = false;
     // small batches replay a captured CUDA graph of the forward (44 launches of a few microseconds each are bound by
     // the host's launch calls): one graph per (batch, max_len, variant), inputs / outputs staged in fixed buffers
     struct FastGraph {
@@ -113,6 +117,7 @@ extern "C" void fsgpu_minilm_destroy(fsgpu_minilm* e) {
         for (DevBuf* b : {&e->ws_h32, &e->ws_pre32, &e->ws_qkv32, &e->ws_ids, &e->ws_lens, &e->ws_out, &e->f_h, &e->f_qkv, &e->f_ctx,
                           &e->f_ffn, &e->g_ids, &e->g_lens, &e->g_out, &e->f_offs})
             b->release();
+        if (e->ev_last) cudaEventDestroy(e->ev_last);
         for (auto& kv : e->f_graphs)
             if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
         for (auto* v : {&e->ev_pending, &e->ev_free})
@@ -559,8 +564,32 @@ static int minilm_embed_fast_locked(const fsgpu_minilm* e, const int32_t* d_ids,
 }
 
 // Caller holds e->mu and has selected the device.
+static int minilm_embed_body_locked(const fsgpu_minilm* e, const int32_t* d_ids, const int32_t* d_lens, uint32_t batch,
+                                    uint32_t max_len, float* d_out, cudaStream_t s, bool sync);
+
+// Every forward goes through here (e->mu held).  The encoder owns ONE set of activation buffers, so a call on stream B
+// must not start while the kernels of the previous call are still running on stream A: B waits on the event recorded
+// at the end of that call (a no-op for back-to-back calls on one stream).  A caller that is CAPTURING its stream gets no
+// such ordering (the replays happen at times the library does not see): replays of one encoder must be ordered by the
+// caller — include/fsgpu.h.
 static int minilm_embed_locked(const fsgpu_minilm* e, const int32_t* d_ids, const int32_t* d_lens, uint32_t batch,
                                uint32_t max_len, float* d_out, cudaStream_t s, bool sync) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    bool capturing = false;
+    if (cudaStreamIsCapturing(s, &st) != cudaSuccess) cudaGetLastError();
+    else capturing = st != cudaStreamCaptureStatusNone;
+    if (!capturing && e->have_last && e->last_stream != s) CUDA_TRY(cudaStreamWaitEvent(s, e->ev_last, 0));
+    int rc = minilm_embed_body_locked(e, d_ids, d_lens, batch, max_len, d_out, s, sync);
+    if (rc || capturing) return rc;
+    if (!e->ev_last) CUDA_TRY(cudaEventCreateWithFlags(&e->ev_last, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(e->ev_last, s));
+    e->last_stream = s;
+    e->have_last = true;
+    return FSGPU_OK;
+}
+
+static int minilm_embed_body_locked(const fsgpu_minilm* e, const int32_t* d_ids, const int32_t* d_lens, uint32_t batch,
+                                    uint32_t max_len, float* d_out, cudaStream_t s, bool sync) {
     if (max_len == 0 || max_len > e->max_pos)
         return fail(FSGPU_ERR_EMBEDDING_FAILED, "minilm: max_len %u outside 1..%u", max_len, e->max_pos);
     const uint64_t rows = (uint64_t)batch * max_len;

@@ -482,6 +482,10 @@ void fsgpu_minilm_destroy(fsgpu_minilm* enc);
  * vector, fastembed_embedder.rs:432-434); out [batch, hidden] f32, L2-normalised. */
 int fsgpu_minilm_embed(const fsgpu_minilm* enc, const int32_t* ids, const int32_t* lens, uint32_t batch,
                        uint32_t max_len, float* out);
+/* Device-resident form, asynchronous on `stream` (NULL: the encoder's own stream, synchronised before returning).
+ * Calls on one encoder are serialised; its activation buffers are shared, so a call on another stream first waits (on
+ * the device) for the previous call's kernels.  A caller that CAPTURES `stream` into a CUDA graph must itself order
+ * the replays of one encoder (the library cannot see them). */
 int fsgpu_minilm_embed_device(const fsgpu_minilm* enc, const int32_t* d_ids, const int32_t* d_lens,
                               uint32_t batch, uint32_t max_len, float* d_out, void* stream);
 int fsgpu_minilm_profile_enable(fsgpu_minilm* enc, int on);

@@ -208,6 +208,31 @@ def test_minilm_packed_rows_equal_the_padded_layout(fs, bert):
                 assert not out["1"][i].any()
 
 
+def test_minilm_calls_on_two_streams_do_not_share_activations_in_flight(enc, bert):
+    """The encoder has ONE set of activation buffers: a forward enqueued on stream B while stream A's forward is still
+    running must wait for it on the device (the event recorded at the end of every call)."""
+    import torch
+
+    rng = np.random.default_rng(31)
+    dev = torch.device("cuda", 0)
+    sets = []
+    for n in (700, 650):
+        lens = rng.integers(1, 33, n).astype(np.int32)
+        ids = rng.integers(1, 2000, (n, 32)).astype(np.int32)
+        sets.append((torch.from_numpy(ids).to(dev), torch.from_numpy(lens).to(dev)))
+    want = [enc.embed_device(i, l).clone() for i, l in sets]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+    for _ in range(5):
+        got = []
+        for (i, l), s in zip(sets, streams):
+            with torch.cuda.stream(s):
+                got.append(enc.embed_device(i, l))
+        torch.cuda.synchronize()
+        for g, w in zip(got, want):
+            assert torch.equal(g, w)
+
+
 def test_minilm_single_product_mode_is_within_tolerance(fs, bert):
     """FSGPU_MINILM_PRODUCTS=1 (plain f16 operands, a third of the tensor work): still inside the
     1e-3 budget on cosine, reported beside the default in the bench."""
