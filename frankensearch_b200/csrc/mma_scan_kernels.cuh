@@ -1436,7 +1436,7 @@ __device__ __forceinline__ void mma_rescore_list(const MmaRefineArgs& args, cons
 
 constexpr uint32_t kMmaTopListCap = 2048;  // dense list of the approximate top-k (ties included) in the refine
 
-__global__ void __launch_bounds__(256) mma_refine_kernel(const MmaRefineArgs args) {
+__global__ void __launch_bounds__(256, 5) mma_refine_kernel(const MmaRefineArgs args) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* cand = reinterpret_cast<uint64_t*>(smem_raw);
     uint64_t* tau = cand + args.buf_cap;
