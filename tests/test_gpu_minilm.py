@@ -188,6 +188,8 @@ def test_minilm_packed_rows_equal_the_padded_layout(fs, bert):
         [rng.integers(1, 2000, 32).tolist() for _ in range(24)],                                  # nothing to pack
         [[], rng.integers(1, 2000, 32).tolist(), [], []] + random_batches(rng, 60, 1, 9) + [[]],
         random_batches(rng, 1500, 1, 32),                                                          # 1500 > 1024: two scan chunks of the offsets kernel
+        [[] for _ in range(300)],                                                                  # 300 padded rows, ZERO packed rows: every kernel has nothing to do
+        [[] for _ in range(299)] + [[7]],                                                          # one packed row
     ]
     for batches in cases:
         out = {}
@@ -201,8 +203,9 @@ def test_minilm_packed_rows_equal_the_padded_layout(fs, bert):
                 e.close()
         assert np.isfinite(out["1"]).all()
         assert np.abs(out["1"] - out["0"]).max() <= 2e-6, np.abs(out["1"] - out["0"]).max()
-        idx = list(range(0, len(batches), max(1, len(batches) // 12)))
-        check(out["1"][idx], mr.reference_embed(bert, [batches[i] for i in idx]), tol=5e-4)
+        idx = [i for i in range(0, len(batches), max(1, len(batches) // 12)) if batches[i]] or [len(batches) - 1]
+        if batches[idx[0]]:
+            check(out["1"][idx], mr.reference_embed(bert, [batches[i] for i in idx]), tol=5e-4)
         for i, b in enumerate(batches):
             if not b:
                 assert not out["1"][i].any()
